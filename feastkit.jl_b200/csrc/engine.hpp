@@ -1,0 +1,138 @@
+// Host-side engine state of libfeastcuda (one handle = one GPU = one solve at a time).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <complex>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/feastcuda.h"
+#include "cxmath.cuh"
+
+namespace feastcuda {
+
+typedef std::complex<double> zc;
+
+struct FcError : std::runtime_error {
+  int code;
+  FcError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define FC_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      throw FcError(FEASTCUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " at " +  \
+                                            __FILE__ + ":" + std::to_string(__LINE__));                \
+  } while (0)
+
+#define FC_REQUIRE(cond, msg)                                      \
+  do {                                                             \
+    if (!(cond)) throw FcError(FEASTCUDA_ERR_ARG, std::string(msg)); \
+  } while (0)
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    FC_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostCsr {
+  int64_t n = 0, nnz = 0;
+  std::vector<int> ptr, col;
+  std::vector<double> val;  // nnz (real) or 2*nnz (complex interleaved)
+  bool cplx = false;
+  bool set = false;
+};
+
+struct DevCsr {
+  DBuf ptr, col, val;
+  bool uploaded = false;
+};
+
+struct HostDense {  // column-major n x n, complex interleaved or real
+  int64_t n = 0;
+  std::vector<double> a;
+  bool cplx = false, set = false;
+};
+
+struct HostBand {   // full general band (2k+1) x n, diagonal row k, values expanded from the input storage
+  int64_t n = 0, k = 0;
+  std::vector<double> ab;  // interleaved complex always (2*(2k+1)*n)
+  bool cplx = false, set = false;
+};
+
+enum OperatorKind { OP_NONE = 0, OP_SPARSE = 1, OP_DENSE = 2, OP_BAND = 3 };
+
+// block-vector slots (each n x ld complex, row-major)
+enum BlockSlot { BS_QB = 0, BS_RHS, BS_ACC, BS_XR, BS_KX, BS_KR, BS_KRH, BS_KP, BS_KV, BS_KS, BS_KT, BS_KB, BS_COUNT };
+
+struct Timer {
+  std::chrono::steady_clock::time_point t0;
+  Timer() : t0(std::chrono::steady_clock::now()) {}
+  double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+}  // namespace feastcuda
+
+struct feastcuda_handle_s {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  int kind = feastcuda::OP_NONE;
+  bool dev_complex = false;  // value type of the uploaded operators
+  feastcuda::HostCsr hA, hB;
+  feastcuda::DevCsr dA, dB;
+  feastcuda::HostDense denseA, denseB;
+  feastcuda::HostBand bandA, bandB;
+  bool has_b = false;
+  int64_t n = 0;
+
+  // workspaces
+  int64_t ws_n = 0;
+  int ws_ld = 0;
+  feastcuda::DBuf blk[feastcuda::BS_COUNT];
+  feastcuda::DBuf partial, partial_r, kstate, small, small2, gram_partial, stage, red_ws;
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_pending;
+
+  // dense / band factor caches (device), one per quadrature node
+  std::vector<feastcuda::DBuf> lu_cache;
+  std::vector<feastcuda::DBuf> piv_cache;
+  std::vector<feastcuda::zc> lu_shift;
+  feastcuda::DBuf dDenseA, dDenseB, dBandA, dBandB;
+  bool dense_uploaded = false, band_uploaded = false;
+
+  // last solve's results (device: blk[BS_XR]); host copies of the small arrays
+  int64_t res_m0 = 0, res_M = 0, res_rank = 0;
+  std::vector<double> res_lambda, res_res;   // lambda interleaved complex for the general solve
+  bool res_general = false;
+  bool have_subspace = false;
+  bool sub_real = false;
+  int64_t sub_m0 = 0;
+
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+
+  feastcuda_stats stats;
+  std::string err;
+};

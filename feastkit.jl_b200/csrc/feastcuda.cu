@@ -1,0 +1,1303 @@
+// libfeastcuda: engine + C ABI.  See include/feastcuda.h for the contract and DESIGN.md for the layout.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "engine.hpp"
+#include "host_math.hpp"
+#include "kernels_block.cuh"
+#include "kernels_reduced.cuh"
+#include "kernels_sparse.cuh"
+#include "dense_band.cuh"
+
+using namespace feastcuda;
+typedef feastcuda_handle_s H;
+
+static thread_local std::string g_last_error;
+
+// =====================================================================================================
+// small utilities
+// =====================================================================================================
+static inline int pow2_ge(int m) { int p = 1; while (p < m) p <<= 1; return p; }
+static inline zd tozd(zc v) { return mk<double>(v.real(), v.imag()); }
+
+static void* pinned_buf(H* h, size_t bytes) {
+  if (bytes > h->pinned_cap) {
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr;
+    h->pinned_cap = 0;
+    FC_CUDA(cudaMallocHost(&h->pinned, bytes));
+    h->pinned_cap = bytes;
+  }
+  return h->pinned;
+}
+
+static void sync(H* h) { FC_CUDA(cudaStreamSynchronize(h->stream)); }
+static void check_launch(H* h) { h->stats.kernel_launches++; FC_CUDA(cudaGetLastError()); }
+
+static zd* blk(H* h, int slot) { return h->blk[slot].as<zd>(); }
+
+static void ensure_workspace(H* h, int64_t n, int m0) {
+  FC_REQUIRE(m0 >= 1 && m0 <= FC_MAXCOLS, "M0 must be in [1,128] on the GPU path");
+  const int ld = std::max(m0, 1);
+  if (h->ws_n != n || h->ws_ld < ld) {
+    h->ws_n = n;
+    h->ws_ld = ld;
+    h->have_subspace = false;
+    for (int s = 0; s < BS_COUNT; ++s) h->blk[s].ensure((size_t)n * ld * sizeof(zd));
+  }
+  const int maxblocks = h->sms * 8;
+  h->partial.ensure((size_t)3 * maxblocks * FC_MAXCOLS * sizeof(zd));
+  h->partial_r.ensure((size_t)maxblocks * FC_MAXCOLS * sizeof(double));
+  h->kstate.ensure(sizeof(KrylovState<double>));
+  h->small.ensure((size_t)8 * FC_MAXCOLS * FC_MAXCOLS * sizeof(zd));
+  h->small2.ensure((size_t)4 * FC_MAXCOLS * sizeof(zd) + 64);
+  h->red_ws.ensure((size_t)4 * FC_MAXCOLS * sizeof(zd));
+}
+
+static int ew_grid(H* h, int64_t n, int mp) {
+  const int rpb = 256 / mp;
+  int64_t g = (n + rpb - 1) / rpb;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)h->sms * 8));
+}
+
+// =====================================================================================================
+// operators: CSR ingest (SparseMatrixCSC -> device CSR)
+// =====================================================================================================
+static void ingest_csr(HostCsr& out, int64_t n, int64_t nnz, const int64_t* ptr, const int64_t* idx, const double* val,
+                       bool cplx, int base, int fmt, int structure) {
+  FC_REQUIRE(n > 0 && nnz >= 0 && ptr && (nnz == 0 || (idx && val)), "set_csr: bad arguments");
+  FC_REQUIRE(nnz < (int64_t)2147483647 && n < (int64_t)2147483647, "set_csr: int32 index range exceeded");
+  FC_REQUIRE(ptr[n] - base == nnz && ptr[0] - base == 0, "set_csr: pointer array inconsistent with nnz");
+  out.n = n;
+  out.nnz = nnz;
+  out.cplx = cplx;
+  const int vs = cplx ? 2 : 1;
+  out.ptr.assign(n + 1, 0);
+  out.col.assign(nnz, 0);
+  out.val.assign((size_t)nnz * vs, 0.0);
+  const bool transpose = (fmt == FEASTCUDA_CSC) && (structure == FEASTCUDA_GEN);
+  const bool conjugate = (fmt == FEASTCUDA_CSC) && (structure == FEASTCUDA_HERM) && cplx;
+  if (!transpose) {
+    for (int64_t i = 0; i <= n; ++i) out.ptr[i] = (int)(ptr[i] - base);
+    for (int64_t p = 0; p < nnz; ++p) {
+      const int64_t j = idx[p] - base;
+      FC_REQUIRE(j >= 0 && j < n, "set_csr: index out of range");
+      out.col[p] = (int)j;
+      if (cplx) { out.val[2 * p] = val[2 * p]; out.val[2 * p + 1] = conjugate ? -val[2 * p + 1] : val[2 * p + 1]; }
+      else out.val[p] = val[p];
+    }
+  } else {
+    std::vector<int> cnt(n + 1, 0);
+    for (int64_t p = 0; p < nnz; ++p) {
+      const int64_t j = idx[p] - base;
+      FC_REQUIRE(j >= 0 && j < n, "set_csr: index out of range");
+      cnt[j + 1]++;
+    }
+    for (int64_t i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+    for (int64_t i = 0; i <= n; ++i) out.ptr[i] = cnt[i];
+    std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+    for (int64_t c = 0; c < n; ++c)
+      for (int64_t p = ptr[c] - base; p < ptr[c + 1] - base; ++p) {
+        const int64_t rrow = idx[p] - base;
+        const int q = pos[rrow]++;
+        out.col[q] = (int)c;
+        if (cplx) { out.val[2 * (size_t)q] = val[2 * p]; out.val[2 * (size_t)q + 1] = val[2 * p + 1]; }
+        else out.val[q] = val[p];
+      }
+  }
+  out.set = true;
+}
+
+static void upload_csr(H* h, const HostCsr& src, DevCsr& dst, bool as_complex) {
+  dst.ptr.ensure((src.n + 1) * sizeof(int));
+  dst.col.ensure(std::max<int64_t>(src.nnz, 1) * sizeof(int));
+  FC_CUDA(cudaMemcpyAsync(dst.ptr.p, src.ptr.data(), (src.n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (src.nnz) FC_CUDA(cudaMemcpyAsync(dst.col.p, src.col.data(), src.nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (as_complex) {
+    std::vector<double> tmp;
+    const double* v = src.val.data();
+    if (!src.cplx) {
+      tmp.assign((size_t)2 * src.nnz, 0.0);
+      for (int64_t p = 0; p < src.nnz; ++p) tmp[2 * p] = src.val[p];
+      v = tmp.data();
+    }
+    dst.val.ensure(std::max<int64_t>(src.nnz, 1) * sizeof(zd));
+    if (src.nnz) FC_CUDA(cudaMemcpyAsync(dst.val.p, v, src.nnz * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+    sync(h);
+  } else {
+    dst.val.ensure(std::max<int64_t>(src.nnz, 1) * sizeof(double));
+    if (src.nnz) FC_CUDA(cudaMemcpyAsync(dst.val.p, src.val.data(), src.nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    sync(h);
+  }
+  dst.uploaded = true;
+}
+
+static void finalize_sparse(H* h) {
+  FC_REQUIRE(h->hA.set, "operator A has not been set");
+  const bool need_cplx = h->hA.cplx || (h->has_b && h->hB.cplx);
+  if (need_cplx != h->dev_complex) { h->dA.uploaded = false; h->dB.uploaded = false; h->dev_complex = need_cplx; }
+  if (!h->dA.uploaded) upload_csr(h, h->hA, h->dA, need_cplx);
+  if (h->has_b && !h->dB.uploaded) upload_csr(h, h->hB, h->dB, need_cplx);
+  h->n = h->hA.n;
+}
+
+// =====================================================================================================
+// launches
+// =====================================================================================================
+struct OpDesc {   // Y = zb*(B X) + za*(A X); use_b = 0 drops the B term, B unset means identity
+  zd za, zb;
+  bool use_a, use_b;
+};
+
+static int spmm_grid(H* h, int64_t n, int m) {
+  const int G = m <= 4 ? 4 : (m <= 8 ? 8 : (m <= 16 ? 16 : 32));
+  const int rpi = 8 * (32 / G);
+  int64_t g = (n + rpi - 1) / rpi;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)h->sms * 4));
+}
+
+template <typename TA, int MODE>
+static void spmm_dispatch(H* h, SpmmArgs<double, TA>& a, int grid) {
+  const int m = a.m;
+#define FC_L(G, NC) k_spmm<double, TA, G, NC, MODE><<<grid, 256, 0, h->stream>>>(a)
+  if (m <= 4) FC_L(4, 1);
+  else if (m <= 8) FC_L(8, 1);
+  else if (m <= 16) FC_L(16, 1);
+  else if (m <= 32) FC_L(32, 1);
+  else if (m <= 64) FC_L(32, 2);
+  else if (m <= 96) FC_L(32, 3);
+  else FC_L(32, 4);
+#undef FC_L
+}
+
+// returns the grid size used (= number of partial rows written per slot)
+template <int MODE>
+static int launch_spmm(H* h, const OpDesc& op, int m, const zd* X, zd* Y, const zd* aux, const zd* lam, bool sample = false) {
+  FC_REQUIRE(h->kind == OP_SPARSE, "sparse operator required");
+  const int grid = spmm_grid(h, h->n, m);
+  int ev = -1;
+  if (sample) {
+    if (h->ev_pool.size() < 64) {
+      cudaEvent_t a, b;
+      FC_CUDA(cudaEventCreate(&a));
+      FC_CUDA(cudaEventCreate(&b));
+      h->ev_pool.push_back(a);
+      h->ev_pool.push_back(b);
+      ev = (int)h->ev_pool.size() - 2;
+    }
+    if (ev >= 0) FC_CUDA(cudaEventRecord(h->ev_pool[ev], h->stream));
+  }
+  if (h->dev_complex) {
+    SpmmArgs<double, zd> a;
+    a.n = h->n; a.m = m; a.ld = h->ws_ld;
+    a.a_ptr = op.use_a ? h->dA.ptr.as<int>() : nullptr; a.a_col = h->dA.col.as<int>(); a.a_val = h->dA.val.as<zd>();
+    const bool bmat = op.use_b && h->has_b;
+    a.b_ptr = bmat ? h->dB.ptr.as<int>() : nullptr; a.b_col = h->dB.col.as<int>(); a.b_val = h->dB.val.as<zd>();
+    a.skip_b = op.use_b ? 0 : 1;
+    a.za = op.za; a.zb = op.zb; a.X = X; a.Y = Y; a.aux = aux; a.lam = lam;
+    a.partial = h->partial.as<zd>(); a.pstride = FC_MAXCOLS;
+    spmm_dispatch<zd, MODE>(h, a, grid);
+  } else {
+    SpmmArgs<double, double> a;
+    a.n = h->n; a.m = m; a.ld = h->ws_ld;
+    a.a_ptr = op.use_a ? h->dA.ptr.as<int>() : nullptr; a.a_col = h->dA.col.as<int>(); a.a_val = h->dA.val.as<double>();
+    const bool bmat = op.use_b && h->has_b;
+    a.b_ptr = bmat ? h->dB.ptr.as<int>() : nullptr; a.b_col = h->dB.col.as<int>(); a.b_val = h->dB.val.as<double>();
+    a.skip_b = op.use_b ? 0 : 1;
+    a.za = op.za; a.zb = op.zb; a.X = X; a.Y = Y; a.aux = aux; a.lam = lam;
+    a.partial = h->partial.as<zd>(); a.pstride = FC_MAXCOLS;
+    spmm_dispatch<double, MODE>(h, a, grid);
+  }
+  check_launch(h);
+  h->stats.spmm_launches++;
+  if (ev >= 0) {
+    FC_CUDA(cudaEventRecord(h->ev_pool[ev + 1], h->stream));
+    h->ev_pending.push_back({ev, ev + 1});
+  }
+  return grid;
+}
+
+static void drain_events(H* h) {
+  for (auto& pr : h->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[pr.first], h->ev_pool[pr.second]) == cudaSuccess) {
+      h->stats.ms_spmm_sampled += ms;
+      h->stats.spmm_sampled++;
+    }
+  }
+  h->ev_pending.clear();
+  // events are reused: keep the pool, hand them out again from the start
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  h->ev_pool.clear();
+}
+
+static OpDesc op_shifted(zc z) { return OpDesc{mk<double>(-1.0, 0.0), tozd(z), true, true}; }
+static OpDesc op_A() { return OpDesc{mk<double>(1.0, 0.0), mk<double>(0.0, 0.0), true, false}; }
+static OpDesc op_B() { return OpDesc{mk<double>(0.0, 0.0), mk<double>(1.0, 0.0), false, true}; }
+
+template <typename T>
+static void reduce_to_host(H* h, const T* partial, int nslots, int nblocks, int m, T* host_out) {
+  T* dev = h->red_ws.as<T>();
+  const size_t sm = ((size_t)nslots * FC_MAXCOLS + 1024) * sizeof(T);
+  k_reduce_partials<T><<<1, 1024, sm, h->stream>>>(partial, nslots, nblocks, FC_MAXCOLS, m, dev);
+  check_launch(h);
+  FC_CUDA(cudaMemcpyAsync(host_out, dev, (size_t)nslots * m * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+}
+
+static void col_norms(H* h, int m, const zd* X, std::vector<double>& out) {
+  const int mp = pow2_ge(m), grid = ew_grid(h, h->ws_n, mp);
+  k_colnorm2<double><<<grid, 256, 0, h->stream>>>(h->ws_n, m, mp, h->ws_ld, X, h->partial_r.as<double>(), FC_MAXCOLS);
+  check_launch(h);
+  out.assign(m, 0.0);
+  reduce_to_host<double>(h, h->partial_r.as<double>(), 1, grid, m, out.data());
+  for (auto& v : out) v = std::sqrt(v);
+}
+
+static void copy_cols(H* h, int m, const zd* src, zd* dst) {
+  FC_CUDA(cudaMemcpy2DAsync(dst, (size_t)h->ws_ld * sizeof(zd), src, (size_t)h->ws_ld * sizeof(zd), (size_t)m * sizeof(zd),
+                            (size_t)h->ws_n, cudaMemcpyDeviceToDevice, h->stream));
+}
+static void zero_cols(H* h, int m, zd* dst) {
+  FC_CUDA(cudaMemset2DAsync(dst, (size_t)h->ws_ld * sizeof(zd), 0, (size_t)m * sizeof(zd), (size_t)h->ws_n, h->stream));
+}
+
+static void axpby_cols(H* h, int m, zc w, double beta, const zd* X, zd* Y) {
+  const int mp = pow2_ge(m), grid = ew_grid(h, h->ws_n, mp);
+  k_axpby_cols<double><<<grid, 256, 0, h->stream>>>(h->ws_n, m, mp, h->ws_ld, h->ws_ld, tozd(w), beta, X, Y);
+  check_launch(h);
+}
+
+static void scale_cols(H* h, int m, const std::vector<zc>& f, const zd* X, zd* Y) {
+  zd* df = h->small2.as<zd>();
+  FC_CUDA(cudaMemcpyAsync(df, f.data(), (size_t)m * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  const int mp = pow2_ge(m), grid = ew_grid(h, h->ws_n, mp);
+  k_scale_cols<double><<<grid, 256, 0, h->stream>>>(h->ws_n, m, mp, h->ws_ld, h->ws_ld, df, X, Y);
+  check_launch(h);
+  sync(h);  // f is host memory owned by the caller
+}
+
+// host (column-major) <-> device (row-major) staging; host buffers go through a pinned bounce buffer
+template <typename TIN>
+static void upload_block(H* h, int64_t n, int m, const TIN* host, zd* dst) {
+  const size_t bytes = (size_t)n * m * sizeof(TIN);
+  h->stage.ensure(bytes);
+  Timer t;
+  FC_CUDA(cudaMemcpyAsync(h->stage.p, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
+  k_col2row<TIN, double><<<grid, 256, 0, h->stream>>>(n, m, n, h->ws_ld, h->stage.as<TIN>(), dst);
+  check_launch(h);
+  sync(h);
+  h->stats.ms_h2d += t.ms();
+}
+template <typename TOUT>
+static void download_block(H* h, int64_t n, int m, const zd* src, TOUT* host) {
+  if (m <= 0) return;
+  const size_t bytes = (size_t)n * m * sizeof(TOUT);
+  h->stage.ensure(bytes);
+  Timer t;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
+  k_row2col<TOUT, double><<<grid, 256, 0, h->stream>>>(n, m, h->ws_ld, n, src, h->stage.as<TOUT>());
+  check_launch(h);
+  FC_CUDA(cudaMemcpyAsync(host, h->stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  h->stats.ms_d2h += t.ms();
+}
+
+// C (a x b, row-major host) = X[:, :a]^H Y[:, :b]
+static void gram_host(H* h, int a, int b, const zd* X, const zd* Y, std::vector<zc>& C) {
+  const int64_t n = h->ws_n;
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->sms * 2));
+  h->gram_partial.ensure((size_t)chunks * a * b * sizeof(zd));
+  dim3 grid(chunks, (a + 63) / 64, (b + 63) / 64);
+  k_gram<double><<<grid, 256, 0, h->stream>>>(n, a, b, h->ws_ld, h->ws_ld, X, Y, h->gram_partial.as<zd>());
+  check_launch(h);
+  zd* out = h->small.as<zd>();
+  const int64_t len = (int64_t)a * b;
+  k_sum_chunks<zd><<<(int)std::min<int64_t>((len + 255) / 256, 1024), 256, 0, h->stream>>>(len, chunks, h->gram_partial.as<zd>(), out);
+  check_launch(h);
+  C.resize((size_t)len);
+  FC_CUDA(cudaMemcpyAsync(C.data(), out, (size_t)len * sizeof(zd), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+}
+
+// Y[:, :b] = X[:, :a] * T  (T row-major a x b on host)
+static void rowtransform(H* h, int a, int b, const zd* X, const std::vector<zc>& T, zd* Y) {
+  zd* dT = h->small.as<zd>() + (size_t)4 * FC_MAXCOLS * FC_MAXCOLS;
+  FC_CUDA(cudaMemcpyAsync(dT, T.data(), (size_t)a * b * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((unsigned)((h->ws_n + 63) / 64), (unsigned)((b + 63) / 64));
+  k_rowtransform<double><<<grid, 256, 0, h->stream>>>(h->ws_n, a, b, h->ws_ld, h->ws_ld, b, X, dT, Y);
+  check_launch(h);
+  sync(h);
+}
+
+// =====================================================================================================
+// block BiCGStab (all m columns in lock step), see oracle/feast_port.py:block_bicgstab for the CPU port
+// =====================================================================================================
+struct SolveOut {
+  std::vector<int> iters;
+  std::vector<double> truenorm, target;
+  std::vector<char> ok;
+  int it_total = 0;
+};
+
+static void block_bicgstab(H* h, zc z, int m, const zd* RHS, zd* X, bool use_x0, const feastcuda_solver_opts& o, double tol,
+                           SolveOut& out) {
+  const int64_t n = h->ws_n;
+  const int64_t ld = h->ws_ld;
+  zd *r = blk(h, BS_KR), *rh = blk(h, BS_KRH), *p = blk(h, BS_KP), *v = blk(h, BS_KV), *s = blk(h, BS_KS), *t = blk(h, BS_KT);
+  zd* xb = blk(h, BS_KB);  // iterate at the start of the current round (restored for diverged columns)
+  const OpDesc S = op_shifted(z);
+  const int mp = pow2_ge(m);
+  const int egrid = ew_grid(h, n, mp);
+  KrylovState<double>* dst = h->kstate.as<KrylovState<double>>();
+  static thread_local KrylovState<double> hst;
+  const int maxiter = std::max(1, o.maxiter);
+  const int max_restarts = std::max(0, o.restart);
+  const int check_every = o.check_every > 0 ? o.check_every : 8;
+
+  std::vector<double> bn, rn(m);
+  col_norms(h, m, RHS, bn);
+  out.target.assign(m, 0.0);
+  for (int c = 0; c < m; ++c) out.target[c] = tol + tol * bn[c];
+  if (!use_x0) zero_cols(h, m, X);
+  out.iters.assign(m, 0);
+  out.it_total = 0;
+  memset(&hst, 0, sizeof(hst));
+  bool first = true;
+  for (int restart = 0; restart <= max_restarts; ++restart) {
+    const int g0 = launch_spmm<SPMM_RESID>(h, S, m, X, r, RHS, nullptr);
+    std::vector<zd> tmp(m);
+    reduce_to_host<zd>(h, h->partial.as<zd>(), 1, g0, m, tmp.data());
+    for (int c = 0; c < m; ++c) rn[c] = std::sqrt(tmp[c].x);
+    if (first) {
+      if (o.inner_rel > 0)
+        for (int c = 0; c < m; ++c) out.target[c] = std::max(out.target[c], o.inner_rel * rn[c]);
+      first = false;
+    }
+    int nact = 0;
+    for (int c = 0; c < m; ++c) {
+      hst.active[c] = rn[c] > out.target[c] ? 1 : 0;
+      nact += hst.active[c];
+      hst.target[c] = out.target[c];
+      hst.rnorm[c] = rn[c];
+      hst.rn0[c] = rn[c];
+      hst.diverged[c] = 0;
+      hst.rho[c] = mk<double>(rn[c] * rn[c], 0.0);
+      hst.alpha[c] = hst.omega[c] = hst.beta[c] = mk<double>(0.0, 0.0);
+      hst.flags[c] = 0;
+      hst.iters[c] = out.iters[c];
+    }
+    hst.n_active = nact;
+    if (nact == 0 || out.it_total >= maxiter) break;
+    FC_CUDA(cudaMemcpyAsync(dst, &hst, sizeof(hst), cudaMemcpyHostToDevice, h->stream));
+    copy_cols(h, m, r, rh);
+    copy_cols(h, m, r, p);
+    copy_cols(h, m, X, xb);
+    int* flag = reinterpret_cast<int*>(pinned_buf(h, 64));
+    while (out.it_total < maxiter) {
+      const bool sample = (out.it_total % 16) == 0;
+      const int g1 = launch_spmm<SPMM_DOT_RHAT>(h, S, m, p, v, rh, nullptr, sample);
+      k_bicg_scal1<double><<<1, 1024, 0, h->stream>>>(dst, h->partial.as<zd>(), g1, FC_MAXCOLS, m);
+      check_launch(h);
+      k_upd_s<double><<<egrid, 256, 0, h->stream>>>(n, m, mp, ld, dst, r, v, s);
+      check_launch(h);
+      const int g2 = launch_spmm<SPMM_DOT_TS>(h, S, m, s, t, rh, nullptr);
+      k_bicg_scal2<double><<<1, 1024, 0, h->stream>>>(dst, h->partial.as<zd>(), g2, FC_MAXCOLS, m);
+      check_launch(h);
+      k_upd_xrp<double><<<egrid, 256, 0, h->stream>>>(n, m, mp, ld, dst, X, r, p, v, s, t, h->partial_r.as<double>(), FC_MAXCOLS);
+      check_launch(h);
+      k_bicg_scal3<double><<<1, 1024, 0, h->stream>>>(dst, h->partial_r.as<double>(), egrid, FC_MAXCOLS, m);
+      check_launch(h);
+      out.it_total++;
+      h->stats.krylov_iters++;
+      if (out.it_total % check_every == 0 || out.it_total >= maxiter) {
+        FC_CUDA(cudaMemcpyAsync(flag, &dst->n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        sync(h);
+        if (*flag == 0) break;
+      }
+    }
+    FC_CUDA(cudaMemcpyAsync(&hst, dst, sizeof(hst), cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+    bool any_div = false;
+    for (int c = 0; c < m; ++c) { out.iters[c] = hst.iters[c]; any_div = any_div || hst.diverged[c]; }
+    if (any_div) {
+      k_restore_cols<double><<<egrid, 256, 0, h->stream>>>(n, m, mp, ld, dst->diverged, xb, X);
+      check_launch(h);
+    }
+  }
+  // true residual of the returned block (the reference's explicit gate, sparse/feast_sparse.jl:189-198)
+  {
+    const int g0 = launch_spmm<SPMM_RESID>(h, S, m, X, r, RHS, nullptr);
+    std::vector<zd> tmp(m);
+    reduce_to_host<zd>(h, h->partial.as<zd>(), 1, g0, m, tmp.data());
+    out.truenorm.assign(m, 0.0);
+    out.ok.assign(m, 0);
+    for (int c = 0; c < m; ++c) {
+      out.truenorm[c] = std::sqrt(tmp[c].x);
+      out.ok[c] = out.truenorm[c] <= 10.0 * out.target[c];
+    }
+  }
+  int64_t ci = 0;
+  for (int c = 0; c < m; ++c) ci += out.iters[c];
+  h->stats.col_iters += ci;
+  drain_events(h);
+}
+
+// =====================================================================================================
+// rank-revealing orthonormalisation (K7: _feast_qr_compress!, core/feast_aux.jl:101-131)
+// in: Z0 (n x ncols in slot `src`), out: orthonormal basis in the returned slot, rank
+// =====================================================================================================
+static int orthonormalize(H* h, int ncols, int src_slot, int tmp_slot, double rank_tol, int* out_slot) {
+  const int64_t n = h->ws_n;
+  int cur = ncols, done = 0, a_slot = src_slot, b_slot = tmp_slot;
+  double thr_abs = -1.0;
+  const double eps = 2.220446049250313e-16;
+  std::vector<zc> G;
+  for (int pass = 0; pass < 16; ++pass) {
+    gram_host(h, cur, cur, blk(h, a_slot), blk(h, a_slot), G);
+    h->stats.ortho_passes++;
+    if (pass == 0) {
+      double dmax = 0.0;
+      for (int j = 0; j < cur; ++j) dmax = std::max(dmax, G[(size_t)j * cur + j].real());
+      if (!(dmax > 0.0)) { *out_slot = a_slot; return 0; }
+      thr_abs = std::max(rank_tol, eps * (double)std::max<int64_t>(n, ncols)) * std::sqrt(dmax);
+    }
+    if (done == cur) {
+      double err = 0.0;
+      for (int i = 0; i < cur; ++i)
+        for (int j = 0; j < cur; ++j) err = std::max(err, std::abs(G[(size_t)i * cur + j] - (i == j ? zc(1.0) : zc(0.0))));
+      if (err <= 1e-14) break;
+    }
+    OrthoPass op = ortho_pass(G, cur, done, thr_abs, 1e-8);
+    const int nout = op.accepted + op.kept;
+    if (nout == 0) { *out_slot = a_slot; return 0; }
+    rowtransform(h, cur, nout, blk(h, a_slot), op.T, blk(h, b_slot));
+    std::swap(a_slot, b_slot);
+    done = op.accepted;
+    cur = nout;
+  }
+  *out_slot = a_slot;
+  return done;
+}
+
+// =====================================================================================================
+// reduced eigenproblem on device (K9)
+// =====================================================================================================
+static void reduced_eig(H* h, int r, const std::vector<zc>& Sq, const std::vector<zc>* Aq, std::vector<double>& lam,
+                        std::vector<zc>& V, int* status) {
+  const size_t rr = (size_t)r * r;
+  zd* base = h->small.as<zd>();
+  zd *dS = base, *dB = base + rr, *dV = base + 2 * rr, *dW = base + 3 * rr, *dX = base + 4 * rr;
+  double* dlam = reinterpret_cast<double*>(base + 5 * rr);
+  int* dstat = reinterpret_cast<int*>(h->small2.as<char>());
+  FC_CUDA(cudaMemcpyAsync(dS, Sq.data(), rr * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  if (Aq) FC_CUDA(cudaMemcpyAsync(dB, Aq->data(), rr * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  ReducedEigArgs<double> a;
+  a.r = r; a.generalized = Aq ? 1 : 0; a.S = dS; a.Bq = dB; a.V = dV; a.W = dW; a.lam = dlam; a.Xout = dX;
+  a.status = dstat; a.sweeps = dstat + 1;
+  k_reduced_eig<double><<<1, 512, 0, h->stream>>>(a);
+  check_launch(h);
+  lam.resize(r);
+  V.resize(rr);
+  int st[2] = {0, 0};
+  FC_CUDA(cudaMemcpyAsync(lam.data(), dlam, r * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  FC_CUDA(cudaMemcpyAsync(V.data(), dX, rr * sizeof(zd), cudaMemcpyDeviceToHost, h->stream));
+  FC_CUDA(cudaMemcpyAsync(st, dstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  *status = st[0];
+  h->stats.jacobi_sweeps += st[1];
+}
+
+static void hermitian_part(std::vector<zc>& M, int r) {  // _feast_hermitian_part!, core/feast_aux.jl:84-92
+  for (int i = 0; i < r; ++i)
+    for (int j = i; j < r; ++j) {
+      const zc v = 0.5 * (M[(size_t)i * r + j] + std::conj(M[(size_t)j * r + i]));
+      M[(size_t)i * r + j] = v;
+      M[(size_t)j * r + i] = std::conj(v);
+    }
+}
+
+// =====================================================================================================
+// NCCL (resolved at run time; the single-GPU path has no NCCL dependency)
+// =====================================================================================================
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static void nccl_load() {
+  if (g_nccl.lib) return;
+  const char* env = getenv("FEASTCUDA_NCCL_LIB");
+  const char* cands[] = {env, "libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; i < 3 && !g_nccl.lib; ++i)
+    if (cands[i]) g_nccl.lib = dlopen(cands[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.lib) throw FcError(FEASTCUDA_ERR_NCCL, "libnccl.so.2 not found (set FEASTCUDA_NCCL_LIB)");
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    throw FcError(FEASTCUDA_ERR_NCCL, "libnccl: missing symbols");
+}
+#define FC_NCCL(call)                                                                                          \
+  do {                                                                                                         \
+    int r_ = (call);                                                                                           \
+    if (r_ != 0)                                                                                               \
+      throw FcError(FEASTCUDA_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+  } while (0)
+
+static void allreduce_block(H* h, zd* buf, int64_t count_zd) {
+  if (h->nranks <= 1) return;
+  Timer t;
+  FC_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count_zd * 2, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->nccl_comm, h->stream));
+  sync(h);
+  h->stats.ms_allreduce += t.ms();
+  h->stats.allreduce_bytes += count_zd * (int64_t)sizeof(zd);
+}
+
+// =====================================================================================================
+// work sharding across ranks
+// =====================================================================================================
+struct WorkItem { int node, c0, nc; };
+
+static std::vector<WorkItem> build_items(int ne, int active, int nranks, int rank, int shard, const std::vector<double>& cost) {
+  std::vector<WorkItem> items;
+  if (nranks <= 1) {
+    for (int e = 0; e < ne; ++e) items.push_back({e, 0, active});
+    return items;
+  }
+  if (shard == FEASTCUDA_SHARD_NODES) {
+    int64_t s, c;
+    host_node_partition(ne, nranks, rank, &s, &c);
+    for (int64_t e = s; e < s + c; ++e) items.push_back({(int)e, 0, active});
+    return items;
+  }
+  if (shard == FEASTCUDA_SHARD_COLUMNS) {
+    const int base = active / nranks, rem = active % nranks;
+    const int c0 = rank * base + std::min(rank, rem), nc = base + (rank < rem ? 1 : 0);
+    if (nc > 0)
+      for (int e = 0; e < ne; ++e) items.push_back({e, c0, nc});
+    return items;
+  }
+  // balanced: the (node, column) cells, node-major, are cut into nranks contiguous runs of equal cost
+  double total = 0.0;
+  for (int e = 0; e < ne; ++e) total += cost[e] * active;
+  const double lo = total * rank / nranks, hi = total * (rank + 1) / nranks;
+  double acc = 0.0;
+  for (int e = 0; e < ne; ++e) {
+    const double ce = cost[e];
+    const double n0 = acc, n1 = acc + ce * active;
+    if (n1 > lo && n0 < hi && ce > 0) {
+      int c0 = (int)std::llround(std::max(0.0, (lo - n0) / ce));
+      int c1 = (int)std::llround(std::min((double)active, (hi - n0) / ce));
+      c0 = std::max(0, std::min(active, c0));
+      c1 = std::max(c0, std::min(active, c1));
+      if (c1 > c0) items.push_back({e, c0, c1 - c0});
+    }
+    acc = n1;
+  }
+  return items;
+}
+
+// =====================================================================================================
+// per-node block solve, any operator kind
+// =====================================================================================================
+static bool node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X, bool use_x0, const feastcuda_solver_opts& o, double tol,
+                       SolveOut& so) {
+  if (h->kind == OP_SPARSE) {
+    block_bicgstab(h, z, m, RHS, X, use_x0, o, tol, so);
+    bool all_ok = true;
+    for (int c = 0; c < m; ++c) all_ok = all_ok && so.ok[c];
+    return all_ok;
+  }
+  if (h->kind == OP_DENSE) return dense_node_solve(h, node, z, m, RHS, X);
+  if (h->kind == OP_BAND) return band_node_solve(h, node, z, m, RHS, X);
+  throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
+}
+
+static void apply_op(H* h, int which, int m, const zd* X, zd* Y) {
+  if (h->kind == OP_SPARSE) {
+    if (which == FEASTCUDA_A) launch_spmm<SPMM_PLAIN>(h, op_A(), m, X, Y, nullptr, nullptr);
+    else launch_spmm<SPMM_PLAIN>(h, op_B(), m, X, Y, nullptr, nullptr);
+  } else if (h->kind == OP_DENSE) dense_apply(h, which, m, X, Y);
+  else if (h->kind == OP_BAND) band_apply(h, which, m, X, Y);
+  else throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
+}
+
+// res_j = ||A x_j - lam_j B x_j||_2 (not yet divided by max(|lam|,1))
+static void eig_residual_norms(H* h, int m, const zd* X, const std::vector<zc>& lam, std::vector<double>& out) {
+  out.assign(m, 0.0);
+  if (m == 0) return;
+  if (h->kind == OP_SPARSE) {
+    zd* dl = h->small2.as<zd>() + 8;
+    FC_CUDA(cudaMemcpyAsync(dl, lam.data(), (size_t)m * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+    OpDesc d = op_shifted(zc(0.0));
+    const int g = launch_spmm<SPMM_EIGRES>(h, d, m, X, nullptr, nullptr, dl);
+    std::vector<zd> tmp(m);
+    reduce_to_host<zd>(h, h->partial.as<zd>(), 1, g, m, tmp.data());
+    for (int c = 0; c < m; ++c) out[c] = std::sqrt(tmp[c].x);
+  } else {
+    // dense / band: R = A X - (B X) diag(lam) with the generic kernels
+    zd *ax = blk(h, BS_KS), *bx = blk(h, BS_KT);
+    apply_op(h, FEASTCUDA_A, m, X, ax);
+    const zd* bxp = X;
+    if (h->has_b) { apply_op(h, FEASTCUDA_B, m, X, bx); bxp = bx; }
+    std::vector<zc> f(m);
+    for (int c = 0; c < m; ++c) f[c] = -lam[c];
+    zd* tmpb = blk(h, BS_KV);
+    scale_cols(h, m, f, bxp, tmpb);
+    axpby_cols(h, m, zc(1.0), 1.0, ax, tmpb);
+    col_norms(h, m, tmpb, out);
+  }
+}
+
+// =====================================================================================================
+// H-RR refinement loop (dense/feast_dense.jl:78-351, sparse/feast_sparse.jl:246-499, banded:561-823)
+// =====================================================================================================
+static feastcuda_solver_opts default_opts() {
+  feastcuda_solver_opts o;
+  memset(&o, 0, sizeof(o));
+  o.solver = FEASTCUDA_SOLVER_BICGSTAB;
+  o.maxiter = 500;
+  o.restart = 3;
+  o.check_every = 8;
+  o.filter = FEASTCUDA_FILTER_REFERENCE;
+  o.shard = FEASTCUDA_SHARD_NODES;
+  return o;
+}
+
+static bool pencil_is_real(H* h) {
+  if (h->kind == OP_SPARSE) return !h->dev_complex;
+  if (h->kind == OP_DENSE) return !h->denseA.cplx && !(h->has_b && h->denseB.cplx);
+  if (h->kind == OP_BAND) return !h->bandA.cplx && !(h->has_b && h->bandB.cplx);
+  return false;
+}
+
+static void prepare_operator(H* h) {
+  if (h->kind == OP_SPARSE) finalize_sparse(h);
+  else if (h->kind == OP_DENSE) dense_prepare(h);
+  else if (h->kind == OP_BAND) band_prepare(h);
+  else throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
+}
+
+static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, const zc* Zne, const zc* Wne, int ne,
+                         const feastcuda_solver_opts* optsp, int64_t* Mout, int64_t* info, double* epsout, int64_t* loopout,
+                         bool subspace_is_real) {
+  Timer ttotal;
+  if (host_feastdefault(fpm)) throw FcError(FEASTCUDA_ERR_ARG, "invalid fpm (feastdefault!)");
+  prepare_operator(h);
+  const int64_t n = h->n;
+  // check_feast_srci_input, core/feast_aux.jl:369-399 (the shim throws ArgumentError before the ccall)
+  FC_REQUIRE(n > 0, "Matrix size N must be positive");
+  FC_REQUIRE(m0 > 0 && m0 <= n, "Number of eigenvalues M0 must be between 1 and N");
+  FC_REQUIRE(Emin < Emax, "Search interval [Emin, Emax] must be valid");
+  FC_REQUIRE(ne >= 1 && ne <= 128 && Zne && Wne, "contour required");
+  FC_REQUIRE(h->have_subspace && h->sub_m0 == m0 && h->ws_n == n, "initial subspace not uploaded for this (n, M0)");
+  feastcuda_solver_opts o = optsp ? *optsp : default_opts();
+  const double tol = (o.tol == 0.0) ? std::pow(10.0, -(double)fpm[2]) : o.tol;
+  const double eps_tol = host_feast_tolerance(fpm);
+  const int maxloop = (int)fpm[3];
+  const bool real_mode = (o.filter == FEASTCUDA_FILTER_TRUE) && pencil_is_real(h) && subspace_is_real;
+  const bool iterative = (h->kind == OP_SPARSE);
+  int shard = o.shard;
+  if (!iterative) shard = FEASTCUDA_SHARD_NODES;
+
+  int active = m0, rank = 0, M = 0, M_found = 0, loop_count = 0;
+  int info_code = 0;
+  double eps_val = INFINITY;
+  std::vector<double> lam(m0, 0.0), res(m0, 0.0);
+  std::vector<double> cost(ne, 1.0);
+  bool have_ritz = false;
+  int qb = BS_QB, xr = BS_XR;  // current basis / Ritz-vector slots (swapped every loop)
+  int res_slot = -1;           // slot holding the Ritz vectors that M_found refers to
+  std::vector<zc> Sq, Aq, V;
+  std::vector<double> lam_red;
+
+  for (int loop_idx = 0; loop_idx <= maxloop; ++loop_idx) {
+    loop_count = loop_idx;
+    h->stats.loops++;
+    Timer tsolve;
+    zd* basis = blk(h, qb);
+    const zd* rhs = basis;
+    if (h->has_b) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
+    zero_cols(h, active, blk(h, BS_ACC));
+    std::vector<WorkItem> items = build_items(ne, active, h->nranks, h->rank, shard, cost);
+    std::vector<double> node_cost(ne, 0.0), node_cols(ne, 0.0);
+    bool failed = false;
+    for (const WorkItem& it : items) {
+      const zc z = Zne[it.node];
+      zd* X = blk(h, BS_KX) + it.c0;
+      bool use_x0 = false;
+      if (iterative && o.ritz_guess && have_ritz) {
+        std::vector<zc> f(it.nc);
+        for (int c = 0; c < it.nc; ++c) f[c] = zc(1.0) / (z - lam[it.c0 + c]);
+        scale_cols(h, it.nc, f, basis + it.c0, X);
+        use_x0 = true;
+      }
+      SolveOut so;
+      const bool ok = node_solve(h, it.node, z, it.nc, rhs + it.c0, X, use_x0, o, tol, so);
+      h->stats.node_solves++;
+      if (iterative) {
+        h->stats.node_iters[it.node] = so.it_total;
+        node_cost[it.node] += (double)so.it_total * it.nc;
+        node_cols[it.node] += it.nc;
+      }
+      if (!ok && (!iterative || o.inner_rel <= 0.0)) { failed = true; info_code = iterative ? 5 : 8; break; }
+      axpby_cols(h, it.nc, 2.0 * Wne[it.node], 1.0, X, blk(h, BS_ACC) + it.c0);
+    }
+    sync(h);
+    h->stats.ms_solve += tsolve.ms();
+    if (h->nranks > 1) {
+      // one exchange per refinement loop: MPI.Allreduce(Q_proj), parallel/feast_mpi.jl:119,341,858
+      int64_t fl[1] = {failed ? 1 : 0};
+      allreduce_block(h, blk(h, BS_ACC), (int64_t)n * h->ws_ld);
+      // failure flag + measured node costs ride along in a tiny second reduction
+      std::vector<double> pack(2 * ne + 1, 0.0);
+      for (int e = 0; e < ne; ++e) { pack[e] = node_cost[e]; pack[ne + e] = node_cols[e]; }
+      pack[2 * ne] = (double)fl[0];
+      double* dp = reinterpret_cast<double*>(h->small2.as<zd>() + 2 * FC_MAXCOLS);
+      FC_CUDA(cudaMemcpyAsync(dp, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      FC_NCCL(g_nccl.AllReduce(dp, dp, pack.size(), 8, 0, h->nccl_comm, h->stream));
+      FC_CUDA(cudaMemcpyAsync(pack.data(), dp, pack.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      sync(h);
+      for (int e = 0; e < ne; ++e) { node_cost[e] = pack[e]; node_cols[e] = pack[ne + e]; }
+      if (pack[2 * ne] > 0) { failed = true; if (!info_code) info_code = iterative ? 5 : 8; }
+    }
+    if (failed) break;
+    if (iterative)
+      for (int e = 0; e < ne; ++e) cost[e] = node_cols[e] > 0 ? std::max(1.0, node_cost[e] / node_cols[e]) : 1.0;
+
+    if (real_mode) {
+      const int mp = pow2_ge(active);
+      k_zero_imag<double><<<ew_grid(h, n, mp), 256, 0, h->stream>>>(n, active, mp, h->ws_ld, blk(h, BS_ACC));
+      check_launch(h);
+    }
+    Timer tortho;
+    int qslot = BS_ACC;
+    rank = orthonormalize(h, active, BS_ACC, BS_KP, std::sqrt(2.220446049250313e-16), &qslot);
+    h->stats.ms_ortho += tortho.ms();
+    if (rank == 0) { info_code = 5; break; }
+    Timer tproj;
+    zd* Q = blk(h, qslot);
+    apply_op(h, FEASTCUDA_A, rank, Q, blk(h, BS_KS));
+    gram_host(h, rank, rank, Q, blk(h, BS_KS), Sq);
+    hermitian_part(Sq, rank);
+    if (h->has_b) {
+      apply_op(h, FEASTCUDA_B, rank, Q, blk(h, BS_KT));
+      gram_host(h, rank, rank, Q, blk(h, BS_KT), Aq);
+      hermitian_part(Aq, rank);
+    }
+    h->stats.ms_project += tproj.ms();
+    Timer teig;
+    int est = 0;
+    reduced_eig(h, rank, Sq, h->has_b ? &Aq : nullptr, lam_red, V, &est);
+    h->stats.ms_eig += teig.ms();
+    if (getenv("FEASTCUDA_VERBOSE"))
+      fprintf(stderr, "[feastcuda r%d] loop %d: rank=%d eig status=%d lam_red[0..2]=%.6e %.6e %.6e\n", h->rank, loop_idx, rank, est,
+              lam_red[0], lam_red[rank > 1 ? 1 : 0], lam_red[rank > 2 ? 2 : 0]);
+    if (est == 1) { info_code = 8; break; }
+    // _feast_reorder_by_interval! (stable partition, core/feast_aux.jl:144-197) folded into V's column order;
+    // unit 2-norm of the M inside Ritz vectors (dense/feast_dense.jl:301-305): ||Q v|| = ||v|| for orthonormal Q
+    std::vector<int> perm;
+    for (int i = 0; i < rank; ++i) if (Emin <= lam_red[i] && lam_red[i] <= Emax) perm.push_back(i);
+    M = (int)perm.size();
+    for (int i = 0; i < rank; ++i) if (!(Emin <= lam_red[i] && lam_red[i] <= Emax)) perm.push_back(i);
+    if (M == 0) { info_code = 5; break; }
+    std::vector<zc> T((size_t)rank * rank);
+    for (int k = 0; k < rank; ++k) {
+      const int srcc = perm[k];
+      double nrm = 1.0;
+      if (k < M) {
+        double s2 = 0.0;
+        for (int i = 0; i < rank; ++i) s2 += std::norm(V[(size_t)i * rank + srcc]);
+        nrm = s2 > 0 ? std::sqrt(s2) : 1.0;
+      }
+      for (int i = 0; i < rank; ++i) T[(size_t)i * rank + k] = V[(size_t)i * rank + srcc] / nrm;
+      lam[k] = lam_red[srcc];
+    }
+    Timer tres;
+    rowtransform(h, rank, rank, Q, T, blk(h, xr));
+    res_slot = xr;
+    std::vector<zc> lamc(M);
+    for (int j = 0; j < M; ++j) lamc[j] = zc(lam[j], 0.0);
+    std::vector<double> rnorm;
+    eig_residual_norms(h, M, blk(h, xr), lamc, rnorm);
+    double max_res = 0.0;
+    for (int j = 0; j < M; ++j) {
+      res[j] = rnorm[j] / std::max(std::fabs(lam[j]), 1.0);
+      max_res = std::max(max_res, res[j]);
+    }
+    h->stats.ms_resid += tres.ms();
+    eps_val = max_res;
+    M_found = M;
+    if (getenv("FEASTCUDA_VERBOSE"))
+      fprintf(stderr, "[feastcuda r%d] loop %d: M=%d rank=%d epsout=%.3e items=%zu iters(last)=%d\n", h->rank, loop_idx, M, rank,
+              eps_val, items.size(), (int)h->stats.node_iters[items.empty() ? 0 : items.back().node]);
+    if (eps_val <= eps_tol) break;
+    if (loop_idx == maxloop) { info_code = 5; break; }
+    active = rank;
+    std::swap(qb, xr);   // Q_basis <- Ritz vectors (dense/feast_dense.jl:336-337)
+    have_ritz = true;
+  }
+  if (M_found == 0 && info_code == 0) info_code = 5;
+  // keep the public result slot fixed: the final Ritz vectors go to BS_XR
+  if (res_slot >= 0 && res_slot != BS_XR) {
+    copy_cols(h, std::max(rank, 1), blk(h, res_slot), blk(h, BS_XR));
+    sync(h);
+  }
+  h->res_m0 = m0;
+  h->res_M = M_found;
+  h->res_rank = rank;
+  h->res_lambda.assign(lam.begin(), lam.end());
+  h->res_res.assign(res.begin(), res.end());
+  h->res_general = false;
+  h->have_subspace = false;  // the basis slot was consumed
+  *Mout = M_found;
+  *info = info_code;
+  *epsout = eps_val;
+  *loopout = loop_count;
+  h->stats.ms_total += ttotal.ms();
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define FC_TRY(hh)  \
+  H* h_ = (hh);     \
+  try {
+#define FC_CATCH                                                  \
+  }                                                               \
+  catch (const FcError& e) {                                      \
+    if (h_) h_->err = e.what(); else g_last_error = e.what();     \
+    return e.code;                                                \
+  }                                                               \
+  catch (const std::exception& e) {                               \
+    if (h_) h_->err = e.what(); else g_last_error = e.what();     \
+    return FEASTCUDA_ERR_STATE;                                   \
+  }                                                               \
+  return FEASTCUDA_OK;
+
+static void bind_device(H* h) { FC_CUDA(cudaSetDevice(h->device)); }
+
+extern "C" {
+
+int feastcuda_version(void) { return 100; }
+
+int feastcuda_create(feastcuda_handle* out, int device) {
+  FC_TRY(nullptr)
+  FC_REQUIRE(out != nullptr, "null handle pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw FcError(FEASTCUDA_ERR_CUDA, std::string("no CUDA device available (libfeastcuda has no CPU fallback): ") + cudaGetErrorString(e));
+  FC_REQUIRE(device >= 0 && device < count, "device index out of range");
+  H* h = new H();
+  memset(&h->stats, 0, sizeof(h->stats));
+  h->device = device;
+  FC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FC_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sms = prop.multiProcessorCount;
+  FC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  *out = h;
+  FC_CATCH
+}
+
+int feastcuda_destroy(feastcuda_handle h) {
+  if (!h) return FEASTCUDA_OK;
+  cudaSetDevice(h->device);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
+  DBuf* bufs[] = {&h->partial, &h->partial_r, &h->kstate, &h->small, &h->small2, &h->gram_partial, &h->stage, &h->red_ws,
+                  &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB};
+  for (DBuf* b : bufs) b->release();
+  for (auto& b : h->lu_cache) b.release();
+  for (auto& b : h->piv_cache) b.release();
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return FEASTCUDA_OK;
+}
+
+const char* feastcuda_last_error(feastcuda_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int feastcuda_feastinit(int64_t* fpm) {
+  if (!fpm) return FEASTCUDA_ERR_ARG;
+  for (int i = 0; i < 64; ++i) fpm[i] = FEAST_UNINIT;
+  return FEASTCUDA_OK;
+}
+int feastcuda_feastdefault(int64_t* fpm) {
+  if (!fpm) return FEASTCUDA_ERR_ARG;
+  return host_feastdefault(fpm) ? FEASTCUDA_ERR_ARG : FEASTCUDA_OK;
+}
+int feastcuda_contour(double Emin, double Emax, int64_t* fpm, double* Zne, double* Wne) {
+  if (!fpm || !Zne || !Wne) return FEASTCUDA_ERR_ARG;
+  const int rc = host_contour(Emin, Emax, fpm, reinterpret_cast<zc*>(Zne), reinterpret_cast<zc*>(Wne));
+  return rc == 0 ? FEASTCUDA_OK : (rc == 2 ? FEASTCUDA_ERR_UNSUPPORTED : FEASTCUDA_ERR_ARG);
+}
+int feastcuda_gcontour(double Emid_re, double Emid_im, double r, int64_t* fpm, double* Zne, double* Wne) {
+  if (!fpm || !Zne || !Wne) return FEASTCUDA_ERR_ARG;
+  return host_gcontour(zc(Emid_re, Emid_im), r, fpm, reinterpret_cast<zc*>(Zne), reinterpret_cast<zc*>(Wne)) ? FEASTCUDA_ERR_ARG : FEASTCUDA_OK;
+}
+int feastcuda_node_partition(int64_t ne, int nranks, int rank, int64_t* start, int64_t* count) {
+  if (!start || !count || nranks < 1 || rank < 0 || rank >= nranks || ne < 0) return FEASTCUDA_ERR_ARG;
+  host_node_partition(ne, nranks, rank, start, count);
+  return FEASTCUDA_OK;
+}
+
+static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t* ptr, const int64_t* idx, const double* val,
+                          bool cplx, int base, int fmt, int structure) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  FC_REQUIRE(which == FEASTCUDA_A || which == FEASTCUDA_B, "which must be A or B");
+  FC_REQUIRE(base == 0 || base == 1, "index_base must be 0 or 1");
+  bind_device(h);
+  if (which == FEASTCUDA_A) {
+    ingest_csr(h->hA, n, nnz, ptr, idx, val, cplx, base, fmt, structure);
+    h->dA.uploaded = false;
+    if (h->kind != OP_SPARSE) { h->has_b = false; h->hB.set = false; }
+    h->kind = OP_SPARSE;
+    h->n = n;
+    h->lu_cache.clear();
+  } else {
+    FC_REQUIRE(h->kind == OP_SPARSE && h->hA.set && h->hA.n == n, "set A (same size, sparse) before B");
+    ingest_csr(h->hB, n, nnz, ptr, idx, val, cplx, base, fmt, structure);
+    h->dB.uploaded = false;
+    h->has_b = true;
+  }
+  FC_CATCH
+}
+int feastcuda_set_csr_d(feastcuda_handle h, int which, int64_t n, int64_t nnz, const int64_t* ptr, const int64_t* idx,
+                        const double* val, int index_base, int fmt, int structure) {
+  return set_csr_common(h, which, n, nnz, ptr, idx, val, false, index_base, fmt, structure);
+}
+int feastcuda_set_csr_z(feastcuda_handle h, int which, int64_t n, int64_t nnz, const int64_t* ptr, const int64_t* idx,
+                        const double* val, int index_base, int fmt, int structure) {
+  return set_csr_common(h, which, n, nnz, ptr, idx, val, true, index_base, fmt, structure);
+}
+int feastcuda_clear_b(feastcuda_handle h) {
+  if (!h) return FEASTCUDA_ERR_ARG;
+  h->has_b = false;
+  h->hB.set = false;
+  h->denseB.set = false;
+  h->bandB.set = false;
+  h->dB.uploaded = false;
+  h->dense_uploaded = false;
+  h->band_uploaded = false;
+  h->lu_cache.clear();
+  return FEASTCUDA_OK;
+}
+
+int feastcuda_set_dense_d(feastcuda_handle h, int which, int64_t n, const double* a, int64_t lda, int structure) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  dense_set(h, which, n, a, lda, false, structure);
+  FC_CATCH
+}
+int feastcuda_set_dense_z(feastcuda_handle h, int which, int64_t n, const double* a, int64_t lda, int structure) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  dense_set(h, which, n, a, lda, true, structure);
+  FC_CATCH
+}
+int feastcuda_set_band_d(feastcuda_handle h, int which, int64_t n, int64_t k, const double* ab, int64_t ldab, int structure) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  band_set(h, which, n, k, ab, ldab, false, structure);
+  FC_CATCH
+}
+int feastcuda_set_band_z(feastcuda_handle h, int which, int64_t n, int64_t k, const double* ab, int64_t ldab, int structure) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  band_set(h, which, n, k, ab, ldab, true, structure);
+  FC_CATCH
+}
+
+
+int feastcuda_upload_subspace(feastcuda_handle h, int64_t m0, const double* Q0, int q0_real) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  FC_REQUIRE(h->kind != OP_NONE, "set the operator first");
+  bind_device(h);
+  prepare_operator(h);
+  FC_REQUIRE(m0 >= 1 && m0 <= h->n, "Number of eigenvalues M0 must be between 1 and N");
+  ensure_workspace(h, h->n, (int)m0);
+  if (Q0 == nullptr) {
+    // library seed: deterministic real Gaussian columns (xorshift + Box-Muller), unit 2-norm -- the stand-in for
+    // _feast_seeded_subspace_complex! (core/feast_tools.jl:22-43), whose Julia RNG stream cannot be reproduced
+    std::vector<double> q((size_t)h->n * m0);
+    uint64_t s = 0x9E3779B97F4A7C15ull ^ ((uint64_t)h->n * 1315423911ull + (uint64_t)m0);
+    auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)((s >> 11) + 1) / 9007199254740993.0; };
+    for (int64_t j = 0; j < m0; ++j) {
+      double nrm = 0.0;
+      for (int64_t i = 0; i < h->n; ++i) {
+        const double u1 = next(), u2 = next();
+        const double g = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+        q[(size_t)j * h->n + i] = g;
+        nrm += g * g;
+      }
+      nrm = nrm > 0 ? std::sqrt(nrm) : 1.0;
+      for (int64_t i = 0; i < h->n; ++i) q[(size_t)j * h->n + i] /= nrm;
+    }
+    upload_block<double>(h, h->n, (int)m0, q.data(), blk(h, BS_QB));
+    h->sub_real = true;
+  } else if (q0_real) {
+    upload_block<double>(h, h->n, (int)m0, Q0, blk(h, BS_QB));
+    h->sub_real = true;
+  } else {
+    upload_block<zd>(h, h->n, (int)m0, reinterpret_cast<const zd*>(Q0), blk(h, BS_QB));
+    h->sub_real = false;
+  }
+  h->have_subspace = true;
+  h->sub_m0 = m0;
+  FC_CATCH
+}
+
+int feastcuda_run_interval(feastcuda_handle h, double Emin, double Emax, int64_t m0, int64_t* fpm, const double* Zne,
+                           const double* Wne, int64_t ne, const feastcuda_solver_opts* opts, int64_t* M, int64_t* info,
+                           double* epsout, int64_t* loop) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr && fpm && M && info && epsout && loop, "null argument");
+  bind_device(h);
+  run_interval(h, Emin, Emax, (int)m0, fpm, reinterpret_cast<const zc*>(Zne), reinterpret_cast<const zc*>(Wne), (int)ne, opts, M, info,
+               epsout, loop, h->sub_real);
+  FC_CATCH
+}
+
+int feastcuda_fetch_results(feastcuda_handle h, int64_t m0, int x_real, double* lambda, double* X, double* res) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  FC_REQUIRE(h->res_m0 == m0, "no results for this M0");
+  bind_device(h);
+  const int M = (int)h->res_M;
+  const int nl = h->res_general ? 2 : 1;
+  if (lambda) for (int j = 0; j < M * nl; ++j) lambda[j] = h->res_lambda[j];
+  if (res) for (int j = 0; j < M; ++j) res[j] = h->res_res[j];
+  if (X && M > 0) {
+    if (x_real) download_block<double>(h, h->n, M, blk(h, BS_XR), X);
+    else download_block<zd>(h, h->n, M, blk(h, BS_XR), reinterpret_cast<zd*>(X));
+  }
+  FC_CATCH
+}
+
+int feastcuda_solve_interval(feastcuda_handle h, double Emin, double Emax, int64_t m0, int64_t* fpm, const double* Zne,
+                             const double* Wne, int64_t ne, const double* Q0, const feastcuda_solver_opts* opts, double* lambda,
+                             double* X, double* res, int64_t* M, int64_t* info, double* epsout, int64_t* loop) {
+  int rc = feastcuda_upload_subspace(h, m0, Q0, opts ? opts->q0_real : 0);
+  if (rc) return rc;
+  rc = feastcuda_run_interval(h, Emin, Emax, m0, fpm, Zne, Wne, ne, opts, M, info, epsout, loop);
+  if (rc) return rc;
+  return feastcuda_fetch_results(h, m0, opts ? opts->x_real : 0, lambda, X, res);
+}
+
+int feastcuda_solve_contour(feastcuda_handle h, double Emid_re, double Emid_im, double r, int64_t m0, int64_t* fpm,
+                            const double* Zne, const double* Wne, int64_t ne, const double* Q0, const feastcuda_solver_opts* opts,
+                            double* lambda, double* X, double* res, int64_t* M, int64_t* info, double* epsout, int64_t* loop) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  (void)Emid_re; (void)Emid_im; (void)r; (void)m0; (void)fpm; (void)Zne; (void)Wne; (void)ne; (void)Q0; (void)opts;
+  (void)lambda; (void)X; (void)res; (void)M; (void)info; (void)epsout; (void)loop;
+  throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "general (G-RCI) solve: not built yet");
+  FC_CATCH
+}
+
+// ---- stage-level entry points ---------------------------------------------------------------------
+static void stage_begin(H* h, int64_t m) {
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  prepare_operator(h);
+  FC_REQUIRE(m >= 1 && m <= FC_MAXCOLS, "m must be in [1,128]");
+  ensure_workspace(h, h->n, std::max<int>((int)m, h->ws_n == h->n ? h->ws_ld : 0));
+}
+
+int feastcuda_spmm_shifted(feastcuda_handle h, double z_re, double z_im, int64_t m, const double* X, double* Y) {
+  FC_TRY(h)
+  stage_begin(h, m);
+  FC_REQUIRE(h->kind == OP_SPARSE, "sparse operator required");
+  upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(X), blk(h, BS_KP));
+  launch_spmm<SPMM_PLAIN>(h, op_shifted(zc(z_re, z_im)), (int)m, blk(h, BS_KP), blk(h, BS_KV), nullptr, nullptr);
+  download_block<zd>(h, h->n, (int)m, blk(h, BS_KV), reinterpret_cast<zd*>(Y));
+  FC_CATCH
+}
+
+int feastcuda_apply(feastcuda_handle h, int which, int64_t m, const double* X, double* Y) {
+  FC_TRY(h)
+  stage_begin(h, m);
+  upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(X), blk(h, BS_KP));
+  if (which == FEASTCUDA_B && !h->has_b) copy_cols(h, (int)m, blk(h, BS_KP), blk(h, BS_KV));
+  else apply_op(h, which, (int)m, blk(h, BS_KP), blk(h, BS_KV));
+  download_block<zd>(h, h->n, (int)m, blk(h, BS_KV), reinterpret_cast<zd*>(Y));
+  FC_CATCH
+}
+
+int feastcuda_block_solve(feastcuda_handle h, double z_re, double z_im, int64_t m, const double* RHS, const double* X0,
+                          const feastcuda_solver_opts* opts, double* Xout, int64_t* iters, double* resid) {
+  FC_TRY(h)
+  stage_begin(h, m);
+  feastcuda_solver_opts o = opts ? *opts : default_opts();
+  upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(RHS), blk(h, BS_RHS));
+  if (X0) upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(X0), blk(h, BS_KX));
+  SolveOut so;
+  const double tol = o.tol == 0.0 ? 1e-12 : o.tol;
+  if (h->kind != OP_SPARSE) { h->lu_cache.clear(); h->lu_shift.clear(); }
+  node_solve(h, 0, zc(z_re, z_im), (int)m, blk(h, BS_RHS), blk(h, BS_KX), X0 != nullptr, o, tol, so);
+  if (h->kind != OP_SPARSE) {
+    // direct solves report the true residual through the generic kernels
+    so.iters.assign(m, 0);
+    so.truenorm.assign(m, 0.0);
+    h->lu_cache.clear();
+    h->lu_shift.clear();
+  }
+  download_block<zd>(h, h->n, (int)m, blk(h, BS_KX), reinterpret_cast<zd*>(Xout));
+  for (int c = 0; c < m; ++c) {
+    if (iters) iters[c] = so.iters.empty() ? 0 : so.iters[c];
+    if (resid) resid[c] = so.truenorm.empty() ? 0.0 : so.truenorm[c];
+  }
+  FC_CATCH
+}
+
+int feastcuda_accumulate(feastcuda_handle h, double w_re, double w_im, int64_t m, const double* Y, double* Qacc) {
+  FC_TRY(h)
+  stage_begin(h, m);
+  upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(Y), blk(h, BS_KP));
+  upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(Qacc), blk(h, BS_ACC));
+  axpby_cols(h, (int)m, zc(w_re, w_im), 1.0, blk(h, BS_KP), blk(h, BS_ACC));
+  download_block<zd>(h, h->n, (int)m, blk(h, BS_ACC), reinterpret_cast<zd*>(Qacc));
+  FC_CATCH
+}
+
+// stage calls that do not involve the operator still need (n, m) workspaces
+static void stage_begin_free(H* h, int64_t n, int64_t m) {
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  FC_REQUIRE(n >= 1 && m >= 1 && m <= FC_MAXCOLS, "bad block shape");
+  ensure_workspace(h, n, std::max<int>((int)m, h->ws_n == n ? h->ws_ld : 0));
+}
+
+int feastcuda_orthonormalize(feastcuda_handle h, int64_t n, int64_t m, const double* W, double rank_tol, double* Q, int64_t* rank) {
+  FC_TRY(h)
+  stage_begin_free(h, n, m);
+  FC_REQUIRE(rank != nullptr, "null rank");
+  upload_block<zd>(h, n, (int)m, reinterpret_cast<const zd*>(W), blk(h, BS_ACC));
+  int slot = BS_ACC;
+  const int rk = orthonormalize(h, (int)m, BS_ACC, BS_KP, rank_tol > 0 ? rank_tol : std::sqrt(2.220446049250313e-16), &slot);
+  *rank = rk;
+  if (rk > 0) download_block<zd>(h, n, rk, blk(h, slot), reinterpret_cast<zd*>(Q));
+  FC_CATCH
+}
+
+int feastcuda_gram(feastcuda_handle h, int64_t n, int64_t m, const double* X, const double* Y, double* C) {
+  FC_TRY(h)
+  stage_begin_free(h, n, m);
+  upload_block<zd>(h, n, (int)m, reinterpret_cast<const zd*>(X), blk(h, BS_KP));
+  upload_block<zd>(h, n, (int)m, reinterpret_cast<const zd*>(Y), blk(h, BS_KV));
+  std::vector<zc> G;
+  gram_host(h, (int)m, (int)m, blk(h, BS_KP), blk(h, BS_KV), G);
+  zc* out = reinterpret_cast<zc*>(C);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) out[(size_t)j * m + i] = G[(size_t)i * m + j];
+  FC_CATCH
+}
+
+int feastcuda_reduced_eig(feastcuda_handle h, int64_t r, const double* Sq, const double* Aq, double* lambda, double* V, int64_t* sweeps) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  FC_REQUIRE(r >= 1 && r <= FC_MAXCOLS && Sq && lambda && V, "bad arguments");
+  h->small.ensure((size_t)8 * FC_MAXCOLS * FC_MAXCOLS * sizeof(zd));
+  h->small2.ensure((size_t)4 * FC_MAXCOLS * sizeof(zd) + 64);
+  const zc* s = reinterpret_cast<const zc*>(Sq);
+  const zc* a = reinterpret_cast<const zc*>(Aq);
+  std::vector<zc> S((size_t)r * r), A;
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < r; ++j) S[(size_t)i * r + j] = s[(size_t)j * r + i];
+  if (a) {
+    A.resize((size_t)r * r);
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < r; ++j) A[(size_t)i * r + j] = a[(size_t)j * r + i];
+  }
+  std::vector<double> lam;
+  std::vector<zc> Vr;
+  int st = 0;
+  const int64_t sw0 = h->stats.jacobi_sweeps;
+  reduced_eig(h, (int)r, S, a ? &A : nullptr, lam, Vr, &st);
+  if (st == 1) throw FcError(FEASTCUDA_ERR_ARG, "reduced_eig: Aq is not positive definite");
+  for (int i = 0; i < r; ++i) lambda[i] = lam[i];
+  zc* vo = reinterpret_cast<zc*>(V);
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < r; ++j) vo[(size_t)j * r + i] = Vr[(size_t)i * r + j];
+  if (sweeps) *sweeps = h->stats.jacobi_sweeps - sw0;
+  FC_CATCH
+}
+
+int feastcuda_residuals(feastcuda_handle h, int64_t m, const double* X, const double* lambda, double* res) {
+  FC_TRY(h)
+  stage_begin(h, m);
+  upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(X), blk(h, BS_KP));
+  std::vector<zc> lam(m);
+  for (int j = 0; j < m; ++j) lam[j] = zc(lambda[2 * j], lambda[2 * j + 1]);
+  std::vector<double> rn;
+  eig_residual_norms(h, (int)m, blk(h, BS_KP), lam, rn);
+  for (int j = 0; j < m; ++j) res[j] = rn[j] / std::max(std::abs(lam[j]), 1.0);
+  FC_CATCH
+}
+
+int feastcuda_nccl_unique_id(char* id128) {
+  FC_TRY(nullptr)
+  FC_REQUIRE(id128 != nullptr, "null id");
+  nccl_load();
+  FC_NCCL(g_nccl.GetUniqueId(id128));
+  FC_CATCH
+}
+
+int feastcuda_nccl_init(feastcuda_handle h, int nranks, int rank, const char* id128) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr && id128 != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "bad arguments");
+  bind_device(h);
+  nccl_load();
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  FC_NCCL(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
+  h->nranks = nranks;
+  h->rank = rank;
+  FC_CATCH
+}
+
+int feastcuda_get_stats(feastcuda_handle h, feastcuda_stats* out) {
+  if (!h || !out) return FEASTCUDA_ERR_ARG;
+  if (h->kind == OP_SPARSE && h->hA.set) {
+    const double vs = h->dev_complex ? 16.0 : 8.0;
+    const int m = h->ws_ld;
+    double b = (double)h->hA.nnz * (vs + 4.0) + 4.0 * (h->hA.n + 1) + 2.0 * (double)h->hA.n * m * 16.0;
+    if (h->has_b) b += (double)h->hB.nnz * (vs + 4.0) + 4.0 * (h->hB.n + 1);
+    h->stats.bytes_spmm_alg = b;
+  }
+  *out = h->stats;
+  return FEASTCUDA_OK;
+}
+int feastcuda_reset_stats(feastcuda_handle h) {
+  if (!h) return FEASTCUDA_ERR_ARG;
+  memset(&h->stats, 0, sizeof(h->stats));
+  return FEASTCUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+"""feastcuda -- host-side mirror of FeastKit.jl's API for the FEAST contour-integration path.
+
+Julia is absent from the build image, so the host code a FeastKit.jl maintainer would write in Julia
+(feastkit.jl_b200/julia/FeastCUDA.jl) is mirrored here in Python with the SAME names, argument order,
+argument meaning and error behaviour (Julia's ``ArgumentError`` -> ``ValueError``; mutating ``name!`` ->
+``name``).  Every function that computes goes through the C ABI of libfeastcuda (include/feastcuda.h);
+nothing here falls back to the CPU, and nothing imports ``oracle/``.
+
+file:line citations are relative to /root/reference/src.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (A, B, CSC, CSR, FILTER_REFERENCE, FILTER_TRUE, GEN, HERM, SHARD_BALANCED, SHARD_COLUMNS, SHARD_NODES,
+                   SOLVER_BICGSTAB, SOLVER_DIRECT, SYM, FeastCudaError, SolverOpts, Stats)
+
+FEAST_UNINITIALIZED = -111
+
+
+@dataclass
+class FeastResult:
+    """FeastResult{T,VT} / FeastGeneralResult{T} (core/feast_types.jl:85-108); arrays trimmed to M."""
+    lambda_: np.ndarray
+    q: np.ndarray
+    M: int
+    res: np.ndarray
+    info: int
+    epsout: float
+    loop: int
+    stats: dict = field(default_factory=dict)
+
+
+# ---- parameters / contours (core/feast_parameters.jl, core/feast_tools.jl) ---------------------------
+def feastinit():
+    """feastinit() -> 64 x -111 (core/feast_parameters.jl:20-24)."""
+    fpm = np.zeros(64, dtype=np.int64)
+    L.check(L.load().feastcuda_feastinit(L.iptr(fpm)))
+    return [int(v) for v in fpm]
+
+
+def feastinit_(fpm):
+    """feastinit!(fpm) (core/feast_parameters.jl:7-18)."""
+    if len(fpm) < 64:
+        raise ValueError("fpm array must have at least 64 elements")
+    for i in range(64):
+        fpm[i] = FEAST_UNINITIALIZED
+    return fpm
+
+
+def feastdefault_(fpm):
+    """feastdefault!(fpm) (core/feast_parameters.jl:41-386); invalid entries raise ValueError."""
+    a = L.fpm_array(fpm)
+    if L.load().feastcuda_feastdefault(L.iptr(a)) != L.OK:
+        raise ValueError("Invalid fpm parameter (feastdefault!)")
+    for i in range(64):
+        fpm[i] = int(a[i])
+    return fpm
+
+
+def feast_tolerance(fpm, dtype=np.float64):
+    """core/feast_parameters.jl:391-405"""
+    e = fpm[2]
+    tol = 1e-12 if (e < 0 or e > 16) else 10.0 ** (-e)
+    if np.dtype(dtype) == np.float32:
+        return max(float(np.float32(tol)), float(np.sqrt(np.finfo(np.float32).eps)))
+    return tol
+
+
+def feast_contour(Emin, Emax, fpm):
+    """feast_contour(Emin, Emax, fpm) -> (Zne, Wne) (core/feast_tools.jl:212-284)."""
+    a = L.fpm_array(fpm)
+    if a[1] == FEAST_UNINITIALIZED or a[1] <= 0:
+        feastdefault_(fpm)
+        a = L.fpm_array(fpm)
+    ne = int(a[1])
+    Z = np.zeros(ne, dtype=np.complex128)
+    W = np.zeros(ne, dtype=np.complex128)
+    rc = L.load().feastcuda_contour(float(Emin), float(Emax), L.iptr(a), Z.ctypes.data_as(L._dp), W.ctypes.data_as(L._dp))
+    if rc == L.ERR_UNSUPPORTED:
+        raise NotImplementedError("Zolotarev quadrature (fpm[16]=2) is not built yet")
+    L.check(rc)
+    return Z, W
+
+
+def feast_gcontour(Emid, r, fpm):
+    """feast_gcontour(Emid, r, fpm) -> (Zne, Wne) (core/feast_tools.jl:286-371)."""
+    a = L.fpm_array(fpm)
+    if a[7] == FEAST_UNINITIALIZED or a[7] <= 0:
+        feastdefault_(fpm)
+        a = L.fpm_array(fpm)
+    ne = int(a[7])
+    Z = np.zeros(ne, dtype=np.complex128)
+    W = np.zeros(ne, dtype=np.complex128)
+    Emid = complex(Emid)
+    L.check(L.load().feastcuda_gcontour(Emid.real, Emid.imag, float(r), L.iptr(a), Z.ctypes.data_as(L._dp), W.ctypes.data_as(L._dp)))
+    return Z, W
+
+
+def check_feast_srci_input(N, M0, Emin, Emax, fpm):
+    """core/feast_aux.jl:369-399 -- thrown host-side before the ccall, as in the reference."""
+    if N <= 0:
+        raise ValueError("Matrix size N must be positive")
+    if M0 <= 0 or M0 > N:
+        raise ValueError("Number of eigenvalues M0 must be between 1 and N")
+    if Emin >= Emax:
+        raise ValueError("Search interval [Emin, Emax] must be valid")
+    if len(fpm) < 64:
+        raise ValueError("fpm array must have at least 64 elements")
+    if 0 < fpm[1] < 3:
+        raise ValueError("Number of integration points must be at least 3")
+    return True
+
+
+def node_partition(ne, nranks, rank):
+    """Block node distribution (parallel/feast_mpi.jl:36-43); returns (start, count), 0-based."""
+    s = np.zeros(1, dtype=np.int64)
+    c = np.zeros(1, dtype=np.int64)
+    L.check(L.load().feastcuda_node_partition(int(ne), int(nranks), int(rank), L.iptr(s), L.iptr(c)))
+    return int(s[0]), int(c[0])
+
+
+# ---- engine handle --------------------------------------------------------------------------------------
+def _as_z(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def _colmajor_z(X):
+    return np.asfortranarray(np.asarray(X, dtype=np.complex128))
+
+
+def _view_d(a):
+    return a.view(np.float64) if a.dtype == np.complex128 else a
+
+
+class Engine:
+    """One libfeastcuda handle bound to one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = L.load()
+        self.h = L._vp()
+        L.check(self.lib.feastcuda_create(C.byref(self.h), int(device)))
+        self.device = device
+        self.n = 0
+        self.distributed = False
+
+    def close(self):
+        if self.h:
+            self.lib.feastcuda_destroy(self.h)
+            self.h = L._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        L.check(rc, self.h)
+
+    # -- operators
+    def set_sparse(self, which, M, structure, fmt=None):
+        """SparseMatrixCSC analogue: scipy CSC (Julia's layout) or CSR."""
+        import scipy.sparse as sp
+        if fmt is None:
+            fmt = CSR if sp.isspmatrix_csr(M) else CSC
+        M = M.tocsr() if fmt == CSR else M.tocsc()
+        M.sort_indices()
+        n = M.shape[0]
+        if M.shape[0] != M.shape[1]:
+            raise ValueError("Matrix must be square")
+        ptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+        idx = np.ascontiguousarray(M.indices, dtype=np.int64)
+        if np.iscomplexobj(M.data):
+            val = _as_z(M.data)
+            self._ck(self.lib.feastcuda_set_csr_z(self.h, which, n, M.nnz, L.iptr(ptr), L.iptr(idx), val.ctypes.data_as(L._dp), 0, fmt, structure))
+        else:
+            val = np.ascontiguousarray(M.data, dtype=np.float64)
+            self._ck(self.lib.feastcuda_set_csr_d(self.h, which, n, M.nnz, L.iptr(ptr), L.iptr(idx), L.dptr(val), 0, fmt, structure))
+        if which == A:
+            self.n = n
+
+    def set_dense(self, which, M, structure):
+        M = np.asarray(M)
+        n = M.shape[0]
+        if M.ndim != 2 or M.shape[1] != n:
+            raise ValueError("Matrix must be square")
+        if np.iscomplexobj(M):
+            a = np.asfortranarray(M, dtype=np.complex128)
+            self._ck(self.lib.feastcuda_set_dense_z(self.h, which, n, a.ctypes.data_as(L._dp), n, structure))
+        else:
+            a = np.asfortranarray(M, dtype=np.float64)
+            self._ck(self.lib.feastcuda_set_dense_d(self.h, which, n, L.dptr(a), n, structure))
+        if which == A:
+            self.n = n
+
+    def set_band(self, which, AB, k, structure):
+        AB = np.asarray(AB)
+        n = AB.shape[1]
+        ldab = AB.shape[0]
+        if np.iscomplexobj(AB):
+            a = np.asfortranarray(AB, dtype=np.complex128)
+            self._ck(self.lib.feastcuda_set_band_z(self.h, which, n, int(k), a.ctypes.data_as(L._dp), ldab, structure))
+        else:
+            a = np.asfortranarray(AB, dtype=np.float64)
+            self._ck(self.lib.feastcuda_set_band_d(self.h, which, n, int(k), L.dptr(a), ldab, structure))
+        if which == A:
+            self.n = n
+
+    def clear_b(self):
+        self._ck(self.lib.feastcuda_clear_b(self.h))
+
+    # -- multi-GPU: one process per GPU, NCCL id distributed through torch.distributed
+    def init_distributed(self):
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() == 1 or self.distributed:
+            return
+        import torch
+        buf = C.create_string_buffer(128)
+        if dist.get_rank() == 0:
+            L.check(self.lib.feastcuda_nccl_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(self.device)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        self._ck(self.lib.feastcuda_nccl_init(self.h, dist.get_world_size(), dist.get_rank(), raw))
+        self.distributed = True
+
+    # -- solves
+    @staticmethod
+    def make_opts(solver="bicgstab", solver_tol=0.0, solver_maxiter=500, solver_restart=3, inner_rel=0.0, ritz_guess=False,
+                  filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False):
+        o = SolverOpts()
+        o.solver = SOLVER_DIRECT if solver == "direct" else SOLVER_BICGSTAB
+        o.tol = float(solver_tol)
+        o.maxiter = int(solver_maxiter)
+        o.restart = int(solver_restart)
+        o.inner_rel = float(inner_rel)
+        o.ritz_guess = int(bool(ritz_guess))
+        o.filter = FILTER_TRUE if filter == "true" else FILTER_REFERENCE
+        o.shard = {"nodes": SHARD_NODES, "columns": SHARD_COLUMNS, "balanced": SHARD_BALANCED}[shard]
+        o.check_every = int(check_every)
+        o.q0_real = int(bool(q0_real))
+        o.x_real = int(bool(x_real))
+        return o
+
+    def upload_subspace(self, M0, Q0=None):
+        if Q0 is None:
+            self._ck(self.lib.feastcuda_upload_subspace(self.h, int(M0), None, 0))
+            return
+        Q0 = np.asarray(Q0)
+        if Q0.shape != (self.n, M0):
+            raise ValueError("Q0 must be N x M0")
+        if np.iscomplexobj(Q0):
+            q = _colmajor_z(Q0)
+            self._ck(self.lib.feastcuda_upload_subspace(self.h, int(M0), q.ctypes.data_as(L._dp), 0))
+        else:
+            q = np.asfortranarray(Q0, dtype=np.float64)
+            self._ck(self.lib.feastcuda_upload_subspace(self.h, int(M0), L.dptr(q), 1))
+
+    def run_interval(self, Emin, Emax, M0, fpm, Zne, Wne, opts):
+        a = L.fpm_array(fpm)
+        Z = _as_z(Zne)
+        W = _as_z(Wne)
+        M = np.zeros(1, dtype=np.int64)
+        info = np.zeros(1, dtype=np.int64)
+        loop = np.zeros(1, dtype=np.int64)
+        eps = np.zeros(1, dtype=np.float64)
+        self._ck(self.lib.feastcuda_run_interval(self.h, float(Emin), float(Emax), int(M0), L.iptr(a), Z.ctypes.data_as(L._dp),
+                                                 W.ctypes.data_as(L._dp), len(Z), C.byref(opts), L.iptr(M), L.iptr(info), L.dptr(eps), L.iptr(loop)))
+        for i in range(64):
+            fpm[i] = int(a[i])
+        return int(M[0]), int(info[0]), float(eps[0]), int(loop[0])
+
+    def fetch_results(self, M0, M, x_real):
+        lam = np.zeros(M0, dtype=np.float64)
+        res = np.zeros(M0, dtype=np.float64)
+        X = np.zeros((self.n, max(M, 1)), dtype=np.float64 if x_real else np.complex128, order="F")
+        self._ck(self.lib.feastcuda_fetch_results(self.h, int(M0), int(x_real), L.dptr(lam), X.ctypes.data_as(L._dp), L.dptr(res)))
+        return lam[:M].copy(), X[:, :M].copy(), res[:M].copy()
+
+    def solve_interval(self, Emin, Emax, M0, fpm, Zne, Wne, Q0=None, x_real=False, **kw):
+        """One C-ABI call with HOST buffers in and out (the end-to-end path)."""
+        a = L.fpm_array(fpm)
+        Z = _as_z(Zne)
+        W = _as_z(Wne)
+        q0_real = Q0 is not None and not np.iscomplexobj(Q0)
+        opts = self.make_opts(q0_real=q0_real, x_real=x_real, **kw)
+        q = None
+        if Q0 is not None:
+            Q0 = np.asarray(Q0)
+            if Q0.shape != (self.n, M0):
+                raise ValueError("Q0 must be N x M0")
+            q = np.asfortranarray(Q0, dtype=np.float64) if q0_real else _colmajor_z(Q0)
+        lam = np.zeros(M0, dtype=np.float64)
+        res = np.zeros(M0, dtype=np.float64)
+        X = np.zeros((self.n, M0), dtype=np.float64 if x_real else np.complex128, order="F")
+        M = np.zeros(1, dtype=np.int64)
+        info = np.zeros(1, dtype=np.int64)
+        loop = np.zeros(1, dtype=np.int64)
+        eps = np.zeros(1, dtype=np.float64)
+        self._ck(self.lib.feastcuda_solve_interval(self.h, float(Emin), float(Emax), int(M0), L.iptr(a), Z.ctypes.data_as(L._dp),
+                                                   W.ctypes.data_as(L._dp), len(Z), None if q is None else q.ctypes.data_as(L._dp),
+                                                   C.byref(opts), L.dptr(lam), X.ctypes.data_as(L._dp), L.dptr(res), L.iptr(M),
+                                                   L.iptr(info), L.dptr(eps), L.iptr(loop)))
+        for i in range(64):
+            fpm[i] = int(a[i])
+        m = int(M[0])
+        return FeastResult(lam[:m].copy(), X[:, :m].copy(), m, res[:m].copy(), int(info[0]), float(eps[0]), int(loop[0]), self.stats())
+
+    # -- stage-level entry points (host buffers)
+    def spmm_shifted(self, z, X):
+        X = _colmajor_z(X)
+        Y = np.zeros_like(X, order="F")
+        z = complex(z)
+        self._ck(self.lib.feastcuda_spmm_shifted(self.h, z.real, z.imag, X.shape[1], X.ctypes.data_as(L._dp), Y.ctypes.data_as(L._dp)))
+        return Y
+
+    def apply(self, which, X):
+        X = _colmajor_z(X)
+        Y = np.zeros_like(X, order="F")
+        self._ck(self.lib.feastcuda_apply(self.h, which, X.shape[1], X.ctypes.data_as(L._dp), Y.ctypes.data_as(L._dp)))
+        return Y
+
+    def block_solve(self, z, RHS, X0=None, **kw):
+        RHS = _colmajor_z(RHS)
+        m = RHS.shape[1]
+        X = np.zeros_like(RHS, order="F")
+        x0 = None if X0 is None else _colmajor_z(X0)
+        iters = np.zeros(m, dtype=np.int64)
+        resid = np.zeros(m, dtype=np.float64)
+        opts = self.make_opts(**kw)
+        z = complex(z)
+        self._ck(self.lib.feastcuda_block_solve(self.h, z.real, z.imag, m, RHS.ctypes.data_as(L._dp),
+                                                None if x0 is None else x0.ctypes.data_as(L._dp), C.byref(opts),
+                                                X.ctypes.data_as(L._dp), L.iptr(iters), L.dptr(resid)))
+        return X, iters, resid
+
+    def accumulate(self, w, Y, Qacc):
+        Y = _colmajor_z(Y)
+        Q = _colmajor_z(Qacc).copy(order="F")
+        w = complex(w)
+        self._ck(self.lib.feastcuda_accumulate(self.h, w.real, w.imag, Y.shape[1], Y.ctypes.data_as(L._dp), Q.ctypes.data_as(L._dp)))
+        return Q
+
+    def orthonormalize(self, W, rank_tol=0.0):
+        W = _colmajor_z(W)
+        n, m = W.shape
+        Q = np.zeros_like(W, order="F")
+        rank = np.zeros(1, dtype=np.int64)
+        self._ck(self.lib.feastcuda_orthonormalize(self.h, n, m, W.ctypes.data_as(L._dp), float(rank_tol), Q.ctypes.data_as(L._dp), L.iptr(rank)))
+        r = int(rank[0])
+        return Q[:, :r].copy(), r
+
+    def gram(self, X, Y):
+        X = _colmajor_z(X)
+        Y = _colmajor_z(Y)
+        n, m = X.shape
+        Cm = np.zeros((m, m), dtype=np.complex128, order="F")
+        self._ck(self.lib.feastcuda_gram(self.h, n, m, X.ctypes.data_as(L._dp), Y.ctypes.data_as(L._dp), Cm.ctypes.data_as(L._dp)))
+        return Cm
+
+    def reduced_eig(self, Sq, Aq=None):
+        Sq = _colmajor_z(Sq)
+        r = Sq.shape[0]
+        Aq_ = None if Aq is None else _colmajor_z(Aq)
+        lam = np.zeros(r, dtype=np.float64)
+        V = np.zeros((r, r), dtype=np.complex128, order="F")
+        sw = np.zeros(1, dtype=np.int64)
+        self._ck(self.lib.feastcuda_reduced_eig(self.h, r, Sq.ctypes.data_as(L._dp), None if Aq_ is None else Aq_.ctypes.data_as(L._dp),
+                                                L.dptr(lam), V.ctypes.data_as(L._dp), L.iptr(sw)))
+        return lam, V, int(sw[0])
+
+    def residuals(self, X, lam):
+        X = _colmajor_z(X)
+        lam = _as_z(lam)
+        res = np.zeros(X.shape[1], dtype=np.float64)
+        self._ck(self.lib.feastcuda_residuals(self.h, X.shape[1], X.ctypes.data_as(L._dp), lam.ctypes.data_as(L._dp), L.dptr(res)))
+        return res
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.feastcuda_get_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._ck(self.lib.feastcuda_reset_stats(self.h))
+
+
+_ENGINES = {}
+
+
+def default_engine(device=None):
+    """Process-wide handle for `device` (default: LOCAL_RANK under torchrun, else 0)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+from .api import *  # noqa: E402,F401,F403  (reference-named drivers)

@@ -1,0 +1,311 @@
+"""Reference-named drivers (the bodies a FeastKit.jl maintainer would replace with ``ccall``s).
+
+Names, positional arguments and keyword arguments follow the reference; ``name!`` is spelled ``name``.
+Engine extras are keyword-only and documented in DESIGN.md: ``Q0`` (initial subspace; Julia's seeded RNG
+stream is not reproducible outside Julia), ``inner_rel`` / ``ritz_guess`` (inexact inner solves),
+``filter`` ("reference" = the reference's complex half-contour sum, "true" = its real part), ``shard``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = [
+    "feast_scsrev", "feast_scsrgv", "feast_hcsrev", "feast_hcsrgv", "feast_scsrevx", "feast_scsrgvx", "feast_hcsrevx",
+    "feast_hcsrgvx", "feast_syev", "feast_sygv", "feast_heev", "feast_hegv", "feast_syevx", "feast_sygvx", "feast_heevx",
+    "feast_hegvx", "feast_sbev", "feast_sbgv", "feast_hbev", "feast_hbgv", "feast", "feast_banded", "issymmetric",
+    "ishermitian",
+]
+
+
+def _eng(engine):
+    from . import default_engine
+    return engine if engine is not None else default_engine()
+
+
+def issymmetric(M):
+    import scipy.sparse as sp
+    if sp.issparse(M):
+        return (abs(M - M.T)).nnz == 0 if M.shape[0] == M.shape[1] else False
+    M = np.asarray(M)
+    return M.shape[0] == M.shape[1] and np.array_equal(M, M.T)
+
+
+def ishermitian(M):
+    import scipy.sparse as sp
+    if sp.issparse(M):
+        return (abs(M - M.conj().T)).nnz == 0 if M.shape[0] == M.shape[1] else False
+    M = np.asarray(M)
+    return M.shape[0] == M.shape[1] and np.array_equal(M, M.conj().T)
+
+
+def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras):
+    """Map the reference keywords (sparse/feast_sparse.jl:246-266) onto feastcuda_solver_opts."""
+    solver_choice = "gmres" if solver == "iterative" else solver
+    if solver_choice not in ("direct", "gmres", "bicgstab"):
+        raise ValueError(f"Unsupported solver option '{solver}'. Use :direct, :gmres, or :iterative.")
+    kw = dict(solver_tol=solver_tol, solver_maxiter=solver_maxiter)
+    # sparse inputs are always served by the lock-step block BiCGStab (there is no sparse LU in the engine);
+    # solver_restart keeps its meaning of "restart budget" (true-residual restarts of the short recurrence)
+    kw["solver"] = "direct" if (kind != "sparse" and solver_choice == "direct") else "bicgstab"
+    kw["solver_restart"] = 3 if solver_restart == 30 else int(solver_restart)
+    if kind == "sparse":
+        # engine defaults for Krylov node solves (DESIGN.md "Inner solves"): start from the previous loop's Ritz pairs
+        # and stop three digits below that guess's residual; inner_rel=0, ritz_guess=False gives the reference's
+        # zero-guess / solve-to-tol / fail-with-info-5 behaviour (sparse/feast_sparse.jl:164-236,359-363)
+        kw["ritz_guess"] = True
+        kw["inner_rel"] = 1e-3
+    kw["filter"] = "true"
+    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every"):
+        if k in extras:
+            kw[k] = extras.pop(k)
+    if extras:
+        raise TypeError(f"unexpected keyword arguments: {sorted(extras)}")
+    return kw
+
+
+def _hermitian_solve(kind, setA, setB, N, Emin, Emax, M0, fpm, real_result, contour=None, solver="direct",
+                     solver_tol=0.0, solver_maxiter=500, solver_restart=30, Q0=None, engine=None, **extras):
+    from . import check_feast_srci_input, feast_contour, feastdefault_
+    eng = _eng(engine)
+    feastdefault_(fpm)
+    check_feast_srci_input(N, M0, float(Emin), float(Emax), fpm)
+    kw = _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
+    setA(eng)
+    if setB is not None:
+        setB(eng)
+    else:
+        eng.clear_b()
+    eng.init_distributed()
+    Zne, Wne = contour if contour is not None else feast_contour(float(Emin), float(Emax), fpm)
+    return eng.solve_interval(float(Emin), float(Emax), int(M0), fpm, Zne, Wne, Q0=Q0, x_real=real_result, **kw)
+
+
+# ---- sparse (sparse/feast_sparse.jl) ---------------------------------------------------------------------
+def _sparse_pair(A, B, structure):
+    import scipy.sparse as sp
+    if not sp.issparse(A):
+        raise TypeError("A must be a sparse matrix (SparseMatrixCSC)")
+    N = A.shape[0]
+    if A.shape[1] != N:
+        raise ValueError("A must be square")
+    if B is not None and B.shape != (N, N):
+        raise ValueError("B must be same size as A")
+    setA = lambda e: e.set_sparse(L.A, A, structure)
+    setB = None if B is None else (lambda e: e.set_sparse(L.B, B, structure))
+    return N, setA, setB
+
+
+def feast_scsrev(A, Emin, Emax, M0, fpm, **kw):
+    """feast_scsrev!(A, Emin, Emax, M0, fpm) -- sparse/feast_sparse.jl:1516-1529 (real symmetric, B = I)."""
+    N, sA, _ = _sparse_pair(A.astype(np.float64), None, L.SYM)
+    return _hermitian_solve("sparse", sA, None, N, Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_scsrgv(A, B, Emin, Emax, M0, fpm, **kw):
+    """feast_scsrgv!(A, B, Emin, Emax, M0, fpm; solver, ...) -- sparse/feast_sparse.jl:713-731."""
+    N, sA, sB = _sparse_pair(A.astype(np.float64), B.astype(np.float64), L.SYM)
+    return _hermitian_solve("sparse", sA, sB, N, Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_hcsrev(A, Emin, Emax, M0, fpm, **kw):
+    """feast_hcsrev! -- sparse/feast_sparse.jl:759-788 (complex Hermitian, B = I)."""
+    if not ishermitian(A):
+        raise ValueError("Matrix A must be Hermitian")
+    N, sA, _ = _sparse_pair(A.astype(np.complex128), None, L.HERM)
+    return _hermitian_solve("sparse", sA, None, N, Emin, Emax, M0, fpm, False, **kw)
+
+
+def feast_hcsrgv(A, B, Emin, Emax, M0, fpm, **kw):
+    """feast_hcsrgv! -- sparse/feast_sparse.jl:815-831."""
+    if not ishermitian(A):
+        raise ValueError("Matrix A must be Hermitian")
+    if not ishermitian(B):
+        raise ValueError("Matrix B must be Hermitian")
+    N, sA, sB = _sparse_pair(A.astype(np.complex128), B.astype(np.complex128), L.HERM)
+    return _hermitian_solve("sparse", sA, sB, N, Emin, Emax, M0, fpm, False, **kw)
+
+
+def feast_scsrevx(A, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    """Custom-contour form, sparse/feast_sparse.jl:751-757."""
+    return feast_scsrev(A, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+def feast_scsrgvx(A, B, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_scsrgv(A, B, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+def feast_hcsrevx(A, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_hcsrev(A, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+def feast_hcsrgvx(A, B, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_hcsrgv(A, B, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+# ---- dense (dense/feast_dense.jl) ------------------------------------------------------------------------
+def _dense_pair(A, B, structure, dtype):
+    A = np.asarray(A, dtype=dtype)
+    N = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != N:
+        raise ValueError("Matrix A must be square")
+    if B is not None:
+        B = np.asarray(B, dtype=dtype)
+        if B.shape != (N, N):
+            raise ValueError("Matrix B must match size of A")
+    if not ishermitian(A):
+        raise ValueError("Matrix A must be Hermitian")
+    if B is not None and not ishermitian(B):
+        raise ValueError("Matrix B must be Hermitian positive definite")
+    setA = lambda e: e.set_dense(L.A, A, structure)
+    setB = None if B is None else (lambda e: e.set_dense(L.B, B, structure))
+    return N, setA, setB
+
+
+def feast_syev(A, Emin, Emax, M0, fpm, **kw):
+    """feast_syev! -- dense/feast_dense.jl:776-797."""
+    N, sA, _ = _dense_pair(A, None, L.SYM, np.float64)
+    return _hermitian_solve("dense", sA, None, N, Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_sygv(A, B, Emin, Emax, M0, fpm, **kw):
+    """feast_sygv! -- dense/feast_dense.jl:356-370."""
+    N, sA, sB = _dense_pair(A, B, L.SYM, np.float64)
+    return _hermitian_solve("dense", sA, sB, N, Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_heev(A, Emin, Emax, M0, fpm, **kw):
+    """feast_heev! -- dense/feast_dense.jl:390-400."""
+    N, sA, _ = _dense_pair(A, None, L.HERM, np.complex128)
+    return _hermitian_solve("dense", sA, None, N, Emin, Emax, M0, fpm, False, **kw)
+
+
+def feast_hegv(A, B, Emin, Emax, M0, fpm, **kw):
+    """feast_hegv! -- dense/feast_dense.jl:799-810."""
+    N, sA, sB = _dense_pair(A, B, L.HERM, np.complex128)
+    return _hermitian_solve("dense", sA, sB, N, Emin, Emax, M0, fpm, False, **kw)
+
+
+def feast_syevx(A, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_syev(A, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+def feast_sygvx(A, B, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_sygv(A, B, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+def feast_heevx(A, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_heev(A, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+def feast_hegvx(A, B, Emin, Emax, M0, fpm, Zne, Wne, **kw):
+    return feast_hegv(A, B, Emin, Emax, M0, fpm, contour=(Zne, Wne), **kw)
+
+
+# ---- banded (banded/feast_banded.jl) ---------------------------------------------------------------------
+def _band_pair(A, ka, B, kb, structure, dtype):
+    A = np.asarray(A, dtype=dtype)
+    N = A.shape[1]
+    if A.shape[0] < ka + 1:
+        raise ValueError("A matrix storage insufficient for kla")
+    if B is not None:
+        B = np.asarray(B, dtype=dtype)
+        if B.shape[0] < kb + 1:
+            raise ValueError("B matrix storage insufficient for klb")
+        if B.shape[1] != N:
+            raise ValueError("B must be same size as A")
+    setA = lambda e: e.set_band(L.A, A, ka, structure)
+    setB = None if B is None else (lambda e: e.set_band(L.B, B, kb, structure))
+    return N, setA, setB
+
+
+def feast_sbev(A, kla, Emin, Emax, M0, fpm, **kw):
+    """feast_sbev! -- banded/feast_banded.jl:1410-1420 (real symmetric band, upper storage)."""
+    N, sA, _ = _band_pair(A, kla, None, 0, L.SYM, np.float64)
+    return _hermitian_solve("band", sA, None, N, Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_sbgv(A, B, kla, klb, Emin, Emax, M0, fpm, **kw):
+    """feast_sbgv! -- banded/feast_banded.jl:9-186."""
+    N, sA, sB = _band_pair(A, kla, B, klb, L.SYM, np.float64)
+    return _hermitian_solve("band", sA, sB, N, Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_hbev(A, kla, Emin, Emax, M0, fpm, **kw):
+    """feast_hbev! -- banded/feast_banded.jl:326-383."""
+    N, sA, _ = _band_pair(A, kla, None, 0, L.HERM, np.complex128)
+    return _hermitian_solve("band", sA, None, N, Emin, Emax, M0, fpm, False, **kw)
+
+
+def feast_hbgv(A, B, kla, klb, Emin, Emax, M0, fpm, **kw):
+    """feast_hbgv! -- banded/feast_banded.jl:385-421."""
+    N, sA, sB = _band_pair(A, kla, B, klb, L.HERM, np.complex128)
+    return _hermitian_solve("band", sA, sB, N, Emin, Emax, M0, fpm, False, **kw)
+
+
+# ---- high level (interfaces/feast_interfaces.jl:143-272, 381-420) ----------------------------------------
+def feast(A, *args, M0=10, fpm=None, **kw):
+    """feast(A, (Emin,Emax); M0, fpm) / feast(A, B, (Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272."""
+    import scipy.sparse as sp
+    from . import feastinit
+    if len(args) == 1:
+        B, interval = None, args[0]
+    elif len(args) == 2:
+        B, interval = args
+    else:
+        raise TypeError("feast(A, interval) or feast(A, B, interval)")
+    Emin, Emax = interval
+    N = A.shape[0]
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Matrix must be square")
+    fpm = feastinit() if fpm is None else fpm
+    M0 = min(int(M0), N)
+    cplx = np.iscomplexobj(A) or (B is not None and np.iscomplexobj(B))
+    if cplx:
+        if not ishermitian(A):
+            raise ValueError("Matrix must be Hermitian for the interval solver; use feast_general")
+    elif not issymmetric(A):
+        raise ValueError("Matrix must be symmetric for the interval solver; use feast_general")
+    if sp.issparse(A):
+        if cplx:
+            return feast_hcsrev(A, Emin, Emax, M0, fpm, **kw) if B is None else feast_hcsrgv(A, sp.csc_matrix(B), Emin, Emax, M0, fpm, **kw)
+        return feast_scsrev(A, Emin, Emax, M0, fpm, **kw) if B is None else feast_scsrgv(A, sp.csc_matrix(B), Emin, Emax, M0, fpm, **kw)
+    if cplx:
+        return feast_heev(A, Emin, Emax, M0, fpm, **kw) if B is None else feast_hegv(A, B, Emin, Emax, M0, fpm, **kw)
+    return feast_syev(A, Emin, Emax, M0, fpm, **kw) if B is None else feast_sygv(A, B, Emin, Emax, M0, fpm, **kw)
+
+
+def feast_banded(A, kla, interval, B=None, klb=0, M0=10, fpm=None, **kw):
+    """feast_banded(A, kla, interval; B, klb, M0, fpm) -- interfaces/feast_interfaces.jl:381-420."""
+    from . import feastinit
+    Emin, Emax = interval
+    fpm = feastinit() if fpm is None else fpm
+    A = np.array(A)
+    M0 = min(int(M0), A.shape[1])
+    if np.iscomplexobj(A):
+        return feast_hbev(A, kla, Emin, Emax, M0, fpm, **kw) if B is None else feast_hbgv(A, np.array(B), kla, klb, Emin, Emax, M0, fpm, **kw)
+    return feast_sbev(A, kla, Emin, Emax, M0, fpm, **kw) if B is None else feast_sbgv(A, np.array(B), kla, klb, Emin, Emax, M0, fpm, **kw)
+
+
+# ---- precision / parallel alias families (interfaces/feast_precision_aliases.jl:10-971) ------------------
+# d/z = Float64/ComplexF64 names forward 1:1; pd/pz = "parallel" aliases: with comm/use_threads the reference
+# picks an MPI/threads backend, here every visible rank of the torch.distributed job takes part.
+def _alias(fn):
+    def wrapper(*a, comm=None, use_threads=None, **kw):
+        return fn(*a, **kw)
+    wrapper.__doc__ = f"alias of {fn.__name__} (interfaces/feast_precision_aliases.jl)"
+    return wrapper
+
+
+_ALIASES = {
+    "dfeast_scsrev": feast_scsrev, "dfeast_scsrgv": feast_scsrgv, "zfeast_hcsrev": feast_hcsrev, "zfeast_hcsrgv": feast_hcsrgv,
+    "dfeast_syev": feast_syev, "dfeast_sygv": feast_sygv, "zfeast_heev": feast_heev, "zfeast_hegv": feast_hegv,
+    "dfeast_sbev": feast_sbev, "dfeast_sbgv": feast_sbgv, "zfeast_hbev": feast_hbev, "zfeast_hbgv": feast_hbgv,
+    "dfeast_scsrevx": feast_scsrevx, "dfeast_scsrgvx": feast_scsrgvx, "zfeast_hcsrevx": feast_hcsrevx, "zfeast_hcsrgvx": feast_hcsrgvx,
+    "dfeast_syevx": feast_syevx, "dfeast_sygvx": feast_sygvx, "zfeast_heevx": feast_heevx, "zfeast_hegvx": feast_hegvx,
+}
+for _name, _fn in list(_ALIASES.items()):
+    globals()[_name] = _alias(_fn)
+    globals()["p" + _name] = _alias(_fn)
+    __all__ += [_name, "p" + _name]

@@ -749,7 +749,12 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
         use_x0 = true;
       }
       SolveOut so;
-      const bool ok = node_solve(h, it.node, z, it.nc, rhs + it.c0, X, use_x0, o, tol, so);
+      feastcuda_solver_opts on = o;
+      if (!use_x0) {  // no Ritz information yet: the first sweep may get its own accuracy / budget
+        if (o.inner_rel0 > 0) on.inner_rel = o.inner_rel0;
+        if (o.maxiter0 > 0) on.maxiter = o.maxiter0;
+      }
+      const bool ok = node_solve(h, it.node, z, it.nc, rhs + it.c0, X, use_x0, on, tol, so);
       h->stats.node_solves++;
       if (iterative) {
         h->stats.node_iters[it.node] = so.it_total;
@@ -816,7 +821,8 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     for (int i = 0; i < rank; ++i) if (Emin <= lam_red[i] && lam_red[i] <= Emax) perm.push_back(i);
     M = (int)perm.size();
     for (int i = 0; i < rank; ++i) if (!(Emin <= lam_red[i] && lam_red[i] <= Emax)) perm.push_back(i);
-    if (M == 0) { info_code = 5; break; }
+    const bool keep_going = o.keep_going && iterative && o.inner_rel > 0 && loop_idx < maxloop;
+    if (M == 0 && !keep_going) { info_code = 5; break; }
     std::vector<zc> T((size_t)rank * rank);
     for (int k = 0; k < rank; ++k) {
       const int srcc = perm[k];
@@ -842,12 +848,12 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       max_res = std::max(max_res, res[j]);
     }
     h->stats.ms_resid += tres.ms();
-    eps_val = max_res;
+    eps_val = M > 0 ? max_res : INFINITY;
     M_found = M;
     if (getenv("FEASTCUDA_VERBOSE"))
       fprintf(stderr, "[feastcuda r%d] loop %d: M=%d rank=%d epsout=%.3e items=%zu iters(last)=%d\n", h->rank, loop_idx, M, rank,
               eps_val, items.size(), (int)h->stats.node_iters[items.empty() ? 0 : items.back().node]);
-    if (eps_val <= eps_tol) break;
+    if (M > 0 && eps_val <= eps_tol) break;
     if (loop_idx == maxloop) { info_code = 5; break; }
     active = rank;
     std::swap(qb, xr);   // Q_basis <- Ritz vectors (dense/feast_dense.jl:336-337)

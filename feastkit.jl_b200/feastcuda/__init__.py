@@ -234,7 +234,8 @@ class Engine:
     # -- solves
     @staticmethod
     def make_opts(solver="bicgstab", solver_tol=0.0, solver_maxiter=500, solver_restart=3, inner_rel=0.0, ritz_guess=False,
-                  filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False):
+                  filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False, inner_rel0=0.0, maxiter0=0,
+                  keep_going=False):
         o = SolverOpts()
         o.solver = SOLVER_DIRECT if solver == "direct" else SOLVER_BICGSTAB
         o.tol = float(solver_tol)
@@ -247,6 +248,9 @@ class Engine:
         o.check_every = int(check_every)
         o.q0_real = int(bool(q0_real))
         o.x_real = int(bool(x_real))
+        o.inner_rel0 = float(inner_rel0)
+        o.maxiter0 = int(maxiter0)
+        o.keep_going = int(bool(keep_going))
         return o
 
     def upload_subspace(self, M0, Q0=None):

@@ -57,7 +57,7 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
         kw["ritz_guess"] = True
         kw["inner_rel"] = 1e-3
     kw["filter"] = "true"
-    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every"):
+    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every", "inner_rel0", "maxiter0", "keep_going"):
         if k in extras:
             kw[k] = extras.pop(k)
     if extras:

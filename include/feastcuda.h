@@ -56,7 +56,11 @@ typedef struct {
   int32_t check_every;   /* host polls the device convergence flag every this many iterations (8)     */
   int32_t q0_real;       /* 1: Q0 is n x m0 REAL column-major (real-symmetric API)                    */
   int32_t x_real;        /* 1: X out is n x m0 REAL column-major = real.(q), dense/feast_dense.jl:372 */
-  int32_t reserved[5];
+  double  inner_rel0;    /* inner_rel used while no Ritz guess exists yet (loop 0); 0 -> inner_rel            */
+  int32_t maxiter0;      /* iteration budget of those first solves; 0 -> maxiter                              */
+  int32_t keep_going;    /* 1 (inexact mode only): M = 0 after a sweep does not abort, the sweep's Ritz      */
+                         /*    vectors seed the next loop (the reference stops with info=5)                   */
+  int32_t reserved[4];
 } feastcuda_solver_opts;
 
 typedef struct {

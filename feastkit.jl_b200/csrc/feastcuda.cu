@@ -11,6 +11,7 @@
 #include "kernels_block.cuh"
 #include "kernels_reduced.cuh"
 #include "kernels_sparse.cuh"
+#include "kernels_lanczos.cuh"
 #include "dense_band.cuh"
 
 using namespace feastcuda;
@@ -174,23 +175,44 @@ static void spmm_dispatch(H* h, SpmmArgs<double, TA>& a, int grid) {
 #undef FC_L
 }
 
+// ---- sampled kernel timings: CUDA events on the launching stream around selected launches ---------------------
+// sample_begin returns a slot (or -1 when the pool is exhausted); `tag` lets the caller discard samples later
+static int sample_begin(H* h, int kind, int tag = 0) {
+  if (h->ev_used + 2 > 512) return -1;
+  while (h->ev_pool.size() < h->ev_used + 2) {
+    cudaEvent_t e;
+    FC_CUDA(cudaEventCreate(&e));
+    h->ev_pool.push_back(e);
+  }
+  const int a = (int)h->ev_used, b = a + 1;
+  h->ev_used += 2;
+  FC_CUDA(cudaEventRecord(h->ev_pool[a], h->stream));
+  h->ev_pending.push_back({kind, tag, a, b});
+  return (int)h->ev_pending.size() - 1;
+}
+static void sample_end(H* h, int slot) {
+  if (slot >= 0) FC_CUDA(cudaEventRecord(h->ev_pool[h->ev_pending[slot].b], h->stream));
+}
+// the stream must be idle; samples whose tag is >= tag_limit are dropped (launches that ran as no-ops)
+static void drain_events(H* h, int tag_limit = 2147483647) {
+  for (auto& sm : h->ev_pending) {
+    float ms = 0.f;
+    if (sm.tag < tag_limit && cudaEventElapsedTime(&ms, h->ev_pool[sm.a], h->ev_pool[sm.b]) == cudaSuccess) {
+      h->stats.ms_kern[sm.kind] += ms;
+      h->stats.n_kern[sm.kind]++;
+      if (sm.kind == FEASTCUDA_KERN_SPMM_Z) { h->stats.ms_spmm_sampled += ms; h->stats.spmm_sampled++; }
+    }
+  }
+  h->ev_pending.clear();
+  h->ev_used = 0;
+}
+
 // returns the grid size used (= number of partial rows written per slot)
 template <int MODE>
 static int launch_spmm(H* h, const OpDesc& op, int m, const zd* X, zd* Y, const zd* aux, const zd* lam, bool sample = false) {
   FC_REQUIRE(h->kind == OP_SPARSE, "sparse operator required");
   const int grid = spmm_grid(h, h->n, m);
-  int ev = -1;
-  if (sample) {
-    if (h->ev_pool.size() < 64) {
-      cudaEvent_t a, b;
-      FC_CUDA(cudaEventCreate(&a));
-      FC_CUDA(cudaEventCreate(&b));
-      h->ev_pool.push_back(a);
-      h->ev_pool.push_back(b);
-      ev = (int)h->ev_pool.size() - 2;
-    }
-    if (ev >= 0) FC_CUDA(cudaEventRecord(h->ev_pool[ev], h->stream));
-  }
+  const int ev = sample ? sample_begin(h, FEASTCUDA_KERN_SPMM_Z) : -1;
   if (h->dev_complex) {
     SpmmArgs<double, zd> a;
     a.n = h->n; a.m = m; a.ld = h->ws_ld;
@@ -214,25 +236,14 @@ static int launch_spmm(H* h, const OpDesc& op, int m, const zd* X, zd* Y, const 
   }
   check_launch(h);
   h->stats.spmm_launches++;
-  if (ev >= 0) {
-    FC_CUDA(cudaEventRecord(h->ev_pool[ev + 1], h->stream));
-    h->ev_pending.push_back({ev, ev + 1});
+  sample_end(h, ev);
+  {
+    const double vs = h->dev_complex ? 16.0 : 8.0;
+    double b = (double)h->hA.nnz * (vs + 4.0) + 4.0 * (h->hA.n + 1) + 2.0 * (double)h->hA.n * m * 16.0;
+    if (h->has_b && op.use_b) b += (double)h->hB.nnz * (vs + 4.0) + 4.0 * (h->hB.n + 1);
+    if (sample) h->stats.bytes_kern[FEASTCUDA_KERN_SPMM_Z] = b;
   }
   return grid;
-}
-
-static void drain_events(H* h) {
-  for (auto& pr : h->ev_pending) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev_pool[pr.first], h->ev_pool[pr.second]) == cudaSuccess) {
-      h->stats.ms_spmm_sampled += ms;
-      h->stats.spmm_sampled++;
-    }
-  }
-  h->ev_pending.clear();
-  // events are reused: keep the pool, hand them out again from the start
-  for (auto e : h->ev_pool) cudaEventDestroy(e);
-  h->ev_pool.clear();
 }
 
 static OpDesc op_shifted(zc z) { return OpDesc{mk<double>(-1.0, 0.0), tozd(z), true, true}; }
@@ -446,6 +457,255 @@ static void block_bicgstab(H* h, zc z, int m, const zd* RHS, zd* X, bool use_x0,
   for (int c = 0; c < m; ++c) ci += out.iters[c];
   h->stats.col_iters += ci;
   drain_events(h);
+}
+
+// =====================================================================================================
+// multi-shift two-pass Lanczos filter (kernels_lanczos.cuh; CPU port: oracle/feast_port.py:feast_hrr_mslanczos)
+// Computes, for the real basis columns [c0, c0+nc) of slot `basis_slot`, the filtered block
+//     Qacc = sum_e Re(2 w_e (z_e I - A)^-1 q)           (sparse/feast_sparse.jl:318-370 with B = I)
+// into the same columns of BS_ACC (complex storage, zero imaginary part).  With Ritz values theta (previous
+// loop) the solves start from x0 = q/(z_e - theta):  x_e = q/(z_e-theta) + (z_e I - A)^-1 (A q - theta q)/(z_e-theta),
+// every residual system shares the start vector A q - theta q, so one recurrence still serves all nodes.
+// =====================================================================================================
+struct MslOut { int k = 0; double maxres = 0.0; bool converged = false; };
+
+static inline int lz_ld(H* h) { return (h->ws_ld + 1) & ~1; }
+static inline double* rblk(H* h, int slot) { return h->blk[slot].as<double>(); }
+
+static int lz_grid_spmm(H* h, int64_t n, int rows_per_step) {
+  int64_t g = (n + rows_per_step - 1) / rows_per_step;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)h->sms * h->lz_ctas_per_sm));
+}
+
+template <int MODE>
+static void lz_launch(H* h, LzArgs& a, int* grid_out) {
+  const int P = (a.m + 1) / 2;
+  // G lanes per row, NC column-pair chunks per lane
+#define FC_LZ(G, NC)                                                                       \
+  do {                                                                                     \
+    if (h->lz_threads >= 1024 && NC == 1) {                                                \
+      const int grid = lz_grid_spmm(h, a.n, 32 * (32 / G));                                \
+      *grid_out = grid;                                                                    \
+      k_lz_spmm<G, NC, MODE, 1024><<<grid, 1024, 0, h->stream>>>(a);                       \
+    } else {                                                                               \
+      const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G));                                \
+      *grid_out = grid;                                                                    \
+      k_lz_spmm<G, NC, MODE, 512><<<grid, 512, 0, h->stream>>>(a);                         \
+    }                                                                                      \
+  } while (0)
+  if (P <= 1) FC_LZ(1, 1);
+  else if (P <= 2) FC_LZ(2, 1);
+  else if (P <= 4) FC_LZ(4, 1);
+  else if (P <= 8) FC_LZ(8, 1);
+  else if (P <= 16) FC_LZ(16, 1);
+  else if (P <= 32) FC_LZ(32, 1);
+  else FC_LZ(32, 2);
+#undef FC_LZ
+  check_launch(h);
+  h->stats.spmm_launches++;
+}
+
+static double lz_bytes_spmm(H* h, int m, int nvec) {
+  return (double)h->hA.nnz * 12.0 + 4.0 * (double)(h->hA.n + 1) + (double)nvec * (double)h->hA.n * m * 8.0;
+}
+
+static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, const double* theta, const zc* Zne, const zc* Wne,
+                       int ne, double target, int kmax, int check_every, MslOut& out) {
+  FC_REQUIRE(h->kind == OP_SPARSE && !h->dev_complex && !h->has_b, "multi-shift Lanczos needs a real standard sparse problem");
+  FC_REQUIRE((c0 & 1) == 0, "column slices must start at an even column");
+  const int64_t n = h->ws_n;
+  const int64_t ldz = h->ws_ld, ld = lz_ld(h);
+  kmax = std::max(1, std::min(kmax, 16384));
+  check_every = std::max(1, check_every);
+  const int P = (nc + 1) / 2;
+  const int pp = pow2_ge(P);
+  const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * 8));
+
+  // ---- device scalars ------------------------------------------------------------------------------------------
+  const size_t rowsz = (size_t)FC_MAXCOLS;
+  const size_t per = (size_t)(kmax + 2) * rowsz;
+  const size_t scal_doubles = 5 * per + rowsz /*scale*/ + 2 * rowsz /*theta, rho*/ + (size_t)(kmax + 2) /*maxres*/;
+  h->lz_scal.ensure(scal_doubles * sizeof(double));
+  h->lz_coef.ensure(per * sizeof(double));
+  h->lz_state.ensure(((size_t)2 * ne * rowsz + ne) * sizeof(zd) + 64);
+  double* base = h->lz_scal.as<double>();
+  FC_CUDA(cudaMemsetAsync(base, 0, scal_doubles * sizeof(double), h->stream));
+  LzScalars S;
+  S.alpha = base; S.beta = base + per; S.inv_beta = base + 2 * per; S.ratio_b = base + 3 * per; S.ratio_a = base + 4 * per;
+  S.scale = base + 5 * per;
+  double* d_theta = S.scale + rowsz;
+  double* d_rho = d_theta + rowsz;
+  S.maxres = d_rho + rowsz;
+  zd* stz = h->lz_state.as<zd>();
+  S.d = stz; S.g = stz + (size_t)ne * rowsz;
+  zd* d_z = stz + (size_t)2 * ne * rowsz;
+  S.z = d_z;
+  S.ne = ne;
+  S.target = target;
+  S.done_k = reinterpret_cast<int*>(d_z + ne);
+  FC_CUDA(cudaMemcpyAsync(d_z, Zne, (size_t)ne * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+
+  // ---- real work blocks (each aliases a complex slot; n x ld doubles) -------------------------------------------
+  double* RQ = rblk(h, BS_KS) + c0;
+  double* RB = rblk(h, BS_KR) + c0;
+  double* UA = rblk(h, BS_KRH) + c0;
+  double* UB = rblk(h, BS_KP) + c0;
+  double* QA = rblk(h, BS_KV) + c0;
+  const zd* basis = blk(h, basis_slot) + c0;
+  double* part = h->partial_r.as<double>();
+
+  std::vector<double> rho(nc, 0.0);
+  if (!have_ritz) {
+    k_lz_real_part<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS);
+    check_launch(h);
+    k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, egrid, FC_MAXCOLS, nc);
+    check_launch(h);
+    FC_CUDA(cudaMemset2DAsync(QA, (size_t)ld * sizeof(double), 0, (size_t)(2 * P) * sizeof(double), (size_t)n, h->stream));
+  } else {
+    // rho(theta) = Re sum_e 2 w_e / (z_e - theta): what the rational filter does to an exact eigenvector
+    for (int c = 0; c < nc; ++c) {
+      zc acc(0.0);
+      for (int e = 0; e < ne; ++e) acc += 2.0 * Wne[e] / (Zne[e] - theta[c]);
+      rho[c] = acc.real();
+    }
+    FC_CUDA(cudaMemcpyAsync(d_theta, theta, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FC_CUDA(cudaMemcpyAsync(d_rho, rho.data(), (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_lz_real_part<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS);
+    check_launch(h);
+    LzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.m = nc; a.ld = ld;
+    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
+    a.U = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
+    a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w;
+    int g = 0;
+    const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
+    lz_launch<LZ_RES>(h, a, &g);
+    sample_end(h, ev);
+    h->stats.bytes_kern[FEASTCUDA_KERN_LZ_RES] = lz_bytes_spmm(h, nc, 3);
+    k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g, FC_MAXCOLS, nc);
+    check_launch(h);
+    sync(h);  // theta / rho are host buffers
+  }
+
+  auto cur = [&](int j) -> double* { return j == 0 ? RB : ((j & 1) ? UA : UB); };
+
+  // ---- pass 1: build T_k, device-side convergence flag ----------------------------------------------------------
+  Timer t1;
+  int* flag = reinterpret_cast<int*>(pinned_buf(h, 64));
+  flag[0] = 0;
+  int done = 0, kfinal = 0;
+  while (done < kmax) {
+    const int batch = std::min(check_every, kmax - done);
+    for (int j = done; j < done + batch; ++j) {
+      LzArgs a;
+      memset(&a, 0, sizeof(a));
+      a.n = n; a.m = nc; a.ld = ld;
+      a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
+      a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1);
+      a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
+      a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w; a.done = S.done_k;
+      const bool smp = (j % 16) == 3;
+      int g = 0;
+      int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
+      lz_launch<LZ_P1>(h, a, &g);
+      sample_end(h, ev);
+      k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, g, FC_MAXCOLS, nc);
+      check_launch(h);
+      ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_UPD, j) : -1;
+      k_lz_update<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
+                                                 S.done_k);
+      check_launch(h);
+      sample_end(h, ev);
+      k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, egrid, FC_MAXCOLS, nc);
+      check_launch(h);
+    }
+    done += batch;
+    FC_CUDA(cudaMemcpyAsync(flag, S.done_k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+    if (flag[0] != 0) { kfinal = flag[0]; out.converged = true; break; }
+  }
+  if (kfinal == 0) kfinal = done;
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = lz_bytes_spmm(h, nc, 3);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_UPD] = 3.0 * (double)n * nc * 8.0;
+  drain_events(h, kfinal);
+  h->stats.lz_steps_p1 += kfinal;
+  h->stats.krylov_iters += kfinal;
+  h->stats.col_iters += (int64_t)kfinal * nc;
+  h->stats.ms_lz_p1 += t1.ms();
+
+  // ---- coefficients c_j = ||b|| sum_e Re(2 w_e F_e [(z_e I - T_k)^-1 e_1]_j), divided by beta_j (unnormalised vectors) ---
+  const int k = kfinal;
+  std::vector<double> al((size_t)k * rowsz), be((size_t)(k + 1) * rowsz), coef((size_t)k * rowsz, 0.0);
+  FC_CUDA(cudaMemcpyAsync(al.data(), S.alpha, al.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  FC_CUDA(cudaMemcpyAsync(be.data(), S.beta, be.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  double mr = 0.0;
+  FC_CUDA(cudaMemcpyAsync(&mr, S.maxres + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  out.k = k;
+  out.maxres = mr;
+  {
+    std::vector<zc> dd(k), ff(k);
+    for (int c = 0; c < nc; ++c) {
+      const double b0 = be[c];
+      if (!(b0 > 0.0)) continue;
+      int kc = k;  // a frozen column's T ends where beta vanished
+      for (int j = 1; j < k; ++j)
+        if (be[(size_t)j * rowsz + c] == 0.0) { kc = j; break; }
+      for (int e = 0; e < ne; ++e) {
+        const zc z = Zne[e];
+        const zc F = have_ritz ? zc(1.0) / (z - theta[c]) : zc(1.0);
+        const zc wf = 2.0 * Wne[e] * F * b0;
+        dd[0] = z - al[c];
+        ff[0] = 1.0;
+        for (int j = 1; j < kc; ++j) {
+          const double bj = be[(size_t)j * rowsz + c];
+          const zc w = -bj / dd[j - 1];
+          dd[j] = (z - al[(size_t)j * rowsz + c]) + w * bj;
+          ff[j] = -w * ff[j - 1];
+        }
+        zc y = ff[kc - 1] / dd[kc - 1];
+        coef[(size_t)(kc - 1) * rowsz + c] += (wf * y).real();
+        for (int j = kc - 2; j >= 0; --j) {
+          y = (ff[j] + be[(size_t)(j + 1) * rowsz + c] * y) / dd[j];
+          coef[(size_t)j * rowsz + c] += (wf * y).real();
+        }
+      }
+      for (int j = 0; j < kc; ++j) coef[(size_t)j * rowsz + c] /= be[(size_t)j * rowsz + c];
+    }
+  }
+  double* d_coef = h->lz_coef.as<double>();
+  FC_CUDA(cudaMemcpyAsync(d_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+
+  // ---- pass 2: same recurrence from the stored scalars, accumulation fused ---------------------------------------
+  Timer t2;
+  for (int j = 0; j < k; ++j) {
+    if (j == k - 1) {
+      k_lz_axpy<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, cur(j), QA);
+      check_launch(h);
+      break;
+    }
+    LzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.m = nc; a.ld = ld;
+    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
+    a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1); a.Q = QA;
+    a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
+    a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
+    a.far_w = h->lz_far_w;
+    const bool smp = (j % 16) == 3;
+    int g = 0;
+    const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
+    lz_launch<LZ_P2>(h, a, &g);
+    sample_end(h, ev);
+  }
+  k_lz_to_complex<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
+  check_launch(h);
+  sync(h);  // coef is a host buffer
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = lz_bytes_spmm(h, nc, 5);
+  drain_events(h);
+  h->stats.lz_steps_p2 += k;
+  h->stats.ms_lz_p2 += t2.ms();
 }
 
 // =====================================================================================================
@@ -735,9 +995,31 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     const zd* rhs = basis;
     if (h->has_b) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
     zero_cols(h, active, blk(h, BS_ACC));
-    std::vector<WorkItem> items = build_items(ne, active, h->nranks, h->rank, shard, cost);
+    const bool use_msl = iterative && o.solver == FEASTCUDA_SOLVER_MSLANCZOS && !h->has_b && real_mode;
+    std::vector<WorkItem> items;
+    if (!use_msl) items = build_items(ne, active, h->nranks, h->rank, shard, cost);
     std::vector<double> node_cost(ne, 0.0), node_cols(ne, 0.0);
     bool failed = false;
+    if (use_msl) {
+      // one real Lanczos recurrence per column serves every node; ranks own contiguous column-pair slices
+      const int npairs = (active + 1) / 2;
+      const int pb = npairs / h->nranks, pr = npairs % h->nranks;
+      const int p0 = h->rank * pb + std::min(h->rank, pr), pn = pb + (h->rank < pr ? 1 : 0);
+      const int c0 = 2 * p0, nc = std::max(0, std::min(active, 2 * (p0 + pn)) - c0);
+      const bool first = !(o.ritz_guess && have_ritz);
+      double target = (first && o.inner_rel0 > 0) ? o.inner_rel0 : o.inner_rel;
+      if (!(target > 0)) target = tol;
+      const int kmax = (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter;
+      if (nc > 0) {
+        MslOut mo;
+        msl_filter(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
+        h->stats.node_solves += ne;
+        for (int e = 0; e < ne && e < 128; ++e) h->stats.node_iters[e] = mo.k;
+        if (getenv("FEASTCUDA_VERBOSE"))
+          fprintf(stderr, "[feastcuda r%d] loop %d: lanczos k=%d maxres=%.3e converged=%d cols=[%d,%d)\n", h->rank, loop_idx, mo.k,
+                  mo.maxres, (int)mo.converged, c0, c0 + nc);
+      }
+    }
     for (const WorkItem& it : items) {
       const zc z = Zne[it.node];
       zd* X = blk(h, BS_KX) + it.c0;
@@ -919,6 +1201,9 @@ int feastcuda_create(feastcuda_handle* out, int device) {
   FC_CUDA(cudaGetDeviceProperties(&prop, device));
   h->sms = prop.multiProcessorCount;
   FC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("FEASTCUDA_LZ_THREADS")) h->lz_threads = atoi(e);
+  if (const char* e = getenv("FEASTCUDA_LZ_CTAS")) h->lz_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
+  if (const char* e = getenv("FEASTCUDA_LZ_FARW")) h->lz_far_w = atoi(e);
   *out = h;
   FC_CATCH
 }
@@ -929,7 +1214,7 @@ int feastcuda_destroy(feastcuda_handle h) {
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
   DBuf* bufs[] = {&h->partial, &h->partial_r, &h->kstate, &h->small, &h->small2, &h->gram_partial, &h->stage, &h->red_ws,
-                  &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB};
+                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB};
   for (DBuf* b : bufs) b->release();
   for (auto& b : h->lu_cache) b.release();
   for (auto& b : h->piv_cache) b.release();

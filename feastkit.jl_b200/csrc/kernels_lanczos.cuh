@@ -1,0 +1,415 @@
+// Multi-shift Lanczos inner solver for the standard real-symmetric FEAST problem (B = I, real basis).
+//
+// All ne shifted systems (z_e I - A) x_e = b of one refinement loop share the Krylov space K(A, b), so the
+// engine runs ONE real Lanczos recurrence per right-hand-side column (all columns in lock step) instead of
+// ne complex Krylov solves (the reference does ne*M0 GMRES calls, sparse/feast_sparse.jl:164-236,318-370),
+// and gets the w_e-weighted sum  Q = sum_e Re(2 w_e x_e)  (sparse/feast_sparse.jl:369) as  V_k c  with
+// c = ||b|| sum_e Re(2 w_e (z_e I - T_k)^-1 e_1)  from the k x k Lanczos tridiagonal T_k of each column.
+// Two passes over the recurrence (no basis is stored):
+//   pass 1  k_lz_spmm<LZ_P1> + k_lz_update: builds T_k; the host tracks every shifted residual
+//           beta_{k+1} |e_k^T (z_e I - T_k)^-1 e_1| and stops the sweep;
+//   pass 2  k_lz_spmm<LZ_P2>: re-runs the recurrence with the stored scalars (bit-identical vectors) and
+//           accumulates Q += c_j v_j in the same kernel -- the accumulation is the solve's epilogue.
+// Vectors are REAL row-major n x ld blocks (ld even; the m active columns of a row are contiguous), each lane
+// owns column PAIRS (one 16-byte load per stored entry).  Lanczos vectors are kept unnormalised:
+// u_j = beta_j v_j, the 1/beta_j factors ride along as per-column scalars.
+//
+// HBM-bound.  Algorithmic bytes per launch (n rows, m columns, nnz entries, 8-byte values, 4-byte indices):
+//   LZ_P1   nnz*12 + 4(n+1) + 3*n*m*8   (gather u_j once, own-row u_{j-1}, write A v_j - beta_j v_{j-1})
+//   update  3*n*m*8
+//   LZ_P2   nnz*12 + 4(n+1) + 5*n*m*8   (+ read/write of the accumulator)
+#pragma once
+#include "cxmath.cuh"
+#include "kernels_block.cuh"
+
+namespace feastcuda {
+
+enum LzMode {
+  LZ_P1 = 0,     // out = (A u) * inv_beta - ratio_b * prev ;   partial[0] = u . out
+  LZ_P2 = 1,     // t as LZ_P1; out = t - ratio_a * u ;  Q += coef * u
+  LZ_RES = 2,    // out = A u - theta * u ;  partial[0] = |out|^2 ;  Q = coef * u      (Ritz-residual start block)
+  LZ_PLAIN = 3   // out = A u
+};
+
+struct LzArgs {
+  int64_t n;
+  int m;                 // active columns
+  int64_t ld;            // row stride in doubles (even)
+  const int* ptr; const int* col; const double* val;
+  const double* U;       // gathered operand
+  const double* prev;    // own-row operand u_{j-1}; nullptr at j = 0
+  double* out;           // own-row result (may alias prev)
+  double* Q;             // accumulator (LZ_P2, LZ_RES)
+  const double* s_inv_beta; const double* s_ratio_b; const double* s_ratio_a;   // per-column scalars of this step
+  const double* s_coef;  // LZ_P2: c_j / beta_j ; LZ_RES: rho(theta_c)
+  const double* s_theta; // LZ_RES
+  double* partial;       // [gridDim.x][pstride]
+  int pstride;
+  int far_w;             // > 0: entries with |col - row| > far_w are loaded without L1 allocation
+  const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
+};
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ldg2_stream(const double* p) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+// acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries of `row`, in CSR order
+template <int G, int NC>
+__device__ __forceinline__ void lz_gather(const LzArgs& a, int64_t row, bool valid, int P, int g, unsigned gmask,
+                                          double2 (&acc)[NC]) {
+  constexpr int UN = (G >= 4) ? 4 : G;
+  int p0 = 0, p1 = 0;
+  if (valid) { p0 = a.ptr[row]; p1 = a.ptr[row + 1]; }
+  for (int pb = p0; pb < p1; pb += G) {
+    const int cnt = min(G, p1 - pb);
+    int myj = (int)row;
+    double mya = 0.0;
+    if (g < cnt) { myj = a.col[pb + g]; mya = a.val[pb + g]; }
+    for (int t = 0; t < cnt; t += UN) {
+      int jj[UN];
+      double aa[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        jj[u] = __shfl_sync(gmask, myj, t + u, G);
+        aa[u] = __shfl_sync(gmask, mya, t + u, G);
+      }
+      double2 xv[UN][NC];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const double* xr = a.U + (int64_t)jj[u] * a.ld;
+        const bool far = a.far_w > 0 && abs(jj[u] - (int)row) > a.far_w;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const int pc = g + G * k;
+          if (pc < P) xv[u][k] = far ? ldg2_stream(xr + 2 * pc) : ldg2(xr + 2 * pc);
+          else xv[u][k] = make_double2(0.0, 0.0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          acc[k].x = fma(aa[u], xv[u][k].x, acc[k].x);
+          acc[k].y = fma(aa[u], xv[u][k].y, acc[k].y);
+        }
+    }
+  }
+}
+
+__device__ __forceinline__ double2 lz_scal2(const double* s, int c0, int m) {
+  double2 v = make_double2(0.0, 0.0);
+  if (s != nullptr) {
+    if (c0 < m) v.x = s[c0];
+    if (c0 + 1 < m) v.y = s[c0 + 1];
+  }
+  return v;
+}
+
+// the two Lanczos vector updates, shared by pass 1 (split over two kernels) and pass 2 (fused): identical rounding
+__device__ __forceinline__ double2 lz_t(double2 acc, double2 ib, double2 rb, double2 pv) {
+  double2 t;
+  t.x = __fma_rn(-rb.x, pv.x, __dmul_rn(acc.x, ib.x));
+  t.y = __fma_rn(-rb.y, pv.y, __dmul_rn(acc.y, ib.y));
+  return t;
+}
+__device__ __forceinline__ double2 lz_next(double2 t, double2 ra, double2 uo) {
+  double2 r;
+  r.x = __fma_rn(-ra.x, uo.x, t.x);
+  r.y = __fma_rn(-ra.y, uo.y, t.y);
+  return r;
+}
+
+template <int G, int NC, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_lz_spmm(LzArgs a) {
+  if (a.done != nullptr && *a.done != 0) return;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
+  constexpr unsigned gm0 = (G >= 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  const unsigned gmask = gm0 << (sub * G);
+  const int wib = threadIdx.x >> 5, wpb = THREADS >> 5;
+  const int64_t step = (int64_t)wpb * RPW;
+  int64_t rpb = (a.n + gridDim.x - 1) / gridDim.x;
+  rpb = ((rpb + step - 1) / step) * step;
+  const int64_t row_begin = (int64_t)blockIdx.x * rpb;
+  const int64_t row_end = min(a.n, row_begin + rpb);
+  const int P = (a.m + 1) >> 1;
+
+  double2 ib[NC], rb[NC], ra[NC], cf[NC], th[NC], dot[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int c0 = 2 * (g + G * k);
+    ib[k] = lz_scal2(a.s_inv_beta, c0, a.m);
+    rb[k] = lz_scal2(a.s_ratio_b, c0, a.m);
+    ra[k] = lz_scal2(a.s_ratio_a, c0, a.m);
+    cf[k] = lz_scal2(a.s_coef, c0, a.m);
+    th[k] = lz_scal2(a.s_theta, c0, a.m);
+    dot[k] = make_double2(0.0, 0.0);
+  }
+
+  for (int64_t rb0 = row_begin + (int64_t)wib * RPW; rb0 < row_end; rb0 += step) {
+    const int64_t row = rb0 + sub;
+    const bool valid = row < row_end;
+    double2 acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] = make_double2(0.0, 0.0);
+    lz_gather<G, NC>(a, row, valid, P, g, gmask, acc);
+    if (valid) {
+      const int64_t ro = row * a.ld;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int pc = g + G * k;
+        if (pc < P) {
+          const int64_t off = ro + 2 * pc;
+          if constexpr (MODE == LZ_PLAIN) {
+            stg2(a.out + off, acc[k]);
+          } else if constexpr (MODE == LZ_RES) {
+            const double2 xo = ldg2(a.U + off);
+            double2 t;
+            t.x = __fma_rn(-th[k].x, xo.x, acc[k].x);
+            t.y = __fma_rn(-th[k].y, xo.y, acc[k].y);
+            stg2(a.out + off, t);
+            dot[k].x = fma(t.x, t.x, dot[k].x);
+            dot[k].y = fma(t.y, t.y, dot[k].y);
+            if (a.Q != nullptr) stg2(a.Q + off, make_double2(cf[k].x * xo.x, cf[k].y * xo.y));
+          } else {
+            const double2 uo = ldg2(a.U + off);
+            const double2 pv = (a.prev != nullptr) ? ldg2(a.prev + off) : make_double2(0.0, 0.0);
+            const double2 t = lz_t(acc[k], ib[k], rb[k], pv);
+            if constexpr (MODE == LZ_P1) {
+              stg2(a.out + off, t);
+              dot[k].x = fma(uo.x, t.x, dot[k].x);
+              dot[k].y = fma(uo.y, t.y, dot[k].y);
+            } else {
+              stg2(a.out + off, lz_next(t, ra[k], uo));
+              double2 q = ldg2(a.Q + off);
+              q.x = fma(cf[k].x, uo.x, q.x);
+              q.y = fma(cf[k].y, uo.y, q.y);
+              stg2(a.Q + off, q);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if constexpr (MODE == LZ_P1 || MODE == LZ_RES) {
+    // fixed-order CTA reduction: every launch sums in the same order (pass 2 relies on pass 1's exact scalars)
+    __shared__ double2 red[(THREADS / 32) * 32 * NC];
+    const int width = G * NC;   // pairs per row group
+#pragma unroll
+    for (int k = 0; k < NC; ++k) red[(wib * RPW + sub) * width + g + G * k] = dot[k];
+    __syncthreads();
+    const int ngroups = wpb * RPW;
+    for (int pc = threadIdx.x; pc < width; pc += THREADS) {
+      if (pc < P) {
+        double sx = 0.0, sy = 0.0;
+        for (int q = 0; q < ngroups; ++q) { const double2 v = red[q * width + pc]; sx += v.x; sy += v.y; }
+        double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
+        o[0] = sx;
+        if (2 * pc + 1 < a.m) o[1] = sy;
+      }
+    }
+  }
+}
+
+// ---- elementwise kernels on real blocks: a thread owns one column PAIR, rows strided ---------------------
+struct EwMap2 {
+  int pc, rsub, rpb;
+  __device__ __forceinline__ EwMap2(int pp) { pc = threadIdx.x % pp; rsub = threadIdx.x / pp; rpb = blockDim.x / pp; }
+};
+
+__device__ __forceinline__ void block_reduce_pairs(double2 v, int pp, int P, int m, double* out_row) {
+  __shared__ double2 red2[256];
+  __syncthreads();
+  red2[threadIdx.x] = v;
+  __syncthreads();
+  if ((int)threadIdx.x < pp && (int)threadIdx.x < P) {
+    double sx = 0.0, sy = 0.0;
+    for (int q = threadIdx.x; q < (int)blockDim.x; q += pp) { sx += red2[q].x; sy += red2[q].y; }
+    out_row[2 * threadIdx.x] = sx;
+    if (2 * (int)threadIdx.x + 1 < m) out_row[2 * threadIdx.x + 1] = sy;
+  }
+}
+
+// pass 1, second half of a step: T (in place) <- T - ratio_a * U ; partial = |T|^2
+__global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_ratio_a,
+                                                   const double* __restrict__ U, double* __restrict__ T,
+                                                   double* __restrict__ partial, int pstride, const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  EwMap2 e(pp);
+  const int P = (m + 1) >> 1;
+  double2 acc = make_double2(0.0, 0.0);
+  if (e.pc < P) {
+    const double2 ra = lz_scal2(s_ratio_a, 2 * e.pc, m);
+    for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+      const int64_t off = row * ld + 2 * e.pc;
+      const double2 r = lz_next(ldg2(T + off), ra, ldg2(U + off));
+      stg2(T + off, r);
+      acc.x = fma(r.x, r.x, acc.x);
+      acc.y = fma(r.y, r.y, acc.y);
+    }
+  }
+  block_reduce_pairs(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
+}
+
+// Q += coef * U  (last pass-2 step: no further Lanczos vector is needed)
+__global__ void __launch_bounds__(256) k_lz_axpy(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_coef,
+                                                 const double* __restrict__ U, double* __restrict__ Q) {
+  EwMap2 e(pp);
+  const int P = (m + 1) >> 1;
+  if (e.pc >= P) return;
+  const double2 cf = lz_scal2(s_coef, 2 * e.pc, m);
+  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+    const int64_t off = row * ld + 2 * e.pc;
+    const double2 u = ldg2(U + off);
+    double2 q = ldg2(Q + off);
+    q.x = fma(cf.x, u.x, q.x);
+    q.y = fma(cf.y, u.y, q.y);
+    stg2(Q + off, q);
+  }
+}
+
+// real part of a complex block -> real block (columns [0, m); the pad column of an odd m is zeroed); partial = |x|^2
+__global__ void __launch_bounds__(256) k_lz_real_part(int64_t n, int m, int pp, int64_t ldz, int64_t ld,
+                                                      const cx<double>* __restrict__ Z, double* __restrict__ X,
+                                                      double* __restrict__ partial, int pstride) {
+  EwMap2 e(pp);
+  const int P = (m + 1) >> 1;
+  double2 acc = make_double2(0.0, 0.0);
+  if (e.pc < P) {
+    const int c0 = 2 * e.pc;
+    for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+      double2 v;
+      v.x = Z[row * ldz + c0].x;
+      v.y = (c0 + 1 < m) ? Z[row * ldz + c0 + 1].x : 0.0;
+      stg2(X + row * ld + c0, v);
+      acc.x = fma(v.x, v.x, acc.x);
+      acc.y = fma(v.y, v.y, acc.y);
+    }
+  }
+  if (partial != nullptr) block_reduce_pairs(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
+}
+
+// real block -> complex block with zero imaginary part
+__global__ void __launch_bounds__(256) k_lz_to_complex(int64_t n, int m, int pp, int64_t ld, int64_t ldz,
+                                                       const double* __restrict__ X, cx<double>* __restrict__ Z) {
+  EwMap2 e(pp);
+  const int P = (m + 1) >> 1;
+  if (e.pc >= P) return;
+  const int c0 = 2 * e.pc;
+  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+    const double2 v = ldg2(X + row * ld + c0);
+    Z[row * ldz + c0] = mk<double>(v.x, 0.0);
+    if (c0 + 1 < m) Z[row * ldz + c0 + 1] = mk<double>(v.y, 0.0);
+  }
+}
+
+// ---- per-step scalar recurrences (one CTA) -------------------------------------------------------------------
+// T arrays: [step][FC_MAXCOLS]; `scale` is the running max(|alpha|, beta) used by the breakdown test.
+// Shift recurrences: for every (node e, column c) the last entry g of (z_e I - T_j)^-1 e_1 is advanced by the LU
+// pivots d of the shifted tridiagonal, so that the residual of every shifted system after j+1 steps,
+// beta_{j+1} |g| (relative to ||b||), is known on the device; when all are below `target` the flag done_k = j+1 is
+// raised and every later launch of the sweep returns immediately.
+struct LzScalars {
+  double* alpha; double* beta; double* inv_beta; double* ratio_b; double* ratio_a;   // [kmax + 1][FC_MAXCOLS]
+  double* scale;                                                                     // [FC_MAXCOLS]
+  cx<double>* d; cx<double>* g;                                                      // [ne][FC_MAXCOLS]
+  const cx<double>* z;                                                               // [ne]
+  int ne;
+  double target;
+  int* done_k;
+  double* maxres;                                                                    // [kmax + 1]
+};
+
+// beta_0 = ||b||  from |b|^2 partials
+__global__ void __launch_bounds__(1024) k_lz_scal_init(LzScalars s, const double* partial, int nblocks, int pstride, int m) {
+  __shared__ double so[FC_MAXCOLS];
+  __shared__ double tmp[1024];
+  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+  const int c = threadIdx.x;
+  if (c < m) {
+    const double b = sqrt(so[c]);
+    const bool ok = b > 1e-290;
+    s.beta[c] = b;
+    s.inv_beta[c] = ok ? 1.0 / b : 0.0;
+    s.ratio_b[c] = 0.0;
+    s.scale[c] = 0.0;
+  }
+  if (threadIdx.x == 0) *s.done_k = 0;
+}
+
+// after LZ_P1 of step j: alpha_j = (u_j . t) / beta_j ; ratio_a = alpha_j / beta_j
+__global__ void __launch_bounds__(1024) k_lz_scal1(LzScalars s, int j, const double* partial, int nblocks, int pstride, int m) {
+  if (*s.done_k != 0) return;
+  __shared__ double so[FC_MAXCOLS];
+  __shared__ double tmp[1024];
+  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+  const int c = threadIdx.x;
+  if (c < m) {
+    const int64_t o = (int64_t)j * FC_MAXCOLS + c;
+    const double ibv = s.inv_beta[o];
+    const double al = so[c] * ibv;
+    s.alpha[o] = al;
+    s.ratio_a[o] = al * ibv;
+    s.scale[c] = fmax(s.scale[c], fabs(al));
+  }
+}
+
+// after the update of step j: beta_{j+1} = ||u_{j+1}||; a column whose Krylov space is exhausted is frozen (inv = 0);
+// then the shifted-residual recurrences and the convergence flag
+__global__ void __launch_bounds__(1024) k_lz_scal2(LzScalars s, int j, const double* partial, int nblocks, int pstride, int m) {
+  if (*s.done_k != 0) return;
+  __shared__ double so[FC_MAXCOLS];
+  __shared__ double tmp[1024];
+  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+  const int c = threadIdx.x;
+  const int64_t row = (int64_t)j * FC_MAXCOLS;
+  if (c < m) {
+    const int64_t o = row + c, o1 = o + FC_MAXCOLS;
+    const double b = sqrt(so[c]);
+    const double sc = s.scale[c];
+    const bool ok = (b > 1e-290) && (b > 1e-13 * sc) && (s.inv_beta[o] != 0.0);
+    s.beta[o1] = ok ? b : 0.0;
+    s.inv_beta[o1] = ok ? 1.0 / b : 0.0;
+    s.ratio_b[o1] = ok ? b * s.inv_beta[o] : 0.0;
+    s.scale[c] = fmax(sc, b);
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int idx = threadIdx.x; idx < s.ne * m; idx += blockDim.x) {
+    const int e = idx / m, cc = idx % m;
+    const cx<double> z = s.z[e];
+    const double al = s.alpha[row + cc], bj = s.beta[row + cc], bn = s.beta[row + FC_MAXCOLS + cc];
+    const int64_t so_ = (int64_t)e * FC_MAXCOLS + cc;
+    cx<double> d, g;
+    if (j == 0) {
+      d = mk<double>(z.x - al, z.y);
+      g = mk<double>(1.0, 0.0) / d;
+    } else {
+      const cx<double> dp = s.d[so_];
+      d = mk<double>(z.x - al, z.y) - mk<double>(bj * bj, 0.0) / dp;
+      g = (bj * s.g[so_]) / d;
+    }
+    s.d[so_] = d;
+    s.g[so_] = g;
+    const double r = bn * sqrt(abs2(g));
+    mx = fmax(mx, r);
+  }
+  __syncthreads();
+  tmp[threadIdx.x] = mx;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) tmp[threadIdx.x] = fmax(tmp[threadIdx.x], tmp[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    s.maxres[j] = tmp[0];
+    if (tmp[0] <= s.target) *s.done_k = j + 1;
+  }
+}
+
+}  // namespace feastcuda

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 from ._lib import (A, B, CSC, CSR, FILTER_REFERENCE, FILTER_TRUE, GEN, HERM, SHARD_BALANCED, SHARD_COLUMNS, SHARD_NODES,
-                   SOLVER_BICGSTAB, SOLVER_DIRECT, SYM, FeastCudaError, SolverOpts, Stats)
+                   SOLVER_BICGSTAB, SOLVER_DIRECT, SOLVER_MSLANCZOS, SYM, FeastCudaError, SolverOpts, Stats)
 
 FEAST_UNINITIALIZED = -111
 
@@ -237,7 +237,7 @@ class Engine:
                   filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False, inner_rel0=0.0, maxiter0=0,
                   keep_going=False):
         o = SolverOpts()
-        o.solver = SOLVER_DIRECT if solver == "direct" else SOLVER_BICGSTAB
+        o.solver = {"direct": SOLVER_DIRECT, "bicgstab": SOLVER_BICGSTAB, "mslanczos": SOLVER_MSLANCZOS}[solver]
         o.tol = float(solver_tol)
         o.maxiter = int(solver_maxiter)
         o.restart = int(solver_restart)
@@ -289,7 +289,8 @@ class Engine:
         return lam[:M].copy(), X[:, :M].copy(), res[:M].copy()
 
     def solve_interval(self, Emin, Emax, M0, fpm, Zne, Wne, Q0=None, x_real=False, **kw):
-        """One C-ABI call with HOST buffers in and out (the end-to-end path)."""
+        """One C-ABI call with HOST buffers in and out (the end-to-end path).  The returned stats describe this solve."""
+        self.reset_stats()
         a = L.fpm_array(fpm)
         Z = _as_z(Zne)
         W = _as_z(Wne)

@@ -15,7 +15,8 @@ OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED, ERR_STATE = range(6)
 A, B = 0, 1
 CSR, CSC = 0, 1
 SYM, HERM, GEN = 0, 1, 2
-SOLVER_DIRECT, SOLVER_BICGSTAB = 0, 1
+SOLVER_DIRECT, SOLVER_BICGSTAB, SOLVER_MSLANCZOS = 0, 1, 2
+KERN_NAMES = ("spmm_z", "lz_p1", "lz_upd", "lz_p2", "lz_res", "k5", "k6", "k7")
 FILTER_REFERENCE, FILTER_TRUE = 0, 1
 SHARD_NODES, SHARD_COLUMNS, SHARD_BALANCED = 0, 1, 2
 
@@ -34,11 +35,15 @@ class Stats(C.Structure):
                 ("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("ms_solve", C.c_double),
                 ("ms_ortho", C.c_double), ("ms_project", C.c_double), ("ms_eig", C.c_double), ("ms_resid", C.c_double),
                 ("ms_allreduce", C.c_double), ("ms_spmm_sampled", C.c_double), ("spmm_sampled", C.c_int64),
-                ("bytes_spmm_alg", C.c_double), ("node_iters", C.c_int64 * 128)]
+                ("bytes_spmm_alg", C.c_double), ("node_iters", C.c_int64 * 128),
+                ("lz_steps_p1", C.c_int64), ("lz_steps_p2", C.c_int64), ("ms_lz_p1", C.c_double), ("ms_lz_p2", C.c_double),
+                ("ms_kern", C.c_double * 8), ("n_kern", C.c_int64 * 8), ("bytes_kern", C.c_double * 8)]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "node_iters"}
-        d["node_iters"] = list(self.node_iters)
+        arrays = ("node_iters", "ms_kern", "n_kern", "bytes_kern")
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in arrays}
+        for k in arrays:
+            d[k] = list(getattr(self, k))
         return d
 
 

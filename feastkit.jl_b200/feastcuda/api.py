@@ -43,12 +43,17 @@ def ishermitian(M):
 def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras):
     """Map the reference keywords (sparse/feast_sparse.jl:246-266) onto feastcuda_solver_opts."""
     solver_choice = "gmres" if solver == "iterative" else solver
-    if solver_choice not in ("direct", "gmres", "bicgstab"):
+    if solver_choice not in ("direct", "gmres", "bicgstab", "mslanczos"):
         raise ValueError(f"Unsupported solver option '{solver}'. Use :direct, :gmres, or :iterative.")
     kw = dict(solver_tol=solver_tol, solver_maxiter=solver_maxiter)
-    # sparse inputs are always served by the lock-step block BiCGStab (there is no sparse LU in the engine);
+    # sparse inputs are served by Krylov solvers (there is no sparse LU in the engine): the multi-shift Lanczos
+    # recurrence where it applies (real symmetric, B = I, real basis -- the engine falls back to the lock-step
+    # block BiCGStab otherwise); solver="bicgstab" forces the per-node complex solves.
     # solver_restart keeps its meaning of "restart budget" (true-residual restarts of the short recurrence)
-    kw["solver"] = "direct" if (kind != "sparse" and solver_choice == "direct") else "bicgstab"
+    if kind != "sparse":
+        kw["solver"] = "direct" if solver_choice == "direct" else "bicgstab"
+    else:
+        kw["solver"] = "bicgstab" if solver_choice == "bicgstab" else "mslanczos"
     kw["solver_restart"] = 3 if solver_restart == 30 else int(solver_restart)
     if kind == "sparse":
         # engine defaults for Krylov node solves (DESIGN.md "Inner solves"): start from the previous loop's Ritz pairs
@@ -68,10 +73,10 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
 def _hermitian_solve(kind, setA, setB, N, Emin, Emax, M0, fpm, real_result, contour=None, solver="direct",
                      solver_tol=0.0, solver_maxiter=500, solver_restart=30, Q0=None, engine=None, **extras):
     from . import check_feast_srci_input, feast_contour, feastdefault_
-    eng = _eng(engine)
     feastdefault_(fpm)
     check_feast_srci_input(N, M0, float(Emin), float(Emax), fpm)
     kw = _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
+    eng = _eng(engine)   # argument errors above are raised before any device is touched, as in the reference
     setA(eng)
     if setB is not None:
         setB(eng)

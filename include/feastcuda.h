@@ -35,7 +35,11 @@ enum { FEASTCUDA_OK = 0, FEASTCUDA_ERR_ARG = 1, FEASTCUDA_ERR_CUDA = 2, FEASTCUD
 enum { FEASTCUDA_A = 0, FEASTCUDA_B = 1 };
 enum { FEASTCUDA_CSR = 0, FEASTCUDA_CSC = 1 };                /* SparseMatrixCSC is CSC, 1-based */
 enum { FEASTCUDA_SYM = 0, FEASTCUDA_HERM = 1, FEASTCUDA_GEN = 2 };
-enum { FEASTCUDA_SOLVER_DIRECT = 0, FEASTCUDA_SOLVER_BICGSTAB = 1 };
+enum { FEASTCUDA_SOLVER_DIRECT = 0,      /* cached per-node LU (dense / banded operators)                        */
+       FEASTCUDA_SOLVER_BICGSTAB = 1,    /* lock-step block BiCGStab, one complex solve per node                 */
+       FEASTCUDA_SOLVER_MSLANCZOS = 2 }; /* multi-shift two-pass Lanczos: ONE real recurrence serves all nodes    */
+                                         /* (standard real-symmetric problems, real basis, FILTER_TRUE; other     */
+                                         /* problems fall back to BICGSTAB inside the GPU engine)                 */
 enum { FEASTCUDA_FILTER_REFERENCE = 0,  /* complex half-contour sum 2*w*Y, dense/feast_dense.jl:231 */
        FEASTCUDA_FILTER_TRUE = 1 };     /* rho = Re g: real part for real-symmetric pencils          */
 enum { FEASTCUDA_SHARD_NODES = 0,       /* block node partition, parallel/feast_mpi.jl:36-43         */
@@ -71,7 +75,21 @@ typedef struct {
   int64_t spmm_sampled;      /* how many launches were sampled                                        */
   double  bytes_spmm_alg;    /* algorithmic bytes of ONE shifted SpMM launch at the last shape        */
   int64_t node_iters[128];   /* BiCGStab iterations of the last refinement loop, per node             */
+  /* multi-shift Lanczos */
+  int64_t lz_steps_p1, lz_steps_p2;   /* Lanczos steps run in pass 1 / pass 2 (all loops)                       */
+  double  ms_lz_p1, ms_lz_p2;         /* wall time of the two passes                                            */
+  /* CUDA-event samples per kernel kind (FEASTCUDA_KERN_*): total ms, launches sampled, algorithmic bytes of  */
+  /* ONE launch at the last sampled shape                                                                      */
+  double  ms_kern[8];
+  int64_t n_kern[8];
+  double  bytes_kern[8];
 } feastcuda_stats;
+
+enum { FEASTCUDA_KERN_SPMM_Z = 0,   /* complex shifted SpMM (BiCGStab)            */
+       FEASTCUDA_KERN_LZ_P1 = 1,    /* Lanczos pass-1 SpMM + dot                   */
+       FEASTCUDA_KERN_LZ_UPD = 2,   /* Lanczos pass-1 vector update + norm         */
+       FEASTCUDA_KERN_LZ_P2 = 3,    /* Lanczos pass-2 fused SpMM + accumulate      */
+       FEASTCUDA_KERN_LZ_RES = 4 }; /* Ritz-residual start block                   */
 
 /* ---- lifetime --------------------------------------------------------------------------------- */
 int feastcuda_create(feastcuda_handle* h, int device);

@@ -183,6 +183,197 @@ def feast_hrr_bicgstab(A, B, Emin, Emax, M0, fpm, Q0, inner_rtol=None, inner_rel
                           loop_count, stats)
 
 
+# --------------------------------------------------------------------------------------------------
+# multi-shift two-pass Lanczos (the engine's solver for standard real-symmetric problems)
+# --------------------------------------------------------------------------------------------------
+def lanczos_pass1(A, b, Zne, kmax, target):
+    """Lock-step Lanczos on the columns of the real block b; stops after the first step k at which every
+    shifted system's residual estimate beta_{k+1} |e_k^T (z_e I - T_k)^-1 e_1| (relative to ||b||) is <= target.
+    Mirrors kernels_lanczos.cuh: k_lz_spmm<LZ_P1> / k_lz_update / k_lz_scal1 / k_lz_scal2 (unnormalised vectors,
+    breakdown freeze at beta <= 1e-13 * max(|alpha|, beta)).  Returns alpha (k x m), beta ((k+1) x m), k, maxres."""
+    n, m = b.shape
+    ne = len(Zne)
+    alpha = np.zeros((kmax, m))
+    beta = np.zeros((kmax + 1, m))
+    beta[0] = np.linalg.norm(b, axis=0)
+    inv = np.where(beta[0] > 1e-290, 1.0 / np.where(beta[0] > 0, beta[0], 1.0), 0.0)
+    scale = np.zeros(m)
+    u_prev = np.zeros_like(b)
+    u = b.copy()
+    ratio_b = np.zeros(m)
+    d = np.zeros((ne, m), dtype=complex)
+    g = np.zeros((ne, m), dtype=complex)
+    k, maxres = 0, math.inf
+    for j in range(kmax):
+        t = (A @ u) * inv - ratio_b * u_prev
+        al = np.einsum("ij,ij->j", u, t) * inv
+        alpha[j] = al
+        scale = np.maximum(scale, np.abs(al))
+        u_next = t - (al * inv) * u
+        bn = np.linalg.norm(u_next, axis=0)
+        ok = (bn > 1e-290) & (bn > 1e-13 * scale) & (inv != 0.0)
+        beta[j + 1] = np.where(ok, bn, 0.0)
+        inv_next = np.where(ok, 1.0 / np.where(bn > 0, bn, 1.0), 0.0)
+        ratio_b = np.where(ok, bn * inv, 0.0)
+        scale = np.maximum(scale, bn)
+        for e in range(ne):
+            if j == 0:
+                d[e] = Zne[e] - al
+                g[e] = 1.0 / d[e]
+            else:
+                dn = (Zne[e] - al) - beta[j] ** 2 / d[e]
+                g[e] = beta[j] * g[e] / dn
+                d[e] = dn
+        maxres = float((beta[j + 1][None, :] * np.abs(g)).max())
+        u_prev, u, inv = u, u_next, inv_next
+        k = j + 1
+        if maxres <= target:
+            break
+    return alpha[:k], beta[:k + 1], k, maxres
+
+
+def lanczos_coefficients(alpha, beta, Zne, Wne, F):
+    """c_j = ||b|| sum_e Re(2 w_e F_e [(z_e I - T_k)^-1 e_1]_j) / beta_j  (k x m); F: ne x m guess factors."""
+    k, m = alpha.shape
+    coef = np.zeros((k, m))
+    for c in range(m):
+        if not beta[0, c] > 0:
+            continue
+        kc = k
+        for j in range(1, k):
+            if beta[j, c] == 0.0:
+                kc = j
+                break
+        for e, z in enumerate(Zne):
+            ab = np.zeros((3, kc), dtype=complex)
+            ab[1] = z - alpha[:kc, c]
+            ab[0, 1:] = -beta[1:kc, c]
+            ab[2, :-1] = -beta[1:kc, c]
+            rhs = np.zeros(kc, dtype=complex)
+            rhs[0] = 1.0
+            import scipy.linalg as sla
+            y = sla.solve_banded((1, 1), ab, rhs)
+            coef[:kc, c] += np.real(2 * Wne[e] * F[e, c] * beta[0, c] * y)
+        coef[:kc, c] /= beta[:kc, c]
+    return coef
+
+
+def lanczos_pass2(A, b, alpha, beta, coef, Q):
+    """Re-run the recurrence with the stored scalars and accumulate Q += coef_j * u_j (k_lz_spmm<LZ_P2>)."""
+    k, m = alpha.shape
+    inv = np.where(beta > 0, 1.0 / np.where(beta > 0, beta, 1.0), 0.0)
+    u_prev = np.zeros_like(b)
+    u = b.copy()
+    for j in range(k):
+        Q += coef[j] * u
+        if j == k - 1:
+            break
+        ratio_b = beta[j] * inv[j - 1] if j > 0 else np.zeros(m)
+        t = (A @ u) * inv[j] - ratio_b * u_prev
+        u_prev, u = u, t - (alpha[j] * inv[j]) * u
+    return Q
+
+
+def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None):
+    """sum_e Re(2 w_e (z_e I - A)^-1 q) for the real block Q; theta (Ritz values) or None (zero guess)."""
+    n, m = Q.shape
+    ne = len(Zne)
+    if theta is None:
+        b = Q
+        F = np.ones((ne, m), dtype=complex)
+        acc = np.zeros((n, m))
+    else:
+        b = A @ Q - Q * theta
+        F = 1.0 / (np.asarray(Zne)[:, None] - theta[None, :])
+        acc = Q * np.real((2 * np.asarray(Wne)[:, None] * F).sum(axis=0))
+    alpha, beta, k, maxres = lanczos_pass1(A, b, Zne, kmax, target)
+    coef = lanczos_coefficients(alpha, beta, Zne, Wne, F)
+    acc = lanczos_pass2(A, b, alpha, beta, coef, acc)
+    if stats is not None:
+        stats["lz_steps"].append(k)
+        stats["lz_maxres"].append(maxres)
+    return acc
+
+
+def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0.0, inner_maxiter=500, ritz_guess=True,
+                        verbose=False, col_slices=None, allreduce=None):
+    """H-RR refinement loop (sparse/feast_sparse.jl:246-499 skeleton, B = I, real symmetric A, real Q0, filter rho = Re g)
+    with the engine's multi-shift Lanczos inner solver.  col_slices(active) -> (c0, nc) emulates one rank of the
+    column-sharded multi-GPU run; allreduce sums the accumulator over ranks."""
+    import scipy.linalg as sla
+    N = A.shape[0]
+    fo.feastdefault(fpm)
+    fo.check_feast_srci_input(N, M0, Emin, Emax, fpm)
+    tol_value = 10.0 ** (-fpm[2])
+    Zne, Wne = fo.feast_contour(Emin, Emax, fpm)
+    Qb = np.array(Q0, dtype=np.float64)
+    maxloop = fpm[3]
+    eps_tol = fo.feast_tolerance(fpm)
+    lam = np.zeros(M0)
+    res = np.zeros(M0)
+    X = np.zeros((N, M0))
+    have_ritz = False
+    active = M0
+    info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
+    stats = {"lz_steps": [], "lz_maxres": []}
+    for loop_idx in range(maxloop + 1):
+        loop_count = loop_idx
+        first = not (ritz_guess and have_ritz)
+        target = inner_rel0 if (first and inner_rel0 > 0) else inner_rel
+        if not target > 0:
+            target = tol_value
+        c0, nc = (0, active) if col_slices is None else col_slices(active)
+        acc = np.zeros((N, active))
+        if nc > 0:
+            acc[:, c0:c0 + nc] = mslanczos_filter(A, Qb[:, c0:c0 + nc], None if first else lam[c0:c0 + nc], Zne, Wne, target,
+                                                  inner_maxiter, stats)
+        if allreduce is not None:
+            acc = allreduce(acc)
+        Qr, rank = fo.qr_compress(np.ascontiguousarray(acc), active)
+        if rank == 0:
+            info = fo.ERR_NO_CONV
+            break
+        Qr = Qr.real
+        Sq = Qr.T @ (A @ Qr)
+        Sq = 0.5 * (Sq + Sq.T)
+        lam_red, v_red = sla.eigh(Sq)
+        Xc = np.zeros((N, M0), dtype=np.complex128)
+        Xc[:, :rank] = Qr @ v_red
+        lam[:rank] = lam_red
+        M = fo.reorder_by_interval(lam, Xc, Emin, Emax, rank)
+        X = Xc.real.copy()
+        if M == 0:
+            info = fo.ERR_NO_CONV
+            break
+        X[:, :M] /= np.linalg.norm(X[:, :M], axis=0)
+        R = A @ X[:, :M] - X[:, :M] * lam[:M]
+        res[:M] = np.linalg.norm(R, axis=0) / np.maximum(np.abs(lam[:M]), 1.0)
+        epsout = float(res[:M].max())
+        M_found = M
+        if verbose:
+            print(f"loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={stats['lz_steps'][-1] if stats['lz_steps'] else 0}", flush=True)
+        if epsout <= eps_tol:
+            break
+        if loop_idx == maxloop:
+            info = fo.ERR_NO_CONV
+            break
+        active = rank
+        Qb = X[:, :active].copy()
+        have_ritz = True
+    return fo.FeastResult(lam[:M_found].copy(), X[:, :M_found].copy(), M_found, res[:M_found].copy(), info, epsout,
+                          loop_count, stats)
+
+
+def time_mslanczos_sample(A, m, steps, seed=0):
+    """CPU-baseline sample: `steps` lock-step Lanczos steps (pass 1 arithmetic) on m real columns; returns seconds."""
+    n = A.shape[0]
+    rng = np.random.default_rng(seed)
+    b = rng.standard_normal((n, m))
+    t0 = time.perf_counter()
+    lanczos_pass1(A, b, np.array([0.5 + 0.5j]), steps, 0.0)
+    return time.perf_counter() - t0
+
+
 def time_bicgstab_sample(A, z, m, iters, seed=0):
     """CPU-baseline sample: `iters` lock-step BiCGStab iterations on m columns; returns seconds."""
     n = A.shape[0]

@@ -3,6 +3,8 @@ import sys, time
 sys.path.insert(0, 'oracle')
 import numpy as np, scipy.sparse as sp, scipy.linalg as sla
 import feast_oracle as fo
+import os
+USE_F = int(os.environ.get("USE_F", "1"))
 
 def lanczos_T(A, b, kmax, Z, F, tolrel, check_every=8):
     """per-column Lanczos in lock step; returns alpha,beta (k x m), norms, k used.
@@ -29,7 +31,7 @@ def lanczos_T(A, b, kmax, Z, F, tolrel, check_every=8):
                 g[e] = beta[j] * g[e] / dn; d[e] = dn
         u_prev = u; u = w / bn
         k = j + 1
-        resid = bn[None, :] * np.abs(g) * np.abs(F)   # relative to ||b||, includes guess factor
+        resid = bn[None, :] * np.abs(g) * (np.abs(F) if USE_F else 1.0)
         if (k % check_every == 0) and resid.max() <= tolrel:
             break
     return alpha[:k], beta[:k + 1], nb, k, resid.max()

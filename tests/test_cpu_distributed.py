@@ -1,0 +1,92 @@
+"""CPU, world_size 2 over gloo: the multi-GPU plan of the engine (DESIGN.md "Multi-GPU") exercised with the NumPy ports.
+
+Lanczos path: every rank filters a contiguous slice of column PAIRS for all nodes; BiCGStab path: every rank owns a
+contiguous block of quadrature nodes (parallel/feast_mpi.jl:36-43).  Either way the n x M0 accumulator is summed with ONE
+all-reduce per refinement loop (MPI.Allreduce of Q_proj, parallel/feast_mpi.jl:119,341,858) and the small Rayleigh-Ritz
+stage is replicated.  The sharded runs must give the single-rank result."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def pair_slice(active, nranks, rank):
+    """Column slice owned by `rank`: contiguous column pairs (run_interval in csrc/feastcuda.cu)."""
+    npairs = (active + 1) // 2
+    pb, pr = divmod(npairs, nranks)
+    p0 = rank * pb + min(rank, pr)
+    pn = pb + (1 if rank < pr else 0)
+    c0 = 2 * p0
+    return c0, max(0, min(active, 2 * (p0 + pn)) - c0)
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import torch
+    import torch.distributed as dist
+    import feast_oracle as fo
+    import feast_port as fp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, M0 = 8, 13
+    A = fo.laplacian_3d(N).astype(float).tocsr()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[6] + ev[7])
+    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
+
+    def allreduce(acc):
+        t = torch.from_numpy(np.ascontiguousarray(acc.view(np.float64) if np.iscomplexobj(acc) else acc))
+        dist.all_reduce(t)
+        return acc
+
+    r = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=800,
+                               col_slices=lambda active: pair_slice(active, world, rank), allreduce=allreduce)
+    ne = 8
+    s, c = fo.node_partition(ne, world, rank)
+    rb = fp.feast_hrr_bicgstab(A, None, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=400,
+                               node_items=lambda loop, active: [(e, 0, active) for e in range(s, s + c)], allreduce=allreduce)
+    if rank == 0:
+        np.savez(out, lam=np.sort(r.lambda_), M=r.M, info=r.info, loop=r.loop, q=r.q, lam_b=np.sort(rb.lambda_), M_b=rb.M,
+                 info_b=rb.info)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pair_slices_tile_the_columns():
+    for active in (1, 2, 7, 13, 35, 64, 128):
+        for P in (1, 2, 3, 4, 8):
+            cols = []
+            for rank in range(P):
+                c0, nc = pair_slice(active, P, rank)
+                assert c0 % 2 == 0 and nc >= 0
+                cols += list(range(c0, c0 + nc))
+            assert cols == list(range(active))
+
+
+@pytest.mark.timeout(600)
+def test_world_size_2_sharded_solves_equal_single_rank(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import feast_oracle as fo
+    import feast_port as fp
+    out = str(tmp_path / "r0.npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    N, M0 = 8, 13
+    A = fo.laplacian_3d(N).astype(float).tocsr()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[6] + ev[7])
+    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
+    r1 = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=800)
+    assert int(got["info"]) == r1.info == 0 and int(got["M"]) == r1.M == 7
+    assert int(got["loop"]) == r1.loop
+    assert np.abs(got["lam"] - np.sort(r1.lambda_)).max() < 1e-12
+    assert np.abs(got["lam"] - ev[:7]).max() < 1e-10
+    assert fo.subspace_angle(got["q"].astype(complex), np.asarray(r1.q, dtype=complex)) < 1e-8
+    assert int(got["info_b"]) == 0 and int(got["M_b"]) == 7 and np.abs(got["lam_b"] - ev[:7]).max() < 1e-10

@@ -101,8 +101,9 @@ def test_ka11_oversized_subspace_rank_compression():
         assert r.loop == ro.loop  # same filter, same basis -> same number of refinement loops
 
 
-@pytest.mark.parametrize("filt,N,M0", [("reference", 10, 48), ("true", 14, 24)])
-def test_laplacian3d_matches_oracle_and_analytic(filt, N, M0):
+@pytest.mark.parametrize("filt,N,M0,solver", [("reference", 10, 48, "bicgstab"), ("true", 14, 24, "bicgstab"),
+                                              ("true", 14, 24, "mslanczos")])
+def test_laplacian3d_matches_oracle_and_analytic(filt, N, M0, solver):
     """Reduced-size config 3: 7-point Laplacian N^3, lowest 10 eigenvalues (multiplicities 1,3,3,3).
 
     The reference's complex half-contour filter |g| decays like 1/distance; with M0=24 on 14^3
@@ -116,9 +117,10 @@ def test_laplacian3d_matches_oracle_and_analytic(filt, N, M0):
     fpm = fc.feastinit()
     if filt == "reference":
         fpm[3] = 60
-    r = fc.feast_scsrev(A, Emin, Emax, M0, list(fpm), Q0=Q0, filter=filt, **TIGHT)
+    r = fc.feast_scsrev(A, Emin, Emax, M0, list(fpm), Q0=Q0, filter=filt, solver=solver, **TIGHT)
     ro = fo.feast_scsrev(A, Emin, Emax, M0, list(fpm), Q0=Q0.astype(complex), filter=filt)
     _check_pairs(r, ro, A)
+    assert (r.stats["lz_steps_p1"] > 0) == (solver == "mslanczos")
     assert np.abs(np.sort(r.lambda_) - ev[:10]).max() < 1e-10
     assert abs(r.loop - ro.loop) <= (1 if filt == "reference" else 0)
 
@@ -150,7 +152,7 @@ def test_inexact_inner_solves_with_ritz_guess_reach_full_accuracy():
     fpm = fc.feastinit()
     fpm[3] = 40
     r = fc.feast_scsrev(A, Emin, Emax, M0, fpm, Q0=Q0, filter="true", inner_rel=0.1, ritz_guess=True, solver_tol=1e-13,
-                        solver_maxiter=40, solver_restart=0)
+                        solver_maxiter=40, solver_restart=0, solver="bicgstab")
     assert r.info == 0 and r.M == 10
     assert np.abs(np.sort(r.lambda_) - ev[:10]).max() < 1e-10
     assert r.res.max() < 1e-12
@@ -212,3 +214,55 @@ def test_resident_three_call_form_equals_single_call(engine):
     r = engine.solve_interval(Emin, Emax, M0, fc.feastinit(), Z, W, Q0=Q0, x_real=True, filter="true", **TIGHT)
     assert M == r.M == 4 and info == r.info == 0
     assert np.array_equal(lam, r.lambda_) and np.array_equal(X, r.q)
+
+
+def test_mslanczos_inexact_matches_cpu_port_loop_for_loop():
+    """The engine's default for real-symmetric standard problems (inner_rel=1e-3, Ritz guess) against its NumPy port
+    (oracle/feast_port.py:feast_hrr_mslanczos): same loops, (nearly) the same Lanczos step counts, same eigenpairs."""
+    import feastcuda as fc
+    import feast_port as fp
+    N, M0 = 16, 24
+    A = fo.laplacian_3d(N).astype(float).tocsc()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
+    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
+    r = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000)
+    rp = fp.feast_hrr_mslanczos(A.tocsr(), Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2000)
+    ro = fo.feast_scsrev(A, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
+    _check_pairs(r, ro, A)
+    assert r.loop == rp.loop
+    steps_port = sum(rp.stats["lz_steps"])
+    assert abs(r.stats["lz_steps_p1"] - steps_port) <= max(4, 0.05 * steps_port)
+    assert r.stats["lz_steps_p2"] == r.stats["lz_steps_p1"]
+    assert fo.subspace_angle(r.q.astype(complex), rp.q.astype(complex)) < 1e-8
+
+
+@pytest.mark.parametrize("M0", [1, 2, 7, 33, 64, 100, 128])
+def test_mslanczos_column_counts(M0):
+    """Every lane mapping of the Lanczos SpMM (column pairs: 1..64 per row, odd counts, two chunks per lane)."""
+    import feastcuda as fc
+    n = 400
+    rng = np.random.default_rng(3)
+    d = np.sort(rng.uniform(1.0, 50.0, n))
+    T = sp.diags([0.3 * np.ones(n - 1), d, 0.3 * np.ones(n - 1)], [-1, 0, 1]).tocsc()
+    w = np.linalg.eigvalsh(T.toarray())
+    want = max(1, min(M0 // 2, 20))
+    Emin, Emax = w[0] - 0.1, 0.5 * (w[want - 1] + w[want])
+    Q0 = fo.seeded_subspace(n, M0, complex_storage=False)
+    fpm = fc.feastinit()
+    fpm[3] = 40
+    r = fc.feast_scsrev(T, Emin, Emax, M0, fpm, Q0=Q0, solver_maxiter=1000)
+    assert r.info == 0 and r.M == want
+    assert np.abs(np.sort(r.lambda_) - w[:want]).max() < 1e-10 * max(1.0, abs(w[want]))
+    assert r.res.max() < 1e-12
+
+
+def test_mslanczos_krylov_exhaustion_tiny_matrices():
+    """n <= number of Lanczos steps: the recurrence terminates (beta = 0), frozen columns stay exact."""
+    import feastcuda as fc
+    for n, iv in ((3, (0.5, 3.5)), (10, (0.0, 4.0)), (2, (0.0, 5.0))):
+        A = fo.laplacian_1d(n).tocsc()
+        r = fc.feast_scsrev(A, iv[0], iv[1], n, fc.feastinit(), Q0=fo.seeded_subspace(n, n, complex_storage=False))
+        assert r.info == 0 and r.M == n
+        assert np.allclose(np.sort(r.lambda_), np.linalg.eigvalsh(A.toarray()), atol=1e-10)
+        assert r.stats["lz_steps_p1"] > 0

@@ -1,0 +1,212 @@
+"""CPU: pins the oracle (oracle/feast_oracle.py, oracle/feast_port.py) against the known-answer cases of the reference's
+own test-suite (tests/golden/reference_known_answers.json) and the committed regression anchors."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import feast_oracle as fo
+import feast_port as fp
+
+G = Path(__file__).resolve().parent / "golden"
+KA = json.loads((G / "reference_known_answers.json").read_text())
+REG = json.loads((G / "engine_regression.json").read_text())
+
+
+def _c(d):
+    return np.array(d["re"]) + 1j * np.array(d["im"])
+
+
+def test_feastinit_sentinel_and_defaults():
+    """runtests.jl:10-70: -111 sentinel; defaults fpm[2]=8, fpm[3]=12, fpm[4]=20, fpm[8]=16; contour lengths."""
+    fpm = fo.feastinit()
+    assert len(fpm) == 64 and all(v == -111 for v in fpm)
+    fo.feastdefault(fpm)
+    assert (fpm[1], fpm[2], fpm[3], fpm[7], fpm[15], fpm[17]) == (8, 12, 20, 16, 0, 100)
+    assert fpm == REG["feastdefault"]
+    Z, W = fo.feast_contour(0.0, 1.0, fo.feastinit())
+    assert len(Z) == len(W) == 8
+    Zg, Wg = fo.feast_gcontour(0.0, 1.0, fo.feastinit())
+    assert len(Zg) == len(Wg) == 16
+    with pytest.raises(ValueError):
+        fo.check_feast_srci_input(10, 0, 0.0, 1.0, fpm)
+    with pytest.raises(ValueError):
+        fo.check_feast_srci_input(10, 4, 1.0, 0.0, fpm)
+
+
+def test_contour_golden_numbers():
+    k = KA["contour_default"]
+    Z, W = fo.feast_contour(k["Emin"], k["Emax"], fo.feastinit())
+    assert abs(Z[0] - complex(*k["Z1"])) < 1e-15 and abs(W[0] - complex(*k["W1"])) < 1e-16
+    assert np.allclose(Z, _c(REG["contour_0.5_1.5"]["Z"]), rtol=0, atol=1e-15)
+    assert np.allclose(W, _c(REG["contour_0.5_1.5"]["W"]), rtol=0, atol=1e-15)
+    # the half-contour rule integrates the indicator: sum 2 Re(w/(z - x)) = 1 inside, ~0 far outside
+    rho = lambda x: np.real(np.sum(2 * W / (Z - x)))
+    assert abs(rho(1.0) - 1.0) < 1e-6 and abs(rho(3.0)) < 1e-6
+    Zg, Wg = fo.feast_gcontour(0.0, 2.0, fo.feastinit())
+    assert np.allclose(Zg, _c(REG["gcontour_0_2"]["Z"]), atol=1e-15) and np.allclose(Wg, _c(REG["gcontour_0_2"]["W"]), atol=1e-15)
+    g = lambda x: np.sum(Wg / (Zg - x))
+    assert abs(g(0.3 + 0.2j) - 1.0) < 1e-6 and abs(g(5.0)) < 1e-6
+
+
+def test_helper_known_answers():
+    k = KA["KA12_reorder"]
+    lam = np.array(k["lambda"])
+    vec = np.array(k["vectors"], dtype=complex)
+    src = vec.copy()
+    m = fo.reorder_by_interval(lam, vec, *k["interval"], len(lam))
+    assert m == k["m"] and lam.tolist() == k["lambda_out"] and np.array_equal(vec, src[:, k["perm"]])
+    k = KA["KA12_sort"]
+    lam, q, res = np.array(k["lambda"]), np.array(k["q"]), np.array(k["res"])
+    q0 = q.copy()
+    fo.feast_sort(lam, q, res, 4)
+    assert lam.tolist() == [1.0, 2.0, 3.0, 4.0] and np.array_equal(q, q0[:, k["perm"]]) and res.tolist() == [0.1, 0.2, 0.3, 0.4]
+    k = KA["KA12_sort_general"]
+    lam = _c(k["lambda"])
+    lam0 = lam.copy()
+    q = np.array(KA["KA12_sort"]["q"], dtype=complex)
+    res = np.array(k["res"])
+    fo.feast_sort_general(lam, q, res, 4)
+    assert np.array_equal(lam, lam0[k["perm"]]) and res.tolist() == [0.1, 0.2, 0.3, 0.4]
+    k = KA["KA12_residual"]
+    A, B, q, lam = np.array(k["A"]), np.diag(k["B_diag"]), np.array(k["q"]), np.array(k["lambda"])
+    want = [np.linalg.norm(A @ q[:, j] - lam[j] * (B @ q[:, j])) / max(abs(lam[j]), 1.0) for j in range(2)]
+    assert np.allclose(fo.feast_residual(A, B, lam, q, 2), want)
+    k = KA["KA12_qr_compress"]
+    src = _c(k["src"])
+    Q, rank = fo.qr_compress(src, 4, rank_tol=np.sqrt(np.finfo(float).eps))
+    assert rank == k["rank"]
+    assert np.allclose(Q.conj().T @ Q, np.eye(rank), atol=1e-12) and np.linalg.norm(src - Q @ (Q.conj().T @ src)) <= 1e-12
+
+
+def test_ka1_ka2_ka3_dense_and_sparse_hermitian():
+    k = KA["KA1"]
+    A = np.array(k["A"])
+    r = fo.feast_sygv(A, np.eye(3), *k["interval"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 3 and np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"])
+    k = KA["KA2"]
+    r = fo.feast_heev(_c(k["A"]), *k["interval"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 3 and np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"])
+    k = KA["KA3"]
+    r = fo.feast_hcsrev(sp.csc_matrix(_c(k["A"])), *k["interval"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 3 and np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"])
+
+
+def test_ka4_general_standard_and_generalized():
+    k = KA["KA4"]
+    A, B = _c(k["A"]), _c(k["B"])
+    r = fo.feast_general(A, None, complex(*k["center"]), k["radius"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 2 and np.allclose(np.sort(r.lambda_.real), k["expected_standard"], atol=k["atol"])
+    r = fo.feast_general(sp.csc_matrix(A), None, complex(*k["center"]), k["radius"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 2 and np.allclose(np.sort(r.lambda_.real), k["expected_standard"], atol=k["atol"])
+    rg = fo.feast_general(A, B, complex(*k["center"]), k["radius"], k["M0"], fo.feastinit(), residual="true")
+    assert rg.M == 2 and np.allclose(np.sort(rg.lambda_.real), k["expected_generalized"], atol=k["atol"])
+
+
+def test_ka5_ka6_ka10_sparse():
+    k = KA["KA5"]
+    A = fo.laplacian_1d(k["n"]).tocsc()
+    r = fo.feast_scsrev(A, *k["interval"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 10 and np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"])
+    k = KA["KA6"]
+    A, B = sp.diags(np.array(k["A_diag"], dtype=complex)).tocsc(), sp.diags(np.array(k["B_diag"], dtype=complex)).tocsc()
+    r = fo.feast_hcsrgv(A, B, *k["interval"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == len(k["expected"]) and np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"])
+    k = KA["KA10"]
+    r = fo.feast_scsrev(sp.diags(k["A_diag"]).tocsc(), *k["interval"], k["M0"], fo.feastinit())
+    assert r.info == 0 and r.M == 3 and np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"])
+    rd = fo.feast_syev(np.diag(k["A_diag"]), *k["interval"], k["M0"], fo.feastinit())
+    assert rd.M == 3 and np.allclose(np.sort(rd.lambda_), k["expected"], atol=k["atol"])
+
+
+def test_ka11_rank_compression_dense_sparse_banded():
+    k = KA["KA11"]
+    n = k["n"]
+    d = np.arange(1.0, n + 1)
+
+    def fpm():
+        f = fo.feastinit()
+        for kk, v in k["fpm"].items():
+            f[int(kk) - 1] = v
+        return f
+    for r in (fo.feast_syev(np.diag(d), *k["interval"], k["M0"], fpm()),
+              fo.feast_scsrev(sp.diags(d).tocsc(), *k["interval"], k["M0"], fpm()),
+              fo.feast_hbev(d.reshape(1, n).astype(complex), 0, *k["interval"], k["M0"], fpm())):
+        assert r.info == 0 and r.M == 2
+        assert np.allclose(np.sort(r.lambda_), k["expected"], atol=k["atol"]) and r.res.max() < k["max_res"]
+
+
+def test_ka8_banded_real_symmetric_moment_solver():
+    """runtests.jl:605-636: 1-D Laplacian n=8 in band storage, (0.5, 3.1) -- S-MOM driver."""
+    n = 8
+    A = fo.laplacian_1d(n).toarray()
+    AB = fo.full_to_banded(A, 1)
+    assert np.allclose(fo.banded_to_full(AB, 1, hermitian=False), A)   # converter round trip, runtests.jl:582-600
+    r = fo.feast_sbev(AB, 1, 0.5, 3.1, 8, fo.feastinit())
+    w = np.linalg.eigvalsh(A)
+    want = w[(w >= 0.5) & (w <= 3.1)]
+    assert r.info == 0 and r.M == len(want) and np.allclose(np.sort(r.lambda_), want, atol=1e-8)
+
+
+def test_ka7_direct_equals_gmres():
+    """runtests.jl:306-395,442-508: the iterative path agrees with the direct one."""
+    A = fo.laplacian_1d(12).tocsc()
+    d = fo.feast_scsrgv(A, sp.identity(12, format="csc"), 0.1, 1.2, 6, fo.feastinit())
+    g = fo.feast_scsrgv(A, sp.identity(12, format="csc"), 0.1, 1.2, 6, fo.feastinit(), solver="gmres", solver_tol=1e-12,
+                        solver_maxiter=400, solver_restart=30)
+    assert d.info == g.info == 0 and d.M == g.M and np.allclose(np.sort(d.lambda_), np.sort(g.lambda_), atol=1e-8)
+
+
+def test_regression_anchor_laplacian3d():
+    for filt in ("true", "reference"):
+        k = REG[f"laplacian3d_N12_{filt}"]
+        A = fo.laplacian_3d(k["N"]).astype(float).tocsc()
+        fpm = fo.feastinit()
+        if filt == "reference":
+            fpm[3] = 60
+        r = fo.feast_scsrev(A, *k["interval"], k["M0"], fpm, Q0=fo.seeded_subspace(k["N"] ** 3, k["M0"]), filter=filt)
+        assert (r.M, r.info, r.loop) == (k["M"], k["info"], k["loop"])
+        assert np.allclose(np.sort(r.lambda_), k["lambda"], rtol=1e-12, atol=1e-13)
+        assert np.allclose(np.sort(r.lambda_), k["analytic"], rtol=1e-10, atol=1e-12)
+
+
+def test_engine_ports_reach_the_reference_eigenpairs():
+    """The NumPy ports of the ENGINE's inner solvers (block BiCGStab, multi-shift Lanczos) converge to the oracle's pairs."""
+    N, M0 = 10, 16
+    A = fo.laplacian_3d(N).astype(float).tocsr()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[6] + ev[7])
+    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
+    ro = fo.feast_scsrev(A.tocsc(), Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
+    rl = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=1000)
+    rb = fp.feast_hrr_bicgstab(A, None, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=400)
+    for r in (rl, rb):
+        assert r.info == 0 and r.M == ro.M == 7
+        assert np.abs(np.sort(r.lambda_) - np.sort(ro.lambda_)).max() < 1e-10
+        assert r.res.max() < 1e-12
+        assert fo.subspace_angle(np.asarray(r.q, dtype=complex), np.asarray(ro.q, dtype=complex)) < 1e-8
+    # tight multi-shift solves reproduce the exact-solve loop count
+    rt = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-10, inner_maxiter=3000)
+    assert rt.loop == ro.loop
+
+
+def test_multishift_lanczos_filter_equals_direct_solves():
+    """One filter application: V_k c from the Lanczos tridiagonal == sum_e Re(2 w_e (z_e I - A)^-1 q) by sparse LU."""
+    import scipy.sparse.linalg as spla
+    n, m = 300, 5
+    rng = np.random.default_rng(1)
+    A = sp.diags([rng.uniform(-1, 0, n - 1), rng.uniform(1, 9, n), np.zeros(n - 1)], [-1, 0, 1]).tocsr()
+    A = ((A + A.T) * 0.5).tocsr()
+    Z, W = fo.feast_contour(2.0, 3.0, fo.feastinit())
+    Q = rng.standard_normal((n, m))
+    want = np.zeros((n, m))
+    for z, w in zip(Z, W):
+        lu = spla.splu((z * sp.identity(n, dtype=complex, format="csc") - A.astype(complex)).tocsc())
+        want += np.real(2 * w * lu.solve(Q.astype(complex)))
+    got = fp.mslanczos_filter(A, Q, None, Z, W, 1e-13, 600)
+    assert np.abs(got - want).max() < 1e-9 * np.abs(want).max()
+    theta = np.linspace(2.1, 2.9, m)
+    got2 = fp.mslanczos_filter(A, Q, theta, Z, W, 1e-13, 600)   # Ritz-guess form is the same operator
+    assert np.abs(got2 - want).max() < 1e-9 * np.abs(want).max()

@@ -110,13 +110,15 @@ struct feastcuda_handle_s {
   feastcuda::DBuf blk[feastcuda::BS_COUNT];
   feastcuda::DBuf partial, partial_r, kstate, small, small2, gram_partial, stage, red_ws;
   feastcuda::DBuf lz_scal, lz_coef, lz_state;   // multi-shift Lanczos: per-step scalars, pass-2 coefficients, shift recurrences
-  int lz_threads = 1024;    // CTA size of the Lanczos SpMM (512 or 1024)
-  int lz_ctas_per_sm = 1;   // persistent CTAs per SM of the Lanczos SpMM (contiguous row chunks keep the band in L1)
+  int lz_threads = 512;     // CTA size of the Lanczos SpMM (512 or 1024)
+  int lz_ctas_per_sm = 2;   // persistent CTAs per SM of the Lanczos SpMM (contiguous row chunks keep the band in L1)
+  int lz_tile_rows = 64;    // rows per round-robin tile of the Lanczos SpMM
   int lz_far_w = 0;         // > 0: stored entries further than this from the diagonal bypass L1 allocation
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   std::vector<cudaEvent_t> ev_pool;   // reusable event pairs for sampled kernel timings
   size_t ev_used = 0;
+  cudaEvent_t ev_run[2] = {nullptr, nullptr};
   struct EvSample { int kind, tag, a, b; };
   std::vector<EvSample> ev_pending;
 

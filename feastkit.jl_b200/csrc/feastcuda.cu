@@ -473,8 +473,9 @@ static inline int lz_ld(H* h) { return (h->ws_ld + 1) & ~1; }
 static inline double* rblk(H* h, int slot) { return h->blk[slot].as<double>(); }
 
 static int lz_grid_spmm(H* h, int64_t n, int rows_per_step) {
-  int64_t g = (n + rows_per_step - 1) / rows_per_step;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)h->sms * h->lz_ctas_per_sm));
+  const int64_t tr = (int64_t)std::max(1, h->lz_tile_rows / rows_per_step) * rows_per_step;   // as in k_lz_spmm
+  const int64_t ntiles = (n + tr - 1) / tr;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)h->sms * h->lz_ctas_per_sm));
 }
 
 template <int MODE>
@@ -577,7 +578,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.n = n; a.m = nc; a.ld = ld;
     a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
     a.U = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
-    a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w;
+    a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w; a.tile_rows = h->lz_tile_rows;
     int g = 0;
     const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
     lz_launch<LZ_RES>(h, a, &g);
@@ -604,7 +605,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
       a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1);
       a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
-      a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w; a.done = S.done_k;
+      a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
       const bool smp = (j % 16) == 3;
       int g = 0;
       int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
@@ -692,7 +693,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1); a.Q = QA;
     a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
     a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
-    a.far_w = h->lz_far_w;
+    a.far_w = h->lz_far_w; a.tile_rows = h->lz_tile_rows;
     const bool smp = (j % 16) == 3;
     int g = 0;
     const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
@@ -1204,6 +1205,7 @@ int feastcuda_create(feastcuda_handle* out, int device) {
   if (const char* e = getenv("FEASTCUDA_LZ_THREADS")) h->lz_threads = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_CTAS")) h->lz_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("FEASTCUDA_LZ_FARW")) h->lz_far_w = atoi(e);
+  if (const char* e = getenv("FEASTCUDA_LZ_TILE")) h->lz_tile_rows = std::max(1, atoi(e));
   *out = h;
   FC_CATCH
 }
@@ -1219,6 +1221,7 @@ int feastcuda_destroy(feastcuda_handle h) {
   for (auto& b : h->lu_cache) b.release();
   for (auto& b : h->piv_cache) b.release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  for (auto e : h->ev_run) if (e) cudaEventDestroy(e);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1369,8 +1372,15 @@ int feastcuda_run_interval(feastcuda_handle h, double Emin, double Emax, int64_t
   FC_TRY(h)
   FC_REQUIRE(h != nullptr && fpm && M && info && epsout && loop, "null argument");
   bind_device(h);
+  if (!h->ev_run[0]) { FC_CUDA(cudaEventCreate(&h->ev_run[0])); FC_CUDA(cudaEventCreate(&h->ev_run[1])); }
+  FC_CUDA(cudaEventRecord(h->ev_run[0], h->stream));
   run_interval(h, Emin, Emax, (int)m0, fpm, reinterpret_cast<const zc*>(Zne), reinterpret_cast<const zc*>(Wne), (int)ne, opts, M, info,
                epsout, loop, h->sub_real);
+  FC_CUDA(cudaEventRecord(h->ev_run[1], h->stream));
+  FC_CUDA(cudaEventSynchronize(h->ev_run[1]));
+  float ms_ev = 0.f;
+  FC_CUDA(cudaEventElapsedTime(&ms_ev, h->ev_run[0], h->ev_run[1]));
+  h->stats.ms_dev_run += ms_ev;
   FC_CATCH
 }
 

@@ -46,6 +46,7 @@ struct LzArgs {
   double* partial;       // [gridDim.x][pstride]
   int pstride;
   int far_w;             // > 0: entries with |col - row| > far_w are loaded without L1 allocation
+  int tile_rows;         // rows per round-robin tile (rounded to the CTA's rows-per-iteration)
   const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
 };
 
@@ -57,18 +58,19 @@ __device__ __forceinline__ double2 ldg2_stream(const double* p) {
 }
 __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
-// acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries of `row`, in CSR order
+// acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries [p0, p1) of `row`, in CSR order.
+// (myj, mya): the group's first G entries, already fetched by the caller one iteration ahead.
 template <int G, int NC>
-__device__ __forceinline__ void lz_gather(const LzArgs& a, int64_t row, bool valid, int P, int g, unsigned gmask,
-                                          double2 (&acc)[NC]) {
+__device__ __forceinline__ void lz_gather(const LzArgs& a, int row, int p0, int p1, int myj, double mya, int P, int g,
+                                          unsigned gmask, double2 (&acc)[NC]) {
   constexpr int UN = (G >= 4) ? 4 : G;
-  int p0 = 0, p1 = 0;
-  if (valid) { p0 = a.ptr[row]; p1 = a.ptr[row + 1]; }
   for (int pb = p0; pb < p1; pb += G) {
     const int cnt = min(G, p1 - pb);
-    int myj = (int)row;
-    double mya = 0.0;
-    if (g < cnt) { myj = a.col[pb + g]; mya = a.val[pb + g]; }
+    if (pb != p0) {
+      myj = row;
+      mya = 0.0;
+      if (g < cnt) { myj = a.col[pb + g]; mya = a.val[pb + g]; }
+    }
     for (int t = 0; t < cnt; t += UN) {
       int jj[UN];
       double aa[UN];
@@ -81,7 +83,7 @@ __device__ __forceinline__ void lz_gather(const LzArgs& a, int64_t row, bool val
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const double* xr = a.U + (int64_t)jj[u] * a.ld;
-        const bool far = a.far_w > 0 && abs(jj[u] - (int)row) > a.far_w;
+        const bool far = a.far_w > 0 && abs(jj[u] - row) > a.far_w;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
           const int pc = g + G * k;
@@ -124,41 +126,86 @@ __device__ __forceinline__ double2 lz_next(double2 t, double2 ra, double2 uo) {
 }
 
 template <int G, int NC, int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_lz_spmm(LzArgs a) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   if (a.done != nullptr && *a.done != 0) return;
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
   constexpr unsigned gm0 = (G >= 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
   const unsigned gmask = gm0 << (sub * G);
   const int wib = threadIdx.x >> 5, wpb = THREADS >> 5;
-  const int64_t step = (int64_t)wpb * RPW;
-  int64_t rpb = (a.n + gridDim.x - 1) / gridDim.x;
-  rpb = ((rpb + step - 1) / step) * step;
-  const int64_t row_begin = (int64_t)blockIdx.x * rpb;
-  const int64_t row_end = min(a.n, row_begin + rpb);
+  constexpr int STEP = (THREADS / 32) * RPW;          // rows the CTA covers per iteration
   const int P = (a.m + 1) >> 1;
+  const int n = (int)a.n;
+  // Rows are dealt to the CTAs in tiles of `tile_rows` consecutive rows, round robin: the whole grid sweeps the matrix as
+  // one moving front, so a vector row fetched as somebody's far neighbour is still in L2 when the front reaches it
+  // (each row of U comes from HBM once), while the near neighbours of a tile stay in the CTA's L1.
+  const int spt = max(1, a.tile_rows / STEP);         // iterations per tile
+  const int TR = spt * STEP;
+  const int ntiles = (n + TR - 1) / TR;
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int niter = my_tiles * spt;
+  auto row_of = [&](int it) -> int {
+    if (it >= niter) return n;
+    const int tile = (int)blockIdx.x + (it / spt) * (int)gridDim.x;
+    return tile * TR + (it % spt) * STEP + wib * RPW + sub;
+  };
 
-  double2 ib[NC], rb[NC], ra[NC], cf[NC], th[NC], dot[NC];
-#pragma unroll
-  for (int k = 0; k < NC; ++k) {
-    const int c0 = 2 * (g + G * k);
-    ib[k] = lz_scal2(a.s_inv_beta, c0, a.m);
-    rb[k] = lz_scal2(a.s_ratio_b, c0, a.m);
-    ra[k] = lz_scal2(a.s_ratio_a, c0, a.m);
-    cf[k] = lz_scal2(a.s_coef, c0, a.m);
-    th[k] = lz_scal2(a.s_theta, c0, a.m);
-    dot[k] = make_double2(0.0, 0.0);
+  // per-column scalars of this step live in shared memory (one 16-byte read per use instead of 20 live registers)
+  __shared__ double2 s_sc[4][FC_MAXCOLS / 2];   // [0] inv_beta | theta, [1] ratio_b, [2] ratio_a, [3] coef
+  for (int i = threadIdx.x; i < 4 * (FC_MAXCOLS / 2); i += THREADS) {
+    const int w = i / (FC_MAXCOLS / 2), pc = i % (FC_MAXCOLS / 2);
+    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta) : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : a.s_coef));
+    s_sc[w][pc] = lz_scal2(src, 2 * pc, a.m);
   }
-
-  for (int64_t rb0 = row_begin + (int64_t)wib * RPW; rb0 < row_end; rb0 += step) {
-    const int64_t row = rb0 + sub;
-    const bool valid = row < row_end;
-    double2 acc[NC];
+  __syncthreads();
+  double2 dot[NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) acc[k] = make_double2(0.0, 0.0);
-    lz_gather<G, NC>(a, row, valid, P, g, gmask, acc);
+  for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
+
+  // software pipeline over the CSR metadata: row pointers two iterations ahead, the first G (col, val) pairs one
+  // iteration ahead, so the vector gathers of an iteration never wait behind a pointer chase.  (Measured on B200: a
+  // deeper pipeline with L2 prefetch of the next iteration's rows costs more in registers/spills than it hides.)
+  int r_cur = row_of(0), r_nxt = row_of(1);
+  int p0_cur = 0, p1_cur = 0, p0_nxt = 0, p1_nxt = 0;
+  if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
+  if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
+  int j_cur = r_cur < n ? r_cur : 0;
+  double a_cur = 0.0;
+  if (g < p1_cur - p0_cur) { j_cur = a.col[p0_cur + g]; a_cur = a.val[p0_cur + g]; }
+
+  for (int it = 0; it < niter; ++it) {
+    const int row = r_cur;
+    const bool valid = row < n;
+    const int r_fut = row_of(it + 2);
+    int p0_fut = 0, p1_fut = 0;
+    if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
+    int j_nxt = r_nxt < n ? r_nxt : 0;
+    double a_nxt = 0.0;
+    if (g < p1_nxt - p0_nxt) { j_nxt = a.col[p0_nxt + g]; a_nxt = a.val[p0_nxt + g]; }
+
+    double2 acc[NC], uo[NC], pv[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      acc[k] = make_double2(0.0, 0.0);
+      uo[k] = make_double2(0.0, 0.0);
+      pv[k] = make_double2(0.0, 0.0);
+    }
+    const int64_t ro = (int64_t)row * a.ld;
     if (valid) {
-      const int64_t ro = row * a.ld;
+      if constexpr (MODE != LZ_PLAIN) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const int pc = g + G * k;
+          if (pc < P) {
+            uo[k] = ldg2(a.U + ro + 2 * pc);
+            if constexpr (MODE == LZ_P1 || MODE == LZ_P2)
+              if (a.prev != nullptr) pv[k] = ldg2(a.prev + ro + 2 * pc);
+          }
+        }
+      }
+    }
+    lz_gather<G, NC>(a, valid ? row : 0, p0_cur, p1_cur, j_cur, a_cur, P, g, gmask, acc);
+    if (valid) {
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         const int pc = g + G * k;
@@ -167,33 +214,34 @@ __global__ void __launch_bounds__(THREADS) k_lz_spmm(LzArgs a) {
           if constexpr (MODE == LZ_PLAIN) {
             stg2(a.out + off, acc[k]);
           } else if constexpr (MODE == LZ_RES) {
-            const double2 xo = ldg2(a.U + off);
+            const double2 th = s_sc[0][pc], cf = s_sc[3][pc];
             double2 t;
-            t.x = __fma_rn(-th[k].x, xo.x, acc[k].x);
-            t.y = __fma_rn(-th[k].y, xo.y, acc[k].y);
+            t.x = __fma_rn(-th.x, uo[k].x, acc[k].x);
+            t.y = __fma_rn(-th.y, uo[k].y, acc[k].y);
             stg2(a.out + off, t);
             dot[k].x = fma(t.x, t.x, dot[k].x);
             dot[k].y = fma(t.y, t.y, dot[k].y);
-            if (a.Q != nullptr) stg2(a.Q + off, make_double2(cf[k].x * xo.x, cf[k].y * xo.y));
+            if (a.Q != nullptr) stg2(a.Q + off, make_double2(cf.x * uo[k].x, cf.y * uo[k].y));
           } else {
-            const double2 uo = ldg2(a.U + off);
-            const double2 pv = (a.prev != nullptr) ? ldg2(a.prev + off) : make_double2(0.0, 0.0);
-            const double2 t = lz_t(acc[k], ib[k], rb[k], pv);
+            const double2 t = lz_t(acc[k], s_sc[0][pc], s_sc[1][pc], pv[k]);
             if constexpr (MODE == LZ_P1) {
               stg2(a.out + off, t);
-              dot[k].x = fma(uo.x, t.x, dot[k].x);
-              dot[k].y = fma(uo.y, t.y, dot[k].y);
+              dot[k].x = fma(uo[k].x, t.x, dot[k].x);
+              dot[k].y = fma(uo[k].y, t.y, dot[k].y);
             } else {
-              stg2(a.out + off, lz_next(t, ra[k], uo));
+              const double2 cf = s_sc[3][pc];
+              stg2(a.out + off, lz_next(t, s_sc[2][pc], uo[k]));
               double2 q = ldg2(a.Q + off);
-              q.x = fma(cf[k].x, uo.x, q.x);
-              q.y = fma(cf[k].y, uo.y, q.y);
+              q.x = fma(cf.x, uo[k].x, q.x);
+              q.y = fma(cf.y, uo[k].y, q.y);
               stg2(a.Q + off, q);
             }
           }
         }
       }
     }
+    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; j_cur = j_nxt; a_cur = a_nxt;
+    r_nxt = r_fut; p0_nxt = p0_fut; p1_nxt = p1_fut;
   }
 
   if constexpr (MODE == LZ_P1 || MODE == LZ_RES) {

@@ -37,7 +37,7 @@ class Stats(C.Structure):
                 ("ms_allreduce", C.c_double), ("ms_spmm_sampled", C.c_double), ("spmm_sampled", C.c_int64),
                 ("bytes_spmm_alg", C.c_double), ("node_iters", C.c_int64 * 128),
                 ("lz_steps_p1", C.c_int64), ("lz_steps_p2", C.c_int64), ("ms_lz_p1", C.c_double), ("ms_lz_p2", C.c_double),
-                ("ms_kern", C.c_double * 8), ("n_kern", C.c_int64 * 8), ("bytes_kern", C.c_double * 8)]
+                ("ms_kern", C.c_double * 8), ("n_kern", C.c_int64 * 8), ("bytes_kern", C.c_double * 8), ("ms_dev_run", C.c_double)]
 
     def as_dict(self):
         arrays = ("node_iters", "ms_kern", "n_kern", "bytes_kern")

@@ -83,6 +83,7 @@ typedef struct {
   double  ms_kern[8];
   int64_t n_kern[8];
   double  bytes_kern[8];
+  double  ms_dev_run;                 /* CUDA-event time (library stream) of the feastcuda_run_interval calls    */
 } feastcuda_stats;
 
 enum { FEASTCUDA_KERN_SPMM_Z = 0,   /* complex shifted SpMM (BiCGStab)            */

@@ -364,14 +364,46 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
                           loop_count, stats)
 
 
-def time_mslanczos_sample(A, m, steps, seed=0):
-    """CPU-baseline sample: `steps` lock-step Lanczos steps (pass 1 arithmetic) on m real columns; returns seconds."""
+_POOL_A = None
+
+
+def _sample_worker(args):
+    """One worker = one slice of columns, like one thread of the reference's threaded backend (parallel/feast_parallel.jl:586)."""
+    m, steps, seed = args
+    A = _POOL_A
     n = A.shape[0]
     rng = np.random.default_rng(seed)
     b = rng.standard_normal((n, m))
+    Z = np.array([0.5 + 0.5j])
     t0 = time.perf_counter()
-    lanczos_pass1(A, b, np.array([0.5 + 0.5j]), steps, 0.0)
-    return time.perf_counter() - t0
+    alpha, beta, k, _ = lanczos_pass1(A, b, Z, steps, 0.0)
+    t1 = time.perf_counter()
+    coef = np.ones((k, m))
+    lanczos_pass2(A, b, alpha, beta, coef, np.zeros((n, m)))
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def time_mslanczos_sample(A, m, steps, workers=1, seed=0):
+    """CPU-baseline sample: `steps` lock-step Lanczos steps of pass 1 and of pass 2 on m real columns, the columns split
+    over `workers` processes.  Returns (seconds pass 1, seconds pass 2) = wall time of the slowest worker."""
+    global _POOL_A
+    _POOL_A = A
+    workers = max(1, min(workers, m))
+    base, rem = divmod(m, workers)
+    jobs = [(base + (1 if w < rem else 0), steps, seed + w) for w in range(workers)]
+    if workers == 1:
+        out = [_sample_worker(jobs[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            t0 = time.perf_counter()
+            out = pool.map(_sample_worker, jobs)
+            wall = time.perf_counter() - t0
+        tot = max(a + b for a, b in out)
+        scale = wall / tot if tot > 0 else 1.0      # include pool overheads in the reported wall time
+        out = [(a * scale, b * scale) for a, b in out]
+    return max(o[0] for o in out), max(o[1] for o in out)
 
 
 def time_bicgstab_sample(A, z, m, iters, seed=0):

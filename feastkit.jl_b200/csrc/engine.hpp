@@ -113,7 +113,6 @@ struct feastcuda_handle_s {
   int lz_threads = 512;     // CTA size of the Lanczos SpMM (512 or 1024)
   int lz_ctas_per_sm = 2;   // persistent CTAs per SM of the Lanczos SpMM (contiguous row chunks keep the band in L1)
   int lz_tile_rows = 64;    // rows per round-robin tile of the Lanczos SpMM
-  int lz_far_w = 0;         // > 0: stored entries further than this from the diagonal bypass L1 allocation
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   std::vector<cudaEvent_t> ev_pool;   // reusable event pairs for sampled kernel timings

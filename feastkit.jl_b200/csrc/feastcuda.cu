@@ -514,6 +514,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
                        int ne, double target, int kmax, int check_every, MslOut& out) {
   FC_REQUIRE(h->kind == OP_SPARSE && !h->dev_complex && !h->has_b, "multi-shift Lanczos needs a real standard sparse problem");
   FC_REQUIRE((c0 & 1) == 0, "column slices must start at an even column");
+  FC_REQUIRE((double)h->ws_n * (double)lz_ld(h) < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   const int64_t n = h->ws_n;
   const int64_t ldz = h->ws_ld, ld = lz_ld(h);
   kmax = std::max(1, std::min(kmax, 16384));
@@ -578,7 +579,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.n = n; a.m = nc; a.ld = ld;
     a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
     a.U = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
-    a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w; a.tile_rows = h->lz_tile_rows;
+    a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
     int g = 0;
     const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
     lz_launch<LZ_RES>(h, a, &g);
@@ -605,7 +606,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
       a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1);
       a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
-      a.partial = part; a.pstride = FC_MAXCOLS; a.far_w = h->lz_far_w; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
+      a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
       const bool smp = (j % 16) == 3;
       int g = 0;
       int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
@@ -693,7 +694,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1); a.Q = QA;
     a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
     a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
-    a.far_w = h->lz_far_w; a.tile_rows = h->lz_tile_rows;
+    a.tile_rows = h->lz_tile_rows;
     const bool smp = (j % 16) == 3;
     int g = 0;
     const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
@@ -1204,7 +1205,6 @@ int feastcuda_create(feastcuda_handle* out, int device) {
   FC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   if (const char* e = getenv("FEASTCUDA_LZ_THREADS")) h->lz_threads = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_CTAS")) h->lz_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
-  if (const char* e = getenv("FEASTCUDA_LZ_FARW")) h->lz_far_w = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_TILE")) h->lz_tile_rows = std::max(1, atoi(e));
   *out = h;
   FC_CATCH

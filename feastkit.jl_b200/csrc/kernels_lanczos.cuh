@@ -45,52 +45,43 @@ struct LzArgs {
   const double* s_theta; // LZ_RES
   double* partial;       // [gridDim.x][pstride]
   int pstride;
-  int far_w;             // > 0: entries with |col - row| > far_w are loaded without L1 allocation
   int tile_rows;         // rows per round-robin tile (rounded to the CTA's rows-per-iteration)
   const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
 };
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __forceinline__ double2 ldg2_stream(const double* p) {
-  double2 v;
-  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
 // acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries [p0, p1) of `row`, in CSR order.
-// (myj, mya): the group's first G entries, already fetched by the caller one iteration ahead.
+// (myo, mya): the group's first G entries, already fetched by the caller one iteration ahead; myo is the ELEMENT offset
+// col*ld of the gathered row (32-bit: the host guarantees n*ld < 2^32), so an address is one IMAD.WIDE from the lane's
+// base pointer Ul[k] = U + 2*(g + G k).  Padding slots of the last batch gather the lane's own row with weight 0 and lanes
+// beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
 template <int G, int NC>
-__device__ __forceinline__ void lz_gather(const LzArgs& a, int row, int p0, int p1, int myj, double mya, int P, int g,
-                                          unsigned gmask, double2 (&acc)[NC]) {
+__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int p0, int p1, unsigned myo, double mya, int g,
+                                          unsigned gmask, const double* const (&Ul)[NC], double2 (&acc)[NC]) {
   constexpr int UN = (G >= 4) ? 4 : G;
+  const unsigned ldu = (unsigned)a.ld;
   for (int pb = p0; pb < p1; pb += G) {
     const int cnt = min(G, p1 - pb);
     if (pb != p0) {
-      myj = row;
+      myo = row_eo;
       mya = 0.0;
-      if (g < cnt) { myj = a.col[pb + g]; mya = a.val[pb + g]; }
+      if (g < cnt) { myo = (unsigned)a.col[pb + g] * ldu; mya = a.val[pb + g]; }
     }
     for (int t = 0; t < cnt; t += UN) {
-      int jj[UN];
+      unsigned eo[UN];
       double aa[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        jj[u] = __shfl_sync(gmask, myj, t + u, G);
+        eo[u] = __shfl_sync(gmask, myo, t + u, G);
         aa[u] = __shfl_sync(gmask, mya, t + u, G);
       }
       double2 xv[UN][NC];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const double* xr = a.U + (int64_t)jj[u] * a.ld;
-        const bool far = a.far_w > 0 && abs(jj[u] - row) > a.far_w;
+      for (int u = 0; u < UN; ++u)
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const int pc = g + G * k;
-          if (pc < P) xv[u][k] = far ? ldg2_stream(xr + 2 * pc) : ldg2(xr + 2 * pc);
-          else xv[u][k] = make_double2(0.0, 0.0);
-        }
-      }
+        for (int k = 0; k < NC; ++k) xv[u][k] = ldg2(Ul[k] + eo[u]);
 #pragma unroll
       for (int u = 0; u < UN; ++u)
 #pragma unroll
@@ -144,10 +135,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   const int ntiles = (n + TR - 1) / TR;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int niter = my_tiles * spt;
-  auto row_of = [&](int it) -> int {
-    if (it >= niter) return n;
-    const int tile = (int)blockIdx.x + (it / spt) * (int)gridDim.x;
-    return tile * TR + (it % spt) * STEP + wib * RPW + sub;
+  // iteration -> row, advanced incrementally (no integer divisions in the loop): `base_f` is the first row of the CTA's
+  // iteration `it_f`, the furthest one the metadata pipeline has looked at
+  const int lane_row = wib * RPW + sub;
+  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR;
+  auto next_row = [&]() -> int {
+    const int r = (it_f < niter) ? base_f + lane_row : n;
+    ++it_f;
+    if (++s_f == spt) { s_f = 0; base_f += ((int)gridDim.x - 1) * TR + STEP; }
+    else base_f += STEP;
+    return r < n ? r : n;
   };
 
   // per-column scalars of this step live in shared memory (one 16-byte read per use instead of 20 live registers)
@@ -162,26 +159,30 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
 #pragma unroll
   for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
 
-  // software pipeline over the CSR metadata: row pointers two iterations ahead, the first G (col, val) pairs one
+  // software pipeline over the CSR metadata: row pointers two iterations ahead, the first G (offset, val) pairs one
   // iteration ahead, so the vector gathers of an iteration never wait behind a pointer chase.  (Measured on B200: a
   // deeper pipeline with L2 prefetch of the next iteration's rows costs more in registers/spills than it hides.)
-  int r_cur = row_of(0), r_nxt = row_of(1);
+  const unsigned ldu = (unsigned)a.ld;
+  const double* Ul[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) Ul[k] = a.U + 2 * min(g + G * k, P - 1);
+  int r_cur = next_row(), r_nxt = next_row();
   int p0_cur = 0, p1_cur = 0, p0_nxt = 0, p1_nxt = 0;
   if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
   if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
-  int j_cur = r_cur < n ? r_cur : 0;
+  unsigned o_cur = (r_cur < n ? (unsigned)r_cur : 0u) * ldu;
   double a_cur = 0.0;
-  if (g < p1_cur - p0_cur) { j_cur = a.col[p0_cur + g]; a_cur = a.val[p0_cur + g]; }
+  if (g < p1_cur - p0_cur) { o_cur = (unsigned)a.col[p0_cur + g] * ldu; a_cur = a.val[p0_cur + g]; }
 
   for (int it = 0; it < niter; ++it) {
     const int row = r_cur;
     const bool valid = row < n;
-    const int r_fut = row_of(it + 2);
+    const int r_fut = next_row();
     int p0_fut = 0, p1_fut = 0;
     if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
-    int j_nxt = r_nxt < n ? r_nxt : 0;
+    unsigned o_nxt = (r_nxt < n ? (unsigned)r_nxt : 0u) * ldu;
     double a_nxt = 0.0;
-    if (g < p1_nxt - p0_nxt) { j_nxt = a.col[p0_nxt + g]; a_nxt = a.val[p0_nxt + g]; }
+    if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = a.val[p0_nxt + g]; }
 
     double2 acc[NC], uo[NC], pv[NC];
 #pragma unroll
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
         }
       }
     }
-    lz_gather<G, NC>(a, valid ? row : 0, p0_cur, p1_cur, j_cur, a_cur, P, g, gmask, acc);
+    lz_gather<G, NC>(a, (valid ? (unsigned)row : 0u) * ldu, p0_cur, p1_cur, o_cur, a_cur, g, gmask, Ul, acc);
     if (valid) {
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
         }
       }
     }
-    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; j_cur = j_nxt; a_cur = a_nxt;
+    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; o_cur = o_nxt; a_cur = a_nxt;
     r_nxt = r_fut; p0_nxt = p0_fut; p1_nxt = p1_fut;
   }
 

@@ -37,7 +37,7 @@ UNIT = "eigenpairs/s"
 # passes each); the CPU arms extrapolate their bounded sample with it.  The live GPU run reports its own count.
 C3_LANCZOS_STEPS = 1683
 C3_M = 35
-SOLVER_KW = dict(solver="mslanczos", inner_rel=1e-3, ritz_guess=True, solver_maxiter=3000, check_every=16, filter="true")
+SOLVER_KW = dict(solver="mslanczos", inner_rel=1e-3, ritz_guess=True, solver_maxiter=3000, check_every=16, filter="true", adaptive=True)
 
 
 def laplacian_3d(N):

@@ -604,7 +604,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       memset(&a, 0, sizeof(a));
       a.n = n; a.m = nc; a.ld = ld;
       a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
-      a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1);
+      a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1);
       a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
       a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
       const bool smp = (j % 16) == 3;
@@ -691,7 +691,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     memset(&a, 0, sizeof(a));
     a.n = n; a.m = nc; a.ld = ld;
     a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
-    a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : nullptr; a.out = cur(j + 1); a.Q = QA;
+    a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1); a.Q = QA;
     a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
     a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
     a.tile_rows = h->lz_tile_rows;
@@ -1011,6 +1011,11 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       const bool first = !(o.ritz_guess && have_ritz);
       double target = (first && o.inner_rel0 > 0) ? o.inner_rel0 : o.inner_rel;
       if (!(target > 0)) target = tol;
+      if (o.adaptive && !first && std::isfinite(eps_val) && eps_val > 0) {
+        // the sweep contracts the eigen-residual by roughly its inner target: when the tolerance is within reach, aim at it
+        const double t = 0.1 * eps_tol / eps_val;
+        if (t >= 1e-5) target = std::min(0.1, t);
+      }
       const int kmax = (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter;
       if (nc > 0) {
         MslOut mo;

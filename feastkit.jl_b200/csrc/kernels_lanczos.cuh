@@ -37,7 +37,7 @@ struct LzArgs {
   int64_t ld;            // row stride in doubles (even)
   const int* ptr; const int* col; const double* val;
   const double* U;       // gathered operand
-  const double* prev;    // own-row operand u_{j-1}; nullptr at j = 0
+  const double* prev;    // own-row operand u_{j-1}; at j = 0 any finite block (the host passes U; ratio_b is 0 there)
   double* out;           // own-row result (may alias prev)
   double* Q;             // accumulator (LZ_P2, LZ_RES)
   const double* s_inv_beta; const double* s_ratio_b; const double* s_ratio_a;   // per-column scalars of this step
@@ -164,8 +164,17 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   // deeper pipeline with L2 prefetch of the next iteration's rows costs more in registers/spills than it hides.)
   const unsigned ldu = (unsigned)a.ld;
   const double* Ul[NC];
+  const double* Pl[NC];   // prev: never null (the host passes U with ratio_b = 0 at j = 0)
+  double* Ol[NC];
+  double* Ql[NC];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) Ul[k] = a.U + 2 * min(g + G * k, P - 1);
+  for (int k = 0; k < NC; ++k) {
+    const int pcl = 2 * min(g + G * k, P - 1);
+    Ul[k] = a.U + pcl;
+    Pl[k] = a.prev + pcl;
+    Ol[k] = a.out + pcl;
+    Ql[k] = a.Q + pcl;
+  }
   int r_cur = next_row(), r_nxt = next_row();
   int p0_cur = 0, p1_cur = 0, p0_nxt = 0, p1_nxt = 0;
   if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
@@ -184,59 +193,44 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
     double a_nxt = 0.0;
     if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = a.val[p0_nxt + g]; }
 
+    // own-row operands first (independent of the gather); invalid rows and inactive lanes read valid dummies
+    const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
     double2 acc[NC], uo[NC], pv[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       acc[k] = make_double2(0.0, 0.0);
-      uo[k] = make_double2(0.0, 0.0);
-      pv[k] = make_double2(0.0, 0.0);
+      if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
+      if constexpr (MODE == LZ_P1 || MODE == LZ_P2) pv[k] = ldg2(Pl[k] + eo_own);
     }
-    const int64_t ro = (int64_t)row * a.ld;
-    if (valid) {
-      if constexpr (MODE != LZ_PLAIN) {
+    lz_gather<G, NC>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, g, gmask, Ul, acc);
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const int pc = g + G * k;
-          if (pc < P) {
-            uo[k] = ldg2(a.U + ro + 2 * pc);
-            if constexpr (MODE == LZ_P1 || MODE == LZ_P2)
-              if (a.prev != nullptr) pv[k] = ldg2(a.prev + ro + 2 * pc);
-          }
-        }
-      }
-    }
-    lz_gather<G, NC>(a, (valid ? (unsigned)row : 0u) * ldu, p0_cur, p1_cur, o_cur, a_cur, g, gmask, Ul, acc);
-    if (valid) {
-#pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int pc = g + G * k;
-        if (pc < P) {
-          const int64_t off = ro + 2 * pc;
-          if constexpr (MODE == LZ_PLAIN) {
-            stg2(a.out + off, acc[k]);
-          } else if constexpr (MODE == LZ_RES) {
-            const double2 th = s_sc[0][pc], cf = s_sc[3][pc];
-            double2 t;
-            t.x = __fma_rn(-th.x, uo[k].x, acc[k].x);
-            t.y = __fma_rn(-th.y, uo[k].y, acc[k].y);
-            stg2(a.out + off, t);
-            dot[k].x = fma(t.x, t.x, dot[k].x);
-            dot[k].y = fma(t.y, t.y, dot[k].y);
-            if (a.Q != nullptr) stg2(a.Q + off, make_double2(cf.x * uo[k].x, cf.y * uo[k].y));
+    for (int k = 0; k < NC; ++k) {
+      const int pc = g + G * k;
+      if (valid && pc < P) {
+        if constexpr (MODE == LZ_PLAIN) {
+          stg2(Ol[k] + eo_own, acc[k]);
+        } else if constexpr (MODE == LZ_RES) {
+          const double2 th = s_sc[0][pc], cf = s_sc[3][pc];
+          double2 t;
+          t.x = __fma_rn(-th.x, uo[k].x, acc[k].x);
+          t.y = __fma_rn(-th.y, uo[k].y, acc[k].y);
+          stg2(Ol[k] + eo_own, t);
+          dot[k].x = fma(t.x, t.x, dot[k].x);
+          dot[k].y = fma(t.y, t.y, dot[k].y);
+          if (a.Q != nullptr) stg2(Ql[k] + eo_own, make_double2(cf.x * uo[k].x, cf.y * uo[k].y));
+        } else {
+          const double2 t = lz_t(acc[k], s_sc[0][pc], s_sc[1][pc], pv[k]);
+          if constexpr (MODE == LZ_P1) {
+            stg2(Ol[k] + eo_own, t);
+            dot[k].x = fma(uo[k].x, t.x, dot[k].x);
+            dot[k].y = fma(uo[k].y, t.y, dot[k].y);
           } else {
-            const double2 t = lz_t(acc[k], s_sc[0][pc], s_sc[1][pc], pv[k]);
-            if constexpr (MODE == LZ_P1) {
-              stg2(a.out + off, t);
-              dot[k].x = fma(uo[k].x, t.x, dot[k].x);
-              dot[k].y = fma(uo[k].y, t.y, dot[k].y);
-            } else {
-              const double2 cf = s_sc[3][pc];
-              stg2(a.out + off, lz_next(t, s_sc[2][pc], uo[k]));
-              double2 q = ldg2(a.Q + off);
-              q.x = fma(cf.x, uo[k].x, q.x);
-              q.y = fma(cf.y, uo[k].y, q.y);
-              stg2(a.Q + off, q);
-            }
+            const double2 cf = s_sc[3][pc];
+            stg2(Ol[k] + eo_own, lz_next(t, s_sc[2][pc], uo[k]));
+            double2 q = ldg2(Ql[k] + eo_own);
+            q.x = fma(cf.x, uo[k].x, q.x);
+            q.y = fma(cf.y, uo[k].y, q.y);
+            stg2(Ql[k] + eo_own, q);
           }
         }
       }

@@ -235,7 +235,7 @@ class Engine:
     @staticmethod
     def make_opts(solver="bicgstab", solver_tol=0.0, solver_maxiter=500, solver_restart=3, inner_rel=0.0, ritz_guess=False,
                   filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False, inner_rel0=0.0, maxiter0=0,
-                  keep_going=False):
+                  keep_going=False, adaptive=False):
         o = SolverOpts()
         o.solver = {"direct": SOLVER_DIRECT, "bicgstab": SOLVER_BICGSTAB, "mslanczos": SOLVER_MSLANCZOS}[solver]
         o.tol = float(solver_tol)
@@ -251,6 +251,7 @@ class Engine:
         o.inner_rel0 = float(inner_rel0)
         o.maxiter0 = int(maxiter0)
         o.keep_going = int(bool(keep_going))
+        o.adaptive = int(bool(adaptive))
         return o
 
     def upload_subspace(self, M0, Q0=None):

@@ -61,8 +61,9 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
         # zero-guess / solve-to-tol / fail-with-info-5 behaviour (sparse/feast_sparse.jl:164-236,359-363)
         kw["ritz_guess"] = True
         kw["inner_rel"] = 1e-3
+        kw["adaptive"] = True
     kw["filter"] = "true"
-    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every", "inner_rel0", "maxiter0", "keep_going"):
+    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every", "inner_rel0", "maxiter0", "keep_going", "adaptive"):
         if k in extras:
             kw[k] = extras.pop(k)
     if extras:

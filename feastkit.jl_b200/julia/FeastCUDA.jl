@@ -1,0 +1,243 @@
+# FeastCUDA.jl -- the Julia host shim: FeastKit.jl's own method names, bodies replaced by `ccall`s into libfeastcuda.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: `julia` is absent from the build image and from the GPU box.  The file is kept
+# mechanical (one table of names -> one generic driver) so that its correctness follows from the C-ABI tests, which drive
+# the very same entry points through ctypes (feastkit.jl_b200/feastcuda/, tests/test_gpu_*.py).
+#
+# Usage inside FeastKit.jl (see INTEGRATION.md):   include("FeastCUDA.jl"); using .FeastCUDA
+# file:line citations are relative to FeastKit.jl/src.
+module FeastCUDA
+
+using LinearAlgebra, SparseArrays
+
+const libfeastcuda = get(ENV, "FEASTCUDA_LIB", joinpath(@__DIR__, "..", "lib", "libfeastcuda.so"))
+
+# ---- mirrors of include/feastcuda.h -------------------------------------------------------------------------------
+const FEASTCUDA_A, FEASTCUDA_B = Cint(0), Cint(1)
+const FEASTCUDA_CSC = Cint(1)
+const FEASTCUDA_SYM, FEASTCUDA_HERM, FEASTCUDA_GEN = Cint(0), Cint(1), Cint(2)
+const SOLVER_DIRECT, SOLVER_BICGSTAB, SOLVER_MSLANCZOS = Cint(0), Cint(1), Cint(2)
+const FILTER_REFERENCE, FILTER_TRUE = Cint(0), Cint(1)
+
+struct SolverOpts              # feastcuda_solver_opts (88 bytes, C layout)
+    solver::Cint
+    tol::Cdouble
+    maxiter::Cint
+    restart::Cint
+    inner_rel::Cdouble
+    ritz_guess::Cint
+    filter::Cint
+    shard::Cint
+    check_every::Cint
+    q0_real::Cint
+    x_real::Cint
+    inner_rel0::Cdouble
+    maxiter0::Cint
+    keep_going::Cint
+    adaptive::Cint
+    reserved::NTuple{3,Cint}
+end
+
+# FeastResult{T,VT} (core/feast_types.jl:85-98) -- same fields, arrays trimmed to M
+struct FeastResult{T<:Real,VT}
+    lambda::Vector{T}
+    q::Matrix{VT}
+    M::Int
+    res::Vector{T}
+    info::Int
+    epsout::T
+    loop::Int
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+end
+
+function check(rc::Cint, h::Ptr{Cvoid}=C_NULL)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:feastcuda_last_error, libfeastcuda), Cstring, (Ptr{Cvoid},), h))
+    rc == 1 ? throw(ArgumentError(msg)) : error("libfeastcuda status $rc: $msg")
+end
+
+const _handle = Ref{Union{Nothing,Handle}}(nothing)
+function handle()
+    if _handle[] === nothing
+        p = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:feastcuda_create, libfeastcuda), Cint, (Ptr{Ptr{Cvoid}}, Cint), p, parse(Cint, get(ENV, "LOCAL_RANK", "0"))))
+        h = Handle(p[])
+        finalizer(x -> ccall((:feastcuda_destroy, libfeastcuda), Cint, (Ptr{Cvoid},), x.ptr), h)
+        _handle[] = h
+    end
+    return _handle[].ptr
+end
+
+# ---- parameters / contours (core/feast_parameters.jl:7-18,41-386; core/feast_tools.jl:212-371) --------------------
+function feastinit!(fpm::Vector{Int})
+    length(fpm) >= 64 || throw(ArgumentError("fpm array must have at least 64 elements"))
+    check(ccall((:feastcuda_feastinit, libfeastcuda), Cint, (Ptr{Int64},), fpm))
+    return fpm
+end
+feastinit() = feastinit!(zeros(Int, 64))
+function feastdefault!(fpm::Vector{Int})
+    ccall((:feastcuda_feastdefault, libfeastcuda), Cint, (Ptr{Int64},), fpm) == 0 ||
+        throw(ArgumentError("Invalid fpm parameter"))
+    return fpm
+end
+function feast_contour(Emin::Real, Emax::Real, fpm::Vector{Int})
+    feastdefault!(fpm)
+    ne = fpm[2]
+    Zne = Vector{ComplexF64}(undef, ne); Wne = Vector{ComplexF64}(undef, ne)
+    check(ccall((:feastcuda_contour, libfeastcuda), Cint, (Cdouble, Cdouble, Ptr{Int64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                Emin, Emax, fpm, Zne, Wne))
+    return (Zne=Zne, Wne=Wne)
+end
+function feast_gcontour(Emid::Number, r::Real, fpm::Vector{Int})
+    feastdefault!(fpm)
+    ne = fpm[8]
+    Zne = Vector{ComplexF64}(undef, ne); Wne = Vector{ComplexF64}(undef, ne)
+    z = ComplexF64(Emid)
+    check(ccall((:feastcuda_gcontour, libfeastcuda), Cint, (Cdouble, Cdouble, Cdouble, Ptr{Int64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                real(z), imag(z), r, fpm, Zne, Wne))
+    return (Zne=Zne, Wne=Wne)
+end
+
+# ---- operators: SparseMatrixCSC{Tv,Int} is CSC, 1-based Int64 -> passed as is (fmt = CSC, index_base = 1) ----------
+function set_sparse!(h, which::Cint, A::SparseMatrixCSC{Float64,Int}, structure::Cint)
+    GC.@preserve A check(ccall((:feastcuda_set_csr_d, libfeastcuda), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Cint, Cint, Cint),
+        h, which, size(A, 1), nnz(A), A.colptr, A.rowval, A.nzval, 1, FEASTCUDA_CSC, structure), h)
+end
+function set_sparse!(h, which::Cint, A::SparseMatrixCSC{ComplexF64,Int}, structure::Cint)
+    GC.@preserve A check(ccall((:feastcuda_set_csr_z, libfeastcuda), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Cint, Cint, Cint),
+        h, which, size(A, 1), nnz(A), A.colptr, A.rowval, A.nzval, 1, FEASTCUDA_CSC, structure), h)
+end
+function set_dense!(h, which::Cint, A::Matrix{Float64}, structure::Cint)
+    GC.@preserve A check(ccall((:feastcuda_set_dense_d, libfeastcuda), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Int64, Cint),
+        h, which, size(A, 1), A, stride(A, 2), structure), h)
+end
+function set_dense!(h, which::Cint, A::Matrix{ComplexF64}, structure::Cint)
+    GC.@preserve A check(ccall((:feastcuda_set_dense_z, libfeastcuda), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{ComplexF64}, Int64, Cint),
+        h, which, size(A, 1), A, stride(A, 2), structure), h)
+end
+function set_band!(h, which::Cint, AB::Matrix{T}, k::Int, structure::Cint) where {T<:Union{Float64,ComplexF64}}
+    sym = T === Float64 ? :feastcuda_set_band_d : :feastcuda_set_band_z
+    GC.@preserve AB check(ccall((sym, libfeastcuda), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{T}, Int64, Cint),
+        h, which, size(AB, 2), k, AB, size(AB, 1), structure), h)
+end
+
+# ---- the generic interval driver: every Hermitian-family name below lands here -------------------------------------
+# replaces _feast_dense_complex_hermitian (dense/feast_dense.jl:78-351), _feast_sparse_hermitian
+# (sparse/feast_sparse.jl:246-499) and _feast_banded_complex_hermitian (banded/feast_banded.jl:561-823)
+function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{Int}, ::Type{VT};
+                         Zne=nothing, Wne=nothing, solver::Symbol=:direct, solver_tol::Real=0.0, solver_maxiter::Int=500,
+                         solver_restart::Int=30, sparse::Bool=false) where {VT}
+    feastdefault!(fpm)
+    # check_feast_srci_input (core/feast_aux.jl:369-399): thrown before any device call, exactly as the reference does
+    N > 0 || throw(ArgumentError("Matrix size N must be positive"))
+    0 < M0 <= N || throw(ArgumentError("Number of eigenvalues M0 must be between 1 and N"))
+    Emin < Emax || throw(ArgumentError("Search interval [Emin, Emax] must be valid"))
+    solver_choice = solver == :iterative ? :gmres : solver
+    solver_choice in (:direct, :gmres, :bicgstab, :mslanczos) ||
+        throw(ArgumentError("Unsupported solver option '$solver'. Use :direct, :gmres, or :iterative."))
+    h = handle()
+    setA!(h)
+    setB! === nothing ? check(ccall((:feastcuda_clear_b, libfeastcuda), Cint, (Ptr{Cvoid},), h), h) : setB!(h)
+    if Zne === nothing
+        c = feast_contour(Emin, Emax, fpm); Zne, Wne = c.Zne, c.Wne
+    end
+    real_result = VT <: Real
+    eng_solver = sparse ? (solver_choice == :bicgstab ? SOLVER_BICGSTAB : SOLVER_MSLANCZOS) :
+                          (solver_choice == :direct ? SOLVER_DIRECT : SOLVER_BICGSTAB)
+    opts = Ref(SolverOpts(eng_solver, solver_tol, solver_maxiter, solver_restart == 30 ? 3 : solver_restart,
+                          sparse ? 1e-3 : 0.0, sparse ? 1 : 0, FILTER_TRUE, 0, 16, 0, real_result ? 1 : 0, 0.0, 0, 0, sparse ? 1 : 0, (Cint(0), Cint(0), Cint(0))))
+    lambda = zeros(Float64, M0); res = zeros(Float64, M0); X = zeros(VT, N, M0)
+    M = Ref{Int64}(0); info = Ref{Int64}(0); loop = Ref{Int64}(0); epsout = Ref{Float64}(0.0)
+    GC.@preserve fpm Zne Wne lambda res X begin
+        check(ccall((:feastcuda_solve_interval, libfeastcuda), Cint,
+            (Ptr{Cvoid}, Cdouble, Cdouble, Int64, Ptr{Int64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Ptr{Cvoid}, Ref{SolverOpts},
+             Ptr{Float64}, Ptr{VT}, Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Float64}, Ref{Int64}),
+            h, Emin, Emax, M0, fpm, Zne, Wne, length(Zne), C_NULL, opts, lambda, X, res, M, info, epsout, loop), h)
+    end
+    m = Int(M[])
+    return FeastResult{Float64,VT}(lambda[1:m], X[:, 1:m], m, res[1:m], Int(info[]), epsout[], Int(loop[]))
+end
+
+# ---- reference names (one line each; `x` variants add the contour) --------------------------------------------------
+# sparse/feast_sparse.jl:1516-1529, 713-731, 759-788, 815-831
+feast_scsrev!(A::SparseMatrixCSC{<:Real}, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_sparse!(h, FEASTCUDA_A, SparseMatrixCSC{Float64,Int}(A), FEASTCUDA_SYM), nothing, size(A, 1), Emin, Emax, M0, fpm, Float64; sparse=true, kw...)
+feast_scsrgv!(A::SparseMatrixCSC{<:Real}, B::SparseMatrixCSC{<:Real}, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_sparse!(h, FEASTCUDA_A, SparseMatrixCSC{Float64,Int}(A), FEASTCUDA_SYM),
+                    h -> set_sparse!(h, FEASTCUDA_B, SparseMatrixCSC{Float64,Int}(B), FEASTCUDA_SYM), size(A, 1), Emin, Emax, M0, fpm, Float64; sparse=true, kw...)
+function feast_hcsrev!(A::SparseMatrixCSC{<:Complex}, Emin, Emax, M0, fpm; kw...)
+    ishermitian(A) || throw(ArgumentError("Matrix A must be Hermitian"))
+    _solve_interval(h -> set_sparse!(h, FEASTCUDA_A, SparseMatrixCSC{ComplexF64,Int}(A), FEASTCUDA_HERM), nothing, size(A, 1), Emin, Emax, M0, fpm, ComplexF64; sparse=true, kw...)
+end
+function feast_hcsrgv!(A::SparseMatrixCSC{<:Complex}, B::SparseMatrixCSC{<:Complex}, Emin, Emax, M0, fpm; kw...)
+    ishermitian(A) || throw(ArgumentError("Matrix A must be Hermitian"))
+    ishermitian(B) || throw(ArgumentError("Matrix B must be Hermitian"))
+    _solve_interval(h -> set_sparse!(h, FEASTCUDA_A, SparseMatrixCSC{ComplexF64,Int}(A), FEASTCUDA_HERM),
+                    h -> set_sparse!(h, FEASTCUDA_B, SparseMatrixCSC{ComplexF64,Int}(B), FEASTCUDA_HERM), size(A, 1), Emin, Emax, M0, fpm, ComplexF64; sparse=true, kw...)
+end
+# dense/feast_dense.jl:776-797, 356-370, 390-400, 799-810
+feast_syev!(A::Matrix{<:Real}, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_dense!(h, FEASTCUDA_A, Matrix{Float64}(A), FEASTCUDA_SYM), nothing, size(A, 1), Emin, Emax, M0, fpm, Float64; kw...)
+feast_sygv!(A::Matrix{<:Real}, B::Matrix{<:Real}, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_dense!(h, FEASTCUDA_A, Matrix{Float64}(A), FEASTCUDA_SYM), h -> set_dense!(h, FEASTCUDA_B, Matrix{Float64}(B), FEASTCUDA_SYM),
+                    size(A, 1), Emin, Emax, M0, fpm, Float64; kw...)
+feast_heev!(A::Matrix{<:Complex}, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_dense!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), FEASTCUDA_HERM), nothing, size(A, 1), Emin, Emax, M0, fpm, ComplexF64; kw...)
+feast_hegv!(A::Matrix{<:Complex}, B::Matrix{<:Complex}, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_dense!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), FEASTCUDA_HERM), h -> set_dense!(h, FEASTCUDA_B, Matrix{ComplexF64}(B), FEASTCUDA_HERM),
+                    size(A, 1), Emin, Emax, M0, fpm, ComplexF64; kw...)
+# banded/feast_banded.jl:1410-1420, 9-186, 326-383, 385-421
+feast_sbev!(A::Matrix{<:Real}, kla::Int, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_band!(h, FEASTCUDA_A, Matrix{Float64}(A), kla, FEASTCUDA_SYM), nothing, size(A, 2), Emin, Emax, M0, fpm, Float64; kw...)
+feast_sbgv!(A::Matrix{<:Real}, B::Matrix{<:Real}, kla::Int, klb::Int, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_band!(h, FEASTCUDA_A, Matrix{Float64}(A), kla, FEASTCUDA_SYM), h -> set_band!(h, FEASTCUDA_B, Matrix{Float64}(B), klb, FEASTCUDA_SYM),
+                    size(A, 2), Emin, Emax, M0, fpm, Float64; kw...)
+feast_hbev!(A::Matrix{<:Complex}, kla::Int, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_band!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), kla, FEASTCUDA_HERM), nothing, size(A, 2), Emin, Emax, M0, fpm, ComplexF64; kw...)
+feast_hbgv!(A::Matrix{<:Complex}, B::Matrix{<:Complex}, kla::Int, klb::Int, Emin, Emax, M0, fpm; kw...) =
+    _solve_interval(h -> set_band!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), kla, FEASTCUDA_HERM), h -> set_band!(h, FEASTCUDA_B, Matrix{ComplexF64}(B), klb, FEASTCUDA_HERM),
+                    size(A, 2), Emin, Emax, M0, fpm, ComplexF64; kw...)
+
+# custom-contour `x` variants (sparse/feast_sparse.jl:751-757 etc.): same call with the caller's nodes
+for f in (:feast_scsrev, :feast_hcsrev, :feast_syev, :feast_heev)
+    @eval $(Symbol(f, "x!"))(A, Emin, Emax, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, Emin, Emax, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
+for f in (:feast_scsrgv, :feast_hcsrgv, :feast_sygv, :feast_hegv)
+    @eval $(Symbol(f, "x!"))(A, B, Emin, Emax, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, B, Emin, Emax, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
+
+# precision / parallel alias families (interfaces/feast_precision_aliases.jl:10-117,163-423,497-771): pure forwarding.
+# With `comm`/`use_threads` the reference picks an MPI/threads backend; here every rank of the job (one process per GPU,
+# feastcuda_nccl_init) takes part and the keyword is accepted and ignored.
+for (alias, target) in ((:dfeast_scsrev!, :feast_scsrev!), (:dfeast_scsrgv!, :feast_scsrgv!), (:zfeast_hcsrev!, :feast_hcsrev!),
+                        (:zfeast_hcsrgv!, :feast_hcsrgv!), (:dfeast_syev!, :feast_syev!), (:dfeast_sygv!, :feast_sygv!),
+                        (:zfeast_heev!, :feast_heev!), (:zfeast_hegv!, :feast_hegv!), (:dfeast_sbev!, :feast_sbev!),
+                        (:dfeast_sbgv!, :feast_sbgv!), (:zfeast_hbev!, :feast_hbev!), (:zfeast_hbgv!, :feast_hbgv!))
+    @eval $alias(args...; comm=nothing, use_threads=nothing, kw...) = $target(args...; kw...)
+    @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = $target(args...; kw...)
+end
+
+# high-level feast(A[,B],(Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272 (dispatch only)
+function feast(A::AbstractMatrix, interval::Tuple; M0::Int=10, fpm=nothing, kw...)
+    size(A, 1) == size(A, 2) || throw(ArgumentError("Matrix must be square"))
+    fpm = fpm === nothing ? feastinit() : fpm
+    M0 = min(M0, size(A, 1))
+    Emin, Emax = interval
+    if eltype(A) <: Complex
+        ishermitian(A) || throw(ArgumentError("Matrix must be Hermitian; use feast_general"))
+        return issparse(A) ? feast_hcsrev!(A, Emin, Emax, M0, fpm; kw...) : feast_heev!(Matrix(A), Emin, Emax, M0, fpm; kw...)
+    end
+    issymmetric(A) || throw(ArgumentError("Matrix must be symmetric; use feast_general"))
+    return issparse(A) ? feast_scsrev!(A, Emin, Emax, M0, fpm; kw...) : feast_syev!(Matrix(A), Emin, Emax, M0, fpm; kw...)
+end
+
+export feastinit, feastinit!, feastdefault!, feast_contour, feast_gcontour, feast, FeastResult,
+       feast_scsrev!, feast_scsrgv!, feast_hcsrev!, feast_hcsrgv!, feast_syev!, feast_sygv!, feast_heev!, feast_hegv!,
+       feast_sbev!, feast_sbgv!, feast_hbev!, feast_hbgv!
+
+end # module

@@ -296,7 +296,7 @@ def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None):
 
 
 def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0.0, inner_maxiter=500, ritz_guess=True,
-                        verbose=False, col_slices=None, allreduce=None):
+                        verbose=False, col_slices=None, allreduce=None, adaptive=False):
     """H-RR refinement loop (sparse/feast_sparse.jl:246-499 skeleton, B = I, real symmetric A, real Q0, filter rho = Re g)
     with the engine's multi-shift Lanczos inner solver.  col_slices(active) -> (c0, nc) emulates one rank of the
     column-sharded multi-GPU run; allreduce sums the accumulator over ranks."""
@@ -322,6 +322,10 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
         target = inner_rel0 if (first and inner_rel0 > 0) else inner_rel
         if not target > 0:
             target = tol_value
+        if adaptive and not first and math.isfinite(epsout) and epsout > 0:
+            t = 0.1 * eps_tol / epsout      # run_interval in csrc/feastcuda.cu: aim the sweep at the tolerance when in reach
+            if t >= 1e-5:
+                target = min(0.1, t)
         c0, nc = (0, active) if col_slices is None else col_slices(active)
         acc = np.zeros((N, active))
         if nc > 0:

@@ -227,7 +227,7 @@ def test_mslanczos_inexact_matches_cpu_port_loop_for_loop():
     Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
     Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
     r = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000)
-    rp = fp.feast_hrr_mslanczos(A.tocsr(), Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2000)
+    rp = fp.feast_hrr_mslanczos(A.tocsr(), Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2000, adaptive=True)
     ro = fo.feast_scsrev(A, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
     _check_pairs(r, ro, A)
     assert r.loop == rp.loop

@@ -1,13 +1,304 @@
-// Dense and banded operator paths -- placeholders until the batched LU kernels land.
+// Dense and banded operator paths of libfeastcuda: per-node LU factors cached on the device (the reference caches
+// `lu(z*B - A)` per node too, dense/feast_dense.jl:186-204, banded/feast_banded.jl:100-112), direct solves on the
+// engine's row-major right-hand-side blocks, operator application for the Rayleigh-Ritz stage.
 #include "dense_band.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+#include "kernels_band.cuh"
+#include "kernels_dense.cuh"
+
 namespace feastcuda {
-static void nyi() { throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "dense/banded operators: not built yet"); }
-void dense_set(feastcuda_handle_s*, int, int64_t, const double*, int64_t, bool, int) { nyi(); }
-void dense_prepare(feastcuda_handle_s*) { nyi(); }
-bool dense_node_solve(feastcuda_handle_s*, int, zc, int, const zd*, zd*) { nyi(); return false; }
-void dense_apply(feastcuda_handle_s*, int, int, const zd*, zd*) { nyi(); }
-void band_set(feastcuda_handle_s*, int, int64_t, int64_t, const double*, int64_t, bool, int) { nyi(); }
-void band_prepare(feastcuda_handle_s*) { nyi(); }
-bool band_node_solve(feastcuda_handle_s*, int, zc, int, const zd*, zd*) { nyi(); return false; }
-void band_apply(feastcuda_handle_s*, int, int, const zd*, zd*) { nyi(); }
+
+typedef feastcuda_handle_s H;
+
+static void launched(H* h) {
+  h->stats.kernel_launches++;
+  FC_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// dense
+// =====================================================================================================
+void dense_set(H* h, int which, int64_t n, const double* a, int64_t lda, bool cplx, int structure) {
+  (void)structure;
+  FC_REQUIRE(n > 0 && a != nullptr && lda >= n, "set_dense: bad arguments");
+  FC_REQUIRE(n < 2147483647 / 2, "set_dense: n too large");
+  FC_REQUIRE(which == FEASTCUDA_A || which == FEASTCUDA_B, "which must be A or B");
+  HostDense& d = (which == FEASTCUDA_A) ? h->denseA : h->denseB;
+  if (which == FEASTCUDA_B) FC_REQUIRE(h->kind == OP_DENSE && h->denseA.set && h->denseA.n == n, "set A (same size, dense) before B");
+  d.n = n;
+  d.cplx = cplx;
+  d.a.assign((size_t)2 * n * n, 0.0);   // always stored as interleaved complex, column-major, ld = n
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < n; ++i) {
+      const size_t o = 2 * ((size_t)j * n + i);
+      if (cplx) { d.a[o] = a[2 * ((size_t)j * lda + i)]; d.a[o + 1] = a[2 * ((size_t)j * lda + i) + 1]; }
+      else d.a[o] = a[(size_t)j * lda + i];
+    }
+  d.set = true;
+  if (which == FEASTCUDA_A) {
+    if (h->kind != OP_DENSE) { h->has_b = false; h->denseB.set = false; }
+    h->kind = OP_DENSE;
+    h->n = n;
+  } else {
+    h->has_b = true;
+  }
+  h->dense_uploaded = false;
+  release_factor_cache(h);
+}
+
+void dense_prepare(H* h) {
+  FC_REQUIRE(h->denseA.set, "operator A has not been set");
+  h->n = h->denseA.n;
+  if (h->dense_uploaded) return;
+  const size_t bytes = (size_t)h->n * h->n * sizeof(zd);
+  h->dDenseA.ensure(bytes);
+  FC_CUDA(cudaMemcpyAsync(h->dDenseA.p, h->denseA.a.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+  if (h->has_b) {
+    h->dDenseB.ensure(bytes);
+    FC_CUDA(cudaMemcpyAsync(h->dDenseB.p, h->denseB.a.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  FC_CUDA(cudaStreamSynchronize(h->stream));
+  h->dense_uploaded = true;
+  release_factor_cache(h);
+}
+
+static void zgemm(H* h, int M, int N, int K, const zd* A, int64_t ars, int64_t acs, const zd* B, int64_t brs, int64_t bcs, zd* C,
+                  int64_t crs, int64_t ccs, double alpha, int beta, int batch = 1, int64_t ab = 0, int64_t bb = 0, int64_t cb = 0) {
+  if (M <= 0 || N <= 0) return;
+  ZgemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.ars = ars; g.acs = acs; g.abatch = ab;
+  g.B = B; g.brs = brs; g.bcs = bcs; g.bbatch = bb;
+  g.C = C; g.crs = crs; g.ccs = ccs; g.cbatch = cb;
+  g.alpha = alpha; g.beta = beta;
+  dim3 grid((M + 63) / 64, (N + 63) / 64, batch);
+  k_zgemm_dmma<<<grid, 256, 0, h->stream>>>(g);
+  launched(h);
+}
+
+// factorise the shifted matrices of `nodes` (all of the same size) in one batch; results go to lu_cache/piv_cache
+static bool dense_factor(H* h, const std::vector<int>& nodes, const std::vector<zc>& shifts) {
+  const int nb = (int)nodes.size();
+  if (nb == 0) return true;
+  const int n = (int)h->n;
+  const int64_t nn = (int64_t)n * n;
+  int maxnode = 0;
+  for (int e : nodes) maxnode = std::max(maxnode, e);
+  if ((int)h->lu_cache.size() <= maxnode) {
+    h->lu_cache.resize(maxnode + 1);
+    h->piv_cache.resize(maxnode + 1);
+    h->lu_shift.resize(maxnode + 1, zc(NAN, NAN));
+  }
+  // nodes are factorised one after the other: the trailing GEMMs fill the GPU on their own; the single-CTA panels are
+  // the latency-bound part (next step: panels of different nodes on separate streams)
+  DBuf dz, dinfo;
+  dz.ensure(sizeof(zd));
+  dinfo.ensure(sizeof(int));
+  bool all_ok = true;
+  for (int q = 0; q < nb; ++q) {
+    const int e = nodes[q];
+    h->lu_cache[e].ensure((size_t)nn * sizeof(zd));
+    h->piv_cache[e].ensure((size_t)2 * n * sizeof(int));
+    zd* LU = h->lu_cache[e].as<zd>();
+    int* ipiv = h->piv_cache[e].as<int>();
+    int* perm = ipiv + n;
+    const zd zz = mk<double>(shifts[q].real(), shifts[q].imag());
+    FC_CUDA(cudaMemcpyAsync(dz.p, &zz, sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+    FC_CUDA(cudaMemsetAsync(dinfo.p, 0, sizeof(int), h->stream));
+    {
+      dim3 grid((unsigned)std::min<int64_t>((nn + 255) / 256, (int64_t)h->sms * 8), 1);
+      k_dense_shift<<<grid, 256, 0, h->stream>>>(n, h->dDenseA.as<zd>(), h->has_b ? h->dDenseB.as<zd>() : nullptr, dz.as<zd>(), LU, nn);
+      launched(h);
+    }
+    for (int k0 = 0; k0 < n; k0 += FC_LU_NB) {
+      const int nbw = std::min(FC_LU_NB, n - k0);
+      k_dense_panel_lu<<<1, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, dinfo.as<int>());
+      launched(h);
+      if (k0 > 0) {
+        k_dense_laswp<<<dim3((k0 + 255) / 256, 1), 256, 0, h->stream>>>(n, k0, nbw, 0, k0, LU, nn, ipiv);
+        launched(h);
+      }
+      const int rest = n - k0 - nbw;
+      if (rest > 0) {
+        k_dense_laswp<<<dim3((rest + 255) / 256, 1), 256, 0, h->stream>>>(n, k0, nbw, k0 + nbw, n, LU, nn, ipiv);
+        launched(h);
+        k_dense_trsm_u12<<<dim3((rest + 127) / 128, 1), 128, 0, h->stream>>>(n, k0, nbw, LU, nn);
+        launched(h);
+        // A22 -= L21 * U12   (all column-major, ld = n)
+        zgemm(h, rest, rest, nbw, LU + (k0 + nbw) + (int64_t)k0 * n, 1, n, LU + k0 + (int64_t)(k0 + nbw) * n, 1, n,
+              LU + (k0 + nbw) + (int64_t)(k0 + nbw) * n, 1, n, -1.0, 1);
+      }
+    }
+    k_dense_piv_to_perm<<<1, 32, 0, h->stream>>>(n, ipiv, perm);
+    launched(h);
+    int info = 0;
+    FC_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FC_CUDA(cudaStreamSynchronize(h->stream));
+    if (info != 0) { all_ok = false; h->lu_shift[e] = zc(NAN, NAN); }
+    else h->lu_shift[e] = shifts[q];
+  }
+  dz.release();
+  dinfo.release();
+  return all_ok;
+}
+
+bool dense_node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X) {
+  const int n = (int)h->n;
+  const int64_t ld = h->ws_ld;
+  if ((int)h->lu_cache.size() <= node || !(h->lu_shift[node] == z)) {
+    if (!dense_factor(h, {node}, {z})) return false;   // exactly singular shifted matrix -> LAPACK info > 0 (dense/feast_dense.jl:198-203)
+  }
+  const zd* LU = h->lu_cache[node].as<zd>();
+  const int* perm = h->piv_cache[node].as<int>() + n;
+  {
+    const int64_t total = (int64_t)n * m;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 8));
+    k_dense_gather_rows<<<grid, 256, 0, h->stream>>>(n, m, ld, perm, RHS, X);
+    launched(h);
+  }
+  const int cgrid = (m + 127) / 128;
+  // forward: L y = P b
+  for (int r0 = 0; r0 < n; r0 += FC_LU_NB) {
+    const int bs = std::min(FC_LU_NB, n - r0);
+    k_dense_trsm_rows<true><<<cgrid, 128, 0, h->stream>>>(n, r0, bs, LU, m, ld, X);
+    launched(h);
+    const int rest = n - r0 - bs;
+    if (rest > 0)
+      zgemm(h, rest, m, bs, LU + (r0 + bs) + (int64_t)r0 * n, 1, n, X + (int64_t)r0 * ld, ld, 1, X + (int64_t)(r0 + bs) * ld, ld, 1, -1.0, 1);
+  }
+  // backward: U x = y
+  const int nblk = (n + FC_LU_NB - 1) / FC_LU_NB;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int r0 = b * FC_LU_NB, bs = std::min(FC_LU_NB, n - r0);
+    k_dense_trsm_rows<false><<<cgrid, 128, 0, h->stream>>>(n, r0, bs, LU, m, ld, X);
+    launched(h);
+    if (r0 > 0) zgemm(h, r0, m, bs, LU + (int64_t)r0 * n, 1, n, X + (int64_t)r0 * ld, ld, 1, X, ld, 1, -1.0, 1);
+  }
+  return true;
+}
+
+void dense_apply(H* h, int which, int m, const zd* X, zd* Y) {
+  const int n = (int)h->n;
+  const int64_t ld = h->ws_ld;
+  const zd* Mx = (which == FEASTCUDA_A) ? h->dDenseA.as<zd>() : h->dDenseB.as<zd>();
+  zgemm(h, n, m, n, Mx, 1, n, X, ld, 1, Y, ld, 1, 1.0, 0);
+}
+
+// =====================================================================================================
+// banded: operators are expanded to general band storage (2k+1) x n, diagonal in row k (banded/feast_banded.jl:263-271);
+// factors in LAPACK gbtrf layout (3k+1) x n with kl = ku = k.
+// =====================================================================================================
+void band_set(H* h, int which, int64_t n, int64_t k, const double* ab, int64_t ldab, bool cplx, int structure) {
+  FC_REQUIRE(n > 0 && k >= 0 && ab != nullptr, "set_band: bad arguments");
+  FC_REQUIRE(which == FEASTCUDA_A || which == FEASTCUDA_B, "which must be A or B");
+  const bool general = (structure == FEASTCUDA_GEN);
+  FC_REQUIRE(ldab >= (general ? 2 * k + 1 : k + 1), "set_band: storage insufficient for the bandwidth");
+  HostBand& d = (which == FEASTCUDA_A) ? h->bandA : h->bandB;
+  if (which == FEASTCUDA_B) FC_REQUIRE(h->kind == OP_BAND && h->bandA.set && h->bandA.n == n, "set A (same size, banded) before B");
+  d.n = n;
+  d.k = k;
+  d.cplx = cplx;
+  const int64_t rows = 2 * k + 1;
+  d.ab.assign((size_t)2 * rows * n, 0.0);
+  auto in = [&](int64_t r, int64_t j) -> zc {
+    const size_t o = (size_t)j * ldab + r;
+    return cplx ? zc(ab[2 * o], ab[2 * o + 1]) : zc(ab[o], 0.0);
+  };
+  auto out = [&](int64_t i, int64_t j, zc v) {   // entry (i, j) of the full matrix, |i - j| <= k
+    const size_t o = 2 * ((size_t)j * rows + (k + i - j));
+    d.ab[o] = v.real();
+    d.ab[o + 1] = v.imag();
+  };
+  for (int64_t j = 0; j < n; ++j) {
+    if (general) {
+      for (int64_t i = std::max<int64_t>(0, j - k); i <= std::min<int64_t>(n - 1, j + k); ++i) out(i, j, in(k + i - j, j));
+    } else {
+      // upper storage (k+1) x n, A[i,j] (i <= j) in row k + i - j (banded/feast_banded.jl:205-214); mirror with conj
+      for (int64_t i = std::max<int64_t>(0, j - k); i <= j; ++i) {
+        const zc v = in(k + i - j, j);
+        out(i, j, v);
+        if (i != j) out(j, i, std::conj(v));
+      }
+    }
+  }
+  d.set = true;
+  if (which == FEASTCUDA_A) {
+    if (h->kind != OP_BAND) { h->has_b = false; h->bandB.set = false; }
+    h->kind = OP_BAND;
+    h->n = n;
+  } else {
+    h->has_b = true;
+  }
+  h->band_uploaded = false;
+  release_factor_cache(h);
+}
+
+void band_prepare(H* h) {
+  FC_REQUIRE(h->bandA.set, "operator A has not been set");
+  h->n = h->bandA.n;
+  if (h->band_uploaded) return;
+  auto up = [&](const HostBand& s, DBuf& d) {
+    const size_t bytes = s.ab.size() * sizeof(double);
+    d.ensure(bytes);
+    FC_CUDA(cudaMemcpyAsync(d.p, s.ab.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+  };
+  up(h->bandA, h->dBandA);
+  if (h->has_b) up(h->bandB, h->dBandB);
+  FC_CUDA(cudaStreamSynchronize(h->stream));
+  h->band_uploaded = true;
+  release_factor_cache(h);
+}
+
+bool band_node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X) {
+  const int n = (int)h->n;
+  const int ka = (int)h->bandA.k, kb = h->has_b ? (int)h->bandB.k : 0;
+  const int k = std::max(ka, kb);
+  const int ldf = 3 * k + 1;
+  const int64_t ld = h->ws_ld;
+  if ((int)h->lu_cache.size() <= node) {
+    h->lu_cache.resize(node + 1);
+    h->piv_cache.resize(node + 1);
+    h->lu_shift.resize(node + 1, zc(NAN, NAN));
+  }
+  if (!(h->lu_shift[node] == z)) {
+    h->lu_cache[node].ensure((size_t)ldf * n * sizeof(zd));
+    h->piv_cache[node].ensure((size_t)(n + 1) * sizeof(int));
+    zd* F = h->lu_cache[node].as<zd>();
+    int* ipiv = h->piv_cache[node].as<int>();
+    int* dinfo = ipiv + n;
+    FC_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), h->stream));
+    const int64_t total = (int64_t)ldf * n;
+    k_band_shift<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 8)), 256, 0, h->stream>>>(
+        n, k, ka, kb, h->dBandA.as<zd>(), h->has_b ? h->dBandB.as<zd>() : nullptr, mk<double>(z.real(), z.imag()), F);
+    launched(h);
+    k_band_lu<<<1, 256, 0, h->stream>>>(n, k, F, ipiv, dinfo);
+    launched(h);
+    int info = 0;
+    FC_CUDA(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FC_CUDA(cudaStreamSynchronize(h->stream));
+    if (info != 0) { h->lu_shift[node] = zc(NAN, NAN); return false; }
+    h->lu_shift[node] = z;
+  }
+  const zd* F = h->lu_cache[node].as<zd>();
+  const int* ipiv = h->piv_cache[node].as<int>();
+  FC_CUDA(cudaMemcpy2DAsync(X, (size_t)ld * sizeof(zd), RHS, (size_t)ld * sizeof(zd), (size_t)m * sizeof(zd), (size_t)n,
+                            cudaMemcpyDeviceToDevice, h->stream));
+  k_band_solve<<<(m + 63) / 64, 64, 0, h->stream>>>(n, k, F, ipiv, m, ld, X);
+  launched(h);
+  return true;
+}
+
+void band_apply(H* h, int which, int m, const zd* X, zd* Y) {
+  const int n = (int)h->n;
+  const HostBand& s = (which == FEASTCUDA_A) ? h->bandA : h->bandB;
+  const zd* AB = (which == FEASTCUDA_A) ? h->dBandA.as<zd>() : h->dBandB.as<zd>();
+  const int64_t total = (int64_t)n * m;
+  k_band_apply<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 8)), 256, 0, h->stream>>>(
+      n, (int)s.k, AB, m, h->ws_ld, X, Y);
+  launched(h);
+}
+
 }  // namespace feastcuda

@@ -143,3 +143,14 @@ struct feastcuda_handle_s {
   feastcuda_stats stats;
   std::string err;
 };
+
+namespace feastcuda {
+// drop every cached per-node factor (device memory included)
+inline void release_factor_cache(feastcuda_handle_s* h) {
+  for (auto& b : h->lu_cache) b.release();
+  for (auto& b : h->piv_cache) b.release();
+  h->lu_cache.clear();
+  h->piv_cache.clear();
+  h->lu_shift.clear();
+}
+}  // namespace feastcuda

@@ -1272,7 +1272,7 @@ static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t
     if (h->kind != OP_SPARSE) { h->has_b = false; h->hB.set = false; }
     h->kind = OP_SPARSE;
     h->n = n;
-    h->lu_cache.clear();
+    release_factor_cache(h);
   } else {
     FC_REQUIRE(h->kind == OP_SPARSE && h->hA.set && h->hA.n == n, "set A (same size, sparse) before B");
     ingest_csr(h->hB, n, nnz, ptr, idx, val, cplx, base, fmt, structure);
@@ -1298,7 +1298,7 @@ int feastcuda_clear_b(feastcuda_handle h) {
   h->dB.uploaded = false;
   h->dense_uploaded = false;
   h->band_uploaded = false;
-  h->lu_cache.clear();
+  release_factor_cache(h);
   return FEASTCUDA_OK;
 }
 
@@ -1464,14 +1464,13 @@ int feastcuda_block_solve(feastcuda_handle h, double z_re, double z_im, int64_t 
   if (X0) upload_block<zd>(h, h->n, (int)m, reinterpret_cast<const zd*>(X0), blk(h, BS_KX));
   SolveOut so;
   const double tol = o.tol == 0.0 ? 1e-12 : o.tol;
-  if (h->kind != OP_SPARSE) { h->lu_cache.clear(); h->lu_shift.clear(); }
+  if (h->kind != OP_SPARSE) release_factor_cache(h);
   node_solve(h, 0, zc(z_re, z_im), (int)m, blk(h, BS_RHS), blk(h, BS_KX), X0 != nullptr, o, tol, so);
   if (h->kind != OP_SPARSE) {
     // direct solves report the true residual through the generic kernels
     so.iters.assign(m, 0);
     so.truenorm.assign(m, 0.0);
-    h->lu_cache.clear();
-    h->lu_shift.clear();
+    release_factor_cache(h);
   }
   download_block<zd>(h, h->n, (int)m, blk(h, BS_KX), reinterpret_cast<zd*>(Xout));
   for (int c = 0; c < m; ++c) {

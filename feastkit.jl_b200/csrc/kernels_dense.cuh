@@ -1,0 +1,277 @@
+// Dense operator kernels: shifted-matrix formation, batched complex LU with partial pivoting (one batch entry per
+// quadrature node), triangular solves on row-major right-hand-side blocks and the complex GEMM they all share.
+//
+// Replaces, for dense inputs, `_feast_dense_shifted_identity_minus!` / `z*B - A` (core/feast_aux.jl:59-74,
+// dense/feast_dense.jl:190-194), `lu(shifted)` -> LAPACK zgetrf (dense/feast_dense.jl:196), `ldiv!` -> zgetrs (:207) and the
+// projections `A*Qr`, `B*Qr` (:252,262).
+//
+// The GEMM runs on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA); a complex product is four real MMAs on split
+// re/im planes staged in shared memory.  tcgen05/TMEM has no FP64 kind, so this register-fragment path IS the FP64
+// tensor-core path of sm_100a.  LU layout is LAPACK's: column-major n x n, unit-lower L below the diagonal, U on and above,
+// pivots as row indices.  Bound: FP64 tensor pipe for the trailing updates (8/3 n^3 flop per node), HBM/latency for panels.
+#pragma once
+#include "cxmath.cuh"
+
+namespace feastcuda {
+
+typedef cx<double> zdd;
+
+// ---- LU_b = z_b * B - A   (B == nullptr: identity) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dense_shift(int64_t n, const zdd* __restrict__ A, const zdd* __restrict__ B,
+                                                     const zdd* __restrict__ z, zdd* __restrict__ LU, int64_t batch_stride) {
+  const zdd zb = z[blockIdx.y];
+  zdd* out = LU + (int64_t)blockIdx.y * batch_stride;
+  const int64_t total = n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx % n, j = idx / n;
+    zdd v = -A[idx];
+    if (B != nullptr) v = v + zb * B[idx];
+    else if (i == j) v = v + zb;
+    out[idx] = v;
+  }
+}
+
+// ---- panel factorisation: columns [k0, k0+nbw) of every batch entry, one CTA per entry ----------------------------------
+// classic right-looking, partial pivoting by max(|re|+|im|) like izamax; row swaps are applied inside the panel only
+// (k_dense_laswp does the rest of the row).  info[b] = first zero pivot (1-based) or 0.
+constexpr int FC_LU_NB = 32;
+
+__global__ void __launch_bounds__(512) k_dense_panel_lu(int n, int k0, int nbw, zdd* __restrict__ LU, int64_t batch_stride,
+                                                        int* __restrict__ ipiv, int* __restrict__ info) {
+  zdd* M = LU + (int64_t)blockIdx.x * batch_stride;
+  int* piv = ipiv + (int64_t)blockIdx.x * n;
+  __shared__ double s_val[512];
+  __shared__ int s_idx[512];
+  __shared__ zdd s_u[FC_LU_NB];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  for (int j = 0; j < nbw; ++j) {
+    const int col = k0 + j;
+    double best = -1.0;
+    int bi = col;
+    for (int i = col + tid; i < n; i += NT) {
+      const zdd v = M[i + (int64_t)col * n];
+      const double a = fabs(v.x) + fabs(v.y);
+      if (a > best) { best = a; bi = i; }
+    }
+    s_val[tid] = best;
+    s_idx[tid] = bi;
+    __syncthreads();
+    for (int w = NT / 2; w > 0; w >>= 1) {
+      if (tid < w) {
+        const double o = s_val[tid + w];
+        const int oi = s_idx[tid + w];
+        if (o > s_val[tid] || (o == s_val[tid] && oi < s_idx[tid])) { s_val[tid] = o; s_idx[tid] = oi; }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      s_p = s_idx[0];
+      piv[col] = s_idx[0];
+      if (!(s_val[0] > 0.0) && info[blockIdx.x] == 0) info[blockIdx.x] = col + 1;
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p != col && tid < nbw) {
+      const int64_t c = (int64_t)(k0 + tid) * n;
+      const zdd t = M[col + c];
+      M[col + c] = M[p + c];
+      M[p + c] = t;
+    }
+    __syncthreads();
+    const zdd pv = M[col + (int64_t)col * n];
+    const bool ok = (fabs(pv.x) + fabs(pv.y)) > 0.0;
+    const zdd inv = ok ? (mk<double>(1.0, 0.0) / pv) : czero<double>();
+    if (tid < nbw) s_u[tid] = M[col + (int64_t)(k0 + tid) * n];
+    __syncthreads();
+    for (int i = col + 1 + tid; i < n; i += NT) {
+      const zdd l = M[i + (int64_t)col * n] * inv;
+      M[i + (int64_t)col * n] = l;
+      for (int c = j + 1; c < nbw; ++c) {
+        zdd* e = M + i + (int64_t)(k0 + c) * n;
+        *e = *e - l * s_u[c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// row interchanges of the panel [k0, k0+nbw) applied to the columns [c0, c1) outside it; one thread per column
+__global__ void __launch_bounds__(256) k_dense_laswp(int n, int k0, int nbw, int c0, int c1, zdd* __restrict__ LU,
+                                                     int64_t batch_stride, const int* __restrict__ ipiv) {
+  zdd* M = LU + (int64_t)blockIdx.y * batch_stride;
+  const int* piv = ipiv + (int64_t)blockIdx.y * n;
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
+  zdd* colp = M + (int64_t)c * n;
+  for (int j = 0; j < nbw; ++j) {
+    const int r = k0 + j, p = piv[r];
+    if (p != r) { const zdd t = colp[r]; colp[r] = colp[p]; colp[p] = t; }
+  }
+}
+
+// U12 = L11^-1 A12 (unit lower L11 = panel rows/cols [k0, k0+nbw)); one thread per column of A12
+__global__ void __launch_bounds__(128) k_dense_trsm_u12(int n, int k0, int nbw, zdd* __restrict__ LU, int64_t batch_stride) {
+  zdd* M = LU + (int64_t)blockIdx.y * batch_stride;
+  __shared__ zdd sL[FC_LU_NB][FC_LU_NB + 1];
+  for (int e = threadIdx.x; e < nbw * nbw; e += blockDim.x) {
+    const int i = e % nbw, j = e / nbw;
+    sL[i][j] = M[(k0 + i) + (int64_t)(k0 + j) * n];
+  }
+  __syncthreads();
+  const int c = k0 + nbw + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  zdd* colp = M + (int64_t)c * n + k0;
+  for (int i = 1; i < nbw; ++i) {
+    zdd s = colp[i];
+    for (int j = 0; j < i; ++j) s = s - sL[i][j] * colp[j];
+    colp[i] = s;
+  }
+}
+
+// ipiv (sequence of transpositions) -> perm with  (P b)[i] = b[perm[i]]
+__global__ void k_dense_piv_to_perm(int n, const int* __restrict__ ipiv, int* __restrict__ perm) {
+  const int* piv = ipiv + (int64_t)blockIdx.x * n;
+  int* pm = perm + (int64_t)blockIdx.x * n;
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < n; ++i) pm[i] = i;
+  for (int i = 0; i < n; ++i) {
+    const int p = piv[i];
+    if (p != i) { const int t = pm[i]; pm[i] = pm[p]; pm[p] = t; }
+  }
+}
+
+// X[i, :] = RHS[perm[i], :]   (row-major n x ld blocks, m active columns)
+__global__ void __launch_bounds__(256) k_dense_gather_rows(int64_t n, int m, int64_t ld, const int* __restrict__ perm,
+                                                           const zdd* __restrict__ RHS, zdd* __restrict__ X) {
+  const int64_t total = n * m;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / m;
+    const int c = (int)(idx % m);
+    X[i * ld + c] = RHS[(int64_t)perm[i] * ld + c];
+  }
+}
+
+// In-place triangular solve of one diagonal block on a row-major block of right-hand sides:
+//   LOWER: rows [r0, r0+bs) of X <- L11^-1 X (unit diagonal);  UPPER: X <- U11^-1 X.  One thread per RHS column.
+template <bool LOWER>
+__global__ void __launch_bounds__(128) k_dense_trsm_rows(int n, int r0, int bs, const zdd* __restrict__ LU, int m, int64_t ld,
+                                                         zdd* __restrict__ X) {
+  __shared__ zdd sT[FC_LU_NB][FC_LU_NB + 1];
+  for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) {
+    const int i = e % bs, j = e / bs;
+    sT[i][j] = LU[(r0 + i) + (int64_t)(r0 + j) * n];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  zdd* xp = X + (int64_t)r0 * ld + c;
+  if (LOWER) {
+    for (int i = 1; i < bs; ++i) {
+      zdd s = xp[(int64_t)i * ld];
+      for (int j = 0; j < i; ++j) s = s - sT[i][j] * xp[(int64_t)j * ld];
+      xp[(int64_t)i * ld] = s;
+    }
+  } else {
+    for (int i = bs - 1; i >= 0; --i) {
+      zdd s = xp[(int64_t)i * ld];
+      for (int j = i + 1; j < bs; ++j) s = s - sT[i][j] * xp[(int64_t)j * ld];
+      xp[(int64_t)i * ld] = s / sT[i][i];
+    }
+  }
+}
+
+// ---- complex GEMM on the FP64 tensor pipe ---------------------------------------------------------------------------------
+// C(M x N) = beta * C + alpha * A(M x K) * B(K x N), alpha = +-1, beta in {0, 1}; every operand is addressed with (row stride,
+// column stride) so that column-major LU blocks and row-major vector blocks mix freely.  CTA tile 64 x 64, K tile 16,
+// 8 warps as 4 (M) x 2 (N), warp tile 16 x 32 = 2 x 4 mma tiles of m8n8k4.
+struct ZgemmArgs {
+  int M, N, K;
+  const zdd* A; int64_t ars, acs, abatch;
+  const zdd* B; int64_t brs, bcs, bbatch;
+  zdd* C; int64_t crs, ccs, cbatch;
+  double alpha;
+  int beta;
+};
+
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k_zgemm_dmma(ZgemmArgs g) {
+  constexpr int TM = 64, TN = 64, TK = 16, LDS = 72;   // LDS = 8 mod 16: conflict-free fragment reads
+  __shared__ double sAr[TK][LDS], sAi[TK][LDS], sBr[TK][LDS], sBi[TK][LDS];
+  const zdd* A = g.A + (int64_t)blockIdx.z * g.abatch;
+  const zdd* B = g.B + (int64_t)blockIdx.z * g.bbatch;
+  zdd* C = g.C + (int64_t)blockIdx.z * g.cbatch;
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { cr[a][b][0] = cr[a][b][1] = 0.0; ci[a][b][0] = ci[a][b][1] = 0.0; }
+  const bool a_mfast = (g.ars == 1), b_nfast = (g.bcs == 1);
+  for (int k0 = 0; k0 < g.K; k0 += TK) {
+    __syncthreads();
+    for (int e = tid; e < TM * TK; e += 256) {
+      const int mm = a_mfast ? (e % TM) : (e / TK), kk = a_mfast ? (e / TM) : (e % TK);
+      zdd v = czero<double>();
+      if (i0 + mm < g.M && k0 + kk < g.K) v = A[(int64_t)(i0 + mm) * g.ars + (int64_t)(k0 + kk) * g.acs];
+      sAr[kk][mm] = v.x;
+      sAi[kk][mm] = v.y;
+    }
+    for (int e = tid; e < TN * TK; e += 256) {
+      const int nn = b_nfast ? (e % TN) : (e / TK), kk = b_nfast ? (e / TN) : (e % TK);
+      zdd v = czero<double>();
+      if (j0 + nn < g.N && k0 + kk < g.K) v = B[(int64_t)(k0 + kk) * g.brs + (int64_t)(j0 + nn) * g.bcs];
+      sBr[kk][nn] = v.x;
+      sBi[kk][nn] = v.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 4) {
+      double ar[2], ai[2], nai[2], br[4], bi[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        ar[a] = sAr[ks + fk][wm + 8 * a + fr];
+        ai[a] = sAi[ks + fk][wm + 8 * a + fr];
+        nai[a] = -ai[a];
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        br[b] = sBr[ks + fk][wn + 8 * b + fr];
+        bi[b] = sBi[ks + fk][wn + 8 * b + fr];
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          dmma_8x8x4(cr[a][b], ar[a], br[b]);
+          dmma_8x8x4(cr[a][b], nai[a], bi[b]);
+          dmma_8x8x4(ci[a][b], ar[a], bi[b]);
+          dmma_8x8x4(ci[a][b], ai[a], br[b]);
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = i0 + wm + 8 * a + fr, j = j0 + wn + 8 * b + 2 * fk + q;
+        if (i < g.M && j < g.N) {
+          zdd* cp = C + (int64_t)i * g.crs + (int64_t)j * g.ccs;
+          zdd v = mk<double>(g.alpha * cr[a][b][q], g.alpha * ci[a][b][q]);
+          if (g.beta) v = v + *cp;
+          *cp = v;
+        }
+      }
+}
+
+}  // namespace feastcuda

@@ -1169,6 +1169,169 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
 }
 
 // =====================================================================================================
+// General (non-Hermitian) FEAST: full contour, one-sided Rayleigh-Ritz -- feast_grci! (kernel/feast_kernel.jl:646-962)
+// driven as feast_gcsrgv! / feast_gegv! / _feast_banded_general do (sparse/feast_sparse.jl:873-1006,
+// dense/feast_dense.jl:402-593, banded/feast_banded.jl:1088-1284).
+// Differences from the reference, both in HOW, not in WHAT converges:
+//   * the filtered block is orthonormalised (rank-revealing, as in the Hermitian drivers) before the projection, so the
+//     reduced pencil (Q^H A Q, Q^H B Q) is well conditioned; the reference projects on the raw block (kernel:790-807);
+//   * residuals are ||A x - lambda B x|| / max(|lambda|, 1); the reference drops B there (kernel:900-906), so its
+//     generalized runs can only stop at fpm[4].
+// =====================================================================================================
+static void run_contour(H* h, zc Emid, double r, int m0, int64_t* fpm, const zc* Zne, const zc* Wne, int ne,
+                        const feastcuda_solver_opts* optsp, int64_t* Mout, int64_t* info, double* epsout, int64_t* loopout) {
+  Timer ttotal;
+  if (host_feastdefault(fpm)) throw FcError(FEASTCUDA_ERR_ARG, "invalid fpm (feastdefault!)");
+  prepare_operator(h);
+  const int64_t n = h->n;
+  // check_feast_grci_input, core/feast_aux.jl:401-425
+  FC_REQUIRE(n > 0, "Matrix size N must be positive");
+  FC_REQUIRE(m0 > 0 && m0 <= n, "Number of eigenvalues M0 must be between 1 and N");
+  FC_REQUIRE(r > 0, "Search radius r must be positive");
+  FC_REQUIRE(ne >= 1 && ne <= 128 && Zne && Wne, "contour required");
+  FC_REQUIRE(h->have_subspace && h->sub_m0 == m0 && h->ws_n == n, "initial subspace not uploaded for this (n, M0)");
+  feastcuda_solver_opts o = optsp ? *optsp : default_opts();
+  const double tol = (o.tol == 0.0) ? std::pow(10.0, -(double)fpm[2]) : o.tol;
+  const double eps_tol = host_feast_tolerance(fpm);
+  const int maxloop = (int)fpm[3];
+  const bool iterative = (h->kind == OP_SPARSE);
+  int shard = iterative ? o.shard : FEASTCUDA_SHARD_NODES;
+
+  int active = m0, rank = 0, M = 0, loop = 0, info_code = 0;
+  double eps_val = 0.0;
+  std::vector<zc> lam(m0, zc(0.0));
+  std::vector<double> res(m0, 0.0), cost(ne, 1.0);
+  int qb = BS_QB, xr = BS_XR, res_slot = -1;
+  std::vector<zc> Sq, Aq, V, lam_red;
+  while (true) {
+    h->stats.loops++;
+    Timer tsolve;
+    zd* basis = blk(h, qb);
+    const zd* rhs = basis;
+    if (h->has_b) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
+    zero_cols(h, active, blk(h, BS_ACC));
+    std::vector<WorkItem> items = build_items(ne, active, h->nranks, h->rank, shard, cost);
+    bool failed = false;
+    for (const WorkItem& it : items) {
+      zd* X = blk(h, BS_KX) + it.c0;
+      SolveOut so;
+      const bool ok = node_solve(h, it.node, Zne[it.node], it.nc, rhs + it.c0, X, false, o, tol, so);
+      h->stats.node_solves++;
+      if (iterative) h->stats.node_iters[it.node] = so.it_total;
+      if (!ok && (!iterative || o.inner_rel <= 0.0)) { failed = true; info_code = iterative ? 5 : 8; break; }
+      axpby_cols(h, it.nc, Wne[it.node], 1.0, X, blk(h, BS_ACC) + it.c0);   // q += w_e Y (kernel:762-766)
+    }
+    sync(h);
+    h->stats.ms_solve += tsolve.ms();
+    if (h->nranks > 1) {
+      allreduce_block(h, blk(h, BS_ACC), (int64_t)n * h->ws_ld);
+      double fl = failed ? 1.0 : 0.0;
+      double* dp = reinterpret_cast<double*>(h->small2.as<zd>() + 2 * FC_MAXCOLS);
+      FC_CUDA(cudaMemcpyAsync(dp, &fl, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      FC_NCCL(g_nccl.AllReduce(dp, dp, 1, 8, 0, h->nccl_comm, h->stream));
+      FC_CUDA(cudaMemcpyAsync(&fl, dp, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      sync(h);
+      if (fl > 0) { failed = true; if (!info_code) info_code = iterative ? 5 : 8; }
+    }
+    if (failed) break;
+    Timer tortho;
+    int qslot = BS_ACC;
+    rank = orthonormalize(h, active, BS_ACC, BS_KP, std::sqrt(2.220446049250313e-16), &qslot);
+    h->stats.ms_ortho += tortho.ms();
+    if (rank == 0) { info_code = 5; break; }
+    Timer tproj;
+    zd* Q = blk(h, qslot);
+    apply_op(h, FEASTCUDA_A, rank, Q, blk(h, BS_KS));
+    gram_host(h, rank, rank, Q, blk(h, BS_KS), Aq);
+    std::vector<zc> C = Aq;
+    if (h->has_b) {
+      apply_op(h, FEASTCUDA_B, rank, Q, blk(h, BS_KT));
+      gram_host(h, rank, rank, Q, blk(h, BS_KT), Sq);
+      if (!host_lu_solve(rank, Sq, C)) { info_code = 8; break; }
+    }
+    h->stats.ms_project += tproj.ms();
+    Timer teig;
+    if (!host_complex_eig(rank, C, lam_red, V)) { info_code = 8; break; }
+    h->stats.ms_eig += teig.ms();
+    // Julia's eigen orders lexicographically by (real, imag); then the stable inside-first partition (core/feast_aux.jl:208-257)
+    std::vector<int> order(rank);
+    for (int i = 0; i < rank; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (lam_red[a].real() != lam_red[b].real()) return lam_red[a].real() < lam_red[b].real();
+      return lam_red[a].imag() < lam_red[b].imag();
+    });
+    std::vector<int> perm;
+    for (int i : order) if (host_inside_gcontour(lam_red[i], Emid, r, fpm)) perm.push_back(i);
+    M = (int)perm.size();
+    for (int i : order) if (!host_inside_gcontour(lam_red[i], Emid, r, fpm)) perm.push_back(i);
+    if (M == 0) { info_code = 5; break; }
+    std::vector<zc> T((size_t)rank * rank);
+    for (int k = 0; k < rank; ++k) {
+      const int src = perm[k];
+      double s2 = 0.0;   // ||Q v|| = ||v|| for orthonormal Q: every Ritz vector leaves with unit 2-norm (kernel:864-876)
+      for (int i = 0; i < rank; ++i) s2 += std::norm(V[(size_t)i * rank + src]);
+      const double nrm = s2 > 0 ? std::sqrt(s2) : 1.0;
+      for (int i = 0; i < rank; ++i) T[(size_t)i * rank + k] = V[(size_t)i * rank + src] / nrm;
+      lam[k] = lam_red[src];
+    }
+    Timer tres;
+    rowtransform(h, rank, rank, Q, T, blk(h, xr));
+    res_slot = xr;
+    std::vector<zc> lamc(lam.begin(), lam.begin() + M);
+    std::vector<double> rnorm;
+    eig_residual_norms(h, M, blk(h, xr), lamc, rnorm);
+    double max_res = 0.0;
+    for (int j = 0; j < M; ++j) {
+      res[j] = rnorm[j] / std::max(std::abs(lam[j]), 1.0);
+      max_res = std::max(max_res, res[j]);
+    }
+    h->stats.ms_resid += tres.ms();
+    eps_val = max_res;
+    if (getenv("FEASTCUDA_VERBOSE"))
+      fprintf(stderr, "[feastcuda r%d] general loop %d: M=%d rank=%d epsout=%.3e\n", h->rank, loop, M, rank, eps_val);
+    if (eps_val <= eps_tol || loop >= maxloop) break;   // kernel:917-925 (no error code at fpm[4], like the reference)
+    ++loop;
+    active = rank;
+    std::swap(qb, xr);
+  }
+  // feast_sort_general!: the M inside pairs ascending in |lambda|, stable (core/feast_tools.jl:684-713)
+  if (res_slot >= 0 && M > 0 && info_code == 0) {
+    std::vector<int> ord(M);
+    for (int i = 0; i < M; ++i) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return std::norm(lam[a]) < std::norm(lam[b]); });
+    std::vector<zc> P((size_t)rank * rank, zc(0.0)), lam2(lam);
+    std::vector<double> res2(res);
+    for (int k = 0; k < rank; ++k) {
+      const int src = k < M ? ord[k] : k;
+      P[(size_t)src * rank + k] = 1.0;
+      lam[k] = lam2[src];
+      if (k < M) res[k] = res2[src];
+    }
+    const int other = (res_slot == BS_XR) ? BS_QB : BS_XR;
+    rowtransform(h, rank, rank, blk(h, res_slot), P, blk(h, other));
+    res_slot = other;
+  }
+  if (M == 0 && info_code == 0) info_code = 5;
+  if (res_slot >= 0 && res_slot != BS_XR) {
+    copy_cols(h, std::max(rank, 1), blk(h, res_slot), blk(h, BS_XR));
+    sync(h);
+  }
+  h->res_m0 = m0;
+  h->res_M = info_code == 0 ? M : 0;
+  h->res_rank = rank;
+  h->res_lambda.assign((size_t)2 * m0, 0.0);
+  for (int j = 0; j < m0; ++j) { h->res_lambda[2 * j] = lam[j].real(); h->res_lambda[2 * j + 1] = lam[j].imag(); }
+  h->res_res.assign(res.begin(), res.end());
+  h->res_general = true;
+  h->have_subspace = false;
+  *Mout = h->res_M;
+  *info = info_code;
+  *epsout = eps_val;
+  *loopout = loop;
+  h->stats.ms_total += ttotal.ms();
+}
+
+// =====================================================================================================
 // C ABI
 // =====================================================================================================
 #define FC_TRY(hh)  \
@@ -1415,15 +1578,25 @@ int feastcuda_solve_interval(feastcuda_handle h, double Emin, double Emax, int64
   return feastcuda_fetch_results(h, m0, opts ? opts->x_real : 0, lambda, X, res);
 }
 
+static int run_contour_guarded(feastcuda_handle h, double Emid_re, double Emid_im, double r, int64_t m0, int64_t* fpm, const double* Zne,
+                               const double* Wne, int64_t ne, const feastcuda_solver_opts* opts, int64_t* M, int64_t* info, double* epsout,
+                               int64_t* loop) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr && fpm && M && info && epsout && loop, "null argument");
+  bind_device(h);
+  run_contour(h, zc(Emid_re, Emid_im), r, (int)m0, fpm, reinterpret_cast<const zc*>(Zne), reinterpret_cast<const zc*>(Wne), (int)ne, opts, M,
+              info, epsout, loop);
+  FC_CATCH
+}
+
 int feastcuda_solve_contour(feastcuda_handle h, double Emid_re, double Emid_im, double r, int64_t m0, int64_t* fpm,
                             const double* Zne, const double* Wne, int64_t ne, const double* Q0, const feastcuda_solver_opts* opts,
                             double* lambda, double* X, double* res, int64_t* M, int64_t* info, double* epsout, int64_t* loop) {
-  FC_TRY(h)
-  FC_REQUIRE(h != nullptr, "null handle");
-  (void)Emid_re; (void)Emid_im; (void)r; (void)m0; (void)fpm; (void)Zne; (void)Wne; (void)ne; (void)Q0; (void)opts;
-  (void)lambda; (void)X; (void)res; (void)M; (void)info; (void)epsout; (void)loop;
-  throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "general (G-RCI) solve: not built yet");
-  FC_CATCH
+  int rc = feastcuda_upload_subspace(h, m0, Q0, opts ? opts->q0_real : 0);
+  if (rc) return rc;
+  rc = run_contour_guarded(h, Emid_re, Emid_im, r, m0, fpm, Zne, Wne, ne, opts, M, info, epsout, loop);
+  if (rc) return rc;
+  return feastcuda_fetch_results(h, m0, 0, lambda, X, res);
 }
 
 // ---- stage-level entry points ---------------------------------------------------------------------

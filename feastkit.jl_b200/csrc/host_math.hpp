@@ -309,4 +309,157 @@ inline OrthoPass ortho_pass(const std::vector<zc>& G, int cur, int done, double 
   return out;
 }
 
+// ---- small dense complex algebra for the general (non-Hermitian) reduced problem ---------------------------------
+// eigen(Aq, Sq) of kernel/feast_kernel.jl:812 (LAPACK zggev in the reference) for r <= 128: C = Sq^-1 Aq by LU with
+// partial pivoting, then Hessenberg + shifted QR (complex Schur form) with back-substituted eigenvectors.
+// All matrices row-major r x r.  Returns false if Sq is singular or the QR iteration does not converge.
+inline bool host_lu_solve(int n, std::vector<zc> M, std::vector<zc>& Bm /* n x n, overwritten by M^-1 Bm */) {
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = std::abs(M[(size_t)k * n + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (std::abs(M[(size_t)i * n + k]) > best) { best = std::abs(M[(size_t)i * n + k]); p = i; }
+    if (!(best > 0.0)) return false;
+    if (p != k)
+      for (int j = 0; j < n; ++j) { std::swap(M[(size_t)k * n + j], M[(size_t)p * n + j]); std::swap(Bm[(size_t)k * n + j], Bm[(size_t)p * n + j]); }
+    const zc inv = zc(1.0) / M[(size_t)k * n + k];
+    for (int i = k + 1; i < n; ++i) {
+      const zc l = M[(size_t)i * n + k] * inv;
+      if (l == zc(0.0)) continue;
+      for (int j = k + 1; j < n; ++j) M[(size_t)i * n + j] -= l * M[(size_t)k * n + j];
+      for (int j = 0; j < n; ++j) Bm[(size_t)i * n + j] -= l * Bm[(size_t)k * n + j];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    const zc inv = zc(1.0) / M[(size_t)i * n + i];
+    for (int j = 0; j < n; ++j) {
+      zc s = Bm[(size_t)i * n + j];
+      for (int k = i + 1; k < n; ++k) s -= M[(size_t)i * n + k] * Bm[(size_t)k * n + j];
+      Bm[(size_t)i * n + j] = s * inv;
+    }
+  }
+  return true;
+}
+
+inline bool host_complex_eig(int n, std::vector<zc> A, std::vector<zc>& lam, std::vector<zc>& V) {
+  auto a = [&](int i, int j) -> zc& { return A[(size_t)i * n + j]; };
+  std::vector<zc> Z((size_t)n * n, zc(0.0));
+  for (int i = 0; i < n; ++i) Z[(size_t)i * n + i] = 1.0;
+  double anorm = 0.0;
+  for (auto& v : A) anorm = std::max(anorm, std::abs(v));
+  if (!(anorm > 0.0)) anorm = 1.0;
+  const double eps = 2.220446049250313e-16;
+  // Householder reduction to upper Hessenberg form, H = Q^H A Q, Z = Q
+  std::vector<zc> v(n);
+  for (int k = 0; k + 2 < n; ++k) {
+    double xn2 = 0.0;
+    for (int i = k + 1; i < n; ++i) xn2 += std::norm(a(i, k));
+    double tail = 0.0;
+    for (int i = k + 2; i < n; ++i) tail += std::norm(a(i, k));
+    if (!(tail > 0.0)) continue;
+    const double xn = std::sqrt(xn2);
+    const zc x0 = a(k + 1, k);
+    const zc ph = std::abs(x0) > 0.0 ? x0 / std::abs(x0) : zc(1.0);
+    const int len = n - k - 1;
+    for (int i = 0; i < len; ++i) v[i] = a(k + 1 + i, k);
+    v[0] += ph * xn;
+    double vn2 = 0.0;
+    for (int i = 0; i < len; ++i) vn2 += std::norm(v[i]);
+    if (!(vn2 > 0.0)) continue;
+    const double f = 2.0 / vn2;
+    for (int j = 0; j < n; ++j) {          // A <- H A
+      zc sdot(0.0);
+      for (int i = 0; i < len; ++i) sdot += std::conj(v[i]) * a(k + 1 + i, j);
+      sdot *= f;
+      for (int i = 0; i < len; ++i) a(k + 1 + i, j) -= v[i] * sdot;
+    }
+    for (int i = 0; i < n; ++i) {          // A <- A H, Z <- Z H
+      zc sdot(0.0), zdot(0.0);
+      for (int j = 0; j < len; ++j) { sdot += a(i, k + 1 + j) * v[j]; zdot += Z[(size_t)i * n + k + 1 + j] * v[j]; }
+      sdot *= f;
+      zdot *= f;
+      for (int j = 0; j < len; ++j) { a(i, k + 1 + j) -= sdot * std::conj(v[j]); Z[(size_t)i * n + k + 1 + j] -= zdot * std::conj(v[j]); }
+    }
+    for (int i = k + 2; i < n; ++i) a(i, k) = 0.0;
+  }
+  // single-shift QR iteration on the active window [l, hi] (Wilkinson shift, Givens rotations), full Schur form
+  int hi = n - 1, iter = 0, total = 0;
+  std::vector<zc> cs(n), sn(n);
+  while (hi >= 0) {
+    int l = hi;
+    while (l > 0) {
+      double sc = std::abs(a(l - 1, l - 1)) + std::abs(a(l, l));
+      if (sc == 0.0) sc = anorm;
+      if (std::abs(a(l, l - 1)) <= eps * sc) { a(l, l - 1) = 0.0; break; }
+      --l;
+    }
+    if (l == hi) { --hi; iter = 0; continue; }
+    if (++total > 60 * n + 200) return false;
+    zc mu;
+    if (iter == 10 || iter == 20) mu = a(hi, hi) + zc(std::abs(a(hi, hi - 1).real()) + std::abs(a(hi, hi - 1).imag()), 0.0);
+    else {
+      const zc p = a(hi - 1, hi - 1), q = a(hi - 1, hi), r = a(hi, hi - 1), t = a(hi, hi);
+      const zc half = 0.5 * (p - t), disc = std::sqrt(half * half + q * r);
+      const zc m1 = 0.5 * (p + t) + disc, m2 = 0.5 * (p + t) - disc;
+      mu = (std::abs(m1 - t) < std::abs(m2 - t)) ? m1 : m2;
+    }
+    ++iter;
+    for (int i = l; i <= hi; ++i) a(i, i) -= mu;
+    for (int k = l; k < hi; ++k) {          // left rotations: zero a(k+1, k)
+      const zc x = a(k, k), y = a(k + 1, k);
+      const double nr = std::sqrt(std::norm(x) + std::norm(y));
+      zc c(1.0), s2(0.0);
+      if (nr > 0.0) { c = x / nr; s2 = y / nr; }
+      cs[k] = c;
+      sn[k] = s2;
+      for (int j = k; j < n; ++j) {
+        const zc u = a(k, j), w = a(k + 1, j);
+        a(k, j) = std::conj(c) * u + std::conj(s2) * w;
+        a(k + 1, j) = -s2 * u + c * w;
+      }
+    }
+    for (int k = l; k < hi; ++k) {          // right rotations (G^H), also accumulated into Z
+      const zc c = cs[k], s2 = sn[k];
+      const int top = std::min(k + 1, hi);
+      for (int i = 0; i <= top; ++i) {
+        const zc u = a(i, k), w = a(i, k + 1);
+        a(i, k) = u * c + w * s2;
+        a(i, k + 1) = -u * std::conj(s2) + w * std::conj(c);
+      }
+      for (int i = 0; i < n; ++i) {
+        const zc u = Z[(size_t)i * n + k], w = Z[(size_t)i * n + k + 1];
+        Z[(size_t)i * n + k] = u * c + w * s2;
+        Z[(size_t)i * n + k + 1] = -u * std::conj(s2) + w * std::conj(c);
+      }
+    }
+    for (int i = l; i <= hi; ++i) a(i, i) += mu;
+  }
+  // eigenvectors of the triangular factor by back substitution, then x = Z y
+  lam.resize(n);
+  V.assign((size_t)n * n, zc(0.0));
+  std::vector<zc> y(n);
+  const double small = eps * anorm;
+  for (int k = 0; k < n; ++k) {
+    lam[k] = a(k, k);
+    y[k] = 1.0;
+    for (int i = k - 1; i >= 0; --i) {
+      zc sdot(0.0);
+      for (int j = i + 1; j <= k; ++j) sdot += a(i, j) * y[j];
+      zc d = a(i, i) - lam[k];
+      if (std::abs(d) < small) d = small;
+      y[i] = -sdot / d;
+    }
+    double nrm = 0.0;
+    for (int i = 0; i < n; ++i) {
+      zc sdot(0.0);
+      for (int j = 0; j <= k; ++j) sdot += Z[(size_t)i * n + j] * y[j];
+      V[(size_t)i * n + k] = sdot;
+      nrm += std::norm(sdot);
+    }
+    nrm = nrm > 0.0 ? std::sqrt(nrm) : 1.0;
+    for (int i = 0; i < n; ++i) V[(size_t)i * n + k] /= nrm;
+  }
+  return true;
+}
+
 }  // namespace feastcuda

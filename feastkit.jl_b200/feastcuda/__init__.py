@@ -116,6 +116,19 @@ def check_feast_srci_input(N, M0, Emin, Emax, fpm):
     return True
 
 
+def check_feast_grci_input(N, M0, Emid, r, fpm):
+    """core/feast_aux.jl:401-425"""
+    if N <= 0:
+        raise ValueError("Matrix size N must be positive")
+    if M0 <= 0 or M0 > N:
+        raise ValueError("Number of eigenvalues M0 must be between 1 and N")
+    if r <= 0:
+        raise ValueError("Search radius r must be positive")
+    if len(fpm) < 64:
+        raise ValueError("fpm array must have at least 64 elements")
+    return True
+
+
 def node_partition(ne, nranks, rank):
     """Block node distribution (parallel/feast_mpi.jl:36-43); returns (start, count), 0-based."""
     s = np.zeros(1, dtype=np.int64)
@@ -314,6 +327,37 @@ class Engine:
                                                    W.ctypes.data_as(L._dp), len(Z), None if q is None else q.ctypes.data_as(L._dp),
                                                    C.byref(opts), L.dptr(lam), X.ctypes.data_as(L._dp), L.dptr(res), L.iptr(M),
                                                    L.iptr(info), L.dptr(eps), L.iptr(loop)))
+        for i in range(64):
+            fpm[i] = int(a[i])
+        m = int(M[0])
+        return FeastResult(lam[:m].copy(), X[:, :m].copy(), m, res[:m].copy(), int(info[0]), float(eps[0]), int(loop[0]), self.stats())
+
+    def solve_contour(self, Emid, r, M0, fpm, Zne, Wne, Q0=None, **kw):
+        """General (non-Hermitian) solve, one C-ABI call with host buffers (feastcuda_solve_contour)."""
+        self.reset_stats()
+        a = L.fpm_array(fpm)
+        Z = _as_z(Zne)
+        W = _as_z(Wne)
+        q0_real = Q0 is not None and not np.iscomplexobj(Q0)
+        opts = self.make_opts(q0_real=q0_real, x_real=False, **kw)
+        q = None
+        if Q0 is not None:
+            Q0 = np.asarray(Q0)
+            if Q0.shape != (self.n, M0):
+                raise ValueError("Q0 must be N x M0")
+            q = np.asfortranarray(Q0, dtype=np.float64) if q0_real else _colmajor_z(Q0)
+        lam = np.zeros(M0, dtype=np.complex128)
+        res = np.zeros(M0, dtype=np.float64)
+        X = np.zeros((self.n, M0), dtype=np.complex128, order="F")
+        M = np.zeros(1, dtype=np.int64)
+        info = np.zeros(1, dtype=np.int64)
+        loop = np.zeros(1, dtype=np.int64)
+        eps = np.zeros(1, dtype=np.float64)
+        Emid = complex(Emid)
+        self._ck(self.lib.feastcuda_solve_contour(self.h, Emid.real, Emid.imag, float(r), int(M0), L.iptr(a), Z.ctypes.data_as(L._dp),
+                                                  W.ctypes.data_as(L._dp), len(Z), None if q is None else q.ctypes.data_as(L._dp),
+                                                  C.byref(opts), lam.ctypes.data_as(L._dp), X.ctypes.data_as(L._dp), L.dptr(res),
+                                                  L.iptr(M), L.iptr(info), L.dptr(eps), L.iptr(loop)))
         for i in range(64):
             fpm[i] = int(a[i])
         m = int(M[0])

@@ -15,7 +15,7 @@ __all__ = [
     "feast_scsrev", "feast_scsrgv", "feast_hcsrev", "feast_hcsrgv", "feast_scsrevx", "feast_scsrgvx", "feast_hcsrevx",
     "feast_hcsrgvx", "feast_syev", "feast_sygv", "feast_heev", "feast_hegv", "feast_syevx", "feast_sygvx", "feast_heevx",
     "feast_hegvx", "feast_sbev", "feast_sbgv", "feast_hbev", "feast_hbgv", "feast", "feast_banded", "issymmetric",
-    "ishermitian",
+    "ishermitian", "feast_general", "feast_gcsrev", "feast_gcsrgv", "feast_geev", "feast_gegv", "feast_gbev", "feast_gbgv",
 ]
 
 
@@ -250,6 +250,109 @@ def feast_hbgv(A, B, kla, klb, Emin, Emax, M0, fpm, **kw):
     return _hermitian_solve("band", sA, sB, N, Emin, Emax, M0, fpm, False, **kw)
 
 
+# ---- general (non-Hermitian) problems: kernel/feast_kernel.jl:646-962 behind the storage drivers ---------------------
+def _general_solve(kind, setA, setB, N, Emid, r, M0, fpm, contour=None, solver="direct", solver_tol=0.0, solver_maxiter=500,
+                   solver_restart=30, Q0=None, engine=None, **extras):
+    from . import check_feast_grci_input, feast_gcontour, feastdefault_
+    feastdefault_(fpm)
+    check_feast_grci_input(N, M0, complex(Emid), float(r), fpm)
+    solver_choice = "gmres" if solver == "iterative" else solver
+    if solver_choice not in ("direct", "gmres", "bicgstab"):
+        raise ValueError(f"Unsupported solver option '{solver}'. Use :direct, :gmres, or :iterative.")
+    kw = dict(solver_tol=solver_tol, solver_maxiter=max(int(solver_maxiter), 2000 if kind == "sparse" else 1),
+              solver="bicgstab" if kind == "sparse" else "direct", solver_restart=3 if solver_restart == 30 else int(solver_restart))
+    for k in ("inner_rel", "shard", "check_every"):
+        if k in extras:
+            kw[k] = extras.pop(k)
+    if extras:
+        raise TypeError(f"unexpected keyword arguments: {sorted(extras)}")
+    eng = _eng(engine)
+    setA(eng)
+    if setB is not None:
+        setB(eng)
+    else:
+        eng.clear_b()
+    eng.init_distributed()
+    Zne, Wne = contour if contour is not None else feast_gcontour(complex(Emid), float(r), fpm)
+    return eng.solve_contour(complex(Emid), float(r), int(M0), fpm, Zne, Wne, Q0=Q0, **kw)
+
+
+def feast_gcsrgv(A, B, Emid, r, M0, fpm, **kw):
+    """feast_gcsrgv!(A, B, Emid, r, M0, fpm; solver, ...) -- sparse/feast_sparse.jl:873-1006."""
+    N, sA, sB = _sparse_pair(A.astype(np.complex128), None if B is None else B.astype(np.complex128), L.GEN)
+    return _general_solve("sparse", sA, sB, N, Emid, r, M0, fpm, **kw)
+
+
+def feast_gcsrev(A, Emid, r, M0, fpm, **kw):
+    """feast_gcsrev! -- sparse/feast_sparse.jl:1531-1551 (B = I)."""
+    return feast_gcsrgv(A, None, Emid, r, M0, fpm, **kw)
+
+
+def _dense_general(A, B):
+    A = np.asarray(A, dtype=np.complex128)
+    N = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != N:
+        raise ValueError("Matrix A must be square")
+    if B is not None:
+        B = np.asarray(B, dtype=np.complex128)
+        if B.shape != (N, N):
+            raise ValueError("Matrix B must match size of A")
+    setA = lambda e: e.set_dense(L.A, A, L.GEN)
+    setB = None if B is None else (lambda e: e.set_dense(L.B, B, L.GEN))
+    return N, setA, setB
+
+
+def feast_gegv(A, B, Emid, r, M0, fpm, **kw):
+    """feast_gegv! -- dense/feast_dense.jl:402-593."""
+    N, sA, sB = _dense_general(A, B)
+    return _general_solve("dense", sA, sB, N, Emid, r, M0, fpm, **kw)
+
+
+def feast_geev(A, Emid, r, M0, fpm, **kw):
+    """feast_geev! -- dense/feast_dense.jl:812-828."""
+    return feast_gegv(A, None, Emid, r, M0, fpm, **kw)
+
+
+def feast_gbgv(A, B, kla, klb, Emid, r, M0, fpm, **kw):
+    """feast_gbgv!: general band (2k+1) x n storage -- banded/feast_banded.jl:1548-1574, 1088-1284."""
+    A = np.asarray(A, dtype=np.complex128)
+    N = A.shape[1]
+    if A.shape[0] < 2 * kla + 1:
+        raise ValueError("A matrix storage insufficient for kla")
+    setA = lambda e: e.set_band(L.A, A, kla, L.GEN)
+    setB = None
+    if B is not None:
+        B = np.asarray(B, dtype=np.complex128)
+        if B.shape[0] < 2 * klb + 1 or B.shape[1] != N:
+            raise ValueError("B matrix storage insufficient for klb")
+        setB = lambda e: e.set_band(L.B, B, klb, L.GEN)
+    return _general_solve("band", setA, setB, N, Emid, r, M0, fpm, **kw)
+
+
+def feast_gbev(A, kla, Emid, r, M0, fpm, **kw):
+    """feast_gbev! -- banded/feast_banded.jl:1576-1600."""
+    return feast_gbgv(A, None, kla, 0, Emid, r, M0, fpm, **kw)
+
+
+def feast_general(A, *args, M0=10, fpm=None, **kw):
+    """feast_general(A, center, radius; M0, fpm) / feast_general(A, B, center, radius; ...) -- interfaces/feast_interfaces.jl:274-379."""
+    import scipy.sparse as sp
+    from . import feastinit
+    if len(args) == 2:
+        B, (center, radius) = None, args
+    elif len(args) == 3:
+        B, center, radius = args
+    else:
+        raise TypeError("feast_general(A, center, radius) or feast_general(A, B, center, radius)")
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Matrix must be square")
+    fpm = feastinit() if fpm is None else fpm
+    M0 = min(int(M0), A.shape[0])
+    if sp.issparse(A):
+        return feast_gcsrgv(sp.csc_matrix(A), None if B is None else sp.csc_matrix(B), center, radius, M0, fpm, **kw)
+    return feast_gegv(np.asarray(A), None if B is None else np.asarray(B), center, radius, M0, fpm, **kw)
+
+
 # ---- high level (interfaces/feast_interfaces.jl:143-272, 381-420) ----------------------------------------
 def feast(A, *args, M0=10, fpm=None, **kw):
     """feast(A, (Emin,Emax); M0, fpm) / feast(A, B, (Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272."""
@@ -310,6 +413,8 @@ _ALIASES = {
     "dfeast_sbev": feast_sbev, "dfeast_sbgv": feast_sbgv, "zfeast_hbev": feast_hbev, "zfeast_hbgv": feast_hbgv,
     "dfeast_scsrevx": feast_scsrevx, "dfeast_scsrgvx": feast_scsrgvx, "zfeast_hcsrevx": feast_hcsrevx, "zfeast_hcsrgvx": feast_hcsrgvx,
     "dfeast_syevx": feast_syevx, "dfeast_sygvx": feast_sygvx, "zfeast_heevx": feast_heevx, "zfeast_hegvx": feast_hegvx,
+    "zfeast_gcsrev": feast_gcsrev, "zfeast_gcsrgv": feast_gcsrgv, "zfeast_geev": feast_geev, "zfeast_gegv": feast_gegv,
+    "zfeast_gbev": feast_gbev, "zfeast_gbgv": feast_gbgv, "zifeast_gcsrev": feast_gcsrev, "zifeast_gcsrgv": feast_gcsrgv,
 }
 for _name, _fn in list(_ALIASES.items()):
     globals()[_name] = _alias(_fn)

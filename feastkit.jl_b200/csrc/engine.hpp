@@ -110,6 +110,12 @@ struct feastcuda_handle_s {
   feastcuda::DBuf blk[feastcuda::BS_COUNT];
   feastcuda::DBuf partial, partial_r, kstate, small, small2, gram_partial, stage, red_ws;
   feastcuda::DBuf lz_scal, lz_coef, lz_state;   // multi-shift Lanczos: per-step scalars, pass-2 coefficients, shift recurrences
+  // staged-gather tile plan (kernels_lanczos.cuh: k_lz_spmm_staged), built lazily per matrix and stage capacity
+  feastcuda::DBuf lzp_wmeta, lzp_run0, lzp_runs, lzp_lcol;
+  int lzp_smax = 0, lzp_ntiles = 0;
+  bool lzp_built = false, lzp_usable = false;
+  int lz_egrid_mult = 4;    // CTAs per SM of the elementwise Lanczos kernels (partial rows the scalar kernels reduce)
+  int lz_staged = 0;        // 1: use the staged gather where the plan allows it
   int lz_threads = 512;     // CTA size of the Lanczos SpMM (512 or 1024)
   int lz_ctas_per_sm = 2;   // persistent CTAs per SM of the Lanczos SpMM (contiguous row chunks keep the band in L1)
   int lz_tile_rows = 64;    // rows per round-robin tile of the Lanczos SpMM

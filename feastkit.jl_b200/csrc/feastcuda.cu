@@ -478,8 +478,93 @@ static int lz_grid_spmm(H* h, int64_t n, int rows_per_step) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)h->sms * h->lz_ctas_per_sm));
 }
 
+// ---- tile plan of the staged gather: greedy tiles of <= LZS_TMAX consecutive rows whose distinct columns fit a stage -----
+static void build_lz_plan(H* h, int smax) {
+  if (h->lzp_built && h->lzp_smax == smax) return;
+  const HostCsr& A = h->hA;
+  const int64_t n = A.n;
+  std::vector<int4> wmeta, runs;
+  std::vector<int> run0{0};
+  std::vector<unsigned short> lcol((size_t)std::max<int64_t>(A.nnz, 1), 0);
+  std::vector<int> cur, tmp, rowc;
+  h->lzp_built = true;
+  h->lzp_smax = smax;
+  h->lzp_usable = false;
+  int64_t row = 0;
+  int ntiles = 0;
+  while (row < n) {
+    cur.clear();
+    int64_t r1 = row;
+    while (r1 < n && r1 - row < LZS_TMAX) {
+      rowc.assign(A.col.begin() + A.ptr[r1], A.col.begin() + A.ptr[r1 + 1]);
+      std::sort(rowc.begin(), rowc.end());
+      tmp.clear();
+      std::set_union(cur.begin(), cur.end(), rowc.begin(), rowc.end(), std::back_inserter(tmp));
+      if ((int)tmp.size() > smax) break;
+      cur.swap(tmp);
+      ++r1;
+    }
+    if (r1 == row) return;   // a single row references more vector rows than a stage holds: keep the direct kernel
+    if (cur.empty()) cur.push_back((int)row);   // rows without entries still need a non-empty stage
+    for (size_t i = 0; i < cur.size();) {
+      size_t j = i + 1;
+      while (j < cur.size() && cur[j] == cur[j - 1] + 1 && j - i < 64) ++j;
+      runs.push_back(make_int4(cur[i], (int)(j - i), (int)i, 0));
+      i = j;
+    }
+    run0.push_back((int)runs.size());
+    for (int w = 0; w < LZS_TMAX; ++w) {
+      const int64_t r = row + w;
+      if (r < r1) {
+        wmeta.push_back(make_int4((int)r, A.ptr[r], A.ptr[r + 1] - A.ptr[r], 0));
+        for (int p = A.ptr[r]; p < A.ptr[r + 1]; ++p)
+          lcol[p] = (unsigned short)(std::lower_bound(cur.begin(), cur.end(), A.col[p]) - cur.begin());
+      } else wmeta.push_back(make_int4(-1, 0, 0, 0));
+    }
+    ++ntiles;
+    row = r1;
+  }
+  h->lzp_wmeta.ensure(wmeta.size() * sizeof(int4));
+  h->lzp_run0.ensure(run0.size() * sizeof(int));
+  h->lzp_runs.ensure(runs.size() * sizeof(int4));
+  h->lzp_lcol.ensure(lcol.size() * sizeof(unsigned short));
+  FC_CUDA(cudaMemcpyAsync(h->lzp_wmeta.p, wmeta.data(), wmeta.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(h->lzp_run0.p, run0.data(), run0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(h->lzp_runs.p, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(h->lzp_lcol.p, lcol.data(), lcol.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  sync(h);
+  h->lzp_ntiles = ntiles;
+  h->lzp_usable = true;
+}
+
+template <int MODE>
+static bool lz_launch_staged(H* h, LzArgs& a, int* grid_out) {
+  const int P = (a.m + 1) / 2;
+  if (!h->lz_staged || P <= 16 || P > 32) return false;
+  const int pitch = P * 16;
+  const int smax = std::min(1024, 51200 / pitch);
+  build_lz_plan(h, smax);
+  if (!h->lzp_usable) return false;
+  const size_t smem = (size_t)2 * smax * pitch + 16;
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[MODE]) {
+    FC_CUDA(cudaFuncSetAttribute(k_lz_spmm_staged<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    attr_set[MODE] = true;
+  }
+  LzPlanDev pl;
+  pl.wmeta = h->lzp_wmeta.as<int4>(); pl.t_run0 = h->lzp_run0.as<int>(); pl.runs = h->lzp_runs.as<int4>();
+  pl.lcol = h->lzp_lcol.as<unsigned short>(); pl.ntiles = h->lzp_ntiles; pl.smax = smax;
+  const int grid = std::max(1, std::min(h->lzp_ntiles, h->sms * 2));
+  *grid_out = grid;
+  k_lz_spmm_staged<MODE><<<grid, LZS_THREADS, smem, h->stream>>>(a, pl);
+  check_launch(h);
+  h->stats.spmm_launches++;
+  return true;
+}
+
 template <int MODE>
 static void lz_launch(H* h, LzArgs& a, int* grid_out) {
+  if (lz_launch_staged<MODE>(h, a, grid_out)) return;
   const int P = (a.m + 1) / 2;
   // G lanes per row, NC column-pair chunks per lane
 #define FC_LZ(G, NC)                                                                       \
@@ -521,7 +606,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   check_every = std::max(1, check_every);
   const int P = (nc + 1) / 2;
   const int pp = pow2_ge(P);
-  const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * 8));
+  const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
 
   // ---- device scalars ------------------------------------------------------------------------------------------
   const size_t rowsz = (size_t)FC_MAXCOLS;
@@ -1014,7 +1099,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       if (o.adaptive && !first && std::isfinite(eps_val) && eps_val > 0) {
         // the sweep contracts the eigen-residual by roughly its inner target: when the tolerance is within reach, aim at it
         const double t = 0.1 * eps_tol / eps_val;
-        if (t >= 1e-5) target = std::min(0.1, t);
+        if (t >= 1e-6) target = std::min(0.1, t);
       }
       const int kmax = (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter;
       if (nc > 0) {
@@ -1374,6 +1459,8 @@ int feastcuda_create(feastcuda_handle* out, int device) {
   if (const char* e = getenv("FEASTCUDA_LZ_THREADS")) h->lz_threads = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_CTAS")) h->lz_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("FEASTCUDA_LZ_TILE")) h->lz_tile_rows = std::max(1, atoi(e));
+  if (const char* e = getenv("FEASTCUDA_LZ_STAGED")) h->lz_staged = atoi(e);
+  if (const char* e = getenv("FEASTCUDA_LZ_EGRID")) h->lz_egrid_mult = std::max(1, std::min(8, atoi(e)));
   *out = h;
   FC_CATCH
 }
@@ -1384,7 +1471,7 @@ int feastcuda_destroy(feastcuda_handle h) {
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
   DBuf* bufs[] = {&h->partial, &h->partial_r, &h->kstate, &h->small, &h->small2, &h->gram_partial, &h->stage, &h->red_ws,
-                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB};
+                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->lzp_wmeta, &h->lzp_run0, &h->lzp_runs, &h->lzp_lcol, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB};
   for (DBuf* b : bufs) b->release();
   for (auto& b : h->lu_cache) b.release();
   for (auto& b : h->piv_cache) b.release();
@@ -1432,6 +1519,7 @@ static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t
   if (which == FEASTCUDA_A) {
     ingest_csr(h->hA, n, nnz, ptr, idx, val, cplx, base, fmt, structure);
     h->dA.uploaded = false;
+    h->lzp_built = false;
     if (h->kind != OP_SPARSE) { h->has_b = false; h->hB.set = false; }
     h->kind = OP_SPARSE;
     h->n = n;

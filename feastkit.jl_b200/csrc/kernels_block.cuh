@@ -132,19 +132,29 @@ __global__ void __launch_bounds__(256) k_colnorm2(int64_t n, int m, int mp, int6
 template <typename T>
 __device__ __forceinline__ void reduce_partials(const T* __restrict__ partial, int nslots, int nblocks, int pstride, int m,
                                                 T* sm_out /*[nslots*FC_MAXCOLS]*/, T* sm_tmp /*[1024]*/) {
-  const int mp = FC_MAXCOLS;
+  // the block's threads are split into `nparts` groups of `mp` (smallest power of two >= m, at least 32) columns: fewer
+  // columns -> more groups -> shorter dependent chains; the summation order is fixed for a given (m, nblocks)
+  int mp = 32;
+  while (mp < m) mp <<= 1;
   const int c = threadIdx.x % mp, part = threadIdx.x / mp, nparts = blockDim.x / mp;
   for (int s = 0; s < nslots; ++s) {
-    T acc = zero_of<T>::v();
-    if (c < m)
-      for (int b = part; b < nblocks; b += nparts) acc = acc + partial[((int64_t)s * nblocks + b) * pstride + c];
+    T acc0 = zero_of<T>::v(), acc1 = zero_of<T>::v();
+    if (c < m) {
+      const T* base = partial + (int64_t)s * nblocks * pstride + c;
+      int b = part;
+      for (; b + nparts < nblocks; b += 2 * nparts) {
+        acc0 = acc0 + base[(int64_t)b * pstride];
+        acc1 = acc1 + base[(int64_t)(b + nparts) * pstride];
+      }
+      if (b < nblocks) acc0 = acc0 + base[(int64_t)b * pstride];
+    }
     __syncthreads();
-    sm_tmp[threadIdx.x] = acc;
+    sm_tmp[threadIdx.x] = acc0 + acc1;
     __syncthreads();
     if (part == 0 && c < m) {
       T t = sm_tmp[c];
       for (int q = 1; q < nparts; ++q) t = t + sm_tmp[q * mp + c];
-      sm_out[s * mp + c] = t;
+      sm_out[s * FC_MAXCOLS + c] = t;
     }
   }
   __syncthreads();

@@ -455,4 +455,210 @@ __global__ void __launch_bounds__(1024) k_lz_scal2(LzScalars s, int j, const dou
   }
 }
 
+
+
+// =====================================================================================================================
+// Staged gather: the distinct vector rows a tile of <= 16 consecutive matrix rows references are brought into shared
+// memory by bulk asynchronous copies (cp.async.bulk + mbarrier, the TMA 1-D path), double buffered, so the bytes in flight
+// cost no registers and the gather itself is LDS.128 from a dense, conflict-free stage.  The tile plan (which vector rows,
+// as runs of consecutive rows; the stage slot of every stored entry) is computed once per matrix on the host
+// (build_lz_plan in feastcuda.cu).  Tiles are dealt round robin to the CTAs like in k_lz_spmm.
+// One warp = one matrix row of the tile; lanes = column pairs (m in (32, 64] uses all lanes).
+// =====================================================================================================================
+constexpr int LZS_TMAX = 16;        // rows per tile = warps per CTA
+constexpr int LZS_THREADS = 32 * LZS_TMAX;
+
+struct LzPlanDev {
+  const int4* wmeta;            // [ntiles * LZS_TMAX] {row (or -1), p0, count, 0}
+  const int* t_run0;            // [ntiles + 1]
+  const int4* runs;             // {first vector row, count, first slot, 0}
+  const unsigned short* lcol;   // [nnz] stage slot of the entry's column
+  int ntiles;
+  int smax;                     // slots per stage
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(LZS_THREADS, 2) k_lz_spmm_staged(LzArgs a, LzPlanDev pl) {
+  if (a.done != nullptr && *a.done != 0) return;
+  extern __shared__ __align__(128) unsigned char lzs_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = (a.m + 1) >> 1;
+  const int pitch = P * 16;                    // bytes of one staged vector row
+  const unsigned ldu = (unsigned)a.ld;
+  unsigned char* stage[2] = {lzs_smem, lzs_smem + (size_t)pl.smax * pitch};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lzs_smem + (size_t)2 * pl.smax * pitch);
+  __shared__ double2 s_sc[4][FC_MAXCOLS / 2];
+  for (int i = tid; i < 4 * (FC_MAXCOLS / 2); i += LZS_THREADS) {
+    const int w = i / (FC_MAXCOLS / 2), pc = i % (FC_MAXCOLS / 2);
+    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta) : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : a.s_coef));
+    s_sc[w][pc] = lz_scal2(src, 2 * pc, a.m);
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int grid = (int)gridDim.x;
+  const int my_tiles = ((int)blockIdx.x < pl.ntiles) ? (pl.ntiles - 1 - (int)blockIdx.x) / grid + 1 : 0;
+  const bool full_width = (a.ld == 2 * (int64_t)P);
+
+  // producer: warp 0 arms the stage's barrier with the byte count, then its lanes issue one bulk copy per run
+  auto issue = [&](int it, int s) {
+    const int tile = (int)blockIdx.x + it * grid;
+    const int r0 = pl.t_run0[tile], r1 = pl.t_run0[tile + 1];
+    if (lane == 0) {
+      const int4 last = pl.runs[r1 - 1];
+      mbar_expect_tx(&bars[s], (unsigned)(last.z + last.y) * (unsigned)pitch);
+    }
+    __syncwarp();
+    for (int r = r0 + lane; r < r1; r += 32) {
+      const int4 ru = pl.runs[r];
+      unsigned char* dst = stage[s] + (size_t)ru.z * pitch;
+      const double* src = a.U + (int64_t)ru.x * a.ld;
+      if (full_width) bulk_g2s(dst, src, (unsigned)ru.y * (unsigned)pitch, &bars[s]);
+      else
+        for (int q = 0; q < ru.y; ++q) bulk_g2s(dst + (size_t)q * pitch, src + (int64_t)q * a.ld, (unsigned)pitch, &bars[s]);
+    }
+  };
+  if (warp == 0) {
+    if (my_tiles > 0) issue(0, 0);
+    if (my_tiles > 1) issue(1, 1);
+  }
+
+  const int pcl = 2 * min(lane, P - 1);
+  const double* Ul = a.U + pcl;
+  const double* Pl = a.prev + pcl;
+  double* Ol = a.out + pcl;
+  double* Ql = a.Q + pcl;
+  const bool lane_ok = lane < P;
+  double2 dot = make_double2(0.0, 0.0);
+
+  // per-warp metadata pipeline: {row, p0, count} two iterations ahead, the row's first 32 (slot, value) pairs one ahead
+  auto meta_of = [&](int it) -> int4 {
+    if (it >= my_tiles) return make_int4(-1, 0, 0, 0);
+    return pl.wmeta[((int64_t)blockIdx.x + (int64_t)it * grid) * LZS_TMAX + warp];
+  };
+  int4 m_cur = meta_of(0), m_nxt = meta_of(1);
+  int l_cur = 0;
+  double a_cur = 0.0;
+  if (lane < m_cur.z) { l_cur = pl.lcol[m_cur.y + lane]; a_cur = a.val[m_cur.y + lane]; }
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int s = it & 1;
+    const int4 m_fut = meta_of(it + 2);
+    int l_nxt = 0;
+    double a_nxt = 0.0;
+    if (lane < m_nxt.z) { l_nxt = pl.lcol[m_nxt.y + lane]; a_nxt = a.val[m_nxt.y + lane]; }
+    const int row = m_cur.x;
+    const bool valid = row >= 0;
+    const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
+    double2 uo = make_double2(0.0, 0.0), pv = make_double2(0.0, 0.0), qv = make_double2(0.0, 0.0);
+    if (valid) {
+      if constexpr (MODE != LZ_PLAIN) uo = ldg2(Ul + eo_own);
+      if constexpr (MODE == LZ_P1 || MODE == LZ_P2) pv = ldg2(Pl + eo_own);
+      if constexpr (MODE == LZ_P2) qv = ldg2(Ql + eo_own);
+    }
+    mbar_wait(&bars[s], (unsigned)((it >> 1) & 1));
+    double2 acc = make_double2(0.0, 0.0);
+    if (valid) {
+      const unsigned char* sb = stage[s] + (lane_ok ? lane : P - 1) * 16;
+      const int p0 = m_cur.y, cnt_all = m_cur.z;
+      int myl = l_cur;
+      double mya = a_cur;
+      for (int pb = 0; pb < cnt_all; pb += 32) {
+        const int cnt = min(32, cnt_all - pb);
+        if (pb != 0) {
+          myl = 0;
+          mya = 0.0;
+          if (lane < cnt) { myl = pl.lcol[p0 + pb + lane]; mya = a.val[p0 + pb + lane]; }
+        }
+        for (int t = 0; t < cnt; t += 4) {
+          int sl[4];
+          double aa[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            sl[u] = __shfl_sync(0xffffffffu, myl, t + u);
+            aa[u] = __shfl_sync(0xffffffffu, mya, t + u);     // lanes >= cnt hold weight 0 and slot 0 (always staged)
+          }
+          double2 xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xv[u] = *reinterpret_cast<const double2*>(sb + (size_t)sl[u] * pitch);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc.x = fma(aa[u], xv[u].x, acc.x);
+            acc.y = fma(aa[u], xv[u].y, acc.y);
+          }
+        }
+      }
+      if (lane_ok) {
+        if constexpr (MODE == LZ_PLAIN) {
+          stg2(Ol + eo_own, acc);
+        } else if constexpr (MODE == LZ_RES) {
+          const double2 th = s_sc[0][lane], cf = s_sc[3][lane];
+          double2 t;
+          t.x = __fma_rn(-th.x, uo.x, acc.x);
+          t.y = __fma_rn(-th.y, uo.y, acc.y);
+          stg2(Ol + eo_own, t);
+          dot.x = fma(t.x, t.x, dot.x);
+          dot.y = fma(t.y, t.y, dot.y);
+          if (a.Q != nullptr) stg2(Ql + eo_own, make_double2(cf.x * uo.x, cf.y * uo.y));
+        } else {
+          const double2 t = lz_t(acc, s_sc[0][lane], s_sc[1][lane], pv);
+          if constexpr (MODE == LZ_P1) {
+            stg2(Ol + eo_own, t);
+            dot.x = fma(uo.x, t.x, dot.x);
+            dot.y = fma(uo.y, t.y, dot.y);
+          } else {
+            const double2 cf = s_sc[3][lane];
+            stg2(Ol + eo_own, lz_next(t, s_sc[2][lane], uo));
+            qv.x = fma(cf.x, uo.x, qv.x);
+            qv.y = fma(cf.y, uo.y, qv.y);
+            stg2(Ql + eo_own, qv);
+          }
+        }
+      }
+    }
+    __syncthreads();                                            // every warp is done reading stage s
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0 && it + 2 < my_tiles) issue(it + 2, s);
+    m_cur = m_nxt; m_nxt = m_fut; l_cur = l_nxt; a_cur = a_nxt;
+  }
+
+  if constexpr (MODE == LZ_P1 || MODE == LZ_RES) {
+    __shared__ double2 red[LZS_TMAX * 32];
+    red[warp * 32 + lane] = dot;
+    __syncthreads();
+    for (int pc = tid; pc < 32; pc += LZS_THREADS) {
+      if (pc < P) {
+        double sx = 0.0, sy = 0.0;
+        for (int q = 0; q < LZS_TMAX; ++q) { const double2 v = red[q * 32 + pc]; sx += v.x; sy += v.y; }
+        double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
+        o[0] = sx;
+        if (2 * pc + 1 < a.m) o[1] = sy;
+      }
+    }
+  }
+}
+
 }  // namespace feastcuda

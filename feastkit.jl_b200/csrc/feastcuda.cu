@@ -1098,7 +1098,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       if (!(target > 0)) target = tol;
       if (o.adaptive && !first && std::isfinite(eps_val) && eps_val > 0) {
         // the sweep contracts the eigen-residual by roughly its inner target: when the tolerance is within reach, aim at it
-        const double t = 0.1 * eps_tol / eps_val;
+        const double t = 2.0 * eps_tol / eps_val;   // measured: a sweep contracts the residual by 0.04..0.25 x its target
         if (t >= 1e-6) target = std::min(0.1, t);
       }
       const int kmax = (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter;

@@ -65,7 +65,7 @@ typedef struct {
   int32_t keep_going;    /* 1 (inexact mode only): M = 0 after a sweep does not abort, the sweep's Ritz      */
                          /*    vectors seed the next loop (the reference stops with info=5)                   */
   int32_t adaptive;      /* 1 (Lanczos path): once the eigen-residual is within reach of the tolerance, the sweep's     */
-                         /*    inner target becomes 0.1*tol/epsout_prev (clamped to [1e-6, 0.1]) so that it is the last one */
+                         /*    inner target becomes 2*tol/epsout_prev (clamped to [1e-6, 0.1]) so that it is the last one */
   int32_t reserved[3];
 } feastcuda_solver_opts;
 

@@ -323,7 +323,7 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
         if not target > 0:
             target = tol_value
         if adaptive and not first and math.isfinite(epsout) and epsout > 0:
-            t = 0.1 * eps_tol / epsout      # run_interval in csrc/feastcuda.cu: aim the sweep at the tolerance when in reach
+            t = 2.0 * eps_tol / epsout      # run_interval in csrc/feastcuda.cu: aim the sweep at the tolerance when in reach
             if t >= 1e-6:
                 target = min(0.1, t)
         c0, nc = (0, active) if col_slices is None else col_slices(active)

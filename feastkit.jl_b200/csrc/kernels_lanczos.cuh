@@ -288,7 +288,26 @@ __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int
   double2 acc = make_double2(0.0, 0.0);
   if (e.pc < P) {
     const double2 ra = lz_scal2(s_ratio_a, 2 * e.pc, m);
-    for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+    const int64_t stride = (int64_t)gridDim.x * e.rpb;
+    int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub;
+    for (; row + 3 * stride < n; row += 4 * stride) {   // four independent rows in flight per thread (narrow blocks are latency bound)
+      double2 tv[4], uv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t off = (row + q * stride) * ld + 2 * e.pc;
+        tv[q] = ldg2(T + off);
+        uv[q] = ldg2(U + off);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t off = (row + q * stride) * ld + 2 * e.pc;
+        const double2 r = lz_next(tv[q], ra, uv[q]);
+        stg2(T + off, r);
+        acc.x = fma(r.x, r.x, acc.x);
+        acc.y = fma(r.y, r.y, acc.y);
+      }
+    }
+    for (; row < n; row += stride) {
       const int64_t off = row * ld + 2 * e.pc;
       const double2 r = lz_next(ldg2(T + off), ra, ldg2(U + off));
       stg2(T + off, r);

@@ -57,14 +57,20 @@ __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<d
 // col*ld of the gathered row (32-bit: the host guarantees n*ld < 2^32), so an address is one IMAD.WIDE from the lane's
 // base pointer Ul[k] = U + 2*(g + G k).  Padding slots of the last batch gather the lane's own row with weight 0 and lanes
 // beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
+// Narrow groups (G <= 4 lanes per row) also receive the row's SECOND chunk of G entries prefetched (myo2, mya2): a
+// 7-point row then needs no dependent metadata load inside the loop even with 4 lanes per row.
 template <int G, int NC>
-__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int p0, int p1, unsigned myo, double mya, int g,
-                                          unsigned gmask, const double* const (&Ul)[NC], double2 (&acc)[NC]) {
+__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int p0, int p1, unsigned myo, double mya, unsigned myo2,
+                                          double mya2, int g, unsigned gmask, const double* const (&Ul)[NC], double2 (&acc)[NC]) {
   constexpr int UN = (G >= 4) ? 4 : G;
+  constexpr bool PF2 = (G <= 4);
   const unsigned ldu = (unsigned)a.ld;
   for (int pb = p0; pb < p1; pb += G) {
     const int cnt = min(G, p1 - pb);
-    if (pb != p0) {
+    if (PF2 && pb == p0 + G) {
+      myo = myo2;
+      mya = mya2;
+    } else if (pb != p0) {
       myo = row_eo;
       mya = 0.0;
       if (g < cnt) { myo = (unsigned)a.col[pb + g] * ldu; mya = a.val[pb + g]; }
@@ -179,9 +185,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   int p0_cur = 0, p1_cur = 0, p0_nxt = 0, p1_nxt = 0;
   if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
   if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
-  unsigned o_cur = (r_cur < n ? (unsigned)r_cur : 0u) * ldu;
-  double a_cur = 0.0;
+  constexpr bool PF2 = (G <= 4);
+  unsigned o_cur = (r_cur < n ? (unsigned)r_cur : 0u) * ldu, o_cur2 = o_cur;
+  double a_cur = 0.0, a_cur2 = 0.0;
   if (g < p1_cur - p0_cur) { o_cur = (unsigned)a.col[p0_cur + g] * ldu; a_cur = a.val[p0_cur + g]; }
+  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = (unsigned)a.col[p0_cur + G + g] * ldu; a_cur2 = a.val[p0_cur + G + g]; }
 
   for (int it = 0; it < niter; ++it) {
     const int row = r_cur;
@@ -189,9 +197,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
     const int r_fut = next_row();
     int p0_fut = 0, p1_fut = 0;
     if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
-    unsigned o_nxt = (r_nxt < n ? (unsigned)r_nxt : 0u) * ldu;
-    double a_nxt = 0.0;
+    unsigned o_nxt = (r_nxt < n ? (unsigned)r_nxt : 0u) * ldu, o_nxt2 = o_nxt;
+    double a_nxt = 0.0, a_nxt2 = 0.0;
     if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = a.val[p0_nxt + g]; }
+    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = (unsigned)a.col[p0_nxt + G + g] * ldu; a_nxt2 = a.val[p0_nxt + G + g]; }
 
     // own-row operands first (independent of the gather); invalid rows and inactive lanes read valid dummies
     const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
       if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
       if constexpr (MODE == LZ_P1 || MODE == LZ_P2) pv[k] = ldg2(Pl[k] + eo_own);
     }
-    lz_gather<G, NC>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, g, gmask, Ul, acc);
+    lz_gather<G, NC>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int pc = g + G * k;
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
         }
       }
     }
-    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; o_cur = o_nxt; a_cur = a_nxt;
+    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; o_cur = o_nxt; a_cur = a_nxt; o_cur2 = o_nxt2; a_cur2 = a_nxt2;
     r_nxt = r_fut; p0_nxt = p0_fut; p1_nxt = p1_fut;
   }
 

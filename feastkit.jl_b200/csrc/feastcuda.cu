@@ -1056,7 +1056,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
   FC_REQUIRE(h->have_subspace && h->sub_m0 == m0 && h->ws_n == n, "initial subspace not uploaded for this (n, M0)");
   feastcuda_solver_opts o = optsp ? *optsp : default_opts();
   const double tol = (o.tol == 0.0) ? std::pow(10.0, -(double)fpm[2]) : o.tol;
-  const double eps_tol = host_feast_tolerance(fpm);
+  const double eps_tol = std::max(host_feast_tolerance(fpm), o.eps_floor > 0 ? o.eps_floor : 0.0);
   const int maxloop = (int)fpm[3];
   const bool real_mode = (o.filter == FEASTCUDA_FILTER_TRUE) && pencil_is_real(h) && subspace_is_real;
   const bool iterative = (h->kind == OP_SPARSE);
@@ -1277,7 +1277,7 @@ static void run_contour(H* h, zc Emid, double r, int m0, int64_t* fpm, const zc*
   FC_REQUIRE(h->have_subspace && h->sub_m0 == m0 && h->ws_n == n, "initial subspace not uploaded for this (n, M0)");
   feastcuda_solver_opts o = optsp ? *optsp : default_opts();
   const double tol = (o.tol == 0.0) ? std::pow(10.0, -(double)fpm[2]) : o.tol;
-  const double eps_tol = host_feast_tolerance(fpm);
+  const double eps_tol = std::max(host_feast_tolerance(fpm), o.eps_floor > 0 ? o.eps_floor : 0.0);
   const int maxloop = (int)fpm[3];
   const bool iterative = (h->kind == OP_SPARSE);
   int shard = iterative ? o.shard : FEASTCUDA_SHARD_NODES;

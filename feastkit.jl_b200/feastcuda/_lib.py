@@ -25,7 +25,7 @@ class SolverOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("tol", C.c_double), ("maxiter", C.c_int32), ("restart", C.c_int32),
                 ("inner_rel", C.c_double), ("ritz_guess", C.c_int32), ("filter", C.c_int32), ("shard", C.c_int32),
                 ("check_every", C.c_int32), ("q0_real", C.c_int32), ("x_real", C.c_int32), ("inner_rel0", C.c_double),
-                ("maxiter0", C.c_int32), ("keep_going", C.c_int32), ("adaptive", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("maxiter0", C.c_int32), ("keep_going", C.c_int32), ("adaptive", C.c_int32), ("reserved", C.c_int32), ("eps_floor", C.c_double)]
 
 
 class Stats(C.Structure):

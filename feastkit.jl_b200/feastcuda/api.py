@@ -63,7 +63,7 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
         kw["inner_rel"] = 1e-3
         kw["adaptive"] = True
     kw["filter"] = "true"
-    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every", "inner_rel0", "maxiter0", "keep_going", "adaptive"):
+    for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every", "inner_rel0", "maxiter0", "keep_going", "adaptive", "eps_floor"):
         if k in extras:
             kw[k] = extras.pop(k)
     if extras:
@@ -261,7 +261,7 @@ def _general_solve(kind, setA, setB, N, Emid, r, M0, fpm, contour=None, solver="
         raise ValueError(f"Unsupported solver option '{solver}'. Use :direct, :gmres, or :iterative.")
     kw = dict(solver_tol=solver_tol, solver_maxiter=max(int(solver_maxiter), 2000 if kind == "sparse" else 1),
               solver="bicgstab" if kind == "sparse" else "direct", solver_restart=3 if solver_restart == 30 else int(solver_restart))
-    for k in ("inner_rel", "shard", "check_every"):
+    for k in ("inner_rel", "shard", "check_every", "eps_floor"):
         if k in extras:
             kw[k] = extras.pop(k)
     if extras:
@@ -420,3 +420,32 @@ for _name, _fn in list(_ALIASES.items()):
     globals()[_name] = _alias(_fn)
     globals()["p" + _name] = _alias(_fn)
     __all__ += [_name, "p" + _name]
+
+
+# Float32 / ComplexF32 families (interfaces/feast_precision_aliases.jl:10-117, 163-423; ps/pc: 497-771): inputs are widened,
+# the engine computes in Float64 and stops at the reference's single-precision tolerance max(10^-fpm[3], sqrt(eps(Float32)))
+# (core/feast_parameters.jl:398-405); results are narrowed to Float32 / ComplexF32 like FeastResult{Float32,...}.
+_EPS32 = float(np.sqrt(np.finfo(np.float32).eps))
+
+
+def _alias32(fn):
+    def wrapper(*a, comm=None, use_threads=None, **kw):
+        from . import FeastResult
+        args = [x.astype(np.complex128 if np.iscomplexobj(x) else np.float64) if hasattr(x, "astype") and hasattr(x, "shape") else x
+                for x in a]
+        if kw.get("Q0") is not None:
+            kw["Q0"] = np.asarray(kw["Q0"]).astype(np.complex128 if np.iscomplexobj(kw["Q0"]) else np.float64)
+        r = fn(*args, eps_floor=_EPS32, **kw)
+        cq = np.complex64 if np.iscomplexobj(r.q) else np.float32
+        cl = np.complex64 if np.iscomplexobj(r.lambda_) else np.float32
+        return FeastResult(r.lambda_.astype(cl), r.q.astype(cq), r.M, r.res.astype(np.float32), r.info, float(np.float32(r.epsout)),
+                           r.loop, r.stats)
+    wrapper.__doc__ = f"single-precision alias of {fn.__name__} (interfaces/feast_precision_aliases.jl)"
+    return wrapper
+
+
+for _name, _fn in list(_ALIASES.items()):
+    _n32 = {"d": "s", "z": "c"}[_name[0]] + _name[1:]
+    globals()[_n32] = _alias32(_fn)
+    globals()["p" + _n32] = _alias32(_fn)
+    __all__ += [_n32, "p" + _n32]

@@ -35,7 +35,8 @@ struct SolverOpts              # feastcuda_solver_opts (88 bytes, C layout)
     maxiter0::Cint
     keep_going::Cint
     adaptive::Cint
-    reserved::NTuple{3,Cint}
+    reserved::Cint
+    eps_floor::Cdouble
 end
 
 # FeastResult{T,VT} (core/feast_types.jl:85-98) -- same fields, arrays trimmed to M
@@ -131,7 +132,7 @@ end
 # (sparse/feast_sparse.jl:246-499) and _feast_banded_complex_hermitian (banded/feast_banded.jl:561-823)
 function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{Int}, ::Type{VT};
                          Zne=nothing, Wne=nothing, solver::Symbol=:direct, solver_tol::Real=0.0, solver_maxiter::Int=500,
-                         solver_restart::Int=30, sparse::Bool=false) where {VT}
+                         solver_restart::Int=30, sparse::Bool=false, eps_floor::Float64=0.0) where {VT}
     feastdefault!(fpm)
     # check_feast_srci_input (core/feast_aux.jl:369-399): thrown before any device call, exactly as the reference does
     N > 0 || throw(ArgumentError("Matrix size N must be positive"))
@@ -150,7 +151,7 @@ function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{
     eng_solver = sparse ? (solver_choice == :bicgstab ? SOLVER_BICGSTAB : SOLVER_MSLANCZOS) :
                           (solver_choice == :direct ? SOLVER_DIRECT : SOLVER_BICGSTAB)
     opts = Ref(SolverOpts(eng_solver, solver_tol, solver_maxiter, solver_restart == 30 ? 3 : solver_restart,
-                          sparse ? 1e-3 : 0.0, sparse ? 1 : 0, FILTER_TRUE, 0, 16, 0, real_result ? 1 : 0, 0.0, 0, 0, sparse ? 1 : 0, (Cint(0), Cint(0), Cint(0))))
+                          sparse ? 1e-3 : 0.0, sparse ? 1 : 0, FILTER_TRUE, 0, 16, 0, real_result ? 1 : 0, 0.0, 0, 0, sparse ? 1 : 0, Cint(0), eps_floor))
     lambda = zeros(Float64, M0); res = zeros(Float64, M0); X = zeros(VT, N, M0)
     M = Ref{Int64}(0); info = Ref{Int64}(0); loop = Ref{Int64}(0); epsout = Ref{Float64}(0.0)
     GC.@preserve fpm Zne Wne lambda res X begin
@@ -220,6 +221,20 @@ for (alias, target) in ((:dfeast_scsrev!, :feast_scsrev!), (:dfeast_scsrgv!, :fe
                         (:dfeast_sbgv!, :feast_sbgv!), (:zfeast_hbev!, :feast_hbev!), (:zfeast_hbgv!, :feast_hbgv!))
     @eval $alias(args...; comm=nothing, use_threads=nothing, kw...) = $target(args...; kw...)
     @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = $target(args...; kw...)
+end
+
+# Float32 / ComplexF32 names (interfaces/feast_precision_aliases.jl:10-117,163-423): inputs are widened, the engine computes in
+# Float64 and stops at the reference's single-precision tolerance max(10^-fpm[3], sqrt(eps(Float32))) (core/feast_parameters.jl:398-405),
+# results are narrowed -- FeastResult{Float32,...} like the reference returns.
+const _EPS32 = Float64(sqrt(eps(Float32)))
+_narrow(r::FeastResult{Float64,Float64}) = FeastResult{Float32,Float32}(Float32.(r.lambda), Float32.(r.q), r.M, Float32.(r.res), r.info, Float32(r.epsout), r.loop)
+_narrow(r::FeastResult{Float64,ComplexF64}) = FeastResult{Float32,ComplexF32}(Float32.(r.lambda), ComplexF32.(r.q), r.M, Float32.(r.res), r.info, Float32(r.epsout), r.loop)
+for (alias, target) in ((:sfeast_scsrev!, :feast_scsrev!), (:sfeast_scsrgv!, :feast_scsrgv!), (:cfeast_hcsrev!, :feast_hcsrev!),
+                        (:cfeast_hcsrgv!, :feast_hcsrgv!), (:sfeast_syev!, :feast_syev!), (:sfeast_sygv!, :feast_sygv!),
+                        (:cfeast_heev!, :feast_heev!), (:cfeast_hegv!, :feast_hegv!), (:sfeast_sbev!, :feast_sbev!),
+                        (:sfeast_sbgv!, :feast_sbgv!), (:cfeast_hbev!, :feast_hbev!), (:cfeast_hbgv!, :feast_hbgv!))
+    @eval $alias(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, kw...))
+    @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, kw...))
 end
 
 # high-level feast(A[,B],(Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272 (dispatch only)

@@ -66,7 +66,9 @@ typedef struct {
                          /*    vectors seed the next loop (the reference stops with info=5)                   */
   int32_t adaptive;      /* 1 (Lanczos path): once the eigen-residual is within reach of the tolerance, the sweep's     */
                          /*    inner target becomes 2*tol/epsout_prev (clamped to [1e-6, 0.1]) so that it is the last one */
-  int32_t reserved[3];
+  int32_t reserved;
+  double  eps_floor;     /* > 0: the convergence tolerance is max(10^-fpm[3], eps_floor) -- the Float32 entry points      */
+                         /*    (sfeast_*, cfeast_*) pass sqrt(eps(Float32)), core/feast_parameters.jl:398-405              */
 } feastcuda_solver_opts;
 
 typedef struct {

@@ -39,6 +39,7 @@ def test_struct_layouts_match_the_header(lib):
     """feastcuda_solver_opts / feastcuda_stats are mirrored field by field (sizes per the C layout rules)."""
     import feastcuda as fc
     assert C.sizeof(fc._lib.SolverOpts) == 88
+    assert fc._lib.SolverOpts.eps_floor.offset == 80
     hdr = (ROOT / "include" / "feastcuda.h").read_text()
     body = hdr[hdr.index("typedef struct {", hdr.index("feastcuda_solver_opts") - 2500):hdr.index("} feastcuda_solver_opts;")]
     fields = re.findall(r"^\s*(?:int32_t|double)\s+(\w+)", body, flags=re.M)

@@ -270,3 +270,26 @@ def test_mslanczos_krylov_exhaustion_tiny_matrices():
         assert r.info == 0 and r.M == n
         assert np.allclose(np.sort(r.lambda_), np.linalg.eigvalsh(A.toarray()), atol=1e-10)
         assert r.stats["lz_steps_p1"] > 0
+
+
+def test_float32_entry_points_types_and_tolerance():
+    """runtests.jl:281-304, 901-919, 1091-1113: s/c names return Float32 data, info == 0, eigenvalues within 1e-4/1e-5."""
+    import feastcuda as fc
+    A = sp.diags([0.5, 1.0, 1.5, 3.0]).tocsc().astype(np.float32)
+    r = fc.psfeast_scsrev(A, np.float32(0.4), np.float32(1.6), 4, fc.feastinit(), Q0=fo.seeded_subspace(4, 4, complex_storage=False))
+    assert r.info == 0 and r.M == 3
+    assert r.lambda_.dtype == np.float32 and r.q.dtype == np.float32 and r.res.dtype == np.float32
+    assert np.allclose(np.sort(r.lambda_), [0.5, 1.0, 1.5], atol=1e-5)
+    N = 12
+    L3 = fo.laplacian_3d(N).astype(np.float32).tocsc()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
+    rs = fc.sfeast_scsrev(L3, Emin, Emax, 20, fc.feastinit(), Q0=fo.seeded_subspace(N ** 3, 20, complex_storage=False))
+    rd = fc.dfeast_scsrev(L3.astype(np.float64), Emin, Emax, 20, fc.feastinit(), Q0=fo.seeded_subspace(N ** 3, 20, complex_storage=False))
+    assert rs.info == 0 and rs.M == rd.M == 10
+    assert np.abs(np.sort(rs.lambda_) - ev[:10]).max() <= 1e-4 * ev[9]
+    assert rs.res.max() <= np.sqrt(np.finfo(np.float32).eps) and rs.loop <= rd.loop   # stops at the Float32 tolerance
+    Ah = np.array([[2.5, 0.2 + 0.1j, 0.0], [0.2 - 0.1j, 3.5, 0.3 - 0.2j], [0.0, 0.3 + 0.2j, 4.0]], dtype=np.complex64)
+    rc = fc.cfeast_heev(Ah, 2.0, 5.0, 3, fc.feastinit(), Q0=fo.seeded_subspace(3, 3))
+    assert rc.info == 0 and rc.M == 3 and rc.q.dtype == np.complex64 and rc.lambda_.dtype == np.float32
+    assert np.allclose(np.sort(rc.lambda_), np.linalg.eigvalsh(Ah.astype(np.complex128)), atol=1e-4)

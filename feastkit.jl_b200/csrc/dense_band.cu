@@ -79,104 +79,127 @@ static void zgemm(H* h, int M, int N, int K, const zd* A, int64_t ars, int64_t a
   launched(h);
 }
 
-// factorise the shifted matrices of `nodes` (all of the same size) in one batch; results go to lu_cache/piv_cache
-static bool dense_factor(H* h, const std::vector<int>& nodes, const std::vector<zc>& shifts) {
-  const int nb = (int)nodes.size();
-  if (nb == 0) return true;
+// ---- batched factorisation / solves: all quadrature nodes of a sweep go through every launch together ---------------
+// dense_pool holds one column-major n x n factor per contour node (slot = node index), dense_piv [ipiv(n) | perm(n)] per
+// slot, dense_xpool one n x ld solution block per node.  The single-CTA panel kernels and the small triangular solves are
+// latency bound: batching over nodes is what fills the GPU there; the trailing GEMMs are batched through blockIdx.z.
+static void dense_ensure_pools(H* h, int nslots) {
+  const int64_t n = h->n;
+  if (h->dense_slots < nslots) {
+    h->dense_pool.release();
+    h->dense_piv.release();
+    h->dense_pool.ensure((size_t)nslots * n * n * sizeof(zd));
+    h->dense_piv.ensure((size_t)nslots * 2 * n * sizeof(int));
+    h->dense_slots = nslots;
+    h->lu_shift.assign(nslots, zc(NAN, NAN));
+  }
+  if ((int)h->lu_shift.size() < nslots) h->lu_shift.resize(nslots, zc(NAN, NAN));
+}
+
+// factorise z_q B - A for the contiguous node range [first, first+count)
+static bool dense_factor_range(H* h, int first, int count, const zc* shifts) {
   const int n = (int)h->n;
-  const int64_t nn = (int64_t)n * n;
-  int maxnode = 0;
-  for (int e : nodes) maxnode = std::max(maxnode, e);
-  if ((int)h->lu_cache.size() <= maxnode) {
-    h->lu_cache.resize(maxnode + 1);
-    h->piv_cache.resize(maxnode + 1);
-    h->lu_shift.resize(maxnode + 1, zc(NAN, NAN));
-  }
-  // nodes are factorised one after the other: the trailing GEMMs fill the GPU on their own; the single-CTA panels are
-  // the latency-bound part (next step: panels of different nodes on separate streams)
+  const int64_t nn = (int64_t)n * n, pst = 2 * (int64_t)n;
+  zd* LU = h->dense_pool.as<zd>() + (int64_t)first * nn;
+  int* ipiv = h->dense_piv.as<int>() + (int64_t)first * pst;
   DBuf dz, dinfo;
-  dz.ensure(sizeof(zd));
-  dinfo.ensure(sizeof(int));
-  bool all_ok = true;
-  for (int q = 0; q < nb; ++q) {
-    const int e = nodes[q];
-    h->lu_cache[e].ensure((size_t)nn * sizeof(zd));
-    h->piv_cache[e].ensure((size_t)2 * n * sizeof(int));
-    zd* LU = h->lu_cache[e].as<zd>();
-    int* ipiv = h->piv_cache[e].as<int>();
-    int* perm = ipiv + n;
-    const zd zz = mk<double>(shifts[q].real(), shifts[q].imag());
-    FC_CUDA(cudaMemcpyAsync(dz.p, &zz, sizeof(zd), cudaMemcpyHostToDevice, h->stream));
-    FC_CUDA(cudaMemsetAsync(dinfo.p, 0, sizeof(int), h->stream));
-    {
-      dim3 grid((unsigned)std::min<int64_t>((nn + 255) / 256, (int64_t)h->sms * 8), 1);
-      k_dense_shift<<<grid, 256, 0, h->stream>>>(n, h->dDenseA.as<zd>(), h->has_b ? h->dDenseB.as<zd>() : nullptr, dz.as<zd>(), LU, nn);
-      launched(h);
-    }
-    for (int k0 = 0; k0 < n; k0 += FC_LU_NB) {
-      const int nbw = std::min(FC_LU_NB, n - k0);
-      k_dense_panel_lu<<<1, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, dinfo.as<int>());
-      launched(h);
-      if (k0 > 0) {
-        k_dense_laswp<<<dim3((k0 + 255) / 256, 1), 256, 0, h->stream>>>(n, k0, nbw, 0, k0, LU, nn, ipiv);
-        launched(h);
-      }
-      const int rest = n - k0 - nbw;
-      if (rest > 0) {
-        k_dense_laswp<<<dim3((rest + 255) / 256, 1), 256, 0, h->stream>>>(n, k0, nbw, k0 + nbw, n, LU, nn, ipiv);
-        launched(h);
-        k_dense_trsm_u12<<<dim3((rest + 127) / 128, 1), 128, 0, h->stream>>>(n, k0, nbw, LU, nn);
-        launched(h);
-        // A22 -= L21 * U12   (all column-major, ld = n)
-        zgemm(h, rest, rest, nbw, LU + (k0 + nbw) + (int64_t)k0 * n, 1, n, LU + k0 + (int64_t)(k0 + nbw) * n, 1, n,
-              LU + (k0 + nbw) + (int64_t)(k0 + nbw) * n, 1, n, -1.0, 1);
-      }
-    }
-    k_dense_piv_to_perm<<<1, 32, 0, h->stream>>>(n, ipiv, perm);
+  dz.ensure((size_t)count * sizeof(zd));
+  dinfo.ensure((size_t)count * sizeof(int));
+  std::vector<zd> zz(count);
+  for (int q = 0; q < count; ++q) zz[q] = mk<double>(shifts[q].real(), shifts[q].imag());
+  FC_CUDA(cudaMemcpyAsync(dz.p, zz.data(), (size_t)count * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  FC_CUDA(cudaMemsetAsync(dinfo.p, 0, (size_t)count * sizeof(int), h->stream));
+  {
+    dim3 grid((unsigned)std::min<int64_t>((nn + 255) / 256, (int64_t)h->sms * 4), count);
+    k_dense_shift<<<grid, 256, 0, h->stream>>>(n, h->dDenseA.as<zd>(), h->has_b ? h->dDenseB.as<zd>() : nullptr, dz.as<zd>(), LU, nn);
     launched(h);
-    int info = 0;
-    FC_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    FC_CUDA(cudaStreamSynchronize(h->stream));
-    if (info != 0) { all_ok = false; h->lu_shift[e] = zc(NAN, NAN); }
-    else h->lu_shift[e] = shifts[q];
   }
+  for (int k0 = 0; k0 < n; k0 += FC_LU_NB) {
+    const int nbw = std::min(FC_LU_NB, n - k0);
+    k_dense_panel_lu<<<count, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, pst, dinfo.as<int>());
+    launched(h);
+    if (k0 > 0) {
+      k_dense_laswp<<<dim3((k0 + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, 0, k0, LU, nn, ipiv, pst);
+      launched(h);
+    }
+    const int rest = n - k0 - nbw;
+    if (rest > 0) {
+      k_dense_laswp<<<dim3((rest + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, k0 + nbw, n, LU, nn, ipiv, pst);
+      launched(h);
+      k_dense_trsm_u12<<<dim3((rest + 127) / 128, count), 128, 0, h->stream>>>(n, k0, nbw, LU, nn);
+      launched(h);
+      // A22 -= L21 * U12   (all column-major, ld = n), every node in the same launch
+      zgemm(h, rest, rest, nbw, LU + (k0 + nbw) + (int64_t)k0 * n, 1, n, LU + k0 + (int64_t)(k0 + nbw) * n, 1, n,
+            LU + (k0 + nbw) + (int64_t)(k0 + nbw) * n, 1, n, -1.0, 1, count, nn, nn, nn);
+    }
+  }
+  k_dense_piv_to_perm<<<count, 32, 0, h->stream>>>(n, ipiv, ipiv + n, pst);
+  launched(h);
+  std::vector<int> info(count, 0);
+  FC_CUDA(cudaMemcpyAsync(info.data(), dinfo.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  FC_CUDA(cudaStreamSynchronize(h->stream));
   dz.release();
   dinfo.release();
+  bool all_ok = true;
+  for (int q = 0; q < count; ++q) {
+    if (info[q] != 0) { all_ok = false; h->lu_shift[first + q] = zc(NAN, NAN); }
+    else h->lu_shift[first + q] = shifts[q];
+  }
   return all_ok;
 }
 
-bool dense_node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X) {
+// X_q = (z_q B - A)^-1 RHS for the node range [first, first+count); X_q = Xbase + q * xbatch (row-major n x ld blocks)
+static void dense_solve_range(H* h, int first, int count, int m, const zd* RHS, zd* Xbase, int64_t xbatch) {
   const int n = (int)h->n;
-  const int64_t ld = h->ws_ld;
-  if ((int)h->lu_cache.size() <= node || !(h->lu_shift[node] == z)) {
-    if (!dense_factor(h, {node}, {z})) return false;   // exactly singular shifted matrix -> LAPACK info > 0 (dense/feast_dense.jl:198-203)
-  }
-  const zd* LU = h->lu_cache[node].as<zd>();
-  const int* perm = h->piv_cache[node].as<int>() + n;
+  const int64_t ld = h->ws_ld, nn = (int64_t)n * n, pst = 2 * (int64_t)n;
+  const zd* LU = h->dense_pool.as<zd>() + (int64_t)first * nn;
+  const int* perm = h->dense_piv.as<int>() + (int64_t)first * pst + n;
   {
     const int64_t total = (int64_t)n * m;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 8));
-    k_dense_gather_rows<<<grid, 256, 0, h->stream>>>(n, m, ld, perm, RHS, X);
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 4));
+    k_dense_gather_rows<<<dim3(gx, count), 256, 0, h->stream>>>(n, m, ld, perm, pst, RHS, Xbase, xbatch);
     launched(h);
   }
   const int cgrid = (m + 127) / 128;
-  // forward: L y = P b
-  for (int r0 = 0; r0 < n; r0 += FC_LU_NB) {
+  for (int r0 = 0; r0 < n; r0 += FC_LU_NB) {     // forward: L y = P b
     const int bs = std::min(FC_LU_NB, n - r0);
-    k_dense_trsm_rows<true><<<cgrid, 128, 0, h->stream>>>(n, r0, bs, LU, m, ld, X);
+    k_dense_trsm_rows<true><<<dim3(cgrid, count), 128, 0, h->stream>>>(n, r0, bs, LU, nn, m, ld, Xbase, xbatch);
     launched(h);
     const int rest = n - r0 - bs;
     if (rest > 0)
-      zgemm(h, rest, m, bs, LU + (r0 + bs) + (int64_t)r0 * n, 1, n, X + (int64_t)r0 * ld, ld, 1, X + (int64_t)(r0 + bs) * ld, ld, 1, -1.0, 1);
+      zgemm(h, rest, m, bs, LU + (r0 + bs) + (int64_t)r0 * n, 1, n, Xbase + (int64_t)r0 * ld, ld, 1, Xbase + (int64_t)(r0 + bs) * ld, ld, 1,
+            -1.0, 1, count, nn, xbatch, xbatch);
   }
-  // backward: U x = y
   const int nblk = (n + FC_LU_NB - 1) / FC_LU_NB;
-  for (int b = nblk - 1; b >= 0; --b) {
+  for (int b = nblk - 1; b >= 0; --b) {          // backward: U x = y
     const int r0 = b * FC_LU_NB, bs = std::min(FC_LU_NB, n - r0);
-    k_dense_trsm_rows<false><<<cgrid, 128, 0, h->stream>>>(n, r0, bs, LU, m, ld, X);
+    k_dense_trsm_rows<false><<<dim3(cgrid, count), 128, 0, h->stream>>>(n, r0, bs, LU, nn, m, ld, Xbase, xbatch);
     launched(h);
-    if (r0 > 0) zgemm(h, r0, m, bs, LU + (int64_t)r0 * n, 1, n, X + (int64_t)r0 * ld, ld, 1, X, ld, 1, -1.0, 1);
+    if (r0 > 0)
+      zgemm(h, r0, m, bs, LU + (int64_t)r0 * n, 1, n, Xbase + (int64_t)r0 * ld, ld, 1, Xbase, ld, 1, -1.0, 1, count, nn, xbatch, xbatch);
   }
+}
+
+bool dense_node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X) {
+  dense_ensure_pools(h, std::max(node + 1, h->dense_slots));
+  if (!(h->lu_shift[node] == z)) {
+    if (!dense_factor_range(h, node, 1, &z)) return false;   // exactly singular shifted matrix -> LAPACK info > 0 (dense/feast_dense.jl:198-203)
+  }
+  dense_solve_range(h, node, 1, m, RHS, X, 0);
+  return true;
+}
+
+// all nodes [first, first+count) of a sweep at once; solutions land in dense_xpool (slot q -> node first+q)
+bool dense_batch_solve(H* h, int ne_total, int first, int count, const zc* shifts, int m, const zd* RHS, zd** Xpool, int64_t* xbatch) {
+  dense_ensure_pools(h, ne_total);
+  bool need = false;
+  for (int q = 0; q < count; ++q) need = need || !(h->lu_shift[first + q] == shifts[q]);
+  if (need && !dense_factor_range(h, first, count, shifts)) return false;
+  const int64_t xb = (int64_t)h->n * h->ws_ld;
+  h->dense_xpool.ensure((size_t)count * xb * sizeof(zd));
+  dense_solve_range(h, first, count, m, RHS, h->dense_xpool.as<zd>(), xb);
+  *Xpool = h->dense_xpool.as<zd>();
+  *xbatch = xb;
   return true;
 }
 

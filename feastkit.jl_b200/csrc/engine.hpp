@@ -132,6 +132,8 @@ struct feastcuda_handle_s {
   std::vector<feastcuda::DBuf> piv_cache;
   std::vector<feastcuda::zc> lu_shift;
   feastcuda::DBuf dDenseA, dDenseB, dBandA, dBandB;
+  feastcuda::DBuf dense_pool, dense_piv, dense_xpool;   // batched dense factors / pivots / per-node solutions
+  int dense_slots = 0;
   bool dense_uploaded = false, band_uploaded = false;
 
   // last solve's results (device: blk[BS_XR]); host copies of the small arrays
@@ -158,5 +160,9 @@ inline void release_factor_cache(feastcuda_handle_s* h) {
   h->lu_cache.clear();
   h->piv_cache.clear();
   h->lu_shift.clear();
+  h->dense_pool.release();
+  h->dense_piv.release();
+  h->dense_xpool.release();
+  h->dense_slots = 0;
 }
 }  // namespace feastcuda

@@ -1012,6 +1012,25 @@ static void eig_residual_norms(H* h, int m, const zd* X, const std::vector<zc>& 
   }
 }
 
+// dense operators: every node of the sweep goes through the batched LU / substitution kernels together
+static bool dense_items_batched(H* h, std::vector<WorkItem>& items, int ne, int active, const zc* Zne, const zc* Wne, double wfac,
+                                const zd* rhs, bool* failed) {
+  if (h->kind != OP_DENSE || items.empty()) return false;
+  for (size_t q = 0; q < items.size(); ++q)
+    if (items[q].c0 != 0 || items[q].nc != active || items[q].node != items[0].node + (int)q) return false;
+  std::vector<zc> zs;
+  for (const WorkItem& it : items) zs.push_back(Zne[it.node]);
+  zd* Xp = nullptr;
+  int64_t xb = 0;
+  const bool ok = dense_batch_solve(h, ne, items[0].node, (int)items.size(), zs.data(), active, rhs, &Xp, &xb);
+  h->stats.node_solves += (int64_t)items.size();
+  if (!ok) *failed = true;
+  else
+    for (size_t q = 0; q < items.size(); ++q) axpby_cols(h, active, wfac * Wne[items[q].node], 1.0, Xp + (int64_t)q * xb, blk(h, BS_ACC));
+  items.clear();
+  return true;
+}
+
 // =====================================================================================================
 // H-RR refinement loop (dense/feast_dense.jl:78-351, sparse/feast_sparse.jl:246-499, banded:561-823)
 // =====================================================================================================
@@ -1112,6 +1131,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
                   mo.maxres, (int)mo.converged, c0, c0 + nc);
       }
     }
+    if (dense_items_batched(h, items, ne, active, Zne, Wne, 2.0, rhs, &failed) && failed) info_code = 8;
     for (const WorkItem& it : items) {
       const zc z = Zne[it.node];
       zd* X = blk(h, BS_KX) + it.c0;
@@ -1297,6 +1317,7 @@ static void run_contour(H* h, zc Emid, double r, int m0, int64_t* fpm, const zc*
     zero_cols(h, active, blk(h, BS_ACC));
     std::vector<WorkItem> items = build_items(ne, active, h->nranks, h->rank, shard, cost);
     bool failed = false;
+    if (dense_items_batched(h, items, ne, active, Zne, Wne, 1.0, rhs, &failed) && failed) info_code = 8;
     for (const WorkItem& it : items) {
       zd* X = blk(h, BS_KX) + it.c0;
       SolveOut so;
@@ -1471,7 +1492,7 @@ int feastcuda_destroy(feastcuda_handle h) {
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
   DBuf* bufs[] = {&h->partial, &h->partial_r, &h->kstate, &h->small, &h->small2, &h->gram_partial, &h->stage, &h->red_ws,
-                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->lzp_wmeta, &h->lzp_run0, &h->lzp_runs, &h->lzp_lcol, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB};
+                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->lzp_wmeta, &h->lzp_run0, &h->lzp_runs, &h->lzp_lcol, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB, &h->dense_pool, &h->dense_piv, &h->dense_xpool};
   for (DBuf* b : bufs) b->release();
   for (auto& b : h->lu_cache) b.release();
   for (auto& b : h->piv_cache) b.release();

@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(256) k_dense_shift(int64_t n, const zdd* __res
 constexpr int FC_LU_NB = 32;
 
 __global__ void __launch_bounds__(512) k_dense_panel_lu(int n, int k0, int nbw, zdd* __restrict__ LU, int64_t batch_stride,
-                                                        int* __restrict__ ipiv, int* __restrict__ info) {
+                                                        int* __restrict__ ipiv, int64_t piv_stride, int* __restrict__ info) {
   zdd* M = LU + (int64_t)blockIdx.x * batch_stride;
-  int* piv = ipiv + (int64_t)blockIdx.x * n;
+  int* piv = ipiv + (int64_t)blockIdx.x * piv_stride;
   __shared__ double s_val[512];
   __shared__ int s_idx[512];
   __shared__ zdd s_u[FC_LU_NB];
@@ -98,9 +98,9 @@ __global__ void __launch_bounds__(512) k_dense_panel_lu(int n, int k0, int nbw, 
 
 // row interchanges of the panel [k0, k0+nbw) applied to the columns [c0, c1) outside it; one thread per column
 __global__ void __launch_bounds__(256) k_dense_laswp(int n, int k0, int nbw, int c0, int c1, zdd* __restrict__ LU,
-                                                     int64_t batch_stride, const int* __restrict__ ipiv) {
+                                                     int64_t batch_stride, const int* __restrict__ ipiv, int64_t piv_stride) {
   zdd* M = LU + (int64_t)blockIdx.y * batch_stride;
-  const int* piv = ipiv + (int64_t)blockIdx.y * n;
+  const int* piv = ipiv + (int64_t)blockIdx.y * piv_stride;
   const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c1) return;
   zdd* colp = M + (int64_t)c * n;
@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(128) k_dense_trsm_u12(int n, int k0, int nbw, 
 }
 
 // ipiv (sequence of transpositions) -> perm with  (P b)[i] = b[perm[i]]
-__global__ void k_dense_piv_to_perm(int n, const int* __restrict__ ipiv, int* __restrict__ perm) {
-  const int* piv = ipiv + (int64_t)blockIdx.x * n;
-  int* pm = perm + (int64_t)blockIdx.x * n;
+__global__ void k_dense_piv_to_perm(int n, const int* __restrict__ ipiv, int* __restrict__ perm, int64_t piv_stride) {
+  const int* piv = ipiv + (int64_t)blockIdx.x * piv_stride;
+  int* pm = perm + (int64_t)blockIdx.x * piv_stride;
   if (threadIdx.x != 0) return;
   for (int i = 0; i < n; ++i) pm[i] = i;
   for (int i = 0; i < n; ++i) {
@@ -142,8 +142,11 @@ __global__ void k_dense_piv_to_perm(int n, const int* __restrict__ ipiv, int* __
 }
 
 // X[i, :] = RHS[perm[i], :]   (row-major n x ld blocks, m active columns)
-__global__ void __launch_bounds__(256) k_dense_gather_rows(int64_t n, int m, int64_t ld, const int* __restrict__ perm,
-                                                           const zdd* __restrict__ RHS, zdd* __restrict__ X) {
+// blockIdx.y = batch entry (one per quadrature node): perm and X advance by their batch strides, RHS is shared
+__global__ void __launch_bounds__(256) k_dense_gather_rows(int64_t n, int m, int64_t ld, const int* __restrict__ perm, int64_t piv_stride,
+                                                           const zdd* __restrict__ RHS, zdd* __restrict__ X, int64_t xbatch) {
+  perm += (int64_t)blockIdx.y * piv_stride;
+  X += (int64_t)blockIdx.y * xbatch;
   const int64_t total = n * m;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx / m;
@@ -155,8 +158,10 @@ __global__ void __launch_bounds__(256) k_dense_gather_rows(int64_t n, int m, int
 // In-place triangular solve of one diagonal block on a row-major block of right-hand sides:
 //   LOWER: rows [r0, r0+bs) of X <- L11^-1 X (unit diagonal);  UPPER: X <- U11^-1 X.  One thread per RHS column.
 template <bool LOWER>
-__global__ void __launch_bounds__(128) k_dense_trsm_rows(int n, int r0, int bs, const zdd* __restrict__ LU, int m, int64_t ld,
-                                                         zdd* __restrict__ X) {
+__global__ void __launch_bounds__(128) k_dense_trsm_rows(int n, int r0, int bs, const zdd* __restrict__ LU, int64_t lubatch, int m,
+                                                         int64_t ld, zdd* __restrict__ X, int64_t xbatch) {
+  LU += (int64_t)blockIdx.y * lubatch;
+  X += (int64_t)blockIdx.y * xbatch;
   __shared__ zdd sT[FC_LU_NB][FC_LU_NB + 1];
   for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) {
     const int i = e % bs, j = e / bs;

@@ -21,6 +21,7 @@ static void launched(H* h) {
 // =====================================================================================================
 // dense
 // =====================================================================================================
+// the caller's column-major matrix goes straight to the device (no host copy is kept); real input is widened there
 void dense_set(H* h, int which, int64_t n, const double* a, int64_t lda, bool cplx, int structure) {
   (void)structure;
   FC_REQUIRE(n > 0 && a != nullptr && lda >= n, "set_dense: bad arguments");
@@ -28,15 +29,23 @@ void dense_set(H* h, int which, int64_t n, const double* a, int64_t lda, bool cp
   FC_REQUIRE(which == FEASTCUDA_A || which == FEASTCUDA_B, "which must be A or B");
   HostDense& d = (which == FEASTCUDA_A) ? h->denseA : h->denseB;
   if (which == FEASTCUDA_B) FC_REQUIRE(h->kind == OP_DENSE && h->denseA.set && h->denseA.n == n, "set A (same size, dense) before B");
+  DBuf& dst = (which == FEASTCUDA_A) ? h->dDenseA : h->dDenseB;
+  const size_t es = cplx ? sizeof(zd) : sizeof(double);
+  dst.ensure((size_t)n * n * sizeof(zd));
+  if (cplx) {
+    FC_CUDA(cudaMemcpy2DAsync(dst.p, (size_t)n * es, a, (size_t)lda * es, (size_t)n * es, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    h->stage.ensure((size_t)n * n * es);
+    FC_CUDA(cudaMemcpy2DAsync(h->stage.p, (size_t)n * es, a, (size_t)lda * es, (size_t)n * es, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    const int64_t total = n * n;
+    k_dense_widen<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 8)), 256, 0, h->stream>>>(
+        total, h->stage.as<double>(), dst.as<zd>());
+    launched(h);
+  }
+  FC_CUDA(cudaStreamSynchronize(h->stream));
   d.n = n;
   d.cplx = cplx;
-  d.a.assign((size_t)2 * n * n, 0.0);   // always stored as interleaved complex, column-major, ld = n
-  for (int64_t j = 0; j < n; ++j)
-    for (int64_t i = 0; i < n; ++i) {
-      const size_t o = 2 * ((size_t)j * n + i);
-      if (cplx) { d.a[o] = a[2 * ((size_t)j * lda + i)]; d.a[o + 1] = a[2 * ((size_t)j * lda + i) + 1]; }
-      else d.a[o] = a[(size_t)j * lda + i];
-    }
+  d.a.clear();
   d.set = true;
   if (which == FEASTCUDA_A) {
     if (h->kind != OP_DENSE) { h->has_b = false; h->denseB.set = false; }
@@ -45,24 +54,13 @@ void dense_set(H* h, int which, int64_t n, const double* a, int64_t lda, bool cp
   } else {
     h->has_b = true;
   }
-  h->dense_uploaded = false;
+  h->dense_uploaded = true;
   release_factor_cache(h);
 }
 
 void dense_prepare(H* h) {
   FC_REQUIRE(h->denseA.set, "operator A has not been set");
   h->n = h->denseA.n;
-  if (h->dense_uploaded) return;
-  const size_t bytes = (size_t)h->n * h->n * sizeof(zd);
-  h->dDenseA.ensure(bytes);
-  FC_CUDA(cudaMemcpyAsync(h->dDenseA.p, h->denseA.a.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-  if (h->has_b) {
-    h->dDenseB.ensure(bytes);
-    FC_CUDA(cudaMemcpyAsync(h->dDenseB.p, h->denseB.a.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-  }
-  FC_CUDA(cudaStreamSynchronize(h->stream));
-  h->dense_uploaded = true;
-  release_factor_cache(h);
 }
 
 static void zgemm(H* h, int M, int N, int K, const zd* A, int64_t ars, int64_t acs, const zd* B, int64_t brs, int64_t bcs, zd* C,

@@ -601,7 +601,9 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   FC_REQUIRE((c0 & 1) == 0, "column slices must start at an even column");
   FC_REQUIRE((double)h->ws_n * (double)lz_ld(h) < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   const int64_t n = h->ws_n;
-  const int64_t ldz = h->ws_ld, ld = lz_ld(h);
+  // the real work blocks are COMPACT: row stride = the slice's own (even) column count, so a rank that owns 8 of 64 columns
+  // streams dense 64-byte rows instead of touching 64 bytes out of every 512
+  const int64_t ldz = h->ws_ld, ld = (nc + 1) & ~1;
   kmax = std::max(1, std::min(kmax, 16384));
   check_every = std::max(1, check_every);
   const int P = (nc + 1) / 2;
@@ -633,11 +635,11 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   FC_CUDA(cudaMemcpyAsync(d_z, Zne, (size_t)ne * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
 
   // ---- real work blocks (each aliases a complex slot; n x ld doubles) -------------------------------------------
-  double* RQ = rblk(h, BS_KS) + c0;
-  double* RB = rblk(h, BS_KR) + c0;
-  double* UA = rblk(h, BS_KRH) + c0;
-  double* UB = rblk(h, BS_KP) + c0;
-  double* QA = rblk(h, BS_KV) + c0;
+  double* RQ = rblk(h, BS_KS);
+  double* RB = rblk(h, BS_KR);
+  double* UA = rblk(h, BS_KRH);
+  double* UB = rblk(h, BS_KP);
+  double* QA = rblk(h, BS_KV);
   const zd* basis = blk(h, basis_slot) + c0;
   double* part = h->partial_r.as<double>();
 

@@ -16,6 +16,11 @@ namespace feastcuda {
 
 typedef cx<double> zdd;
 
+// real column-major input -> complex storage
+__global__ void __launch_bounds__(256) k_dense_widen(int64_t total, const double* __restrict__ src, zdd* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) dst[i] = mk<double>(src[i], 0.0);
+}
+
 // ---- LU_b = z_b * B - A   (B == nullptr: identity) ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dense_shift(int64_t n, const zdd* __restrict__ A, const zdd* __restrict__ B,
                                                      const zdd* __restrict__ z, zdd* __restrict__ LU, int64_t batch_stride) {

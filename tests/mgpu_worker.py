@@ -36,6 +36,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         out[name] = {"ok_all_ranks": bool(t[0].item() == 1.0), "loop": r.loop, "M": r.M, "info": r.info, "epsout": r.epsout,
                      "allreduce_bytes": r.stats["allreduce_bytes"], "lz_steps": r.stats["lz_steps_p1"], "world": world}
+    # dense (LU per node, nodes sharded by the reference's block rule) and general (full contour) solves
+    rng = np.random.default_rng(3)
+    n = 160
+    Qm, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    d = np.sort(rng.uniform(0.0, 10.0, n))
+    Ad = (Qm * d) @ Qm.T
+    Ad = 0.5 * (Ad + Ad.T)
+    r = fc.pdfeast_syev(Ad, 0.5 * (d[29] + d[30]), 0.5 * (d[37] + d[38]), 20, fc.feastinit(), Q0=fo.seeded_subspace(n, 20, complex_storage=False))
+    ok = r.info == 0 and r.M == 8 and float(np.abs(np.sort(r.lambda_) - d[30:38]).max()) < 1e-10 * d[-1] and float(r.res.max()) < 1e-12
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["dense_nodes"] = {"ok_all_ranks": bool(t[0].item() == 1.0), "loop": r.loop, "M": r.M, "info": r.info, "epsout": r.epsout,
+                          "allreduce_bytes": r.stats["allreduce_bytes"], "world": world}
+    nt = 120
+    a_, b_, c_ = 0.3 + 0.2j, 1.0 + 0.1j, 0.95 - 0.05j
+    At = np.diag(b_ * np.ones(nt - 1), -1) + np.diag(a_ * np.ones(nt)) + np.diag(c_ * np.ones(nt - 1), 1)
+    lam = a_ + 2 * np.sqrt(b_ * c_) * np.cos(np.arange(1, nt + 1) * np.pi / (nt + 1))
+    Emid, rad = 0.3 + 0.2j, 0.3
+    inside = [l for l in lam if abs(l - Emid) <= rad]
+    r = fc.pzfeast_geev(At, Emid, rad, 24, fc.feastinit(), Q0=fo.seeded_subspace(nt, 24))
+    ok = r.info == 0 and r.M == len(inside) and all(min(abs(g - x) for x in inside) < 1e-9 for g in r.lambda_) and float(r.res.max()) < 1e-12
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["general_nodes"] = {"ok_all_ranks": bool(t[0].item() == 1.0), "loop": r.loop, "M": r.M, "info": r.info, "epsout": r.epsout,
+                            "allreduce_bytes": r.stats["allreduce_bytes"], "world": world}
     if rank == 0:
         Path(sys.argv[1]).write_text(json.dumps(out))
     dist.barrier()

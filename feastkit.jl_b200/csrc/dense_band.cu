@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #include "kernels_band.cuh"
 #include "kernels_dense.cuh"
@@ -73,7 +74,14 @@ static void zgemm(H* h, int M, int N, int K, const zd* A, int64_t ars, int64_t a
   g.C = C; g.crs = crs; g.ccs = ccs; g.cbatch = cb;
   g.alpha = alpha; g.beta = beta;
   dim3 grid((M + 63) / 64, (N + 63) / 64, batch);
-  k_zgemm_dmma<<<grid, 256, 0, h->stream>>>(g);
+  static const int variant = getenv("FEASTCUDA_GEMM") ? atoi(getenv("FEASTCUDA_GEMM")) : 2;   // 2: cp.async double-buffered operands (default), 1: synchronous staging
+  if (variant == 2) {
+    static bool attr = false;
+    if (!attr) { FC_CUDA(cudaFuncSetAttribute(k_zgemm_dmma_async, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    k_zgemm_dmma_async<<<grid, 256, 64 * 1024, h->stream>>>(g);
+  } else {
+    k_zgemm_dmma<<<grid, 256, 0, h->stream>>>(g);
+  }
   launched(h);
 }
 

@@ -284,4 +284,91 @@ __global__ void __launch_bounds__(256) k_zgemm_dmma(ZgemmArgs g) {
       }
 }
 
+// ---- the same GEMM with an asynchronous, double-buffered operand pipeline -----------------------------------------------
+// Operands stay interleaved (re, im) in shared memory and are staged by cp.async (LDGSTS, 16 bytes = one complex entry per
+// request, zero-filled outside the matrix), two K tiles in flight; a fragment read is one LDS.128 that delivers both planes.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) k_zgemm_dmma_async(ZgemmArgs g) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  extern __shared__ __align__(16) unsigned char zg_smem[];
+  zdd (*sA)[TK][TM] = reinterpret_cast<zdd (*)[TK][TM]>(zg_smem);                                   // [2][TK][TM]
+  zdd (*sB)[TK][TN] = reinterpret_cast<zdd (*)[TK][TN]>(zg_smem + 2 * TK * TM * sizeof(zdd));       // [2][TK][TN]
+  const zdd* A = g.A + (int64_t)blockIdx.z * g.abatch;
+  const zdd* B = g.B + (int64_t)blockIdx.z * g.bbatch;
+  zdd* C = g.C + (int64_t)blockIdx.z * g.cbatch;
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { cr[a][b][0] = cr[a][b][1] = 0.0; ci[a][b][0] = ci[a][b][1] = 0.0; }
+  const bool a_mfast = (g.ars == 1), b_nfast = (g.bcs == 1);
+  auto issue = [&](int st, int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * 256;
+      const int mm = a_mfast ? (e % TM) : (e / TK), ka = a_mfast ? (e / TM) : (e % TK);
+      const bool va = (i0 + mm < g.M) && (k0 + ka < g.K);
+      cp_async16(&sA[st][ka][mm], va ? (A + (int64_t)(i0 + mm) * g.ars + (int64_t)(k0 + ka) * g.acs) : A, va);
+      const int nn = b_nfast ? (e % TN) : (e / TK), kb = b_nfast ? (e / TN) : (e % TK);
+      const bool vb = (j0 + nn < g.N) && (k0 + kb < g.K);
+      cp_async16(&sB[st][kb][nn], vb ? (B + (int64_t)(k0 + kb) * g.brs + (int64_t)(j0 + nn) * g.bcs) : B, vb);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0, 0);
+  int st = 0;
+  for (int k0 = 0; k0 < g.K; k0 += TK) {
+    const bool more = k0 + TK < g.K;
+    if (more) {
+      issue(st ^ 1, k0 + TK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 4) {
+      zdd av[2], bv[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) av[a] = sA[st][ks + fk][wm + 8 * a + fr];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = sB[st][ks + fk][wn + 8 * b + fr];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          dmma_8x8x4(cr[a][b], av[a].x, bv[b].x);
+          dmma_8x8x4(cr[a][b], -av[a].y, bv[b].y);
+          dmma_8x8x4(ci[a][b], av[a].x, bv[b].y);
+          dmma_8x8x4(ci[a][b], av[a].y, bv[b].x);
+        }
+    }
+    __syncthreads();
+    st ^= 1;
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = i0 + wm + 8 * a + fr, j = j0 + wn + 8 * b + 2 * fk + q;
+        if (i < g.M && j < g.N) {
+          zdd* cp = C + (int64_t)i * g.crs + (int64_t)j * g.ccs;
+          zdd v = mk<double>(g.alpha * cr[a][b][q], g.alpha * ci[a][b][q]);
+          if (g.beta) v = v + *cp;
+          *cp = v;
+        }
+      }
+}
+
 }  // namespace feastcuda

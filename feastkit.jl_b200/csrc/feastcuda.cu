@@ -1323,7 +1323,16 @@ static void run_contour(H* h, zc Emid, double r, int m0, int64_t* fpm, const zc*
     for (const WorkItem& it : items) {
       zd* X = blk(h, BS_KX) + it.c0;
       SolveOut so;
-      const bool ok = node_solve(h, it.node, Zne[it.node], it.nc, rhs + it.c0, X, false, o, tol, so);
+      bool use_x0 = false;
+      if (iterative && o.ritz_guess && loop > 0) {
+        // Ritz-pair start x0 = q/(z - theta): the solve only has to correct the eigen-residual, so inexact inner solves
+        // (inner_rel) keep contracting it from sweep to sweep
+        std::vector<zc> f(it.nc);
+        for (int c = 0; c < it.nc; ++c) f[c] = zc(1.0) / (Zne[it.node] - lam[it.c0 + c]);
+        scale_cols(h, it.nc, f, basis + it.c0, X);
+        use_x0 = true;
+      }
+      const bool ok = node_solve(h, it.node, Zne[it.node], it.nc, rhs + it.c0, X, use_x0, o, tol, so);
       h->stats.node_solves++;
       if (iterative) h->stats.node_iters[it.node] = so.it_total;
       if (!ok && (!iterative || o.inner_rel <= 0.0)) { failed = true; info_code = iterative ? 5 : 8; break; }

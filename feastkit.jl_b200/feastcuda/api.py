@@ -261,7 +261,7 @@ def _general_solve(kind, setA, setB, N, Emid, r, M0, fpm, contour=None, solver="
         raise ValueError(f"Unsupported solver option '{solver}'. Use :direct, :gmres, or :iterative.")
     kw = dict(solver_tol=solver_tol, solver_maxiter=max(int(solver_maxiter), 2000 if kind == "sparse" else 1),
               solver="bicgstab" if kind == "sparse" else "direct", solver_restart=3 if solver_restart == 30 else int(solver_restart))
-    for k in ("inner_rel", "shard", "check_every", "eps_floor"):
+    for k in ("inner_rel", "shard", "check_every", "eps_floor", "ritz_guess"):
         if k in extras:
             kw[k] = extras.pop(k)
     if extras:

@@ -59,6 +59,7 @@ struct HostCsr {
   std::vector<double> val;  // nnz (real) or 2*nnz (complex interleaved)
   bool cplx = false;
   bool set = false;
+  int structure = 0;   // FEASTCUDA_SYM / HERM / GEN as declared at set time
 };
 
 struct DevCsr {

@@ -76,6 +76,7 @@ static void ingest_csr(HostCsr& out, int64_t n, int64_t nnz, const int64_t* ptr,
   out.n = n;
   out.nnz = nnz;
   out.cplx = cplx;
+  out.structure = structure;
   const int vs = cplx ? 2 : 1;
   out.ptr.assign(n + 1, 0);
   out.col.assign(nnz, 0);
@@ -469,7 +470,6 @@ static void block_bicgstab(H* h, zc z, int m, const zd* RHS, zd* X, bool use_x0,
 // =====================================================================================================
 struct MslOut { int k = 0; double maxres = 0.0; bool converged = false; };
 
-static inline int lz_ld(H* h) { return (h->ws_ld + 1) & ~1; }
 static inline double* rblk(H* h, int slot) { return h->blk[slot].as<double>(); }
 
 static int lz_grid_spmm(H* h, int64_t n, int rows_per_step) {
@@ -562,21 +562,21 @@ static bool lz_launch_staged(H* h, LzArgs& a, int* grid_out) {
   return true;
 }
 
-template <int MODE>
+template <int MODE, bool CPLX>
 static void lz_launch(H* h, LzArgs& a, int* grid_out) {
-  if (lz_launch_staged<MODE>(h, a, grid_out)) return;
-  const int P = (a.m + 1) / 2;
+  if (!CPLX && lz_launch_staged<MODE>(h, a, grid_out)) return;
+  const int P = CPLX ? a.m : (a.m + 1) / 2;
   // G lanes per row, NC column-pair chunks per lane
 #define FC_LZ(G, NC)                                                                       \
   do {                                                                                     \
     if (h->lz_threads >= 1024 && NC == 1) {                                                \
       const int grid = lz_grid_spmm(h, a.n, 32 * (32 / G));                                \
       *grid_out = grid;                                                                    \
-      k_lz_spmm<G, NC, MODE, 1024><<<grid, 1024, 0, h->stream>>>(a);                       \
+      k_lz_spmm<G, NC, MODE, 1024, CPLX><<<grid, 1024, 0, h->stream>>>(a);                 \
     } else {                                                                               \
       const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G));                                \
       *grid_out = grid;                                                                    \
-      k_lz_spmm<G, NC, MODE, 512><<<grid, 512, 0, h->stream>>>(a);                         \
+      k_lz_spmm<G, NC, MODE, 512, CPLX><<<grid, 512, 0, h->stream>>>(a);                   \
     }                                                                                      \
   } while (0)
   if (P <= 1) FC_LZ(1, 1);
@@ -591,22 +591,24 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
   h->stats.spmm_launches++;
 }
 
-static double lz_bytes_spmm(H* h, int m, int nvec) {
-  return (double)h->hA.nnz * 12.0 + 4.0 * (double)(h->hA.n + 1) + (double)nvec * (double)h->hA.n * m * 8.0;
+static double lz_bytes_spmm(H* h, int m, int nvec, bool cplx) {
+  const double es = cplx ? 16.0 : 8.0;
+  return (double)h->hA.nnz * (es + 4.0) + 4.0 * (double)(h->hA.n + 1) + (double)nvec * (double)h->hA.n * m * es;
 }
 
+template <bool CPLX>
 static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, const double* theta, const zc* Zne, const zc* Wne,
                        int ne, double target, int kmax, int check_every, MslOut& out) {
-  FC_REQUIRE(h->kind == OP_SPARSE && !h->dev_complex && !h->has_b, "multi-shift Lanczos needs a real standard sparse problem");
-  FC_REQUIRE((c0 & 1) == 0, "column slices must start at an even column");
-  FC_REQUIRE((double)h->ws_n * (double)lz_ld(h) < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
+  FC_REQUIRE(h->kind == OP_SPARSE && h->dev_complex == CPLX && !h->has_b, "multi-shift Lanczos needs a standard sparse Hermitian problem");
+  FC_REQUIRE(CPLX || (c0 & 1) == 0, "column slices must start at an even column");
   const int64_t n = h->ws_n;
-  // the real work blocks are COMPACT: row stride = the slice's own (even) column count, so a rank that owns 8 of 64 columns
-  // streams dense 64-byte rows instead of touching 64 bytes out of every 512
-  const int64_t ldz = h->ws_ld, ld = (nc + 1) & ~1;
+  // the work blocks are COMPACT: row stride = the slice's own column count (in doubles: even(nc) real, 2 nc complex), so a
+  // rank that owns 8 of 64 columns streams dense 64-byte rows instead of touching 64 bytes out of every 512
+  const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : ((nc + 1) & ~1);
+  FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   kmax = std::max(1, std::min(kmax, 16384));
   check_every = std::max(1, check_every);
-  const int P = (nc + 1) / 2;
+  const int P = CPLX ? nc : (nc + 1) / 2;
   const int pp = pow2_ge(P);
   const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
 
@@ -645,7 +647,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
 
   std::vector<double> rho(nc, 0.0);
   if (!have_ritz) {
-    k_lz_real_part<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS);
+    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS);
     check_launch(h);
     k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, egrid, FC_MAXCOLS, nc);
     check_launch(h);
@@ -659,19 +661,19 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     }
     FC_CUDA(cudaMemcpyAsync(d_theta, theta, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     FC_CUDA(cudaMemcpyAsync(d_rho, rho.data(), (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_lz_real_part<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS);
+    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS);
     check_launch(h);
     LzArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.m = nc; a.ld = ld;
-    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
+    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
     a.U = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
     a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
     int g = 0;
     const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
-    lz_launch<LZ_RES>(h, a, &g);
+    lz_launch<LZ_RES, CPLX>(h, a, &g);
     sample_end(h, ev);
-    h->stats.bytes_kern[FEASTCUDA_KERN_LZ_RES] = lz_bytes_spmm(h, nc, 3);
+    h->stats.bytes_kern[FEASTCUDA_KERN_LZ_RES] = lz_bytes_spmm(h, nc, 3, CPLX);
     k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g, FC_MAXCOLS, nc);
     check_launch(h);
     sync(h);  // theta / rho are host buffers
@@ -690,19 +692,19 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       LzArgs a;
       memset(&a, 0, sizeof(a));
       a.n = n; a.m = nc; a.ld = ld;
-      a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
+      a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
       a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1);
       a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
       a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
       const bool smp = (j % 16) == 3;
       int g = 0;
       int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
-      lz_launch<LZ_P1>(h, a, &g);
+      lz_launch<LZ_P1, CPLX>(h, a, &g);
       sample_end(h, ev);
       k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, g, FC_MAXCOLS, nc);
       check_launch(h);
       ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_UPD, j) : -1;
-      k_lz_update<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
+      k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
                                                  S.done_k);
       check_launch(h);
       sample_end(h, ev);
@@ -715,8 +717,8 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     if (flag[0] != 0) { kfinal = flag[0]; out.converged = true; break; }
   }
   if (kfinal == 0) kfinal = done;
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = lz_bytes_spmm(h, nc, 3);
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_UPD] = 3.0 * (double)n * nc * 8.0;
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = lz_bytes_spmm(h, nc, 3, CPLX);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_UPD] = 3.0 * (double)n * nc * (CPLX ? 16.0 : 8.0);
   drain_events(h, kfinal);
   h->stats.lz_steps_p1 += kfinal;
   h->stats.krylov_iters += kfinal;
@@ -770,14 +772,14 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   Timer t2;
   for (int j = 0; j < k; ++j) {
     if (j == k - 1) {
-      k_lz_axpy<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, cur(j), QA);
+      k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, cur(j), QA);
       check_launch(h);
       break;
     }
     LzArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.m = nc; a.ld = ld;
-    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.as<double>();
+    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
     a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1); a.Q = QA;
     a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
     a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
@@ -785,13 +787,13 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     const bool smp = (j % 16) == 3;
     int g = 0;
     const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
-    lz_launch<LZ_P2>(h, a, &g);
+    lz_launch<LZ_P2, CPLX>(h, a, &g);
     sample_end(h, ev);
   }
-  k_lz_to_complex<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
+  k_lz_to_complex<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
   check_launch(h);
   sync(h);  // coef is a host buffer
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = lz_bytes_spmm(h, nc, 5);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = lz_bytes_spmm(h, nc, 5, CPLX);
   drain_events(h);
   h->stats.lz_steps_p2 += k;
   h->stats.ms_lz_p2 += t2.ms();
@@ -1103,17 +1105,21 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     const zd* rhs = basis;
     if (h->has_b) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
     zero_cols(h, active, blk(h, BS_ACC));
-    const bool use_msl = iterative && o.solver == FEASTCUDA_SOLVER_MSLANCZOS && !h->has_b && real_mode;
+    // multi-shift Lanczos: standard Hermitian problems with the true filter rho = Re g -- real symmetric with a real basis (real
+    // arithmetic) or complex Hermitian (complex vectors, real tridiagonal: the coefficients of rho are real either way)
+    const bool cplx_msl = iterative && h->dev_complex && !h->has_b && o.filter == FEASTCUDA_FILTER_TRUE && h->hA.structure != FEASTCUDA_GEN;
+    const bool use_msl = iterative && o.solver == FEASTCUDA_SOLVER_MSLANCZOS && !h->has_b && (real_mode || cplx_msl);
     std::vector<WorkItem> items;
     if (!use_msl) items = build_items(ne, active, h->nranks, h->rank, shard, cost);
     std::vector<double> node_cost(ne, 0.0), node_cols(ne, 0.0);
     bool failed = false;
     if (use_msl) {
       // one real Lanczos recurrence per column serves every node; ranks own contiguous column-pair slices
-      const int npairs = (active + 1) / 2;
+      const int epc = cplx_msl ? 1 : 2;                     // columns per 16-byte element
+      const int npairs = (active + epc - 1) / epc;
       const int pb = npairs / h->nranks, pr = npairs % h->nranks;
       const int p0 = h->rank * pb + std::min(h->rank, pr), pn = pb + (h->rank < pr ? 1 : 0);
-      const int c0 = 2 * p0, nc = std::max(0, std::min(active, 2 * (p0 + pn)) - c0);
+      const int c0 = epc * p0, nc = std::max(0, std::min(active, epc * (p0 + pn)) - c0);
       const bool first = !(o.ritz_guess && have_ritz);
       double target = (first && o.inner_rel0 > 0) ? o.inner_rel0 : o.inner_rel;
       if (!(target > 0)) target = tol;
@@ -1125,7 +1131,8 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       const int kmax = (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter;
       if (nc > 0) {
         MslOut mo;
-        msl_filter(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
+        if (cplx_msl) msl_filter<true>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
+        else msl_filter<false>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
         h->stats.node_solves += ne;
         for (int e = 0; e < ne && e < 128; ++e) h->stats.node_iters[e] = mo.k;
         if (getenv("FEASTCUDA_VERBOSE"))

@@ -35,7 +35,7 @@ struct LzArgs {
   int64_t n;
   int m;                 // active columns
   int64_t ld;            // row stride in doubles (even)
-  const int* ptr; const int* col; const double* val;
+  const int* ptr; const int* col; const void* val;   // val: double (real symmetric) or cx<double> (complex Hermitian)
   const double* U;       // gathered operand
   const double* prev;    // own-row operand u_{j-1}; at j = 0 any finite block (the host passes U; ratio_b is 0 there)
   double* out;           // own-row result (may alias prev)
@@ -52,6 +52,41 @@ struct LzArgs {
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
+// Element semantics.  Real problems: a 16-byte element is a PAIR of real columns, matrix entries are doubles.  Complex
+// Hermitian problems (CPLX): an element is ONE complex column (re, im), matrix entries are cx<double>; T_k stays real, so
+// the per-column scalars apply to both components and a dot product is the sum of the two component products.
+template <bool CPLX> struct LzVal;
+template <> struct LzVal<false> {
+  typedef double T;
+  static __device__ __forceinline__ T zero() { return 0.0; }
+  static __device__ __forceinline__ T load(const void* v, int i) { return reinterpret_cast<const double*>(v)[i]; }
+  static __device__ __forceinline__ T shfl(unsigned mask, T a, int src, int width) { return __shfl_sync(mask, a, src, width); }
+  static __device__ __forceinline__ void fma_acc(double2& acc, T a, double2 x) { acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); }
+};
+template <> struct LzVal<true> {
+  typedef double2 T;
+  static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
+  static __device__ __forceinline__ T load(const void* v, int i) { return reinterpret_cast<const double2*>(v)[i]; }
+  static __device__ __forceinline__ T shfl(unsigned mask, T a, int src, int width) {
+    return make_double2(__shfl_sync(mask, a.x, src, width), __shfl_sync(mask, a.y, src, width));
+  }
+  static __device__ __forceinline__ void fma_acc(double2& acc, T a, double2 x) {
+    acc.x = fma(a.x, x.x, acc.x); acc.x = fma(-a.y, x.y, acc.x);
+    acc.y = fma(a.x, x.y, acc.y); acc.y = fma(a.y, x.x, acc.y);
+  }
+};
+// per-element scalars from a per-column array: real -> (s[2e], s[2e+1]); complex -> (s[e], s[e])
+template <bool CPLX>
+__device__ __forceinline__ double2 lz_scal(const double* s, int e, int m) {
+  double2 v = make_double2(0.0, 0.0);
+  if (s != nullptr) {
+    if (CPLX) { if (e < m) v.x = v.y = s[e]; }
+    else { if (2 * e < m) v.x = s[2 * e]; if (2 * e + 1 < m) v.y = s[2 * e + 1]; }
+  }
+  return v;
+}
+template <bool CPLX> __device__ __forceinline__ int lz_elems(int m) { return CPLX ? m : ((m + 1) >> 1); }
+
 // acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries [p0, p1) of `row`, in CSR order.
 // (myo, mya): the group's first G entries, already fetched by the caller one iteration ahead; myo is the ELEMENT offset
 // col*ld of the gathered row (32-bit: the host guarantees n*ld < 2^32), so an address is one IMAD.WIDE from the lane's
@@ -59,9 +94,11 @@ __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<d
 // beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
 // Narrow groups (G <= 4 lanes per row) also receive the row's SECOND chunk of G entries prefetched (myo2, mya2): a
 // 7-point row then needs no dependent metadata load inside the loop even with 4 lanes per row.
-template <int G, int NC>
-__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int p0, int p1, unsigned myo, double mya, unsigned myo2,
-                                          double mya2, int g, unsigned gmask, const double* const (&Ul)[NC], double2 (&acc)[NC]) {
+template <int G, int NC, bool CPLX>
+__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int p0, int p1, unsigned myo, typename LzVal<CPLX>::T mya,
+                                          unsigned myo2, typename LzVal<CPLX>::T mya2, int g, unsigned gmask,
+                                          const double* const (&Ul)[NC], double2 (&acc)[NC]) {
+  typedef LzVal<CPLX> V;
   constexpr int UN = (G >= 4) ? 4 : G;
   constexpr bool PF2 = (G <= 4);
   const unsigned ldu = (unsigned)a.ld;
@@ -72,16 +109,16 @@ __device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int 
       mya = mya2;
     } else if (pb != p0) {
       myo = row_eo;
-      mya = 0.0;
-      if (g < cnt) { myo = (unsigned)a.col[pb + g] * ldu; mya = a.val[pb + g]; }
+      mya = V::zero();
+      if (g < cnt) { myo = (unsigned)a.col[pb + g] * ldu; mya = V::load(a.val, pb + g); }
     }
     for (int t = 0; t < cnt; t += UN) {
       unsigned eo[UN];
-      double aa[UN];
+      typename V::T aa[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         eo[u] = __shfl_sync(gmask, myo, t + u, G);
-        aa[u] = __shfl_sync(gmask, mya, t + u, G);
+        aa[u] = V::shfl(gmask, mya, t + u, G);
       }
       double2 xv[UN][NC];
 #pragma unroll
@@ -91,10 +128,7 @@ __device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int 
 #pragma unroll
       for (int u = 0; u < UN; ++u)
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          acc[k].x = fma(aa[u], xv[u][k].x, acc[k].x);
-          acc[k].y = fma(aa[u], xv[u][k].y, acc[k].y);
-        }
+        for (int k = 0; k < NC; ++k) V::fma_acc(acc[k], aa[u], xv[u][k]);
     }
   }
 }
@@ -122,8 +156,9 @@ __device__ __forceinline__ double2 lz_next(double2 t, double2 ra, double2 uo) {
   return r;
 }
 
-template <int G, int NC, int MODE, int THREADS>
+template <int G, int NC, int MODE, int THREADS, bool CPLX = false>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
+  typedef LzVal<CPLX> V;
   if (a.done != nullptr && *a.done != 0) return;
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
@@ -131,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   const unsigned gmask = gm0 << (sub * G);
   const int wib = threadIdx.x >> 5, wpb = THREADS >> 5;
   constexpr int STEP = (THREADS / 32) * RPW;          // rows the CTA covers per iteration
-  const int P = (a.m + 1) >> 1;
+  const int P = lz_elems<CPLX>(a.m);                  // 16-byte elements per row: column pairs (real) or complex columns
   const int n = (int)a.n;
   // Rows are dealt to the CTAs in tiles of `tile_rows` consecutive rows, round robin: the whole grid sweeps the matrix as
   // one moving front, so a vector row fetched as somebody's far neighbour is still in L2 when the front reaches it
@@ -158,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   for (int i = threadIdx.x; i < 4 * (FC_MAXCOLS / 2); i += THREADS) {
     const int w = i / (FC_MAXCOLS / 2), pc = i % (FC_MAXCOLS / 2);
     const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta) : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : a.s_coef));
-    s_sc[w][pc] = lz_scal2(src, 2 * pc, a.m);
+    s_sc[w][pc] = lz_scal<CPLX>(src, pc, a.m);
   }
   __syncthreads();
   double2 dot[NC];
@@ -187,9 +222,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
   constexpr bool PF2 = (G <= 4);
   unsigned o_cur = (r_cur < n ? (unsigned)r_cur : 0u) * ldu, o_cur2 = o_cur;
-  double a_cur = 0.0, a_cur2 = 0.0;
-  if (g < p1_cur - p0_cur) { o_cur = (unsigned)a.col[p0_cur + g] * ldu; a_cur = a.val[p0_cur + g]; }
-  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = (unsigned)a.col[p0_cur + G + g] * ldu; a_cur2 = a.val[p0_cur + G + g]; }
+  typename V::T a_cur = V::zero(), a_cur2 = V::zero();
+  if (g < p1_cur - p0_cur) { o_cur = (unsigned)a.col[p0_cur + g] * ldu; a_cur = V::load(a.val, p0_cur + g); }
+  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = (unsigned)a.col[p0_cur + G + g] * ldu; a_cur2 = V::load(a.val, p0_cur + G + g); }
 
   for (int it = 0; it < niter; ++it) {
     const int row = r_cur;
@@ -198,9 +233,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
     int p0_fut = 0, p1_fut = 0;
     if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
     unsigned o_nxt = (r_nxt < n ? (unsigned)r_nxt : 0u) * ldu, o_nxt2 = o_nxt;
-    double a_nxt = 0.0, a_nxt2 = 0.0;
-    if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = a.val[p0_nxt + g]; }
-    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = (unsigned)a.col[p0_nxt + G + g] * ldu; a_nxt2 = a.val[p0_nxt + G + g]; }
+    typename V::T a_nxt = V::zero(), a_nxt2 = V::zero();
+    if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = V::load(a.val, p0_nxt + g); }
+    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = (unsigned)a.col[p0_nxt + G + g] * ldu; a_nxt2 = V::load(a.val, p0_nxt + G + g); }
 
     // own-row operands first (independent of the gather); invalid rows and inactive lanes read valid dummies
     const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
@@ -211,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
       if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
       if constexpr (MODE == LZ_P1 || MODE == LZ_P2) pv[k] = ldg2(Pl[k] + eo_own);
     }
-    lz_gather<G, NC>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
+    lz_gather<G, NC, CPLX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int pc = g + G * k;
@@ -260,9 +295,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
       if (pc < P) {
         double sx = 0.0, sy = 0.0;
         for (int q = 0; q < ngroups; ++q) { const double2 v = red[q * width + pc]; sx += v.x; sy += v.y; }
-        double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
-        o[0] = sx;
-        if (2 * pc + 1 < a.m) o[1] = sy;
+        if (CPLX) a.partial[(int64_t)blockIdx.x * a.pstride + pc] = sx + sy;   // Re(conj(u) t) = sum of both components
+        else {
+          double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
+          o[0] = sx;
+          if (2 * pc + 1 < a.m) o[1] = sy;
+        }
       }
     }
   }
@@ -274,6 +312,7 @@ struct EwMap2 {
   __device__ __forceinline__ EwMap2(int pp) { pc = threadIdx.x % pp; rsub = threadIdx.x / pp; rpb = blockDim.x / pp; }
 };
 
+template <bool CPLX>
 __device__ __forceinline__ void block_reduce_pairs(double2 v, int pp, int P, int m, double* out_row) {
   __shared__ double2 red2[256];
   __syncthreads();
@@ -282,21 +321,25 @@ __device__ __forceinline__ void block_reduce_pairs(double2 v, int pp, int P, int
   if ((int)threadIdx.x < pp && (int)threadIdx.x < P) {
     double sx = 0.0, sy = 0.0;
     for (int q = threadIdx.x; q < (int)blockDim.x; q += pp) { sx += red2[q].x; sy += red2[q].y; }
-    out_row[2 * threadIdx.x] = sx;
-    if (2 * (int)threadIdx.x + 1 < m) out_row[2 * threadIdx.x + 1] = sy;
+    if (CPLX) out_row[threadIdx.x] = sx + sy;
+    else {
+      out_row[2 * threadIdx.x] = sx;
+      if (2 * (int)threadIdx.x + 1 < m) out_row[2 * threadIdx.x + 1] = sy;
+    }
   }
 }
 
 // pass 1, second half of a step: T (in place) <- T - ratio_a * U ; partial = |T|^2
+template <bool CPLX>
 __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_ratio_a,
                                                    const double* __restrict__ U, double* __restrict__ T,
                                                    double* __restrict__ partial, int pstride, const int* __restrict__ done) {
   if (done != nullptr && *done != 0) return;
   EwMap2 e(pp);
-  const int P = (m + 1) >> 1;
+  const int P = lz_elems<CPLX>(m);
   double2 acc = make_double2(0.0, 0.0);
   if (e.pc < P) {
-    const double2 ra = lz_scal2(s_ratio_a, 2 * e.pc, m);
+    const double2 ra = lz_scal<CPLX>(s_ratio_a, e.pc, m);
     const int64_t stride = (int64_t)gridDim.x * e.rpb;
     int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub;
     for (; row + 3 * stride < n; row += 4 * stride) {   // four independent rows in flight per thread (narrow blocks are latency bound)
@@ -324,16 +367,17 @@ __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int
       acc.y = fma(r.y, r.y, acc.y);
     }
   }
-  block_reduce_pairs(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
+  block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
 }
 
 // Q += coef * U  (last pass-2 step: no further Lanczos vector is needed)
+template <bool CPLX>
 __global__ void __launch_bounds__(256) k_lz_axpy(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_coef,
                                                  const double* __restrict__ U, double* __restrict__ Q) {
   EwMap2 e(pp);
-  const int P = (m + 1) >> 1;
+  const int P = lz_elems<CPLX>(m);
   if (e.pc >= P) return;
-  const double2 cf = lz_scal2(s_coef, 2 * e.pc, m);
+  const double2 cf = lz_scal<CPLX>(s_coef, e.pc, m);
   for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
     const int64_t off = row * ld + 2 * e.pc;
     const double2 u = ldg2(U + off);
@@ -344,38 +388,49 @@ __global__ void __launch_bounds__(256) k_lz_axpy(int64_t n, int m, int pp, int64
   }
 }
 
-// real part of a complex block -> real block (columns [0, m); the pad column of an odd m is zeroed); partial = |x|^2
+// engine block (complex storage, row stride ldz) -> compact Lanczos block.  Real problems keep the real part of the m columns
+// as column pairs (the pad column of an odd m is zeroed); complex problems copy the m complex columns.  partial = |x|^2
+template <bool CPLX>
 __global__ void __launch_bounds__(256) k_lz_real_part(int64_t n, int m, int pp, int64_t ldz, int64_t ld,
                                                       const cx<double>* __restrict__ Z, double* __restrict__ X,
                                                       double* __restrict__ partial, int pstride) {
   EwMap2 e(pp);
-  const int P = (m + 1) >> 1;
+  const int P = lz_elems<CPLX>(m);
   double2 acc = make_double2(0.0, 0.0);
   if (e.pc < P) {
-    const int c0 = 2 * e.pc;
     for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
       double2 v;
-      v.x = Z[row * ldz + c0].x;
-      v.y = (c0 + 1 < m) ? Z[row * ldz + c0 + 1].x : 0.0;
-      stg2(X + row * ld + c0, v);
+      if (CPLX) {
+        const cx<double> z = Z[row * ldz + e.pc];
+        v = make_double2(z.x, z.y);
+      } else {
+        const int c0 = 2 * e.pc;
+        v.x = Z[row * ldz + c0].x;
+        v.y = (c0 + 1 < m) ? Z[row * ldz + c0 + 1].x : 0.0;
+      }
+      stg2(X + row * ld + 2 * e.pc, v);
       acc.x = fma(v.x, v.x, acc.x);
       acc.y = fma(v.y, v.y, acc.y);
     }
   }
-  if (partial != nullptr) block_reduce_pairs(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
+  if (partial != nullptr) block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
 }
 
-// real block -> complex block with zero imaginary part
+// compact Lanczos block -> engine block (real problems: zero imaginary part)
+template <bool CPLX>
 __global__ void __launch_bounds__(256) k_lz_to_complex(int64_t n, int m, int pp, int64_t ld, int64_t ldz,
                                                        const double* __restrict__ X, cx<double>* __restrict__ Z) {
   EwMap2 e(pp);
-  const int P = (m + 1) >> 1;
+  const int P = lz_elems<CPLX>(m);
   if (e.pc >= P) return;
-  const int c0 = 2 * e.pc;
   for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
-    const double2 v = ldg2(X + row * ld + c0);
-    Z[row * ldz + c0] = mk<double>(v.x, 0.0);
-    if (c0 + 1 < m) Z[row * ldz + c0 + 1] = mk<double>(v.y, 0.0);
+    const double2 v = ldg2(X + row * ld + 2 * e.pc);
+    if (CPLX) Z[row * ldz + e.pc] = mk<double>(v.x, v.y);
+    else {
+      const int c0 = 2 * e.pc;
+      Z[row * ldz + c0] = mk<double>(v.x, 0.0);
+      if (c0 + 1 < m) Z[row * ldz + c0 + 1] = mk<double>(v.y, 0.0);
+    }
   }
 }
 
@@ -590,14 +645,14 @@ __global__ void __launch_bounds__(LZS_THREADS, 2) k_lz_spmm_staged(LzArgs a, LzP
   int4 m_cur = meta_of(0), m_nxt = meta_of(1);
   int l_cur = 0;
   double a_cur = 0.0;
-  if (lane < m_cur.z) { l_cur = pl.lcol[m_cur.y + lane]; a_cur = a.val[m_cur.y + lane]; }
+  if (lane < m_cur.z) { l_cur = pl.lcol[m_cur.y + lane]; a_cur = reinterpret_cast<const double*>(a.val)[m_cur.y + lane]; }
 
   for (int it = 0; it < my_tiles; ++it) {
     const int s = it & 1;
     const int4 m_fut = meta_of(it + 2);
     int l_nxt = 0;
     double a_nxt = 0.0;
-    if (lane < m_nxt.z) { l_nxt = pl.lcol[m_nxt.y + lane]; a_nxt = a.val[m_nxt.y + lane]; }
+    if (lane < m_nxt.z) { l_nxt = pl.lcol[m_nxt.y + lane]; a_nxt = reinterpret_cast<const double*>(a.val)[m_nxt.y + lane]; }
     const int row = m_cur.x;
     const bool valid = row >= 0;
     const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
@@ -619,7 +674,7 @@ __global__ void __launch_bounds__(LZS_THREADS, 2) k_lz_spmm_staged(LzArgs a, LzP
         if (pb != 0) {
           myl = 0;
           mya = 0.0;
-          if (lane < cnt) { myl = pl.lcol[p0 + pb + lane]; mya = a.val[p0 + pb + lane]; }
+          if (lane < cnt) { myl = pl.lcol[p0 + pb + lane]; mya = reinterpret_cast<const double*>(a.val)[p0 + pb + lane]; }
         }
         for (int t = 0; t < cnt; t += 4) {
           int sl[4];

@@ -206,7 +206,7 @@ def lanczos_pass1(A, b, Zne, kmax, target):
     k, maxres = 0, math.inf
     for j in range(kmax):
         t = (A @ u) * inv - ratio_b * u_prev
-        al = np.einsum("ij,ij->j", u, t) * inv
+        al = np.einsum("ij,ij->j", u.conj(), t).real * inv     # real for Hermitian A (complex vectors allowed)
         alpha[j] = al
         scale = np.maximum(scale, np.abs(al))
         u_next = t - (al * inv) * u
@@ -281,7 +281,7 @@ def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None):
     if theta is None:
         b = Q
         F = np.ones((ne, m), dtype=complex)
-        acc = np.zeros((n, m))
+        acc = np.zeros((n, m), dtype=Q.dtype)
     else:
         b = A @ Q - Q * theta
         F = 1.0 / (np.asarray(Zne)[:, None] - theta[None, :])
@@ -306,12 +306,14 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
     fo.check_feast_srci_input(N, M0, Emin, Emax, fpm)
     tol_value = 10.0 ** (-fpm[2])
     Zne, Wne = fo.feast_contour(Emin, Emax, fpm)
-    Qb = np.array(Q0, dtype=np.float64)
+    cplx = np.iscomplexobj(A) or np.iscomplexobj(Q0)     # complex Hermitian A: complex vectors, real tridiagonal and coefficients
+    wdt = np.complex128 if cplx else np.float64
+    Qb = np.array(Q0, dtype=wdt)
     maxloop = fpm[3]
     eps_tol = fo.feast_tolerance(fpm)
     lam = np.zeros(M0)
     res = np.zeros(M0)
-    X = np.zeros((N, M0))
+    X = np.zeros((N, M0), dtype=wdt)
     have_ritz = False
     active = M0
     info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
@@ -327,7 +329,7 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
             if t >= 1e-6:
                 target = min(0.1, t)
         c0, nc = (0, active) if col_slices is None else col_slices(active)
-        acc = np.zeros((N, active))
+        acc = np.zeros((N, active), dtype=wdt)
         if nc > 0:
             acc[:, c0:c0 + nc] = mslanczos_filter(A, Qb[:, c0:c0 + nc], None if first else lam[c0:c0 + nc], Zne, Wne, target,
                                                   inner_maxiter, stats)
@@ -337,15 +339,16 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
         if rank == 0:
             info = fo.ERR_NO_CONV
             break
-        Qr = Qr.real
-        Sq = Qr.T @ (A @ Qr)
-        Sq = 0.5 * (Sq + Sq.T)
+        if not cplx:
+            Qr = Qr.real
+        Sq = Qr.conj().T @ (A @ Qr)
+        Sq = 0.5 * (Sq + Sq.conj().T)
         lam_red, v_red = sla.eigh(Sq)
         Xc = np.zeros((N, M0), dtype=np.complex128)
         Xc[:, :rank] = Qr @ v_red
         lam[:rank] = lam_red
         M = fo.reorder_by_interval(lam, Xc, Emin, Emax, rank)
-        X = Xc.real.copy()
+        X = Xc.copy() if cplx else Xc.real.copy()
         if M == 0:
             info = fo.ERR_NO_CONV
             break

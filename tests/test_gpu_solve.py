@@ -293,3 +293,35 @@ def test_float32_entry_points_types_and_tolerance():
     rc = fc.cfeast_heev(Ah, 2.0, 5.0, 3, fc.feastinit(), Q0=fo.seeded_subspace(3, 3))
     assert rc.info == 0 and rc.M == 3 and rc.q.dtype == np.complex64 and rc.lambda_.dtype == np.float32
     assert np.allclose(np.sort(rc.lambda_), np.linalg.eigvalsh(Ah.astype(np.complex128)), atol=1e-4)
+
+
+@pytest.mark.parametrize("M0", [16, 40])
+def test_complex_hermitian_standard_runs_the_lanczos_path(M0):
+    """zfeast_hcsrev! (sparse/feast_sparse.jl:759-788) on a gauge-transformed 3-D Laplacian: complex Hermitian, analytic spectrum.
+    The engine runs the multi-shift Lanczos recurrence on complex vectors (true filter, real tridiagonal)."""
+    import feastcuda as fc
+    import feast_port as fp
+    N = 10
+    n = N ** 3
+    L = fo.laplacian_3d(N).astype(complex).tocsr()
+    phi = np.random.default_rng(7).uniform(0, 2 * np.pi, n)
+    D = sp.diags(np.exp(1j * phi))
+    A = (D @ L @ D.conj()).tocsr()
+    A = ((A + A.conj().T) * 0.5).tocsc()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
+    Q0 = fo.seeded_subspace(n, M0)
+    r = fc.zfeast_hcsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000)
+    ro = fo.feast_hcsrev(A, Emin, Emax, M0, fo.feastinit(), Q0=Q0, filter="true")
+    _check_pairs(r, ro, A)
+    assert r.stats["lz_steps_p1"] > 0 and r.q.dtype == np.complex128
+    assert np.abs(np.sort(r.lambda_) - ev[:10]).max() < 1e-10
+    rp = fp.feast_hrr_mslanczos(A.tocsr(), Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2000, adaptive=True)
+    assert abs(r.loop - rp.loop) <= 1
+    assert fo.subspace_angle(r.q, rp.q) < 1e-8
+    # the per-node complex BiCGStab (reference filter) reaches the same pairs
+    fpm = fc.feastinit()
+    fpm[3] = 60
+    rb = fc.zfeast_hcsrev(A, Emin, Emax, 48, list(fpm), Q0=fo.seeded_subspace(n, 48), solver="bicgstab", filter="reference",
+                          solver_tol=1e-12, solver_maxiter=4000, ritz_guess=True, inner_rel=1e-9)
+    assert rb.info == 0 and rb.M == 10 and np.abs(np.sort(rb.lambda_) - ev[:10]).max() < 1e-10

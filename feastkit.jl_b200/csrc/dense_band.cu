@@ -108,9 +108,15 @@ static bool dense_factor_range(H* h, int first, int count, const zc* shifts) {
   const int64_t nn = (int64_t)n * n, pst = 2 * (int64_t)n;
   zd* LU = h->dense_pool.as<zd>() + (int64_t)first * nn;
   int* ipiv = h->dense_piv.as<int>() + (int64_t)first * pst;
-  DBuf dz, dinfo;
+  DBuf dz, dinfo, dpart;
   dz.ensure((size_t)count * sizeof(zd));
   dinfo.ensure((size_t)count * sizeof(int));
+  // CTAs per node of the cooperative panel kernel: enough to spread a tall panel, few enough to be co-resident
+  static const int coop_env = getenv("FEASTCUDA_PANEL_CPN") ? atoi(getenv("FEASTCUDA_PANEL_CPN")) : -1;
+  int cpn = 1;
+  if (n >= 2048) cpn = std::max(1, std::min(32, h->sms / std::max(1, count)));
+  if (coop_env >= 1) cpn = coop_env;
+  dpart.ensure((size_t)count * cpn * (sizeof(double) + sizeof(int)) + 64);
   std::vector<zd> zz(count);
   for (int q = 0; q < count; ++q) zz[q] = mk<double>(shifts[q].real(), shifts[q].imag());
   FC_CUDA(cudaMemcpyAsync(dz.p, zz.data(), (size_t)count * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
@@ -122,7 +128,19 @@ static bool dense_factor_range(H* h, int first, int count, const zc* shifts) {
   }
   for (int k0 = 0; k0 < n; k0 += FC_LU_NB) {
     const int nbw = std::min(FC_LU_NB, n - k0);
-    k_dense_panel_lu<<<count, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, pst, dinfo.as<int>());
+    if (cpn > 1) {
+      int n_ = n, k0_ = k0, nbw_ = nbw, cpn_ = cpn;
+      zd* lu_ = LU;
+      int64_t nn_ = nn, pst_ = pst;
+      int* ipiv_ = ipiv;
+      int* info_ = dinfo.as<int>();
+      double* pv_ = dpart.as<double>();
+      int* pi_ = reinterpret_cast<int*>(dpart.as<double>() + (size_t)count * cpn);
+      void* args[] = {&n_, &k0_, &nbw_, &lu_, &nn_, &ipiv_, &pst_, &info_, &cpn_, &pv_, &pi_};
+      FC_CUDA(cudaLaunchCooperativeKernel((void*)k_dense_panel_lu_coop, dim3(count * cpn), dim3(512), args, 0, h->stream));
+    } else {
+      k_dense_panel_lu<<<count, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, pst, dinfo.as<int>());
+    }
     launched(h);
     if (k0 > 0) {
       k_dense_laswp<<<dim3((k0 + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, 0, k0, LU, nn, ipiv, pst);
@@ -146,6 +164,7 @@ static bool dense_factor_range(H* h, int first, int count, const zc* shifts) {
   FC_CUDA(cudaStreamSynchronize(h->stream));
   dz.release();
   dinfo.release();
+  dpart.release();
   bool all_ok = true;
   for (int q = 0; q < count; ++q) {
     if (info[q] != 0) { all_ok = false; h->lu_shift[first + q] = zc(NAN, NAN); }

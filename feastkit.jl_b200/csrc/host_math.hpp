@@ -6,6 +6,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <limits>
 #include <vector>
 
 namespace feastcuda {
@@ -458,6 +459,119 @@ inline bool host_complex_eig(int n, std::vector<zc> A, std::vector<zc>& lam, std
     }
     nrm = nrm > 0.0 ? std::sqrt(nrm) : 1.0;
     for (int i = 0; i < n; ++i) V[(size_t)i * n + k] /= nrm;
+  }
+  return true;
+}
+
+// Eigenpairs of the small pencil S v = lambda B v (row-major r x r) that tolerates a rank-deficient B, the way the
+// reference's eigen(Sq, Aq) (LAPACK QZ, kernel/feast_kernel.jl:186, :532) does for FEAST moment matrices when the search
+// space is larger than the number of eigenvalues inside: Householder QR with column pivoting B P = Q R reveals the
+// numerical rank k; rows k.. of Q^H S P and of R carry only round-off when the null spaces of S and B coincide (the moment
+// case: both are Q0^H f(A) Q0), so the k finite eigenpairs come from the leading k x k blocks and the remaining r-k
+// directions are reported as lambda = +inf with the null-space basis vector P e_j.  A regular pencil with singular B
+// (significant trailing rows of Q^H S P) eliminates them by a Schur complement instead.
+inline bool host_pencil_eig(int n, const std::vector<zc>& S, const std::vector<zc>& B, std::vector<zc>& lam, std::vector<zc>& V,
+                            int* rank_out = nullptr) {
+  for (const zc& v : S) if (!std::isfinite(v.real()) || !std::isfinite(v.imag())) return false;
+  for (const zc& v : B) if (!std::isfinite(v.real()) || !std::isfinite(v.imag())) return false;
+  std::vector<zc> R = B, T = S;
+  std::vector<int> perm(n);
+  for (int j = 0; j < n; ++j) perm[j] = j;
+  auto r_ = [&](int i, int j) -> zc& { return R[(size_t)i * n + j]; };
+  auto t_ = [&](int i, int j) -> zc& { return T[(size_t)i * n + j]; };
+  std::vector<double> cn(n);
+  std::vector<zc> w(n);
+  double r11 = 0.0;
+  int k = 0;
+  for (; k < n; ++k) {
+    int p = k;
+    double best = -1.0;
+    for (int j = k; j < n; ++j) {
+      double s = 0.0;
+      for (int i = k; i < n; ++i) s += std::norm(r_(i, j));
+      cn[j] = s;
+      if (s > best) { best = s; p = j; }
+    }
+    best = std::sqrt(std::max(best, 0.0));
+    if (k == 0) r11 = best;
+    if (!(best > 1e-13 * r11) || !(best > 0.0)) break;
+    if (p != k) {
+      for (int i = 0; i < n; ++i) { std::swap(r_(i, k), r_(i, p)); std::swap(t_(i, k), t_(i, p)); }
+      std::swap(perm[k], perm[p]);
+    }
+    // Householder H = I - 2 w w^H / (w^H w) zeroing R[k+1.., k]; applied from the left to R and to T (= Q^H S P)
+    const zc x0 = r_(k, k);
+    const zc phase = std::abs(x0) > 0.0 ? x0 / std::abs(x0) : zc(1.0);
+    for (int i = k; i < n; ++i) w[i] = r_(i, k);
+    w[k] += phase * best;
+    double wn = 0.0;
+    for (int i = k; i < n; ++i) wn += std::norm(w[i]);
+    if (wn > 0.0) {
+      for (int pass = 0; pass < 2; ++pass) {
+        std::vector<zc>& M = pass == 0 ? R : T;
+        for (int j = (pass == 0 ? k : 0); j < n; ++j) {
+          zc d(0.0);
+          for (int i = k; i < n; ++i) d += std::conj(w[i]) * M[(size_t)i * n + j];
+          d *= 2.0 / wn;
+          for (int i = k; i < n; ++i) M[(size_t)i * n + j] -= d * w[i];
+        }
+      }
+    }
+  }
+  if (rank_out) *rank_out = k;
+  lam.assign(n, zc(std::numeric_limits<double>::infinity(), 0.0));
+  V.assign((size_t)n * n, zc(0.0));
+  for (int j = k; j < n; ++j) V[(size_t)perm[j] * n + j] = 1.0;
+  if (k == 0) return true;
+  std::vector<zc> T11((size_t)k * k), R11((size_t)k * k);
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) { T11[(size_t)i * k + j] = t_(i, j); R11[(size_t)i * k + j] = r_(i, j); }
+  const int m = n - k;
+  std::vector<zc> Xel;  // m x k: w2 = -Xel w1 when the trailing rows of T are significant
+  if (m > 0) {
+    double tn = 0.0, bn = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i < k ? tn : bn) = std::max(i < k ? tn : bn, std::abs(t_(i, j)));
+    if (bn > 1e-8 * std::max(tn, 1e-300)) {
+      std::vector<zc> T22((size_t)m * m), T21((size_t)m * m, zc(0.0));
+      // solve T22 X = T21 column block by block of width m (host_lu_solve works on square right-hand sides)
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) T22[(size_t)i * m + j] = t_(k + i, k + j);
+      Xel.assign((size_t)m * k, zc(0.0));
+      for (int c0 = 0; c0 < k; c0 += m) {
+        std::fill(T21.begin(), T21.end(), zc(0.0));
+        for (int i = 0; i < m; ++i)
+          for (int j = 0; j < std::min(m, k - c0); ++j) T21[(size_t)i * m + j] = t_(k + i, c0 + j);
+        if (!host_lu_solve(m, T22, T21)) return false;
+        for (int i = 0; i < m; ++i)
+          for (int j = 0; j < std::min(m, k - c0); ++j) Xel[(size_t)i * k + c0 + j] = T21[(size_t)i * m + j];
+      }
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+          zc st(0.0), sr(0.0);
+          for (int l = 0; l < m; ++l) { st += t_(i, k + l) * Xel[(size_t)l * k + j]; sr += r_(i, k + l) * Xel[(size_t)l * k + j]; }
+          T11[(size_t)i * k + j] -= st;
+          R11[(size_t)i * k + j] -= sr;
+        }
+    }
+  }
+  if (!host_lu_solve(k, R11, T11)) return false;
+  std::vector<zc> lk, Vk;
+  if (!host_complex_eig(k, T11, lk, Vk)) return false;
+  for (int c = 0; c < k; ++c) {
+    lam[c] = lk[c];
+    std::vector<zc> full(n, zc(0.0));
+    for (int i = 0; i < k; ++i) full[i] = Vk[(size_t)i * k + c];
+    if (!Xel.empty())
+      for (int l = 0; l < m; ++l) {
+        zc s(0.0);
+        for (int i = 0; i < k; ++i) s += Xel[(size_t)l * k + i] * Vk[(size_t)i * k + c];
+        full[k + l] = -s;
+      }
+    double nrm = 0.0;
+    for (int i = 0; i < n; ++i) nrm += std::norm(full[i]);
+    nrm = nrm > 0.0 ? std::sqrt(nrm) : 1.0;
+    for (int i = 0; i < n; ++i) V[(size_t)perm[i] * n + c] = full[i] / nrm;
   }
   return true;
 }

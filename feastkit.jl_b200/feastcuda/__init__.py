@@ -427,6 +427,27 @@ class Engine:
                                                 L.dptr(lam), V.ctypes.data_as(L._dp), L.iptr(sw)))
         return lam, V, int(sw[0])
 
+    def rowtransform(self, X, T):
+        """Y = X @ T on the device (back-projection of the RCI kernels / drivers)."""
+        X = _colmajor_z(X)
+        T = _colmajor_z(T)
+        n, a = X.shape
+        b = T.shape[1]
+        Y = np.zeros((n, b), dtype=np.complex128, order="F")
+        self._ck(self.lib.feastcuda_rowtransform(self.h, n, a, b, X.ctypes.data_as(L._dp), T.ctypes.data_as(L._dp), Y.ctypes.data_as(L._dp)))
+        return Y
+
+    def eig_general(self, A, B=None):
+        """eigen(A, B) of a small general pencil: (lambda, V) with unit-norm columns."""
+        A = _colmajor_z(A)
+        r = A.shape[0]
+        B_ = None if B is None else _colmajor_z(B)
+        lam = np.zeros(r, dtype=np.complex128)
+        V = np.zeros((r, r), dtype=np.complex128, order="F")
+        self._ck(self.lib.feastcuda_eig_general(self.h, r, A.ctypes.data_as(L._dp), None if B_ is None else B_.ctypes.data_as(L._dp),
+                                                lam.ctypes.data_as(L._dp), V.ctypes.data_as(L._dp)))
+        return lam, V
+
     def residuals(self, X, lam):
         X = _colmajor_z(X)
         lam = _as_z(lam)
@@ -457,3 +478,5 @@ def default_engine(device=None):
 
 
 from .api import *  # noqa: E402,F401,F403  (reference-named drivers)
+from .rci import (FeastRCIState, Ref, dfeast_srci, feast_grci, feast_hrci, feast_srci, pdfeast_srci, zfeast_grci,  # noqa: E402,F401
+                  zfeast_hrci)

@@ -92,6 +92,8 @@ SIGNATURES = {
     "feastcuda_gram": [_vp, C.c_int64, C.c_int64, _dp, _dp, _dp],
     "feastcuda_reduced_eig": [_vp, C.c_int64, _dp, _dp, _dp, _dp, _ip],
     "feastcuda_residuals": [_vp, C.c_int64, _dp, _dp, _dp],
+    "feastcuda_rowtransform": [_vp, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp],
+    "feastcuda_eig_general": [_vp, C.c_int64, _dp, _dp, _dp, _dp],
     "feastcuda_nccl_unique_id": [C.c_char_p],
     "feastcuda_nccl_init": [_vp, C.c_int, C.c_int, C.c_char_p],
     "feastcuda_node_partition": [C.c_int64, C.c_int, C.c_int, _ip, _ip],

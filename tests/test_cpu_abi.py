@@ -153,3 +153,39 @@ def test_product_never_imports_the_oracle():
         text = path.read_text()
         assert not re.search(r"^\s*(import|from)\s+(feast_oracle|feast_port|oracle)\b", text, flags=re.M), path
         assert "sys.path" not in text or "oracle" not in text, path
+
+
+def test_rci_init_handshake(lib):
+    """runtests.jl:72-118, 1115-1126 (KA14): after INIT info == 0 and ijob == 10 (Feast_RCI_FACTORIZE) for srci/hrci/grci/pdfeast_srci;
+    invalid sizes come back as FeastError codes in `info`, not exceptions (kernel/feast_kernel.jl:19-35)."""
+    import feastcuda as fc
+    N, M0 = 10, 4
+
+    def bufs(cplx_q):
+        return dict(work=np.zeros((N, M0)), workc=np.zeros((N, M0), dtype=complex),
+                    Aq=np.zeros((M0, M0), dtype=complex if cplx_q else float), Sq=np.zeros((M0, M0), dtype=complex if cplx_q else float),
+                    lam=np.zeros(M0, dtype=complex if cplx_q == "g" else float), q=np.zeros((N, M0), dtype=complex if cplx_q else float),
+                    res=np.zeros(M0))
+    for fn, cplx_q, args in ((fc.feast_srci, False, (0.0, 1.0)), (fc.pdfeast_srci, False, (0.0, 1.0)), (fc.feast_hrci, True, (0.0, 1.0)),
+                             (fc.feast_grci, "g", (0.0 + 0.0j, 1.0))):
+        b = bufs(cplx_q)
+        ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
+        fpm = fc.feastinit()
+        st = fn(ijob, N, Ze, b["work"], b["workc"], b["Aq"], b["Sq"], fpm, eps, loop, args[0], args[1], M0, b["lam"], b["q"], mode, b["res"], info)
+        assert info.v == 0 and ijob.v == 10 and loop.v == 0
+        assert st.initialized and st.ne == (16 if cplx_q == "g" else 8) and abs(Ze.v - st.Zne[0]) == 0
+        assert fpm[49] == 1 and fpm[50] == st.ne                      # fpm[50], fpm[51] of the reference
+        blk = b["workc"] if cplx_q else b["work"]
+        assert np.allclose(np.linalg.norm(blk, axis=0), 1.0)          # unit-norm seeded subspace
+    b = bufs(False)
+    ijob, info = fc.Ref(-1), fc.Ref(-1)
+    fc.feast_srci(ijob, N, fc.Ref(0j), b["work"], b["workc"], b["Aq"], b["Sq"], fc.feastinit(), fc.Ref(0.0), fc.Ref(0), 1.0, 0.0, M0,
+                  b["lam"], b["q"], fc.Ref(0), b["res"], info)
+    assert info.v == 3 and ijob.v == -1                                # Feast_ERROR_EMIN_EMAX
+    info = fc.Ref(-1)
+    fc.feast_srci(fc.Ref(-1), N, fc.Ref(0j), b["work"], b["workc"], b["Aq"], b["Sq"], fc.feastinit(), fc.Ref(0.0), fc.Ref(0), 0.0, 1.0, 11,
+                  b["lam"], b["q"], fc.Ref(0), b["res"], info)
+    assert info.v == 2                                                  # Feast_ERROR_M0
+    with pytest.raises(ValueError):
+        fc.feast_srci(fc.Ref(99), N, fc.Ref(0j), b["work"], b["workc"], b["Aq"], b["Sq"], fc.feastinit(), fc.Ref(0.0), fc.Ref(0), 0.0, 1.0,
+                      M0, b["lam"], b["q"], fc.Ref(0), b["res"], fc.Ref(0), state=fc.FeastRCIState())

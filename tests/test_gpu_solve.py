@@ -6,6 +6,7 @@ subspace (Julia's seeded RNG is not reproducible outside Julia, SURVEY.md §8a a
 """
 import numpy as np
 import pytest
+import scipy.linalg as sla
 import scipy.sparse as sp
 
 import feast_oracle as fo
@@ -352,3 +353,84 @@ def test_staged_gather_variant_matches_the_direct_kernel(monkeypatch):
     assert np.abs(np.sort(r0.lambda_) - np.sort(r1.lambda_)).max() < 1e-12
     assert r1.res.max() < 1e-12 and fo.subspace_angle(r0.q.astype(complex), r1.q.astype(complex)) < 1e-8
     assert abs(r0.stats["lz_steps_p1"] - r1.stats["lz_steps_p1"]) <= 16     # same recurrence up to the dot products' summation order
+
+
+def _rci_drive(fn, A, B, N, M0, Emin, Emax, engine, hermitian, maxiter=400, stop_at_first_mult=False, solver="bicgstab"):
+    """The caller's side of the reverse-communication loop (banded/feast_banded.jl:76-180 shape): factorize = remember the
+    shift, solve = one block solve on the device, mult_a = A q on the device."""
+    import feastcuda as fc
+    ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
+    work = np.zeros((N, M0))
+    workc = np.zeros((N, M0), dtype=complex)
+    dt = complex if hermitian else float
+    Aq, Sq = np.zeros((M0, M0), dtype=dt), np.zeros((M0, M0), dtype=dt)
+    lam, q, res = np.zeros(M0), np.zeros((N, M0), dtype=dt), np.zeros(M0)
+    fpm = fc.feastinit()
+    state = fc.FeastRCIState()
+    z = 0j
+    for _ in range(maxiter):
+        fn(ijob, N, Ze, work, workc, Aq, Sq, fpm, eps, loop, Emin, Emax, M0, lam, q, mode, res, info, state=state, engine=engine)
+        if ijob.v == 10:
+            z = Ze.v
+        elif ijob.v == 11:
+            rhs = workc[:, :M0] if hermitian else work[:, :M0].astype(complex)
+            if B is not None:
+                rhs = engine.apply(fc.B, rhs)
+            X, _, _ = engine.block_solve(z, rhs, solver_tol=1e-13, solver_maxiter=4000, solver=solver)
+            workc[:, :M0] = X
+        elif ijob.v == 30:
+            if stop_at_first_mult:
+                break
+            AX = engine.apply(fc.A, np.asarray(q[:, :mode.v], dtype=complex))
+            if hermitian:
+                workc[:, :mode.v] = AX
+            else:
+                work[:, :mode.v] = AX.real
+        elif ijob.v == 0:
+            break
+    return lam[:mode.v].copy(), np.array(q[:, :mode.v]), res[:mode.v].copy(), info.v, loop.v, eps.v, state
+
+
+def test_rci_state_machines_drive_a_full_solve(engine):
+    """feast_srci! / feast_hrci! (kernel/feast_kernel.jl:7-293, 397-644) with the caller's work done through the stage-level
+    entry points: KA10 (diag(0.5,1,1.5,3), [0.4,1.6] -> 0.5,1,1.5), the n=10 1-D Laplacian (test_parallel_backends.jl:63-168)
+    and a 3x3 complex Hermitian matrix; compared with the oracle's moment solver."""
+    import feastcuda as fc
+    A = sp.diags([0.5, 1.0, 1.5, 3.0]).tocsc()
+    engine.set_sparse(fc.A, A, fc.SYM)
+    engine.clear_b()
+    lam, q, res, info, loop, eps, st = _rci_drive(fc.feast_srci, A, None, 4, 4, 0.4, 1.6, engine, False)
+    assert info == 0 and np.allclose(lam, [0.5, 1.0, 1.5], atol=1e-8) and res.max() < 1e-10
+    L1 = fo.laplacian_1d(10).tocsc()
+    # the reference drives feast_srci! with band LU factorisations (banded/feast_banded.jl:76-180): same here, on the device
+    engine.set_band(fc.A, fo.full_to_banded(L1.toarray(), 1), 1, fc.SYM)
+    engine.clear_b()
+    lam, q, res, info, loop, eps, st = _rci_drive(fc.pdfeast_srci, L1, None, 10, 8, 0.1, 1.9, engine, False, solver="direct")
+    w = np.linalg.eigvalsh(L1.toarray())
+    want = w[(w >= 0.1) & (w <= 1.9)]
+    # M0 = 8 > 4 eigenvalues inside: Aq is rank deficient; the null directions must be deflated, not returned as Ritz values
+    # (LAPACK's QZ, hence the reference and the oracle, may report an arbitrary value for them)
+    assert info == 0, st.extra
+    assert len(lam) == len(want) and np.allclose(lam, want, atol=1e-8)
+    lam5, _, res5, info5, _, _, st5 = _rci_drive(fc.feast_srci, L1, None, 10, 5, 0.1, 1.9, engine, False, solver="direct")
+    ro = fo.feast_smom(L1, None, 0.1, 1.9, 5, fo.feastinit())
+    assert info5 == ro.info == 0 and len(lam5) == ro.M and np.allclose(lam5, ro.lambda_[:ro.M], atol=1e-8), st5.extra
+    assert np.all(np.diff(lam) >= 0) and res.max() < 1e-10                      # feast_sort!: ascending at exit
+    for j in range(len(lam)):
+        assert np.linalg.norm(L1 @ q[:, j] - lam[j] * q[:, j]) / np.linalg.norm(q[:, j]) < 1e-9
+    # H-MOM keeps the reference's half-contour sums 2 w_e Y without a Hermitian part (kernel/feast_kernel.jl:516-524), so its
+    # first-sweep Ritz values are those of (Q0^H h(A) Q0, Q0^H g(A) Q0), g = sum 2w/(z-x), h = sum 2wz/(z-x): restated here
+    v = np.array([0.1 + 0.2j, -0.05 + 0.1j])
+    Ah = sp.diags([np.conj(v), np.array([2.0, 3.0, 4.0], dtype=complex), v], [-1, 0, 1]).tocsc()
+    engine.set_dense(fc.A, Ah.toarray(), fc.HERM)
+    engine.clear_b()
+    lam, q, res, info, loop, eps, st = _rci_drive(fc.feast_hrci, Ah, None, 3, 3, 1.5, 4.5, engine, True, stop_at_first_mult=True, solver="direct")
+    Z, W = fo.feast_contour(1.5, 4.5, fo.feastdefault(fo.feastinit()))
+    Ad = Ah.toarray()
+    G = sum(2 * w * np.linalg.inv(z * np.eye(3) - Ad) for z, w in zip(Z, W))
+    H = sum(2 * w * z * np.linalg.inv(z * np.eye(3) - Ad) for z, w in zip(Z, W))
+    Q0 = st.Q0
+    want_h = np.sort(sla.eigvals(Q0.conj().T @ H @ Q0, Q0.conj().T @ G @ Q0).real)
+    assert np.allclose(st.zAq, Q0.conj().T @ G @ Q0, atol=1e-10) and np.allclose(st.zSq, Q0.conj().T @ H @ Q0, atol=1e-10)
+    assert np.allclose(np.sort(lam), want_h[(want_h >= 1.5) & (want_h <= 4.5)], atol=1e-9)
+    assert abs(lam[np.argmin(abs(lam - 3.0))] - np.linalg.eigvalsh(Ad)[1]) < 0.05          # exact only near the centre

@@ -237,6 +237,106 @@ for (alias, target) in ((:sfeast_scsrev!, :feast_scsrev!), (:sfeast_scsrgv!, :fe
     @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, kw...))
 end
 
+# ---- general (non-Hermitian) family: feast_gcsrgv!/gcsrev! sparse/feast_sparse.jl:873-1006,1531-1545;
+# feast_gegv!/geev! dense/feast_dense.jl:402-593,812-823; feast_gbgv!/gbev! banded/feast_banded.jl:1548-1600 ----------------
+struct FeastGeneralResult{T<:Real}            # core/feast_types.jl:100-118
+    lambda::Vector{Complex{T}}
+    q::Matrix{Complex{T}}
+    M::Int
+    res::Vector{T}
+    info::Int
+    epsout::T
+    loop::Int
+end
+
+function _solve_contour(setA!, setB!, N::Int, Emid::Number, r::Real, M0::Int, fpm::Vector{Int};
+                        Zne=nothing, Wne=nothing, solver::Symbol=:direct, solver_tol::Real=0.0, solver_maxiter::Int=500,
+                        solver_restart::Int=30, sparse::Bool=false)
+    feastdefault!(fpm)
+    # check_feast_grci_input (core/feast_aux.jl:401-425)
+    N > 0 || throw(ArgumentError("Matrix size N must be positive"))
+    0 < M0 <= N || throw(ArgumentError("Number of eigenvalues M0 must be between 1 and N"))
+    r > 0 || throw(ArgumentError("Search radius r must be positive"))
+    h = handle()
+    setA!(h)
+    setB! === nothing ? check(ccall((:feastcuda_clear_b, libfeastcuda), Cint, (Ptr{Cvoid},), h), h) : setB!(h)
+    if Zne === nothing
+        c = feast_gcontour(Emid, r, fpm); Zne, Wne = c.Zne, c.Wne
+    end
+    z = ComplexF64(Emid)
+    opts = Ref(SolverOpts(sparse ? SOLVER_BICGSTAB : SOLVER_DIRECT, solver_tol, solver_maxiter, solver_restart == 30 ? 3 : solver_restart,
+                          0.0, 0, FILTER_REFERENCE, 0, 16, 0, 0, 0.0, 0, 0, 0, Cint(0), 0.0))
+    lambda = zeros(ComplexF64, M0); res = zeros(Float64, M0); X = zeros(ComplexF64, N, M0)
+    M = Ref{Int64}(0); info = Ref{Int64}(0); loop = Ref{Int64}(0); epsout = Ref{Float64}(0.0)
+    GC.@preserve fpm Zne Wne lambda res X begin
+        check(ccall((:feastcuda_solve_contour, libfeastcuda), Cint,
+            (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Int64, Ptr{Int64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Ptr{Cvoid}, Ref{SolverOpts},
+             Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Float64}, Ref{Int64}),
+            h, real(z), imag(z), r, M0, fpm, Zne, Wne, length(Zne), C_NULL, opts, lambda, X, res, M, info, epsout, loop), h)
+    end
+    m = Int(M[])
+    return FeastGeneralResult{Float64}(lambda[1:m], X[:, 1:m], m, res[1:m], Int(info[]), epsout[], Int(loop[]))
+end
+
+feast_gcsrev!(A::SparseMatrixCSC, Emid, r, M0, fpm; kw...) =
+    _solve_contour(h -> set_sparse!(h, FEASTCUDA_A, SparseMatrixCSC{ComplexF64,Int}(A), FEASTCUDA_GEN), nothing, size(A, 1), Emid, r, M0, fpm; sparse=true, kw...)
+feast_gcsrgv!(A::SparseMatrixCSC, B::SparseMatrixCSC, Emid, r, M0, fpm; kw...) =
+    _solve_contour(h -> set_sparse!(h, FEASTCUDA_A, SparseMatrixCSC{ComplexF64,Int}(A), FEASTCUDA_GEN),
+                   h -> set_sparse!(h, FEASTCUDA_B, SparseMatrixCSC{ComplexF64,Int}(B), FEASTCUDA_GEN), size(A, 1), Emid, r, M0, fpm; sparse=true, kw...)
+feast_geev!(A::Matrix, Emid, r, M0, fpm; kw...) =
+    _solve_contour(h -> set_dense!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), FEASTCUDA_GEN), nothing, size(A, 1), Emid, r, M0, fpm; kw...)
+feast_gegv!(A::Matrix, B::Matrix, Emid, r, M0, fpm; kw...) =
+    _solve_contour(h -> set_dense!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), FEASTCUDA_GEN), h -> set_dense!(h, FEASTCUDA_B, Matrix{ComplexF64}(B), FEASTCUDA_GEN),
+                   size(A, 1), Emid, r, M0, fpm; kw...)
+for f in (:feast_gcsrev, :feast_geev)
+    @eval $(Symbol(f, "x!"))(A, Emid, r, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, Emid, r, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
+for f in (:feast_gcsrgv, :feast_gegv)
+    @eval $(Symbol(f, "x!"))(A, B, Emid, r, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, B, Emid, r, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
+function feast_general(A::AbstractMatrix, center::Number, radius::Real; M0::Int=10, fpm=nothing, kw...)   # interfaces/feast_interfaces.jl:274-379
+    size(A, 1) == size(A, 2) || throw(ArgumentError("Matrix must be square"))
+    fpm = fpm === nothing ? feastinit() : fpm
+    M0 = min(M0, size(A, 1))
+    return issparse(A) ? feast_gcsrev!(A, center, radius, M0, fpm; kw...) : feast_geev!(Matrix(A), center, radius, M0, fpm; kw...)
+end
+
+# ---- multi-GPU attach (replaces the MPI communicator of parallel/feast_mpi.jl:9-54): rank 0 creates the id, the
+# application broadcasts its 128 bytes (MPI.Bcast!, a file, Distributed), every rank attaches its handle ------------------
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:feastcuda_nccl_unique_id, libfeastcuda), Cint, (Ptr{UInt8},), id))
+    return id
+end
+nccl_init!(nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:feastcuda_nccl_init, libfeastcuda), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), handle(), nranks, rank, id), handle())
+
+# ---- stage-level wrappers: the block arithmetic inside feast_srci!/feast_hrci!/feast_grci! (kernel/feast_kernel.jl) ------
+# Q_proj .+= w .* Y (:143,:519,:766)
+accumulate!(Qacc::Matrix{ComplexF64}, w::Number, Y::Matrix{ComplexF64}) = (check(ccall((:feastcuda_accumulate, libfeastcuda), Cint,
+    (Ptr{Cvoid}, Cdouble, Cdouble, Int64, Ptr{ComplexF64}, Ptr{ComplexF64}), handle(), real(w), imag(w), size(Y, 2), Y, Qacc), handle()); Qacc)
+# Q0' * Y (:147,:522)
+function gram(X::Matrix{ComplexF64}, Y::Matrix{ComplexF64})
+    C = zeros(ComplexF64, size(X, 2), size(X, 2))
+    check(ccall((:feastcuda_gram, libfeastcuda), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                handle(), size(X, 1), size(X, 2), X, Y, C), handle())
+    return C
+end
+# Q_proj * V (:187,:547,:838-845)
+function rowtransform(X::Matrix{ComplexF64}, T::Matrix{ComplexF64})
+    Y = zeros(ComplexF64, size(X, 1), size(T, 2))
+    check(ccall((:feastcuda_rowtransform, libfeastcuda), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                handle(), size(X, 1), size(X, 2), size(T, 2), X, T, Y), handle())
+    return Y
+end
+# eigen(Sq, Aq) (:175,:539,:812)
+function eig_general(S::Matrix{ComplexF64}, B::Union{Nothing,Matrix{ComplexF64}}=nothing)
+    r = size(S, 1); lambda = zeros(ComplexF64, r); V = zeros(ComplexF64, r, r)
+    check(ccall((:feastcuda_eig_general, libfeastcuda), Cint, (Ptr{Cvoid}, Int64, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                handle(), r, S, B === nothing ? C_NULL : pointer(B), lambda, V), handle())
+    return lambda, V
+end
+
 # high-level feast(A[,B],(Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272 (dispatch only)
 function feast(A::AbstractMatrix, interval::Tuple; M0::Int=10, fpm=nothing, kw...)
     size(A, 1) == size(A, 2) || throw(ArgumentError("Matrix must be square"))
@@ -253,6 +353,7 @@ end
 
 export feastinit, feastinit!, feastdefault!, feast_contour, feast_gcontour, feast, FeastResult,
        feast_scsrev!, feast_scsrgv!, feast_hcsrev!, feast_hcsrgv!, feast_syev!, feast_sygv!, feast_heev!, feast_hegv!,
-       feast_sbev!, feast_sbgv!, feast_hbev!, feast_hbgv!
+       feast_sbev!, feast_sbgv!, feast_hbev!, feast_hbgv!,
+       FeastGeneralResult, feast_general, feast_gcsrev!, feast_gcsrgv!, feast_geev!, feast_gegv!
 
 end # module

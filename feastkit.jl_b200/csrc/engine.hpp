@@ -64,7 +64,8 @@ struct HostCsr {
 
 struct DevCsr {
   DBuf ptr, col, val;
-  bool uploaded = false;
+  DBuf val32;               // FP32 copy of the entries (mixed-precision Lanczos vectors, real operators only)
+  bool uploaded = false, val32_ready = false;
 };
 
 struct HostDense {  // column-major n x n, complex interleaved or real

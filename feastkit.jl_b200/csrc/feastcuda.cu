@@ -12,6 +12,7 @@
 #include "kernels_reduced.cuh"
 #include "kernels_sparse.cuh"
 #include "kernels_lanczos.cuh"
+#include "kernels_lanczos_f32.cuh"
 #include "dense_band.cuh"
 
 using namespace feastcuda;
@@ -591,6 +592,31 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
   h->stats.spmm_launches++;
 }
 
+template <int MODE>
+static void lz32_launch(H* h, LzArgs32& a, int* grid_out) {
+  const int P = (a.m + 3) / 4;   // 4-column elements per row = lanes per row
+#define FC_LZ32(G)                                                                 \
+  do {                                                                             \
+    const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G));                          \
+    *grid_out = grid;                                                              \
+    k_lz32_spmm<G, MODE, 512><<<grid, 512, 0, h->stream>>>(a);                     \
+  } while (0)
+  if (P <= 1) FC_LZ32(1);
+  else if (P <= 2) FC_LZ32(2);
+  else if (P <= 4) FC_LZ32(4);
+  else if (P <= 8) FC_LZ32(8);
+  else if (P <= 16) FC_LZ32(16);
+  else FC_LZ32(32);
+#undef FC_LZ32
+  check_launch(h);
+  h->stats.spmm_launches++;
+}
+
+// FP32 vectors: nvec32 float blocks + nvec64 double blocks per launch
+static double lz32_bytes_spmm(H* h, int m, int nvec32, int nvec64) {
+  return (double)h->hA.nnz * 8.0 + 4.0 * (double)(h->hA.n + 1) + (double)h->hA.n * m * (4.0 * nvec32 + 8.0 * nvec64);
+}
+
 static double lz_bytes_spmm(H* h, int m, int nvec, bool cplx) {
   const double es = cplx ? 16.0 : 8.0;
   return (double)h->hA.nnz * (es + 4.0) + 4.0 * (double)(h->hA.n + 1) + (double)nvec * (double)h->hA.n * m * es;
@@ -598,19 +624,23 @@ static double lz_bytes_spmm(H* h, int m, int nvec, bool cplx) {
 
 template <bool CPLX>
 static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, const double* theta, const zc* Zne, const zc* Wne,
-                       int ne, double target, int kmax, int check_every, MslOut& out) {
+                       int ne, double target, int kmax, int check_every, MslOut& out, bool mixed = false) {
   FC_REQUIRE(h->kind == OP_SPARSE && h->dev_complex == CPLX && !h->has_b, "multi-shift Lanczos needs a standard sparse Hermitian problem");
   FC_REQUIRE(CPLX || (c0 & 1) == 0, "column slices must start at an even column");
   const int64_t n = h->ws_n;
   // the work blocks are COMPACT: row stride = the slice's own column count (in doubles: even(nc) real, 2 nc complex), so a
   // rank that owns 8 of 64 columns streams dense 64-byte rows instead of touching 64 bytes out of every 512
-  const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : ((nc + 1) & ~1);
+  // mixed precision (FP32 Lanczos vectors, real problems): 4-column elements, so every compact block is padded to a multiple of 4
+  mixed = mixed && !CPLX && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
+  const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : (mixed ? ((nc + 3) & ~3) : ((nc + 1) & ~1));
   FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   kmax = std::max(1, std::min(kmax, 16384));
   check_every = std::max(1, check_every);
   const int P = CPLX ? nc : (nc + 1) / 2;
   const int pp = pow2_ge(P);
   const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
+  const int pp4 = pow2_ge((nc + 3) / 4);
+  const int egrid4 = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp4) - 1) / (256 / pp4), (int64_t)h->sms * h->lz_egrid_mult));
 
   // ---- device scalars ------------------------------------------------------------------------------------------
   const size_t rowsz = (size_t)FC_MAXCOLS;
@@ -646,12 +676,13 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   double* part = h->partial_r.as<double>();
 
   std::vector<double> rho(nc, 0.0);
+  if (mixed) FC_CUDA(cudaMemsetAsync(QA, 0, (size_t)n * (size_t)ld * sizeof(double), h->stream));   // pad columns included
   if (!have_ritz) {
     k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS);
     check_launch(h);
     k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, egrid, FC_MAXCOLS, nc);
     check_launch(h);
-    FC_CUDA(cudaMemset2DAsync(QA, (size_t)ld * sizeof(double), 0, (size_t)(2 * P) * sizeof(double), (size_t)n, h->stream));
+    if (!mixed) FC_CUDA(cudaMemset2DAsync(QA, (size_t)ld * sizeof(double), 0, (size_t)(2 * P) * sizeof(double), (size_t)n, h->stream));
   } else {
     // rho(theta) = Re sum_e 2 w_e / (z_e - theta): what the rational filter does to an exact eigenvector
     for (int c = 0; c < nc; ++c) {
@@ -680,6 +711,29 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   }
 
   auto cur = [&](int j) -> double* { return j == 0 ? RB : ((j & 1) ? UA : UB); };
+  // mixed precision: the FP64 start block (basis or Ritz residual) is rounded once; the three FP32 vectors alias FP64 slots
+  float* F0 = reinterpret_cast<float*>(RQ);
+  auto cur32 = [&](int j) -> float* { return j == 0 ? F0 : reinterpret_cast<float*>((j & 1) ? UA : UB); };
+  if (mixed) {
+    if (!h->dA.val32_ready) {
+      h->dA.val32.ensure((size_t)std::max<int64_t>(h->hA.nnz, 1) * sizeof(float));
+      k_lz32_vals<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(h->hA.nnz, h->dA.val.as<double>(), h->dA.val32.as<float>());
+      check_launch(h);
+      h->dA.val32_ready = true;
+    }
+    k_lz32_narrow<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, RB, F0);
+    check_launch(h);
+  }
+  auto args32 = [&](int j) {
+    LzArgs32 a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.m = nc; a.ld = ld;
+    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val32.as<float>();
+    a.U = cur32(j); a.prev = j > 0 ? cur32(j - 1) : cur32(j); a.out = cur32(j + 1);
+    a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
+    a.tile_rows = h->lz_tile_rows;
+    return a;
+  };
 
   // ---- pass 1: build T_k, device-side convergence flag ----------------------------------------------------------
   Timer t1;
@@ -689,26 +743,36 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   while (done < kmax) {
     const int batch = std::min(check_every, kmax - done);
     for (int j = done; j < done + batch; ++j) {
-      LzArgs a;
-      memset(&a, 0, sizeof(a));
-      a.n = n; a.m = nc; a.ld = ld;
-      a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
-      a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1);
-      a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
-      a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
       const bool smp = (j % 16) == 3;
       int g = 0;
       int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
-      lz_launch<LZ_P1, CPLX>(h, a, &g);
+      if (mixed) {
+        LzArgs32 a = args32(j);
+        a.partial = part; a.pstride = FC_MAXCOLS; a.done = S.done_k;
+        lz32_launch<LZ_P1>(h, a, &g);
+      } else {
+        LzArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = n; a.m = nc; a.ld = ld;
+        a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
+        a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1);
+        a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
+        a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
+        lz_launch<LZ_P1, CPLX>(h, a, &g);
+      }
       sample_end(h, ev);
       k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, g, FC_MAXCOLS, nc);
       check_launch(h);
       ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_UPD, j) : -1;
-      k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
-                                                 S.done_k);
+      if (mixed)
+        k_lz32_update<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, S.ratio_a + (size_t)j * rowsz, cur32(j), cur32(j + 1), part, FC_MAXCOLS,
+                                                     S.done_k);
+      else
+        k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
+                                                   S.done_k);
       check_launch(h);
       sample_end(h, ev);
-      k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, egrid, FC_MAXCOLS, nc);
+      k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, mixed ? egrid4 : egrid, FC_MAXCOLS, nc);
       check_launch(h);
     }
     done += batch;
@@ -717,10 +781,11 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     if (flag[0] != 0) { kfinal = flag[0]; out.converged = true; break; }
   }
   if (kfinal == 0) kfinal = done;
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = lz_bytes_spmm(h, nc, 3, CPLX);
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_UPD] = 3.0 * (double)n * nc * (CPLX ? 16.0 : 8.0);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = mixed ? lz32_bytes_spmm(h, nc, 3, 0) : lz_bytes_spmm(h, nc, 3, CPLX);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_UPD] = 3.0 * (double)n * nc * (mixed ? 4.0 : (CPLX ? 16.0 : 8.0));
   drain_events(h, kfinal);
   h->stats.lz_steps_p1 += kfinal;
+  if (mixed) h->stats.lz_steps_fp32 += kfinal;
   h->stats.krylov_iters += kfinal;
   h->stats.col_iters += (int64_t)kfinal * nc;
   h->stats.ms_lz_p1 += t1.ms();
@@ -772,28 +837,35 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   Timer t2;
   for (int j = 0; j < k; ++j) {
     if (j == k - 1) {
-      k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, cur(j), QA);
+      if (mixed) k_lz32_axpy<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, d_coef + (size_t)j * rowsz, cur32(j), QA);
+      else k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, cur(j), QA);
       check_launch(h);
       break;
     }
-    LzArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = n; a.m = nc; a.ld = ld;
-    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
-    a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1); a.Q = QA;
-    a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
-    a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
-    a.tile_rows = h->lz_tile_rows;
     const bool smp = (j % 16) == 3;
     int g = 0;
     const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
-    lz_launch<LZ_P2, CPLX>(h, a, &g);
+    if (mixed) {
+      LzArgs32 a = args32(j);
+      a.Q = QA; a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
+      lz32_launch<LZ_P2>(h, a, &g);
+    } else {
+      LzArgs a;
+      memset(&a, 0, sizeof(a));
+      a.n = n; a.m = nc; a.ld = ld;
+      a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
+      a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1); a.Q = QA;
+      a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
+      a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
+      a.tile_rows = h->lz_tile_rows;
+      lz_launch<LZ_P2, CPLX>(h, a, &g);
+    }
     sample_end(h, ev);
   }
   k_lz_to_complex<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
   check_launch(h);
   sync(h);  // coef is a host buffer
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = lz_bytes_spmm(h, nc, 5, CPLX);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = mixed ? lz32_bytes_spmm(h, nc, 3, 2) : lz_bytes_spmm(h, nc, 5, CPLX);
   drain_events(h);
   h->stats.lz_steps_p2 += k;
   h->stats.ms_lz_p2 += t2.ms();
@@ -1092,6 +1164,9 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
   std::vector<double> lam(m0, 0.0), res(m0, 0.0);
   std::vector<double> cost(ne, 1.0);
   bool have_ritz = false;
+  // fpm[42] ("single-precision solver"): FP32 Lanczos vectors until a sweep stops contracting the residual, then FP64
+  bool use_fp32 = o.mixed == 1 || (o.mixed == 2 && fpm[41] == 1);
+  double eps_before_sweep = INFINITY;
   int qb = BS_QB, xr = BS_XR;  // current basis / Ritz-vector slots (swapped every loop)
   int res_slot = -1;           // slot holding the Ritz vectors that M_found refers to
   std::vector<zc> Sq, Aq, V;
@@ -1132,12 +1207,13 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       if (nc > 0) {
         MslOut mo;
         if (cplx_msl) msl_filter<true>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
-        else msl_filter<false>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
+        else msl_filter<false>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo,
+                               use_fp32);
         h->stats.node_solves += ne;
         for (int e = 0; e < ne && e < 128; ++e) h->stats.node_iters[e] = mo.k;
         if (getenv("FEASTCUDA_VERBOSE"))
-          fprintf(stderr, "[feastcuda r%d] loop %d: lanczos k=%d maxres=%.3e converged=%d cols=[%d,%d)\n", h->rank, loop_idx, mo.k,
-                  mo.maxres, (int)mo.converged, c0, c0 + nc);
+          fprintf(stderr, "[feastcuda r%d] loop %d: lanczos k=%d maxres=%.3e converged=%d cols=[%d,%d) target=%.1e fp32=%d\n", h->rank,
+                  loop_idx, mo.k, mo.maxres, (int)mo.converged, c0, c0 + nc, target, (int)use_fp32);
       }
     }
     if (dense_items_batched(h, items, ne, active, Zne, Wne, 2.0, rhs, &failed) && failed) info_code = 8;
@@ -1253,6 +1329,9 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     h->stats.ms_resid += tres.ms();
     eps_val = M > 0 ? max_res : INFINITY;
     M_found = M;
+    // a refined FP32 sweep that gained less than a factor 4 has hit single precision's attainable accuracy for this spectrum
+    if (use_fp32 && have_ritz && std::isfinite(eps_before_sweep) && !(eps_val <= 0.25 * eps_before_sweep)) use_fp32 = false;
+    eps_before_sweep = eps_val;
     if (getenv("FEASTCUDA_VERBOSE"))
       fprintf(stderr, "[feastcuda r%d] loop %d: M=%d rank=%d epsout=%.3e items=%zu iters(last)=%d\n", h->rank, loop_idx, M, rank,
               eps_val, items.size(), (int)h->stats.node_iters[items.empty() ? 0 : items.back().node]);
@@ -1558,6 +1637,7 @@ static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t
   if (which == FEASTCUDA_A) {
     ingest_csr(h->hA, n, nnz, ptr, idx, val, cplx, base, fmt, structure);
     h->dA.uploaded = false;
+    h->dA.val32_ready = false;
     h->lzp_built = false;
     if (h->kind != OP_SPARSE) { h->has_b = false; h->hB.set = false; }
     h->kind = OP_SPARSE;

@@ -248,7 +248,7 @@ class Engine:
     @staticmethod
     def make_opts(solver="bicgstab", solver_tol=0.0, solver_maxiter=500, solver_restart=3, inner_rel=0.0, ritz_guess=False,
                   filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False, inner_rel0=0.0, maxiter0=0,
-                  keep_going=False, adaptive=False, eps_floor=0.0):
+                  keep_going=False, adaptive=False, eps_floor=0.0, mixed=False):
         o = SolverOpts()
         o.solver = {"direct": SOLVER_DIRECT, "bicgstab": SOLVER_BICGSTAB, "mslanczos": SOLVER_MSLANCZOS}[solver]
         o.tol = float(solver_tol)
@@ -266,6 +266,7 @@ class Engine:
         o.keep_going = int(bool(keep_going))
         o.adaptive = int(bool(adaptive))
         o.eps_floor = float(eps_floor)
+        o.mixed = 2 if mixed == "fpm" else int(bool(mixed))      # "fpm": follow fpm[42] (core/feast_parameters.jl:316-319)
         return o
 
     def upload_subspace(self, M0, Q0=None):

@@ -25,7 +25,7 @@ class SolverOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("tol", C.c_double), ("maxiter", C.c_int32), ("restart", C.c_int32),
                 ("inner_rel", C.c_double), ("ritz_guess", C.c_int32), ("filter", C.c_int32), ("shard", C.c_int32),
                 ("check_every", C.c_int32), ("q0_real", C.c_int32), ("x_real", C.c_int32), ("inner_rel0", C.c_double),
-                ("maxiter0", C.c_int32), ("keep_going", C.c_int32), ("adaptive", C.c_int32), ("reserved", C.c_int32), ("eps_floor", C.c_double)]
+                ("maxiter0", C.c_int32), ("keep_going", C.c_int32), ("adaptive", C.c_int32), ("mixed", C.c_int32), ("eps_floor", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -37,7 +37,8 @@ class Stats(C.Structure):
                 ("ms_allreduce", C.c_double), ("ms_spmm_sampled", C.c_double), ("spmm_sampled", C.c_int64),
                 ("bytes_spmm_alg", C.c_double), ("node_iters", C.c_int64 * 128),
                 ("lz_steps_p1", C.c_int64), ("lz_steps_p2", C.c_int64), ("ms_lz_p1", C.c_double), ("ms_lz_p2", C.c_double),
-                ("ms_kern", C.c_double * 8), ("n_kern", C.c_int64 * 8), ("bytes_kern", C.c_double * 8), ("ms_dev_run", C.c_double)]
+                ("ms_kern", C.c_double * 8), ("n_kern", C.c_int64 * 8), ("bytes_kern", C.c_double * 8), ("ms_dev_run", C.c_double),
+                ("lz_steps_fp32", C.c_int64)]
 
     def as_dict(self):
         arrays = ("node_iters", "ms_kern", "n_kern", "bytes_kern")

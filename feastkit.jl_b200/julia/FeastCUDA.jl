@@ -35,7 +35,7 @@ struct SolverOpts              # feastcuda_solver_opts (88 bytes, C layout)
     maxiter0::Cint
     keep_going::Cint
     adaptive::Cint
-    reserved::Cint
+    mixed::Cint
     eps_floor::Cdouble
 end
 

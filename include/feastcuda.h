@@ -66,7 +66,9 @@ typedef struct {
                          /*    vectors seed the next loop (the reference stops with info=5)                   */
   int32_t adaptive;      /* 1 (Lanczos path): once the eigen-residual is within reach of the tolerance, the sweep's     */
                          /*    inner target becomes 2*tol/epsout_prev (clamped to [1e-6, 0.1]) so that it is the last one */
-  int32_t reserved;
+  int32_t mixed;         /* 1, or 2 = when fpm[42] == 1 (Lanczos path, real symmetric): fpm[42] "single-precision solver" (core/feast_parameters.jl:316-319) --  */
+                         /*    FP32 Krylov vectors and matrix entries, FP64 scalars/accumulator/Rayleigh-Ritz; falls back to    */
+                         /*    FP64 vectors when a refined sweep gains less than a factor 4                                     */
   double  eps_floor;     /* > 0: the convergence tolerance is max(10^-fpm[3], eps_floor) -- the Float32 entry points      */
                          /*    (sfeast_*, cfeast_*) pass sqrt(eps(Float32)), core/feast_parameters.jl:398-405              */
 } feastcuda_solver_opts;
@@ -88,6 +90,7 @@ typedef struct {
   int64_t n_kern[8];
   double  bytes_kern[8];
   double  ms_dev_run;                 /* CUDA-event time (library stream) of the feastcuda_run_interval calls    */
+  int64_t lz_steps_fp32;              /* pass-1 Lanczos steps run with FP32 vectors (opts.mixed)                 */
 } feastcuda_stats;
 
 enum { FEASTCUDA_KERN_SPMM_Z = 0,   /* complex shifted SpMM (BiCGStab)            */

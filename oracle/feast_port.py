@@ -186,31 +186,48 @@ def feast_hrr_bicgstab(A, B, Emin, Emax, M0, fpm, Q0, inner_rtol=None, inner_rel
 # --------------------------------------------------------------------------------------------------
 # multi-shift two-pass Lanczos (the engine's solver for standard real-symmetric problems)
 # --------------------------------------------------------------------------------------------------
-def lanczos_pass1(A, b, Zne, kmax, target):
+_A32_CACHE = {}
+
+
+def _narrow_operator(A):
+    """FP32 copy of the operator's entries (k_lz32_vals), cached per matrix object."""
+    key = id(A)
+    if key not in _A32_CACHE:
+        _A32_CACHE.clear()
+        _A32_CACHE[key] = A.astype(np.float32)
+    return _A32_CACHE[key]
+
+
+def lanczos_pass1(A, b, Zne, kmax, target, mixed=False):
     """Lock-step Lanczos on the columns of the real block b; stops after the first step k at which every
     shifted system's residual estimate beta_{k+1} |e_k^T (z_e I - T_k)^-1 e_1| (relative to ||b||) is <= target.
     Mirrors kernels_lanczos.cuh: k_lz_spmm<LZ_P1> / k_lz_update / k_lz_scal1 / k_lz_scal2 (unnormalised vectors,
-    breakdown freeze at beta <= 1e-13 * max(|alpha|, beta)).  Returns alpha (k x m), beta ((k+1) x m), k, maxres."""
+    breakdown freeze at beta <= 1e-13 * max(|alpha|, beta)).  Returns alpha (k x m), beta ((k+1) x m), k, maxres.
+    mixed: kernels_lanczos_f32.cuh -- FP32 vectors/entries/applied scalars, FP64 dot products and recurrences."""
     n, m = b.shape
+    vdt = np.float32 if mixed else b.dtype
+    Aop = _narrow_operator(A) if mixed else A
+    rnd = (lambda x: np.asarray(x, dtype=np.float32)) if mixed else (lambda x: x)
     ne = len(Zne)
     alpha = np.zeros((kmax, m))
     beta = np.zeros((kmax + 1, m))
     beta[0] = np.linalg.norm(b, axis=0)
     inv = np.where(beta[0] > 1e-290, 1.0 / np.where(beta[0] > 0, beta[0], 1.0), 0.0)
     scale = np.zeros(m)
-    u_prev = np.zeros_like(b)
-    u = b.copy()
+    u = b.astype(vdt)
+    u_prev = np.zeros_like(u)
     ratio_b = np.zeros(m)
     d = np.zeros((ne, m), dtype=complex)
     g = np.zeros((ne, m), dtype=complex)
     k, maxres = 0, math.inf
+    acc_dt = np.float64 if mixed else None
     for j in range(kmax):
-        t = (A @ u) * inv - ratio_b * u_prev
-        al = np.einsum("ij,ij->j", u.conj(), t).real * inv     # real for Hermitian A (complex vectors allowed)
+        t = (Aop @ u) * rnd(inv) - rnd(ratio_b) * u_prev
+        al = np.einsum("ij,ij->j", u.conj(), t, dtype=acc_dt).real * inv     # real for Hermitian A (complex vectors allowed)
         alpha[j] = al
         scale = np.maximum(scale, np.abs(al))
-        u_next = t - (al * inv) * u
-        bn = np.linalg.norm(u_next, axis=0)
+        u_next = t - rnd(al * inv) * u
+        bn = np.sqrt(np.einsum("ij,ij->j", u_next.conj(), u_next, dtype=acc_dt).real)
         ok = (bn > 1e-290) & (bn > 1e-13 * scale) & (inv != 0.0)
         beta[j + 1] = np.where(ok, bn, 0.0)
         inv_next = np.where(ok, 1.0 / np.where(bn > 0, bn, 1.0), 0.0)
@@ -258,23 +275,27 @@ def lanczos_coefficients(alpha, beta, Zne, Wne, F):
     return coef
 
 
-def lanczos_pass2(A, b, alpha, beta, coef, Q):
-    """Re-run the recurrence with the stored scalars and accumulate Q += coef_j * u_j (k_lz_spmm<LZ_P2>)."""
+def lanczos_pass2(A, b, alpha, beta, coef, Q, mixed=False):
+    """Re-run the recurrence with the stored scalars and accumulate Q += coef_j * u_j (k_lz_spmm<LZ_P2>; mixed:
+    k_lz32_spmm<LZ_P2>, FP32 vectors into the FP64 accumulator)."""
     k, m = alpha.shape
     inv = np.where(beta > 0, 1.0 / np.where(beta > 0, beta, 1.0), 0.0)
-    u_prev = np.zeros_like(b)
-    u = b.copy()
+    vdt = np.float32 if mixed else b.dtype
+    Aop = _narrow_operator(A) if mixed else A
+    rnd = (lambda x: np.asarray(x, dtype=np.float32)) if mixed else (lambda x: x)
+    u = b.astype(vdt)
+    u_prev = np.zeros_like(u)
     for j in range(k):
         Q += coef[j] * u
         if j == k - 1:
             break
         ratio_b = beta[j] * inv[j - 1] if j > 0 else np.zeros(m)
-        t = (A @ u) * inv[j] - ratio_b * u_prev
-        u_prev, u = u, t - (alpha[j] * inv[j]) * u
+        t = (Aop @ u) * rnd(inv[j]) - rnd(ratio_b) * u_prev
+        u_prev, u = u, t - rnd(alpha[j] * inv[j]) * u
     return Q
 
 
-def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None):
+def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None, mixed=False):
     """sum_e Re(2 w_e (z_e I - A)^-1 q) for the real block Q; theta (Ritz values) or None (zero guess)."""
     n, m = Q.shape
     ne = len(Zne)
@@ -286,9 +307,10 @@ def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None):
         b = A @ Q - Q * theta
         F = 1.0 / (np.asarray(Zne)[:, None] - theta[None, :])
         acc = Q * np.real((2 * np.asarray(Wne)[:, None] * F).sum(axis=0))
-    alpha, beta, k, maxres = lanczos_pass1(A, b, Zne, kmax, target)
+    mixed = mixed and not np.iscomplexobj(b)
+    alpha, beta, k, maxres = lanczos_pass1(A, b, Zne, kmax, target, mixed)
     coef = lanczos_coefficients(alpha, beta, Zne, Wne, F)
-    acc = lanczos_pass2(A, b, alpha, beta, coef, acc)
+    acc = lanczos_pass2(A, b, alpha, beta, coef, acc, mixed)
     if stats is not None:
         stats["lz_steps"].append(k)
         stats["lz_maxres"].append(maxres)
@@ -296,10 +318,11 @@ def mslanczos_filter(A, Q, theta, Zne, Wne, target, kmax, stats=None):
 
 
 def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0.0, inner_maxiter=500, ritz_guess=True,
-                        verbose=False, col_slices=None, allreduce=None, adaptive=False):
+                        verbose=False, col_slices=None, allreduce=None, adaptive=False, mixed=False):
     """H-RR refinement loop (sparse/feast_sparse.jl:246-499 skeleton, B = I, real symmetric A, real Q0, filter rho = Re g)
     with the engine's multi-shift Lanczos inner solver.  col_slices(active) -> (c0, nc) emulates one rank of the
-    column-sharded multi-GPU run; allreduce sums the accumulator over ranks."""
+    column-sharded multi-GPU run; allreduce sums the accumulator over ranks.  mixed: FP32 Lanczos vectors (fpm[42]) until a
+    refined sweep gains less than a factor 4, then FP64 -- run_interval's rule."""
     import scipy.linalg as sla
     N = A.shape[0]
     fo.feastdefault(fpm)
@@ -317,7 +340,8 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
     have_ritz = False
     active = M0
     info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
-    stats = {"lz_steps": [], "lz_maxres": []}
+    stats = {"lz_steps": [], "lz_maxres": [], "fp32_sweeps": 0}
+    use_fp32, eps_before = bool(mixed) and not cplx, math.inf
     for loop_idx in range(maxloop + 1):
         loop_count = loop_idx
         first = not (ritz_guess and have_ritz)
@@ -332,7 +356,8 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
         acc = np.zeros((N, active), dtype=wdt)
         if nc > 0:
             acc[:, c0:c0 + nc] = mslanczos_filter(A, Qb[:, c0:c0 + nc], None if first else lam[c0:c0 + nc], Zne, Wne, target,
-                                                  inner_maxiter, stats)
+                                                  inner_maxiter, stats, use_fp32)
+            stats["fp32_sweeps"] += int(use_fp32)
         if allreduce is not None:
             acc = allreduce(acc)
         Qr, rank = fo.qr_compress(np.ascontiguousarray(acc), active)
@@ -357,6 +382,9 @@ def feast_hrr_mslanczos(A, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_rel0=0
         res[:M] = np.linalg.norm(R, axis=0) / np.maximum(np.abs(lam[:M]), 1.0)
         epsout = float(res[:M].max())
         M_found = M
+        if use_fp32 and have_ritz and math.isfinite(eps_before) and not epsout <= 0.25 * eps_before:
+            use_fp32 = False
+        eps_before = epsout
         if verbose:
             print(f"loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={stats['lz_steps'][-1] if stats['lz_steps'] else 0}", flush=True)
         if epsout <= eps_tol:

@@ -41,7 +41,8 @@ def test_struct_layouts_match_the_header(lib):
     assert C.sizeof(fc._lib.SolverOpts) == 88
     assert fc._lib.SolverOpts.eps_floor.offset == 80
     hdr = (ROOT / "include" / "feastcuda.h").read_text()
-    body = hdr[hdr.index("typedef struct {", hdr.index("feastcuda_solver_opts") - 2500):hdr.index("} feastcuda_solver_opts;")]
+    end = hdr.index("} feastcuda_solver_opts;")
+    body = hdr[hdr.rindex("typedef struct {", 0, end):end]
     fields = re.findall(r"^\s*(?:int32_t|double)\s+(\w+)", body, flags=re.M)
     assert fields == [f for f, _ in fc._lib.SolverOpts._fields_]
     sbody = hdr[hdr.index("typedef struct {", hdr.index("} feastcuda_solver_opts;")):hdr.index("} feastcuda_stats;")]

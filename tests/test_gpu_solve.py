@@ -242,6 +242,36 @@ def test_mslanczos_inexact_matches_cpu_port_loop_for_loop():
     assert ra.loop <= r.loop
 
 
+@pytest.mark.parametrize("N,M0,k_in", [(16, 24, 9), (20, 7, 3), (12, 61, 18)])
+def test_mixed_precision_lanczos_reaches_fp64_pairs(N, M0, k_in):
+    """fpm[42] = 1 ("single-precision solver", core/feast_parameters.jl:316-319; opts.mixed): FP32 Lanczos vectors inside the FP64
+    refinement loop.  Same M, eigenvalues, residuals and subspace as the oracle; step counts track the NumPy port of the mixed
+    recurrence (oracle/feast_port.py, mixed=True); column counts that are not multiples of 4 exercise the padded elements."""
+    import feastcuda as fc
+    import feast_port as fp
+    A = fo.laplacian_3d(N).astype(float).tocsc()
+    ev = fo.laplacian_3d_eigs(N)
+    gaps = [i for i in range(k_in, k_in + 30) if ev[i + 1] - ev[i] > 1e-3]
+    Emin, Emax = 0.0, 0.5 * (ev[gaps[0]] + ev[gaps[0] + 1])
+    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
+    ro = fo.feast_scsrev(A, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
+    r = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000, mixed=True)
+    _check_pairs(r, ro, A)
+    assert r.stats["lz_steps_fp32"] > 0 and r.stats["lz_steps_fp32"] <= r.stats["lz_steps_p1"]
+    rp = fp.feast_hrr_mslanczos(A.tocsr(), Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2000, adaptive=True, mixed=True)
+    steps_port = sum(rp.stats["lz_steps"])
+    assert rp.info == 0 and abs(r.loop - rp.loop) <= 1
+    assert abs(r.stats["lz_steps_p1"] - steps_port) <= max(16, 0.25 * steps_port)
+    # "fpm" mode follows fpm[42]: default 1 -> FP32 vectors, 0 -> FP64 only
+    fpm = fc.feastinit()
+    fpm[41] = 0
+    r0 = fc.feast_scsrev(A, Emin, Emax, M0, fpm, Q0=Q0, solver_maxiter=2000, mixed="fpm")
+    r1 = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000, mixed="fpm")
+    assert r0.stats["lz_steps_fp32"] == 0 and r1.stats["lz_steps_fp32"] > 0
+    _check_pairs(r0, ro, A)
+    _check_pairs(r1, ro, A)
+
+
 @pytest.mark.parametrize("M0", [1, 2, 7, 33, 64, 100, 128])
 def test_mslanczos_column_counts(M0):
     """Every lane mapping of the Lanczos SpMM (column pairs: 1..64 per row, odd counts, two chunks per lane)."""

@@ -190,6 +190,11 @@ def test_engine_ports_reach_the_reference_eigenpairs():
     # tight multi-shift solves reproduce the exact-solve loop count
     rt = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-10, inner_maxiter=3000)
     assert rt.loop == ro.loop
+    # fpm[42] "single-precision solver": FP32 Lanczos vectors inside the FP64 refinement loop reach the same pairs
+    rm = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=1000, adaptive=True, mixed=True)
+    assert rm.info == 0 and rm.M == ro.M and rm.stats["fp32_sweeps"] >= 2
+    assert np.abs(np.sort(rm.lambda_) - np.sort(ro.lambda_)).max() < 1e-10 and rm.res.max() < 1e-12
+    assert fo.subspace_angle(np.asarray(rm.q, dtype=complex), np.asarray(ro.q, dtype=complex)) < 1e-8
 
 
 def test_multishift_lanczos_filter_equals_direct_solves():

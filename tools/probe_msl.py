@@ -15,7 +15,7 @@ Z,W=fc.feast_contour(Emin,Emax,fpm)
 for rep in range(reps):
     eng.reset_stats()
     t=time.time()
-    r=eng.solve_interval(Emin,Emax,M0,list(fpm),Z,W,Q0=Q0,x_real=True,filter="true",solver="mslanczos",inner_rel=rel,inner_rel0=rel0,ritz_guess=True,solver_maxiter=kmax,check_every=16,adaptive=bool(int(os.environ.get("ADAPTIVE","1"))))
+    r=eng.solve_interval(Emin,Emax,M0,list(fpm),Z,W,Q0=Q0,x_real=True,filter="true",solver="mslanczos",inner_rel=rel,inner_rel0=rel0,ritz_guess=True,solver_maxiter=kmax,check_every=16,adaptive=bool(int(os.environ.get("ADAPTIVE","1"))),mixed=bool(int(os.environ.get("MIXED","0"))))
     dt=time.time()-t
     st=r.stats
     print("rep",rep,"time",dt,"info",r.info,"M",r.M,"loops",r.loop,"epsout",r.epsout, "env", {k:v for k,v in os.environ.items() if k.startswith("FEASTCUDA")})

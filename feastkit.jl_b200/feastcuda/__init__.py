@@ -35,6 +35,9 @@ class FeastResult:
     stats: dict = field(default_factory=dict)
 
 
+FeastGeneralResult = FeastResult     # core/feast_types.jl:100-118: same fields, complex lambda
+
+
 # ---- parameters / contours (core/feast_parameters.jl, core/feast_tools.jl) ---------------------------
 def feastinit():
     """feastinit() -> 64 x -111 (core/feast_parameters.jl:20-24)."""
@@ -479,5 +482,6 @@ def default_engine(device=None):
 
 
 from .api import *  # noqa: E402,F401,F403  (reference-named drivers)
+from .families import *  # noqa: E402,F401,F403  (complex-symmetric and polynomial names)
 from .rci import (FeastRCIState, Ref, dfeast_srci, feast_grci, feast_hrci, feast_srci, pdfeast_srci, zfeast_grci,  # noqa: E402,F401
                   zfeast_hrci)

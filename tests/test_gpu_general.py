@@ -104,3 +104,70 @@ def test_general_generalized_dense_random():
     for j in range(res.M):
         x = res.q[:, j]
         assert np.linalg.norm(A @ x - res.lambda_[j] * (B @ x)) / max(abs(res.lambda_[j]), 1.0) < 1e-10
+
+
+def test_complex_symmetric_families_dense_sparse_banded():
+    """runtests.jl:241-274 -- complex-symmetric 4x4 pencil (transpose-symmetric, not Hermitian), center 1+0.1i, radius 1.5:
+    feast_gegv_complex_sym!/feast_geev_complex_sym! find eigvals(A, B) inside the contour (atol 1e-7 in the reference), reject a
+    non-symmetric matrix; the sparse (feast_scsr*_complex!) and banded (feast_sb*_complex!) names reach the same values."""
+    import feastcuda as fc
+    A = np.array([[0.3 + 0.2j, 0.1 + 0.4j, 0, 0], [0.1 + 0.4j, 0.9 - 0.1j, 0.2j, 0], [0, 0.2j, 1.4 + 0.3j, 0.15 - 0.1j],
+                  [0, 0, 0.15 - 0.1j, 2.2 + 0.1j]], dtype=complex)
+    B = np.diag([1.0, 1.1, 1.2, 1.3]).astype(complex)
+    Emid, r = 1.0 + 0.1j, 1.5
+    fpm0 = fo.feastdefault(fo.feastinit())
+    inside = lambda w: [x for x in w if fo.feast_inside_gcontour(x, Emid, r, fpm0)]
+    want_g, want_s = inside(sla.eigvals(A, B)), inside(np.linalg.eigvals(A))
+    Q0 = fo.seeded_subspace(4, 4)
+    rg = fc.feast_gegv_complex_sym(A.copy(), B.copy(), Emid, r, 4, fc.feastinit(), Q0=Q0)
+    assert rg.info == 0 and rg.M == len(want_g)
+    _match(rg.lambda_, want_g, 1e-9)
+    rs = fc.feast_geev_complex_sym(A.copy(), Emid, r, 4, fc.feastinit(), Q0=Q0)
+    assert rs.info == 0 and rs.M == len(want_s)
+    _match(rs.lambda_, want_s, 1e-9)
+    for j in range(rs.M):
+        x = rs.q[:, j]
+        assert np.linalg.norm(A @ x - rs.lambda_[j] * x) < 1e-10 * max(1.0, abs(rs.lambda_[j]))
+    with pytest.raises(ValueError):
+        fc.feast_geev_complex_sym(np.array([[1, 2], [0, 3]], dtype=complex), Emid, r, 2, fc.feastinit())
+    rsp = fc.feast_scsrgv_complex(sp.csc_matrix(A), sp.csc_matrix(B), Emid, r, 4, fc.feastinit(), Q0=Q0)
+    assert rsp.info == 0
+    _match(rsp.lambda_, want_g, 1e-8)
+    rse = fc.feast_scsrev_complex(sp.csc_matrix(A), Emid, r, 4, fc.feastinit(), Q0=Q0)
+    _match(rse.lambda_, want_s, 1e-8)
+    with pytest.raises(ValueError):
+        fc.feast_scsrev_complex(sp.csc_matrix(np.array([[1, 2], [0, 3]], dtype=complex)), Emid, r, 2, fc.feastinit())
+    rb = fc.feast_sbgv_complex(fo.full_to_banded(A, 1), fo.full_to_banded(B, 0), 1, 0, Emid, r, 4, fc.feastinit(), Q0=Q0)
+    assert rb.info == 0
+    _match(rb.lambda_, want_g, 1e-9)
+    rbe = fc.feast_sbev_complex(fo.full_to_banded(A, 1), 1, Emid, r, 4, fc.feastinit(), Q0=Q0)
+    _match(rbe.lambda_, want_s, 1e-9)
+
+
+def test_polynomial_families_via_companion_linearisation():
+    """feast_pep!/feast_gepev!/feast_sypev!/feast_polynomial (dense/feast_dense.jl:715-772,946-978; interfaces:448-462): a damped
+    quadratic problem (lambda^2 M + lambda C + K) q = 0; eigenvalues inside the circle against LAPACK on the companion pencil,
+    and P(lambda) q = 0 for the returned leading-block vectors."""
+    import feastcuda as fc
+    rng = np.random.default_rng(5)
+    N = 6
+    K = np.diag(np.linspace(1.0, 6.0, N)) + 0.05 * rng.standard_normal((N, N))
+    K = 0.5 * (K + K.T)
+    Cd = 0.1 * np.eye(N)
+    M = np.eye(N)
+    Al, Bl = fc.companion_linearization([K, Cd, M])
+    w = sla.eigvals(Al, Bl)
+    Emid, r = 0.0 + 1.6j, 0.75
+    fpm0 = fo.feastdefault(fo.feastinit())
+    want = [x for x in w if fo.feast_inside_gcontour(x, Emid, r, fpm0)]
+    assert len(want) == 5                                   # M0 * d = 6 search columns
+    res = fc.feast_sypev([K, Cd, M], 2, Emid, r, 3, fc.feastinit())
+    assert res.info == 0 and res.M == len(want) and res.q.shape == (N, res.M)
+    _match(res.lambda_, want, 1e-8)
+    for j in range(res.M):
+        lam, x = res.lambda_[j], res.q[:, j]
+        assert np.linalg.norm((K + lam * Cd + lam * lam * M) @ x) < 1e-8 * np.linalg.norm(x)
+    rp = fc.feast_polynomial([K.astype(complex), Cd.astype(complex), M.astype(complex)], Emid, r, M0=3, fpm=fc.feastinit())
+    _match(rp.lambda_, want, 1e-8)
+    with pytest.raises(ValueError):
+        fc.feast_pep([K, Cd], 2, Emid, r, 3, fc.feastinit())

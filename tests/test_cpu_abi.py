@@ -190,3 +190,30 @@ def test_rci_init_handshake(lib):
     with pytest.raises(ValueError):
         fc.feast_srci(fc.Ref(99), N, fc.Ref(0j), b["work"], b["workc"], b["Aq"], b["Sq"], fc.feastinit(), fc.Ref(0.0), fc.Ref(0), 0.0, 1.0,
                       M0, b["lam"], b["q"], fc.Ref(0), b["res"], fc.Ref(0), state=fc.FeastRCIState())
+
+
+def test_complex_symmetric_and_polynomial_host_helpers():
+    """Host-side parts of the complex-symmetric / polynomial families (no GPU): symmetry checks raise before any device call
+    (runtests.jl:270-273), the symmetric band expands to the general band without conjugation, the companion pencil
+    (dense/feast_dense.jl:727-760) has the polynomial's eigenpairs."""
+    import scipy.linalg as sla
+    import feastcuda as fc
+    from feastcuda.families import _symmetric_band_to_general
+    with pytest.raises(ValueError, match="complex-symmetric"):
+        fc.feast_geev_complex_sym(np.array([[1, 2], [0, 3]], dtype=complex), 1.0 + 0.1j, 1.5, 2, fc.feastinit())
+    with pytest.raises(ValueError, match="d\\+1 coefficient"):
+        fc.feast_pep([np.eye(2), np.eye(2)], 2, 0j, 1.0, 2, fc.feastinit())
+    rng = np.random.default_rng(0)
+    n, k = 9, 2
+    A = np.zeros((n, n), dtype=complex)
+    for d in range(k + 1):
+        v = rng.standard_normal(n - d) + 1j * rng.standard_normal(n - d)
+        A += np.diag(v, d) + (np.diag(v, -d) if d else 0)
+    assert np.array_equal(fo.general_banded_to_full(_symmetric_band_to_general(fo.full_to_banded(A, k), k), k), A)
+    N = 4
+    K, Cm, M = rng.standard_normal((N, N)), rng.standard_normal((N, N)), np.eye(N) + 0.1 * rng.standard_normal((N, N))
+    Al, Bl = fc.companion_linearization([K, Cm, M])
+    w, V = sla.eig(Al, Bl)
+    for i, lam in enumerate(w):
+        assert np.linalg.norm((K + lam * Cm + lam * lam * M) @ V[:N, i]) < 1e-10 * np.linalg.norm(V[:N, i]) * max(1, abs(lam)) ** 2
+        assert np.allclose(V[N:, i], lam * V[:N, i], atol=1e-10 * max(1, abs(lam)))

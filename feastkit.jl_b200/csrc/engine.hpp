@@ -80,7 +80,7 @@ struct HostBand {   // full general band (2k+1) x n, diagonal row k, values expa
   bool cplx = false, set = false;
 };
 
-enum OperatorKind { OP_NONE = 0, OP_SPARSE = 1, OP_DENSE = 2, OP_BAND = 3 };
+enum OperatorKind { OP_NONE = 0, OP_SPARSE = 1, OP_DENSE = 2, OP_BAND = 3, OP_MATFREE = 4 };
 
 // block-vector slots (each n x ld complex, row-major)
 enum BlockSlot { BS_QB = 0, BS_RHS, BS_ACC, BS_XR, BS_KX, BS_KR, BS_KRH, BS_KP, BS_KV, BS_KS, BS_KT, BS_KB, BS_COUNT };
@@ -98,6 +98,8 @@ struct feastcuda_handle_s {
   int sms = 148;
   cudaStream_t stream = nullptr;
   int kind = feastcuda::OP_NONE;
+  feastcuda_apply_fn mf_apply = nullptr;   // OP_MATFREE: the caller's device mat-vec (real symmetric A, B = I)
+  void* mf_ctx = nullptr;
   bool dev_complex = false;  // value type of the uploaded operators
   feastcuda::HostCsr hA, hB;
   feastcuda::DevCsr dA, dB;

@@ -13,6 +13,7 @@
 #include "kernels_sparse.cuh"
 #include "kernels_lanczos.cuh"
 #include "kernels_lanczos_f32.cuh"
+#include "kernels_matfree.cuh"
 #include "dense_band.cuh"
 
 using namespace feastcuda;
@@ -625,13 +626,15 @@ static double lz_bytes_spmm(H* h, int m, int nvec, bool cplx) {
 template <bool CPLX>
 static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, const double* theta, const zc* Zne, const zc* Wne,
                        int ne, double target, int kmax, int check_every, MslOut& out, bool mixed = false) {
-  FC_REQUIRE(h->kind == OP_SPARSE && h->dev_complex == CPLX && !h->has_b, "multi-shift Lanczos needs a standard sparse Hermitian problem");
+  const bool matfree = h->kind == OP_MATFREE;
+  FC_REQUIRE(((h->kind == OP_SPARSE && h->dev_complex == CPLX) || (matfree && !CPLX)) && !h->has_b,
+             "multi-shift Lanczos needs a standard sparse Hermitian (or matrix-free real symmetric) problem");
   FC_REQUIRE(CPLX || (c0 & 1) == 0, "column slices must start at an even column");
   const int64_t n = h->ws_n;
   // the work blocks are COMPACT: row stride = the slice's own column count (in doubles: even(nc) real, 2 nc complex), so a
   // rank that owns 8 of 64 columns streams dense 64-byte rows instead of touching 64 bytes out of every 512
   // mixed precision (FP32 Lanczos vectors, real problems): 4-column elements, so every compact block is padded to a multiple of 4
-  mixed = mixed && !CPLX && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
+  mixed = mixed && !CPLX && !matfree && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
   const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : (mixed ? ((nc + 3) & ~3) : ((nc + 1) & ~1));
   FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   kmax = std::max(1, std::min(kmax, 16384));
@@ -672,6 +675,13 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   double* UA = rblk(h, BS_KRH);
   double* UB = rblk(h, BS_KP);
   double* QA = rblk(h, BS_KV);
+  double* MW = rblk(h, BS_KT);   // matrix-free: W = A U from the caller's callback
+  auto mf_apply = [&](const double* X, double* Y) {
+    h->mf_apply(h->mf_ctx, n, (int64_t)nc, X, ld, Y, ld, (void*)h->stream);
+    h->stats.kernel_launches++;
+    h->stats.spmm_launches++;
+  };
+  if (matfree) FC_CUDA(cudaMemsetAsync(MW, 0, (size_t)n * (size_t)ld * sizeof(double), h->stream));   // pad column of an odd slice
   const zd* basis = blk(h, basis_slot) + c0;
   double* part = h->partial_r.as<double>();
 
@@ -702,9 +712,15 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
     int g = 0;
     const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
-    lz_launch<LZ_RES, CPLX>(h, a, &g);
+    if (matfree) {
+      mf_apply(RQ, MW);
+      k_mf_step<LZ_RES><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, MW, RQ, nullptr, RB, QA, d_theta, nullptr, nullptr, d_rho, part, FC_MAXCOLS,
+                                                      nullptr);
+      check_launch(h);
+      g = egrid;
+    } else lz_launch<LZ_RES, CPLX>(h, a, &g);
     sample_end(h, ev);
-    h->stats.bytes_kern[FEASTCUDA_KERN_LZ_RES] = lz_bytes_spmm(h, nc, 3, CPLX);
+    h->stats.bytes_kern[FEASTCUDA_KERN_LZ_RES] = matfree ? 4.0 * 8.0 * (double)n * nc : lz_bytes_spmm(h, nc, 3, CPLX);
     k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g, FC_MAXCOLS, nc);
     check_launch(h);
     sync(h);  // theta / rho are host buffers
@@ -746,7 +762,14 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       const bool smp = (j % 16) == 3;
       int g = 0;
       int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
-      if (mixed) {
+      if (matfree) {
+        mf_apply(cur(j), MW);
+        k_mf_step<LZ_P1><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, MW, cur(j), j > 0 ? cur(j - 1) : cur(j), cur(j + 1), nullptr,
+                                                       S.inv_beta + (size_t)j * rowsz, S.ratio_b + (size_t)j * rowsz, nullptr, nullptr, part,
+                                                       FC_MAXCOLS, S.done_k);
+        check_launch(h);
+        g = egrid;
+      } else if (mixed) {
         LzArgs32 a = args32(j);
         a.partial = part; a.pstride = FC_MAXCOLS; a.done = S.done_k;
         lz32_launch<LZ_P1>(h, a, &g);
@@ -781,7 +804,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     if (flag[0] != 0) { kfinal = flag[0]; out.converged = true; break; }
   }
   if (kfinal == 0) kfinal = done;
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = mixed ? lz32_bytes_spmm(h, nc, 3, 0) : lz_bytes_spmm(h, nc, 3, CPLX);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = matfree ? 4.0 * 8.0 * (double)n * nc : (mixed ? lz32_bytes_spmm(h, nc, 3, 0) : lz_bytes_spmm(h, nc, 3, CPLX));
   h->stats.bytes_kern[FEASTCUDA_KERN_LZ_UPD] = 3.0 * (double)n * nc * (mixed ? 4.0 : (CPLX ? 16.0 : 8.0));
   drain_events(h, kfinal);
   h->stats.lz_steps_p1 += kfinal;
@@ -845,7 +868,13 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     const bool smp = (j % 16) == 3;
     int g = 0;
     const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
-    if (mixed) {
+    if (matfree) {
+      mf_apply(cur(j), MW);
+      k_mf_step<LZ_P2><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, MW, cur(j), j > 0 ? cur(j - 1) : cur(j), cur(j + 1), QA,
+                                                     S.inv_beta + (size_t)j * rowsz, S.ratio_b + (size_t)j * rowsz,
+                                                     S.ratio_a + (size_t)j * rowsz, d_coef + (size_t)j * rowsz, nullptr, 0, nullptr);
+      check_launch(h);
+    } else if (mixed) {
       LzArgs32 a = args32(j);
       a.Q = QA; a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
       lz32_launch<LZ_P2>(h, a, &g);
@@ -865,7 +894,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   k_lz_to_complex<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
   check_launch(h);
   sync(h);  // coef is a host buffer
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = mixed ? lz32_bytes_spmm(h, nc, 3, 2) : lz_bytes_spmm(h, nc, 5, CPLX);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = matfree ? 6.0 * 8.0 * (double)n * nc : (mixed ? lz32_bytes_spmm(h, nc, 3, 2) : lz_bytes_spmm(h, nc, 5, CPLX));
   drain_events(h);
   h->stats.lz_steps_p2 += k;
   h->stats.ms_lz_p2 += t2.ms();
@@ -1049,6 +1078,8 @@ static bool node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X, bool u
   }
   if (h->kind == OP_DENSE) return dense_node_solve(h, node, z, m, RHS, X);
   if (h->kind == OP_BAND) return band_node_solve(h, node, z, m, RHS, X);
+  if (h->kind == OP_MATFREE)
+    throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "matrix-free operators are served by the multi-shift Lanczos filter only (real basis, true filter)");
   throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
 }
 
@@ -1058,7 +1089,13 @@ static void apply_op(H* h, int which, int m, const zd* X, zd* Y) {
     else launch_spmm<SPMM_PLAIN>(h, op_B(), m, X, Y, nullptr, nullptr);
   } else if (h->kind == OP_DENSE) dense_apply(h, which, m, X, Y);
   else if (h->kind == OP_BAND) band_apply(h, which, m, X, Y);
-  else throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
+  else if (h->kind == OP_MATFREE) {
+    // real operator on a complex block: the interleaved (re, im) columns are 2m real columns of a row-major block
+    if (which != FEASTCUDA_A) throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "matrix-free problems are standard (B = I)");
+    h->mf_apply(h->mf_ctx, h->n, 2 * (int64_t)m, reinterpret_cast<const double*>(X), 2 * h->ws_ld, reinterpret_cast<double*>(Y), 2 * h->ws_ld,
+                (void*)h->stream);
+    h->stats.kernel_launches++;
+  } else throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
 }
 
 // res_j = ||A x_j - lam_j B x_j||_2 (not yet divided by max(|lam|,1))
@@ -1126,6 +1163,7 @@ static bool pencil_is_real(H* h) {
   if (h->kind == OP_SPARSE) return !h->dev_complex;
   if (h->kind == OP_DENSE) return !h->denseA.cplx && !(h->has_b && h->denseB.cplx);
   if (h->kind == OP_BAND) return !h->bandA.cplx && !(h->has_b && h->bandB.cplx);
+  if (h->kind == OP_MATFREE) return true;
   return false;
 }
 
@@ -1133,6 +1171,7 @@ static void prepare_operator(H* h) {
   if (h->kind == OP_SPARSE) finalize_sparse(h);
   else if (h->kind == OP_DENSE) dense_prepare(h);
   else if (h->kind == OP_BAND) band_prepare(h);
+  else if (h->kind == OP_MATFREE) FC_REQUIRE(h->mf_apply != nullptr && !h->has_b, "matrix-free operator: callback missing or B set");
   else throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
 }
 
@@ -1154,7 +1193,8 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
   const double eps_tol = std::max(host_feast_tolerance(fpm), o.eps_floor > 0 ? o.eps_floor : 0.0);
   const int maxloop = (int)fpm[3];
   const bool real_mode = (o.filter == FEASTCUDA_FILTER_TRUE) && pencil_is_real(h) && subspace_is_real;
-  const bool iterative = (h->kind == OP_SPARSE);
+  const bool matfree = (h->kind == OP_MATFREE);
+  const bool iterative = (h->kind == OP_SPARSE) || matfree;
   int shard = o.shard;
   if (!iterative) shard = FEASTCUDA_SHARD_NODES;
 
@@ -1182,8 +1222,10 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     zero_cols(h, active, blk(h, BS_ACC));
     // multi-shift Lanczos: standard Hermitian problems with the true filter rho = Re g -- real symmetric with a real basis (real
     // arithmetic) or complex Hermitian (complex vectors, real tridiagonal: the coefficients of rho are real either way)
-    const bool cplx_msl = iterative && h->dev_complex && !h->has_b && o.filter == FEASTCUDA_FILTER_TRUE && h->hA.structure != FEASTCUDA_GEN;
-    const bool use_msl = iterative && o.solver == FEASTCUDA_SOLVER_MSLANCZOS && !h->has_b && (real_mode || cplx_msl);
+    const bool cplx_msl = iterative && !matfree && h->dev_complex && !h->has_b && o.filter == FEASTCUDA_FILTER_TRUE && h->hA.structure != FEASTCUDA_GEN;
+    const bool use_msl = iterative && (o.solver == FEASTCUDA_SOLVER_MSLANCZOS || matfree) && !h->has_b && (real_mode || cplx_msl);
+    if (matfree && !use_msl)
+      throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "matrix-free operators need a real initial subspace and filter = TRUE (multi-shift Lanczos)");
     std::vector<WorkItem> items;
     if (!use_msl) items = build_items(ne, active, h->nranks, h->rank, shard, cost);
     std::vector<double> node_cost(ne, 0.0), node_cols(ne, 0.0);
@@ -1670,6 +1712,23 @@ int feastcuda_clear_b(feastcuda_handle h) {
   h->band_uploaded = false;
   release_factor_cache(h);
   return FEASTCUDA_OK;
+}
+
+int feastcuda_set_matfree_d(feastcuda_handle h, int64_t n, feastcuda_apply_fn apply_a, void* ctx) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  FC_REQUIRE(n >= 1 && apply_a != nullptr, "matrix-free operator: n >= 1 and a callback are required");
+  bind_device(h);
+  release_factor_cache(h);
+  h->kind = OP_MATFREE;
+  h->mf_apply = apply_a;
+  h->mf_ctx = ctx;
+  h->n = n;
+  h->has_b = false;
+  h->hA.set = false;
+  h->hB.set = false;
+  h->dev_complex = false;
+  FC_CATCH
 }
 
 int feastcuda_set_dense_d(feastcuda_handle h, int which, int64_t n, const double* a, int64_t lda, int structure) {

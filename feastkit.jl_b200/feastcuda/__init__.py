@@ -38,6 +38,19 @@ class FeastResult:
 FeastGeneralResult = FeastResult     # core/feast_types.jl:100-118: same fields, complex lambda
 
 
+class _DevBlock:
+    """A row-major (rows, cols) float64 block at a raw device address, exposed through __cuda_array_interface__."""
+
+    def __init__(self, ptr, rows, cols, ld):
+        self.__cuda_array_interface__ = {"shape": (int(rows), int(cols)), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": (int(ld) * 8, 8)}
+
+
+def _device_view(ptr, rows, cols, ld, dev):
+    import torch
+    return torch.as_tensor(_DevBlock(ptr, rows, cols, ld), device=dev)
+
+
 # ---- parameters / contours (core/feast_parameters.jl, core/feast_tools.jl) ---------------------------
 def feastinit():
     """feastinit() -> 64 x -111 (core/feast_parameters.jl:20-24)."""
@@ -176,6 +189,10 @@ class Engine:
             pass
 
     def _ck(self, rc):
+        err = getattr(self, "_matfree_error", None)
+        if err is not None:            # an exception inside a Python matrix-free callback cannot cross the C frames: re-raise it here
+            self._matfree_error = None
+            raise err
         L.check(rc, self.h)
 
     # -- operators
@@ -229,6 +246,37 @@ class Engine:
 
     def clear_b(self):
         self._ck(self.lib.feastcuda_clear_b(self.h))
+
+    def set_matfree(self, n, apply, ctx=None):
+        """Matrix-free real symmetric A (B = I): `apply` is either a C function pointer of type feastcuda_apply_fn (an int
+        address or a ctypes function, with `ctx` passed through as its void* context -- e.g. the example operator in
+        examples/matfree_laplacian.cu) or a Python callable apply(Y, X) that receives the device blocks as torch CUDA tensor
+        views of shape (n, ncols) and must fill Y = A @ X with torch operations (they are enqueued on the library's stream)."""
+        if callable(apply) and not isinstance(apply, C._CFuncPtr):
+            user = apply
+
+            def trampoline(_ctx, nn, ncols, xp, ldx, yp, ldy, stream):
+                import torch
+                dev = torch.device("cuda", self.device)
+                if getattr(self, "_matfree_error", None) is not None:
+                    return
+                try:
+                    with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=dev)):
+                        X = _device_view(xp, nn, ncols, ldx, dev)
+                        Y = _device_view(yp, nn, ncols, ldy, dev)
+                        user(Y, X)
+                except BaseException as exc:   # noqa: BLE001
+                    self._matfree_error = exc
+
+            fn = L.APPLY_FN(trampoline)
+            self._matfree_keep = (fn, user)
+            addr, cx = C.cast(fn, C.c_void_p), None
+        else:
+            self._matfree_keep = (apply, ctx)
+            addr = C.cast(apply, C.c_void_p) if isinstance(apply, C._CFuncPtr) else C.c_void_p(int(apply))
+            cx = ctx if (ctx is None or isinstance(ctx, (int, C.c_void_p))) else C.cast(C.pointer(ctx), C.c_void_p)
+        self._ck(self.lib.feastcuda_set_matfree_d(self.h, int(n), addr, cx))
+        self.n = int(n)
 
     # -- multi-GPU: one process per GPU, NCCL id distributed through torch.distributed
     def init_distributed(self):

@@ -48,6 +48,10 @@ class Stats(C.Structure):
         return d
 
 
+# feastcuda_apply_fn: void (*)(void* ctx, int64 n, int64 ncols, const double* X, int64 ldx, double* Y, int64 ldy, void* stream)
+APPLY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p)
+
+
 class FeastCudaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libfeastcuda status {code}: {msg}")
@@ -73,6 +77,7 @@ SIGNATURES = {
     "feastcuda_set_csr_d": [_vp, C.c_int, C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int],
     "feastcuda_set_csr_z": [_vp, C.c_int, C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int],
     "feastcuda_clear_b": [_vp],
+    "feastcuda_set_matfree_d": [_vp, C.c_int64, C.c_void_p, C.c_void_p],
     "feastcuda_set_dense_d": [_vp, C.c_int, C.c_int64, _dp, C.c_int64, C.c_int],
     "feastcuda_set_dense_z": [_vp, C.c_int, C.c_int64, _dp, C.c_int64, C.c_int],
     "feastcuda_set_band_d": [_vp, C.c_int, C.c_int64, C.c_int64, _dp, C.c_int64, C.c_int],

@@ -15,7 +15,7 @@ __all__ = [
     "feast_scsrev", "feast_scsrgv", "feast_hcsrev", "feast_hcsrgv", "feast_scsrevx", "feast_scsrgvx", "feast_hcsrevx",
     "feast_hcsrgvx", "feast_syev", "feast_sygv", "feast_heev", "feast_hegv", "feast_syevx", "feast_sygvx", "feast_heevx",
     "feast_hegvx", "feast_sbev", "feast_sbgv", "feast_hbev", "feast_hbgv", "feast", "feast_banded", "issymmetric",
-    "ishermitian", "feast_general", "feast_gcsrev", "feast_gcsrgv", "feast_geev", "feast_gegv", "feast_gbev", "feast_gbgv",
+    "ishermitian", "feast_matvec", "feast_sparse_matvec", "feast_general", "feast_gcsrev", "feast_gcsrgv", "feast_geev", "feast_gegv", "feast_gbev", "feast_gbgv",
 ]
 
 
@@ -395,6 +395,44 @@ def feast_banded(A, kla, interval, B=None, klb=0, M0=10, fpm=None, **kw):
     if np.iscomplexobj(A):
         return feast_hbev(A, kla, Emin, Emax, M0, fpm, **kw) if B is None else feast_hbgv(A, np.array(B), kla, klb, Emin, Emax, M0, fpm, **kw)
     return feast_sbev(A, kla, Emin, Emax, M0, fpm, **kw) if B is None else feast_sbgv(A, np.array(B), kla, klb, Emin, Emax, M0, fpm, **kw)
+
+
+# ---- matrix-free (interfaces/feast_interfaces.jl:465-481, sparse/feast_sparse.jl:1284-1471) -------------------------------
+def _is_identity_operator(B_mul, N, engine):
+    """The reference's feast_matvec always takes a B_mul!; the engine's matrix-free path is the standard problem, so a B
+    operator is accepted iff it acts as the identity on a random device block."""
+    import torch
+    dev = torch.device("cuda", _eng(engine).device)
+    X = torch.randn(N, 2, dtype=torch.float64, device=dev)
+    Y = torch.zeros_like(X)
+    B_mul(Y, X)
+    return bool(torch.equal(Y, X))
+
+
+def feast_sparse_matvec(A_matvec, B_matvec, N, Emin, Emax, M0, fpm, **kw):
+    """feast_sparse_matvec!(A_matvec!, B_matvec!, N, Emin, Emax, M0, fpm) -- sparse/feast_sparse.jl:1284-1471.
+
+    A_matvec is the DEVICE operator: a Python callable A_matvec(Y, X) on torch CUDA tensor views (n x ncols blocks; fill
+    Y = A @ X), or a (function pointer, ctx) pair for a compiled feastcuda_apply_fn.  The reference runs one GMRES per (node,
+    column) around host closures; here one multi-shift Lanczos recurrence per column calls the operator once per step for all
+    columns.  B_matvec: None, or an operator that acts as the identity (anything else: NotImplementedError)."""
+    if N <= 0:
+        raise ValueError("Matrix size N must be positive")
+    if B_matvec is not None and not _is_identity_operator(B_matvec, int(N), kw.get("engine")):
+        raise NotImplementedError("matrix-free generalized problems (B != I) are not supported by the multi-shift Lanczos filter")
+    if isinstance(A_matvec, tuple):
+        setA = lambda e: e.set_matfree(int(N), A_matvec[0], A_matvec[1])
+    else:
+        setA = lambda e: e.set_matfree(int(N), A_matvec)
+    return _hermitian_solve("sparse", setA, None, int(N), Emin, Emax, M0, fpm, True, **kw)
+
+
+def feast_matvec(A_mul, B_mul, N, interval, M0=10, fpm=None, **kw):
+    """feast_matvec(A_mul!, B_mul!, N, interval; M0, fpm) -- interfaces/feast_interfaces.jl:465-481."""
+    from . import feastinit
+    Emin, Emax = interval
+    fpm = feastinit() if fpm is None else fpm
+    return feast_sparse_matvec(A_mul, B_mul, N, Emin, Emax, M0, fpm, **kw)
 
 
 # ---- precision / parallel alias families (interfaces/feast_precision_aliases.jl:10-971) ------------------

@@ -237,6 +237,17 @@ for (alias, target) in ((:sfeast_scsrev!, :feast_scsrev!), (:sfeast_scsrgv!, :fe
     @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, kw...))
 end
 
+# ---- matrix-free: feast_matvec(A_mul!, B_mul!, N, interval) interfaces/feast_interfaces.jl:465-481 -> feast_sparse_matvec!
+# sparse/feast_sparse.jl:1284-1471.  The operator is a DEVICE callback of C type feastcuda_apply_fn
+#   (ctx::Ptr{Cvoid}, n::Int64, ncols::Int64, X::Ptr{Float64}, ldx::Int64, Y::Ptr{Float64}, ldy::Int64, stream::Ptr{Cvoid}) -> Cvoid
+# that enqueues Y = A*X for row-major device blocks on `stream`: either a symbol of the user's own CUDA library
+# (`cglobal((:my_apply, "libmyops.so"))`) or an `@cfunction` whose body launches the user's kernels.  B must be the identity.
+function feast_matvec(apply::Ptr{Cvoid}, ctx::Ptr{Cvoid}, N::Int, interval::Tuple{<:Real,<:Real}; M0::Int=10, fpm=nothing, kw...)
+    fpm = fpm === nothing ? feastinit() : fpm
+    setA! = h -> check(ccall((:feastcuda_set_matfree_d, libfeastcuda), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}), h, N, apply, ctx), h)
+    return _solve_interval(setA!, nothing, N, Float64(interval[1]), Float64(interval[2]), M0, fpm, Float64; sparse=true, kw...)
+end
+
 # ---- general (non-Hermitian) family: feast_gcsrgv!/gcsrev! sparse/feast_sparse.jl:873-1006,1531-1545;
 # feast_gegv!/geev! dense/feast_dense.jl:402-593,812-823; feast_gbgv!/gbev! banded/feast_banded.jl:1548-1600 ----------------
 struct FeastGeneralResult{T<:Real}            # core/feast_types.jl:100-118
@@ -354,6 +365,6 @@ end
 export feastinit, feastinit!, feastdefault!, feast_contour, feast_gcontour, feast, FeastResult,
        feast_scsrev!, feast_scsrgv!, feast_hcsrev!, feast_hcsrgv!, feast_syev!, feast_sygv!, feast_heev!, feast_hegv!,
        feast_sbev!, feast_sbgv!, feast_hbev!, feast_hbgv!,
-       FeastGeneralResult, feast_general, feast_gcsrev!, feast_gcsrgv!, feast_geev!, feast_gegv!
+       feast_matvec, FeastGeneralResult, feast_general, feast_gcsrev!, feast_gcsrgv!, feast_geev!, feast_gegv!
 
 end # module

@@ -124,6 +124,15 @@ int feastcuda_set_csr_d(feastcuda_handle h, int which, int64_t n, int64_t nnz, c
 int feastcuda_set_csr_z(feastcuda_handle h, int which, int64_t n, int64_t nnz, const int64_t* ptr,
                         const int64_t* idx, const double* val /* 2*nnz */, int index_base, int fmt, int structure);
 int feastcuda_clear_b(feastcuda_handle h);
+/* Matrix-free REAL SYMMETRIC standard problems: feast_matvec(A_mul!, B_mul!, N, interval) interfaces/feast_interfaces.jl:465-481
+ * -> feast_sparse_matvec! sparse/feast_sparse.jl:1284-1471 (there: host closures + per-column GMRES).  Here the operator is a DEVICE
+ * callback: `apply(ctx, n, ncols, X, ldx, Y, ldy, stream)` must enqueue on `stream` (a cudaStream_t) work that writes
+ * Y[i*ldy + c] = sum_j A[i,j] X[j*ldx + c] for 0 <= c < ncols (row-major blocks of doubles in device memory; X and Y never
+ * alias; the same input must give the same bits on every call: pass 2 of the Lanczos filter replays pass 1).  The solve uses the
+ * multi-shift Lanczos filter (B = I only); every other operator/solver combination returns FEASTCUDA_ERR_UNSUPPORTED. */
+typedef void (*feastcuda_apply_fn)(void* ctx, int64_t n, int64_t ncols, const double* X, int64_t ldx, double* Y, int64_t ldy, void* stream);
+int feastcuda_set_matfree_d(feastcuda_handle h, int64_t n, feastcuda_apply_fn apply_a, void* ctx);
+
 /* Dense column-major n x n, lda >= n (feast_syev!/sygv!/heev!/hegv!/geev!/gegv! dense/feast_dense.jl) */
 int feastcuda_set_dense_d(feastcuda_handle h, int which, int64_t n, const double* a, int64_t lda, int structure);
 int feastcuda_set_dense_z(feastcuda_handle h, int which, int64_t n, const double* a, int64_t lda, int structure);

@@ -596,6 +596,9 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
 template <int MODE>
 static void lz32_launch(H* h, LzArgs32& a, int* grid_out) {
   const int P = (a.m + 3) / 4;   // 4-column elements per row = lanes per row
+  // shape: 2 CTAs x 512 threads, 4 gathers in flight per lane (64 registers).  Measured on B200 and rejected (n = 1e6, 64 columns,
+  // pass 1 / pass 2): 3 x 256 threads with 8 gathers in flight (80 registers) 0.264 / 0.354 ms and 2 x 384 / 8: 0.270 / 0.356 ms
+  // against 0.242 / 0.344 ms -- resident warps matter more than loads in flight per warp.
 #define FC_LZ32(G)                                                                 \
   do {                                                                             \
     const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G));                          \

@@ -77,14 +77,11 @@ __device__ __forceinline__ void lz32_dot(double (&d)[4], float4 x, float4 y) {
   d[3] = fma((double)x.w, (double)y.w, d[3]);
 }
 
-#ifndef LZ32_UN
-#define LZ32_UN 4
-#endif
 // acc += sum_p val[p] * U[col[p], element]  over the stored entries [p0, p1) of the row, CSR order (see lz_gather)
-template <int G>
+template <int G, int UNMAX>
 __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, int p0, int p1, unsigned myo, float mya, unsigned myo2,
                                             float mya2, int g, unsigned gmask, const float* Ul, float4& acc) {
-  constexpr int UN = (G >= LZ32_UN) ? LZ32_UN : G;
+  constexpr int UN = (G >= UNMAX) ? UNMAX : G;   // gathers in flight per lane
   constexpr bool PF2 = (G <= 4);
   const unsigned ldu = (unsigned)a.ld;
   for (int pb = p0; pb < p1; pb += G) {
@@ -120,8 +117,9 @@ __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, 
 }
 
 // MODE: LZ_P1 (out = (A u) inv_beta - ratio_b prev; partial = u . out) or LZ_P2 (out = t - ratio_a u; Q += coef u)
-template <int G, int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz32_spmm(LzArgs32 a) {
+// (THREADS, MINB, UNMAX): 512 x 2 CTAs/SM x 4 gathers in flight (64 registers) or fewer resident warps with more loads in flight each
+template <int G, int MODE, int THREADS, int MINB = 1024 / THREADS, int UNMAX = 4>
+__global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
   static_assert(MODE == LZ_P1 || MODE == LZ_P2, "FP32 vectors exist only inside the two Lanczos passes");
   if (a.done != nullptr && *a.done != 0) return;
   constexpr int RPW = 32 / G;
@@ -194,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz32_spmm(LzArgs32 
       q1 = ldg2(Ql + eo_own + 2);
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    lz32_gather<G>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
+    lz32_gather<G, UNMAX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
     if (valid && g < P) {
       const float4 t = lz32_t(acc, s_sc[0][g], s_sc[1][g], pv);
       if constexpr (MODE == LZ_P1) {

@@ -473,6 +473,8 @@ def _alias32(fn):
                 for x in a]
         if kw.get("Q0") is not None:
             kw["Q0"] = np.asarray(kw["Q0"]).astype(np.complex128 if np.iscomplexobj(kw["Q0"]) else np.float64)
+        if fn in (feast_scsrev, feast_scsrevx):
+            kw.setdefault("mixed", True)      # single-precision names: FP32 Krylov vectors (the outer loop stays FP64)
         r = fn(*args, eps_floor=_EPS32, **kw)
         cq = np.complex64 if np.iscomplexobj(r.q) else np.float32
         cl = np.complex64 if np.iscomplexobj(r.lambda_) else np.float32

@@ -132,7 +132,7 @@ end
 # (sparse/feast_sparse.jl:246-499) and _feast_banded_complex_hermitian (banded/feast_banded.jl:561-823)
 function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{Int}, ::Type{VT};
                          Zne=nothing, Wne=nothing, solver::Symbol=:direct, solver_tol::Real=0.0, solver_maxiter::Int=500,
-                         solver_restart::Int=30, sparse::Bool=false, eps_floor::Float64=0.0) where {VT}
+                         solver_restart::Int=30, sparse::Bool=false, eps_floor::Float64=0.0, mixed::Int=0) where {VT}
     feastdefault!(fpm)
     # check_feast_srci_input (core/feast_aux.jl:369-399): thrown before any device call, exactly as the reference does
     N > 0 || throw(ArgumentError("Matrix size N must be positive"))
@@ -151,7 +151,8 @@ function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{
     eng_solver = sparse ? (solver_choice == :bicgstab ? SOLVER_BICGSTAB : SOLVER_MSLANCZOS) :
                           (solver_choice == :direct ? SOLVER_DIRECT : SOLVER_BICGSTAB)
     opts = Ref(SolverOpts(eng_solver, solver_tol, solver_maxiter, solver_restart == 30 ? 3 : solver_restart,
-                          sparse ? 1e-3 : 0.0, sparse ? 1 : 0, FILTER_TRUE, 0, 16, 0, real_result ? 1 : 0, 0.0, 0, 0, sparse ? 1 : 0, Cint(0), eps_floor))
+                          sparse ? 1e-3 : 0.0, sparse ? 1 : 0, FILTER_TRUE, 0, 16, 0, real_result ? 1 : 0, 0.0, 0, 0, sparse ? 1 : 0,
+                          Cint(mixed) #= 1: FP32 Lanczos vectors, 2: follow fpm[42] =#, eps_floor))
     lambda = zeros(Float64, M0); res = zeros(Float64, M0); X = zeros(VT, N, M0)
     M = Ref{Int64}(0); info = Ref{Int64}(0); loop = Ref{Int64}(0); epsout = Ref{Float64}(0.0)
     GC.@preserve fpm Zne Wne lambda res X begin
@@ -233,8 +234,9 @@ for (alias, target) in ((:sfeast_scsrev!, :feast_scsrev!), (:sfeast_scsrgv!, :fe
                         (:cfeast_hcsrgv!, :feast_hcsrgv!), (:sfeast_syev!, :feast_syev!), (:sfeast_sygv!, :feast_sygv!),
                         (:cfeast_heev!, :feast_heev!), (:cfeast_hegv!, :feast_hegv!), (:sfeast_sbev!, :feast_sbev!),
                         (:sfeast_sbgv!, :feast_sbgv!), (:cfeast_hbev!, :feast_hbev!), (:cfeast_hbgv!, :feast_hbgv!))
-    @eval $alias(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, kw...))
-    @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, kw...))
+    mx = target === :feast_scsrev! ? 1 : 0       # single-precision sparse names: FP32 Krylov vectors inside the FP64 refinement loop
+    @eval $alias(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, mixed=$mx, kw...))
+    @eval $(Symbol("p", alias))(args...; comm=nothing, use_threads=nothing, kw...) = _narrow($target(args...; eps_floor=_EPS32, mixed=$mx, kw...))
 end
 
 # ---- matrix-free: feast_matvec(A_mul!, B_mul!, N, interval) interfaces/feast_interfaces.jl:465-481 -> feast_sparse_matvec!

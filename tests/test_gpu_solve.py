@@ -320,6 +320,7 @@ def test_float32_entry_points_types_and_tolerance():
     assert rs.info == 0 and rs.M == rd.M == 10
     assert np.abs(np.sort(rs.lambda_) - ev[:10]).max() <= 1e-4 * ev[9]
     assert rs.res.max() <= np.sqrt(np.finfo(np.float32).eps) and rs.loop <= rd.loop   # stops at the Float32 tolerance
+    assert rs.stats["lz_steps_fp32"] == rs.stats["lz_steps_p1"] > 0 and rd.stats["lz_steps_fp32"] == 0   # s-names: FP32 Krylov vectors
     Ah = np.array([[2.5, 0.2 + 0.1j, 0.0], [0.2 - 0.1j, 3.5, 0.3 - 0.2j], [0.0, 0.3 + 0.2j, 4.0]], dtype=np.complex64)
     rc = fc.cfeast_heev(Ah, 2.0, 5.0, 3, fc.feastinit(), Q0=fo.seeded_subspace(3, 3))
     assert rc.info == 0 and rc.M == 3 and rc.q.dtype == np.complex64 and rc.lambda_.dtype == np.float32

@@ -860,15 +860,21 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   FC_CUDA(cudaMemcpyAsync(d_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
 
   // ---- pass 2: same recurrence from the stored scalars, accumulation fused ---------------------------------------
+  // Q is read-modify-written every SECOND step: step j holds u_j and u_{j-1} as own-row operands, so odd steps add both
+  // contributions and even steps carry no Q traffic at all (the staged and matrix-free variants accumulate every step)
   Timer t2;
+  const bool paired = !matfree && !(h->lz_staged && !mixed && !CPLX);
   for (int j = 0; j < k; ++j) {
     if (j == k - 1) {
-      if (mixed) k_lz32_axpy<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, d_coef + (size_t)j * rowsz, cur32(j), QA);
-      else k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, cur(j), QA);
-      check_launch(h);
+      for (int jj = (paired && j >= 1 && ((j - 1) & 1) == 0) ? j - 1 : j; jj <= j; ++jj) {   // a skipped even step k-2 is added here
+        if (mixed) k_lz32_axpy<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, d_coef + (size_t)jj * rowsz, cur32(jj), QA);
+        else k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)jj * rowsz, cur(jj), QA);
+        check_launch(h);
+      }
       break;
     }
-    const bool smp = (j % 16) == 3;
+    const int q_mode = paired ? ((j & 1) ? 2 : 1) : 0;
+    const bool smp = (j % 16) == 3 || (j % 16) == 10;   // one heavy (odd) and one light (even) step per 16
     int g = 0;
     const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P2, j) : -1;
     if (matfree) {
@@ -880,6 +886,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     } else if (mixed) {
       LzArgs32 a = args32(j);
       a.Q = QA; a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
+      a.q_mode = q_mode; a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
       lz32_launch<LZ_P2>(h, a, &g);
     } else {
       LzArgs a;
@@ -889,6 +896,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1); a.Q = QA;
       a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
       a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
+      a.q_mode = q_mode; a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
       a.tile_rows = h->lz_tile_rows;
       lz_launch<LZ_P2, CPLX>(h, a, &g);
     }
@@ -897,7 +905,11 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   k_lz_to_complex<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
   check_launch(h);
   sync(h);  // coef is a host buffer
-  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] = matfree ? 6.0 * 8.0 * (double)n * nc : (mixed ? lz32_bytes_spmm(h, nc, 3, 2) : lz_bytes_spmm(h, nc, 5, CPLX));
+  // algorithmic bytes of an AVERAGE pass-2 launch: paired accumulation moves the accumulator in every second launch only
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] =
+      matfree ? 6.0 * 8.0 * (double)n * nc
+              : (mixed ? 0.5 * (lz32_bytes_spmm(h, nc, 3, paired ? 0 : 2) + lz32_bytes_spmm(h, nc, 3, 2))
+                       : 0.5 * (lz_bytes_spmm(h, nc, paired ? 3 : 5, CPLX) + lz_bytes_spmm(h, nc, 5, CPLX)));
   drain_events(h);
   h->stats.lz_steps_p2 += k;
   h->stats.ms_lz_p2 += t2.ms();

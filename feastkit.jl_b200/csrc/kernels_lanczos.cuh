@@ -47,6 +47,10 @@ struct LzArgs {
   int pstride;
   int tile_rows;         // rows per round-robin tile (rounded to the CTA's rows-per-iteration)
   const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
+  // LZ_P2 accumulates every second step: the own-row operands u_j (U) and u_{j-1} (prev) are both in registers, so one
+  // read-modify-write of Q serves two steps.  0: Q += coef*u_j ; 1: leave Q alone ; 2: Q += coef_prev*u_{j-1} + coef*u_j
+  int q_mode;
+  const double* s_coef_prev;
 };
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -189,13 +193,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
   };
 
   // per-column scalars of this step live in shared memory (one 16-byte read per use instead of 20 live registers)
-  __shared__ double2 s_sc[4][FC_MAXCOLS / 2];   // [0] inv_beta | theta, [1] ratio_b, [2] ratio_a, [3] coef
-  for (int i = threadIdx.x; i < 4 * (FC_MAXCOLS / 2); i += THREADS) {
+  __shared__ double2 s_sc[5][FC_MAXCOLS / 2];   // [0] inv_beta | theta, [1] ratio_b, [2] ratio_a, [3] coef, [4] coef of the previous step
+  for (int i = threadIdx.x; i < 5 * (FC_MAXCOLS / 2); i += THREADS) {
     const int w = i / (FC_MAXCOLS / 2), pc = i % (FC_MAXCOLS / 2);
-    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta) : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : a.s_coef));
+    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta)
+                                 : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : (w == 3 ? a.s_coef : a.s_coef_prev)));
     s_sc[w][pc] = lz_scal<CPLX>(src, pc, a.m);
   }
   __syncthreads();
+  const int q_mode = a.q_mode;
   double2 dot[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
@@ -269,12 +275,19 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
             dot[k].x = fma(uo[k].x, t.x, dot[k].x);
             dot[k].y = fma(uo[k].y, t.y, dot[k].y);
           } else {
-            const double2 cf = s_sc[3][pc];
             stg2(Ol[k] + eo_own, lz_next(t, s_sc[2][pc], uo[k]));
-            double2 q = ldg2(Ql[k] + eo_own);
-            q.x = fma(cf.x, uo[k].x, q.x);
-            q.y = fma(cf.y, uo[k].y, q.y);
-            stg2(Ql[k] + eo_own, q);
+            if (q_mode != 1) {
+              const double2 cf = s_sc[3][pc];
+              double2 q = ldg2(Ql[k] + eo_own);
+              if (q_mode == 2) {
+                const double2 cp = s_sc[4][pc];
+                q.x = fma(cp.x, pv[k].x, q.x);
+                q.y = fma(cp.y, pv[k].y, q.y);
+              }
+              q.x = fma(cf.x, uo[k].x, q.x);
+              q.y = fma(cf.y, uo[k].y, q.y);
+              stg2(Ql[k] + eo_own, q);
+            }
           }
         }
       }

@@ -36,6 +36,8 @@ struct LzArgs32 {
   int pstride;
   int tile_rows;
   const int* done;
+  int q_mode;                  // as LzArgs::q_mode (0: Q += coef*u_j, 1: skip, 2: Q += coef_prev*u_{j-1} + coef*u_j)
+  const double* s_coef_prev;
 };
 
 __device__ __forceinline__ float4 ldg4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -148,12 +150,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
 
   __shared__ float4 s_sc[3][FC_MAXCOLS / 4];     // [0] inv_beta, [1] ratio_b, [2] ratio_a
   __shared__ double s_cf[FC_MAXCOLS];            // coef (pass 2)
+  __shared__ double s_cp[FC_MAXCOLS];            // coef of the previous step (q_mode 2)
   for (int i = threadIdx.x; i < 3 * (FC_MAXCOLS / 4); i += THREADS) {
     const int w = i / (FC_MAXCOLS / 4), pc = i % (FC_MAXCOLS / 4);
     s_sc[w][pc] = lz32_scal(w == 0 ? a.s_inv_beta : (w == 1 ? a.s_ratio_b : a.s_ratio_a), pc, a.m);
   }
-  for (int i = threadIdx.x; i < FC_MAXCOLS; i += THREADS) s_cf[i] = (MODE == LZ_P2 && a.s_coef != nullptr && i < a.m) ? a.s_coef[i] : 0.0;
+  for (int i = threadIdx.x; i < FC_MAXCOLS; i += THREADS) {
+    s_cf[i] = (MODE == LZ_P2 && a.s_coef != nullptr && i < a.m) ? a.s_coef[i] : 0.0;
+    s_cp[i] = (MODE == LZ_P2 && a.s_coef_prev != nullptr && i < a.m) ? a.s_coef_prev[i] : 0.0;
+  }
   __syncthreads();
+  const int q_mode = a.q_mode;
   double dot[4] = {0.0, 0.0, 0.0, 0.0};
 
   const unsigned ldu = (unsigned)a.ld;
@@ -188,8 +195,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
     const float4 pv = ldg4f(Pl + eo_own);
     double2 q0 = make_double2(0.0, 0.0), q1 = q0;
     if constexpr (MODE == LZ_P2) {
-      q0 = ldg2(Ql + eo_own);
-      q1 = ldg2(Ql + eo_own + 2);
+      if (q_mode != 1) {
+        q0 = ldg2(Ql + eo_own);
+        q1 = ldg2(Ql + eo_own + 2);
+      }
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     lz32_gather<G, UNMAX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
@@ -200,13 +209,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
         lz32_dot(dot, uo, t);
       } else {
         stg4f(Ol + eo_own, lz32_next(t, s_sc[2][g], uo));
-        const double* cf = s_cf + 4 * g;
-        q0.x = fma(cf[0], (double)uo.x, q0.x);
-        q0.y = fma(cf[1], (double)uo.y, q0.y);
-        q1.x = fma(cf[2], (double)uo.z, q1.x);
-        q1.y = fma(cf[3], (double)uo.w, q1.y);
-        stg2(Ql + eo_own, q0);
-        stg2(Ql + eo_own + 2, q1);
+        if (q_mode != 1) {
+          if (q_mode == 2) {
+            const double* cp = s_cp + 4 * g;
+            q0.x = fma(cp[0], (double)pv.x, q0.x);
+            q0.y = fma(cp[1], (double)pv.y, q0.y);
+            q1.x = fma(cp[2], (double)pv.z, q1.x);
+            q1.y = fma(cp[3], (double)pv.w, q1.y);
+          }
+          const double* cf = s_cf + 4 * g;
+          q0.x = fma(cf[0], (double)uo.x, q0.x);
+          q0.y = fma(cf[1], (double)uo.y, q0.y);
+          q1.x = fma(cf[2], (double)uo.z, q1.x);
+          q1.y = fma(cf[3], (double)uo.w, q1.y);
+          stg2(Ql + eo_own, q0);
+          stg2(Ql + eo_own + 2, q1);
+        }
       }
     }
     r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; o_cur = o_nxt; a_cur = a_nxt; o_cur2 = o_nxt2; a_cur2 = a_nxt2;

@@ -119,6 +119,7 @@ struct feastcuda_handle_s {
   int lzp_smax = 0, lzp_ntiles = 0;
   bool lzp_built = false, lzp_usable = false;
   int lz_egrid_mult = 4;    // CTAs per SM of the elementwise Lanczos kernels (partial rows the scalar kernels reduce)
+  int lz_paired = 1;        // pass 2 accumulates Q every second step (0: every step)
   int lz_staged = 0;        // 1: use the staged gather where the plan allows it
   int lz_threads = 512;     // CTA size of the Lanczos SpMM (512 or 1024)
   int lz_ctas_per_sm = 2;   // persistent CTAs per SM of the Lanczos SpMM (contiguous row chunks keep the band in L1)

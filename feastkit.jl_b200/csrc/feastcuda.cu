@@ -472,7 +472,7 @@ static void block_bicgstab(H* h, zc z, int m, const zd* RHS, zd* X, bool use_x0,
 // =====================================================================================================
 struct MslOut { int k = 0; double maxres = 0.0; bool converged = false; };
 
-static inline double* rblk(H* h, int slot) { return h->blk[slot].as<double>(); }
+static inline double* rblk(H* h, int slot) { return reinterpret_cast<double*>(blk(h, slot)); }
 
 static int lz_grid_spmm(H* h, int64_t n, int rows_per_step) {
   const int64_t tr = (int64_t)std::max(1, h->lz_tile_rows / rows_per_step) * rows_per_step;   // as in k_lz_spmm
@@ -566,7 +566,9 @@ static bool lz_launch_staged(H* h, LzArgs& a, int* grid_out) {
 
 template <int MODE, bool CPLX>
 static void lz_launch(H* h, LzArgs& a, int* grid_out) {
-  if (!CPLX && lz_launch_staged<MODE>(h, a, grid_out)) return;
+  if constexpr (MODE <= LZ_PLAIN) {   // the staged variant has no paired-accumulation modes
+    if (!CPLX && lz_launch_staged<MODE>(h, a, grid_out)) return;
+  }
   const int P = CPLX ? a.m : (a.m + 1) / 2;
   // G lanes per row, NC column-pair chunks per lane
 #define FC_LZ(G, NC)                                                                       \
@@ -581,12 +583,13 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
       k_lz_spmm<G, NC, MODE, 512, CPLX><<<grid, 512, 0, h->stream>>>(a);                   \
     }                                                                                      \
   } while (0)
-  if (P <= 1) FC_LZ(1, 1);
-  else if (P <= 2) FC_LZ(2, 1);
-  else if (P <= 4) FC_LZ(4, 1);
-  else if (P <= 8) FC_LZ(8, 1);
-  else if (P <= 16) FC_LZ(16, 1);
-  else if (P <= 32) FC_LZ(32, 1);
+  const int Pd = P;   // lanes per row = elements per row (wider groups for narrow blocks measured slower: idle lanes still issue)
+  if (Pd <= 1) FC_LZ(1, 1);
+  else if (Pd <= 2) FC_LZ(2, 1);
+  else if (Pd <= 4) FC_LZ(4, 1);
+  else if (Pd <= 8) FC_LZ(8, 1);
+  else if (Pd <= 16) FC_LZ(16, 1);
+  else if (Pd <= 32) FC_LZ(32, 1);
   else FC_LZ(32, 2);
 #undef FC_LZ
   check_launch(h);
@@ -863,7 +866,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   // Q is read-modify-written every SECOND step: step j holds u_j and u_{j-1} as own-row operands, so odd steps add both
   // contributions and even steps carry no Q traffic at all (the staged and matrix-free variants accumulate every step)
   Timer t2;
-  const bool paired = !matfree && !(h->lz_staged && !mixed && !CPLX);
+  const bool paired = h->lz_paired && !matfree && !(h->lz_staged && !mixed && !CPLX);
   for (int j = 0; j < k; ++j) {
     if (j == k - 1) {
       for (int jj = (paired && j >= 1 && ((j - 1) & 1) == 0) ? j - 1 : j; jj <= j; ++jj) {   // a skipped even step k-2 is added here
@@ -886,8 +889,10 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     } else if (mixed) {
       LzArgs32 a = args32(j);
       a.Q = QA; a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
-      a.q_mode = q_mode; a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
-      lz32_launch<LZ_P2>(h, a, &g);
+      a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
+      if (q_mode == 0) lz32_launch<LZ_P2>(h, a, &g);
+      else if (q_mode == 1) lz32_launch<LZ_P2_SKIP>(h, a, &g);
+      else lz32_launch<LZ_P2_PAIR>(h, a, &g);
     } else {
       LzArgs a;
       memset(&a, 0, sizeof(a));
@@ -896,9 +901,11 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1); a.Q = QA;
       a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
       a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
-      a.q_mode = q_mode; a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
+      a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
       a.tile_rows = h->lz_tile_rows;
-      lz_launch<LZ_P2, CPLX>(h, a, &g);
+      if (q_mode == 0) lz_launch<LZ_P2, CPLX>(h, a, &g);
+      else if (q_mode == 1) lz_launch<LZ_P2_SKIP, CPLX>(h, a, &g);
+      else lz_launch<LZ_P2_PAIR, CPLX>(h, a, &g);
     }
     sample_end(h, ev);
   }
@@ -1634,6 +1641,7 @@ int feastcuda_create(feastcuda_handle* out, int device) {
   if (const char* e = getenv("FEASTCUDA_LZ_THREADS")) h->lz_threads = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_CTAS")) h->lz_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("FEASTCUDA_LZ_TILE")) h->lz_tile_rows = std::max(1, atoi(e));
+  if (const char* e = getenv("FEASTCUDA_LZ_PAIRED")) h->lz_paired = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_STAGED")) h->lz_staged = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_EGRID")) h->lz_egrid_mult = std::max(1, std::min(8, atoi(e)));
   *out = h;

@@ -28,8 +28,13 @@ enum LzMode {
   LZ_P1 = 0,     // out = (A u) * inv_beta - ratio_b * prev ;   partial[0] = u . out
   LZ_P2 = 1,     // t as LZ_P1; out = t - ratio_a * u ;  Q += coef * u
   LZ_RES = 2,    // out = A u - theta * u ;  partial[0] = |out|^2 ;  Q = coef * u      (Ritz-residual start block)
-  LZ_PLAIN = 3   // out = A u
+  LZ_PLAIN = 3,  // out = A u
+  // pass 2 with the accumulator touched every SECOND step: step j holds u_j (U) and u_{j-1} (prev) as own-row operands, so one
+  // read-modify-write of Q serves two steps (compile-time variants: a run-time switch cost the narrow kernels their schedule)
+  LZ_P2_SKIP = 4,   // as LZ_P2 without any Q traffic
+  LZ_P2_PAIR = 5    // as LZ_P2 with Q += coef_prev * u_{j-1} + coef * u_j
 };
+__host__ __device__ constexpr bool lz_is_p2(int mode) { return mode == LZ_P2 || mode == LZ_P2_SKIP || mode == LZ_P2_PAIR; }
 
 struct LzArgs {
   int64_t n;
@@ -47,10 +52,7 @@ struct LzArgs {
   int pstride;
   int tile_rows;         // rows per round-robin tile (rounded to the CTA's rows-per-iteration)
   const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
-  // LZ_P2 accumulates every second step: the own-row operands u_j (U) and u_{j-1} (prev) are both in registers, so one
-  // read-modify-write of Q serves two steps.  0: Q += coef*u_j ; 1: leave Q alone ; 2: Q += coef_prev*u_{j-1} + coef*u_j
-  int q_mode;
-  const double* s_coef_prev;
+  const double* s_coef_prev;   // LZ_P2_PAIR: c_{j-1} / beta_{j-1}
 };
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -201,7 +203,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
     s_sc[w][pc] = lz_scal<CPLX>(src, pc, a.m);
   }
   __syncthreads();
-  const int q_mode = a.q_mode;
   double2 dot[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
     for (int k = 0; k < NC; ++k) {
       acc[k] = make_double2(0.0, 0.0);
       if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
-      if constexpr (MODE == LZ_P1 || MODE == LZ_P2) pv[k] = ldg2(Pl[k] + eo_own);
+      if constexpr (MODE == LZ_P1 || lz_is_p2(MODE)) pv[k] = ldg2(Pl[k] + eo_own);
     }
     lz_gather<G, NC, CPLX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
 #pragma unroll
@@ -276,10 +277,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
             dot[k].y = fma(uo[k].y, t.y, dot[k].y);
           } else {
             stg2(Ol[k] + eo_own, lz_next(t, s_sc[2][pc], uo[k]));
-            if (q_mode != 1) {
+            if constexpr (MODE != LZ_P2_SKIP) {
               const double2 cf = s_sc[3][pc];
               double2 q = ldg2(Ql[k] + eo_own);
-              if (q_mode == 2) {
+              if constexpr (MODE == LZ_P2_PAIR) {
                 const double2 cp = s_sc[4][pc];
                 q.x = fma(cp.x, pv[k].x, q.x);
                 q.y = fma(cp.y, pv[k].y, q.y);

@@ -36,8 +36,7 @@ struct LzArgs32 {
   int pstride;
   int tile_rows;
   const int* done;
-  int q_mode;                  // as LzArgs::q_mode (0: Q += coef*u_j, 1: skip, 2: Q += coef_prev*u_{j-1} + coef*u_j)
-  const double* s_coef_prev;
+  const double* s_coef_prev;   // LZ_P2_PAIR: c_{j-1} / beta_{j-1}
 };
 
 __device__ __forceinline__ float4 ldg4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -122,7 +121,7 @@ __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, 
 // (THREADS, MINB, UNMAX): 512 x 2 CTAs/SM x 4 gathers in flight (64 registers) or fewer resident warps with more loads in flight each
 template <int G, int MODE, int THREADS, int MINB = 1024 / THREADS, int UNMAX = 4>
 __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
-  static_assert(MODE == LZ_P1 || MODE == LZ_P2, "FP32 vectors exist only inside the two Lanczos passes");
+  static_assert(MODE == LZ_P1 || lz_is_p2(MODE), "FP32 vectors exist only inside the two Lanczos passes");
   if (a.done != nullptr && *a.done != 0) return;
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
@@ -156,11 +155,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
     s_sc[w][pc] = lz32_scal(w == 0 ? a.s_inv_beta : (w == 1 ? a.s_ratio_b : a.s_ratio_a), pc, a.m);
   }
   for (int i = threadIdx.x; i < FC_MAXCOLS; i += THREADS) {
-    s_cf[i] = (MODE == LZ_P2 && a.s_coef != nullptr && i < a.m) ? a.s_coef[i] : 0.0;
-    s_cp[i] = (MODE == LZ_P2 && a.s_coef_prev != nullptr && i < a.m) ? a.s_coef_prev[i] : 0.0;
+    s_cf[i] = (lz_is_p2(MODE) && a.s_coef != nullptr && i < a.m) ? a.s_coef[i] : 0.0;
+    s_cp[i] = (MODE == LZ_P2_PAIR && a.s_coef_prev != nullptr && i < a.m) ? a.s_coef_prev[i] : 0.0;
   }
   __syncthreads();
-  const int q_mode = a.q_mode;
   double dot[4] = {0.0, 0.0, 0.0, 0.0};
 
   const unsigned ldu = (unsigned)a.ld;
@@ -194,11 +192,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
     const float4 uo = ldg4f(Ul + eo_own);
     const float4 pv = ldg4f(Pl + eo_own);
     double2 q0 = make_double2(0.0, 0.0), q1 = q0;
-    if constexpr (MODE == LZ_P2) {
-      if (q_mode != 1) {
-        q0 = ldg2(Ql + eo_own);
-        q1 = ldg2(Ql + eo_own + 2);
-      }
+    if constexpr (MODE == LZ_P2 || MODE == LZ_P2_PAIR) {
+      q0 = ldg2(Ql + eo_own);
+      q1 = ldg2(Ql + eo_own + 2);
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     lz32_gather<G, UNMAX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
@@ -209,8 +205,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
         lz32_dot(dot, uo, t);
       } else {
         stg4f(Ol + eo_own, lz32_next(t, s_sc[2][g], uo));
-        if (q_mode != 1) {
-          if (q_mode == 2) {
+        if constexpr (MODE != LZ_P2_SKIP) {
+          if constexpr (MODE == LZ_P2_PAIR) {
             const double* cp = s_cp + 4 * g;
             q0.x = fma(cp[0], (double)pv.x, q0.x);
             q0.y = fma(cp[1], (double)pv.y, q0.y);

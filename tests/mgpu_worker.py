@@ -28,6 +28,7 @@ def main():
     Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
     out = {}
     for name, kw in (("mslanczos_columns", dict(solver="mslanczos", solver_maxiter=2000)),
+                     ("mslanczos_mixed_columns", dict(solver="mslanczos", solver_maxiter=2000, mixed=True)),
                      ("bicgstab_nodes", dict(solver="bicgstab", solver_maxiter=400, inner_rel=1e-3, ritz_guess=True, shard="nodes")),
                      ("bicgstab_balanced", dict(solver="bicgstab", solver_maxiter=400, inner_rel=1e-3, ritz_guess=True, shard="balanced"))):
         r = fc.pdfeast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, **kw)
@@ -36,6 +37,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         out[name] = {"ok_all_ranks": bool(t[0].item() == 1.0), "loop": r.loop, "M": r.M, "info": r.info, "epsout": r.epsout,
                      "allreduce_bytes": r.stats["allreduce_bytes"], "lz_steps": r.stats["lz_steps_p1"], "world": world}
+    # matrix-free operator (compiled CUDA stencil callback), columns sharded like the CSR Lanczos path
+    import ctypes as C
+
+    class LaplacianGrid(C.Structure):
+        _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int)]
+
+    ex = C.CDLL(str(ROOT / "feastkit.jl_b200" / "lib" / "libfeastcuda_examples.so"))
+    grid = LaplacianGrid(N, N, N)
+    r = fc.feast_matvec((ex.feastcuda_example_laplacian3d, grid), None, N ** 3, (Emin, Emax), M0=M0, fpm=fc.feastinit(), Q0=Q0,
+                        solver_maxiter=2000)
+    ok = (r.info == 0 and r.M == 10 and float(np.abs(np.sort(r.lambda_) - ev[:10]).max()) < 1e-10 and float(r.res.max()) < 1e-12)
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["matfree_columns"] = {"ok_all_ranks": bool(t[0].item() == 1.0), "loop": r.loop, "M": r.M, "info": r.info, "epsout": r.epsout,
+                              "allreduce_bytes": r.stats["allreduce_bytes"], "lz_steps": r.stats["lz_steps_p1"], "world": world}
     # dense (LU per node, nodes sharded by the reference's block rule) and general (full contour) solves
     rng = np.random.default_rng(3)
     n = 160

@@ -35,7 +35,7 @@ METRIC = "FEAST solve eigenpairs/s (sparse 3D Laplacian n=1M, M0=64, 8 nodes; wa
 UNIT = "eigenpairs/s"
 # Lanczos steps the engine needed for this config on B200 (gpurun_out/r1_msl100.log: 718 + 662 + 303 over 3 sweeps, both
 # passes each); the CPU arms extrapolate their bounded sample with it.  The live GPU run reports its own count.
-C3_LANCZOS_STEPS = 1683
+C3_LANCZOS_STEPS = 1785
 C3_M = 35
 SOLVER_KW = dict(solver="mslanczos", inner_rel=1e-3, ritz_guess=True, solver_maxiter=3000, check_every=16, filter="true", adaptive=True)
 
@@ -222,11 +222,12 @@ def run_gpu(args):
     # secondary leg, reported beside the headline and never mixed into it: the same solve with fpm[42]'s "single-precision
     # solver" (FP32 Lanczos vectors inside the FP64 refinement loop, opts.mixed)
     opts_fp64 = opts
-    opts = eng.make_opts(q0_real=True, x_real=True, shard="columns", mixed=True, **SOLVER_KW)
-    resident_step()
+    opts = eng.make_opts(q0_real=True, x_real=True, shard="columns", mixed=not args.no_mixed, **SOLVER_KW)
+    if not args.no_mixed:
+        resident_step()
     eng.reset_stats()
     mx_ms, mx_last = [], None
-    for _ in range(max(1, args.steps // 2 + 1)):
+    for _ in range(1 if args.no_mixed else max(1, args.steps // 2 + 1)):
         ms, mM, minfo, meps, mloop = resident_step()
         mx_ms.append(ms)
         mx_last = (mM, minfo, meps, mloop)
@@ -295,7 +296,7 @@ def run_gpu(args):
            "e2e": {"value": r.M / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
                    "h2d_bytes_per_step": int(Q0.nbytes), "d2h_bytes_per_step": int(r.q.nbytes + r.lambda_.nbytes + r.res.nbytes)},
            "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-           "mixed_precision": {
+           "mixed_precision": None if args.no_mixed else {
                "what": "same solve with opts.mixed (fpm[42] 'single-precision solver'): FP32 Lanczos vectors and matrix entries, FP64 "
                        "scalars, accumulator, Rayleigh-Ritz and residuals; not the headline",
                "ms_per_step": mx_step, "value": mx_last[0] / (mx_step / 1e3), "unit": UNIT,
@@ -320,6 +321,7 @@ def main():
     ap.add_argument("--m0", type=int, default=64)
     ap.add_argument("--cpu-sample-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the secondary mixed-precision leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,8 +13,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture(scope="session", autouse=True)
 def built_lib():
+    """Every test session starts from current in-tree libraries (libfeastcuda.so and the example operators); build() is a no-op
+    when they are newer than their sources."""
     import __graft_entry__ as g
     g.build()
     return g.LIB

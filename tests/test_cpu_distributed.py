@@ -46,13 +46,16 @@ def _worker(rank, world, port, out):
 
     r = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=800,
                                col_slices=lambda active: pair_slice(active, world, rank), allreduce=allreduce)
+    # fpm[42] mixed precision: FP32 Lanczos vectors on every rank's slice, same FP64 all-reduce and Rayleigh-Ritz stage
+    rm = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=800, adaptive=True, mixed=True,
+                                col_slices=lambda active: pair_slice(active, world, rank), allreduce=allreduce)
     ne = 8
     s, c = fo.node_partition(ne, world, rank)
     rb = fp.feast_hrr_bicgstab(A, None, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=400,
                                node_items=lambda loop, active: [(e, 0, active) for e in range(s, s + c)], allreduce=allreduce)
     if rank == 0:
         np.savez(out, lam=np.sort(r.lambda_), M=r.M, info=r.info, loop=r.loop, q=r.q, lam_b=np.sort(rb.lambda_), M_b=rb.M,
-                 info_b=rb.info)
+                 info_b=rb.info, lam_m=np.sort(rm.lambda_), M_m=rm.M, info_m=rm.info, res_m=rm.res.max(), fp32_sweeps=rm.stats["fp32_sweeps"])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -90,3 +93,5 @@ def test_world_size_2_sharded_solves_equal_single_rank(tmp_path):
     assert np.abs(got["lam"] - ev[:7]).max() < 1e-10
     assert fo.subspace_angle(got["q"].astype(complex), np.asarray(r1.q, dtype=complex)) < 1e-8
     assert int(got["info_b"]) == 0 and int(got["M_b"]) == 7 and np.abs(got["lam_b"] - ev[:7]).max() < 1e-10
+    assert int(got["info_m"]) == 0 and int(got["M_m"]) == 7 and np.abs(got["lam_m"] - ev[:7]).max() < 1e-10
+    assert float(got["res_m"]) < 1e-12 and int(got["fp32_sweeps"]) >= 2

@@ -271,10 +271,12 @@ def run_gpu(args):
     traffic = None
     prof = ROOT / "profiles" / "ncu_summary.json"
     if prof.exists() and dom:
-        traffic = json.loads(prof.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+        summ = json.loads(prof.read_text())
+        # pass 2 alternates two launch kinds (accumulating / skipping): its per-launch traffic is their average
+        traffic = summ.get("lz_p2_paired_average" if dom == "lz_p2" and "lz_p2_paired_average" in summ else dom, {}).get("dram_bytes_per_launch")
     roofline = None
     if dom:
-        roofline = {"bound": "hbm", "kernel": {"lz_p1": "k_lz_spmm<LZ_P1>", "lz_p2": "k_lz_spmm<LZ_P2>", "lz_upd": "k_lz_update"}[dom],
+        roofline = {"bound": "hbm", "kernel": {"lz_p1": "k_lz_spmm<LZ_P1>", "lz_p2": "k_lz_spmm<LZ_P2_PAIR|LZ_P2_SKIP> (pass 2, average launch)", "lz_upd": "k_lz_update"}[dom],
                     "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": traffic,
                     "peak_source": peak_src, "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"],
                     "share_of_step": share[dom] / (ms_step * args.steps), "all_kernels": kern}

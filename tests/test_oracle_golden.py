@@ -215,3 +215,20 @@ def test_multishift_lanczos_filter_equals_direct_solves():
     theta = np.linspace(2.1, 2.9, m)
     got2 = fp.mslanczos_filter(A, Q, theta, Z, W, 1e-13, 600)   # Ritz-guess form is the same operator
     assert np.abs(got2 - want).max() < 1e-9 * np.abs(want).max()
+
+
+def test_mixed_precision_port_on_an_ill_conditioned_interval():
+    """FP32 Lanczos vectors (fpm[42]) on a 1-D Laplacian whose interval sits at the bottom of the spectrum (shifted systems with
+    condition ~1e5): the FP64 refinement loop still reaches the FP64 pairs, at the price of more Lanczos steps (loss of
+    orthogonality delays the FP32 recurrence) -- the reason the engine keeps mixed precision opt-in."""
+    n, M0 = 400, 12
+    A = fo.laplacian_1d(n).tocsr().astype(float)
+    w = 2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    Emin, Emax = 0.0, 0.5 * (w[5] + w[6])
+    Q0 = fo.seeded_subspace(n, M0, complex_storage=False)
+    r64 = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2400, adaptive=True)
+    r32 = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2400, adaptive=True, mixed=True)
+    for r in (r64, r32):
+        assert r.info == 0 and r.M == 6 and r.res.max() < 1e-12
+        assert np.abs(np.sort(r.lambda_) - w[:6]).max() < 1e-12
+    assert r32.stats["fp32_sweeps"] >= 1 and sum(r32.stats["lz_steps"]) >= sum(r64.stats["lz_steps"])

@@ -78,6 +78,17 @@ def main():
                            "q": [[0.8, 0.1], [0.3, 0.7], [0.5, 0.6]], "lambda": [4.2, 5.8]}
     src = np.array([[1.0, 2.0, 0.0, 1.0e-15], [1.0j, 2.0j, 1.0, 1.0e-15j], [0, 0, 1.0j, 0], [0, 0, 0, 0]], dtype=complex)
     ka["KA12_qr_compress"] = {"cite": "test/test_allocation_helpers.jl:274-292", "src": cplx(src), "rank": 2}
+    # KA15 complex-symmetric dense pencil, runtests.jl:241-268 (feast_gegv_complex_sym! / feast_geev_complex_sym!, atol 1e-7 there)
+    Acs = np.array([[0.3 + 0.2j, 0.1 + 0.4j, 0, 0], [0.1 + 0.4j, 0.9 - 0.1j, 0.2j, 0], [0, 0.2j, 1.4 + 0.3j, 0.15 - 0.1j],
+                    [0, 0, 0.15 - 0.1j, 2.2 + 0.1j]], dtype=complex)
+    Bcs = np.array([1.0, 1.1, 1.2, 1.3])
+    center, radius = 1.0 + 0.1j, 1.5
+    fpm15 = fo.feastdefault(fo.feastinit())
+    import scipy.linalg as sla
+    inside = lambda w: [x for x in w if fo.feast_inside_gcontour(x, center, radius, fpm15)]
+    ka["KA15_complex_symmetric"] = {"cite": "test/runtests.jl:241-268", "A": cplx(Acs), "B_diag": Bcs.tolist(), "center": [center.real, center.imag],
+                                    "radius": radius, "M0": 4, "expected_generalized": cplx(inside(sla.eigvals(Acs, np.diag(Bcs).astype(complex)))),
+                                    "expected_standard": cplx(inside(np.linalg.eigvals(Acs))), "atol": 1e-7}
     # contour golden numbers: feast_contour(0.5, 1.5, fpm) with the defaults (8 Gauss nodes, circle),
     # formula core/feast_tools.jl:242-262 evaluated with numpy leggauss
     ka["contour_default"] = {"cite": "src/core/feast_tools.jl:212-284", "Emin": 0.5, "Emax": 1.5, "ne": 8,

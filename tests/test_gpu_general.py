@@ -111,13 +111,13 @@ def test_complex_symmetric_families_dense_sparse_banded():
     feast_gegv_complex_sym!/feast_geev_complex_sym! find eigvals(A, B) inside the contour (atol 1e-7 in the reference), reject a
     non-symmetric matrix; the sparse (feast_scsr*_complex!) and banded (feast_sb*_complex!) names reach the same values."""
     import feastcuda as fc
-    A = np.array([[0.3 + 0.2j, 0.1 + 0.4j, 0, 0], [0.1 + 0.4j, 0.9 - 0.1j, 0.2j, 0], [0, 0.2j, 1.4 + 0.3j, 0.15 - 0.1j],
-                  [0, 0, 0.15 - 0.1j, 2.2 + 0.1j]], dtype=complex)
-    B = np.diag([1.0, 1.1, 1.2, 1.3]).astype(complex)
-    Emid, r = 1.0 + 0.1j, 1.5
-    fpm0 = fo.feastdefault(fo.feastinit())
-    inside = lambda w: [x for x in w if fo.feast_inside_gcontour(x, Emid, r, fpm0)]
-    want_g, want_s = inside(sla.eigvals(A, B)), inside(np.linalg.eigvals(A))
+    import json
+    from pathlib import Path
+    k = json.loads((Path(__file__).parent / "golden" / "reference_known_answers.json").read_text())["KA15_complex_symmetric"]
+    un = lambda c: np.array(c["re"]) + 1j * np.array(c["im"])
+    A, B = un(k["A"]), np.diag(np.array(k["B_diag"], dtype=complex))
+    Emid, r = complex(*k["center"]), k["radius"]
+    want_g, want_s = list(un(k["expected_generalized"])), list(un(k["expected_standard"]))
     Q0 = fo.seeded_subspace(4, 4)
     rg = fc.feast_gegv_complex_sym(A.copy(), B.copy(), Emid, r, 4, fc.feastinit(), Q0=Q0)
     assert rg.info == 0 and rg.M == len(want_g)

@@ -232,3 +232,18 @@ def test_mixed_precision_port_on_an_ill_conditioned_interval():
         assert r.info == 0 and r.M == 6 and r.res.max() < 1e-12
         assert np.abs(np.sort(r.lambda_) - w[:6]).max() < 1e-12
     assert r32.stats["fp32_sweeps"] >= 1 and sum(r32.stats["lz_steps"]) >= sum(r64.stats["lz_steps"])
+
+
+def test_ka15_complex_symmetric_pencil():
+    """runtests.jl:241-268: the complex-symmetric wrappers must find eigvals(A, B) inside the circle (atol 1e-7).  The oracle's
+    general solver (one-sided Rayleigh-Ritz) is what the engine routes these names through."""
+    k = KA["KA15_complex_symmetric"]
+    un = lambda c: np.array(c["re"]) + 1j * np.array(c["im"])
+    A, B = un(k["A"]), np.diag(np.array(k["B_diag"], dtype=complex))
+    assert np.array_equal(A, A.T) and not np.allclose(A, A.conj().T)          # symmetric, not Hermitian
+    center = complex(*k["center"])
+    for Bm, want in ((B, un(k["expected_generalized"])), (None, un(k["expected_standard"]))):
+        r = fo.feast_general(A, Bm, center, k["radius"], k["M0"], fo.feastinit())
+        assert r.info == 0 and r.M == len(want)
+        for lam in r.lambda_:
+            assert np.abs(want - lam).min() < k["atol"]

@@ -212,6 +212,12 @@ end
 for f in (:feast_scsrgv, :feast_hcsrgv, :feast_sygv, :feast_hegv)
     @eval $(Symbol(f, "x!"))(A, B, Emin, Emax, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, B, Emin, Emax, M0, fpm; Zne=Zne, Wne=Wne, kw...)
 end
+for f in (:feast_sbev, :feast_hbev)     # banded/feast_banded.jl:1422-1440, 326-383
+    @eval $(Symbol(f, "x!"))(A, kla, Emin, Emax, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, kla, Emin, Emax, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
+for f in (:feast_sbgv, :feast_hbgv)
+    @eval $(Symbol(f, "x!"))(A, B, kla, klb, Emin, Emax, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, B, kla, klb, Emin, Emax, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
 
 # precision / parallel alias families (interfaces/feast_precision_aliases.jl:10-117,163-423,497-771): pure forwarding.
 # With `comm`/`use_threads` the reference picks an MPI/threads backend; here every rank of the job (one process per GPU,
@@ -314,6 +320,91 @@ function feast_general(A::AbstractMatrix, center::Number, radius::Real; M0::Int=
     return issparse(A) ? feast_gcsrev!(A, center, radius, M0, fpm; kw...) : feast_geev!(Matrix(A), center, radius, M0, fpm; kw...)
 end
 
+# general band storage (2k+1) x n, diagonal in row k+1: feast_gbgv!/gbev! banded/feast_banded.jl:1548-1600
+feast_gbgv!(A::Matrix, B::Matrix, ka::Int, kb::Int, Emid, r, M0, fpm; kw...) =
+    _solve_contour(h -> set_band!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), ka, FEASTCUDA_GEN), h -> set_band!(h, FEASTCUDA_B, Matrix{ComplexF64}(B), kb, FEASTCUDA_GEN),
+                   size(A, 2), Emid, r, M0, fpm; kw...)
+feast_gbev!(A::Matrix, ka::Int, Emid, r, M0, fpm; kw...) =
+    _solve_contour(h -> set_band!(h, FEASTCUDA_A, Matrix{ComplexF64}(A), ka, FEASTCUDA_GEN), nothing, size(A, 2), Emid, r, M0, fpm; kw...)
+feast_gbgvx!(A, B, ka, kb, Emid, r, M0, fpm, Zne, Wne; kw...) = feast_gbgv!(A, B, ka, kb, Emid, r, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+feast_gbevx!(A, ka, Emid, r, M0, fpm, Zne, Wne; kw...) = feast_gbev!(A, ka, Emid, r, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+
+# ---- complex-symmetric names (A == transpose(A)): dense/feast_dense.jl:1261-1286, sparse/feast_sparse.jl:1038-1095,
+# banded/feast_banded.jl:1469-1525.  Validation as in the reference (core/feast_aux.jl:665-668), then the general-contour
+# engine (orthonormalised one-sided Rayleigh-Ritz instead of the transpose-bilinear CS-RR projection: same eigenvalues inside).
+_check_complex_symmetric(A) = issymmetric(A) || throw(ArgumentError("Matrix must be complex-symmetric (equal to its transpose)."))
+function feast_gegv_complex_sym!(A::Matrix{<:Complex}, B::Matrix{<:Complex}, Emid, r, M0, fpm; kw...)
+    _check_complex_symmetric(A); _check_complex_symmetric(B)
+    return feast_gegv!(A, B, Emid, r, M0, fpm; kw...)
+end
+function feast_geev_complex_sym!(A::Matrix{<:Complex}, Emid, r, M0, fpm; kw...)
+    _check_complex_symmetric(A)
+    return feast_geev!(A, Emid, r, M0, fpm; kw...)
+end
+function feast_scsrgv_complex!(A::SparseMatrixCSC{<:Complex}, B::SparseMatrixCSC{<:Complex}, Emid, r, M0, fpm; kw...)
+    _check_complex_symmetric(A); _check_complex_symmetric(B)
+    return feast_gcsrgv!(A, B, Emid, r, M0, fpm; kw...)
+end
+function feast_scsrev_complex!(A::SparseMatrixCSC{<:Complex}, Emid, r, M0, fpm; kw...)
+    _check_complex_symmetric(A)
+    return feast_gcsrev!(A, Emid, r, M0, fpm; kw...)
+end
+# symmetric upper band (k+1) x n (diagonal in the last row) -> general band (2k+1) x n, no conjugation
+function _symmetric_band_to_general(AB::Matrix{<:Complex}, k::Int)
+    n = size(AB, 2)
+    GB = zeros(ComplexF64, 2k + 1, n)
+    for d in 0:k
+        GB[k + 1 - d, d+1:n] .= AB[k + 1 - d, d+1:n]            # A[j-d, j]
+        d > 0 && (GB[k + 1 + d, 1:n-d] .= AB[k + 1 - d, d+1:n])  # mirrored entry A[j, j-d]
+    end
+    return GB
+end
+feast_sbgv_complex!(A::Matrix{<:Complex}, B::Matrix{<:Complex}, ka::Int, kb::Int, Emid, r, M0, fpm; kw...) =
+    feast_gbgv!(_symmetric_band_to_general(A, ka), _symmetric_band_to_general(B, kb), ka, kb, Emid, r, M0, fpm; kw...)
+feast_sbev_complex!(A::Matrix{<:Complex}, ka::Int, Emid, r, M0, fpm; kw...) =
+    feast_gbev!(_symmetric_band_to_general(A, ka), ka, Emid, r, M0, fpm; kw...)
+
+# ---- polynomial problems: feast_pep! dense/feast_dense.jl:715-772 (first companion linearisation, M0*d columns, leading-block
+# eigenvectors), wrappers :946-987, feast_polynomial interfaces/feast_interfaces.jl:448-462
+function feast_pep!(A::Vector{<:Matrix}, d::Int, Emid, r, M0::Int, fpm::Vector{Int}; kw...)
+    length(A) == d + 1 || throw(ArgumentError("Need d+1 coefficient matrices"))
+    N = size(A[1], 1)
+    all(size(Ai) == (N, N) for Ai in A) || throw(ArgumentError("All matrices must be same size"))
+    DN = d * N
+    A_lin = zeros(ComplexF64, DN, DN); B_lin = zeros(ComplexF64, DN, DN)
+    for i in 1:d-1
+        A_lin[(i-1)*N+1:i*N, i*N+1:(i+1)*N] .= Matrix{ComplexF64}(I, N, N)
+        B_lin[(i-1)*N+1:i*N, (i-1)*N+1:i*N] .= Matrix{ComplexF64}(I, N, N)
+    end
+    for j in 1:d
+        A_lin[(d-1)*N+1:d*N, (j-1)*N+1:j*N] .= -A[j]
+    end
+    B_lin[(d-1)*N+1:d*N, (d-1)*N+1:d*N] .= A[d+1]
+    res = feast_gegv!(A_lin, B_lin, Emid, r, M0 * d, fpm; kw...)
+    return FeastGeneralResult{Float64}(res.lambda, res.q[1:N, :], res.M, res.res, res.info, res.epsout, res.loop)
+end
+feast_gepev!(A, d, Emid, r, M0, fpm; kw...) = feast_pep!(A, d, Emid, r, M0, fpm; kw...)
+feast_hepev!(A, d, Emid, r, M0, fpm; kw...) = feast_pep!(A, d, Emid, r, M0, fpm; kw...)
+feast_sypev!(A::Vector{<:Matrix{<:Real}}, d, Emid, r, M0, fpm; kw...) = feast_pep!([ComplexF64.(Ai) for Ai in A], d, Emid, r, M0, fpm; kw...)
+for f in (:feast_gepev, :feast_hepev, :feast_sypev)
+    @eval $(Symbol(f, "x!"))(A, d, Emid, r, M0, fpm, Zne, Wne; kw...) = $(Symbol(f, "!"))(A, d, Emid, r, M0, fpm; Zne=Zne, Wne=Wne, kw...)
+end
+function feast_polynomial(coeffs::Vector{<:AbstractMatrix}, center::Number, radius::Real; M0::Int=10, fpm=nothing, kw...)
+    fpm = fpm === nothing ? feastinit() : fpm
+    return feast_pep!([Matrix{ComplexF64}(c) for c in coeffs], length(coeffs) - 1, center, radius, M0, fpm; kw...)
+end
+
+# feast_banded(A, kla, interval; B, klb, M0, fpm) -- interfaces/feast_interfaces.jl:381-420
+function feast_banded(A::Matrix, kla::Int, interval::Tuple; B=nothing, klb::Int=0, M0::Int=10, fpm=nothing, kw...)
+    fpm = fpm === nothing ? feastinit() : fpm
+    Emin, Emax = interval
+    M0 = min(M0, size(A, 2))
+    if eltype(A) <: Complex
+        return B === nothing ? feast_hbev!(copy(A), kla, Emin, Emax, M0, fpm; kw...) : feast_hbgv!(copy(A), copy(B), kla, klb, Emin, Emax, M0, fpm; kw...)
+    end
+    return B === nothing ? feast_sbev!(copy(A), kla, Emin, Emax, M0, fpm; kw...) : feast_sbgv!(copy(A), copy(B), kla, klb, Emin, Emax, M0, fpm; kw...)
+end
+
 # ---- multi-GPU attach (replaces the MPI communicator of parallel/feast_mpi.jl:9-54): rank 0 creates the id, the
 # application broadcasts its 128 bytes (MPI.Bcast!, a file, Distributed), every rank attaches its handle ------------------
 function nccl_unique_id()
@@ -367,6 +458,8 @@ end
 export feastinit, feastinit!, feastdefault!, feast_contour, feast_gcontour, feast, FeastResult,
        feast_scsrev!, feast_scsrgv!, feast_hcsrev!, feast_hcsrgv!, feast_syev!, feast_sygv!, feast_heev!, feast_hegv!,
        feast_sbev!, feast_sbgv!, feast_hbev!, feast_hbgv!,
-       feast_matvec, FeastGeneralResult, feast_general, feast_gcsrev!, feast_gcsrgv!, feast_geev!, feast_gegv!
+       feast_matvec, FeastGeneralResult, feast_general, feast_gcsrev!, feast_gcsrgv!, feast_geev!, feast_gegv!, feast_gbev!, feast_gbgv!,
+       feast_geev_complex_sym!, feast_gegv_complex_sym!, feast_scsrev_complex!, feast_scsrgv_complex!, feast_sbev_complex!,
+       feast_sbgv_complex!, feast_pep!, feast_gepev!, feast_hepev!, feast_sypev!, feast_polynomial, feast_banded
 
 end # module

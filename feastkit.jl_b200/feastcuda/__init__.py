@@ -132,6 +132,28 @@ def check_feast_srci_input(N, M0, Emin, Emax, fpm):
     return True
 
 
+def feast_inside_contour(lam, Emin, Emax):
+    """feast_inside_contour (core/feast_tools.jl:619-621): closed interval."""
+    return Emin <= lam <= Emax
+
+
+def feast_inside_gcontour(lam, Emid, r, fpm=None):
+    """feast_inside_gcontour(lambda, Emid, r; fpm) (core/feast_tools.jl:623-650): membership in the ellipse of half-axes r and
+    r*fpm[18]/100 rotated by fpm[19] degrees about Emid -- the same rule as host_inside_gcontour in csrc/host_math.hpp."""
+    import math
+    w = complex(lam) - complex(Emid)
+    aspect, rot = 1.0, 0.0
+    if fpm is not None and len(fpm) >= 19:
+        if fpm[17] > 0:
+            aspect = fpm[17] * 0.01
+        if fpm[18] != 0:
+            rot = (fpm[18] / 180.0) * math.pi
+    if rot != 0.0:
+        w *= complex(math.cos(-rot), math.sin(-rot))
+    x, y = w.real / r, w.imag / (r * aspect)
+    return x * x + y * y <= 1.0
+
+
 def check_feast_grci_input(N, M0, Emid, r, fpm):
     """core/feast_aux.jl:401-425"""
     if N <= 0:

@@ -9,7 +9,7 @@ argument order and state handling:
 `feast_srci` (real symmetric, kernel/feast_kernel.jl:7-293) and `feast_hrci` (complex Hermitian, :397-644) are the moment
 (S-MOM / H-MOM) variants: per node Q_proj += 2 w_e Y, zAq += 2 w_e Q0^H Y, zSq += 2 w_e z_e Q0^H Y; after the sweep
 eigen(Sq, Aq), q = Q_proj V, stable inside-first partition, residuals from the caller's A*q.  `feast_grci` (:646-962) is the
-general one-sided variant on the full contour.
+general one-sided variant on the full contour (q += w_e Y, MULT_B and MULT_A requests for the projections, eigen(Aq, Sq)).
 
 Reference behaviour kept as is: `feast_hrci` accumulates the half-contour sums 2 w_e Y WITHOUT a Hermitian part
 (kernel/feast_kernel.jl:516-524), so its moments are Q0^H g(A) Q0 with the complex g(x) = sum_e 2 w_e / (z_e - x) and
@@ -232,9 +232,12 @@ def feast_hrci(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax
 
 
 def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda_, q, mode, res, info, state=None, engine=None):
-    """feast_grci! -- kernel/feast_kernel.jl:646-962 (general, full contour): INIT handshake and per-node accumulation
-    `q += w_e * workc`; the projection stage is served by `feast_general` (the engine's orthonormalised one-sided RR)."""
-    from . import feast_gcontour, feastdefault_
+    """feast_grci!(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda, q, mode, res, info; state)
+    -- kernel/feast_kernel.jl:646-962 (general one-sided variant, full contour).  Job sequence per refinement loop:
+    10 FACTORIZE -> 11 SOLVE (every node: q += w_e * workc) -> 40 MULT_B (workc <- B q) -> 30 MULT_A (workc <- A q; Aq, Sq formed,
+    eigen(Aq, Sq), inside-contour partition, q <- normalised q V) -> 30 MULT_A (workc <- A q[:, :M]; residuals without B) ->
+    0 DONE or 10 again.  The block arithmetic runs on the device through the stage-level entry points."""
+    from . import feast_gcontour, feast_inside_gcontour, feast_tolerance, feastdefault_
     state = state if state is not None else FeastRCIState()
     if ijob.v == RCI_INIT:
         feastdefault_(fpm)
@@ -252,10 +255,17 @@ def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0,
         state.Zne, state.Wne, state.ne, state.e, state.initialized = Z.copy(), W.copy(), len(Z), 1, True
         fpm[49], fpm[50], fpm[51], fpm[52] = 1, len(Z), 0, 1
         loop.v = 0
-        for a in (Aq, Sq, lambda_, q, res, workc):
+        user = np.array(workc[:, :M0]) if fpm[4] == 1 else None      # fpm[5]: user-provided initial subspace
+        for a in (Aq, Sq, lambda_, q, res, workc, work):
             a[...] = 0
-        state.Q0 = _seed_subspace(N, M0, True)
-        workc[:, :M0] = state.Q0
+        if user is not None:
+            for j in range(M0):
+                nrm = np.linalg.norm(user[:, j])
+                workc[:, j] = user[:, j] / nrm if nrm > 0 else _seed_subspace(N, 1, True)[:, 0]
+        else:
+            workc[:, :M0] = _seed_subspace(N, M0, True)
+        state.Q0 = np.array(workc[:, :M0], dtype=np.complex128)
+        state.extra["mult_a_for_projection"] = False
         Ze.v = complex(Z[0])
         ijob.v = RCI_FACTORIZE
         return state
@@ -263,8 +273,9 @@ def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0,
         workc[:, :M0] = state.Q0                                       # kernel/feast_kernel.jl:743-750
         ijob.v = RCI_SOLVE
         return state
+    eng = _engine(engine)
+    inside = lambda z: bool(feast_inside_gcontour(complex(z), complex(Emid), float(r), fpm))
     if ijob.v == RCI_SOLVE:
-        eng = _engine(engine)
         e = state.e
         q[:, :M0] = eng.accumulate(state.Wne[e - 1], np.asarray(workc[:, :M0], dtype=np.complex128), np.asarray(q[:, :M0], dtype=np.complex128))
         state.e = e + 1
@@ -273,8 +284,86 @@ def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0,
             Ze.v = complex(state.Zne[e])
             ijob.v = RCI_FACTORIZE
             return state
-        raise NotImplementedError("feast_grci: after the contour sweep use feast_general / feast_gcsrgv (one-sided Rayleigh-Ritz on the device)")
-    raise ValueError(f"FEAST RCI kernel (General): Invalid job code ijob={ijob.v}")
+        state.e = 1
+        fpm[49] = 1
+        work[...] = 0
+        ijob.v = RCI_MULT_B                                            # caller: workc[:, :M0] <- B * q[:, :M0]
+        mode.v = M0
+        return state
+    if ijob.v == RCI_MULT_B:
+        Sq[:M0, :M0] = eng.gram(np.asarray(q[:, :M0], dtype=np.complex128), np.asarray(workc[:, :M0], dtype=np.complex128))   # q^H (B q)
+        workc[...] = 0
+        ijob.v = RCI_MULT_A                                            # caller: workc[:, :M0] <- A * q[:, :M0]
+        mode.v = M0
+        state.extra["mult_a_for_projection"] = True
+        return state
+    if ijob.v == RCI_MULT_A:
+        if state.extra.get("mult_a_for_projection"):
+            state.extra["mult_a_for_projection"] = False
+            Aq[:M0, :M0] = eng.gram(np.asarray(q[:, :M0], dtype=np.complex128), np.asarray(workc[:, :M0], dtype=np.complex128))  # q^H (A q)
+            try:
+                lam_red, V = eng.eig_general(np.asarray(Aq[:M0, :M0], dtype=np.complex128), np.asarray(Sq[:M0, :M0], dtype=np.complex128))
+            except Exception as err:                                   # kernel/feast_kernel.jl:885-891 catch
+                state.extra["error"] = str(err)
+                info.v = ERR_LAPACK
+                ijob.v = RCI_DONE
+                fpm[52] = 0
+                state.initialized = False
+                return state
+            flags = [bool(np.isfinite(z)) and inside(z) for z in lam_red]
+            perm = [i for i in range(M0) if flags[i]] + [i for i in range(M0) if not flags[i]]
+            M = sum(flags)
+            fpm[51] = M
+            state.M = M
+            if M == 0:
+                info.v = ERR_NO_CONV
+                ijob.v = RCI_DONE
+                fpm[52] = 0
+                state.initialized = False
+                return state
+            X = eng.rowtransform(np.asarray(q[:, :M0], dtype=np.complex128), np.asarray(V, dtype=np.complex128))[:, perm]   # q V, all M0
+            nrm2 = np.real(np.diag(eng.gram(X, X)))
+            scale = np.where(nrm2 > 0, 1.0 / np.sqrt(np.where(nrm2 > 0, nrm2, 1.0)), 1.0)
+            q[:, :M0] = eng.rowtransform(X, np.diag(scale).astype(np.complex128))                   # unit 2-norm columns
+            lambda_[:M0] = np.asarray(lam_red)[perm]
+            workc[...] = 0
+            ijob.v = RCI_MULT_A                                        # caller: workc[:, :M] <- A * q[:, :M] (residuals)
+            mode.v = M
+            return state
+        M = fpm[51]
+        Lq = eng.rowtransform(np.asarray(q[:, :M], dtype=np.complex128), np.diag(lambda_[:M]).astype(np.complex128))
+        R = eng.accumulate(-1.0, Lq, np.asarray(workc[:, :M], dtype=np.complex128))
+        nrm2 = np.real(np.diag(eng.gram(R, R)))
+        res[:M] = np.sqrt(np.maximum(nrm2, 0.0)) / np.maximum(np.abs(lambda_[:M]), 1.0)      # B is not part of it (:900-906)
+        epsout.v = float(res[:M].max())
+        if epsout.v <= feast_tolerance(fpm) or loop.v >= fpm[3]:
+            order = np.argsort(np.abs(lambda_[:M]), kind="stable")                            # feast_sort_general!: by |lambda|
+            lambda_[:M] = lambda_[:M][order]
+            q[:, :M] = q[:, :M][:, order]
+            res[:M] = res[:M][order]
+            mode.v = M
+            ijob.v = RCI_DONE
+            fpm[52] = 0
+            state.initialized = False
+            return state
+        loop.v += 1
+        state.Q0 = np.array(q[:, :M0], dtype=np.complex128)
+        Aq[...] = 0
+        Sq[...] = 0
+        q[...] = 0
+        workc[:, :M0] = state.Q0
+        Z, W = feast_gcontour(complex(Emid), float(r), fpm)
+        state.Zne, state.Wne, state.ne, state.e = Z.copy(), W.copy(), len(Z), 1
+        fpm[49] = 1
+        Ze.v = complex(Z[0])
+        ijob.v = RCI_FACTORIZE
+        return state
+    if ijob.v == RCI_DONE:
+        state.initialized = False
+        return state
+    state.initialized = False
+    raise ValueError(f"FEAST RCI kernel (General): Invalid job code ijob={ijob.v}. Expected: -1 (init), 10 (factorize), 11 (solve), "
+                     "40 (mult_b), 30 (mult_a), or 0 (done)")
 
 
 # parallel alias of the real RCI kernel: interfaces/feast_precision_aliases.jl + parallel/feast_parallel_rci.jl:47-266

@@ -1,0 +1,147 @@
+"""CPU tests of the reverse-communication state machines' HOST logic (feastcuda/rci.py) with a NumPy stand-in for the engine's
+stage-level entry points (accumulate / gram / rowtransform / eig_general are GPU-tested one by one in tests/test_gpu_stages.py
+and driven through the real engine in tests/test_gpu_solve.py).  The stand-in lives here, in test code: it checks the job-code
+sequencing, the Ref/fpm bookkeeping and the arithmetic order of kernel/feast_kernel.jl, not the device kernels."""
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import feast_oracle as fo
+
+
+class NumpyStages:
+    """What the four stage calls compute, in NumPy (reference arithmetic: kernel/feast_kernel.jl:143-187, 766-845)."""
+
+    def accumulate(self, w, Y, Q):
+        return Q + w * Y
+
+    def gram(self, X, Y):
+        return X.conj().T @ Y
+
+    def rowtransform(self, X, T):
+        return X @ T
+
+    def eig_general(self, S, B=None):
+        lam, V = sla.eig(S) if B is None else sla.eig(S, B)
+        V = V / np.linalg.norm(V, axis=0)
+        return lam, V
+
+
+def _drive_general(A, B, Emid, r, M0, fpm=None, maxiter=2000):
+    """The caller's side of feast_grci!: sparse LU per node (factorize), block solves, B q and A q products."""
+    import feastcuda as fc
+    N = A.shape[0]
+    Bm = sp.identity(N, dtype=complex, format="csc") if B is None else sp.csc_matrix(B, dtype=complex)
+    Am = sp.csc_matrix(A, dtype=complex)
+    ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
+    work, workc = np.zeros((N, M0)), np.zeros((N, M0), dtype=complex)
+    Aq, Sq = np.zeros((M0, M0), dtype=complex), np.zeros((M0, M0), dtype=complex)
+    lam, q, res = np.zeros(M0, dtype=complex), np.zeros((N, M0), dtype=complex), np.zeros(M0)
+    fpm = fc.feastinit() if fpm is None else fpm
+    state = fc.FeastRCIState()
+    eng = NumpyStages()
+    lu, jobs = None, []
+    for _ in range(maxiter):
+        fc.feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, eps, loop, Emid, r, M0, lam, q, mode, res, info, state=state, engine=eng)
+        jobs.append(ijob.v)
+        if ijob.v == 10:
+            lu = spla.splu((Ze.v * Bm - Am).tocsc())
+        elif ijob.v == 11:
+            workc[:, :M0] = lu.solve(np.asarray(Bm @ workc[:, :M0]))
+        elif ijob.v == 40:
+            workc[:, :mode.v] = Bm @ q[:, :mode.v]
+        elif ijob.v == 30:
+            workc[:, :mode.v] = Am @ q[:, :mode.v]
+        elif ijob.v == 0:
+            break
+    return lam[:mode.v].copy(), q[:, :mode.v].copy(), res[:mode.v].copy(), info.v, loop.v, eps.v, jobs, state
+
+
+def test_grci_full_loop_matches_lapack_and_the_oracle():
+    """feast_grci! (kernel/feast_kernel.jl:646-962) driven to convergence on a non-Hermitian pencil: job sequence
+    10,11 (x ne), 40, 30, 30, then 0 or 10 again; eigenvalues inside the circle against LAPACK and the oracle's feast_general."""
+    rng = np.random.default_rng(2)
+    n, M0 = 60, 12
+    d = np.linspace(-1.0, 3.0, n) + 0.3j * np.sin(np.arange(n))
+    A = np.diag(d) + 0.02 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    B = np.diag(1.0 + 0.1 * rng.random(n)).astype(complex)
+    Emid, r = 0.4 + 0.1j, 0.33
+    fpm0 = fo.feastdefault(fo.feastinit())
+    for Bm in (None, B):
+        w = sla.eigvals(A) if Bm is None else sla.eigvals(A, Bm)
+        want = [x for x in w if fo.feast_inside_gcontour(x, Emid, r, fpm0)]
+        assert 3 <= len(want) <= M0 - 2
+        lam, q, res, info, loops, eps, jobs, st = _drive_general(A, Bm, Emid, r, M0)
+        assert info == 0 and len(lam) == len(want)
+        for x in lam:
+            assert min(abs(x - y) for y in want) < 1e-9
+        assert np.all(np.diff(np.abs(lam)) >= -1e-15)                      # feast_sort_general!: ascending |lambda|
+        Bq = q if Bm is None else Bm @ q
+        for j in range(len(lam)):
+            assert np.linalg.norm(A @ q[:, j] - lam[j] * Bq[:, j]) < 1e-9 * max(1.0, abs(lam[j]))
+            assert abs(np.linalg.norm(q[:, j]) - 1.0) < 1e-12
+        ne = 16
+        first = jobs[:2 * ne + 3]
+        assert first == [10, 11] * ne + [40, 30, 30]
+        assert jobs[-1] == 0 and not st.initialized
+        ro = fo.feast_general(A, Bm, Emid, r, M0, fo.feastinit())
+        assert ro.M == len(lam)
+
+
+def test_grci_argument_codes_and_empty_contour():
+    import feastcuda as fc
+    N, M0 = 8, 3
+    mk = lambda: (np.zeros((N, M0)), np.zeros((N, M0), dtype=complex), np.zeros((M0, M0), dtype=complex), np.zeros((M0, M0), dtype=complex),
+                  np.zeros(M0, dtype=complex), np.zeros((N, M0), dtype=complex), np.zeros(M0))
+    for args, code in (((0j, 0.0), 4), ((0j, -1.0), 4)):
+        work, workc, Aq, Sq, lam, q, res = mk()
+        info = fc.Ref(-1)
+        fc.feast_grci(fc.Ref(-1), N, fc.Ref(0j), work, workc, Aq, Sq, fc.feastinit(), fc.Ref(0.0), fc.Ref(0), args[0], args[1], M0, lam, q,
+                      fc.Ref(0), res, info)
+        assert info.v == code                                              # Feast_ERROR_EMID_R
+    # a contour that holds no eigenvalue ends with info = 5 (Feast_ERROR_NO_CONVERGENCE) after the first projection
+    A = np.diag(np.arange(1.0, N + 1)).astype(complex)
+    lam, q, res, info, loops, eps, jobs, st = _drive_general(A, None, 20.0 + 0j, 0.5, M0)
+    assert info == 5 and st.M == 0 and jobs[-1] == 0 and not st.initialized
+
+
+def test_srci_logic_with_the_stand_in_engine():
+    """feast_srci! host logic on CPU: the same drive as tests/test_gpu_solve.py::test_rci_state_machines_drive_a_full_solve with the
+    NumPy stand-in -- rank-deficient moment matrices (M0 = 8, four eigenvalues inside) included."""
+    import feastcuda as fc
+    L1 = fo.laplacian_1d(10).tocsc()
+    N, M0, Emin, Emax = 10, 8, 0.1, 1.9
+
+    class Stages(NumpyStages):
+        def eig_general(self, S, B=None):
+            # rank-revealing like feastcuda_eig_general: eigenpairs on the numerical range of B, the rest +inf
+            U, sv, Vh = np.linalg.svd(B)
+            k = int((sv > 1e-13 * sv[0]).sum())
+            lam = np.full(S.shape[0], np.inf, dtype=complex)
+            V = np.zeros_like(S, dtype=complex)
+            l, y = sla.eig(U[:, :k].conj().T @ S @ Vh[:k].conj().T, np.diag(sv[:k]).astype(complex))
+            lam[:k] = l
+            V[:, :k] = Vh[:k].conj().T @ y
+            V[:, k:] = Vh[k:].conj().T
+            return lam, V / np.linalg.norm(V, axis=0)
+
+    ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
+    work, workc = np.zeros((N, M0)), np.zeros((N, M0), dtype=complex)
+    Aq, Sq = np.zeros((M0, M0)), np.zeros((M0, M0))
+    lam, q, res = np.zeros(M0), np.zeros((N, M0)), np.zeros(M0)
+    fpm, state, eng, z = fc.feastinit(), fc.FeastRCIState(), Stages(), 0j
+    Ad = L1.toarray().astype(complex)
+    for _ in range(400):
+        fc.feast_srci(ijob, N, Ze, work, workc, Aq, Sq, fpm, eps, loop, Emin, Emax, M0, lam, q, mode, res, info, state=state, engine=eng)
+        if ijob.v == 10:
+            z = Ze.v
+        elif ijob.v == 11:
+            workc[:, :M0] = np.linalg.solve(z * np.eye(N) - Ad, work[:, :M0].astype(complex))
+        elif ijob.v == 30:
+            work[:, :mode.v] = (Ad @ q[:, :mode.v]).real
+        elif ijob.v == 0:
+            break
+    w = np.linalg.eigvalsh(L1.toarray())
+    want = w[(w >= Emin) & (w <= Emax)]
+    assert info.v == 0 and mode.v == len(want) and np.allclose(lam[:mode.v], want, atol=1e-9) and res[:mode.v].max() < 1e-10

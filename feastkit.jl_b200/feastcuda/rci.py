@@ -76,7 +76,7 @@ def _seed_subspace(N, M0, complex_storage):
 
 
 def _moment_rci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state, hermitian,
-                engine):
+                engine, contour=None):
     from . import feast_contour, feast_tolerance, feastdefault_
     # srci: trial block / A*q travel in the real `work`, solutions in `workc`; hrci: everything travels in the complex `workc`
     io = workc if hermitian else work
@@ -92,7 +92,7 @@ def _moment_rci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax,
         if Emin >= Emax:
             info.v = ERR_EMIN_EMAX
             return
-        Z, W = feast_contour(Emin, Emax, fpm)
+        Z, W = _custom(contour) if contour is not None else feast_contour(Emin, Emax, fpm)
         state.Zne, state.Wne, state.ne, state.e, state.initialized = Z.copy(), W.copy(), len(Z), 1, True
         fpm[49], fpm[50], fpm[51], fpm[52] = 1, len(Z), 0, 1          # fpm[50..53] (1-based): node counter, ne, M, initialised
         loop.v = 0
@@ -216,22 +216,35 @@ def _moment_rci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax,
                      "30 (mult_a), or 0 (done)")
 
 
-def feast_srci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state=None, engine=None):
+def _custom(contour):
+    """(Zne, Wne) of a custom-contour call (with_custom_contour, kernel/feast_kernel.jl:294-336)."""
+    Z, W = np.asarray(contour[0], dtype=np.complex128), np.asarray(contour[1], dtype=np.complex128)
+    if Z.ndim != 1 or Z.shape != W.shape or len(Z) == 0:
+        raise ValueError("custom contour: Zne and Wne must be non-empty vectors of equal length")
+    return Z, W
+
+
+def feast_srci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state=None, engine=None,
+               contour=None):
     """feast_srci!(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda, q, mode, res, info; state)
     -- kernel/feast_kernel.jl:7-293 (real symmetric)."""
     state = state if state is not None else FeastRCIState()
-    _moment_rci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state, False, engine)
+    _moment_rci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state, False, engine,
+                contour)
     return state
 
 
-def feast_hrci(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state=None, engine=None):
+def feast_hrci(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state=None, engine=None,
+               contour=None):
     """feast_hrci! -- kernel/feast_kernel.jl:397-644 (complex Hermitian; q, zAq, zSq complex)."""
     state = state if state is not None else FeastRCIState()
-    _moment_rci(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state, True, engine)
+    _moment_rci(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, state, True, engine,
+                contour)
     return state
 
 
-def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda_, q, mode, res, info, state=None, engine=None):
+def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda_, q, mode, res, info, state=None, engine=None,
+               contour=None):
     """feast_grci!(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda, q, mode, res, info; state)
     -- kernel/feast_kernel.jl:646-962 (general one-sided variant, full contour).  Job sequence per refinement loop:
     10 FACTORIZE -> 11 SOLVE (every node: q += w_e * workc) -> 40 MULT_B (workc <- B q) -> 30 MULT_A (workc <- A q; Aq, Sq formed,
@@ -251,7 +264,7 @@ def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0,
         if r <= 0:
             info.v = ERR_EMID_R
             return state
-        Z, W = feast_gcontour(complex(Emid), float(r), fpm)
+        Z, W = _custom(contour) if contour is not None else feast_gcontour(complex(Emid), float(r), fpm)
         state.Zne, state.Wne, state.ne, state.e, state.initialized = Z.copy(), W.copy(), len(Z), 1, True
         fpm[49], fpm[50], fpm[51], fpm[52] = 1, len(Z), 0, 1
         loop.v = 0
@@ -352,7 +365,7 @@ def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0,
         Sq[...] = 0
         q[...] = 0
         workc[:, :M0] = state.Q0
-        Z, W = feast_gcontour(complex(Emid), float(r), fpm)
+        Z, W = _custom(contour) if contour is not None else feast_gcontour(complex(Emid), float(r), fpm)
         state.Zne, state.Wne, state.ne, state.e = Z.copy(), W.copy(), len(Z), 1
         fpm[49] = 1
         Ze.v = complex(Z[0])
@@ -366,7 +379,21 @@ def feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0,
                      "40 (mult_b), 30 (mult_a), or 0 (done)")
 
 
-# parallel alias of the real RCI kernel: interfaces/feast_precision_aliases.jl + parallel/feast_parallel_rci.jl:47-266
+# custom-contour forms (kernel/feast_kernel.jl:294-336): the caller's nodes and weights replace feast_contour / feast_gcontour
+def feast_srcix(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, Zne, Wne, **kw):
+    return feast_srci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, contour=(Zne, Wne), **kw)
+
+
+def feast_hrcix(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, Zne, Wne, **kw):
+    return feast_hrci(ijob, N, Ze, work, workc, zAq, zSq, fpm, epsout, loop, Emin, Emax, M0, lambda_, q, mode, res, info, contour=(Zne, Wne), **kw)
+
+
+def feast_grcix(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda_, q, mode, res, info, Zne, Wne, **kw):
+    return feast_grci(ijob, N, Ze, work, workc, Aq, Sq, fpm, epsout, loop, Emid, r, M0, lambda_, q, mode, res, info, contour=(Zne, Wne), **kw)
+
+
+# parallel alias of the real RCI kernel (interfaces/feast_precision_aliases.jl + parallel/feast_parallel_rci.jl:47-266) and the
+# solver-neutral "iterative FEAST" names (kernel/feast_kernel.jl:346-395): same state machines
 def pdfeast_srci(*a, **kw):
     return feast_srci(*a, **kw)
 
@@ -374,3 +401,6 @@ def pdfeast_srci(*a, **kw):
 dfeast_srci = feast_srci
 zfeast_hrci = feast_hrci
 zfeast_grci = feast_grci
+ifeast_srci = feast_srci
+ifeast_hrci = feast_hrci
+ifeast_grci = feast_grci

@@ -28,6 +28,22 @@ class NumpyStages:
         return lam, V
 
 
+class RankRevealingStages(NumpyStages):
+    """eig_general as feastcuda_eig_general does it for FEAST moment pencils: eigenpairs on the numerical range of B, the null
+    directions reported as +inf (LAPACK's QZ may return an arbitrary value for them)."""
+
+    def eig_general(self, S, B=None):
+        U, sv, Vh = np.linalg.svd(B)
+        k = int((sv > 1e-13 * sv[0]).sum())
+        lam = np.full(S.shape[0], np.inf, dtype=complex)
+        V = np.zeros_like(S, dtype=complex)
+        l, y = sla.eig(U[:, :k].conj().T @ S @ Vh[:k].conj().T, np.diag(sv[:k]).astype(complex))
+        lam[:k] = l
+        V[:, :k] = Vh[:k].conj().T @ y
+        V[:, k:] = Vh[k:].conj().T
+        return lam, V / np.linalg.norm(V, axis=0)
+
+
 def _drive_general(A, B, Emid, r, M0, fpm=None, maxiter=2000):
     """The caller's side of feast_grci!: sparse LU per node (factorize), block solves, B q and A q products."""
     import feastcuda as fc
@@ -113,24 +129,12 @@ def test_srci_logic_with_the_stand_in_engine():
     L1 = fo.laplacian_1d(10).tocsc()
     N, M0, Emin, Emax = 10, 8, 0.1, 1.9
 
-    class Stages(NumpyStages):
-        def eig_general(self, S, B=None):
-            # rank-revealing like feastcuda_eig_general: eigenpairs on the numerical range of B, the rest +inf
-            U, sv, Vh = np.linalg.svd(B)
-            k = int((sv > 1e-13 * sv[0]).sum())
-            lam = np.full(S.shape[0], np.inf, dtype=complex)
-            V = np.zeros_like(S, dtype=complex)
-            l, y = sla.eig(U[:, :k].conj().T @ S @ Vh[:k].conj().T, np.diag(sv[:k]).astype(complex))
-            lam[:k] = l
-            V[:, :k] = Vh[:k].conj().T @ y
-            V[:, k:] = Vh[k:].conj().T
-            return lam, V / np.linalg.norm(V, axis=0)
 
     ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
     work, workc = np.zeros((N, M0)), np.zeros((N, M0), dtype=complex)
     Aq, Sq = np.zeros((M0, M0)), np.zeros((M0, M0))
     lam, q, res = np.zeros(M0), np.zeros((N, M0)), np.zeros(M0)
-    fpm, state, eng, z = fc.feastinit(), fc.FeastRCIState(), Stages(), 0j
+    fpm, state, eng, z = fc.feastinit(), fc.FeastRCIState(), RankRevealingStages(), 0j
     Ad = L1.toarray().astype(complex)
     for _ in range(400):
         fc.feast_srci(ijob, N, Ze, work, workc, Aq, Sq, fpm, eps, loop, Emin, Emax, M0, lam, q, mode, res, info, state=state, engine=eng)
@@ -145,3 +149,69 @@ def test_srci_logic_with_the_stand_in_engine():
     w = np.linalg.eigvalsh(L1.toarray())
     want = w[(w >= Emin) & (w <= Emax)]
     assert info.v == 0 and mode.v == len(want) and np.allclose(lam[:mode.v], want, atol=1e-9) and res[:mode.v].max() < 1e-10
+
+
+def test_custom_contour_rci_names_use_the_callers_nodes():
+    """feast_srcix!/feast_grcix! (kernel/feast_kernel.jl:294-336): the caller's (Zne, Wne) replace the default quadrature -- a
+    16-node Gauss contour passed explicitly gives the state machine 16 nodes and the same eigenvalues; ifeast_* are the same
+    functions."""
+    import feastcuda as fc
+    assert fc.ifeast_srci is fc.feast_srci and fc.ifeast_hrci is fc.feast_hrci and fc.ifeast_grci is fc.feast_grci
+    N, M0, Emin, Emax = 10, 6, 0.1, 1.9
+    L1 = fo.laplacian_1d(N).toarray().astype(complex)
+    fpm16 = fo.feastinit()
+    fpm16[1] = 16
+    Z, W = fo.feast_contour(Emin, Emax, fo.feastdefault(fpm16))
+    ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
+    work, workc = np.zeros((N, M0)), np.zeros((N, M0), dtype=complex)
+    Aq, Sq = np.zeros((M0, M0)), np.zeros((M0, M0))
+    lam, q, res = np.zeros(M0), np.zeros((N, M0)), np.zeros(M0)
+    fpm, state, eng, z, nodes = fc.feastinit(), fc.FeastRCIState(), RankRevealingStages(), 0j, []
+    for _ in range(400):
+        fc.feast_srcix(ijob, N, Ze, work, workc, Aq, Sq, fpm, eps, loop, Emin, Emax, M0, lam, q, mode, res, info, Z, W, state=state, engine=eng)
+        if ijob.v == 10:
+            z = Ze.v
+            nodes.append(z)
+        elif ijob.v == 11:
+            workc[:, :M0] = np.linalg.solve(z * np.eye(N) - L1, work[:, :M0].astype(complex))
+        elif ijob.v == 30:
+            work[:, :mode.v] = (L1 @ q[:, :mode.v]).real
+        elif ijob.v == 0:
+            break
+    w = np.linalg.eigvalsh(L1.real)
+    want = w[(w >= Emin) & (w <= Emax)]
+    assert info.v == 0 and state.ne == 16 and np.allclose(nodes[:16], Z) and np.allclose(lam[:mode.v], want, atol=1e-9)
+    import pytest
+    with pytest.raises(ValueError):
+        fc.feast_srcix(fc.Ref(-1), N, fc.Ref(0j), work, workc, Aq, Sq, fc.feastinit(), fc.Ref(0.0), fc.Ref(0), Emin, Emax, M0, lam, q,
+                       fc.Ref(0), res, fc.Ref(0), Z, W[:-1])
+
+
+def test_hrci_first_sweep_reproduces_the_reference_moments():
+    """feast_hrci! (kernel/feast_kernel.jl:397-644) accumulates 2 w_e Y without a Hermitian part: after one contour sweep the
+    moments are Q0^H g(A) Q0 and Q0^H h(A) Q0 with g = sum 2w/(z-x), h = sum 2wz/(z-x) -- restated here and compared."""
+    import feastcuda as fc
+    v = np.array([0.1 + 0.2j, -0.05 + 0.1j])
+    Ah = (np.diag([2.0, 3.0, 4.0]).astype(complex) + np.diag(v, 1) + np.diag(np.conj(v), -1))
+    N = M0 = 3
+    Emin, Emax = 1.5, 4.5
+    ijob, Ze, eps, loop, mode, info = fc.Ref(-1), fc.Ref(0j), fc.Ref(0.0), fc.Ref(0), fc.Ref(0), fc.Ref(-1)
+    work, workc = np.zeros((N, M0)), np.zeros((N, M0), dtype=complex)
+    zAq, zSq = np.zeros((M0, M0), dtype=complex), np.zeros((M0, M0), dtype=complex)
+    lam, q, res = np.zeros(M0), np.zeros((N, M0), dtype=complex), np.zeros(M0)
+    fpm, state, eng, z = fc.feastinit(), fc.FeastRCIState(), NumpyStages(), 0j
+    for _ in range(100):
+        fc.feast_hrci(ijob, N, Ze, work, workc, zAq, zSq, fpm, eps, loop, Emin, Emax, M0, lam, q, mode, res, info, state=state, engine=eng)
+        if ijob.v == 10:
+            z = Ze.v
+        elif ijob.v == 11:
+            workc[:, :M0] = np.linalg.solve(z * np.eye(N) - Ah, workc[:, :M0])
+        elif ijob.v in (30, 0):
+            break
+    Z, W = fo.feast_contour(Emin, Emax, fo.feastdefault(fo.feastinit()))
+    G = sum(2 * w * np.linalg.inv(zz * np.eye(N) - Ah) for zz, w in zip(Z, W))
+    H = sum(2 * w * zz * np.linalg.inv(zz * np.eye(N) - Ah) for zz, w in zip(Z, W))
+    Q0 = state.Q0
+    assert ijob.v == 30 and np.allclose(zAq, Q0.conj().T @ G @ Q0, atol=1e-12) and np.allclose(zSq, Q0.conj().T @ H @ Q0, atol=1e-12)
+    want = np.sort(sla.eigvals(Q0.conj().T @ H @ Q0, Q0.conj().T @ G @ Q0).real)
+    assert np.allclose(np.sort(lam[:mode.v]), want[(want >= Emin) & (want <= Emax)], atol=1e-10)

@@ -226,15 +226,66 @@ def _band_pair(A, ka, B, kb, structure, dtype):
     return N, setA, setB
 
 
-def feast_sbev(A, kla, Emin, Emax, M0, fpm, **kw):
-    """feast_sbev! -- banded/feast_banded.jl:1410-1420 (real symmetric band, upper storage)."""
+def _smom_banded(N, setA, setB, Emin, Emax, M0, fpm, Q0=None, engine=None, contour=None):
+    """The reference's own route for real symmetric bands (banded/feast_banded.jl:9-186): the moment kernel feast_srci! driven
+    with one band LU per node (FACTORIZE), block solves of (Ze B - A) X = B work (SOLVE) and band mat-vecs (MULT_A), every piece
+    on the device (feastcuda_block_solve / feastcuda_apply and the stage calls inside feast_srci)."""
+    from . import FeastResult, check_feast_srci_input, feastdefault_
+    from .rci import FeastRCIState, Ref, feast_srci
+    feastdefault_(fpm)
+    check_feast_srci_input(N, M0, float(Emin), float(Emax), fpm)
+    eng = _eng(engine)
+    setA(eng)
+    if setB is not None:
+        setB(eng)
+    else:
+        eng.clear_b()
+    ijob, Ze, eps, loop, mode, info = Ref(-1), Ref(0j), Ref(0.0), Ref(0), Ref(0), Ref(-1)
+    work, workc = np.zeros((N, M0)), np.zeros((N, M0), dtype=np.complex128)
+    Aq, Sq = np.zeros((M0, M0)), np.zeros((M0, M0))
+    lam, q, res = np.zeros(M0), np.zeros((N, M0)), np.zeros(M0)
+    if Q0 is not None:                                   # fpm[5] = 1: the caller's initial subspace travels in `work`
+        fpm[4] = 1
+        work[:, :M0] = np.asarray(Q0, dtype=np.float64)
+    state, z = FeastRCIState(), 0j
+    ne = len(contour[0]) if contour is not None else int(fpm[1])
+    for _ in range((int(fpm[3]) + 2) * (2 * ne + 2) + 8):      # every refinement loop issues 2 jobs per node + MULT_A; +1 for INIT
+        feast_srci(ijob, N, Ze, work, workc, Aq, Sq, fpm, eps, loop, float(Emin), float(Emax), M0, lam, q, mode, res, info, state=state,
+                   engine=eng, contour=contour)
+        if ijob.v == 0 or (ijob.v == -1 and info.v != 0):      # DONE, or INIT refused the arguments (info = FeastError code)
+            break
+        if ijob.v == 10:
+            z = Ze.v
+        elif ijob.v == 11:
+            rhs = work[:, :M0].astype(np.complex128)
+            if setB is not None:
+                rhs = eng.apply(L.B, rhs)
+            workc[:, :M0] = eng.block_solve(z, rhs, solver="direct")[0]
+        elif ijob.v == 30:
+            work[:, :mode.v] = eng.apply(L.A, np.asarray(q[:, :mode.v], dtype=np.complex128)).real
+    M = int(state.M)
+    return FeastResult(lam[:M].copy(), q[:, :M].copy(), M, res[:M].copy(), int(info.v), float(eps.v), int(loop.v), eng.stats())
+
+
+
+
+def feast_sbev(A, kla, Emin, Emax, M0, fpm, method="hrr", **kw):
+    """feast_sbev! -- banded/feast_banded.jl:1410-1420 (real symmetric band, upper storage).  method="smom": the reference's
+    moment route through feast_srci! (see feast_sbgv)."""
     N, sA, _ = _band_pair(A, kla, None, 0, L.SYM, np.float64)
+    if method == "smom":
+        return _smom_banded(N, sA, None, Emin, Emax, M0, fpm, Q0=kw.pop("Q0", None), engine=kw.pop("engine", None), contour=kw.pop("contour", None))
     return _hermitian_solve("band", sA, None, N, Emin, Emax, M0, fpm, True, **kw)
 
 
-def feast_sbgv(A, B, kla, klb, Emin, Emax, M0, fpm, **kw):
-    """feast_sbgv! -- banded/feast_banded.jl:9-186."""
+def feast_sbgv(A, B, kla, klb, Emin, Emax, M0, fpm, method="hrr", **kw):
+    """feast_sbgv! -- banded/feast_banded.jl:9-186.  The reference drives the moment kernel feast_srci! with band LUs here;
+    method="hrr" (default) runs the engine's QR-compress + Rayleigh-Ritz loop on the same band kernels (same converged pairs,
+    residuals with B), method="smom" reproduces the reference's route step for step: feast_srci! on the stage calls, band LU
+    solves and band mat-vecs on the device, residuals ||A q - lambda q|| without B as kernel/feast_kernel.jl:250 has them."""
     N, sA, sB = _band_pair(A, kla, B, klb, L.SYM, np.float64)
+    if method == "smom":
+        return _smom_banded(N, sA, sB, Emin, Emax, M0, fpm, Q0=kw.pop("Q0", None), engine=kw.pop("engine", None), contour=kw.pop("contour", None))
     return _hermitian_solve("band", sA, sB, N, Emin, Emax, M0, fpm, True, **kw)
 
 

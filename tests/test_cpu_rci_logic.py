@@ -215,3 +215,65 @@ def test_hrci_first_sweep_reproduces_the_reference_moments():
     assert ijob.v == 30 and np.allclose(zAq, Q0.conj().T @ G @ Q0, atol=1e-12) and np.allclose(zSq, Q0.conj().T @ H @ Q0, atol=1e-12)
     want = np.sort(sla.eigvals(Q0.conj().T @ H @ Q0, Q0.conj().T @ G @ Q0).real)
     assert np.allclose(np.sort(lam[:mode.v]), want[(want >= Emin) & (want <= Emax)], atol=1e-10)
+
+
+class BandStandIn(RankRevealingStages):
+    """NumPy stand-in for the engine calls the S-MOM banded route makes (set_band / clear_b / apply / block_solve / stats)."""
+
+    def __init__(self):
+        self.ops = {}
+
+    def set_band(self, which, AB, k, structure):
+        self.ops[which] = fo.banded_to_full(np.asarray(AB, dtype=complex), k, hermitian=True)
+
+    def clear_b(self):
+        self.ops.pop(1, None)
+
+    def apply(self, which, X):
+        return self.ops[which] @ X
+
+    def block_solve(self, z, rhs, **kw):
+        n = rhs.shape[0]
+        Bm = self.ops.get(1, np.eye(n))
+        return np.linalg.solve(z * Bm - self.ops[0], rhs), None, None
+
+    def stats(self):
+        return {}
+
+
+def test_banded_smom_route_follows_the_reference_driver():
+    """feast_sbev!/feast_sbgv! the reference's way (banded/feast_banded.jl:9-186: feast_srci! + band LU per node), opt-in in the
+    mirror (method="smom"): same eigenpairs and loop count as the oracle's restatement of that driver (oracle feast_sbev -> S-MOM)."""
+    import feastcuda as fc
+    rng = np.random.default_rng(4)
+    n, k, M0 = 60, 2, 10
+    A = np.diag(np.linspace(1.0, 12.0, n))
+    for d in range(1, k + 1):
+        v = 0.1 * rng.standard_normal(n - d)
+        A += np.diag(v, d) + np.diag(v, -d)
+    w = np.linalg.eigvalsh(A)
+    Emin, Emax = 0.5 * (w[9] + w[10]), 0.5 * (w[15] + w[16])
+    AB = fo.full_to_banded(A, k)
+    Q0 = fo.seeded_subspace(n, M0, complex_storage=False)
+    r = fc.feast_sbev(AB, k, Emin, Emax, M0, fc.feastinit(), method="smom", engine=BandStandIn(), Q0=Q0)
+    ro = fo.feast_smom(A, None, Emin, Emax, M0, fo.feastinit(), Q0=Q0)
+    assert r.info == 0 and r.M == 6
+    assert np.allclose(r.lambda_, w[10:16], atol=1e-10) and r.res.max() < 1e-10
+    # M0 = 10 > 6 eigenvalues inside makes the moment pencil rank deficient: LAPACK's QZ (the reference, the oracle) then returns
+    # arbitrary values for the null directions, some inside the interval, and loses digits on the true ones (here the oracle
+    # reports M = 8 and 3.8591 for the eigenvalue 3.8617); the engine's rank-revealing reduced solve does not.
+    assert ro.info == 0 and ro.M >= r.M
+    # with M0 equal to the eigenvalue count the pencil is regular and both routes agree value for value and loop for loop
+    Q6 = fo.seeded_subspace(n, 6, complex_storage=False)
+    r6 = fc.feast_sbev(AB, k, Emin, Emax, 6, fc.feastinit(), method="smom", engine=BandStandIn(), Q0=Q6)
+    o6 = fo.feast_smom(A, None, Emin, Emax, 6, fo.feastinit(), Q0=Q6)
+    assert r6.info == o6.info == 0 and r6.M == o6.M == 6 and r6.loop == o6.loop
+    assert np.allclose(r6.lambda_, np.sort(o6.lambda_), atol=1e-10) and np.allclose(r6.lambda_, w[10:16], atol=1e-10)
+    assert fo.subspace_angle(r6.q.astype(complex), np.asarray(o6.q, dtype=complex)) < 1e-8
+    for j in range(r.M):
+        assert np.linalg.norm(A @ r.q[:, j] - r.lambda_[j] * r.q[:, j]) < 1e-9 * np.linalg.norm(r.q[:, j])
+    assert r.q.dtype == np.float64 and np.all(np.diff(r.lambda_) > 0)
+    # argument errors are FeastError codes of the RCI kernel or host-side exceptions, as in the reference
+    import pytest
+    with pytest.raises(ValueError):
+        fc.feast_sbev(AB, k, Emax, Emin, M0, fc.feastinit(), method="smom", engine=BandStandIn())

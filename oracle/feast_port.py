@@ -449,3 +449,148 @@ def time_bicgstab_sample(A, z, m, iters, seed=0):
     t0 = time.perf_counter()
     block_bicgstab(A, None, z, RHS, None, rtol=0.0, atol=0.0, maxiter=iters, max_restarts=0)
     return time.perf_counter() - t0
+
+
+# ======================================================================================================================
+# Row-sharded variant of the multi-shift Lanczos solve -- the multi-GPU scheme planned in DESIGN.md §8 (item 3), restated
+# on the CPU so that its arithmetic, its communication pattern and its parity with the single-rank solve can be tested
+# before any CUDA exists for it.  Every rank owns the rows [r0, r1) of A and of every block vector:
+#   * SpMM: the rank needs the rows of u its stored columns reference ("halo"); `exchange(local_block)` returns the block
+#     of ALL rows (an all-gather here; NVLink peer loads of the halo rows only in the CUDA design);
+#   * the two dot products of a pass-1 step become `allreduce_small` calls on m numbers; pass 2 needs none;
+#   * the Rayleigh-Ritz stage acts on local rows: Gram matrices are summed with `allreduce_small`, row transforms are local.
+# Orthonormalisation: CholQR2 through the eigen-decomposition of the Gram matrix with the rank threshold of
+# _feast_qr_compress! (core/feast_aux.jl:101-131) applied to the singular values sqrt(eig(G)).
+# ======================================================================================================================
+def _rows_orthonormalize(acc_loc, allreduce_small, n_total, rank_tol=None):
+    m = acc_loc.shape[1]
+    eps = np.finfo(np.float64).eps
+    rank_tol = math.sqrt(eps) if rank_tol is None else rank_tol
+    G = allreduce_small(acc_loc.conj().T @ acc_loc)
+    w, V = np.linalg.eigh(0.5 * (G + G.conj().T))
+    sv = np.sqrt(np.maximum(w, 0.0))
+    if not sv.max() > 0:
+        return acc_loc[:, :0].copy(), 0
+    keep = sv > max(rank_tol, eps * max(n_total, m)) * sv.max()
+    rank = int(keep.sum())
+    Q = acc_loc @ (V[:, keep] / sv[keep])
+    for _ in range(2):                                   # re-orthonormalise: CholQR2
+        G2 = allreduce_small(Q.conj().T @ Q)
+        Lc = np.linalg.cholesky(0.5 * (G2 + G2.conj().T))
+        Q = np.linalg.solve(Lc, Q.conj().T).conj().T
+    return Q, rank
+
+
+def feast_hrr_mslanczos_rows(A, Emin, Emax, M0, fpm, Q0, r0, r1, exchange, allreduce_small, inner_rel=1e-3, inner_maxiter=500,
+                             adaptive=True, verbose=False):
+    """One rank of the row-sharded solve (real symmetric A, B = I).  Returns the FeastResult with THIS rank's rows of q."""
+    N = A.shape[0]
+    fo.feastdefault(fpm)
+    fo.check_feast_srci_input(N, M0, Emin, Emax, fpm)
+    Zne, Wne = fo.feast_contour(Emin, Emax, fpm)
+    ne = len(Zne)
+    eps_tol = fo.feast_tolerance(fpm)
+    A_loc = A[r0:r1].tocsr()
+    dots = lambda X, Y: allreduce_small(np.einsum("ij,ij->j", X, Y))
+    apply_rows = lambda X_loc: A_loc @ exchange(X_loc)
+
+    def filter_rows(Q_loc, theta, target):
+        m = Q_loc.shape[1]
+        if theta is None:
+            b, F, acc = Q_loc.copy(), np.ones((ne, m), dtype=complex), np.zeros_like(Q_loc)
+        else:
+            b = apply_rows(Q_loc) - Q_loc * theta
+            F = 1.0 / (np.asarray(Zne)[:, None] - theta[None, :])
+            acc = Q_loc * np.real((2 * np.asarray(Wne)[:, None] * F).sum(axis=0))
+        # pass 1 (lanczos_pass1 with distributed dots)
+        alpha, beta = np.zeros((inner_maxiter, m)), np.zeros((inner_maxiter + 1, m))
+        beta[0] = np.sqrt(dots(b, b))
+        inv = np.where(beta[0] > 1e-290, 1.0 / np.where(beta[0] > 0, beta[0], 1.0), 0.0)
+        scale, ratio_b = np.zeros(m), np.zeros(m)
+        u_prev, u = np.zeros_like(b), b.copy()
+        d, g = np.zeros((ne, m), dtype=complex), np.zeros((ne, m), dtype=complex)
+        k = 0
+        for j in range(inner_maxiter):
+            t = apply_rows(u) * inv - ratio_b * u_prev
+            al = dots(u, t) * inv
+            alpha[j] = al
+            scale = np.maximum(scale, np.abs(al))
+            u_next = t - (al * inv) * u
+            bn = np.sqrt(dots(u_next, u_next))
+            ok = (bn > 1e-290) & (bn > 1e-13 * scale) & (inv != 0.0)
+            beta[j + 1] = np.where(ok, bn, 0.0)
+            inv_next = np.where(ok, 1.0 / np.where(bn > 0, bn, 1.0), 0.0)
+            ratio_b = np.where(ok, bn * inv, 0.0)
+            scale = np.maximum(scale, bn)
+            for e in range(ne):
+                if j == 0:
+                    d[e] = Zne[e] - al
+                    g[e] = 1.0 / d[e]
+                else:
+                    dn = (Zne[e] - al) - beta[j] ** 2 / d[e]
+                    g[e] = beta[j] * g[e] / dn
+                    d[e] = dn
+            maxres = float((beta[j + 1][None, :] * np.abs(g)).max())
+            u_prev, u, inv = u, u_next, inv_next
+            k = j + 1
+            if maxres <= target:
+                break
+        alpha, beta = alpha[:k], beta[:k + 1]
+        coef = lanczos_coefficients(alpha, beta, Zne, Wne, F)        # replicated: every rank holds the same scalars
+        # pass 2: no reductions at all
+        invb = np.where(beta > 0, 1.0 / np.where(beta > 0, beta, 1.0), 0.0)
+        u_prev, u = np.zeros_like(b), b.copy()
+        for j in range(k):
+            acc += coef[j] * u
+            if j == k - 1:
+                break
+            rb = beta[j] * invb[j - 1] if j > 0 else np.zeros(m)
+            t = apply_rows(u) * invb[j] - rb * u_prev
+            u_prev, u = u, t - (alpha[j] * invb[j]) * u
+        return acc, k
+
+    Qb = np.array(Q0[r0:r1], dtype=np.float64)
+    lam, res = np.zeros(M0), np.zeros(M0)
+    X = np.zeros((r1 - r0, M0))
+    have_ritz, active = False, M0
+    info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
+    stats = {"lz_steps": [], "exchanges": 0, "small_allreduces": 0}
+    for loop_idx in range(fpm[3] + 1):
+        loop_count = loop_idx
+        target = inner_rel
+        if adaptive and have_ritz and math.isfinite(epsout) and epsout > 0:
+            t = 2.0 * eps_tol / epsout
+            if t >= 1e-6:
+                target = min(0.1, t)
+        acc, k = filter_rows(Qb[:, :active], lam[:active].copy() if have_ritz else None, target)
+        stats["lz_steps"].append(k)
+        Qr, rank = _rows_orthonormalize(acc, allreduce_small, N)
+        if rank == 0:
+            info = fo.ERR_NO_CONV
+            break
+        Sq = allreduce_small(Qr.T @ apply_rows(Qr))
+        lam_red, v_red = np.linalg.eigh(0.5 * (Sq + Sq.T))
+        Xc = np.zeros((r1 - r0, M0), dtype=complex)
+        Xc[:, :rank] = Qr @ v_red
+        lam[:rank] = lam_red
+        M = fo.reorder_by_interval(lam, Xc, Emin, Emax, rank)
+        X = Xc.real.copy()
+        if M == 0:
+            info = fo.ERR_NO_CONV
+            break
+        X[:, :M] /= np.sqrt(dots(X[:, :M], X[:, :M]))
+        R = apply_rows(X[:, :M]) - X[:, :M] * lam[:M]
+        res[:M] = np.sqrt(dots(R, R)) / np.maximum(np.abs(lam[:M]), 1.0)
+        epsout = float(res[:M].max())
+        M_found = M
+        if verbose:
+            print(f"rows[{r0}:{r1}] loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={k}", flush=True)
+        if epsout <= eps_tol:
+            break
+        if loop_idx == fpm[3]:
+            info = fo.ERR_NO_CONV
+            break
+        active = rank
+        Qb = X[:, :active].copy()
+        have_ritz = True
+    return fo.FeastResult(lam[:M_found].copy(), X[:, :M_found].copy(), M_found, res[:M_found].copy(), info, epsout, loop_count, stats)

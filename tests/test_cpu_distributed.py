@@ -95,3 +95,76 @@ def test_world_size_2_sharded_solves_equal_single_rank(tmp_path):
     assert int(got["info_b"]) == 0 and int(got["M_b"]) == 7 and np.abs(got["lam_b"] - ev[:7]).max() < 1e-10
     assert int(got["info_m"]) == 0 and int(got["M_m"]) == 7 and np.abs(got["lam_m"] - ev[:7]).max() < 1e-10
     assert float(got["res_m"]) < 1e-12 and int(got["fp32_sweeps"]) >= 2
+
+
+def _rows_worker(rank, world, port, out):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import torch
+    import torch.distributed as dist
+    import feast_oracle as fo
+    import feast_port as fp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, M0 = 8, 13
+    n = N ** 3
+    A = fo.laplacian_3d(N).astype(float).tocsr()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[6] + ev[7])
+    Q0 = fo.seeded_subspace(n, M0, complex_storage=False)
+    bounds = [n * r // world for r in range(world + 1)]
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    counts = {"exchange": 0, "small": 0, "small_bytes": 0}
+
+    def exchange(X_loc):                    # all-gather of row blocks: the halo exchange of the CUDA design moves a subset of it
+        counts["exchange"] += 1
+        m = X_loc.shape[1]
+        parts = [torch.zeros((bounds[r + 1] - bounds[r], m), dtype=torch.float64) for r in range(world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(X_loc)))
+        return np.concatenate([p.numpy() for p in parts], axis=0)
+
+    def allreduce_small(a):
+        counts["small"] += 1
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)).copy())
+        counts["small_bytes"] += t.numel() * 8
+        dist.all_reduce(t)
+        return t.numpy()
+
+    r = fp.feast_hrr_mslanczos_rows(A, Emin, Emax, M0, fo.feastinit(), Q0, r0, r1, exchange, allreduce_small, inner_maxiter=800)
+    full_q = exchange(r.q) if r.M else np.zeros((n, 0))
+    if rank == 0:
+        np.savez(out, lam=np.sort(r.lambda_), M=r.M, info=r.info, loop=r.loop, q=full_q, steps=sum(r.stats["lz_steps"]),
+                 small=counts["small"], small_bytes=counts["small_bytes"], exchanges=counts["exchange"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_world_size_2_row_sharded_lanczos_equals_single_rank(tmp_path):
+    """The row-sharded scheme planned for the 8-GPU target: every rank owns half the rows of A and of every
+    block vector; halo rows are exchanged for each mat-vec, dot products and Gram matrices are small all-reduces, pass 2 needs no
+    reduction.  Must reproduce the single-rank solve: same M, eigenvalues, loop count, subspace; the communication per Lanczos step
+    is two m-vector all-reduces in pass 1 and none in pass 2."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import feast_oracle as fo
+    import feast_port as fp
+    out = str(tmp_path / "rows.npz")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_rows_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    N, M0 = 8, 13
+    A = fo.laplacian_3d(N).astype(float).tocsr()
+    ev = fo.laplacian_3d_eigs(N)
+    Emin, Emax = 0.0, 0.5 * (ev[6] + ev[7])
+    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
+    r1 = fp.feast_hrr_mslanczos(A, Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=800, adaptive=True)
+    assert int(got["info"]) == r1.info == 0 and int(got["M"]) == r1.M == 7 and int(got["loop"]) == r1.loop
+    assert np.abs(got["lam"] - ev[:7]).max() < 1e-10 and np.abs(got["lam"] - np.sort(r1.lambda_)).max() < 1e-11
+    assert fo.subspace_angle(got["q"].astype(complex), np.asarray(r1.q, dtype=complex)) < 1e-8
+    steps = int(got["steps"])
+    assert abs(steps - sum(r1.stats["lz_steps"])) <= 3
+    # communication budget: 2 small all-reduces per pass-1 step (+1 for ||b|| per sweep), a handful per Rayleigh-Ritz stage
+    sweeps = int(got["loop"]) + 1
+    assert int(got["small"]) <= 2 * steps + 12 * sweeps
+    assert int(got["small_bytes"]) <= (2 * steps + 4 * sweeps) * M0 * 8 + 8 * sweeps * M0 * M0 * 8

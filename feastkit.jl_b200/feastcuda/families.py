@@ -143,6 +143,8 @@ def feast_pep(A, d, Emid, r, M0, fpm, **kw):
     from . import FeastGeneralResult
     if len(A) != d + 1:
         raise ValueError("Need d+1 coefficient matrices")
+    if d < 1:
+        raise ValueError("Polynomial degree d must be at least 1")
     N = np.asarray(A[0]).shape[0]
     for Ai in A:
         if np.asarray(Ai).shape != (N, N):

@@ -468,7 +468,7 @@ inline bool host_complex_eig(int n, std::vector<zc> A, std::vector<zc>& lam, std
 // space is larger than the number of eigenvalues inside: Householder QR with column pivoting B P = Q R reveals the
 // numerical rank k; rows k.. of Q^H S P and of R carry only round-off when the null spaces of S and B coincide (the moment
 // case: both are Q0^H f(A) Q0), so the k finite eigenpairs come from the leading k x k blocks and the remaining r-k
-// directions are reported as lambda = +inf with the null-space basis vector P e_j.  A regular pencil with singular B
+// directions are reported as lambda = +inf with the coordinate vector P e_j of a pivoted-out column (V stays regular).  A regular pencil with singular B
 // (significant trailing rows of Q^H S P) eliminates them by a Schur complement instead.
 inline bool host_pencil_eig(int n, const std::vector<zc>& S, const std::vector<zc>& B, std::vector<zc>& lam, std::vector<zc>& V,
                             int* rank_out = nullptr) {

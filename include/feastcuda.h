@@ -193,7 +193,7 @@ int feastcuda_rowtransform(feastcuda_handle h, int64_t n, int64_t a, int64_t b, 
 /* eigen(A, B) of the small general reduced pencil (r <= 128; B NULL = identity): kernel/feast_kernel.jl:175,539,812
  * (LAPACK zggev in the reference).  A, B column-major complex r x r; lambda: 2*r doubles; V: r x r column-major, unit 2-norm columns.
  * A rank-deficient B (FEAST moment matrices when M0 exceeds the eigenvalue count inside) is deflated by a column-pivoted QR:
- * the null directions come back as lambda = +inf with the null-space basis vector, the finite pairs from the leading block */
+ * the remaining directions come back as lambda = +inf with the coordinate vector of a pivoted-out column (V stays regular), the finite pairs from the leading block */
 int feastcuda_eig_general(feastcuda_handle h, int64_t r, const double* A, const double* B, double* lambda, double* V);
 /* res_j = ||A x_j - lambda_j B x_j|| / max(|lambda_j|,1): dense/feast_dense.jl:309-322 */
 int feastcuda_residuals(feastcuda_handle h, int64_t m, const double* X, const double* lambda /* complex, 2*m */, double* res);

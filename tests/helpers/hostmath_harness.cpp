@@ -34,6 +34,16 @@ int hm_complex_eig(long n, const double* A, double* lambda, double* V) {
   to_colmajor(n, Vr, V);
   return 0;
 }
+// one pass of the Gram-driven orthonormalisation: G (cur x cur, column-major) -> T (cur x nout, column-major, caller allocates
+// cur x cur); out3 = {accepted, kept, dropped}
+void hm_ortho_pass(long cur, long done, const double* G, double thr_abs, double safe, double* T, long* out3) {
+  OrthoPass op = ortho_pass(from_colmajor(cur, G), (int)cur, (int)done, thr_abs, safe);
+  const long nout = op.accepted + op.kept;
+  zc* t = reinterpret_cast<zc*>(T);
+  for (long i = 0; i < cur; ++i)
+    for (long j = 0; j < nout; ++j) t[(size_t)j * cur + i] = op.T[(size_t)i * nout + j];
+  out3[0] = op.accepted; out3[1] = op.kept; out3[2] = op.dropped;
+}
 // X = M^-1 Bm (n x n right-hand sides), 0 on success
 int hm_lu_solve(long n, const double* M, const double* Bm, double* X) {
   std::vector<zc> b = from_colmajor(n, Bm);

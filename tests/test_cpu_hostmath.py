@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import scipy.linalg as sla
 
+import feast_oracle as fo
+
 ROOT = Path(__file__).resolve().parents[1]
 SRC = ROOT / "tests" / "helpers" / "hostmath_harness.cpp"
 OUT = ROOT / "tests" / "helpers" / "libhostmath_harness.so"
@@ -127,3 +129,56 @@ def test_pencil_eig_infinite_eigenvalues_and_bad_input(hm):
     assert pencil_eig(hm, S, np.zeros((6, 6)))[0] == 0                            # B = 0: every eigenvalue infinite
     S[0, 0] = np.nan
     assert pencil_eig(hm, S, B)[0] == -1                                          # non-finite input is refused
+
+
+def _orthonormalize(hm, Z, rank_tol=0.0):
+    """The engine's orthonormalize() loop (csrc/feastcuda.cu) with NumPy standing in for the device Gram / row-transform
+    kernels: Gram -> ortho_pass (host steering) -> Z <- Z T, until every kept column is accepted and the Gram is the identity."""
+    n, ncols = Z.shape
+    cur, done, thr_abs, eps = ncols, 0, -1.0, np.finfo(float).eps
+    passes = 0
+    for p in range(16):
+        G = _f(Z.conj().T @ Z)
+        passes += 1
+        if p == 0:
+            dmax = G.diagonal().real.max()
+            if not dmax > 0:
+                return Z[:, :0], 0, passes
+            thr_abs = max(rank_tol, eps * max(n, ncols)) * np.sqrt(dmax)
+        if done == cur and np.abs(G - np.eye(cur)).max() <= 1e-14:
+            break
+        T = np.zeros((cur, cur), dtype=np.complex128, order="F")
+        out3 = (C.c_long * 3)()
+        hm.hm_ortho_pass(C.c_long(cur), C.c_long(done), _ptr(G), C.c_double(thr_abs), C.c_double(1e-8), _ptr(T), out3)
+        accepted, kept = int(out3[0]), int(out3[1])
+        if accepted + kept == 0:
+            return Z[:, :0], 0, passes
+        Z = Z @ T[:, :accepted + kept]
+        done, cur = accepted, accepted + kept
+    return Z[:, :done], done, passes
+
+
+def test_gram_driven_orthonormalisation_matches_pivoted_qr(hm):
+    """K7 of the engine (_feast_qr_compress!, core/feast_aux.jl:101-131): same numerical rank and the same range as the
+    pivoted-QR restatement in the oracle, orthonormal to 1e-14 -- on a well-conditioned block, on graded columns (condition 1e10)
+    and on rank-deficient blocks including the reference's own fixture (test_allocation_helpers.jl:274-292)."""
+    rng = np.random.default_rng(11)
+    n = 300
+    blocks = {
+        "well": rng.standard_normal((n, 24)) + 1j * rng.standard_normal((n, 24)),
+        "graded": (rng.standard_normal((n, 20)) + 1j * rng.standard_normal((n, 20))) * np.logspace(0, -10, 20),
+        "deficient": (rng.standard_normal((n, 7)) + 1j * rng.standard_normal((n, 7))) @ (rng.standard_normal((7, 18)) + 0j),
+        "filtered": np.linalg.qr(rng.standard_normal((n, n)))[0][:, :30] * np.r_[np.ones(9), np.full(21, 1e-17)] @ rng.standard_normal((30, 30)),
+    }
+    src = np.array([[1.0, 2.0, 0.0, 1.0e-15], [1.0j, 2.0j, 1.0, 1.0e-15j], [0, 0, 1.0j, 0], [0, 0, 0, 0]], dtype=complex)
+    blocks["ka12"] = src
+    for name, Zb in blocks.items():
+        Zb = np.asarray(Zb, dtype=complex)
+        rank_tol = np.sqrt(np.finfo(float).eps)                                   # the reference's default threshold
+        Q, rank, passes = _orthonormalize(hm, Zb.copy(), rank_tol)
+        Qo, rank_o = fo.qr_compress(Zb, Zb.shape[1])
+        assert rank == rank_o, (name, rank, rank_o)
+        assert np.abs(Q.conj().T @ Q - np.eye(rank)).max() < 1e-13, name
+        assert fo.subspace_angle(Q, Qo) < 1e-7, name
+        assert passes <= 6, (name, passes)
+    assert _orthonormalize(hm, np.zeros((10, 3), dtype=complex))[1] == 0

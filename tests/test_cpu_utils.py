@@ -1,0 +1,79 @@
+"""CPU tests of the host-side API helpers (feastcuda/utils.py): the reference's "Performance utilities" test set
+(test/runtests.jl:1224-1246) plus the rational-filter evaluators and the custom-contour weights."""
+import io
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import feast_oracle as fo
+
+
+def test_performance_utilities_like_the_reference_testset():
+    import feastcuda as fc
+    buf = io.StringIO()
+    assert fc.feast_memory_estimate(50, 8, np.float64, io=buf) == 50 * 8 * 8 + 50 * 8 * 16 + 2 * 64 * 8 + (50 * 8 + 16) * 8
+    assert "Total estimate" in buf.getvalue()
+    assert fc.feast_memory_estimate(10 ** 6, 64, device=True, io=io.StringIO()) == 12 * 10 ** 6 * 64 * 16
+    A = np.diag([1.0, 2.0, 3.0, 4.0])
+    lo, hi = fc.feast_validate_interval(A, (1.5, 3.5))
+    assert lo <= hi and (lo, hi) == (1.0, 4.0)
+    L1 = fo.laplacian_1d(6)
+    assert fc.feast_validate_interval(sp.csc_matrix(L1), (0.5, 1.0)) == (0.0, 4.0)
+    with pytest.raises(ValueError):
+        fc.feast_validate_interval(A, (2.0, 1.0))
+    with pytest.warns(UserWarning):
+        fc.feast_validate_interval(A, (10.0, 11.0))
+    res = fc.FeastResult(np.array([1.0, 2.0]), np.eye(2), 2, np.array([1e-12, 1e-12]), 0, 1e-12, 3)
+    out = io.StringIO()
+    fc.feast_summary(res, out)
+    assert "Eigenvalues found:  2" in out.getvalue() and "Success" in out.getvalue() and out.getvalue().count("residual") == 3
+
+
+def test_feast_set_defaults_and_validation():
+    import feastcuda as fc
+    fpm = fc.feastinit()
+    assert fc.feast_set_defaults(fpm, print_level=0, integration_points=16, tolerance_exp=10, max_refinement=5) is fpm
+    assert fpm[:4] == [0, 16, 10, 5]
+    for bad in (dict(print_level=2), dict(integration_points=0), dict(tolerance_exp=17), dict(max_refinement=0)):
+        with pytest.raises(ValueError):
+            fc.feast_set_defaults(fc.feastinit(), **bad)
+    with pytest.raises(ValueError):
+        fc.feast_set_defaults([0] * 10)
+
+
+def test_rational_filter_values():
+    """feast_rational / feast_rationalx (core/feast_tools.jl:483-540): ~1 inside the interval, ~0 outside, 1/2 at the end points;
+    feast_grational(x) on the full contour likewise; both argument orders of the x forms."""
+    import feastcuda as fc
+    fpm = fc.feastinit()
+    Emin, Emax = 1.0, 3.0
+    lam = np.array([0.0, 1.0, 1.5, 2.0, 2.9, 3.0, 4.0, 10.0])
+    f = fc.feast_rational(lam, Emin, Emax, fpm)
+    Z, W = fo.feast_contour(Emin, Emax, fo.feastdefault(fo.feastinit()))
+    want = np.array([2 * sum((w / (z - x)).real for z, w in zip(Z, W)) for x in lam])
+    assert np.allclose(f, want, atol=1e-14)
+    assert abs(f[3] - 1.0) < 1e-6 and abs(f[1] - 0.5) < 1e-3 and abs(f[5] - 0.5) < 1e-3 and abs(f[0]) < 0.05 and abs(f[7]) < 1e-8
+    assert np.allclose(fc.feast_rationalx(Z, W, lam), f) and np.allclose(fc.feast_rationalx(lam, Z, W), f)
+    assert fc.feast_rational_expert is fc.feast_rationalx
+    lamc = np.array([0.2 + 0.1j, 0.9j, 3.0 + 0j])
+    g = fc.feast_grational(lamc, 0j, 1.0, fc.feastinit())
+    Zg, Wg = fo.feast_gcontour(0j, 1.0, fo.feastdefault(fo.feastinit()))
+    assert np.allclose(g, [sum(w / (z - x) for z, w in zip(Zg, Wg)) for x in lamc], atol=1e-14)
+    assert abs(g[0] - 1.0) < 1e-6 and abs(g[2]) < 1e-6
+    assert np.allclose(fc.feast_grationalx(lamc, Zg, Wg), g)
+    with pytest.raises(ValueError):
+        fc.feast_rationalx(Z, W[:-1], lam)
+
+
+def test_customcontour_weights_match_the_oracle():
+    """feast_customcontour (core/feast_tools.jl:378-398): W_i = (Z_{i+1} - Z_{i-1}) / (2 ne), fpm[2] = ne."""
+    import feastcuda as fc
+    theta = 2 * np.pi * (np.arange(12) + 0.5) / 12
+    nodes = 2.0 + 1.5 * np.exp(1j * theta)
+    fpm = fc.feastinit()
+    Z, W = fc.feast_customcontour(nodes, fpm)
+    Zo, Wo = fo.feast_customcontour(nodes, fo.feastinit())
+    assert fpm[1] == 12 and np.allclose(Z, Zo) and np.allclose(W, Wo)
+    with pytest.raises(ValueError):
+        fc.feast_customcontour([], fc.feastinit())

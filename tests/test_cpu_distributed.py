@@ -14,6 +14,14 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 
 
+def _free_port():
+    """A TCP port nobody listens on right now (fixed pid-derived ports collided with other processes once in a while)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def pair_slice(active, nranks, rank):
     """Column slice owned by `rank`: contiguous column pairs (run_interval in csrc/feastcuda.cu)."""
     npairs = (active + 1) // 2
@@ -78,7 +86,7 @@ def test_world_size_2_sharded_solves_equal_single_rank(tmp_path):
     import feast_oracle as fo
     import feast_port as fp
     out = str(tmp_path / "r0.npz")
-    port = 29500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     got = np.load(out)
     N, M0 = 8, 13
@@ -150,7 +158,7 @@ def test_world_size_2_row_sharded_lanczos_equals_single_rank(tmp_path):
     import feast_oracle as fo
     import feast_port as fp
     out = str(tmp_path / "rows.npz")
-    port = 31500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_rows_worker, args=(2, port, out), nprocs=2, join=True)
     got = np.load(out)
     N, M0 = 8, 13

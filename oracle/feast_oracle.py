@@ -843,6 +843,60 @@ def feast_smom(A, B, Emin, Emax, M0, fpm, Q0=None, contour=None):
     return FeastResult(lam[:M].copy(), q[:, :M].copy(), M, res[:M].copy(), info, epsout, loop)
 
 
+def feast_hmom(A, B, Emin, Emax, M0, fpm, Q0=None, contour=None, max_sweeps=None):
+    """Complex-Hermitian moment FEAST: feast_hrci! (kernel/feast_kernel.jl:397-644) with a direct-solve driver.
+
+    Restated AS WRITTEN: the half-contour sums use 2 w_e Y without a Hermitian part (:516-524), so the moments are
+    Q0^H g(A) Q0 and Q0^H h(A) Q0 with the complex g(x) = sum 2w/(z-x), h(x) = sum 2wz/(z-x) = c + x g(x), c = sum 2w; the Ritz
+    values real(eig(zSq, zAq)) equal x + Re(c / g(x)) -- exact only at the centre of the interval.  The reference has no internal
+    caller and tests only the INIT handshake of this routine.  Returns (FeastResult, zAq, zSq of the last sweep)."""
+    N = A.shape[0]
+    feastdefault(fpm)
+    Zne, Wne = contour if contour is not None else feast_contour(Emin, Emax, fpm)
+    ne = len(Zne)
+    Q0 = seeded_subspace(N, M0) if Q0 is None else np.array(Q0, dtype=np.complex128)
+    Ac = A.astype(np.complex128)
+    Bc = None if B is None else B.astype(np.complex128)
+    fac = [None] * ne
+    lam, q, res = np.zeros(M0), np.zeros((N, M0), dtype=np.complex128), np.zeros(M0)
+    eps_tol, maxloop = feast_tolerance(fpm), fpm[3]
+    info, epsout, loop, M, sweeps = SUCCESS, 0.0, 0, 0, 0
+    zAq = zSq = None
+    while True:
+        Q_proj = np.zeros((N, M0), dtype=np.complex128)
+        zAq = np.zeros((M0, M0), dtype=np.complex128)
+        zSq = np.zeros((M0, M0), dtype=np.complex128)
+        rhs = Q0 if Bc is None else Bc @ Q0
+        for e in range(ne):
+            if fac[e] is None:
+                fac[e] = _factor(Ac, Bc, Zne[e])
+            Y = _solve_factor(fac[e], rhs)
+            w = 2 * Wne[e]
+            Q_proj += w * Y
+            mom = Q0.conj().T @ Y
+            zAq += w * mom
+            zSq += w * Zne[e] * mom
+        sweeps += 1
+        wv, V = sla.eig(zSq, zAq)
+        lam[:] = wv.real
+        q[:, :] = Q_proj @ V
+        M = reorder_by_interval(lam, q, Emin, Emax, M0)
+        if M == 0:
+            info = ERR_NO_CONV
+            break
+        for j in range(M):
+            rv = (Ac @ q[:, j]) - lam[j] * q[:, j]
+            res[j] = np.linalg.norm(rv) / max(abs(lam[j]), 1.0)
+        epsout = float(res[:M].max())
+        if epsout <= eps_tol or loop >= maxloop or (max_sweeps is not None and sweeps >= max_sweeps):
+            if max_sweeps is None or sweeps < max_sweeps:
+                feast_sort(lam, q, res, M)
+            break
+        loop += 1
+        Q0 = q[:, :M0].copy()
+    return FeastResult(lam[:M].copy(), q[:, :M].copy(), M, res[:M].copy(), info, epsout, loop), zAq, zSq
+
+
 def feast_sbgv(AB, BB, kla, klb, Emin, Emax, M0, fpm, **kw):
     """banded/feast_banded.jl:9-186: real symmetric banded generalized via S-MOM."""
     A = banded_to_full(np.asarray(AB, dtype=float), kla, hermitian=False)

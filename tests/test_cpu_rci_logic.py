@@ -215,6 +215,14 @@ def test_hrci_first_sweep_reproduces_the_reference_moments():
     assert ijob.v == 30 and np.allclose(zAq, Q0.conj().T @ G @ Q0, atol=1e-12) and np.allclose(zSq, Q0.conj().T @ H @ Q0, atol=1e-12)
     want = np.sort(sla.eigvals(Q0.conj().T @ H @ Q0, Q0.conj().T @ G @ Q0).real)
     assert np.allclose(np.sort(lam[:mode.v]), want[(want >= Emin) & (want <= Emax)], atol=1e-10)
+    # the oracle's restatement of the whole routine (feast_hmom) gives the same first sweep from the same Q0
+    ro, oAq, oSq = fo.feast_hmom(Ah, None, Emin, Emax, M0, fo.feastinit(), Q0=Q0, max_sweeps=1)
+    assert np.allclose(oAq, zAq, atol=1e-12) and np.allclose(oSq, zSq, atol=1e-12) and ro.M == mode.v
+    assert np.allclose(np.sort(ro.lambda_), np.sort(lam[:mode.v]), atol=1e-10)
+    # ... and documents the defect: only the eigenvalue at the centre of the interval (3.0 here) comes out right
+    exact = np.linalg.eigvalsh(Ah)
+    errs = np.abs(np.sort(ro.lambda_) - exact)
+    assert errs[1] < 0.05 and errs[0] > 0.1 and errs[2] > 0.1
 
 
 class BandStandIn(RankRevealingStages):

@@ -190,12 +190,13 @@ _A32_CACHE = {}
 
 
 def _narrow_operator(A):
-    """FP32 copy of the operator's entries (k_lz32_vals), cached per matrix object."""
-    key = id(A)
-    if key not in _A32_CACHE:
-        _A32_CACHE.clear()
-        _A32_CACHE[key] = A.astype(np.float32)
-    return _A32_CACHE[key]
+    """FP32 copy of the operator's entries (k_lz32_vals), cached for the LAST matrix object (the entry keeps a reference to
+    it: an id() alone can be reused by a different matrix after garbage collection)."""
+    ent = _A32_CACHE.get("last")
+    if ent is None or ent[0] is not A:
+        ent = (A, A.astype(np.float32))
+        _A32_CACHE["last"] = ent
+    return ent[1]
 
 
 def lanczos_pass1(A, b, Zne, kmax, target, mixed=False):
@@ -585,6 +586,179 @@ def feast_hrr_mslanczos_rows(A, Emin, Emax, M0, fpm, Q0, r0, r1, exchange, allre
         M_found = M
         if verbose:
             print(f"rows[{r0}:{r1}] loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={k}", flush=True)
+        if epsout <= eps_tol:
+            break
+        if loop_idx == fpm[3]:
+            info = fo.ERR_NO_CONV
+            break
+        active = rank
+        Qb = X[:, :active].copy()
+        have_ritz = True
+    return fo.FeastResult(lam[:M_found].copy(), X[:, :M_found].copy(), M_found, res[:M_found].copy(), info, epsout, loop_count, stats)
+
+
+# ======================================================================================================================
+# Generalized Hermitian problems A x = lambda B x (B Hermitian positive definite) with the multi-shift Lanczos filter --
+# the design for BASELINE configs[3], restated on the CPU before any CUDA exists for it.
+# C = B^-1 A is self-adjoint in the B-inner product <x, y>_B = x^H B y, and (z B - A)^-1 B q = (z I - C)^-1 q, so ONE Lanczos
+# recurrence in that inner product serves every node exactly as in the standard case: T_k is real, the true filter
+# rho(C) q = V_k rho(T_k) e_1 ||q||_B has real coefficients, no adjoint solves are needed.  A step costs one product with A
+# and one solve with B (mass matrices are well conditioned: Jacobi-preconditioned CG, a fixed and small number of products
+# with B); the B-images p_j = B v_j ride along so that no extra product with B is needed for the norms:
+#     r = A v_j - alpha_j p_j - beta_j p_{j-1},   w = B^-1 r,   beta_{j+1}^2 = w^H r,   v_{j+1} = w / beta_{j+1},   p_{j+1} = r / beta_{j+1}
+# with alpha_j = Re(v_j^H A v_j).  Pass 2 replays the recurrence (deterministic inner solves) and accumulates Q += c_j v_j.
+# ======================================================================================================================
+def jacobi_pcg(B, R, tol=1e-14, maxiter=200, stats=None):
+    """Lock-step block CG with Jacobi preconditioning for B X = R (B Hermitian positive definite), every column to
+    ||r|| <= tol ||r0||; deterministic (pass 2 of the filter replays it)."""
+    dinv = 1.0 / np.real(B.diagonal())
+    X = np.zeros_like(R)
+    r = R.copy()
+    z = r * dinv[:, None]
+    p = z.copy()
+    rz = np.einsum("ij,ij->j", r.conj(), z).real
+    r0 = np.linalg.norm(r, axis=0)
+    it = 0
+    for it in range(1, maxiter + 1):
+        Bp = B @ p
+        pBp = np.einsum("ij,ij->j", p.conj(), Bp).real
+        a = np.where(pBp > 0, rz / np.where(pBp > 0, pBp, 1.0), 0.0)
+        X += a * p
+        r -= a * Bp
+        if np.all(np.linalg.norm(r, axis=0) <= tol * np.maximum(r0, 1e-300)):
+            break
+        z = r * dinv[:, None]
+        rz_new = np.einsum("ij,ij->j", r.conj(), z).real
+        p = z + np.where(rz > 0, rz_new / np.where(rz > 0, rz, 1.0), 0.0) * p
+        rz = rz_new
+    if stats is not None:
+        stats["pcg_iters"].append(it)
+    return X
+
+
+def mslanczos_filter_gen(A, B, Q, theta, Zne, Wne, target, kmax, stats=None, inner_tol=1e-14):
+    """sum_e Herm_B-part of 2 w_e (z_e B - A)^-1 B q for the block Q (complex Hermitian pencil, B HPD); theta = Ritz values or None."""
+    n, m = Q.shape
+    ne = len(Zne)
+    solveB = lambda R: jacobi_pcg(B, R, inner_tol, stats=stats)
+    if theta is None:
+        b, F, acc = Q.astype(complex), np.ones((ne, m), dtype=complex), np.zeros((n, m), dtype=complex)
+    else:
+        b = solveB(A @ Q - (B @ Q) * theta)                               # C q - theta q
+        F = 1.0 / (np.asarray(Zne)[:, None] - theta[None, :])
+        acc = Q * np.real((2 * np.asarray(Wne)[:, None] * F).sum(axis=0))
+    pb = B @ b
+    beta0 = np.sqrt(np.maximum(np.einsum("ij,ij->j", b.conj(), pb).real, 0.0))
+    inv0 = np.where(beta0 > 1e-290, 1.0 / np.where(beta0 > 0, beta0, 1.0), 0.0)
+
+    def run(k_fixed=None, alpha=None, beta=None, coef=None, out=None):
+        al_l, be_l = [], [beta0]
+        v, p = b * inv0, pb * inv0
+        p_prev = np.zeros_like(p)
+        bj = np.zeros(m)
+        d = np.zeros((ne, m), dtype=complex)
+        g = np.zeros((ne, m), dtype=complex)
+        scale = np.zeros(m)
+        k = 0
+        steps = kmax if k_fixed is None else k_fixed
+        for j in range(steps):
+            if out is not None:
+                out += coef[j] * v
+                if j == steps - 1:
+                    break
+            Av = A @ v
+            if alpha is None:
+                al = np.einsum("ij,ij->j", v.conj(), Av).real
+            else:
+                al = alpha[j]
+            r = Av - al * p - bj * p_prev
+            w = solveB(r)
+            if beta is None:
+                bn2 = np.einsum("ij,ij->j", w.conj(), r).real
+                bn = np.sqrt(np.maximum(bn2, 0.0))
+                scale = np.maximum(scale, np.maximum(np.abs(al), bn))
+                ok = (bn > 1e-290) & (bn > 1e-13 * scale)
+                bn = np.where(ok, bn, 0.0)
+            else:
+                bn = beta[j + 1]
+            invn = np.where(bn > 0, 1.0 / np.where(bn > 0, bn, 1.0), 0.0)
+            if alpha is None:
+                al_l.append(al)
+                be_l.append(bn)
+                for e in range(ne):
+                    if j == 0:
+                        d[e] = Zne[e] - al
+                        g[e] = 1.0 / d[e]
+                    else:
+                        dn = (Zne[e] - al) - bj ** 2 / d[e]
+                        g[e] = bj * g[e] / dn
+                        d[e] = dn
+                k = j + 1
+                if float((bn[None, :] * np.abs(g)).max()) <= target:
+                    break
+            p_prev, p, v, bj = p, r * invn, w * invn, bn
+        return np.array(al_l), np.array(be_l), k
+
+    alpha, beta, k = run()
+    beta_T = beta.copy()
+    beta_T[0] = beta0                                                        # lanczos_coefficients scales by ||b|| = beta[0]
+    coef = lanczos_coefficients(alpha, beta_T[:k + 1], Zne, Wne, F)
+    # lanczos_coefficients returns c_j / beta_j for UNNORMALISED vectors u_j = beta_j v_j; here the vectors are normalised
+    coef = coef * beta_T[:k]
+    run(k_fixed=k, alpha=alpha, beta=beta, coef=coef, out=acc)
+    if stats is not None:
+        stats["lz_steps"].append(k)
+    return acc
+
+
+def feast_hrr_mslanczos_gen(A, B, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_maxiter=2000, adaptive=True, verbose=False,
+                            b_solve_tol=1e-8):
+    """H-RR refinement loop for the generalized Hermitian problem with the B-inner-product multi-shift Lanczos filter.
+    b_solve_tol: relative accuracy of the inner solves with B (the recurrence tolerates 1e-6: measured 2 sweeps at every setting
+    between 1e-14 and 1e-6 on the reduced configs[3] pair, a few more Lanczos steps for the loosest)."""
+    import scipy.linalg as sla
+    N = A.shape[0]
+    fo.feastdefault(fpm)
+    fo.check_feast_srci_input(N, M0, Emin, Emax, fpm)
+    Zne, Wne = fo.feast_contour(Emin, Emax, fpm)
+    eps_tol = fo.feast_tolerance(fpm)
+    Qb = np.array(Q0, dtype=complex)
+    lam, res = np.zeros(M0), np.zeros(M0)
+    X = np.zeros((N, M0), dtype=complex)
+    have_ritz, active = False, M0
+    info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
+    stats = {"lz_steps": [], "pcg_iters": []}
+    for loop_idx in range(fpm[3] + 1):
+        loop_count = loop_idx
+        target = inner_rel
+        if adaptive and have_ritz and math.isfinite(epsout) and epsout > 0:
+            t = 2.0 * eps_tol / epsout
+            if t >= 1e-6:
+                target = min(0.1, t)
+        acc = mslanczos_filter_gen(A, B, Qb[:, :active], lam[:active].copy() if have_ritz else None, Zne, Wne, target, inner_maxiter, stats,
+                                   b_solve_tol)
+        Qr, rank = fo.qr_compress(np.ascontiguousarray(acc), active)
+        if rank == 0:
+            info = fo.ERR_NO_CONV
+            break
+        Aq = Qr.conj().T @ (A @ Qr)
+        Bq = Qr.conj().T @ (B @ Qr)
+        lam_red, v_red = sla.eigh(0.5 * (Aq + Aq.conj().T), 0.5 * (Bq + Bq.conj().T))
+        Xc = np.zeros((N, M0), dtype=complex)
+        Xc[:, :rank] = Qr @ v_red
+        lam[:rank] = lam_red
+        M = fo.reorder_by_interval(lam, Xc, Emin, Emax, rank)
+        X = Xc
+        if M == 0:
+            info = fo.ERR_NO_CONV
+            break
+        X[:, :M] /= np.linalg.norm(X[:, :M], axis=0)
+        R = A @ X[:, :M] - (B @ X[:, :M]) * lam[:M]
+        res[:M] = np.linalg.norm(R, axis=0) / np.maximum(np.abs(lam[:M]), 1.0)
+        epsout = float(res[:M].max())
+        M_found = M
+        if verbose:
+            print(f"loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={stats['lz_steps'][-1]} pcg~{int(np.mean(stats['pcg_iters'][-5:]))}", flush=True)
         if epsout <= eps_tol:
             break
         if loop_idx == fpm[3]:

@@ -5,6 +5,7 @@ from pathlib import Path
 
 import numpy as np
 import pytest
+import scipy.linalg as sla
 import scipy.sparse as sp
 
 import feast_oracle as fo
@@ -247,3 +248,38 @@ def test_ka15_complex_symmetric_pencil():
         assert r.info == 0 and r.M == len(want)
         for lam in r.lambda_:
             assert np.abs(want - lam).min() < k["atol"]
+
+
+def test_generalized_multishift_lanczos_port_on_the_reduced_config3_pair():
+    """The design for BASELINE configs[3] (complex Hermitian FEM stiffness/mass pair): one Lanczos recurrence in the B-inner
+    product serves all 16 nodes; B^-1 by Jacobi-PCG.  Same pairs as the oracle's zfeast_hcsrgv! restatement."""
+    import scipy.sparse as sp
+
+    def k1(n, h):
+        return sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) / h
+
+    def m1(n, h):
+        return h * sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]) / 6
+    dims = (7, 6, 5)
+    hs = [1.0 / (n + 1) for n in dims]
+    Ks, Ms = [k1(n, h) for n, h in zip(dims, hs)], [m1(n, h) for n, h in zip(dims, hs)]
+    K = sp.kron(sp.kron(Ks[0], Ms[1]), Ms[2]) + sp.kron(sp.kron(Ms[0], Ks[1]), Ms[2]) + sp.kron(sp.kron(Ms[0], Ms[1]), Ks[2])
+    Mass = sp.kron(sp.kron(Ms[0], Ms[1]), Ms[2])
+    n = K.shape[0]
+    D = sp.diags(np.exp(1j * np.random.default_rng(7).uniform(0, 2 * np.pi, n)))
+    A = (D @ K @ D.conj()).tocsr()
+    B = (D @ Mass @ D.conj()).tocsr()
+    A, B = ((A + A.conj().T) * 0.5).tocsr(), ((B + B.conj().T) * 0.5).tocsr()
+    w = np.sort(sla.eigh(A.toarray(), B.toarray(), eigvals_only=True))
+    want, M0 = 6, 16
+    assert w[want] - w[want - 1] > 1e-6 * w[want]
+    Emin, Emax = 0.0, 0.5 * (w[want - 1] + w[want])
+    Q0 = fo.seeded_subspace(n, M0)
+    fpm = fo.feastinit()
+    fpm[1] = 16
+    r = fp.feast_hrr_mslanczos_gen(A, B, Emin, Emax, M0, fpm, Q0)
+    ro = fo.feast_hcsrgv(A.tocsc(), B.tocsc(), Emin, Emax, M0, fo.feastinit(), Q0=Q0)
+    assert r.info == ro.info == 0 and r.M == ro.M == want
+    assert np.abs(np.sort(r.lambda_) - w[:want]).max() < 1e-10 * w[want] and r.res.max() < 1e-12
+    assert fo.subspace_angle(np.asarray(r.q), np.asarray(ro.q, dtype=complex)) < 1e-8
+    assert r.loop <= 2 and max(r.stats["pcg_iters"]) < 80

@@ -389,6 +389,7 @@ def feast_general(A, *args, M0=10, fpm=None, **kw):
     """feast_general(A, center, radius; M0, fpm) / feast_general(A, B, center, radius; ...) -- interfaces/feast_interfaces.jl:274-379."""
     import scipy.sparse as sp
     from . import feastinit
+    _select_backend(kw)
     if len(args) == 2:
         B, (center, radius) = None, args
     elif len(args) == 3:
@@ -404,11 +405,76 @@ def feast_general(A, *args, M0=10, fpm=None, **kw):
     return feast_gegv(np.asarray(A), None if B is None else np.asarray(B), center, radius, M0, fpm, **kw)
 
 
+# ---- backend keywords of the high-level API (interfaces/feast_interfaces.jl:24-58, test/test_backend_api.jl) -----------------
+_BACKENDS = ("serial", "auto", "threads", "distributed", "mpi")
+
+
+def _normalize_parallel(parallel):
+    if parallel is True:
+        return "auto"
+    if parallel is False:
+        return "serial"
+    if isinstance(parallel, str):
+        return parallel.lstrip(":")
+    raise ValueError(f"Invalid parallel option: {parallel}")
+
+
+def _normalize_backend(parallel, backend):
+    """`parallel` is the legacy keyword, `backend` its explicit replacement; both only when they agree."""
+    if backend is not None:
+        requested = str(backend).lstrip(":")
+        if parallel is not None:
+            legacy = _normalize_parallel(parallel)
+            if legacy != requested:
+                raise ValueError(f"Conflicting backend requests: backend={requested} and parallel={legacy}")
+    elif parallel is not None:
+        requested = _normalize_parallel(parallel)
+    else:
+        requested = "serial"
+    if requested not in _BACKENDS:
+        raise ValueError(f"Unknown backend: {requested}. Use :serial, :auto, :threads, :distributed, or :mpi")
+    return requested
+
+
+def _select_backend(kw):
+    """Pops backend/parallel/strict_backend/use_threads/comm from the keywords and validates them like the reference.  Every
+    accepted choice runs on the GPU engine: :serial and :auto always; :distributed / :mpi mean "all ranks of the running
+    torch.distributed job" and are refused (ArgumentError -> ValueError) when there is no such job, as the reference refuses
+    them without workers / MPI; there is no threads backend (one process drives one GPU), so an explicit :threads is refused
+    the way the reference refuses it for inputs its threaded path does not serve."""
+    backend, parallel = kw.pop("backend", None), kw.pop("parallel", None)
+    strict = bool(kw.pop("strict_backend", False))
+    kw.pop("use_threads", None)
+    kw.pop("comm", None)
+    requested = _normalize_backend(parallel, backend)
+    fallback = (not strict) and (backend in ("auto", ":auto") or (backend is None and (parallel is True or parallel in ("auto", ":auto"))))
+    if requested in ("serial", "auto"):
+        return requested
+    if requested == "threads":
+        if fallback:
+            return "serial"
+        raise ValueError("Backend :threads is not available: libfeastcuda drives one GPU per process (use :serial, :auto, or "
+                         ":distributed/:mpi under torchrun)")
+    world = 1
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size()
+    except Exception:   # noqa: BLE001
+        world = 1
+    if world <= 1:
+        if fallback:
+            return "serial"
+        raise ValueError(f"Backend :{requested} requested but no multi-process job is running (launch one process per GPU with torchrun)")
+    return requested
+
+
 # ---- high level (interfaces/feast_interfaces.jl:143-272, 381-420) ----------------------------------------
 def feast(A, *args, M0=10, fpm=None, **kw):
     """feast(A, (Emin,Emax); M0, fpm) / feast(A, B, (Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272."""
     import scipy.sparse as sp
     from . import feastinit
+    _select_backend(kw)
     if len(args) == 1:
         B, interval = None, args[0]
     elif len(args) == 2:
@@ -439,6 +505,7 @@ def feast(A, *args, M0=10, fpm=None, **kw):
 def feast_banded(A, kla, interval, B=None, klb=0, M0=10, fpm=None, **kw):
     """feast_banded(A, kla, interval; B, klb, M0, fpm) -- interfaces/feast_interfaces.jl:381-420."""
     from . import feastinit
+    _select_backend(kw)
     Emin, Emax = interval
     fpm = feastinit() if fpm is None else fpm
     A = np.array(A)

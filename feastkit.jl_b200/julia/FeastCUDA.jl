@@ -442,7 +442,25 @@ function eig_general(S::Matrix{ComplexF64}, B::Union{Nothing,Matrix{ComplexF64}}
 end
 
 # high-level feast(A[,B],(Emin,Emax); M0, fpm) -- interfaces/feast_interfaces.jl:143-272 (dispatch only)
-function feast(A::AbstractMatrix, interval::Tuple; M0::Int=10, fpm=nothing, kw...)
+# backend keywords (interfaces/feast_interfaces.jl:24-58): validated like the reference; every accepted choice runs on the GPU
+# engine (:distributed / :mpi = all ranks attached with nccl_init!; there is no threads backend: one process drives one GPU)
+function _select_backend(backend, parallel, strict_backend::Bool, nranks::Int)
+    norm(p) = p === true ? :auto : p === false ? :serial : p isa Symbol ? p : throw(ArgumentError("Invalid parallel option: $p"))
+    requested = backend !== nothing ? backend : parallel !== nothing ? norm(parallel) : :serial
+    backend !== nothing && parallel !== nothing && norm(parallel) != backend &&
+        throw(ArgumentError("Conflicting backend requests: backend=$backend and parallel=$(norm(parallel))"))
+    requested in (:serial, :auto, :threads, :distributed, :mpi) ||
+        throw(ArgumentError("Unknown backend: $requested. Use :serial, :auto, :threads, :distributed, or :mpi"))
+    fallback = !strict_backend && (backend === :auto || (backend === nothing && (parallel === true || parallel === :auto)))
+    requested in (:serial, :auto) && return requested
+    available = requested !== :threads && nranks > 1
+    available || fallback || throw(ArgumentError("Backend :$requested is not available"))
+    return available ? requested : :serial
+end
+
+function feast(A::AbstractMatrix, interval::Tuple; M0::Int=10, fpm=nothing, backend=nothing, parallel=nothing,
+               strict_backend::Bool=false, use_threads=nothing, comm=nothing, nranks::Int=1, kw...)
+    _select_backend(backend, parallel, strict_backend, nranks)
     size(A, 1) == size(A, 2) || throw(ArgumentError("Matrix must be square"))
     fpm = fpm === nothing ? feastinit() : fpm
     M0 = min(M0, size(A, 1))

@@ -77,3 +77,30 @@ def test_customcontour_weights_match_the_oracle():
     assert fpm[1] == 12 and np.allclose(Z, Zo) and np.allclose(W, Wo)
     with pytest.raises(ValueError):
         fc.feast_customcontour([], fc.feastinit())
+
+
+def test_backend_keywords_follow_the_reference_rules():
+    """test/test_backend_api.jl:25-66: `parallel` and `backend` must agree, unknown names and unavailable explicit backends are
+    ArgumentErrors (raised before any device is touched), :auto may fall back."""
+    import feastcuda as fc
+    from feastcuda.api import _normalize_backend, _select_backend
+    assert _normalize_backend(None, None) == "serial" and _normalize_backend(True, None) == "auto" and _normalize_backend(False, None) == "serial"
+    assert _normalize_backend("serial", "serial") == "serial" and _normalize_backend(None, ":mpi") == "mpi"
+    with pytest.raises(ValueError, match="Conflicting"):
+        _normalize_backend("threads", "serial")
+    with pytest.raises(ValueError, match="Unknown backend"):
+        _normalize_backend(None, "bogus")
+    A = np.diag(2.0 * np.ones(10)) - np.diag(np.ones(9), 1) - np.diag(np.ones(9), -1)
+    B = np.eye(10)
+    for bad in (dict(backend="serial", parallel="threads"), dict(backend="bogus"), dict(backend="threads"), dict(parallel="threads"),
+                dict(backend="mpi"), dict(backend="distributed")):
+        with pytest.raises(ValueError):
+            fc.feast(A, B, (0.1, 3.9), M0=10, fpm=fc.feastinit(), **bad)
+    with pytest.raises(ValueError):
+        fc.feast_general(A.astype(complex), 0j, 3.0, M0=10, fpm=fc.feastinit(), backend="threads")
+    # fallbacks: :auto, parallel=true, and a non-strict legacy request resolve to the engine without raising
+    for ok in (dict(backend="auto"), dict(parallel=True), dict(backend="serial"), dict(parallel=False)):
+        kw = dict(ok, comm=None, use_threads=None)
+        assert _select_backend(kw) in ("serial", "auto") and kw == {}
+    with pytest.raises(ValueError):
+        _select_backend(dict(backend="auto", strict_backend=True, parallel="threads"))

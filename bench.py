@@ -140,7 +140,7 @@ def config_dict(args):
     return {"workload": f"configs[2]: sparse 3D 7-point Laplacian CSR n={args.grid ** 3} Float64, M0={args.m0}, 8 Gauss nodes, "
                         f"interval (0, mid(lambda_35, lambda_36)) -> M=35, fpm[3]=12",
             "grid": args.grid, "n": args.grid ** 3, "M0": args.m0, "nodes": 8, "inner_solver": "multi-shift two-pass Lanczos",
-            "inner_rel": SOLVER_KW["inner_rel"], "parallelism": f"columns x{args.gpus}",
+            "inner_rel": SOLVER_KW["inner_rel"], "parallelism": f"{args.shard if args.gpus > 1 else 'single GPU'} x{args.gpus}",
             "l2": "inputs larger than L2 (each block vector is 512 MB, L2 is 126 MB)"}
 
 
@@ -167,10 +167,12 @@ def run_gpu(args):
     eng.set_sparse(fc.A, A, fc.SYM)
     eng.clear_b()
     eng.init_distributed()
+    shard = args.shard if world > 1 else "columns"
+    eng.set_row_sharding(shard == "rows")
     fpm = fc.feastinit()
     fc.feastdefault_(fpm)
     Z, W = fc.feast_contour(Emin, Emax, fpm)
-    opts = eng.make_opts(q0_real=True, x_real=True, shard="columns", **SOLVER_KW)
+    opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, **SOLVER_KW)
     # pinned host copies of the step's input (e2e leg)
     Q0_pinned = torch.from_numpy(Q0.T.copy()).pin_memory()   # (M0, n) C-order == (n, M0) column-major
     Q0_host = Q0_pinned.numpy().T
@@ -191,7 +193,7 @@ def run_gpu(args):
     def e2e_step():
         barrier()
         t0 = time.perf_counter()
-        r = eng.solve_interval(Emin, Emax, args.m0, list(fpm), Z, W, Q0=Q0_host, x_real=True, shard="columns", **SOLVER_KW)
+        r = eng.solve_interval(Emin, Emax, args.m0, list(fpm), Z, W, Q0=Q0_host, x_real=True, shard=shard, gather_rows=False, **SOLVER_KW)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, r
 
@@ -222,7 +224,7 @@ def run_gpu(args):
     # secondary leg, reported beside the headline and never mixed into it: the same solve with fpm[42]'s "single-precision
     # solver" (FP32 Lanczos vectors inside the FP64 refinement loop, opts.mixed)
     opts_fp64 = opts
-    opts = eng.make_opts(q0_real=True, x_real=True, shard="columns", mixed=not args.no_mixed, **SOLVER_KW)
+    opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, mixed=not args.no_mixed, **SOLVER_KW)
     mx_ms, mx_last, mx_error, st_mx, mx_step, mx_lam, mx_res = [], None, None, None, float("nan"), None, None
     try:      # the secondary leg must never cost the headline its JSON line
         if not args.no_mixed:
@@ -325,6 +327,7 @@ def main():
     ap.add_argument("--grid", type=int, default=100, help="grid points per dimension (n = grid^3)")
     ap.add_argument("--m0", type=int, default=64)
     ap.add_argument("--cpu-sample-steps", type=int, default=8)
+    ap.add_argument("--shard", default="rows", choices=["rows", "columns"], help="multi-GPU partition of the Lanczos filter (N > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mixed", action="store_true", help="skip the secondary mixed-precision leg (profiling runs)")
     args = ap.parse_args()

@@ -37,8 +37,10 @@ struct FcError : std::runtime_error {
 struct DBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;   // false: a view into the shared arena of a row-sharded run
   void ensure(size_t bytes) {
     if (bytes <= cap) return;
+    if (!owned) throw FcError(FEASTCUDA_ERR_STATE, "arena slot too small");
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -46,9 +48,10 @@ struct DBuf {
     cap = bytes;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -114,13 +117,12 @@ struct feastcuda_handle_s {
   feastcuda::DBuf blk[feastcuda::BS_COUNT];
   feastcuda::DBuf partial, partial_r, kstate, small, small2, gram_partial, stage, red_ws;
   feastcuda::DBuf lz_scal, lz_coef, lz_state;   // multi-shift Lanczos: per-step scalars, pass-2 coefficients, shift recurrences
-  // staged-gather tile plan (kernels_lanczos.cuh: k_lz_spmm_staged), built lazily per matrix and stage capacity
-  feastcuda::DBuf lzp_wmeta, lzp_run0, lzp_runs, lzp_lcol;
-  int lzp_smax = 0, lzp_ntiles = 0;
-  bool lzp_built = false, lzp_usable = false;
+  // generalized Lanczos filter: Chebyshev inner solver for B (spectral interval of D^-1 B, 1/diag(B) on the device)
+  bool cheb_ready = false, cheb_usable = false;
+  double cheb_lo = 0.0, cheb_hi = 0.0;
+  feastcuda::DBuf cheb_dinv;
   int lz_egrid_mult = 4;    // CTAs per SM of the elementwise Lanczos kernels (partial rows the scalar kernels reduce)
   int lz_paired = 1;        // pass 2 accumulates Q every second step (0: every step)
-  int lz_staged = 0;        // 1: use the staged gather where the plan allows it
   int lz_threads = 512;     // CTA size of the Lanczos SpMM (512 or 1024)
   int lz_ctas_per_sm = 2;   // persistent CTAs per SM of the Lanczos SpMM (contiguous row chunks keep the band in L1)
   int lz_tile_rows = 64;    // rows per round-robin tile of the Lanczos SpMM
@@ -152,6 +154,19 @@ struct feastcuda_handle_s {
   // multi-GPU
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // row-sharded runs (feastcuda_set_row_sharding): every rank owns a contiguous block of rows of A and of every block vector; `n` is
+  // the LOCAL row count then.  All block slots and the mailbox of the one-shot reductions live in ONE allocation (the arena), opened
+  // in every peer process by cudaIpcOpenMemHandle, so the gather kernels read halo rows straight from the owner's HBM over NVLink.
+  bool row_sharded = false;
+  int64_t n_glob = 0, row0 = 0, nloc_max = 0;
+  void* arena = nullptr;                       // local arena
+  size_t arena_bytes = 0, arena_slot_bytes = 0, arena_mbox_off = 0;
+  void* peer_arena[16] = {nullptr};            // every rank's arena as mapped in this process (peer_arena[rank] == arena)
+  feastcuda::DBuf goff;                        // pre-resolved gather offsets of A's local rows (kernels_lanczos.cuh: k_lz_resolve), two row strides cached
+  int64_t goff_rowbytes = 0, goff_rowbytes2[2] = {0, 0};
+  int goff_next = 0;
+  int64_t nnz_loc = 0;                         // stored entries of the local rows
+  unsigned long long xseq = 0;                 // sequence number of the last cross-rank exchange
 
   feastcuda_stats stats;
   std::string err;

@@ -43,6 +43,13 @@ static void check_launch(H* h) { h->stats.kernel_launches++; FC_CUDA(cudaGetLast
 
 static zd* blk(H* h, int slot) { return h->blk[slot].as<zd>(); }
 
+static void arena_allocate(H* h, int ld);
+static void fill_xchg(H* h, LzXchg& x);
+static const long long* resolve_goff(H* h, int64_t rowbytes);
+static void xbarrier(H* h);
+static void allreduce_small(H* h, double* dev, size_t count);
+static void sharded_apply(H* h, int m, const cx<double>* X, cx<double>* Y, const double* theta, std::vector<double>* norms2);
+
 static void ensure_workspace(H* h, int64_t n, int m0) {
   FC_REQUIRE(m0 >= 1 && m0 <= FC_MAXCOLS, "M0 must be in [1,128] on the GPU path");
   const int ld = std::max(m0, 1);
@@ -50,7 +57,8 @@ static void ensure_workspace(H* h, int64_t n, int m0) {
     h->ws_n = n;
     h->ws_ld = ld;
     h->have_subspace = false;
-    for (int s = 0; s < BS_COUNT; ++s) h->blk[s].ensure((size_t)n * ld * sizeof(zd));
+    if (h->row_sharded) arena_allocate(h, ld);
+    else for (int s = 0; s < BS_COUNT; ++s) h->blk[s].ensure((size_t)n * ld * sizeof(zd));
   }
   const int maxblocks = h->sms * 8;
   h->partial.ensure((size_t)3 * maxblocks * FC_MAXCOLS * sizeof(zd));
@@ -140,13 +148,66 @@ static void upload_csr(H* h, const HostCsr& src, DevCsr& dst, bool as_complex) {
   dst.uploaded = true;
 }
 
+// contiguous block of rows owned by `rank` (the rule of feastcuda_node_partition applied to rows) and the owner of a global row
+static void row_block(int64_t n, int nranks, int rank, int64_t* r0, int64_t* cnt) {
+  const int64_t base = n / nranks, rem = n % nranks;
+  *r0 = rank * base + std::min<int64_t>(rank, rem);
+  *cnt = base + (rank < rem ? 1 : 0);
+}
+
+// row-sharded upload: this rank's rows only; a column index becomes (owner << LZ_OWNER_SHIFT) | row local to the owner
+static void upload_csr_rows(H* h, const HostCsr& src, DevCsr& dst) {
+  FC_REQUIRE(!src.cplx, "row sharding: real symmetric operators only");
+  const int64_t n = src.n;
+  const int P = h->nranks;
+  int64_t r0 = 0, cnt = 0;
+  row_block(n, P, h->rank, &r0, &cnt);
+  const int64_t base = n / P, rem = n % P, bound = rem * (base + 1);
+  FC_REQUIRE(base + 1 < ((int64_t)1 << LZ_OWNER_SHIFT), "row sharding: too many rows per rank for the column encoding");
+  const int p0 = src.ptr[r0], p1 = src.ptr[r0 + cnt];
+  std::vector<int> ptr(cnt + 1), col((size_t)std::max(1, p1 - p0));
+  for (int64_t i = 0; i <= cnt; ++i) ptr[i] = src.ptr[r0 + i] - p0;
+  for (int p = p0; p < p1; ++p) {
+    const int64_t c = src.col[p];
+    int64_t owner, first;
+    if (c < bound) { owner = c / (base + 1); first = owner * (base + 1); }
+    else { owner = rem + (base > 0 ? (c - bound) / base : 0); first = bound + (owner - rem) * base; }
+    col[p - p0] = (int)(((unsigned)owner << LZ_OWNER_SHIFT) | (unsigned)(c - first));
+  }
+  dst.ptr.ensure((cnt + 1) * sizeof(int));
+  dst.col.ensure(col.size() * sizeof(int));
+  dst.val.ensure((size_t)std::max(1, p1 - p0) * sizeof(double));
+  FC_CUDA(cudaMemcpyAsync(dst.ptr.p, ptr.data(), (cnt + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(dst.col.p, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (p1 > p0) FC_CUDA(cudaMemcpyAsync(dst.val.p, src.val.data() + p0, (size_t)(p1 - p0) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  sync(h);
+  dst.uploaded = true;
+  h->nnz_loc = p1 - p0;
+  h->goff_rowbytes2[0] = h->goff_rowbytes2[1] = 0;
+}
+
 static void finalize_sparse(H* h) {
   FC_REQUIRE(h->hA.set, "operator A has not been set");
   const bool need_cplx = h->hA.cplx || (h->has_b && h->hB.cplx);
   if (need_cplx != h->dev_complex) { h->dA.uploaded = false; h->dB.uploaded = false; h->dev_complex = need_cplx; }
+  if (h->row_sharded) {
+    FC_REQUIRE(!h->has_b && !need_cplx, "row sharding serves standard real symmetric sparse problems (multi-shift Lanczos filter)");
+    int64_t r0 = 0, cnt = 0;
+    row_block(h->hA.n, h->nranks, h->rank, &r0, &cnt);
+    FC_REQUIRE(cnt >= 1, "row sharding: fewer rows than ranks");
+    h->n_glob = h->hA.n;
+    h->row0 = r0;
+    h->n = cnt;
+    h->nloc_max = h->hA.n / h->nranks + ((h->hA.n % h->nranks) ? 1 : 0);
+    if (!h->dA.uploaded) upload_csr_rows(h, h->hA, h->dA);
+    return;
+  }
   if (!h->dA.uploaded) upload_csr(h, h->hA, h->dA, need_cplx);
   if (h->has_b && !h->dB.uploaded) upload_csr(h, h->hB, h->dB, need_cplx);
   h->n = h->hA.n;
+  h->n_glob = h->hA.n;
+  h->row0 = 0;
+  h->nnz_loc = h->hA.nnz;
 }
 
 // =====================================================================================================
@@ -296,12 +357,16 @@ static void scale_cols(H* h, int m, const std::vector<zc>& f, const zd* X, zd* Y
 }
 
 // host (column-major) <-> device (row-major) staging; host buffers go through a pinned bounce buffer
+// Row-sharded runs: the host array is the GLOBAL n_glob x m block, only this rank's rows [row0, row0 + n) cross the bus.
 template <typename TIN>
 static void upload_block(H* h, int64_t n, int m, const TIN* host, zd* dst) {
   const size_t bytes = (size_t)n * m * sizeof(TIN);
   h->stage.ensure(bytes);
   Timer t;
-  FC_CUDA(cudaMemcpyAsync(h->stage.p, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  if (h->row_sharded && n == h->n)
+    FC_CUDA(cudaMemcpy2DAsync(h->stage.p, (size_t)n * sizeof(TIN), host + h->row0, (size_t)h->n_glob * sizeof(TIN), (size_t)n * sizeof(TIN),
+                              (size_t)m, cudaMemcpyHostToDevice, h->stream));
+  else FC_CUDA(cudaMemcpyAsync(h->stage.p, host, bytes, cudaMemcpyHostToDevice, h->stream));
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
   k_col2row<TIN, double><<<grid, 256, 0, h->stream>>>(n, m, n, h->ws_ld, h->stage.as<TIN>(), dst);
   check_launch(h);
@@ -317,7 +382,10 @@ static void download_block(H* h, int64_t n, int m, const zd* src, TOUT* host) {
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
   k_row2col<TOUT, double><<<grid, 256, 0, h->stream>>>(n, m, h->ws_ld, n, src, h->stage.as<TOUT>());
   check_launch(h);
-  FC_CUDA(cudaMemcpyAsync(host, h->stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (h->row_sharded && n == h->n)   // this rank's rows of the global host block; the other rows are left untouched
+    FC_CUDA(cudaMemcpy2DAsync(host + h->row0, (size_t)h->n_glob * sizeof(TOUT), h->stage.p, (size_t)n * sizeof(TOUT), (size_t)n * sizeof(TOUT),
+                              (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+  else FC_CUDA(cudaMemcpyAsync(host, h->stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
   sync(h);
   h->stats.ms_d2h += t.ms();
 }
@@ -334,6 +402,7 @@ static void gram_host(H* h, int a, int b, const zd* X, const zd* Y, std::vector<
   const int64_t len = (int64_t)a * b;
   k_sum_chunks<zd><<<(int)std::min<int64_t>((len + 255) / 256, 1024), 256, 0, h->stream>>>(len, chunks, h->gram_partial.as<zd>(), out);
   check_launch(h);
+  if (h->row_sharded) allreduce_small(h, reinterpret_cast<double*>(out), (size_t)2 * len);   // local rows -> all rows
   C.resize((size_t)len);
   FC_CUDA(cudaMemcpyAsync(C.data(), out, (size_t)len * sizeof(zd), cudaMemcpyDeviceToHost, h->stream));
   sync(h);
@@ -474,113 +543,32 @@ struct MslOut { int k = 0; double maxres = 0.0; bool converged = false; };
 
 static inline double* rblk(H* h, int slot) { return reinterpret_cast<double*>(blk(h, slot)); }
 
-static int lz_grid_spmm(H* h, int64_t n, int rows_per_step) {
+static int lz_grid_spmm(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0) {
   const int64_t tr = (int64_t)std::max(1, h->lz_tile_rows / rows_per_step) * rows_per_step;   // as in k_lz_spmm
   const int64_t ntiles = (n + tr - 1) / tr;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)h->sms * h->lz_ctas_per_sm));
-}
-
-// ---- tile plan of the staged gather: greedy tiles of <= LZS_TMAX consecutive rows whose distinct columns fit a stage -----
-static void build_lz_plan(H* h, int smax) {
-  if (h->lzp_built && h->lzp_smax == smax) return;
-  const HostCsr& A = h->hA;
-  const int64_t n = A.n;
-  std::vector<int4> wmeta, runs;
-  std::vector<int> run0{0};
-  std::vector<unsigned short> lcol((size_t)std::max<int64_t>(A.nnz, 1), 0);
-  std::vector<int> cur, tmp, rowc;
-  h->lzp_built = true;
-  h->lzp_smax = smax;
-  h->lzp_usable = false;
-  int64_t row = 0;
-  int ntiles = 0;
-  while (row < n) {
-    cur.clear();
-    int64_t r1 = row;
-    while (r1 < n && r1 - row < LZS_TMAX) {
-      rowc.assign(A.col.begin() + A.ptr[r1], A.col.begin() + A.ptr[r1 + 1]);
-      std::sort(rowc.begin(), rowc.end());
-      tmp.clear();
-      std::set_union(cur.begin(), cur.end(), rowc.begin(), rowc.end(), std::back_inserter(tmp));
-      if ((int)tmp.size() > smax) break;
-      cur.swap(tmp);
-      ++r1;
-    }
-    if (r1 == row) return;   // a single row references more vector rows than a stage holds: keep the direct kernel
-    if (cur.empty()) cur.push_back((int)row);   // rows without entries still need a non-empty stage
-    for (size_t i = 0; i < cur.size();) {
-      size_t j = i + 1;
-      while (j < cur.size() && cur[j] == cur[j - 1] + 1 && j - i < 64) ++j;
-      runs.push_back(make_int4(cur[i], (int)(j - i), (int)i, 0));
-      i = j;
-    }
-    run0.push_back((int)runs.size());
-    for (int w = 0; w < LZS_TMAX; ++w) {
-      const int64_t r = row + w;
-      if (r < r1) {
-        wmeta.push_back(make_int4((int)r, A.ptr[r], A.ptr[r + 1] - A.ptr[r], 0));
-        for (int p = A.ptr[r]; p < A.ptr[r + 1]; ++p)
-          lcol[p] = (unsigned short)(std::lower_bound(cur.begin(), cur.end(), A.col[p]) - cur.begin());
-      } else wmeta.push_back(make_int4(-1, 0, 0, 0));
-    }
-    ++ntiles;
-    row = r1;
-  }
-  h->lzp_wmeta.ensure(wmeta.size() * sizeof(int4));
-  h->lzp_run0.ensure(run0.size() * sizeof(int));
-  h->lzp_runs.ensure(runs.size() * sizeof(int4));
-  h->lzp_lcol.ensure(lcol.size() * sizeof(unsigned short));
-  FC_CUDA(cudaMemcpyAsync(h->lzp_wmeta.p, wmeta.data(), wmeta.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-  FC_CUDA(cudaMemcpyAsync(h->lzp_run0.p, run0.data(), run0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  FC_CUDA(cudaMemcpyAsync(h->lzp_runs.p, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-  FC_CUDA(cudaMemcpyAsync(h->lzp_lcol.p, lcol.data(), lcol.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
-  sync(h);
-  h->lzp_ntiles = ntiles;
-  h->lzp_usable = true;
-}
-
-template <int MODE>
-static bool lz_launch_staged(H* h, LzArgs& a, int* grid_out) {
-  const int P = (a.m + 1) / 2;
-  if (!h->lz_staged || P <= 16 || P > 32) return false;
-  const int pitch = P * 16;
-  const int smax = std::min(1024, 51200 / pitch);
-  build_lz_plan(h, smax);
-  if (!h->lzp_usable) return false;
-  const size_t smem = (size_t)2 * smax * pitch + 16;
-  static bool attr_set[4] = {false, false, false, false};
-  if (!attr_set[MODE]) {
-    FC_CUDA(cudaFuncSetAttribute(k_lz_spmm_staged<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    attr_set[MODE] = true;
-  }
-  LzPlanDev pl;
-  pl.wmeta = h->lzp_wmeta.as<int4>(); pl.t_run0 = h->lzp_run0.as<int>(); pl.runs = h->lzp_runs.as<int4>();
-  pl.lcol = h->lzp_lcol.as<unsigned short>(); pl.ntiles = h->lzp_ntiles; pl.smax = smax;
-  const int grid = std::max(1, std::min(h->lzp_ntiles, h->sms * 2));
-  *grid_out = grid;
-  k_lz_spmm_staged<MODE><<<grid, LZS_THREADS, smem, h->stream>>>(a, pl);
-  check_launch(h);
-  h->stats.spmm_launches++;
-  return true;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)h->sms * (ctas_per_sm > 0 ? ctas_per_sm : h->lz_ctas_per_sm)));
 }
 
 template <int MODE, bool CPLX>
 static void lz_launch(H* h, LzArgs& a, int* grid_out) {
-  if constexpr (MODE <= LZ_PLAIN) {   // the staged variant has no paired-accumulation modes
-    if (!CPLX && lz_launch_staged<MODE>(h, a, grid_out)) return;
-  }
   const int P = CPLX ? a.m : (a.m + 1) / 2;
   // G lanes per row, NC column-pair chunks per lane
 #define FC_LZ(G, NC)                                                                       \
   do {                                                                                     \
-    if (h->lz_threads >= 1024 && NC == 1) {                                                \
-      const int grid = lz_grid_spmm(h, a.n, 32 * (32 / G));                                \
-      *grid_out = grid;                                                                    \
-      k_lz_spmm<G, NC, MODE, 1024, CPLX><<<grid, 1024, 0, h->stream>>>(a);                 \
+    if (NC == 1 && h->lz_threads >= 1024 && a.goff == nullptr) {                                                \
+      if constexpr (NC == 1) {                                                             \
+        const int grid = lz_grid_spmm(h, a.n, 32 * (32 / G));                              \
+        *grid_out = grid;                                                                  \
+        k_lz_spmm<G, NC, MODE, 1024, CPLX><<<grid, 1024, 0, h->stream>>>(a);               \
+      }                                                                                    \
     } else {                                                                               \
-      const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G));                                \
+      const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0);               \
       *grid_out = grid;                                                                    \
-      k_lz_spmm<G, NC, MODE, 512, CPLX><<<grid, 512, 0, h->stream>>>(a);                   \
+      if (a.goff != nullptr) {                                                             \
+        if constexpr (!CPLX && NC <= 2 && MODE <= LZ_P2_PAIR)                              \
+          k_lz_spmm<G, NC, MODE, 512, CPLX, true><<<grid, 512, 0, h->stream>>>(a);         \
+        else throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "row-sharded gather: real blocks only"); \
+      } else k_lz_spmm<G, NC, MODE, 512, CPLX><<<grid, 512, 0, h->stream>>>(a);            \
     }                                                                                      \
   } while (0)
   const int Pd = P;   // lanes per row = elements per row (wider groups for narrow blocks measured slower: idle lanes still issue)
@@ -590,7 +578,11 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
   else if (Pd <= 8) FC_LZ(8, 1);
   else if (Pd <= 16) FC_LZ(16, 1);
   else if (Pd <= 32) FC_LZ(32, 1);
-  else FC_LZ(32, 2);
+  else if (Pd <= 64) FC_LZ(32, 2);
+  else if constexpr (CPLX) {   // complex blocks wider than 64 columns (real blocks: 128 columns = 64 pairs)
+    if (Pd <= 96) FC_LZ(32, 3);
+    else FC_LZ(32, 4);
+  } else throw FcError(FEASTCUDA_ERR_ARG, "Lanczos SpMM: more than 128 real columns");
 #undef FC_LZ
   check_launch(h);
   h->stats.spmm_launches++;
@@ -621,12 +613,49 @@ static void lz32_launch(H* h, LzArgs32& a, int* grid_out) {
 
 // FP32 vectors: nvec32 float blocks + nvec64 double blocks per launch
 static double lz32_bytes_spmm(H* h, int m, int nvec32, int nvec64) {
-  return (double)h->hA.nnz * 8.0 + 4.0 * (double)(h->hA.n + 1) + (double)h->hA.n * m * (4.0 * nvec32 + 8.0 * nvec64);
+  return (double)h->nnz_loc * 8.0 + 4.0 * (double)(h->n + 1) + (double)h->n * m * (4.0 * nvec32 + 8.0 * nvec64);
 }
 
 static double lz_bytes_spmm(H* h, int m, int nvec, bool cplx) {
-  const double es = cplx ? 16.0 : 8.0;
-  return (double)h->hA.nnz * (es + 4.0) + 4.0 * (double)(h->hA.n + 1) + (double)nvec * (double)h->hA.n * m * es;
+  const double es = cplx ? 16.0 : 8.0;   // a row-sharded operator carries 8-byte pre-resolved offsets instead of 4-byte column indices
+  return (double)h->nnz_loc * (es + (h->row_sharded ? 8.0 : 4.0)) + 4.0 * (double)(h->n + 1) + (double)nvec * (double)h->n * m * es;
+}
+
+// c_j = ||b|| sum_e Re(2 w_e F_e [(z_e I - T_k)^-1 e_1]_j) / beta_j for the unnormalised Lanczos vectors of every column: complex Thomas
+// solves of the shifted tridiagonals (the pivots have Im d_j >= Im z_e > 0: no pivoting needed); F_e = 1/(z_e - theta) with a Ritz start
+static void lz_host_coefficients(int k, int nc, const std::vector<double>& al, const std::vector<double>& be, bool have_ritz,
+                                 const double* theta, const zc* Zne, const zc* Wne, int ne, std::vector<double>& coef) {
+  const size_t rowsz = (size_t)FC_MAXCOLS;
+  {
+    std::vector<zc> dd(k), ff(k);
+    for (int c = 0; c < nc; ++c) {
+      const double b0 = be[c];
+      if (!(b0 > 0.0)) continue;
+      int kc = k;  // a frozen column's T ends where beta vanished
+      for (int j = 1; j < k; ++j)
+        if (be[(size_t)j * rowsz + c] == 0.0) { kc = j; break; }
+      for (int e = 0; e < ne; ++e) {
+        const zc z = Zne[e];
+        const zc F = have_ritz ? zc(1.0) / (z - theta[c]) : zc(1.0);
+        const zc wf = 2.0 * Wne[e] * F * b0;
+        dd[0] = z - al[c];
+        ff[0] = 1.0;
+        for (int j = 1; j < kc; ++j) {
+          const double bj = be[(size_t)j * rowsz + c];
+          const zc w = -bj / dd[j - 1];
+          dd[j] = (z - al[(size_t)j * rowsz + c]) + w * bj;
+          ff[j] = -w * ff[j - 1];
+        }
+        zc y = ff[kc - 1] / dd[kc - 1];
+        coef[(size_t)(kc - 1) * rowsz + c] += (wf * y).real();
+        for (int j = kc - 2; j >= 0; --j) {
+          y = (ff[j] + be[(size_t)(j + 1) * rowsz + c] * y) / dd[j];
+          coef[(size_t)j * rowsz + c] += (wf * y).real();
+        }
+      }
+      for (int j = 0; j < kc; ++j) coef[(size_t)j * rowsz + c] /= be[(size_t)j * rowsz + c];
+    }
+  }
 }
 
 template <bool CPLX>
@@ -640,7 +669,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   // the work blocks are COMPACT: row stride = the slice's own column count (in doubles: even(nc) real, 2 nc complex), so a
   // rank that owns 8 of 64 columns streams dense 64-byte rows instead of touching 64 bytes out of every 512
   // mixed precision (FP32 Lanczos vectors, real problems): 4-column elements, so every compact block is padded to a multiple of 4
-  mixed = mixed && !CPLX && !matfree && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
+  mixed = mixed && !CPLX && !matfree && !h->row_sharded && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
   const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : (mixed ? ((nc + 3) & ~3) : ((nc + 1) & ~1));
   FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   kmax = std::max(1, std::min(kmax, 16384));
@@ -673,7 +702,20 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   S.ne = ne;
   S.target = target;
   S.done_k = reinterpret_cast<int*>(d_z + ne);
+  int* ticket = S.done_k + 4;
+  FC_CUDA(cudaMemsetAsync(S.done_k, 0, 64, h->stream));
   FC_CUDA(cudaMemcpyAsync(d_z, Zne, (size_t)ne * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  // what the last CTA of a producer kernel does with the partial sums (pass 1) / the step barrier of row-sharded runs (pass 2)
+  const bool sharded = h->row_sharded;
+  auto mk_tail = [&](int kind, int j) {
+    LzTail t;
+    memset(&t, 0, sizeof(t));
+    if (matfree || kind == LZ_TAIL_NONE) return t;
+    t.kind = kind; t.j = j; t.ticket = ticket; t.s = S;
+    fill_xchg(h, t.x);
+    return t;
+  };
+  const int bar_kind = sharded ? LZ_TAIL_BARRIER : LZ_TAIL_NONE;
 
   // ---- real work blocks (each aliases a complex slot; n x ld doubles) -------------------------------------------
   double* RQ = rblk(h, BS_KS);
@@ -694,10 +736,12 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   std::vector<double> rho(nc, 0.0);
   if (mixed) FC_CUDA(cudaMemsetAsync(QA, 0, (size_t)n * (size_t)ld * sizeof(double), h->stream));   // pad columns included
   if (!have_ritz) {
-    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS);
+    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS, mk_tail(LZ_TAIL_INIT, 0));
     check_launch(h);
-    k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, egrid, FC_MAXCOLS, nc);
-    check_launch(h);
+    if (matfree) {
+      k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, egrid, FC_MAXCOLS, nc);
+      check_launch(h);
+    }
     if (!mixed) FC_CUDA(cudaMemset2DAsync(QA, (size_t)ld * sizeof(double), 0, (size_t)(2 * P) * sizeof(double), (size_t)n, h->stream));
   } else {
     // rho(theta) = Re sum_e 2 w_e / (z_e - theta): what the rational filter does to an exact eigenvector
@@ -708,14 +752,16 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     }
     FC_CUDA(cudaMemcpyAsync(d_theta, theta, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     FC_CUDA(cudaMemcpyAsync(d_rho, rho.data(), (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS);
+    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS, mk_tail(bar_kind, 0));
     check_launch(h);
     LzArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.m = nc; a.ld = ld;
     a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
-    a.U = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
+    a.U = RQ; a.prev = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
     a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
+    a.tail = mk_tail(LZ_TAIL_INIT, 0);
+    if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
     int g = 0;
     const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
     if (matfree) {
@@ -727,8 +773,10 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     } else lz_launch<LZ_RES, CPLX>(h, a, &g);
     sample_end(h, ev);
     h->stats.bytes_kern[FEASTCUDA_KERN_LZ_RES] = matfree ? 4.0 * 8.0 * (double)n * nc : lz_bytes_spmm(h, nc, 3, CPLX);
-    k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g, FC_MAXCOLS, nc);
-    check_launch(h);
+    if (matfree) {
+      k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g, FC_MAXCOLS, nc);
+      check_launch(h);
+    }
     sync(h);  // theta / rho are host buffers
   }
 
@@ -778,6 +826,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       } else if (mixed) {
         LzArgs32 a = args32(j);
         a.partial = part; a.pstride = FC_MAXCOLS; a.done = S.done_k;
+        a.tail = mk_tail(LZ_TAIL_ALPHA, j);
         lz32_launch<LZ_P1>(h, a, &g);
       } else {
         LzArgs a;
@@ -787,22 +836,28 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
         a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1);
         a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
         a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
+        a.tail = mk_tail(LZ_TAIL_ALPHA, j);
+        if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
         lz_launch<LZ_P1, CPLX>(h, a, &g);
       }
       sample_end(h, ev);
-      k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, g, FC_MAXCOLS, nc);
-      check_launch(h);
+      if (matfree) {
+        k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, g, FC_MAXCOLS, nc);
+        check_launch(h);
+      }
       ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_UPD, j) : -1;
       if (mixed)
         k_lz32_update<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, S.ratio_a + (size_t)j * rowsz, cur32(j), cur32(j + 1), part, FC_MAXCOLS,
-                                                     S.done_k);
+                                                     S.done_k, mk_tail(LZ_TAIL_BETA, j));
       else
         k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
-                                                   S.done_k);
+                                                   S.done_k, mk_tail(LZ_TAIL_BETA, j));
       check_launch(h);
       sample_end(h, ev);
-      k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, mixed ? egrid4 : egrid, FC_MAXCOLS, nc);
-      check_launch(h);
+      if (matfree) {
+        k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, egrid, FC_MAXCOLS, nc);
+        check_launch(h);
+      }
     }
     done += batch;
     FC_CUDA(cudaMemcpyAsync(flag, S.done_k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -829,36 +884,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   sync(h);
   out.k = k;
   out.maxres = mr;
-  {
-    std::vector<zc> dd(k), ff(k);
-    for (int c = 0; c < nc; ++c) {
-      const double b0 = be[c];
-      if (!(b0 > 0.0)) continue;
-      int kc = k;  // a frozen column's T ends where beta vanished
-      for (int j = 1; j < k; ++j)
-        if (be[(size_t)j * rowsz + c] == 0.0) { kc = j; break; }
-      for (int e = 0; e < ne; ++e) {
-        const zc z = Zne[e];
-        const zc F = have_ritz ? zc(1.0) / (z - theta[c]) : zc(1.0);
-        const zc wf = 2.0 * Wne[e] * F * b0;
-        dd[0] = z - al[c];
-        ff[0] = 1.0;
-        for (int j = 1; j < kc; ++j) {
-          const double bj = be[(size_t)j * rowsz + c];
-          const zc w = -bj / dd[j - 1];
-          dd[j] = (z - al[(size_t)j * rowsz + c]) + w * bj;
-          ff[j] = -w * ff[j - 1];
-        }
-        zc y = ff[kc - 1] / dd[kc - 1];
-        coef[(size_t)(kc - 1) * rowsz + c] += (wf * y).real();
-        for (int j = kc - 2; j >= 0; --j) {
-          y = (ff[j] + be[(size_t)(j + 1) * rowsz + c] * y) / dd[j];
-          coef[(size_t)j * rowsz + c] += (wf * y).real();
-        }
-      }
-      for (int j = 0; j < kc; ++j) coef[(size_t)j * rowsz + c] /= be[(size_t)j * rowsz + c];
-    }
-  }
+  lz_host_coefficients(k, nc, al, be, have_ritz, theta, Zne, Wne, ne, coef);
   double* d_coef = h->lz_coef.as<double>();
   FC_CUDA(cudaMemcpyAsync(d_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
 
@@ -866,7 +892,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   // Q is read-modify-written every SECOND step: step j holds u_j and u_{j-1} as own-row operands, so odd steps add both
   // contributions and even steps carry no Q traffic at all (the staged and matrix-free variants accumulate every step)
   Timer t2;
-  const bool paired = h->lz_paired && !matfree && !(h->lz_staged && !mixed && !CPLX);
+  const bool paired = h->lz_paired && !matfree;
   for (int j = 0; j < k; ++j) {
     if (j == k - 1) {
       for (int jj = (paired && j >= 1 && ((j - 1) & 1) == 0) ? j - 1 : j; jj <= j; ++jj) {   // a skipped even step k-2 is added here
@@ -903,6 +929,8 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
       a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
       a.tile_rows = h->lz_tile_rows;
+      a.tail = mk_tail(bar_kind, j);
+      if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
       if (q_mode == 0) lz_launch<LZ_P2, CPLX>(h, a, &g);
       else if (q_mode == 1) lz_launch<LZ_P2_SKIP, CPLX>(h, a, &g);
       else lz_launch<LZ_P2_PAIR, CPLX>(h, a, &g);
@@ -923,6 +951,330 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
 }
 
 // =====================================================================================================
+// Generalized Hermitian problems A x = lambda B x (B Hermitian positive definite) on the multi-shift Lanczos filter
+// (CPU restatement: oracle/feast_port.py:mslanczos_filter_gen_cheb).  (z B - A)^-1 B q = (z I - B^-1 A)^-1 q and B^-1 A is
+// self-adjoint in the B-inner product, so ONE recurrence in that inner product serves every node with a REAL tridiagonal, like
+// the standard case.  The inner solves with B are a FIXED Chebyshev polynomial P = p_K(D^-1 B) D^-1 (k_lz_spmm<LZ_CHEB>: no dot
+// products, no data-dependent control flow), so the recurrence is an exact Lanczos process for the neighbouring pencil
+// (A, P^-1); the images s_j = P^-1 u_j ride along (s_{j+1} is the right-hand side of the solve that produced u_{j+1}):
+//     t = A u_j / beta_j - (beta_j / beta_{j-1}) s_{j-1},   alpha_j beta_j = Re(u_j^H t)                 k_lz_spmm<LZ_P1>
+//     s_{j+1} = t - (alpha_j / beta_j) s_j                                                             k_lz_update
+//     u_{j+1} = P s_{j+1},   beta_{j+1}^2 = Re(u_{j+1}^H s_{j+1})                                      k_lz_spmm<LZ_CHEB / LZ_CHEB_DOT>
+// The per-step scalar kernels, the shifted-residual recurrences and the host-side tridiagonal solves are those of msl_filter.
+// =====================================================================================================
+static bool cheb_prepare(H* h) {
+  if (h->cheb_ready) return h->cheb_usable;
+  h->cheb_ready = true;
+  h->cheb_usable = false;
+  const HostCsr& B = h->hB;
+  if (!B.set || B.structure == FEASTCUDA_GEN) return false;
+  const int64_t n = B.n;
+  const int vs = B.cplx ? 2 : 1;
+  std::vector<double> d(n, 0.0), dinv(n), sq(n);
+  double hi = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    double rs = 0.0;
+    for (int p = B.ptr[i]; p < B.ptr[i + 1]; ++p) {
+      const double re = B.val[(size_t)vs * p], im = B.cplx ? B.val[(size_t)vs * p + 1] : 0.0;
+      rs += std::hypot(re, im);
+      if (B.col[p] == i) d[i] = re;
+    }
+    if (!(d[i] > 0.0)) return false;          // not positive definite: the caller keeps the per-node Krylov solves
+    dinv[i] = 1.0 / d[i];
+    sq[i] = std::sqrt(dinv[i]);
+    hi = std::max(hi, rs * dinv[i]);          // Gershgorin bound of D^-1 B
+  }
+  // smallest Ritz value of a short Lanczos run on D^-1/2 B D^-1/2 (an upper bound of the smallest eigenvalue), times a safety factor
+  const int steps = (int)std::min<int64_t>(40, n);
+  std::vector<zc> v(n), vp(n, zc(0.0)), w(n);
+  double nrm = 0.0;
+  for (int64_t i = 0; i < n; ++i) { v[i] = std::cos(1.0 + (double)i * 0.7548776662466927); nrm += std::norm(v[i]); }
+  nrm = std::sqrt(nrm);
+  for (auto& x : v) x /= nrm;
+  std::vector<double> al, be;
+  double beta = 0.0;
+  for (int it = 0; it < steps; ++it) {
+    for (int64_t i = 0; i < n; ++i) {
+      zc acc(0.0);
+      for (int p = B.ptr[i]; p < B.ptr[i + 1]; ++p) {
+        const int j = B.col[p];
+        const zc bij = B.cplx ? zc(B.val[2 * (size_t)p], B.val[2 * (size_t)p + 1]) : zc(B.val[p], 0.0);
+        acc += bij * (sq[j] * v[j]);
+      }
+      w[i] = sq[i] * acc;
+    }
+    double a = 0.0;
+    for (int64_t i = 0; i < n; ++i) a += (std::conj(v[i]) * w[i]).real();
+    double b2 = 0.0;
+    for (int64_t i = 0; i < n; ++i) { w[i] -= a * v[i] + beta * vp[i]; b2 += std::norm(w[i]); }
+    al.push_back(a);
+    beta = std::sqrt(b2);
+    if (!(beta > 1e-12 * hi)) break;
+    be.push_back(beta);
+    for (int64_t i = 0; i < n; ++i) { vp[i] = v[i]; v[i] = w[i] / beta; }
+  }
+  // smallest eigenvalue of the Lanczos tridiagonal by bisection on its Sturm sequence
+  const int k = (int)al.size();
+  auto count_below = [&](double x) {
+    int cnt = 0;
+    double q = 1.0;
+    for (int i = 0; i < k; ++i) {
+      const double b2 = i > 0 ? be[i - 1] * be[i - 1] : 0.0;
+      q = al[i] - x - (i > 0 ? b2 / q : 0.0);
+      if (q == 0.0) q = 1e-300;
+      if (q < 0.0) ++cnt;
+    }
+    return cnt;
+  };
+  double lo_b = -hi, hi_b = 2.0 * hi;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo_b + hi_b);
+    if (count_below(mid) >= 1) hi_b = mid; else lo_b = mid;
+  }
+  const double ritz_min = 0.5 * (lo_b + hi_b);
+  if (!(ritz_min > 1e-3 * hi)) return false;     // too ill-conditioned for a fixed low-degree polynomial
+  h->cheb_lo = 0.85 * ritz_min;
+  h->cheb_hi = hi;
+  h->cheb_dinv.ensure((size_t)n * sizeof(double));
+  FC_CUDA(cudaMemcpyAsync(h->cheb_dinv.p, dinv.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  sync(h);
+  h->cheb_usable = true;
+  if (getenv("FEASTCUDA_VERBOSE")) fprintf(stderr, "[feastcuda r%d] Chebyshev interval of D^-1 B: [%.4e, %.4e]\n", h->rank, h->cheb_lo, h->cheb_hi);
+  return true;
+}
+
+static int cheb_degree(double lo, double hi, double delta) {
+  const double kap = hi / lo, sg = (std::sqrt(kap) - 1.0) / (std::sqrt(kap) + 1.0);
+  int K = 2;
+  while (2.0 * std::pow(sg, K) / (1.0 + std::pow(sg, 2 * K)) > delta && K < 400) ++K;
+  return K;
+}
+
+template <bool CPLX>
+static void msl_filter_gen(H* h, int basis_slot, int c0, int nc, bool have_ritz, const double* theta, const zc* Zne, const zc* Wne,
+                           int ne, double target, int kmax, int check_every, double cheb_delta, MslOut& out) {
+  FC_REQUIRE(h->kind == OP_SPARSE && h->dev_complex == CPLX && h->has_b && h->cheb_usable,
+             "generalized multi-shift Lanczos needs a sparse Hermitian pencil with a positive definite B");
+  FC_REQUIRE(CPLX || (c0 & 1) == 0, "column slices must start at an even column");
+  const int64_t n = h->ws_n;
+  const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : ((nc + 1) & ~1);
+  FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
+  kmax = std::max(1, std::min(kmax, 16384));
+  check_every = std::max(1, check_every);
+  const int P = CPLX ? nc : (nc + 1) / 2;
+  const int pp = pow2_ge(P);
+  const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
+  const int K = cheb_degree(h->cheb_lo, h->cheb_hi, cheb_delta);
+  const double* dinv = h->cheb_dinv.as<double>();
+
+  // ---- device scalars (layout as in msl_filter) -------------------------------------------------------------------
+  const size_t rowsz = (size_t)FC_MAXCOLS;
+  const size_t per = (size_t)(kmax + 2) * rowsz;
+  const size_t scal_doubles = 5 * per + rowsz + 2 * rowsz + (size_t)(kmax + 2);
+  h->lz_scal.ensure(scal_doubles * sizeof(double));
+  h->lz_coef.ensure(per * sizeof(double));
+  h->lz_state.ensure(((size_t)2 * ne * rowsz + ne) * sizeof(zd) + 64);
+  double* base = h->lz_scal.as<double>();
+  FC_CUDA(cudaMemsetAsync(base, 0, scal_doubles * sizeof(double), h->stream));
+  LzScalars S;
+  S.alpha = base; S.beta = base + per; S.inv_beta = base + 2 * per; S.ratio_b = base + 3 * per; S.ratio_a = base + 4 * per;
+  S.scale = base + 5 * per;
+  double* d_theta = S.scale + rowsz;
+  double* d_rho = d_theta + rowsz;
+  S.maxres = d_rho + rowsz;
+  zd* stz = h->lz_state.as<zd>();
+  S.d = stz; S.g = stz + (size_t)ne * rowsz;
+  zd* d_z = stz + (size_t)2 * ne * rowsz;
+  S.z = d_z;
+  S.ne = ne;
+  S.target = target;
+  S.done_k = reinterpret_cast<int*>(d_z + ne);
+  FC_CUDA(cudaMemcpyAsync(d_z, Zne, (size_t)ne * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+
+  // ---- compact work blocks ------------------------------------------------------------------------------------------
+  double* RQ = rblk(h, BS_KS);                                             // the basis slice (start block only)
+  double* SV[2] = {rblk(h, BS_KR), rblk(h, BS_KRH)};                       // s_j / s_{j-1}
+  double* VV[3] = {rblk(h, BS_KP), rblk(h, BS_KT), rblk(h, BS_KX)};        // u_j and the two Chebyshev iterates
+  double* QA = rblk(h, BS_KV);
+  const zd* basis = blk(h, basis_slot) + c0;
+  double* part = h->partial_r.as<double>();
+  const double th_c = 0.5 * (h->cheb_hi + h->cheb_lo), de_c = 0.5 * (h->cheb_hi - h->cheb_lo), sg_c = th_c / de_c;
+
+  auto args0 = [&]() {
+    LzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.m = nc; a.ld = ld; a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
+    return a;
+  };
+  auto use_A = [&](LzArgs& a) { a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p; };
+  auto use_B = [&](LzArgs& a) { a.ptr = h->dB.ptr.as<int>(); a.col = h->dB.col.as<int>(); a.val = h->dB.val.p; };
+  const double cheb_bytes = (double)h->hB.nnz * ((CPLX ? 16.0 : 8.0) + 4.0) + 4.0 * (double)(n + 1) + 8.0 * (double)n +
+                            4.0 * (double)n * nc * (CPLX ? 16.0 : 8.0);
+  // X = P R: K Chebyshev steps; the result lands in xa or xb (returned); the last step leaves Re(X^H R) in `part`
+  int g_last = 0, cur_j = 0;
+  int64_t cheb_count = 0;
+  auto cheb_solve = [&](const double* R, double* xa, double* xb, const int* done) -> double* {
+    k_lz_cheb_first<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, 1.0 / th_c, dinv, R, xa, done);
+    check_launch(h);
+    double rho_prev = 1.0 / sg_c;
+    double* x = xa;      // x_i
+    double* xo = xb;     // x_{i-1} (i = 1: never read with weight, prev = x)
+    for (int i = 1; i < K; ++i) {
+      const double rho = 1.0 / (2.0 * sg_c - rho_prev);
+      LzArgs a = args0();
+      use_B(a);
+      a.U = x; a.prev = (i == 1) ? x : xo; a.out = xo; a.rhs = R; a.dinv = dinv; a.done = done;
+      a.c1 = rho * rho_prev; a.c2 = 2.0 * rho / de_c;
+      const bool smp = (cheb_count++ % 64) == 5;
+      const int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_CHEB, cur_j) : -1;
+      if (i == K - 1) lz_launch<LZ_CHEB_DOT, CPLX>(h, a, &g_last);
+      else lz_launch<LZ_CHEB, CPLX>(h, a, &g_last);
+      sample_end(h, ev);
+      std::swap(x, xo);
+      rho_prev = rho;
+    }
+    return x;
+  };
+
+  // ---- start block: s_0 = B q (or A q - theta B q), u_0 = P s_0, beta_0^2 = Re(u_0^H s_0) ----------------------------
+  std::vector<double> rho(nc, 0.0);
+  k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS, LzTail{});
+  check_launch(h);
+  FC_CUDA(cudaMemsetAsync(QA, 0, (size_t)n * (size_t)ld * sizeof(double), h->stream));
+  int g = 0;
+  if (!have_ritz) {
+    LzArgs a = args0();
+    use_B(a);
+    a.U = RQ; a.prev = RQ; a.out = SV[0];
+    lz_launch<LZ_PLAIN, CPLX>(h, a, &g);
+  } else {
+    for (int c = 0; c < nc; ++c) {
+      zc acc(0.0);
+      for (int e = 0; e < ne; ++e) acc += 2.0 * Wne[e] / (Zne[e] - theta[c]);
+      rho[c] = acc.real();
+    }
+    FC_CUDA(cudaMemcpyAsync(d_theta, theta, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FC_CUDA(cudaMemcpyAsync(d_rho, rho.data(), (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LzArgs a = args0();
+    use_B(a);
+    a.U = RQ; a.prev = RQ; a.out = VV[1];                       // B q
+    lz_launch<LZ_PLAIN, CPLX>(h, a, &g);
+    LzArgs r = args0();
+    use_A(r);
+    r.U = RQ; r.prev = RQ; r.out = SV[0]; r.own = VV[1]; r.s_theta = d_theta; r.s_coef = d_rho; r.Q = nullptr;   // A q - theta (B q)
+    lz_launch<LZ_RES, CPLX>(h, r, &g);
+    k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_rho, RQ, QA);      // Q = rho(theta) q
+    check_launch(h);
+    sync(h);   // theta / rho are host buffers
+  }
+  double* Ucur = cheb_solve(SV[0], VV[0], VV[1], nullptr);
+  double* free_a = (Ucur == VV[0]) ? VV[1] : VV[0];
+  double* free_b = VV[2];
+  k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g_last, FC_MAXCOLS, nc);
+  check_launch(h);
+  // the start vectors are needed again by pass 2: keep copies (u_0 in RQ's slot once q is no longer needed, s_0 in BS_KB)
+  double* U0 = RQ;
+  double* S0 = rblk(h, BS_KB);
+  FC_CUDA(cudaMemcpyAsync(U0, Ucur, (size_t)n * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(S0, SV[0], (size_t)n * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+
+  // one Lanczos step with the given buffers; pass 1 raises the scalars, pass 2 replays them
+  auto step = [&](int j, double*& U, double*& fa, double*& fb, int& si, bool pass1, const int* done) {
+    double* s_cur = SV[si];
+    double* s_oth = SV[si ^ 1];
+    cur_j = pass1 ? j : 0;
+    LzArgs a = args0();
+    use_A(a);
+    a.U = U; a.prev = j > 0 ? s_oth : U; a.out = s_oth; a.done = done;
+    a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
+    int gg = 0;
+    const bool smp = pass1 && (j % 16) == 3;
+    int ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_P1, j) : -1;
+    lz_launch<LZ_P1, CPLX>(h, a, &gg);
+    sample_end(h, ev);
+    if (pass1) {
+      k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, gg, FC_MAXCOLS, nc);
+      check_launch(h);
+    }
+    k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, s_cur, s_oth, part, FC_MAXCOLS, done, LzTail{});
+    check_launch(h);
+    double* unew = cheb_solve(s_oth, fa, fb, done);
+    if (pass1) {
+      k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, g_last, FC_MAXCOLS, nc);
+      check_launch(h);
+    }
+    double* other = (unew == fa) ? fb : fa;
+    fa = U;          // the old u_j is free now
+    fb = other;
+    U = unew;
+    si ^= 1;
+  };
+
+  // ---- pass 1 ---------------------------------------------------------------------------------------------------------
+  Timer t1;
+  int* flag = reinterpret_cast<int*>(pinned_buf(h, 64));
+  flag[0] = 0;
+  int done = 0, kfinal = 0, si = 0;
+  {
+    double *U = Ucur, *fa = free_a, *fb = free_b;
+    while (done < kmax) {
+      const int batch = std::min(check_every, kmax - done);
+      for (int j = done; j < done + batch; ++j) step(j, U, fa, fb, si, true, S.done_k);
+      done += batch;
+      FC_CUDA(cudaMemcpyAsync(flag, S.done_k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      sync(h);
+      if (flag[0] != 0) { kfinal = flag[0]; out.converged = true; break; }
+    }
+  }
+  if (kfinal == 0) kfinal = done;
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P1] = lz_bytes_spmm(h, nc, 3, CPLX);
+  h->stats.bytes_kern[FEASTCUDA_KERN_LZ_CHEB] = cheb_bytes;
+  drain_events(h, kfinal);
+  h->stats.lz_steps_p1 += kfinal;
+  h->stats.krylov_iters += kfinal;
+  h->stats.col_iters += (int64_t)kfinal * nc;
+  h->stats.ms_lz_p1 += t1.ms();
+
+  // ---- coefficients (host, as in msl_filter) ----------------------------------------------------------------------------
+  const int k = kfinal;
+  std::vector<double> al((size_t)k * rowsz), be((size_t)(k + 1) * rowsz), coef((size_t)k * rowsz, 0.0);
+  FC_CUDA(cudaMemcpyAsync(al.data(), S.alpha, al.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  FC_CUDA(cudaMemcpyAsync(be.data(), S.beta, be.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  double mr = 0.0;
+  FC_CUDA(cudaMemcpyAsync(&mr, S.maxres + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  out.k = k;
+  out.maxres = mr;
+  lz_host_coefficients(k, nc, al, be, have_ritz, theta, Zne, Wne, ne, coef);
+  double* d_coef = h->lz_coef.as<double>();
+  FC_CUDA(cudaMemcpyAsync(d_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+
+  // ---- pass 2: replay from (u_0, s_0) with the stored scalars, Q += (c_j / beta_j) u_j ----------------------------------
+  Timer t2;
+  {
+    // buffers: u_0 and s_0 were saved; every other block is free again
+    double* U = VV[0];
+    FC_CUDA(cudaMemcpyAsync(U, U0, (size_t)n * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    FC_CUDA(cudaMemcpyAsync(SV[0], S0, (size_t)n * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    double *fa = VV[1], *fb = VV[2];
+    int si2 = 0;
+    for (int j = 0; j < k; ++j) {
+      k_lz_axpy<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, d_coef + (size_t)j * rowsz, U, QA);
+      check_launch(h);
+      if (j == k - 1) break;
+      step(j, U, fa, fb, si2, false, nullptr);
+    }
+  }
+  k_lz_to_complex<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
+  check_launch(h);
+  sync(h);
+  drain_events(h);
+  h->stats.lz_steps_p2 += k;
+  h->stats.ms_lz_p2 += t2.ms();
+  h->stats.cheb_degree = K;
+}
+
+// =====================================================================================================
 // rank-revealing orthonormalisation (K7: _feast_qr_compress!, core/feast_aux.jl:101-131)
 // in: Z0 (n x ncols in slot `src`), out: orthonormal basis in the returned slot, rank
 // =====================================================================================================
@@ -939,7 +1291,7 @@ static int orthonormalize(H* h, int ncols, int src_slot, int tmp_slot, double ra
       double dmax = 0.0;
       for (int j = 0; j < cur; ++j) dmax = std::max(dmax, G[(size_t)j * cur + j].real());
       if (!(dmax > 0.0)) { *out_slot = a_slot; return 0; }
-      thr_abs = std::max(rank_tol, eps * (double)std::max<int64_t>(n, ncols)) * std::sqrt(dmax);
+      thr_abs = std::max(rank_tol, eps * (double)std::max<int64_t>(h->row_sharded ? h->n_glob : n, ncols)) * std::sqrt(dmax);
     }
     if (done == cur) {
       double err = 0.0;
@@ -1006,6 +1358,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -1022,6 +1375,7 @@ static void nccl_load() {
   g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
@@ -1041,6 +1395,107 @@ static void allreduce_block(H* h, zd* buf, int64_t count_zd) {
   sync(h);
   h->stats.ms_allreduce += t.ms();
   h->stats.allreduce_bytes += count_zd * (int64_t)sizeof(zd);
+}
+
+// =====================================================================================================
+// Row-sharded runs: the arena (all block slots + the mailbox of the one-shot reductions) and its peer mappings
+// =====================================================================================================
+static void allreduce_small(H* h, double* dev, size_t count) {   // sum over ranks, in place (device buffer)
+  if (h->nranks <= 1) return;
+  FC_NCCL(g_nccl.AllReduce(dev, dev, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->nccl_comm, h->stream));
+  h->stats.allreduce_bytes += (int64_t)(count * sizeof(double));
+}
+
+static void arena_release(H* h) {
+  if (!h->arena) return;
+  cudaStreamSynchronize(h->stream);
+  for (int p = 0; p < h->nranks && p < 16; ++p)
+    if (p != h->rank && h->peer_arena[p]) { cudaIpcCloseMemHandle(h->peer_arena[p]); h->peer_arena[p] = nullptr; }
+  if (h->nranks > 1 && h->nccl_comm) {   // nobody frees while a peer still has the mapping open
+    double* d = h->small2.as<double>();
+    if (d) { g_nccl.AllReduce(d, d, 1, 8, 0, h->nccl_comm, h->stream); cudaStreamSynchronize(h->stream); }
+  }
+  for (int s = 0; s < BS_COUNT; ++s) { h->blk[s].p = nullptr; h->blk[s].cap = 0; h->blk[s].owned = true; }
+  cudaFree(h->arena);
+  h->arena = nullptr;
+  h->arena_bytes = 0;
+}
+
+static void arena_allocate(H* h, int ld) {
+  FC_REQUIRE(h->nranks >= 1 && h->nranks <= LZ_MAXRANKS, "row sharding: at most 16 ranks");
+  h->small2.ensure((size_t)4 * FC_MAXCOLS * sizeof(zd) + 64);
+  arena_release(h);
+  for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
+  const size_t slot = (((size_t)h->nloc_max * (size_t)ld * sizeof(zd)) + 255) & ~(size_t)255;
+  h->arena_slot_bytes = slot;
+  h->arena_mbox_off = (size_t)BS_COUNT * slot;
+  h->arena_bytes = h->arena_mbox_off + ((sizeof(LzMailbox) + 255) & ~(size_t)255);
+  FC_CUDA(cudaMalloc(&h->arena, h->arena_bytes));
+  FC_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+  for (int s = 0; s < BS_COUNT; ++s) {
+    h->blk[s].p = (char*)h->arena + (size_t)s * slot;
+    h->blk[s].cap = slot;
+    h->blk[s].owned = false;
+  }
+  h->peer_arena[h->rank] = h->arena;
+  h->goff_rowbytes2[0] = h->goff_rowbytes2[1] = 0;
+  h->xseq = 0;
+  if (h->nranks > 1) {
+    // every rank's cudaIpcMemHandle_t travels through one ncclAllGather; the peers' arenas are then mapped into this process
+    cudaIpcMemHandle_t mine;
+    FC_CUDA(cudaIpcGetMemHandle(&mine, h->arena));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DBuf hb;
+    hb.ensure((size_t)64 * h->nranks);
+    FC_CUDA(cudaMemcpyAsync((char*)hb.p + 64 * h->rank, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+    FC_REQUIRE(g_nccl.AllGather != nullptr, "libnccl: ncclAllGather missing");
+    FC_NCCL(g_nccl.AllGather((char*)hb.p + 64 * h->rank, hb.p, 64, /*ncclChar*/ 0, h->nccl_comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(h->nranks);
+    FC_CUDA(cudaMemcpyAsync(all.data(), hb.p, (size_t)64 * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+    hb.release();
+    for (int p = 0; p < h->nranks; ++p)
+      if (p != h->rank) FC_CUDA(cudaIpcOpenMemHandle(&h->peer_arena[p], all[p], cudaIpcMemLazyEnablePeerAccess));
+  }
+  sync(h);
+}
+
+static void fill_xchg(H* h, LzXchg& x) {
+  memset(&x, 0, sizeof(x));
+  x.nranks = 1;
+  if (!h->row_sharded || h->nranks <= 1) return;
+  x.nranks = h->nranks;
+  x.rank = h->rank;
+  x.seq = ++h->xseq;
+  for (int p = 0; p < h->nranks; ++p) x.mbox[p] = reinterpret_cast<LzMailbox*>((char*)h->peer_arena[p] + h->arena_mbox_off);
+}
+
+// every rank has finished its previous kernels on the block slots (before a kernel gathers rows the peers just wrote)
+static void xbarrier(H* h) {
+  if (!h->row_sharded || h->nranks <= 1) return;
+  LzXchg x;
+  fill_xchg(h, x);
+  k_lz_barrier<<<1, 128, 0, h->stream>>>(x);
+  check_launch(h);
+}
+
+// gather offsets of A's local rows for blocks whose rows are `rowbytes` apart (two strides are in use: the compact Lanczos blocks
+// and the engine's complex blocks viewed as interleaved real columns)
+static const long long* resolve_goff(H* h, int64_t rowbytes) {
+  const int64_t nnz = h->nnz_loc;
+  const int slot = (h->goff_rowbytes2[0] == rowbytes) ? 0 : ((h->goff_rowbytes2[1] == rowbytes) ? 1 : -1);
+  if (slot >= 0) return h->goff.as<long long>() + (size_t)slot * (size_t)std::max<int64_t>(nnz, 1);
+  const int use = h->goff_next;
+  h->goff_next ^= 1;
+  h->goff.ensure((size_t)2 * (size_t)std::max<int64_t>(nnz, 1) * sizeof(long long));
+  long long* out = h->goff.as<long long>() + (size_t)use * (size_t)std::max<int64_t>(nnz, 1);
+  LzArenas ar;
+  memset(&ar, 0, sizeof(ar));
+  for (int p = 0; p < h->nranks; ++p) ar.base[p] = (const char*)h->peer_arena[p];
+  k_lz_resolve<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(nnz, h->dA.col.as<int>(), (long long)rowbytes, h->rank, ar, out);
+  check_launch(h);
+  h->goff_rowbytes2[use] = rowbytes;
+  return out;
 }
 
 // =====================================================================================================
@@ -1106,6 +1561,11 @@ static bool node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X, bool u
 }
 
 static void apply_op(H* h, int which, int m, const zd* X, zd* Y) {
+  if (h->row_sharded) {
+    FC_REQUIRE(which == FEASTCUDA_A, "row sharding: B = I");
+    sharded_apply(h, m, X, Y, nullptr, nullptr);
+    return;
+  }
   if (h->kind == OP_SPARSE) {
     if (which == FEASTCUDA_A) launch_spmm<SPMM_PLAIN>(h, op_A(), m, X, Y, nullptr, nullptr);
     else launch_spmm<SPMM_PLAIN>(h, op_B(), m, X, Y, nullptr, nullptr);
@@ -1120,10 +1580,56 @@ static void apply_op(H* h, int which, int m, const zd* X, zd* Y) {
   } else throw FcError(FEASTCUDA_ERR_STATE, "no operator set");
 }
 
+// Row-sharded runs: Y = A X (theta == nullptr) or R = A X - X diag(theta) with ||R_j||^2 in `norms2`, on the engine's complex blocks
+// viewed as 2m interleaved REAL columns (A is real), by the Lanczos gather kernel -- halo rows come from the peers' HBM
+static void sharded_apply(H* h, int m, const zd* X, zd* Y, const double* theta, std::vector<double>* norms2) {
+  FC_REQUIRE(h->kind == OP_SPARSE && !h->dev_complex && !h->has_b, "row sharding: standard real symmetric sparse problems only");
+  xbarrier(h);   // the peers have written the rows this launch gathers
+  const int64_t ldr = 2 * (int64_t)h->ws_ld;
+  double* part = h->partial_r.as<double>();
+  double* d_theta = reinterpret_cast<double*>(h->small2.as<zd>() + 8);
+  if (norms2) norms2->assign(m, 0.0);
+  for (int c0 = 0; c0 < m; c0 += 64) {     // at most 128 real columns per launch
+    const int mc = std::min(64, m - c0);
+    LzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = h->n; a.m = 2 * mc; a.ld = ldr;
+    a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
+    a.goff = resolve_goff(h, ldr * (int64_t)sizeof(double));
+    a.U = reinterpret_cast<const double*>(X + c0); a.prev = a.U;
+    a.out = reinterpret_cast<double*>(Y + c0);
+    a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
+    int g = 0;
+    if (theta == nullptr) lz_launch<LZ_PLAIN, false>(h, a, &g);
+    else {
+      std::vector<double> th2(2 * mc);
+      for (int c = 0; c < mc; ++c) th2[2 * c] = th2[2 * c + 1] = theta[c0 + c];
+      FC_CUDA(cudaMemcpyAsync(d_theta, th2.data(), th2.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      a.s_theta = d_theta;
+      lz_launch<LZ_RES, false>(h, a, &g);
+      double* dev = h->red_ws.as<double>();
+      k_reduce_partials<double><<<1, 1024, ((size_t)FC_MAXCOLS + 1024) * sizeof(double), h->stream>>>(part, 1, g, FC_MAXCOLS, 2 * mc, dev);
+      check_launch(h);
+      allreduce_small(h, dev, (size_t)2 * mc);
+      std::vector<double> tmp(2 * mc);
+      FC_CUDA(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      sync(h);   // th2 / tmp are host buffers
+      for (int c = 0; c < mc; ++c) (*norms2)[c0 + c] = tmp[2 * c] + tmp[2 * c + 1];
+    }
+  }
+}
+
 // res_j = ||A x_j - lam_j B x_j||_2 (not yet divided by max(|lam|,1))
 static void eig_residual_norms(H* h, int m, const zd* X, const std::vector<zc>& lam, std::vector<double>& out) {
   out.assign(m, 0.0);
   if (m == 0) return;
+  if (h->row_sharded) {
+    std::vector<double> th(m), n2;
+    for (int c = 0; c < m; ++c) th[c] = lam[c].real();
+    sharded_apply(h, m, X, blk(h, BS_KT), th.data(), &n2);
+    for (int c = 0; c < m; ++c) out[c] = std::sqrt(n2[c]);
+    return;
+  }
   if (h->kind == OP_SPARSE) {
     zd* dl = h->small2.as<zd>() + 8;
     FC_CUDA(cudaMemcpyAsync(dl, lam.data(), (size_t)m * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
@@ -1206,7 +1712,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
   const int64_t n = h->n;
   // check_feast_srci_input, core/feast_aux.jl:369-399 (the shim throws ArgumentError before the ccall)
   FC_REQUIRE(n > 0, "Matrix size N must be positive");
-  FC_REQUIRE(m0 > 0 && m0 <= n, "Number of eigenvalues M0 must be between 1 and N");
+  FC_REQUIRE(m0 > 0 && m0 <= (h->row_sharded ? h->n_glob : n), "Number of eigenvalues M0 must be between 1 and N");
   FC_REQUIRE(Emin < Emax, "Search interval [Emin, Emax] must be valid");
   FC_REQUIRE(ne >= 1 && ne <= 128 && Zne && Wne, "contour required");
   FC_REQUIRE(h->have_subspace && h->sub_m0 == m0 && h->ws_n == n, "initial subspace not uploaded for this (n, M0)");
@@ -1240,25 +1746,32 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     Timer tsolve;
     zd* basis = blk(h, qb);
     const zd* rhs = basis;
-    if (h->has_b) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
+    // generalized Hermitian pencils with a positive definite B: the same recurrence in the B-inner product (msl_filter_gen)
+    const bool use_gen = iterative && !matfree && h->has_b && o.solver == FEASTCUDA_SOLVER_MSLANCZOS && o.filter == FEASTCUDA_FILTER_TRUE &&
+                         h->hA.structure != FEASTCUDA_GEN && (real_mode || h->dev_complex) && cheb_prepare(h);
+    if (h->has_b && !use_gen) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
     zero_cols(h, active, blk(h, BS_ACC));
     // multi-shift Lanczos: standard Hermitian problems with the true filter rho = Re g -- real symmetric with a real basis (real
     // arithmetic) or complex Hermitian (complex vectors, real tridiagonal: the coefficients of rho are real either way)
     const bool cplx_msl = iterative && !matfree && h->dev_complex && !h->has_b && o.filter == FEASTCUDA_FILTER_TRUE && h->hA.structure != FEASTCUDA_GEN;
-    const bool use_msl = iterative && (o.solver == FEASTCUDA_SOLVER_MSLANCZOS || matfree) && !h->has_b && (real_mode || cplx_msl);
+    const bool use_msl = use_gen || (iterative && (o.solver == FEASTCUDA_SOLVER_MSLANCZOS || matfree) && !h->has_b && (real_mode || cplx_msl));
     if (matfree && !use_msl)
       throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "matrix-free operators need a real initial subspace and filter = TRUE (multi-shift Lanczos)");
+    if (h->row_sharded && !(use_msl && real_mode && !use_gen))
+      throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "row sharding serves the real symmetric multi-shift Lanczos filter (real basis, filter = TRUE)");
     std::vector<WorkItem> items;
     if (!use_msl) items = build_items(ne, active, h->nranks, h->rank, shard, cost);
     std::vector<double> node_cost(ne, 0.0), node_cols(ne, 0.0);
     bool failed = false;
     if (use_msl) {
       // one real Lanczos recurrence per column serves every node; ranks own contiguous column-pair slices
-      const int epc = cplx_msl ? 1 : 2;                     // columns per 16-byte element
+      const bool cplx_vec = use_gen ? h->dev_complex : cplx_msl;
+      const int epc = cplx_vec ? 1 : 2;                     // columns per 16-byte element
       const int npairs = (active + epc - 1) / epc;
       const int pb = npairs / h->nranks, pr = npairs % h->nranks;
       const int p0 = h->rank * pb + std::min(h->rank, pr), pn = pb + (h->rank < pr ? 1 : 0);
-      const int c0 = epc * p0, nc = std::max(0, std::min(active, epc * (p0 + pn)) - c0);
+      int c0 = epc * p0, nc = std::max(0, std::min(active, epc * (p0 + pn)) - c0);
+      if (h->row_sharded) { c0 = 0; nc = active; }     // every rank filters all columns of its own rows
       const bool first = !(o.ritz_guess && have_ritz);
       double target = (first && o.inner_rel0 > 0) ? o.inner_rel0 : o.inner_rel;
       if (!(target > 0)) target = tol;
@@ -1270,7 +1783,14 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       const int kmax = (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter;
       if (nc > 0) {
         MslOut mo;
-        if (cplx_msl) msl_filter<true>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
+        if (use_gen) {
+          // accuracy of the Chebyshev inner solves with B: the filter of the neighbouring pencil (A, P^-1) only has to stay below the
+          // sweep's own contraction
+          const double d0 = o.b_delta > 0 ? o.b_delta : 1e-4;
+          const double delta = first ? d0 : std::min(d0, std::max(1e-10, 1e-3 * target));
+          if (h->dev_complex) msl_filter_gen<true>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, delta, mo);
+          else msl_filter_gen<false>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, delta, mo);
+        } else if (cplx_msl) msl_filter<true>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo);
         else msl_filter<false>(h, qb, c0, nc, !first, lam.data() + c0, Zne, Wne, ne, target, kmax, o.check_every > 0 ? o.check_every : 16, mo,
                                use_fp32);
         h->stats.node_solves += ne;
@@ -1312,7 +1832,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
     if (h->nranks > 1) {
       // one exchange per refinement loop: MPI.Allreduce(Q_proj), parallel/feast_mpi.jl:119,341,858
       int64_t fl[1] = {failed ? 1 : 0};
-      allreduce_block(h, blk(h, BS_ACC), (int64_t)n * h->ws_ld);
+      if (!h->row_sharded) allreduce_block(h, blk(h, BS_ACC), (int64_t)n * h->ws_ld);   // row-sharded: the local rows are complete
       // failure flag + measured node costs ride along in a tiny second reduction
       std::vector<double> pack(2 * ne + 1, 0.0);
       for (int e = 0; e < ne; ++e) { pack[e] = node_cost[e]; pack[ne + e] = node_cols[e]; }
@@ -1642,7 +2162,6 @@ int feastcuda_create(feastcuda_handle* out, int device) {
   if (const char* e = getenv("FEASTCUDA_LZ_CTAS")) h->lz_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("FEASTCUDA_LZ_TILE")) h->lz_tile_rows = std::max(1, atoi(e));
   if (const char* e = getenv("FEASTCUDA_LZ_PAIRED")) h->lz_paired = atoi(e);
-  if (const char* e = getenv("FEASTCUDA_LZ_STAGED")) h->lz_staged = atoi(e);
   if (const char* e = getenv("FEASTCUDA_LZ_EGRID")) h->lz_egrid_mult = std::max(1, std::min(8, atoi(e)));
   *out = h;
   FC_CATCH
@@ -1651,10 +2170,11 @@ int feastcuda_create(feastcuda_handle* out, int device) {
 int feastcuda_destroy(feastcuda_handle h) {
   if (!h) return FEASTCUDA_OK;
   cudaSetDevice(h->device);
+  if (h->arena) arena_release(h);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
   DBuf* bufs[] = {&h->partial, &h->partial_r, &h->kstate, &h->small, &h->small2, &h->gram_partial, &h->stage, &h->red_ws,
-                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->lzp_wmeta, &h->lzp_run0, &h->lzp_runs, &h->lzp_lcol, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB, &h->dense_pool, &h->dense_piv, &h->dense_xpool};
+                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->goff, &h->cheb_dinv, &h->dA.val32, &h->dB.val32, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB, &h->dense_pool, &h->dense_piv, &h->dense_xpool};
   for (DBuf* b : bufs) b->release();
   for (auto& b : h->lu_cache) b.release();
   for (auto& b : h->piv_cache) b.release();
@@ -1703,7 +2223,6 @@ static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t
     ingest_csr(h->hA, n, nnz, ptr, idx, val, cplx, base, fmt, structure);
     h->dA.uploaded = false;
     h->dA.val32_ready = false;
-    h->lzp_built = false;
     if (h->kind != OP_SPARSE) { h->has_b = false; h->hB.set = false; }
     h->kind = OP_SPARSE;
     h->n = n;
@@ -1790,8 +2309,10 @@ int feastcuda_upload_subspace(feastcuda_handle h, int64_t m0, const double* Q0, 
   FC_REQUIRE(h->kind != OP_NONE, "set the operator first");
   bind_device(h);
   prepare_operator(h);
-  FC_REQUIRE(m0 >= 1 && m0 <= h->n, "Number of eigenvalues M0 must be between 1 and N");
+  const int64_t ng = h->row_sharded ? h->n_glob : h->n;
+  FC_REQUIRE(m0 >= 1 && m0 <= ng, "Number of eigenvalues M0 must be between 1 and N");
   ensure_workspace(h, h->n, (int)m0);
+  FC_REQUIRE(!(h->row_sharded && Q0 == nullptr), "row sharding: pass the initial subspace (the library seed is generated per handle)");
   if (Q0 == nullptr) {
     // library seed: deterministic real Gaussian columns (xorshift + Box-Muller), unit 2-norm -- the stand-in for
     // _feast_seeded_subspace_complex! (core/feast_tools.jl:22-43), whose Julia RNG stream cannot be reproduced
@@ -2087,6 +2608,36 @@ int feastcuda_nccl_init(feastcuda_handle h, int nranks, int rank, const char* id
   FC_NCCL(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
   h->nranks = nranks;
   h->rank = rank;
+  FC_CATCH
+}
+
+int feastcuda_set_row_sharding(feastcuda_handle h, int on) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr, "null handle");
+  bind_device(h);
+  const bool want = on != 0 && h->nranks > 1;
+  if (want != h->row_sharded) {
+    if (h->arena) arena_release(h);
+    for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
+    h->row_sharded = want;
+    h->ws_n = 0;
+    h->ws_ld = 0;
+    h->have_subspace = false;
+    h->dA.uploaded = false;
+    h->dB.uploaded = false;
+    h->dA.val32_ready = false;
+  }
+  FC_CATCH
+}
+
+int feastcuda_row_range(feastcuda_handle h, int64_t* row0, int64_t* nrows, int64_t* nglobal) {
+  FC_TRY(h)
+  FC_REQUIRE(h != nullptr && row0 && nrows && nglobal, "null argument");
+  bind_device(h);
+  prepare_operator(h);
+  *row0 = h->row_sharded ? h->row0 : 0;
+  *nrows = h->n;
+  *nglobal = h->row_sharded ? h->n_glob : h->n;
   FC_CATCH
 }
 

@@ -32,423 +32,16 @@ enum LzMode {
   // pass 2 with the accumulator touched every SECOND step: step j holds u_j (U) and u_{j-1} (prev) as own-row operands, so one
   // read-modify-write of Q serves two steps (compile-time variants: a run-time switch cost the narrow kernels their schedule)
   LZ_P2_SKIP = 4,   // as LZ_P2 without any Q traffic
-  LZ_P2_PAIR = 5    // as LZ_P2 with Q += coef_prev * u_{j-1} + coef * u_j
+  LZ_P2_PAIR = 5,   // as LZ_P2 with Q += coef_prev * u_{j-1} + coef * u_j
+  // one step of the three-term Chebyshev iteration for M x = rhs (M = the CSR operand; generalized problems: the inner solves with B):
+  //   out = u + c1 (u - prev) + c2 dinv[row] (rhs - M u)          (u gathered, prev / rhs own-row, out may alias prev)
+  // c1 = c2-independent of the column, so a solve is a FIXED polynomial in M: no dot products, no data-dependent control flow
+  LZ_CHEB = 6,
+  LZ_CHEB_DOT = 7   // as LZ_CHEB;  partial[0] = Re(conj(out) . rhs)   (last step: beta^2 = u_{j+1}^H s_{j+1})
 };
 __host__ __device__ constexpr bool lz_is_p2(int mode) { return mode == LZ_P2 || mode == LZ_P2_SKIP || mode == LZ_P2_PAIR; }
 
-struct LzArgs {
-  int64_t n;
-  int m;                 // active columns
-  int64_t ld;            // row stride in doubles (even)
-  const int* ptr; const int* col; const void* val;   // val: double (real symmetric) or cx<double> (complex Hermitian)
-  const double* U;       // gathered operand
-  const double* prev;    // own-row operand u_{j-1}; at j = 0 any finite block (the host passes U; ratio_b is 0 there)
-  double* out;           // own-row result (may alias prev)
-  double* Q;             // accumulator (LZ_P2, LZ_RES)
-  const double* s_inv_beta; const double* s_ratio_b; const double* s_ratio_a;   // per-column scalars of this step
-  const double* s_coef;  // LZ_P2: c_j / beta_j ; LZ_RES: rho(theta_c)
-  const double* s_theta; // LZ_RES
-  double* partial;       // [gridDim.x][pstride]
-  int pstride;
-  int tile_rows;         // rows per round-robin tile (rounded to the CTA's rows-per-iteration)
-  const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
-  const double* s_coef_prev;   // LZ_P2_PAIR: c_{j-1} / beta_{j-1}
-};
-
-__device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
-
-// Element semantics.  Real problems: a 16-byte element is a PAIR of real columns, matrix entries are doubles.  Complex
-// Hermitian problems (CPLX): an element is ONE complex column (re, im), matrix entries are cx<double>; T_k stays real, so
-// the per-column scalars apply to both components and a dot product is the sum of the two component products.
-template <bool CPLX> struct LzVal;
-template <> struct LzVal<false> {
-  typedef double T;
-  static __device__ __forceinline__ T zero() { return 0.0; }
-  static __device__ __forceinline__ T load(const void* v, int i) { return reinterpret_cast<const double*>(v)[i]; }
-  static __device__ __forceinline__ T shfl(unsigned mask, T a, int src, int width) { return __shfl_sync(mask, a, src, width); }
-  static __device__ __forceinline__ void fma_acc(double2& acc, T a, double2 x) { acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); }
-};
-template <> struct LzVal<true> {
-  typedef double2 T;
-  static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
-  static __device__ __forceinline__ T load(const void* v, int i) { return reinterpret_cast<const double2*>(v)[i]; }
-  static __device__ __forceinline__ T shfl(unsigned mask, T a, int src, int width) {
-    return make_double2(__shfl_sync(mask, a.x, src, width), __shfl_sync(mask, a.y, src, width));
-  }
-  static __device__ __forceinline__ void fma_acc(double2& acc, T a, double2 x) {
-    acc.x = fma(a.x, x.x, acc.x); acc.x = fma(-a.y, x.y, acc.x);
-    acc.y = fma(a.x, x.y, acc.y); acc.y = fma(a.y, x.x, acc.y);
-  }
-};
-// per-element scalars from a per-column array: real -> (s[2e], s[2e+1]); complex -> (s[e], s[e])
-template <bool CPLX>
-__device__ __forceinline__ double2 lz_scal(const double* s, int e, int m) {
-  double2 v = make_double2(0.0, 0.0);
-  if (s != nullptr) {
-    if (CPLX) { if (e < m) v.x = v.y = s[e]; }
-    else { if (2 * e < m) v.x = s[2 * e]; if (2 * e + 1 < m) v.y = s[2 * e + 1]; }
-  }
-  return v;
-}
-template <bool CPLX> __device__ __forceinline__ int lz_elems(int m) { return CPLX ? m : ((m + 1) >> 1); }
-
-// acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries [p0, p1) of `row`, in CSR order.
-// (myo, mya): the group's first G entries, already fetched by the caller one iteration ahead; myo is the ELEMENT offset
-// col*ld of the gathered row (32-bit: the host guarantees n*ld < 2^32), so an address is one IMAD.WIDE from the lane's
-// base pointer Ul[k] = U + 2*(g + G k).  Padding slots of the last batch gather the lane's own row with weight 0 and lanes
-// beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
-// Narrow groups (G <= 4 lanes per row) also receive the row's SECOND chunk of G entries prefetched (myo2, mya2): a
-// 7-point row then needs no dependent metadata load inside the loop even with 4 lanes per row.
-template <int G, int NC, bool CPLX>
-__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo, int p0, int p1, unsigned myo, typename LzVal<CPLX>::T mya,
-                                          unsigned myo2, typename LzVal<CPLX>::T mya2, int g, unsigned gmask,
-                                          const double* const (&Ul)[NC], double2 (&acc)[NC]) {
-  typedef LzVal<CPLX> V;
-  constexpr int UN = (G >= 4) ? 4 : G;
-  constexpr bool PF2 = (G <= 4);
-  const unsigned ldu = (unsigned)a.ld;
-  for (int pb = p0; pb < p1; pb += G) {
-    const int cnt = min(G, p1 - pb);
-    if (PF2 && pb == p0 + G) {
-      myo = myo2;
-      mya = mya2;
-    } else if (pb != p0) {
-      myo = row_eo;
-      mya = V::zero();
-      if (g < cnt) { myo = (unsigned)a.col[pb + g] * ldu; mya = V::load(a.val, pb + g); }
-    }
-    for (int t = 0; t < cnt; t += UN) {
-      unsigned eo[UN];
-      typename V::T aa[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        eo[u] = __shfl_sync(gmask, myo, t + u, G);
-        aa[u] = V::shfl(gmask, mya, t + u, G);
-      }
-      double2 xv[UN][NC];
-#pragma unroll
-      for (int u = 0; u < UN; ++u)
-#pragma unroll
-        for (int k = 0; k < NC; ++k) xv[u][k] = ldg2(Ul[k] + eo[u]);
-#pragma unroll
-      for (int u = 0; u < UN; ++u)
-#pragma unroll
-        for (int k = 0; k < NC; ++k) V::fma_acc(acc[k], aa[u], xv[u][k]);
-    }
-  }
-}
-
-__device__ __forceinline__ double2 lz_scal2(const double* s, int c0, int m) {
-  double2 v = make_double2(0.0, 0.0);
-  if (s != nullptr) {
-    if (c0 < m) v.x = s[c0];
-    if (c0 + 1 < m) v.y = s[c0 + 1];
-  }
-  return v;
-}
-
-// the two Lanczos vector updates, shared by pass 1 (split over two kernels) and pass 2 (fused): identical rounding
-__device__ __forceinline__ double2 lz_t(double2 acc, double2 ib, double2 rb, double2 pv) {
-  double2 t;
-  t.x = __fma_rn(-rb.x, pv.x, __dmul_rn(acc.x, ib.x));
-  t.y = __fma_rn(-rb.y, pv.y, __dmul_rn(acc.y, ib.y));
-  return t;
-}
-__device__ __forceinline__ double2 lz_next(double2 t, double2 ra, double2 uo) {
-  double2 r;
-  r.x = __fma_rn(-ra.x, uo.x, t.x);
-  r.y = __fma_rn(-ra.y, uo.y, t.y);
-  return r;
-}
-
-template <int G, int NC, int MODE, int THREADS, bool CPLX = false>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_lz_spmm(LzArgs a) {
-  typedef LzVal<CPLX> V;
-  if (a.done != nullptr && *a.done != 0) return;
-  constexpr int RPW = 32 / G;
-  const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
-  constexpr unsigned gm0 = (G >= 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-  const unsigned gmask = gm0 << (sub * G);
-  const int wib = threadIdx.x >> 5, wpb = THREADS >> 5;
-  constexpr int STEP = (THREADS / 32) * RPW;          // rows the CTA covers per iteration
-  const int P = lz_elems<CPLX>(a.m);                  // 16-byte elements per row: column pairs (real) or complex columns
-  const int n = (int)a.n;
-  // Rows are dealt to the CTAs in tiles of `tile_rows` consecutive rows, round robin: the whole grid sweeps the matrix as
-  // one moving front, so a vector row fetched as somebody's far neighbour is still in L2 when the front reaches it
-  // (each row of U comes from HBM once), while the near neighbours of a tile stay in the CTA's L1.
-  const int spt = max(1, a.tile_rows / STEP);         // iterations per tile
-  const int TR = spt * STEP;
-  const int ntiles = (n + TR - 1) / TR;
-  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int niter = my_tiles * spt;
-  // iteration -> row, advanced incrementally (no integer divisions in the loop): `base_f` is the first row of the CTA's
-  // iteration `it_f`, the furthest one the metadata pipeline has looked at
-  const int lane_row = wib * RPW + sub;
-  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR;
-  auto next_row = [&]() -> int {
-    const int r = (it_f < niter) ? base_f + lane_row : n;
-    ++it_f;
-    if (++s_f == spt) { s_f = 0; base_f += ((int)gridDim.x - 1) * TR + STEP; }
-    else base_f += STEP;
-    return r < n ? r : n;
-  };
-
-  // per-column scalars of this step live in shared memory (one 16-byte read per use instead of 20 live registers)
-  __shared__ double2 s_sc[5][FC_MAXCOLS / 2];   // [0] inv_beta | theta, [1] ratio_b, [2] ratio_a, [3] coef, [4] coef of the previous step
-  for (int i = threadIdx.x; i < 5 * (FC_MAXCOLS / 2); i += THREADS) {
-    const int w = i / (FC_MAXCOLS / 2), pc = i % (FC_MAXCOLS / 2);
-    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta)
-                                 : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : (w == 3 ? a.s_coef : a.s_coef_prev)));
-    s_sc[w][pc] = lz_scal<CPLX>(src, pc, a.m);
-  }
-  __syncthreads();
-  double2 dot[NC];
-#pragma unroll
-  for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
-
-  // software pipeline over the CSR metadata: row pointers two iterations ahead, the first G (offset, val) pairs one
-  // iteration ahead, so the vector gathers of an iteration never wait behind a pointer chase.  (Measured on B200: a
-  // deeper pipeline with L2 prefetch of the next iteration's rows costs more in registers/spills than it hides.)
-  const unsigned ldu = (unsigned)a.ld;
-  const double* Ul[NC];
-  const double* Pl[NC];   // prev: never null (the host passes U with ratio_b = 0 at j = 0)
-  double* Ol[NC];
-  double* Ql[NC];
-#pragma unroll
-  for (int k = 0; k < NC; ++k) {
-    const int pcl = 2 * min(g + G * k, P - 1);
-    Ul[k] = a.U + pcl;
-    Pl[k] = a.prev + pcl;
-    Ol[k] = a.out + pcl;
-    Ql[k] = a.Q + pcl;
-  }
-  int r_cur = next_row(), r_nxt = next_row();
-  int p0_cur = 0, p1_cur = 0, p0_nxt = 0, p1_nxt = 0;
-  if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
-  if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
-  constexpr bool PF2 = (G <= 4);
-  unsigned o_cur = (r_cur < n ? (unsigned)r_cur : 0u) * ldu, o_cur2 = o_cur;
-  typename V::T a_cur = V::zero(), a_cur2 = V::zero();
-  if (g < p1_cur - p0_cur) { o_cur = (unsigned)a.col[p0_cur + g] * ldu; a_cur = V::load(a.val, p0_cur + g); }
-  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = (unsigned)a.col[p0_cur + G + g] * ldu; a_cur2 = V::load(a.val, p0_cur + G + g); }
-
-  for (int it = 0; it < niter; ++it) {
-    const int row = r_cur;
-    const bool valid = row < n;
-    const int r_fut = next_row();
-    int p0_fut = 0, p1_fut = 0;
-    if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
-    unsigned o_nxt = (r_nxt < n ? (unsigned)r_nxt : 0u) * ldu, o_nxt2 = o_nxt;
-    typename V::T a_nxt = V::zero(), a_nxt2 = V::zero();
-    if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = V::load(a.val, p0_nxt + g); }
-    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = (unsigned)a.col[p0_nxt + G + g] * ldu; a_nxt2 = V::load(a.val, p0_nxt + G + g); }
-
-    // own-row operands first (independent of the gather); invalid rows and inactive lanes read valid dummies
-    const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
-    double2 acc[NC], uo[NC], pv[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      acc[k] = make_double2(0.0, 0.0);
-      if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
-      if constexpr (MODE == LZ_P1 || lz_is_p2(MODE)) pv[k] = ldg2(Pl[k] + eo_own);
-    }
-    lz_gather<G, NC, CPLX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int pc = g + G * k;
-      if (valid && pc < P) {
-        if constexpr (MODE == LZ_PLAIN) {
-          stg2(Ol[k] + eo_own, acc[k]);
-        } else if constexpr (MODE == LZ_RES) {
-          const double2 th = s_sc[0][pc], cf = s_sc[3][pc];
-          double2 t;
-          t.x = __fma_rn(-th.x, uo[k].x, acc[k].x);
-          t.y = __fma_rn(-th.y, uo[k].y, acc[k].y);
-          stg2(Ol[k] + eo_own, t);
-          dot[k].x = fma(t.x, t.x, dot[k].x);
-          dot[k].y = fma(t.y, t.y, dot[k].y);
-          if (a.Q != nullptr) stg2(Ql[k] + eo_own, make_double2(cf.x * uo[k].x, cf.y * uo[k].y));
-        } else {
-          const double2 t = lz_t(acc[k], s_sc[0][pc], s_sc[1][pc], pv[k]);
-          if constexpr (MODE == LZ_P1) {
-            stg2(Ol[k] + eo_own, t);
-            dot[k].x = fma(uo[k].x, t.x, dot[k].x);
-            dot[k].y = fma(uo[k].y, t.y, dot[k].y);
-          } else {
-            stg2(Ol[k] + eo_own, lz_next(t, s_sc[2][pc], uo[k]));
-            if constexpr (MODE != LZ_P2_SKIP) {
-              const double2 cf = s_sc[3][pc];
-              double2 q = ldg2(Ql[k] + eo_own);
-              if constexpr (MODE == LZ_P2_PAIR) {
-                const double2 cp = s_sc[4][pc];
-                q.x = fma(cp.x, pv[k].x, q.x);
-                q.y = fma(cp.y, pv[k].y, q.y);
-              }
-              q.x = fma(cf.x, uo[k].x, q.x);
-              q.y = fma(cf.y, uo[k].y, q.y);
-              stg2(Ql[k] + eo_own, q);
-            }
-          }
-        }
-      }
-    }
-    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; o_cur = o_nxt; a_cur = a_nxt; o_cur2 = o_nxt2; a_cur2 = a_nxt2;
-    r_nxt = r_fut; p0_nxt = p0_fut; p1_nxt = p1_fut;
-  }
-
-  if constexpr (MODE == LZ_P1 || MODE == LZ_RES) {
-    // fixed-order CTA reduction: every launch sums in the same order (pass 2 relies on pass 1's exact scalars)
-    __shared__ double2 red[(THREADS / 32) * 32 * NC];
-    const int width = G * NC;   // pairs per row group
-#pragma unroll
-    for (int k = 0; k < NC; ++k) red[(wib * RPW + sub) * width + g + G * k] = dot[k];
-    __syncthreads();
-    const int ngroups = wpb * RPW;
-    for (int pc = threadIdx.x; pc < width; pc += THREADS) {
-      if (pc < P) {
-        double sx = 0.0, sy = 0.0;
-        for (int q = 0; q < ngroups; ++q) { const double2 v = red[q * width + pc]; sx += v.x; sy += v.y; }
-        if (CPLX) a.partial[(int64_t)blockIdx.x * a.pstride + pc] = sx + sy;   // Re(conj(u) t) = sum of both components
-        else {
-          double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
-          o[0] = sx;
-          if (2 * pc + 1 < a.m) o[1] = sy;
-        }
-      }
-    }
-  }
-}
-
-// ---- elementwise kernels on real blocks: a thread owns one column PAIR, rows strided ---------------------
-struct EwMap2 {
-  int pc, rsub, rpb;
-  __device__ __forceinline__ EwMap2(int pp) { pc = threadIdx.x % pp; rsub = threadIdx.x / pp; rpb = blockDim.x / pp; }
-};
-
-template <bool CPLX>
-__device__ __forceinline__ void block_reduce_pairs(double2 v, int pp, int P, int m, double* out_row) {
-  __shared__ double2 red2[256];
-  __syncthreads();
-  red2[threadIdx.x] = v;
-  __syncthreads();
-  if ((int)threadIdx.x < pp && (int)threadIdx.x < P) {
-    double sx = 0.0, sy = 0.0;
-    for (int q = threadIdx.x; q < (int)blockDim.x; q += pp) { sx += red2[q].x; sy += red2[q].y; }
-    if (CPLX) out_row[threadIdx.x] = sx + sy;
-    else {
-      out_row[2 * threadIdx.x] = sx;
-      if (2 * (int)threadIdx.x + 1 < m) out_row[2 * threadIdx.x + 1] = sy;
-    }
-  }
-}
-
-// pass 1, second half of a step: T (in place) <- T - ratio_a * U ; partial = |T|^2
-template <bool CPLX>
-__global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_ratio_a,
-                                                   const double* __restrict__ U, double* __restrict__ T,
-                                                   double* __restrict__ partial, int pstride, const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
-  EwMap2 e(pp);
-  const int P = lz_elems<CPLX>(m);
-  double2 acc = make_double2(0.0, 0.0);
-  if (e.pc < P) {
-    const double2 ra = lz_scal<CPLX>(s_ratio_a, e.pc, m);
-    const int64_t stride = (int64_t)gridDim.x * e.rpb;
-    int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub;
-    for (; row + 3 * stride < n; row += 4 * stride) {   // four independent rows in flight per thread (narrow blocks are latency bound)
-      double2 tv[4], uv[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t off = (row + q * stride) * ld + 2 * e.pc;
-        tv[q] = ldg2(T + off);
-        uv[q] = ldg2(U + off);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t off = (row + q * stride) * ld + 2 * e.pc;
-        const double2 r = lz_next(tv[q], ra, uv[q]);
-        stg2(T + off, r);
-        acc.x = fma(r.x, r.x, acc.x);
-        acc.y = fma(r.y, r.y, acc.y);
-      }
-    }
-    for (; row < n; row += stride) {
-      const int64_t off = row * ld + 2 * e.pc;
-      const double2 r = lz_next(ldg2(T + off), ra, ldg2(U + off));
-      stg2(T + off, r);
-      acc.x = fma(r.x, r.x, acc.x);
-      acc.y = fma(r.y, r.y, acc.y);
-    }
-  }
-  block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
-}
-
-// Q += coef * U  (last pass-2 step: no further Lanczos vector is needed)
-template <bool CPLX>
-__global__ void __launch_bounds__(256) k_lz_axpy(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_coef,
-                                                 const double* __restrict__ U, double* __restrict__ Q) {
-  EwMap2 e(pp);
-  const int P = lz_elems<CPLX>(m);
-  if (e.pc >= P) return;
-  const double2 cf = lz_scal<CPLX>(s_coef, e.pc, m);
-  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
-    const int64_t off = row * ld + 2 * e.pc;
-    const double2 u = ldg2(U + off);
-    double2 q = ldg2(Q + off);
-    q.x = fma(cf.x, u.x, q.x);
-    q.y = fma(cf.y, u.y, q.y);
-    stg2(Q + off, q);
-  }
-}
-
-// engine block (complex storage, row stride ldz) -> compact Lanczos block.  Real problems keep the real part of the m columns
-// as column pairs (the pad column of an odd m is zeroed); complex problems copy the m complex columns.  partial = |x|^2
-template <bool CPLX>
-__global__ void __launch_bounds__(256) k_lz_real_part(int64_t n, int m, int pp, int64_t ldz, int64_t ld,
-                                                      const cx<double>* __restrict__ Z, double* __restrict__ X,
-                                                      double* __restrict__ partial, int pstride) {
-  EwMap2 e(pp);
-  const int P = lz_elems<CPLX>(m);
-  double2 acc = make_double2(0.0, 0.0);
-  if (e.pc < P) {
-    for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
-      double2 v;
-      if (CPLX) {
-        const cx<double> z = Z[row * ldz + e.pc];
-        v = make_double2(z.x, z.y);
-      } else {
-        const int c0 = 2 * e.pc;
-        v.x = Z[row * ldz + c0].x;
-        v.y = (c0 + 1 < m) ? Z[row * ldz + c0 + 1].x : 0.0;
-      }
-      stg2(X + row * ld + 2 * e.pc, v);
-      acc.x = fma(v.x, v.x, acc.x);
-      acc.y = fma(v.y, v.y, acc.y);
-    }
-  }
-  if (partial != nullptr) block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
-}
-
-// compact Lanczos block -> engine block (real problems: zero imaginary part)
-template <bool CPLX>
-__global__ void __launch_bounds__(256) k_lz_to_complex(int64_t n, int m, int pp, int64_t ld, int64_t ldz,
-                                                       const double* __restrict__ X, cx<double>* __restrict__ Z) {
-  EwMap2 e(pp);
-  const int P = lz_elems<CPLX>(m);
-  if (e.pc >= P) return;
-  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
-    const double2 v = ldg2(X + row * ld + 2 * e.pc);
-    if (CPLX) Z[row * ldz + e.pc] = mk<double>(v.x, v.y);
-    else {
-      const int c0 = 2 * e.pc;
-      Z[row * ldz + c0] = mk<double>(v.x, 0.0);
-      if (c0 + 1 < m) Z[row * ldz + c0 + 1] = mk<double>(v.y, 0.0);
-    }
-  }
-}
-
-// ---- per-step scalar recurrences (one CTA) -------------------------------------------------------------------
+// ---- per-step scalar recurrences -------------------------------------------------------------------------------
 // T arrays: [step][FC_MAXCOLS]; `scale` is the running max(|alpha|, beta) used by the breakdown test.
 // Shift recurrences: for every (node e, column c) the last entry g of (z_e I - T_j)^-1 e_1 is advanced by the LU
 // pivots d of the shifted tridiagonal, so that the residual of every shifted system after j+1 steps,
@@ -465,11 +58,94 @@ struct LzScalars {
   double* maxres;                                                                    // [kmax + 1]
 };
 
-// beta_0 = ||b||  from |b|^2 partials
-__global__ void __launch_bounds__(1024) k_lz_scal_init(LzScalars s, const double* partial, int nblocks, int pstride, int m) {
-  __shared__ double so[FC_MAXCOLS];
-  __shared__ double tmp[1024];
-  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+// Row-sharded multi-GPU runs (one process per GPU, every rank owns a block of rows of A and of every vector): the per-step dot
+// products are summed over the ranks by a ONE-SHOT exchange through peer memory -- every rank stores its m partial sums into a
+// mailbox in each peer's HBM (NVLink stores), raises a sequence flag there, waits for the flags of all peers in its own mailbox and
+// adds the nranks rows in rank order (so every rank gets the same bits and takes the same decisions).  The exchange runs in the
+// tail of the kernel that produced the partial sums: no NCCL call, no extra launch.  Two consecutive exchanges use different
+// slots; a rank can be at most one exchange ahead of its peers (it needs their contribution to finish the current one).
+constexpr int LZ_MAXRANKS = 16;
+constexpr int LZ_MBOX_SLOTS = 4;
+struct LzMailbox {   // lives in every rank's shared arena (zeroed at allocation)
+  double data[LZ_MBOX_SLOTS][LZ_MAXRANKS][FC_MAXCOLS];
+  unsigned long long flag[LZ_MBOX_SLOTS][LZ_MAXRANKS];
+};
+struct LzXchg {
+  int nranks, rank;                    // nranks <= 1: single GPU, nothing below is used
+  unsigned long long seq;              // sequence number of this exchange (host counter, identical on every rank)
+  LzMailbox* mbox[LZ_MAXRANKS];        // every rank's mailbox as mapped in THIS process (mbox[rank] is local memory)
+};
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// so[0..m) (shared memory, local sums) -> sums over all ranks.  Called by every thread of ONE CTA per rank.
+// m = 0: pure barrier (pass 2: "every rank has finished this step").
+__device__ __forceinline__ void lz_exchange(const LzXchg& x, double* so, int m) {
+  if (x.nranks <= 1) return;
+  const int slot = (int)(x.seq & (LZ_MBOX_SLOTS - 1));
+  __syncthreads();
+  for (int i = threadIdx.x; i < x.nranks * m; i += blockDim.x) {
+    const int p = i / m, c = i % m;
+    x.mbox[p]->data[slot][x.rank][c] = so[c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < x.nranks) {
+    __threadfence_system();
+    st_sys_u64(&x.mbox[threadIdx.x]->flag[slot][x.rank], x.seq);
+    const unsigned long long* mine = &x.mbox[x.rank]->flag[slot][threadIdx.x];
+    while (ld_sys_u64(mine) != x.seq) { __nanosleep(20); }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < m) {
+    double s = 0.0;
+    for (int p = 0; p < x.nranks; ++p) s += ld_sys_f64(&x.mbox[x.rank]->data[slot][p][threadIdx.x]);
+    so[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// fixed-order sum of the per-CTA partial rows (L2 reads: the rows were written by other CTAs of the same launch)
+__device__ __forceinline__ void lz_reduce_rows(const double* partial, int nblocks, int pstride, int m, double* so /*[FC_MAXCOLS]*/,
+                                               double* tmp /*[blockDim.x]*/) {
+  int mp = 32;
+  while (mp < m) mp <<= 1;
+  const int c = threadIdx.x % mp, part = threadIdx.x / mp, nparts = max(1, (int)blockDim.x / mp);
+  double acc0 = 0.0, acc1 = 0.0;
+  if (c < m && part < nparts) {
+    const double* base = partial + c;
+    int b = part;
+    for (; b + nparts < nblocks; b += 2 * nparts) {
+      acc0 += __ldcg(base + (int64_t)b * pstride);
+      acc1 += __ldcg(base + (int64_t)(b + nparts) * pstride);
+    }
+    if (b < nblocks) acc0 += __ldcg(base + (int64_t)b * pstride);
+  }
+  __syncthreads();
+  tmp[threadIdx.x] = acc0 + acc1;
+  __syncthreads();
+  if (part == 0 && c < m) {
+    double t = tmp[c];
+    for (int q = 1; q < nparts; ++q) t += tmp[q * mp + c];
+    so[c] = t;
+  }
+  __syncthreads();
+}
+
+// beta_0 = ||b||  from the (global) sums of |b|^2
+__device__ __forceinline__ void lz_scalars_init(const LzScalars& s, const double* so, int m) {
   const int c = threadIdx.x;
   if (c < m) {
     const double b = sqrt(so[c]);
@@ -483,11 +159,7 @@ __global__ void __launch_bounds__(1024) k_lz_scal_init(LzScalars s, const double
 }
 
 // after LZ_P1 of step j: alpha_j = (u_j . t) / beta_j ; ratio_a = alpha_j / beta_j
-__global__ void __launch_bounds__(1024) k_lz_scal1(LzScalars s, int j, const double* partial, int nblocks, int pstride, int m) {
-  if (*s.done_k != 0) return;
-  __shared__ double so[FC_MAXCOLS];
-  __shared__ double tmp[1024];
-  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+__device__ __forceinline__ void lz_scalars_alpha(const LzScalars& s, int j, const double* so, int m) {
   const int c = threadIdx.x;
   if (c < m) {
     const int64_t o = (int64_t)j * FC_MAXCOLS + c;
@@ -500,12 +172,8 @@ __global__ void __launch_bounds__(1024) k_lz_scal1(LzScalars s, int j, const dou
 }
 
 // after the update of step j: beta_{j+1} = ||u_{j+1}||; a column whose Krylov space is exhausted is frozen (inv = 0);
-// then the shifted-residual recurrences and the convergence flag
-__global__ void __launch_bounds__(1024) k_lz_scal2(LzScalars s, int j, const double* partial, int nblocks, int pstride, int m) {
-  if (*s.done_k != 0) return;
-  __shared__ double so[FC_MAXCOLS];
-  __shared__ double tmp[1024];
-  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+// then the shifted-residual recurrences and the convergence flag.  tmp: [blockDim.x] doubles of shared memory
+__device__ __forceinline__ void lz_scalars_beta(const LzScalars& s, int j, const double* so, int m, double* tmp) {
   const int c = threadIdx.x;
   const int64_t row = (int64_t)j * FC_MAXCOLS;
   if (c < m) {
@@ -552,208 +220,571 @@ __global__ void __launch_bounds__(1024) k_lz_scal2(LzScalars s, int j, const dou
   }
 }
 
-
-
-// =====================================================================================================================
-// Staged gather: the distinct vector rows a tile of <= 16 consecutive matrix rows references are brought into shared
-// memory by bulk asynchronous copies (cp.async.bulk + mbarrier, the TMA 1-D path), double buffered, so the bytes in flight
-// cost no registers and the gather itself is LDS.128 from a dense, conflict-free stage.  The tile plan (which vector rows,
-// as runs of consecutive rows; the stage slot of every stored entry) is computed once per matrix on the host
-// (build_lz_plan in feastcuda.cu).  Tiles are dealt round robin to the CTAs like in k_lz_spmm.
-// One warp = one matrix row of the tile; lanes = column pairs (m in (32, 64] uses all lanes).
-// =====================================================================================================================
-constexpr int LZS_TMAX = 16;        // rows per tile = warps per CTA
-constexpr int LZS_THREADS = 32 * LZS_TMAX;
-
-struct LzPlanDev {
-  const int4* wmeta;            // [ntiles * LZS_TMAX] {row (or -1), p0, count, 0}
-  const int* t_run0;            // [ntiles + 1]
-  const int4* runs;             // {first vector row, count, first slot, 0}
-  const unsigned short* lcol;   // [nnz] stage slot of the entry's column
-  int ntiles;
-  int smax;                     // slots per stage
+// Tail of a producer kernel: the LAST CTA to finish (ticket counter) sums the per-CTA partial rows in a fixed order, exchanges the
+// sums with the other ranks and runs the scalar recurrences that used to be separate one-CTA launches.
+enum LzTailKind { LZ_TAIL_NONE = 0, LZ_TAIL_INIT = 1, LZ_TAIL_ALPHA = 2, LZ_TAIL_BETA = 3, LZ_TAIL_BARRIER = 4 };
+struct LzTail {
+  int kind;          // LzTailKind
+  int j;             // Lanczos step
+  int* ticket;       // device counter, zero between launches
+  LzScalars s;
+  LzXchg x;
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(LZS_THREADS, 2) k_lz_spmm_staged(LzArgs a, LzPlanDev pl) {
-  if (a.done != nullptr && *a.done != 0) return;
-  extern __shared__ __align__(128) unsigned char lzs_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int P = (a.m + 1) >> 1;
-  const int pitch = P * 16;                    // bytes of one staged vector row
-  const unsigned ldu = (unsigned)a.ld;
-  unsigned char* stage[2] = {lzs_smem, lzs_smem + (size_t)pl.smax * pitch};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lzs_smem + (size_t)2 * pl.smax * pitch);
-  __shared__ double2 s_sc[4][FC_MAXCOLS / 2];
-  for (int i = tid; i < 4 * (FC_MAXCOLS / 2); i += LZS_THREADS) {
-    const int w = i / (FC_MAXCOLS / 2), pc = i % (FC_MAXCOLS / 2);
-    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta) : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : a.s_coef));
-    s_sc[w][pc] = lz_scal2(src, 2 * pc, a.m);
-  }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// every thread of the CTA calls this after the CTA's partial row is written (or with nothing written for LZ_TAIL_BARRIER);
+// blockDim.x must be a power of two >= 128
+// scratch: FC_MAXCOLS + blockDim.x doubles of shared memory the caller no longer needs
+__device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, int pstride, int m, double* scratch) {
+  if (t.kind == LZ_TAIL_NONE) return;
+  __shared__ int s_last;
+  double* t_so = scratch;
+  double* t_tmp = scratch + FC_MAXCOLS;
+  if (t.x.nranks > 1) __threadfence_system();   // this CTA's vector rows must be visible to the peers before the flag is raised
+  else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int tk = atomicAdd(t.ticket, 1);
+    s_last = (tk == (int)gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-
-  const int grid = (int)gridDim.x;
-  const int my_tiles = ((int)blockIdx.x < pl.ntiles) ? (pl.ntiles - 1 - (int)blockIdx.x) / grid + 1 : 0;
-  const bool full_width = (a.ld == 2 * (int64_t)P);
-
-  // producer: warp 0 arms the stage's barrier with the byte count, then its lanes issue one bulk copy per run
-  auto issue = [&](int it, int s) {
-    const int tile = (int)blockIdx.x + it * grid;
-    const int r0 = pl.t_run0[tile], r1 = pl.t_run0[tile + 1];
-    if (lane == 0) {
-      const int4 last = pl.runs[r1 - 1];
-      mbar_expect_tx(&bars[s], (unsigned)(last.z + last.y) * (unsigned)pitch);
-    }
-    __syncwarp();
-    for (int r = r0 + lane; r < r1; r += 32) {
-      const int4 ru = pl.runs[r];
-      unsigned char* dst = stage[s] + (size_t)ru.z * pitch;
-      const double* src = a.U + (int64_t)ru.x * a.ld;
-      if (full_width) bulk_g2s(dst, src, (unsigned)ru.y * (unsigned)pitch, &bars[s]);
-      else
-        for (int q = 0; q < ru.y; ++q) bulk_g2s(dst + (size_t)q * pitch, src + (int64_t)q * a.ld, (unsigned)pitch, &bars[s]);
-    }
-  };
-  if (warp == 0) {
-    if (my_tiles > 0) issue(0, 0);
-    if (my_tiles > 1) issue(1, 1);
+  if (!s_last) return;
+  __threadfence();
+  if (t.kind == LZ_TAIL_BARRIER) {
+    lz_exchange(t.x, t_so, 0);
+  } else {
+    lz_reduce_rows(partial, (int)gridDim.x, pstride, m, t_so, t_tmp);
+    lz_exchange(t.x, t_so, m);
+    if (t.kind == LZ_TAIL_INIT) lz_scalars_init(t.s, t_so, m);
+    else if (t.kind == LZ_TAIL_ALPHA) lz_scalars_alpha(t.s, t.j, t_so, m);
+    else lz_scalars_beta(t.s, t.j, t_so, m, t_tmp);
   }
+  if (threadIdx.x == 0) *t.ticket = 0;
+}
 
-  const int pcl = 2 * min(lane, P - 1);
-  const double* Ul = a.U + pcl;
-  const double* Pl = a.prev + pcl;
-  double* Ol = a.out + pcl;
-  double* Ql = a.Q + pcl;
-  const bool lane_ok = lane < P;
-  double2 dot = make_double2(0.0, 0.0);
+// one-CTA forms (matrix-free and generalized paths, whose producers are not fused)
+__global__ void __launch_bounds__(1024) k_lz_scal_init(LzScalars s, const double* partial, int nblocks, int pstride, int m) {
+  __shared__ double so[FC_MAXCOLS];
+  __shared__ double tmp[1024];
+  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+  lz_scalars_init(s, so, m);
+}
+__global__ void __launch_bounds__(1024) k_lz_scal1(LzScalars s, int j, const double* partial, int nblocks, int pstride, int m) {
+  if (*s.done_k != 0) return;
+  __shared__ double so[FC_MAXCOLS];
+  __shared__ double tmp[1024];
+  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+  lz_scalars_alpha(s, j, so, m);
+}
+__global__ void __launch_bounds__(1024) k_lz_scal2(LzScalars s, int j, const double* partial, int nblocks, int pstride, int m) {
+  if (*s.done_k != 0) return;
+  __shared__ double so[FC_MAXCOLS];
+  __shared__ double tmp[1024];
+  reduce_partials<double>(partial, 1, nblocks, pstride, m, so, tmp);
+  lz_scalars_beta(s, j, so, m, tmp);
+}
 
-  // per-warp metadata pipeline: {row, p0, count} two iterations ahead, the row's first 32 (slot, value) pairs one ahead
-  auto meta_of = [&](int it) -> int4 {
-    if (it >= my_tiles) return make_int4(-1, 0, 0, 0);
-    return pl.wmeta[((int64_t)blockIdx.x + (int64_t)it * grid) * LZS_TMAX + warp];
+struct LzArgs {
+  int64_t n;
+  int m;                 // active columns
+  int64_t ld;            // row stride in doubles (even)
+  const int* ptr; const int* col; const void* val;   // val: double (real symmetric) or cx<double> (complex Hermitian)
+  const double* U;       // gathered operand
+  const double* prev;    // own-row operand u_{j-1}; at j = 0 any finite block (the host passes U; ratio_b is 0 there)
+  double* out;           // own-row result (may alias prev)
+  double* Q;             // accumulator (LZ_P2, LZ_RES)
+  const double* s_inv_beta; const double* s_ratio_b; const double* s_ratio_a;   // per-column scalars of this step
+  const double* s_coef;  // LZ_P2: c_j / beta_j ; LZ_RES: rho(theta_c)
+  const double* s_theta; // LZ_RES
+  double* partial;       // [gridDim.x][pstride]
+  int pstride;
+  int tile_rows;         // rows per round-robin tile (rounded to the CTA's rows-per-iteration)
+  const int* done;       // device flag: nonzero once pass 1 has converged -> the launch is a no-op (nullptr: always run)
+  const double* s_coef_prev;   // LZ_P2_PAIR: c_{j-1} / beta_{j-1}
+  const double* own;     // LZ_RES: own-row operand of the theta term (generalized problems: B q); nullptr -> U
+  const double* rhs;     // LZ_CHEB*: right-hand side block (own row)
+  const double* dinv;    // LZ_CHEB*: 1 / diag(M), one double per row
+  double c1, c2;         // LZ_CHEB*: recurrence coefficients of this step
+  LzTail tail;           // what the last CTA does after the row loop (pass 1: the step's scalars; sharded pass 2: the step barrier)
+  // row-sharded runs: `n` rows are this rank's block; the uploaded column index of an entry is (owner rank << LZ_OWNER_SHIFT) | row
+  // local to the owner, resolved once per row stride into `goff`
+  const long long* goff; // row-sharded runs: per stored entry, the byte offset from a local block to the gathered row (k_lz_resolve)
+};
+constexpr int LZ_OWNER_SHIFT = 26;
+struct LzArenas { const char* base[LZ_MAXRANKS]; };   // arena base of every rank as mapped in this process
+__host__ __device__ constexpr bool lz_is_cheb(int mode) { return mode == LZ_CHEB || mode == LZ_CHEB_DOT; }
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+// Element semantics.  Real problems: a 16-byte element is a PAIR of real columns, matrix entries are doubles.  Complex
+// Hermitian problems (CPLX): an element is ONE complex column (re, im), matrix entries are cx<double>; T_k stays real, so
+// the per-column scalars apply to both components and a dot product is the sum of the two component products.
+template <bool CPLX> struct LzVal;
+template <> struct LzVal<false> {
+  typedef double T;
+  static __device__ __forceinline__ T zero() { return 0.0; }
+  static __device__ __forceinline__ T load(const void* v, int i) { return reinterpret_cast<const double*>(v)[i]; }
+  static __device__ __forceinline__ T shfl(unsigned mask, T a, int src, int width) { return __shfl_sync(mask, a, src, width); }
+  static __device__ __forceinline__ void fma_acc(double2& acc, T a, double2 x) { acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); }
+};
+template <> struct LzVal<true> {
+  typedef double2 T;
+  static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
+  static __device__ __forceinline__ T load(const void* v, int i) { return reinterpret_cast<const double2*>(v)[i]; }
+  static __device__ __forceinline__ T shfl(unsigned mask, T a, int src, int width) {
+    return make_double2(__shfl_sync(mask, a.x, src, width), __shfl_sync(mask, a.y, src, width));
+  }
+  static __device__ __forceinline__ void fma_acc(double2& acc, T a, double2 x) {
+    acc.x = fma(a.x, x.x, acc.x); acc.x = fma(-a.y, x.y, acc.x);
+    acc.y = fma(a.x, x.y, acc.y); acc.y = fma(a.y, x.x, acc.y);
+  }
+};
+// per-element scalars from a per-column array: real -> (s[2e], s[2e+1]); complex -> (s[e], s[e])
+template <bool CPLX>
+__device__ __forceinline__ double2 lz_scal(const double* s, int e, int m) {
+  double2 v = make_double2(0.0, 0.0);
+  if (s != nullptr) {
+    if (CPLX) { if (e < m) v.x = v.y = s[e]; }
+    else { if (2 * e < m) v.x = s[2 * e]; if (2 * e + 1 < m) v.y = s[2 * e + 1]; }
+  }
+  return v;
+}
+template <bool CPLX> __device__ __forceinline__ int lz_elems(int m) { return CPLX ? m : ((m + 1) >> 1); }
+
+// acc[k] += sum_p val[p] * U[col[p], pair(g + G k)]  for the stored entries [p0, p1) of `row`, in CSR order.
+// (myo, mya): the group's first G entries, already fetched by the caller one iteration ahead; myo is the ELEMENT offset
+// col*ld of the gathered row (32-bit: the host guarantees n*ld < 2^32), so an address is one IMAD.WIDE from the lane's
+// base pointer Ul[k] = U + 2*(g + G k).  Padding slots of the last batch gather the lane's own row with weight 0 and lanes
+// beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
+// Narrow groups (G <= 4 lanes per row) also receive the row's SECOND chunk of G entries prefetched (myo2, mya2): a
+// 7-point row then needs no dependent metadata load inside the loop even with 4 lanes per row.
+// Row-sharded runs (SHARD): the metadata of an entry is a pre-resolved 64-bit BYTE offset from the local block to the gathered row
+// (k_lz_resolve: (arena[owner] - arena[self]) + local_row * row_bytes; the owner's copy of a block sits at the same arena offset as
+// the local one), so a halo row in a peer's HBM is read by the same load as a local row, over NVLink.
+template <bool SHARD> struct LzOff;
+template <> struct LzOff<false> {
+  typedef unsigned T;
+  static __device__ __forceinline__ T meta(const LzArgs& a, int p, unsigned ldu) { return (unsigned)a.col[p] * ldu; }
+  static __device__ __forceinline__ T own(unsigned eo_own) { return eo_own; }
+  static __device__ __forceinline__ const double* at(const double* base, T o) { return base + o; }
+};
+template <> struct LzOff<true> {
+  typedef long long T;
+  static __device__ __forceinline__ T meta(const LzArgs& a, int p, unsigned) { return a.goff[p]; }
+  static __device__ __forceinline__ T own(unsigned eo_own) { return (long long)eo_own * 8; }
+  static __device__ __forceinline__ const double* at(const double* base, T o) {
+    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + o);
+  }
+};
+
+template <int G, int NC, bool CPLX, bool SHARD>
+__device__ __forceinline__ void lz_gather(const LzArgs& a, unsigned row_eo_, int p0, int p1, typename LzOff<SHARD>::T myo, typename LzVal<CPLX>::T mya,
+                                          typename LzOff<SHARD>::T myo2, typename LzVal<CPLX>::T mya2, int g, unsigned gmask,
+                                          const double* const (&Ul)[NC], double2 (&acc)[NC]) {
+  typedef LzVal<CPLX> V;
+  typedef LzOff<SHARD> OF;
+  constexpr int UN = (G >= 4) ? 4 : G;
+  constexpr bool PF2 = (G <= 4);
+  const unsigned ldu = (unsigned)a.ld;
+  const typename OF::T row_eo = OF::own(row_eo_);
+  for (int pb = p0; pb < p1; pb += G) {
+    const int cnt = min(G, p1 - pb);
+    if (PF2 && pb == p0 + G) {
+      myo = myo2;
+      mya = mya2;
+    } else if (pb != p0) {
+      myo = row_eo;
+      mya = V::zero();
+      if (g < cnt) { myo = OF::meta(a, pb + g, ldu); mya = V::load(a.val, pb + g); }
+    }
+    for (int t = 0; t < cnt; t += UN) {
+      typename OF::T eo[UN];
+      typename V::T aa[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        eo[u] = __shfl_sync(gmask, myo, t + u, G);
+        aa[u] = V::shfl(gmask, mya, t + u, G);
+      }
+      double2 xv[UN][NC];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) xv[u][k] = ldg2(OF::at(Ul[k], eo[u]));
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) V::fma_acc(acc[k], aa[u], xv[u][k]);
+    }
+  }
+}
+
+__device__ __forceinline__ double2 lz_scal2(const double* s, int c0, int m) {
+  double2 v = make_double2(0.0, 0.0);
+  if (s != nullptr) {
+    if (c0 < m) v.x = s[c0];
+    if (c0 + 1 < m) v.y = s[c0 + 1];
+  }
+  return v;
+}
+
+// the two Lanczos vector updates, shared by pass 1 (split over two kernels) and pass 2 (fused): identical rounding
+__device__ __forceinline__ double2 lz_t(double2 acc, double2 ib, double2 rb, double2 pv) {
+  double2 t;
+  t.x = __fma_rn(-rb.x, pv.x, __dmul_rn(acc.x, ib.x));
+  t.y = __fma_rn(-rb.y, pv.y, __dmul_rn(acc.y, ib.y));
+  return t;
+}
+__device__ __forceinline__ double2 lz_next(double2 t, double2 ra, double2 uo) {
+  double2 r;
+  r.x = __fma_rn(-ra.x, uo.x, t.x);
+  r.y = __fma_rn(-ra.y, uo.y, t.y);
+  return r;
+}
+
+template <int G, int NC, int MODE, int THREADS, bool CPLX = false, bool SHARD = false>
+__global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_spmm(LzArgs a) {
+  typedef LzVal<CPLX> V;
+  typedef LzOff<SHARD> OF;
+  typedef typename OF::T off_t;
+  if (a.done != nullptr && *a.done != 0) return;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
+  constexpr unsigned gm0 = (G >= 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  const unsigned gmask = gm0 << (sub * G);
+  const int wib = threadIdx.x >> 5, wpb = THREADS >> 5;
+  constexpr int STEP = (THREADS / 32) * RPW;          // rows the CTA covers per iteration
+  const int P = lz_elems<CPLX>(a.m);                  // 16-byte elements per row: column pairs (real) or complex columns
+  const int n = (int)a.n;
+  // Rows are dealt to the CTAs in tiles of `tile_rows` consecutive rows, round robin: the whole grid sweeps the matrix as
+  // one moving front, so a vector row fetched as somebody's far neighbour is still in L2 when the front reaches it
+  // (each row of U comes from HBM once), while the near neighbours of a tile stay in the CTA's L1.
+  const int spt = max(1, a.tile_rows / STEP);         // iterations per tile
+  const int TR = spt * STEP;
+  const int ntiles = (n + TR - 1) / TR;
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int niter = my_tiles * spt;
+  // iteration -> row, advanced incrementally (no integer divisions in the loop): `base_f` is the first row of the CTA's
+  // iteration `it_f`, the furthest one the metadata pipeline has looked at
+  const int lane_row = wib * RPW + sub;
+  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR;
+  auto next_row = [&]() -> int {
+    const int r = (it_f < niter) ? base_f + lane_row : n;
+    ++it_f;
+    if (++s_f == spt) { s_f = 0; base_f += ((int)gridDim.x - 1) * TR + STEP; }
+    else base_f += STEP;
+    return r < n ? r : n;
   };
-  int4 m_cur = meta_of(0), m_nxt = meta_of(1);
-  int l_cur = 0;
-  double a_cur = 0.0;
-  if (lane < m_cur.z) { l_cur = pl.lcol[m_cur.y + lane]; a_cur = reinterpret_cast<const double*>(a.val)[m_cur.y + lane]; }
 
-  for (int it = 0; it < my_tiles; ++it) {
-    const int s = it & 1;
-    const int4 m_fut = meta_of(it + 2);
-    int l_nxt = 0;
-    double a_nxt = 0.0;
-    if (lane < m_nxt.z) { l_nxt = pl.lcol[m_nxt.y + lane]; a_nxt = reinterpret_cast<const double*>(a.val)[m_nxt.y + lane]; }
-    const int row = m_cur.x;
-    const bool valid = row >= 0;
+  // per-column scalars of this step live in shared memory (one 16-byte read per use instead of 20 live registers)
+  constexpr int SCW = CPLX ? FC_MAXCOLS : FC_MAXCOLS / 2;   // elements per row: complex columns or real column pairs
+  __shared__ double2 s_sc[5][SCW];   // [0] inv_beta | theta, [1] ratio_b, [2] ratio_a, [3] coef, [4] coef of the previous step
+  for (int i = threadIdx.x; i < 5 * SCW; i += THREADS) {
+    const int w = i / SCW, pc = i % SCW;
+    const double* src = (w == 0) ? (MODE == LZ_RES ? a.s_theta : a.s_inv_beta)
+                                 : (w == 1 ? a.s_ratio_b : (w == 2 ? a.s_ratio_a : (w == 3 ? a.s_coef : a.s_coef_prev)));
+    s_sc[w][pc] = lz_scal<CPLX>(src, pc, a.m);
+  }
+  __syncthreads();
+  double2 dot[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
+
+  // software pipeline over the CSR metadata: row pointers two iterations ahead, the first G (offset, val) pairs one
+  // iteration ahead, so the vector gathers of an iteration never wait behind a pointer chase.  (Measured on B200: a
+  // deeper pipeline with L2 prefetch of the next iteration's rows costs more in registers/spills than it hides.)
+  const unsigned ldu = (unsigned)a.ld;
+  const double* Ul[NC];
+  const double* Pl[NC];   // prev: never null (the host passes U with ratio_b = 0 at j = 0)
+  double* Ol[NC];
+  double* Ql[NC];
+  const double* Wl[NC];   // LZ_RES: own-row operand of the theta term; LZ_CHEB*: the right-hand side
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int pcl = 2 * min(g + G * k, P - 1);
+    Ul[k] = a.U + pcl;
+    Pl[k] = a.prev + pcl;
+    Ol[k] = a.out + pcl;
+    Ql[k] = a.Q + pcl;
+    Wl[k] = (lz_is_cheb(MODE) ? a.rhs : (a.own != nullptr ? a.own : a.U)) + pcl;
+  }
+  int r_cur = next_row(), r_nxt = next_row();
+  int p0_cur = 0, p1_cur = 0, p0_nxt = 0, p1_nxt = 0;
+  if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
+  if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
+  constexpr bool PF2 = (G <= 4);
+  off_t o_cur = OF::own((r_cur < n ? (unsigned)r_cur : 0u) * ldu), o_cur2 = o_cur;
+  typename V::T a_cur = V::zero(), a_cur2 = V::zero();
+  if (g < p1_cur - p0_cur) { o_cur = OF::meta(a, p0_cur + g, ldu); a_cur = V::load(a.val, p0_cur + g); }
+  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = OF::meta(a, p0_cur + G + g, ldu); a_cur2 = V::load(a.val, p0_cur + G + g); }
+
+  for (int it = 0; it < niter; ++it) {
+    const int row = r_cur;
+    const bool valid = row < n;
+    const int r_fut = next_row();
+    int p0_fut = 0, p1_fut = 0;
+    if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
+    off_t o_nxt = OF::own((r_nxt < n ? (unsigned)r_nxt : 0u) * ldu), o_nxt2 = o_nxt;
+    typename V::T a_nxt = V::zero(), a_nxt2 = V::zero();
+    if (g < p1_nxt - p0_nxt) { o_nxt = OF::meta(a, p0_nxt + g, ldu); a_nxt = V::load(a.val, p0_nxt + g); }
+    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = OF::meta(a, p0_nxt + G + g, ldu); a_nxt2 = V::load(a.val, p0_nxt + G + g); }
+
+    // own-row operands first (independent of the gather); invalid rows and inactive lanes read valid dummies
     const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
-    double2 uo = make_double2(0.0, 0.0), pv = make_double2(0.0, 0.0), qv = make_double2(0.0, 0.0);
-    if (valid) {
-      if constexpr (MODE != LZ_PLAIN) uo = ldg2(Ul + eo_own);
-      if constexpr (MODE == LZ_P1 || MODE == LZ_P2) pv = ldg2(Pl + eo_own);
-      if constexpr (MODE == LZ_P2) qv = ldg2(Ql + eo_own);
+    double2 acc[NC], uo[NC], pv[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      acc[k] = make_double2(0.0, 0.0);
+      if constexpr (MODE == LZ_RES) uo[k] = ldg2(Wl[k] + eo_own);
+      else if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
+      if constexpr (MODE == LZ_P1 || lz_is_p2(MODE) || lz_is_cheb(MODE)) pv[k] = ldg2(Pl[k] + eo_own);
     }
-    mbar_wait(&bars[s], (unsigned)((it >> 1) & 1));
-    double2 acc = make_double2(0.0, 0.0);
-    if (valid) {
-      const unsigned char* sb = stage[s] + (lane_ok ? lane : P - 1) * 16;
-      const int p0 = m_cur.y, cnt_all = m_cur.z;
-      int myl = l_cur;
-      double mya = a_cur;
-      for (int pb = 0; pb < cnt_all; pb += 32) {
-        const int cnt = min(32, cnt_all - pb);
-        if (pb != 0) {
-          myl = 0;
-          mya = 0.0;
-          if (lane < cnt) { myl = pl.lcol[p0 + pb + lane]; mya = reinterpret_cast<const double*>(a.val)[p0 + pb + lane]; }
-        }
-        for (int t = 0; t < cnt; t += 4) {
-          int sl[4];
-          double aa[4];
+    double2 rh[NC];
+    double di = 0.0;
+    if constexpr (lz_is_cheb(MODE)) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            sl[u] = __shfl_sync(0xffffffffu, myl, t + u);
-            aa[u] = __shfl_sync(0xffffffffu, mya, t + u);     // lanes >= cnt hold weight 0 and slot 0 (always staged)
-          }
-          double2 xv[4];
+      for (int k = 0; k < NC; ++k) rh[k] = ldg2(Wl[k] + eo_own);
+      di = a.dinv[valid ? row : 0] * a.c2;
+    }
+    lz_gather<G, NC, CPLX, SHARD>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) xv[u] = *reinterpret_cast<const double2*>(sb + (size_t)sl[u] * pitch);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc.x = fma(aa[u], xv[u].x, acc.x);
-            acc.y = fma(aa[u], xv[u].y, acc.y);
-          }
-        }
-      }
-      if (lane_ok) {
+    for (int k = 0; k < NC; ++k) {
+      const int pc = g + G * k;
+      if (valid && pc < P) {
         if constexpr (MODE == LZ_PLAIN) {
-          stg2(Ol + eo_own, acc);
+          stg2(Ol[k] + eo_own, acc[k]);
+        } else if constexpr (lz_is_cheb(MODE)) {
+          double2 o;
+          o.x = fma(di, rh[k].x - acc[k].x, fma(a.c1, uo[k].x - pv[k].x, uo[k].x));
+          o.y = fma(di, rh[k].y - acc[k].y, fma(a.c1, uo[k].y - pv[k].y, uo[k].y));
+          stg2(Ol[k] + eo_own, o);
+          if constexpr (MODE == LZ_CHEB_DOT) {
+            dot[k].x = fma(o.x, rh[k].x, dot[k].x);
+            dot[k].y = fma(o.y, rh[k].y, dot[k].y);
+          }
         } else if constexpr (MODE == LZ_RES) {
-          const double2 th = s_sc[0][lane], cf = s_sc[3][lane];
+          const double2 th = s_sc[0][pc], cf = s_sc[3][pc];
           double2 t;
-          t.x = __fma_rn(-th.x, uo.x, acc.x);
-          t.y = __fma_rn(-th.y, uo.y, acc.y);
-          stg2(Ol + eo_own, t);
-          dot.x = fma(t.x, t.x, dot.x);
-          dot.y = fma(t.y, t.y, dot.y);
-          if (a.Q != nullptr) stg2(Ql + eo_own, make_double2(cf.x * uo.x, cf.y * uo.y));
+          t.x = __fma_rn(-th.x, uo[k].x, acc[k].x);
+          t.y = __fma_rn(-th.y, uo[k].y, acc[k].y);
+          stg2(Ol[k] + eo_own, t);
+          dot[k].x = fma(t.x, t.x, dot[k].x);
+          dot[k].y = fma(t.y, t.y, dot[k].y);
+          if (a.Q != nullptr) stg2(Ql[k] + eo_own, make_double2(cf.x * uo[k].x, cf.y * uo[k].y));
         } else {
-          const double2 t = lz_t(acc, s_sc[0][lane], s_sc[1][lane], pv);
+          const double2 t = lz_t(acc[k], s_sc[0][pc], s_sc[1][pc], pv[k]);
           if constexpr (MODE == LZ_P1) {
-            stg2(Ol + eo_own, t);
-            dot.x = fma(uo.x, t.x, dot.x);
-            dot.y = fma(uo.y, t.y, dot.y);
+            stg2(Ol[k] + eo_own, t);
+            dot[k].x = fma(uo[k].x, t.x, dot[k].x);
+            dot[k].y = fma(uo[k].y, t.y, dot[k].y);
           } else {
-            const double2 cf = s_sc[3][lane];
-            stg2(Ol + eo_own, lz_next(t, s_sc[2][lane], uo));
-            qv.x = fma(cf.x, uo.x, qv.x);
-            qv.y = fma(cf.y, uo.y, qv.y);
-            stg2(Ql + eo_own, qv);
+            stg2(Ol[k] + eo_own, lz_next(t, s_sc[2][pc], uo[k]));
+            if constexpr (MODE != LZ_P2_SKIP) {
+              const double2 cf = s_sc[3][pc];
+              double2 q = ldg2(Ql[k] + eo_own);
+              if constexpr (MODE == LZ_P2_PAIR) {
+                const double2 cp = s_sc[4][pc];
+                q.x = fma(cp.x, pv[k].x, q.x);
+                q.y = fma(cp.y, pv[k].y, q.y);
+              }
+              q.x = fma(cf.x, uo[k].x, q.x);
+              q.y = fma(cf.y, uo[k].y, q.y);
+              stg2(Ql[k] + eo_own, q);
+            }
           }
         }
       }
     }
-    __syncthreads();                                            // every warp is done reading stage s
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 0 && it + 2 < my_tiles) issue(it + 2, s);
-    m_cur = m_nxt; m_nxt = m_fut; l_cur = l_nxt; a_cur = a_nxt;
+    r_cur = r_nxt; p0_cur = p0_nxt; p1_cur = p1_nxt; o_cur = o_nxt; a_cur = a_nxt; o_cur2 = o_nxt2; a_cur2 = a_nxt2;
+    r_nxt = r_fut; p0_nxt = p0_fut; p1_nxt = p1_fut;
   }
 
-  if constexpr (MODE == LZ_P1 || MODE == LZ_RES) {
-    __shared__ double2 red[LZS_TMAX * 32];
-    red[warp * 32 + lane] = dot;
+  __shared__ double2 red[(THREADS / 32) * 32 * NC];   // CTA reduction of the dot products, then the tail's scratch
+  if constexpr (MODE == LZ_P1 || MODE == LZ_RES || MODE == LZ_CHEB_DOT) {
+    // fixed-order CTA reduction: every launch sums in the same order (pass 2 relies on pass 1's exact scalars)
+    const int width = G * NC;   // pairs per row group
+#pragma unroll
+    for (int k = 0; k < NC; ++k) red[(wib * RPW + sub) * width + g + G * k] = dot[k];
     __syncthreads();
-    for (int pc = tid; pc < 32; pc += LZS_THREADS) {
+    const int ngroups = wpb * RPW;
+    for (int pc = threadIdx.x; pc < width; pc += THREADS) {
       if (pc < P) {
         double sx = 0.0, sy = 0.0;
-        for (int q = 0; q < LZS_TMAX; ++q) { const double2 v = red[q * 32 + pc]; sx += v.x; sy += v.y; }
-        double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
-        o[0] = sx;
-        if (2 * pc + 1 < a.m) o[1] = sy;
+        for (int q = 0; q < ngroups; ++q) { const double2 v = red[q * width + pc]; sx += v.x; sy += v.y; }
+        if (CPLX) a.partial[(int64_t)blockIdx.x * a.pstride + pc] = sx + sy;   // Re(conj(u) t) = sum of both components
+        else {
+          double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
+          o[0] = sx;
+          if (2 * pc + 1 < a.m) o[1] = sy;
+        }
       }
+    }
+  }
+  __syncthreads();
+  lz_tail(a.tail, a.partial, a.pstride, a.m, reinterpret_cast<double*>(red));
+}
+
+// ---- elementwise kernels on real blocks: a thread owns one column PAIR, rows strided ---------------------
+struct EwMap2 {
+  int pc, rsub, rpb;
+  __device__ __forceinline__ EwMap2(int pp) { pc = threadIdx.x % pp; rsub = threadIdx.x / pp; rpb = blockDim.x / pp; }
+};
+
+template <bool CPLX>
+__device__ __forceinline__ void block_reduce_pairs(double2 v, int pp, int P, int m, double* out_row) {
+  __shared__ double2 red2[256];
+  __syncthreads();
+  red2[threadIdx.x] = v;
+  __syncthreads();
+  if ((int)threadIdx.x < pp && (int)threadIdx.x < P) {
+    double sx = 0.0, sy = 0.0;
+    for (int q = threadIdx.x; q < (int)blockDim.x; q += pp) { sx += red2[q].x; sy += red2[q].y; }
+    if (CPLX) out_row[threadIdx.x] = sx + sy;
+    else {
+      out_row[2 * threadIdx.x] = sx;
+      if (2 * (int)threadIdx.x + 1 < m) out_row[2 * threadIdx.x + 1] = sy;
+    }
+  }
+}
+
+// pass 1, second half of a step: T (in place) <- T - ratio_a * U ; partial = |T|^2
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_ratio_a,
+                                                   const double* __restrict__ U, double* __restrict__ T,
+                                                   double* __restrict__ partial, int pstride, const int* __restrict__ done,
+                                                   LzTail tail) {
+  if (done != nullptr && *done != 0) return;
+  EwMap2 e(pp);
+  const int P = lz_elems<CPLX>(m);
+  double2 acc = make_double2(0.0, 0.0);
+  if (e.pc < P) {
+    const double2 ra = lz_scal<CPLX>(s_ratio_a, e.pc, m);
+    const int64_t stride = (int64_t)gridDim.x * e.rpb;
+    int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub;
+    for (; row + 3 * stride < n; row += 4 * stride) {   // four independent rows in flight per thread (narrow blocks are latency bound)
+      double2 tv[4], uv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t off = (row + q * stride) * ld + 2 * e.pc;
+        tv[q] = ldg2(T + off);
+        uv[q] = ldg2(U + off);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t off = (row + q * stride) * ld + 2 * e.pc;
+        const double2 r = lz_next(tv[q], ra, uv[q]);
+        stg2(T + off, r);
+        acc.x = fma(r.x, r.x, acc.x);
+        acc.y = fma(r.y, r.y, acc.y);
+      }
+    }
+    for (; row < n; row += stride) {
+      const int64_t off = row * ld + 2 * e.pc;
+      const double2 r = lz_next(ldg2(T + off), ra, ldg2(U + off));
+      stg2(T + off, r);
+      acc.x = fma(r.x, r.x, acc.x);
+      acc.y = fma(r.y, r.y, acc.y);
+    }
+  }
+  block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
+  __shared__ double tail_scratch[FC_MAXCOLS + 256];
+  lz_tail(tail, partial, pstride, m, tail_scratch);
+}
+
+// Q += coef * U  (last pass-2 step: no further Lanczos vector is needed)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_lz_axpy(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_coef,
+                                                 const double* __restrict__ U, double* __restrict__ Q) {
+  EwMap2 e(pp);
+  const int P = lz_elems<CPLX>(m);
+  if (e.pc >= P) return;
+  const double2 cf = lz_scal<CPLX>(s_coef, e.pc, m);
+  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+    const int64_t off = row * ld + 2 * e.pc;
+    const double2 u = ldg2(U + off);
+    double2 q = ldg2(Q + off);
+    q.x = fma(cf.x, u.x, q.x);
+    q.y = fma(cf.y, u.y, q.y);
+    stg2(Q + off, q);
+  }
+}
+
+// first Chebyshev step from X_0 = 0:  X = c * dinv[row] * R
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_lz_cheb_first(int64_t n, int m, int pp, int64_t ld, double c, const double* __restrict__ dinv,
+                                                       const double* __restrict__ R, double* __restrict__ X, const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  EwMap2 e(pp);
+  const int P = lz_elems<CPLX>(m);
+  if (e.pc >= P) return;
+  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+    const int64_t off = row * ld + 2 * e.pc;
+    const double f = c * dinv[row];
+    const double2 r = ldg2(R + off);
+    stg2(X + off, make_double2(f * r.x, f * r.y));
+  }
+}
+
+// engine block (complex storage, row stride ldz) -> compact Lanczos block.  Real problems keep the real part of the m columns
+// as column pairs (the pad column of an odd m is zeroed); complex problems copy the m complex columns.  partial = |x|^2
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_lz_real_part(int64_t n, int m, int pp, int64_t ldz, int64_t ld,
+                                                      const cx<double>* __restrict__ Z, double* __restrict__ X,
+                                                      double* __restrict__ partial, int pstride, LzTail tail) {
+  EwMap2 e(pp);
+  const int P = lz_elems<CPLX>(m);
+  double2 acc = make_double2(0.0, 0.0);
+  if (e.pc < P) {
+    for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+      double2 v;
+      if (CPLX) {
+        const cx<double> z = Z[row * ldz + e.pc];
+        v = make_double2(z.x, z.y);
+      } else {
+        const int c0 = 2 * e.pc;
+        v.x = Z[row * ldz + c0].x;
+        v.y = (c0 + 1 < m) ? Z[row * ldz + c0 + 1].x : 0.0;
+      }
+      stg2(X + row * ld + 2 * e.pc, v);
+      acc.x = fma(v.x, v.x, acc.x);
+      acc.y = fma(v.y, v.y, acc.y);
+    }
+  }
+  if (partial != nullptr) block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
+  __shared__ double tail_scratch[FC_MAXCOLS + 256];
+  lz_tail(tail, partial, pstride, m, tail_scratch);
+}
+
+// cross-rank barrier of row-sharded runs (before a kernel gathers rows that the peers' previous kernel wrote)
+__global__ void __launch_bounds__(128) k_lz_barrier(LzXchg x) {
+  __shared__ double dummy[1];
+  lz_exchange(x, dummy, 0);
+}
+
+// pre-resolved gather offsets of a row-sharded operator: enc = (owner << LZ_OWNER_SHIFT) | row local to the owner
+__global__ void __launch_bounds__(256) k_lz_resolve(int64_t nnz, const int* __restrict__ enc, long long row_bytes, int self,
+                                                    LzArenas ar, long long* __restrict__ goff) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned e = (unsigned)enc[i];
+    const int owner = (int)(e >> LZ_OWNER_SHIFT);
+    const long long local = (long long)(e & ((1u << LZ_OWNER_SHIFT) - 1u));
+    goff[i] = (long long)(ar.base[owner] - ar.base[self]) + local * row_bytes;
+  }
+}
+
+// compact Lanczos block -> engine block (real problems: zero imaginary part)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_lz_to_complex(int64_t n, int m, int pp, int64_t ld, int64_t ldz,
+                                                       const double* __restrict__ X, cx<double>* __restrict__ Z) {
+  EwMap2 e(pp);
+  const int P = lz_elems<CPLX>(m);
+  if (e.pc >= P) return;
+  for (int64_t row = (int64_t)blockIdx.x * e.rpb + e.rsub; row < n; row += (int64_t)gridDim.x * e.rpb) {
+    const double2 v = ldg2(X + row * ld + 2 * e.pc);
+    if (CPLX) Z[row * ldz + e.pc] = mk<double>(v.x, v.y);
+    else {
+      const int c0 = 2 * e.pc;
+      Z[row * ldz + c0] = mk<double>(v.x, 0.0);
+      if (c0 + 1 < m) Z[row * ldz + c0 + 1] = mk<double>(v.y, 0.0);
     }
   }
 }

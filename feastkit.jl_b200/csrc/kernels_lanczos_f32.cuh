@@ -37,6 +37,7 @@ struct LzArgs32 {
   int tile_rows;
   const int* done;
   const double* s_coef_prev;   // LZ_P2_PAIR: c_{j-1} / beta_{j-1}
+  LzTail tail;           // pass 1: the step's scalar recurrences, run by the last CTA (kernels_lanczos.cuh)
 };
 
 __device__ __forceinline__ float4 ldg4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -227,9 +228,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
     r_nxt = r_fut; p0_nxt = p0_fut; p1_nxt = p1_fut;
   }
 
+  __shared__ double red[(THREADS / 32) * 32 * 4];
   if constexpr (MODE == LZ_P1) {
     // fixed-order CTA reduction (pass 2 relies on pass 1's exact scalars)
-    __shared__ double red[(THREADS / 32) * 32 * 4];
     const int width = 4 * G;   // columns per row group
 #pragma unroll
     for (int q = 0; q < 4; ++q) red[(wib * RPW + sub) * width + 4 * g + q] = dot[q];
@@ -243,6 +244,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
       }
     }
   }
+  __syncthreads();
+  lz_tail(a.tail, a.partial, a.pstride, a.m, red);
 }
 
 // ---- elementwise kernels: a thread owns one 4-column element, rows strided (pp = power of two >= elements per row) -------
@@ -265,7 +268,7 @@ __device__ __forceinline__ void block_reduce_quads(const double (&v)[4], int pp,
 // pass 1, second half of a step: T (in place) <- T - ratio_a * U ; partial = |T|^2
 __global__ void __launch_bounds__(256) k_lz32_update(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_ratio_a,
                                                      const float* __restrict__ U, float* __restrict__ T, double* __restrict__ partial,
-                                                     int pstride, const int* __restrict__ done) {
+                                                     int pstride, const int* __restrict__ done, LzTail tail) {
   if (done != nullptr && *done != 0) return;
   EwMap2 e(pp);
   const int P = (m + 3) >> 2;
@@ -298,6 +301,8 @@ __global__ void __launch_bounds__(256) k_lz32_update(int64_t n, int m, int pp, i
     }
   }
   block_reduce_quads(acc, pp, m, partial + (int64_t)blockIdx.x * pstride);
+  __shared__ double tail_scratch[FC_MAXCOLS + 256];
+  lz_tail(tail, partial, pstride, m, tail_scratch);
 }
 
 // Q (double) += coef * U (float)   (last pass-2 step)

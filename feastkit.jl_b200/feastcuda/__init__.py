@@ -317,11 +317,36 @@ class Engine:
         self._ck(self.lib.feastcuda_nccl_init(self.h, dist.get_world_size(), dist.get_rank(), raw))
         self.distributed = True
 
+    def set_row_sharding(self, on=True):
+        """Row-sharded multi-GPU mode (feastcuda_set_row_sharding): call after init_distributed; a no-op on one rank."""
+        self._ck(self.lib.feastcuda_set_row_sharding(self.h, int(bool(on))))
+        self.row_sharded = bool(on) and self.distributed
+
+    def row_range(self):
+        """(row0, nrows, nglobal): this rank's block of rows (the whole matrix without row sharding)."""
+        a = np.zeros(3, dtype=np.int64)
+        self._ck(self.lib.feastcuda_row_range(self.h, L.iptr(a[0:1]), L.iptr(a[1:2]), L.iptr(a[2:3])))
+        return int(a[0]), int(a[1]), int(a[2])
+
+    def _gather_rows(self, X):
+        """Row-sharded results: every rank holds its own rows of X; fill in the others (torch.distributed all_reduce of the zero-padded
+        block -- the drop-in API returns the full eigenvectors on every rank like the reference's MPI drivers)."""
+        import torch
+        import torch.distributed as dist
+        row0, nrows, _ = self.row_range()
+        full = np.zeros_like(X)
+        full[row0:row0 + nrows] = X[row0:row0 + nrows]
+        t = torch.from_numpy(np.ascontiguousarray(full).view(np.float64))
+        if dist.get_backend() == "nccl":
+            t = t.cuda(self.device)
+        dist.all_reduce(t)
+        return t.cpu().numpy().view(X.dtype).reshape(X.shape)
+
     # -- solves
     @staticmethod
     def make_opts(solver="bicgstab", solver_tol=0.0, solver_maxiter=500, solver_restart=3, inner_rel=0.0, ritz_guess=False,
                   filter="reference", shard="nodes", check_every=8, q0_real=False, x_real=False, inner_rel0=0.0, maxiter0=0,
-                  keep_going=False, adaptive=False, eps_floor=0.0, mixed=False):
+                  keep_going=False, adaptive=False, eps_floor=0.0, mixed=False, b_delta=0.0):
         o = SolverOpts()
         o.solver = {"direct": SOLVER_DIRECT, "bicgstab": SOLVER_BICGSTAB, "mslanczos": SOLVER_MSLANCZOS}[solver]
         o.tol = float(solver_tol)
@@ -330,7 +355,7 @@ class Engine:
         o.inner_rel = float(inner_rel)
         o.ritz_guess = int(bool(ritz_guess))
         o.filter = FILTER_TRUE if filter == "true" else FILTER_REFERENCE
-        o.shard = {"nodes": SHARD_NODES, "columns": SHARD_COLUMNS, "balanced": SHARD_BALANCED}[shard]
+        o.shard = {"nodes": SHARD_NODES, "columns": SHARD_COLUMNS, "balanced": SHARD_BALANCED, "rows": SHARD_COLUMNS}[shard]
         o.check_every = int(check_every)
         o.q0_real = int(bool(q0_real))
         o.x_real = int(bool(x_real))
@@ -339,6 +364,7 @@ class Engine:
         o.keep_going = int(bool(keep_going))
         o.adaptive = int(bool(adaptive))
         o.eps_floor = float(eps_floor)
+        o.b_delta = float(b_delta)
         o.mixed = 2 if mixed == "fpm" else int(bool(mixed))      # "fpm": follow fpm[42] (core/feast_parameters.jl:316-319)
         return o
 
@@ -378,7 +404,11 @@ class Engine:
         return lam[:M].copy(), X[:, :M].copy(), res[:M].copy()
 
     def solve_interval(self, Emin, Emax, M0, fpm, Zne, Wne, Q0=None, x_real=False, **kw):
-        """One C-ABI call with HOST buffers in and out (the end-to-end path).  The returned stats describe this solve."""
+        """One C-ABI call with HOST buffers in and out (the end-to-end path).  The returned stats describe this solve.
+        shard="rows" (multi-rank runs): row-sharded mode; gather_rows=False leaves only this rank's rows of q filled."""
+        gather_rows = kw.pop("gather_rows", True)
+        if self.distributed:
+            self.set_row_sharding(kw.get("shard") == "rows")
         self.reset_stats()
         a = L.fpm_array(fpm)
         Z = _as_z(Zne)
@@ -405,7 +435,10 @@ class Engine:
         for i in range(64):
             fpm[i] = int(a[i])
         m = int(M[0])
-        return FeastResult(lam[:m].copy(), X[:, :m].copy(), m, res[:m].copy(), int(info[0]), float(eps[0]), int(loop[0]), self.stats())
+        Xm = X[:, :m].copy()
+        if getattr(self, "row_sharded", False) and gather_rows and m > 0:
+            Xm = self._gather_rows(Xm)
+        return FeastResult(lam[:m].copy(), Xm, m, res[:m].copy(), int(info[0]), float(eps[0]), int(loop[0]), self.stats())
 
     def solve_contour(self, Emid, r, M0, fpm, Zne, Wne, Q0=None, **kw):
         """General (non-Hermitian) solve, one C-ABI call with host buffers (feastcuda_solve_contour)."""

@@ -16,16 +16,17 @@ A, B = 0, 1
 CSR, CSC = 0, 1
 SYM, HERM, GEN = 0, 1, 2
 SOLVER_DIRECT, SOLVER_BICGSTAB, SOLVER_MSLANCZOS = 0, 1, 2
-KERN_NAMES = ("spmm_z", "lz_p1", "lz_upd", "lz_p2", "lz_res", "k5", "k6", "k7")
+KERN_NAMES = ("spmm_z", "lz_p1", "lz_upd", "lz_p2", "lz_res", "lz_cheb", "k6", "k7")
 FILTER_REFERENCE, FILTER_TRUE = 0, 1
-SHARD_NODES, SHARD_COLUMNS, SHARD_BALANCED = 0, 1, 2
+SHARD_NODES, SHARD_COLUMNS, SHARD_BALANCED = 0, 1, 2      # "rows" is a mode of the handle (feastcuda_set_row_sharding)
 
 
 class SolverOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("tol", C.c_double), ("maxiter", C.c_int32), ("restart", C.c_int32),
                 ("inner_rel", C.c_double), ("ritz_guess", C.c_int32), ("filter", C.c_int32), ("shard", C.c_int32),
                 ("check_every", C.c_int32), ("q0_real", C.c_int32), ("x_real", C.c_int32), ("inner_rel0", C.c_double),
-                ("maxiter0", C.c_int32), ("keep_going", C.c_int32), ("adaptive", C.c_int32), ("mixed", C.c_int32), ("eps_floor", C.c_double)]
+                ("maxiter0", C.c_int32), ("keep_going", C.c_int32), ("adaptive", C.c_int32), ("mixed", C.c_int32), ("eps_floor", C.c_double),
+                ("b_delta", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -38,7 +39,7 @@ class Stats(C.Structure):
                 ("bytes_spmm_alg", C.c_double), ("node_iters", C.c_int64 * 128),
                 ("lz_steps_p1", C.c_int64), ("lz_steps_p2", C.c_int64), ("ms_lz_p1", C.c_double), ("ms_lz_p2", C.c_double),
                 ("ms_kern", C.c_double * 8), ("n_kern", C.c_int64 * 8), ("bytes_kern", C.c_double * 8), ("ms_dev_run", C.c_double),
-                ("lz_steps_fp32", C.c_int64)]
+                ("lz_steps_fp32", C.c_int64), ("cheb_degree", C.c_int64)]
 
     def as_dict(self):
         arrays = ("node_iters", "ms_kern", "n_kern", "bytes_kern")
@@ -103,6 +104,8 @@ SIGNATURES = {
     "feastcuda_nccl_unique_id": [C.c_char_p],
     "feastcuda_nccl_init": [_vp, C.c_int, C.c_int, C.c_char_p],
     "feastcuda_node_partition": [C.c_int64, C.c_int, C.c_int, _ip, _ip],
+    "feastcuda_set_row_sharding": [_vp, C.c_int],
+    "feastcuda_row_range": [_vp, _ip, _ip, _ip],
     "feastcuda_get_stats": [_vp, C.POINTER(Stats)],
     "feastcuda_reset_stats": [_vp],
 }

@@ -19,7 +19,7 @@ const FEASTCUDA_SYM, FEASTCUDA_HERM, FEASTCUDA_GEN = Cint(0), Cint(1), Cint(2)
 const SOLVER_DIRECT, SOLVER_BICGSTAB, SOLVER_MSLANCZOS = Cint(0), Cint(1), Cint(2)
 const FILTER_REFERENCE, FILTER_TRUE = Cint(0), Cint(1)
 
-struct SolverOpts              # feastcuda_solver_opts (88 bytes, C layout)
+struct SolverOpts              # feastcuda_solver_opts (96 bytes, C layout)
     solver::Cint
     tol::Cdouble
     maxiter::Cint
@@ -37,6 +37,7 @@ struct SolverOpts              # feastcuda_solver_opts (88 bytes, C layout)
     adaptive::Cint
     mixed::Cint
     eps_floor::Cdouble
+    b_delta::Cdouble           # generalized Lanczos path: accuracy of the Chebyshev solves with B (0 -> 1e-4)
 end
 
 # FeastResult{T,VT} (core/feast_types.jl:85-98) -- same fields, arrays trimmed to M
@@ -152,7 +153,7 @@ function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{
                           (solver_choice == :direct ? SOLVER_DIRECT : SOLVER_BICGSTAB)
     opts = Ref(SolverOpts(eng_solver, solver_tol, solver_maxiter, solver_restart == 30 ? 3 : solver_restart,
                           sparse ? 1e-3 : 0.0, sparse ? 1 : 0, FILTER_TRUE, 0, 16, 0, real_result ? 1 : 0, 0.0, 0, 0, sparse ? 1 : 0,
-                          Cint(mixed) #= 1: FP32 Lanczos vectors, 2: follow fpm[42] =#, eps_floor))
+                          Cint(mixed) #= 1: FP32 Lanczos vectors, 2: follow fpm[42] =#, eps_floor, 0.0))
     lambda = zeros(Float64, M0); res = zeros(Float64, M0); X = zeros(VT, N, M0)
     M = Ref{Int64}(0); info = Ref{Int64}(0); loop = Ref{Int64}(0); epsout = Ref{Float64}(0.0)
     GC.@preserve fpm Zne Wne lambda res X begin
@@ -284,7 +285,7 @@ function _solve_contour(setA!, setB!, N::Int, Emid::Number, r::Real, M0::Int, fp
     end
     z = ComplexF64(Emid)
     opts = Ref(SolverOpts(sparse ? SOLVER_BICGSTAB : SOLVER_DIRECT, solver_tol, solver_maxiter, solver_restart == 30 ? 3 : solver_restart,
-                          0.0, 0, FILTER_REFERENCE, 0, 16, 0, 0, 0.0, 0, 0, 0, Cint(0), 0.0))
+                          0.0, 0, FILTER_REFERENCE, 0, 16, 0, 0, 0.0, 0, 0, 0, Cint(0), 0.0, 0.0))
     lambda = zeros(ComplexF64, M0); res = zeros(Float64, M0); X = zeros(ComplexF64, N, M0)
     M = Ref{Int64}(0); info = Ref{Int64}(0); loop = Ref{Int64}(0); epsout = Ref{Float64}(0.0)
     GC.@preserve fpm Zne Wne lambda res X begin

@@ -71,6 +71,8 @@ typedef struct {
                          /*    FP64 vectors when a refined sweep gains less than a factor 4                                     */
   double  eps_floor;     /* > 0: the convergence tolerance is max(10^-fpm[3], eps_floor) -- the Float32 entry points      */
                          /*    (sfeast_*, cfeast_*) pass sqrt(eps(Float32)), core/feast_parameters.jl:398-405              */
+  double  b_delta;       /* generalized Lanczos path (B Hermitian positive definite): accuracy of the Chebyshev inner solves  */
+                         /*    with B in the first sweep (0 -> 1e-4); later sweeps use min(b_delta, 1e-3 * inner target)       */
 } feastcuda_solver_opts;
 
 typedef struct {
@@ -91,13 +93,15 @@ typedef struct {
   double  bytes_kern[8];
   double  ms_dev_run;                 /* CUDA-event time (library stream) of the feastcuda_run_interval calls    */
   int64_t lz_steps_fp32;              /* pass-1 Lanczos steps run with FP32 vectors (opts.mixed)                 */
+  int64_t cheb_degree;                /* generalized Lanczos path: Chebyshev steps per inner solve with B (last sweep) */
 } feastcuda_stats;
 
 enum { FEASTCUDA_KERN_SPMM_Z = 0,   /* complex shifted SpMM (BiCGStab)            */
        FEASTCUDA_KERN_LZ_P1 = 1,    /* Lanczos pass-1 SpMM + dot                   */
        FEASTCUDA_KERN_LZ_UPD = 2,   /* Lanczos pass-1 vector update + norm         */
        FEASTCUDA_KERN_LZ_P2 = 3,    /* Lanczos pass-2 fused SpMM + accumulate      */
-       FEASTCUDA_KERN_LZ_RES = 4 }; /* Ritz-residual start block                   */
+       FEASTCUDA_KERN_LZ_RES = 4,   /* Ritz-residual start block                   */
+       FEASTCUDA_KERN_LZ_CHEB = 5 };/* one Chebyshev step of the inner solve with B (generalized Lanczos filter) */
 
 /* ---- lifetime --------------------------------------------------------------------------------- */
 int feastcuda_create(feastcuda_handle* h, int device);
@@ -204,6 +208,14 @@ int feastcuda_residuals(feastcuda_handle h, int64_t m, const double* X, const do
  * (torch.distributed / MPI / files). */
 int feastcuda_nccl_unique_id(char* id128);
 int feastcuda_nccl_init(feastcuda_handle h, int nranks, int rank, const char* id128);
+/* Row sharding (after feastcuda_nccl_init, before the operator is uploaded; real symmetric sparse standard problems on the
+ * multi-shift Lanczos filter): every rank owns a contiguous block of rows of A and of every block vector (the block rule of
+ * parallel/feast_mpi.jl:36-43 applied to rows), halo rows are read from the owner's HBM over NVLink inside the gather kernels, the
+ * per-step dot products are one-shot reductions through peer memory, Gram matrices and residual norms are summed by small
+ * all-reduces; Q0 / X stay GLOBAL n x m0 host arrays of which each rank reads / writes its own rows only. */
+int feastcuda_set_row_sharding(feastcuda_handle h, int on);
+/* rows [row0, row0 + nrows) of the global order nglobal are this rank's (nrows = nglobal without row sharding) */
+int feastcuda_row_range(feastcuda_handle h, int64_t* row0, int64_t* nrows, int64_t* nglobal);
 /* node block owned by `rank`: (start, count), 0-based -- parallel/feast_mpi.jl:36-43 */
 int feastcuda_node_partition(int64_t ne, int nranks, int rank, int64_t* start, int64_t* count);
 

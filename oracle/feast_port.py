@@ -896,3 +896,207 @@ def feast_general_msarnoldi(A, B, Emid, r, M0, fpm, Q0, inner_rel=1e-3, inner_ma
     lam_out, q_out, res_out = lam[:M_found].copy(), X[:, :M_found].copy(), res[:M_found].copy()
     fo.feast_sort_general(lam_out, q_out, res_out, M_found)
     return fo.FeastResult(lam_out, q_out, M_found, res_out, info, epsout, loop_count, stats)
+
+
+# ======================================================================================================================
+# The generalized Hermitian filter as the CUDA engine runs it (csrc/feastcuda.cu:msl_filter_gen): the inner solves with B are
+# a FIXED Chebyshev polynomial P = p_K(D^-1 B) D^-1 (D = diag B; no dot products, no data-dependent branches), so the recurrence
+# is an EXACT Lanczos process for the neighbouring pencil (A, P^-1): self-adjoint in the P^-1 inner product, which is never
+# applied -- the images s_j = P^-1 u_j ride along (s_{j+1} is the right-hand side of the solve that produced u_{j+1}).
+# Vectors are unnormalised (u_j = beta_j v_j, s_j = beta_j P^-1 v_j) like in the standard path, the scalars are the same
+# (alpha_j beta_j = u_j^H t, beta_{j+1}^2 = u_{j+1}^H s_{j+1}), and so are the host-side tridiagonal solves.
+# ======================================================================================================================
+def chebyshev_setup(B, steps=40, safety=0.85):
+    """Spectral interval [lo, hi] of D^-1 B for the Chebyshev inner solver: hi from Gershgorin's bound (safe), lo from the smallest Ritz
+    value of a short Lanczos run on D^-1/2 B D^-1/2 times a safety factor (a Ritz value bounds the smallest eigenvalue from above)."""
+    import scipy.sparse as sp
+    import scipy.linalg as sla
+    d = np.real(B.diagonal())
+    assert np.all(d > 0)
+    dinv = 1.0 / d
+    absB = abs(sp.csr_matrix(B))
+    hi = float((absB @ np.ones(B.shape[0]) * dinv).max())
+    n = B.shape[0]
+    s = np.sqrt(dinv)
+    v = np.cos(1.0 + np.arange(n) * 0.7548776662466927)     # deterministic quasi-random start (golden-ratio-like increment)
+    v = v / np.linalg.norm(v)
+    v_prev = np.zeros(n)
+    al, be = [], []
+    beta = 0.0
+    for _ in range(min(steps, n)):
+        w = s * (B @ (s * v))
+        w = np.real(w) if not np.iscomplexobj(B) else w
+        a = float(np.real(np.vdot(v, w)))
+        w = w - a * v - beta * v_prev
+        beta = float(np.linalg.norm(w))
+        al.append(a)
+        if beta < 1e-12 * hi:
+            break
+        be.append(beta)
+        v_prev, v = v, w / beta
+    k = len(al)
+    ritz = sla.eigvalsh_tridiagonal(np.array(al), np.array(be[:k - 1])) if k > 1 else np.array(al)
+    lo = max(safety * float(ritz.min()), 1e-3 * hi)
+    return dinv, lo, hi
+
+
+def chebyshev_degree(lo, hi, delta):
+    """Smallest K with the Chebyshev error bound 2 s^K / (1 + s^2K) <= delta, s = (sqrt(kappa)-1)/(sqrt(kappa)+1)."""
+    kap = hi / lo
+    s = (math.sqrt(kap) - 1.0) / (math.sqrt(kap) + 1.0)
+    K = 1
+    while 2.0 * s ** K / (1.0 + s ** (2 * K)) > delta and K < 400:
+        K += 1
+    return K
+
+
+def chebyshev_solve(B, dinv, lo, hi, R, K):
+    """X = p_K(D^-1 B) D^-1 R: K steps of the three-term Chebyshev iteration from X_0 = 0 (k_lz_spmm<LZ_CHEB>)."""
+    theta, delta = 0.5 * (hi + lo), 0.5 * (hi - lo)
+    sigma = theta / delta
+    x_prev = np.zeros_like(R)
+    x = (dinv[:, None] * R) / theta
+    rho_prev = 1.0 / sigma
+    for _ in range(1, K):
+        rho = 1.0 / (2.0 * sigma - rho_prev)
+        x_new = x + rho * rho_prev * (x - x_prev) + (2.0 * rho / delta) * (dinv[:, None] * (R - B @ x))
+        x_prev, x, rho_prev = x, x_new, rho
+    return x
+
+
+def mslanczos_filter_gen_cheb(A, B, cheb, K, Q, theta, Zne, Wne, target, kmax, stats=None):
+    """Engine-order restatement: start s_0 = B q (or A q - theta B q), u_0 = P s_0; step: t = A u_j / beta_j - (beta_j/beta_{j-1}) s_{j-1},
+    alpha_j beta_j = Re(u_j^H t), s_{j+1} = t - (alpha_j/beta_j) s_j, u_{j+1} = P s_{j+1}, beta_{j+1}^2 = Re(u_{j+1}^H s_{j+1})."""
+    dinv, lo, hi = cheb
+    n, m = Q.shape
+    ne = len(Zne)
+    P = lambda R: chebyshev_solve(B, dinv, lo, hi, R, K)
+    Qc = Q.astype(complex)
+    if theta is None:
+        s0, F, acc = B @ Qc, np.ones((ne, m), dtype=complex), np.zeros((n, m), dtype=complex)
+    else:
+        s0 = A @ Qc - (B @ Qc) * theta
+        F = 1.0 / (np.asarray(Zne)[:, None] - theta[None, :])
+        acc = Qc * np.real((2 * np.asarray(Wne)[:, None] * F).sum(axis=0))
+    u0 = P(s0)
+    beta0 = np.sqrt(np.maximum(np.einsum("ij,ij->j", u0.conj(), s0).real, 0.0))
+
+    def run(alpha=None, beta=None, coef=None, out=None):
+        al_l, be_l = [], [beta0]
+        u, s, s_prev = u0, s0, np.zeros_like(s0)
+        bj = beta0
+        inv = np.where(bj > 1e-290, 1.0 / np.where(bj > 0, bj, 1.0), 0.0)
+        ratio_b = np.zeros(m)
+        scale = np.zeros(m)
+        d = np.zeros((ne, m), dtype=complex)
+        g = np.zeros((ne, m), dtype=complex)
+        k = 0
+        steps = kmax if alpha is None else len(alpha)
+        for j in range(steps):
+            if out is not None:
+                out += coef[j] * u
+                if j == steps - 1:
+                    break
+            t = (A @ u) * inv - ratio_b * s_prev
+            if alpha is None:
+                al = np.einsum("ij,ij->j", u.conj(), t).real * inv
+                al_l.append(al)
+                scale = np.maximum(scale, np.abs(al))
+            else:
+                al = alpha[j]
+            s_new = t - (al * inv) * s
+            u_new = P(s_new)
+            if alpha is None:
+                bn = np.sqrt(np.maximum(np.einsum("ij,ij->j", u_new.conj(), s_new).real, 0.0))
+                ok = (bn > 1e-290) & (bn > 1e-13 * scale) & (inv != 0.0)
+                bn = np.where(ok, bn, 0.0)
+                be_l.append(bn)
+                scale = np.maximum(scale, bn)
+                for e in range(ne):
+                    if j == 0:
+                        d[e] = Zne[e] - al
+                        g[e] = 1.0 / d[e]
+                    else:
+                        dn = (Zne[e] - al) - bj ** 2 / d[e]
+                        g[e] = bj * g[e] / dn
+                        d[e] = dn
+                k = j + 1
+            else:
+                bn = beta[j + 1]
+            inv_new = np.where(bn > 0, 1.0 / np.where(bn > 0, bn, 1.0), 0.0)
+            ratio_b = np.where(bn > 0, bn * inv, 0.0)
+            s_prev, s, u, bj, inv = s, s_new, u_new, bn, inv_new
+            if alpha is None and float((bn[None, :] * np.abs(g)).max()) <= target:
+                break
+        return np.array(al_l), np.array(be_l), k
+
+    alpha, beta, k = run()
+    coef = lanczos_coefficients(alpha, beta[:k + 1], Zne, Wne, F)          # c_j / beta_j for the unnormalised u_j
+    run(alpha=alpha, beta=beta, coef=coef, out=acc)
+    if stats is not None:
+        stats["lz_steps"].append(k)
+        stats["cheb_degree"].append(K)
+    return acc
+
+
+def feast_hrr_mslanczos_gen_cheb(A, B, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, inner_maxiter=4000, adaptive=True, verbose=False,
+                                 b_delta0=1e-4, b_delta_min=1e-9):
+    """H-RR loop around mslanczos_filter_gen_cheb, as run_interval drives msl_filter_gen.  The Chebyshev accuracy follows the outer
+    residual: delta = b_delta0 in the first sweep, then clamp(1e-2 * epsout, b_delta_min, b_delta0) -- the filter of the pencil
+    (A, P^-1) differs from the exact one by O(delta |z| / dist), which only has to stay below the sweep's contraction."""
+    import scipy.linalg as sla
+    N = A.shape[0]
+    fo.feastdefault(fpm)
+    fo.check_feast_srci_input(N, M0, Emin, Emax, fpm)
+    Zne, Wne = fo.feast_contour(Emin, Emax, fpm)
+    eps_tol = fo.feast_tolerance(fpm)
+    cheb = chebyshev_setup(B)
+    Qb = np.array(Q0, dtype=complex)
+    lam, res = np.zeros(M0), np.zeros(M0)
+    X = np.zeros((N, M0), dtype=complex)
+    have_ritz, active = False, M0
+    info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
+    stats = {"lz_steps": [], "cheb_degree": [], "cheb_interval": cheb[1:]}
+    for loop_idx in range(fpm[3] + 1):
+        loop_count = loop_idx
+        target, delta = inner_rel, b_delta0
+        if have_ritz and math.isfinite(epsout) and epsout > 0:
+            delta = min(b_delta0, max(b_delta_min, 1e-2 * epsout))
+            if adaptive:
+                t = 2.0 * eps_tol / epsout
+                if t >= 1e-6:
+                    target = min(0.1, t)
+        K = chebyshev_degree(cheb[1], cheb[2], delta)
+        acc = mslanczos_filter_gen_cheb(A, B, cheb, K, Qb[:, :active], lam[:active].copy() if have_ritz else None, Zne, Wne, target,
+                                        inner_maxiter, stats)
+        Qr, rank = fo.qr_compress(np.ascontiguousarray(acc), active)
+        if rank == 0:
+            info = fo.ERR_NO_CONV
+            break
+        Aq = Qr.conj().T @ (A @ Qr)
+        Bq = Qr.conj().T @ (B @ Qr)
+        lam_red, v_red = sla.eigh(0.5 * (Aq + Aq.conj().T), 0.5 * (Bq + Bq.conj().T))
+        Xc = np.zeros((N, M0), dtype=complex)
+        Xc[:, :rank] = Qr @ v_red
+        lam[:rank] = lam_red
+        M = fo.reorder_by_interval(lam, Xc, Emin, Emax, rank)
+        X = Xc
+        if M == 0:
+            info = fo.ERR_NO_CONV
+            break
+        X[:, :M] /= np.linalg.norm(X[:, :M], axis=0)
+        R = A @ X[:, :M] - (B @ X[:, :M]) * lam[:M]
+        res[:M] = np.linalg.norm(R, axis=0) / np.maximum(np.abs(lam[:M]), 1.0)
+        epsout = float(res[:M].max())
+        M_found = M
+        if verbose:
+            print(f"loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={stats['lz_steps'][-1]} K={K} delta={delta:.1e}", flush=True)
+        if epsout <= eps_tol:
+            break
+        if loop_idx == fpm[3]:
+            info = fo.ERR_NO_CONV
+            break
+        active = rank
+        Qb = X[:, :active].copy()
+        have_ritz = True
+    return fo.FeastResult(lam[:M_found].copy(), X[:, :M_found].copy(), M_found, res[:M_found].copy(), info, epsout, loop_count, stats)

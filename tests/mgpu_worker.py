@@ -27,12 +27,16 @@ def main():
     Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
     Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
     out = {}
-    for name, kw in (("mslanczos_columns", dict(solver="mslanczos", solver_maxiter=2000)),
+    for name, kw in (("mslanczos_rows", dict(solver="mslanczos", solver_maxiter=2000, shard="rows")),
+                     ("mslanczos_columns", dict(solver="mslanczos", solver_maxiter=2000)),
                      ("mslanczos_mixed_columns", dict(solver="mslanczos", solver_maxiter=2000, mixed=True)),
                      ("bicgstab_nodes", dict(solver="bicgstab", solver_maxiter=400, inner_rel=1e-3, ritz_guess=True, shard="nodes")),
                      ("bicgstab_balanced", dict(solver="bicgstab", solver_maxiter=400, inner_rel=1e-3, ritz_guess=True, shard="balanced"))):
         r = fc.pdfeast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, **kw)
         ok = (r.info == 0 and r.M == 10 and float(np.abs(np.sort(r.lambda_) - ev[:10]).max()) < 1e-10 and float(r.res.max()) < 1e-12)
+        if ok:      # the returned vectors are the full eigenvectors on every rank (row-sharded runs gather them)
+            R = A @ r.q - r.q * r.lambda_
+            ok = float(np.linalg.norm(R, axis=0).max()) < 1e-11 and float(np.abs(np.linalg.norm(r.q, axis=0) - 1).max()) < 1e-10
         t = torch.tensor([1.0 if ok else 0.0, float(r.loop)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         out[name] = {"ok_all_ranks": bool(t[0].item() == 1.0), "loop": r.loop, "M": r.M, "info": r.info, "epsout": r.epsout,

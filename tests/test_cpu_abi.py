@@ -38,7 +38,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_layouts_match_the_header(lib):
     """feastcuda_solver_opts / feastcuda_stats are mirrored field by field (sizes per the C layout rules)."""
     import feastcuda as fc
-    assert C.sizeof(fc._lib.SolverOpts) == 88
+    assert C.sizeof(fc._lib.SolverOpts) == 96
     assert fc._lib.SolverOpts.eps_floor.offset == 80
     hdr = (ROOT / "include" / "feastcuda.h").read_text()
     end = hdr.index("} feastcuda_solver_opts;")

@@ -359,33 +359,6 @@ def test_complex_hermitian_standard_runs_the_lanczos_path(M0):
     assert rb.info == 0 and rb.M == 10 and np.abs(np.sort(rb.lambda_) - ev[:10]).max() < 1e-10
 
 
-def test_staged_gather_variant_matches_the_direct_kernel(monkeypatch):
-    """k_lz_spmm_staged (cp.async.bulk + mbarrier ring, FEASTCUDA_LZ_STAGED=1) against the default register-path kernel."""
-    import feastcuda as fc
-    N, M0 = 14, 40          # 20 column pairs: inside the staged kernel's range (17..32 pairs)
-    A = fo.laplacian_3d(N).astype(float).tocsr()
-    ev = fo.laplacian_3d_eigs(N)
-    Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
-    Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
-    fpm = fc.feastinit()
-    fc.feastdefault_(fpm)
-    Z, W = fc.feast_contour(Emin, Emax, fpm)
-    kw = dict(x_real=True, filter="true", solver="mslanczos", inner_rel=1e-3, ritz_guess=True, solver_maxiter=2000)
-    out = []
-    for staged in ("0", "1"):
-        monkeypatch.setenv("FEASTCUDA_LZ_STAGED", staged)
-        eng = fc.Engine(0)
-        eng.set_sparse(fc.A, A, fc.SYM)
-        eng.clear_b()
-        out.append(eng.solve_interval(Emin, Emax, M0, list(fpm), Z, W, Q0=Q0, **kw))
-        eng.close()
-    r0, r1 = out
-    assert r0.info == r1.info == 0 and r0.M == r1.M == 10 and r0.loop == r1.loop
-    assert np.abs(np.sort(r0.lambda_) - np.sort(r1.lambda_)).max() < 1e-12
-    assert r1.res.max() < 1e-12 and fo.subspace_angle(r0.q.astype(complex), r1.q.astype(complex)) < 1e-8
-    assert abs(r0.stats["lz_steps_p1"] - r1.stats["lz_steps_p1"]) <= 16     # same recurrence up to the dot products' summation order
-
-
 def _rci_drive(fn, A, B, N, M0, Emin, Emax, engine, hermitian, maxiter=400, stop_at_first_mult=False, solver="bicgstab"):
     """The caller's side of the reverse-communication loop (banded/feast_banded.jl:76-180 shape): factorize = remember the
     shift, solve = one block solve on the device, mult_a = A q on the device."""

@@ -167,7 +167,7 @@ def run_gpu(args):
     eng.set_sparse(fc.A, A, fc.SYM)
     eng.clear_b()
     eng.init_distributed()
-    shard = args.shard if world > 1 else "columns"
+    shard = args.shard if (world > 1 or os.environ.get("FEASTCUDA_FORCE_ROWS")) else "columns"
     eng.set_row_sharding(shard == "rows")
     fpm = fc.feastinit()
     fc.feastdefault_(fpm)

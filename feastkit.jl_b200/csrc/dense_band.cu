@@ -49,10 +49,11 @@ void dense_set(H* h, int which, int64_t n, const double* a, int64_t lda, bool cp
   d.a.clear();
   d.set = true;
   if (which == FEASTCUDA_A) {
-    if (h->kind != OP_DENSE) { h->has_b = false; h->denseB.set = false; }
+    if (h->kind != OP_DENSE || (h->has_b && h->denseB.n != n)) { h->has_b = false; h->denseB.set = false; }   // a B of another size never survives a new A
     h->kind = OP_DENSE;
     h->n = n;
   } else {
+    FC_REQUIRE(h->kind == OP_DENSE && h->denseA.set && h->denseA.n == n, "set A (same size, dense) before B");
     h->has_b = true;
   }
   h->dense_uploaded = true;
@@ -274,10 +275,11 @@ void band_set(H* h, int which, int64_t n, int64_t k, const double* ab, int64_t l
   }
   d.set = true;
   if (which == FEASTCUDA_A) {
-    if (h->kind != OP_BAND) { h->has_b = false; h->bandB.set = false; }
+    if (h->kind != OP_BAND || (h->has_b && h->bandB.n != n)) { h->has_b = false; h->bandB.set = false; }   // a B of another size never survives a new A
     h->kind = OP_BAND;
     h->n = n;
   } else {
+    FC_REQUIRE(h->kind == OP_BAND && h->bandA.set && h->bandA.n == n, "set A (same size, banded) before B");
     h->has_b = true;
   }
   h->band_uploaded = false;

@@ -165,6 +165,9 @@ struct feastcuda_handle_s {
   feastcuda::DBuf goff;                        // pre-resolved gather offsets of A's local rows (kernels_lanczos.cuh: k_lz_resolve), two row strides cached
   int64_t goff_rowbytes = 0, goff_rowbytes2[2] = {0, 0};
   int goff_next = 0;
+  feastcuda::DBuf tile_order;                  // order in which the gather kernels deal their row tiles (halo tiles spread out)
+  int tile_order_tr = 0;
+  feastcuda::DBuf lz_ticket, lz_grows;         // counters and group sums of the two-level tail reductions (kernels_lanczos.cuh: lz_tail)
   int64_t nnz_loc = 0;                         // stored entries of the local rows
   unsigned long long xseq = 0;                 // sequence number of the last cross-rank exchange
 

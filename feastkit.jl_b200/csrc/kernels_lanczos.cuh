@@ -223,10 +223,12 @@ __device__ __forceinline__ void lz_scalars_beta(const LzScalars& s, int j, const
 // Tail of a producer kernel: the LAST CTA to finish (ticket counter) sums the per-CTA partial rows in a fixed order, exchanges the
 // sums with the other ranks and runs the scalar recurrences that used to be separate one-CTA launches.
 enum LzTailKind { LZ_TAIL_NONE = 0, LZ_TAIL_INIT = 1, LZ_TAIL_ALPHA = 2, LZ_TAIL_BETA = 3, LZ_TAIL_BARRIER = 4 };
+constexpr int LZ_TAIL_GROUP = 16;   // CTAs per first-level group of the two-level tail reduction
 struct LzTail {
   int kind;          // LzTailKind
   int j;             // Lanczos step
-  int* ticket;       // device counter, zero between launches
+  int* ticket;       // device counters, zero between launches: [0] groups finished, [1 + g] CTAs of group g finished
+  double* grows;     // [ngroups][FC_MAXCOLS] group sums (first level of the reduction)
   LzScalars s;
   LzXchg x;
 };
@@ -242,9 +244,27 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   if (t.x.nranks > 1) __threadfence_system();   // this CTA's vector rows must be visible to the peers before the flag is raised
   else __threadfence();
   __syncthreads();
+  // two levels, both in a fixed order: the last CTA of every group of LZ_TAIL_GROUP consecutive CTAs sums the group's rows, the last
+  // group to finish sums the group sums (a single CTA summing several hundred rows would cost more than the kernels it replaced)
+  const int grp = (int)blockIdx.x / LZ_TAIL_GROUP, ngroups = ((int)gridDim.x + LZ_TAIL_GROUP - 1) / LZ_TAIL_GROUP;
+  const int gsize = min(LZ_TAIL_GROUP, (int)gridDim.x - grp * LZ_TAIL_GROUP);
   if (threadIdx.x == 0) {
+    const int tk = atomicAdd(t.ticket + 1 + grp, 1);
+    s_last = (tk == gsize - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (t.kind != LZ_TAIL_BARRIER) {
+    lz_reduce_rows(partial + (int64_t)grp * LZ_TAIL_GROUP * pstride, gsize, pstride, m, t_so, t_tmp);
+    if ((int)threadIdx.x < m) t.grows[(int64_t)grp * FC_MAXCOLS + threadIdx.x] = t_so[threadIdx.x];
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    t.ticket[1 + grp] = 0;
     const int tk = atomicAdd(t.ticket, 1);
-    s_last = (tk == (int)gridDim.x - 1) ? 1 : 0;
+    s_last = (tk == ngroups - 1) ? 1 : 0;
   }
   __syncthreads();
   if (!s_last) return;
@@ -252,7 +272,7 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   if (t.kind == LZ_TAIL_BARRIER) {
     lz_exchange(t.x, t_so, 0);
   } else {
-    lz_reduce_rows(partial, (int)gridDim.x, pstride, m, t_so, t_tmp);
+    lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
     lz_exchange(t.x, t_so, m);
     if (t.kind == LZ_TAIL_INIT) lz_scalars_init(t.s, t_so, m);
     else if (t.kind == LZ_TAIL_ALPHA) lz_scalars_alpha(t.s, t.j, t_so, m);
@@ -308,6 +328,7 @@ struct LzArgs {
   // row-sharded runs: `n` rows are this rank's block; the uploaded column index of an entry is (owner rank << LZ_OWNER_SHIFT) | row
   // local to the owner, resolved once per row stride into `goff`
   const long long* goff; // row-sharded runs: per stored entry, the byte offset from a local block to the gathered row (k_lz_resolve)
+  const int* tile_order; // row-sharded runs: the order in which the row tiles are dealt to the CTAs (nullptr: natural order)
 };
 constexpr int LZ_OWNER_SHIFT = 26;
 struct LzArenas { const char* base[LZ_MAXRANKS]; };   // arena base of every rank as mapped in this process
@@ -465,13 +486,22 @@ __global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_
   const int niter = my_tiles * spt;
   // iteration -> row, advanced incrementally (no integer divisions in the loop): `base_f` is the first row of the CTA's
   // iteration `it_f`, the furthest one the metadata pipeline has looked at
+  // Row-sharded runs deal the tiles in the order `tile_order` (host: the tiles that touch halo rows are spread evenly among the
+  // interior ones, so the NVLink latency of a halo gather is hidden behind local rows instead of stalling every CTA at once at
+  // both ends of the sweep).
   const int lane_row = wib * RPW + sub;
-  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR;
+  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR, t_f = (int)blockIdx.x;
+  if (SHARD && a.tile_order != nullptr && my_tiles > 0) base_f = a.tile_order[t_f] * TR;
   auto next_row = [&]() -> int {
     const int r = (it_f < niter) ? base_f + lane_row : n;
     ++it_f;
-    if (++s_f == spt) { s_f = 0; base_f += ((int)gridDim.x - 1) * TR + STEP; }
-    else base_f += STEP;
+    if (++s_f == spt) {
+      s_f = 0;
+      if (SHARD && a.tile_order != nullptr) {
+        t_f += (int)gridDim.x;
+        base_f = (it_f < niter) ? a.tile_order[t_f] * TR : 0;
+      } else base_f += ((int)gridDim.x - 1) * TR + STEP;
+    } else base_f += STEP;
     return r < n ? r : n;
   };
 

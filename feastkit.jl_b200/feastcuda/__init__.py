@@ -13,6 +13,8 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -320,7 +322,7 @@ class Engine:
     def set_row_sharding(self, on=True):
         """Row-sharded multi-GPU mode (feastcuda_set_row_sharding): call after init_distributed; a no-op on one rank."""
         self._ck(self.lib.feastcuda_set_row_sharding(self.h, int(bool(on))))
-        self.row_sharded = bool(on) and self.distributed
+        self.row_sharded = bool(on) and (self.distributed or bool(os.environ.get("FEASTCUDA_FORCE_ROWS")))
 
     def row_range(self):
         """(row0, nrows, nglobal): this rank's block of rows (the whole matrix without row sharding)."""

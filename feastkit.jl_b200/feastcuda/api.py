@@ -40,6 +40,16 @@ def ishermitian(M):
     return M.shape[0] == M.shape[1] and np.array_equal(M, M.conj().T)
 
 
+M0_CAP = 128
+
+
+def _check_m0_cap(M0):
+    """Known divergence from the reference (which accepts any 0 < M0 <= N): the device block kernels hold at most 128 columns."""
+    if int(M0) > M0_CAP:
+        raise ValueError(f"M0 = {int(M0)} exceeds the {M0_CAP}-column cap of the GPU block kernels: slice the interval into "
+                         f"sub-intervals holding fewer eigenvalues (INTEGRATION.md, 'Known divergences')")
+
+
 def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras):
     """Map the reference keywords (sparse/feast_sparse.jl:246-266) onto feastcuda_solver_opts."""
     solver_choice = "gmres" if solver == "iterative" else solver
@@ -54,7 +64,7 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
         kw["solver"] = "direct" if solver_choice == "direct" else "bicgstab"
     else:
         kw["solver"] = "bicgstab" if solver_choice == "bicgstab" else "mslanczos"
-    kw["solver_restart"] = 3 if solver_restart == 30 else int(solver_restart)
+    kw["solver_restart"] = 3 if solver_restart is None else int(solver_restart)     # None = the caller left the keyword alone
     if kind == "sparse":
         # engine defaults for Krylov node solves (DESIGN.md "Inner solves"): start from the previous loop's Ritz pairs
         # and stop three digits below that guess's residual; inner_rel=0, ritz_guess=False gives the reference's
@@ -72,10 +82,11 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
 
 
 def _hermitian_solve(kind, setA, setB, N, Emin, Emax, M0, fpm, real_result, contour=None, solver="direct",
-                     solver_tol=0.0, solver_maxiter=500, solver_restart=30, Q0=None, engine=None, **extras):
+                     solver_tol=0.0, solver_maxiter=500, solver_restart=None, Q0=None, engine=None, **extras):
     from . import check_feast_srci_input, feast_contour, feastdefault_
     feastdefault_(fpm)
     check_feast_srci_input(N, M0, float(Emin), float(Emax), fpm)
+    _check_m0_cap(M0)
     kw = _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
     eng = _eng(engine)   # argument errors above are raised before any device is touched, as in the reference
     setA(eng)
@@ -302,16 +313,23 @@ def feast_hbgv(A, B, kla, klb, Emin, Emax, M0, fpm, **kw):
 
 
 # ---- general (non-Hermitian) problems: kernel/feast_kernel.jl:646-962 behind the storage drivers ---------------------
-def _general_solve(kind, setA, setB, N, Emid, r, M0, fpm, contour=None, solver="direct", solver_tol=0.0, solver_maxiter=500,
-                   solver_restart=30, Q0=None, engine=None, **extras):
+def _general_solve(kind, setA, setB, N, Emid, r, M0, fpm, contour=None, solver="direct", solver_tol=0.0, solver_maxiter=None,
+                   solver_restart=None, Q0=None, engine=None, **extras):
     from . import check_feast_grci_input, feast_gcontour, feastdefault_
     feastdefault_(fpm)
     check_feast_grci_input(N, M0, complex(Emid), float(r), fpm)
     solver_choice = "gmres" if solver == "iterative" else solver
     if solver_choice not in ("direct", "gmres", "bicgstab"):
         raise ValueError(f"Unsupported solver option '{solver}'. Use :direct, :gmres, or :iterative.")
-    kw = dict(solver_tol=solver_tol, solver_maxiter=max(int(solver_maxiter), 2000 if kind == "sparse" else 1),
-              solver="bicgstab" if kind == "sparse" else "direct", solver_restart=3 if solver_restart == 30 else int(solver_restart))
+    _check_m0_cap(M0)
+    # the reference's defaults (500 iterations, restart 30) belong to its per-column GMRES; the engine's lock-step Krylov solves get their
+    # own defaults only when the caller left the keywords alone -- explicit values are passed through unchanged
+    if solver_maxiter is None:
+        solver_maxiter = 2000 if kind == "sparse" else 500
+    if solver_restart is None:
+        solver_restart = 3
+    kw = dict(solver_tol=solver_tol, solver_maxiter=int(solver_maxiter),
+              solver="bicgstab" if kind == "sparse" else "direct", solver_restart=int(solver_restart))
     for k in ("inner_rel", "shard", "check_every", "eps_floor", "ritz_guess"):
         if k in extras:
             kw[k] = extras.pop(k)

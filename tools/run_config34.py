@@ -19,7 +19,9 @@ if which == 3:
     Q0 = rng.standard_normal((n, M0)) + 0j; Q0 /= np.linalg.norm(Q0, axis=0)
     fpm = fc.feastinit(); fpm[1] = 16; fpm[3] = 40
     t = time.time()
-    r = fc.zfeast_hcsrgv(A, B, Emin, Emax, M0, fpm, Q0=Q0, solver_maxiter=maxiter, ritz_guess=True, inner_rel=inner_rel)
+    import os
+    r = fc.zfeast_hcsrgv(A, B, Emin, Emax, M0, fpm, Q0=Q0, solver_maxiter=maxiter, ritz_guess=True, inner_rel=inner_rel,
+                         b_delta=float(os.environ.get("B_DELTA", "0")))
     dt = time.time() - t
     print("config3 time", dt, "info", r.info, "M", r.M, "want", want, "loops", r.loop, "epsout", r.epsout)
     if r.M == want: print("eig err rel", np.abs(np.sort(r.lambda_) - w[:want]).max() / w[want])
@@ -48,4 +50,8 @@ else:
     dt = time.time() - t
     print("config4 time", dt, "info", r.info, "M", r.M, "inside", len(inside), "loops", r.loop, "epsout", r.epsout)
     if r.M == len(inside): print("eig err", max(min(abs(g - x) for x in inside) for g in r.lambda_))
-print({k: v for k, v in r.stats.items() if k in ("ms_total", "ms_solve", "krylov_iters", "spmm_launches", "node_solves")})
+print({k: v for k, v in r.stats.items() if k in ("ms_total", "ms_solve", "krylov_iters", "spmm_launches", "node_solves", "cheb_degree", "lz_steps_p1")})
+for i, nm in enumerate(fc._lib.KERN_NAMES):
+    if r.stats["n_kern"][i]:
+        avg = r.stats["ms_kern"][i] / r.stats["n_kern"][i]
+        print(f"  {nm}: avg {avg:.4f} ms, {r.stats['bytes_kern'][i] / avg / 1e6:.0f} GB/s algorithmic, {r.stats['n_kern'][i]} samples")

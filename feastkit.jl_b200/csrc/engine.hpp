@@ -11,6 +11,7 @@
 
 #include "../../include/feastcuda.h"
 #include "cxmath.cuh"
+#include "peer_arena.hpp"
 
 namespace feastcuda {
 
@@ -121,6 +122,11 @@ struct feastcuda_handle_s {
   bool cheb_ready = false, cheb_usable = false;
   double cheb_lo = 0.0, cheb_hi = 0.0;
   feastcuda::DBuf cheb_dinv;
+  // general pencils on the two-sided Lanczos filter: row-scaled operators D^-1 A, D^-1 B and their conjugate transposes
+  bool g2_ready = false, g2_usable = false;
+  double g2_q = 0.0;                            // Jacobi contraction bound of D^-1 B (0: B = I)
+  feastcuda::DevCsr g2A, g2Ah, g2B, g2Bh;
+  feastcuda::DBuf g2_ones;
   int lz_egrid_mult = 4;    // CTAs per SM of the elementwise Lanczos kernels (partial rows the scalar kernels reduce)
   int lz_paired = 1;        // pass 2 accumulates Q every second step (0: every step)
   int lz_threads = 512;     // CTA size of the Lanczos SpMM (512 or 1024)
@@ -155,10 +161,13 @@ struct feastcuda_handle_s {
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
   // row-sharded runs (feastcuda_set_row_sharding): every rank owns a contiguous block of rows of A and of every block vector; `n` is
-  // the LOCAL row count then.  All block slots and the mailbox of the one-shot reductions live in ONE allocation (the arena), opened
-  // in every peer process by cudaIpcOpenMemHandle, so the gather kernels read halo rows straight from the owner's HBM over NVLink.
+  // the LOCAL row count then.  All block slots and the mailbox of the one-shot reductions live in ONE allocation per rank (the arena);
+  // the arenas of all ranks are mapped into one contiguous virtual range in every process (peer_arena.hpp), so the gather kernels read
+  // halo rows straight from the owner's HBM over NVLink.
   bool row_sharded = false;
   int64_t n_glob = 0, row0 = 0, nloc_max = 0;
+  feastcuda::PeerArena parena;                 // the ranks' arenas in one contiguous virtual range (peer_arena.hpp)
+  unsigned long long ipc_token = 0;            // names the descriptor-passing sockets of this communicator
   void* arena = nullptr;                       // local arena
   size_t arena_bytes = 0, arena_slot_bytes = 0, arena_mbox_off = 0;
   void* peer_arena[16] = {nullptr};            // every rank's arena as mapped in this process (peer_arena[rank] == arena)

@@ -14,6 +14,7 @@
 #include "kernels_lanczos.cuh"
 #include "kernels_lanczos_f32.cuh"
 #include "kernels_matfree.cuh"
+#include "kernels_twosided.cuh"
 #include "dense_band.cuh"
 
 using namespace feastcuda;
@@ -45,7 +46,7 @@ static zd* blk(H* h, int slot) { return h->blk[slot].as<zd>(); }
 
 static void arena_allocate(H* h, int ld);
 static void fill_xchg(H* h, LzXchg& x);
-static const long long* resolve_goff(H* h, int64_t rowbytes);
+static const int* resolve_goff(H* h, int64_t rowbytes);
 static void xbarrier(H* h);
 static void allreduce_small(H* h, double* dev, size_t count);
 static void sharded_apply(H* h, int m, const cx<double>* X, cx<double>* Y, const double* theta, std::vector<double>* norms2);
@@ -684,8 +685,8 @@ static double lz32_bytes_spmm(H* h, int m, int nvec32, int nvec64) {
 }
 
 static double lz_bytes_spmm(H* h, int m, int nvec, bool cplx) {
-  const double es = cplx ? 16.0 : 8.0;   // a row-sharded operator carries 8-byte pre-resolved offsets instead of 4-byte column indices
-  return (double)h->nnz_loc * (es + (h->row_sharded ? 8.0 : 4.0)) + 4.0 * (double)(h->n + 1) + (double)nvec * (double)h->n * m * es;
+  const double es = cplx ? 16.0 : 8.0;
+  return (double)h->nnz_loc * (es + 4.0) + 4.0 * (double)(h->n + 1) + (double)nvec * (double)h->n * m * es;
 }
 
 // c_j = ||b|| sum_e Re(2 w_e F_e [(z_e I - T_k)^-1 e_1]_j) / beta_j for the unnormalised Lanczos vectors of every column: complex Thomas
@@ -1349,6 +1350,365 @@ static void msl_filter_gen(H* h, int basis_slot, int c0, int nc, bool have_ritz,
 }
 
 // =====================================================================================================
+// General (non-Hermitian) pencils on a SHARED Krylov space: two-sided multi-shift Lanczos, two passes.
+// (z B - A)^-1 B q = (z I - C)^-1 q with C = B^-1 A; the non-Hermitian Lanczos relation  C V_k = V_k T_k + delta_{k+1} v_{k+1} e_k^T  (T_k complex
+// tridiagonal, W_k^H V_k = diag(d)) does not depend on z, so ONE recurrence per column serves every node of the full contour:
+//     x_e = ||b|| V_k (z_e I - T_k)^-1 e_1,      residual_e = delta_{k+1} |e_k^T (z_e I - T_k)^-1 e_1| ||b||      (||v_j||_2 = 1)
+// and  q = sum_e w_e x_e = V_k c  (kernel/feast_kernel.jl:762-766 accumulates q += w_e Y_e node by node).  Pass 1 builds T_k (the recurrence
+// scalars live on the HOST: two small reductions per step against ~30 SpMM launches), pass 2 replays the v-sequence alone and accumulates.
+// The rows are scaled by diag(B)^-1 once (C is unchanged); the solves with B' = D^-1 B are a fixed number of Jacobi sweeps
+// x <- x + (r - B' x)  (k_lz_spmm<LZ_CHEB> with c1 = 0, c2 = 1), available when B' is strictly diagonally dominant by rows and by columns
+// (mass-like perturbations of the identity, configs[4]); the same polynomial in B'^H gives the exact adjoint for the w-sequence.
+// The reference runs ne x M0 GMRES solves per loop here (sparse/feast_sparse.jl:873-1006 -> solve_shifted_iterative!, :164-236).
+// =====================================================================================================
+static void host_transpose_conj(int64_t n, const std::vector<int>& ptr, const std::vector<int>& col, const std::vector<zc>& val,
+                                std::vector<int>& tptr, std::vector<int>& tcol, std::vector<zc>& tval) {
+  const size_t nnz = col.size();
+  tptr.assign(n + 1, 0);
+  tcol.assign(nnz, 0);
+  tval.assign(nnz, zc(0.0));
+  for (size_t p = 0; p < nnz; ++p) tptr[col[p] + 1]++;
+  for (int64_t i = 0; i < n; ++i) tptr[i + 1] += tptr[i];
+  std::vector<int> pos(tptr.begin(), tptr.end() - 1);
+  for (int64_t i = 0; i < n; ++i)
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) {
+      const int q = pos[col[p]]++;
+      tcol[q] = (int)i;
+      tval[q] = std::conj(val[p]);
+    }
+}
+
+static void upload_csr_z(H* h, int64_t n, const std::vector<int>& ptr, const std::vector<int>& col, const std::vector<zc>& val, DevCsr& dst) {
+  dst.ptr.ensure((n + 1) * sizeof(int));
+  dst.col.ensure(std::max<size_t>(col.size(), 1) * sizeof(int));
+  dst.val.ensure(std::max<size_t>(val.size(), 1) * sizeof(zd));
+  FC_CUDA(cudaMemcpyAsync(dst.ptr.p, ptr.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (!col.empty()) {
+    FC_CUDA(cudaMemcpyAsync(dst.col.p, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FC_CUDA(cudaMemcpyAsync(dst.val.p, val.data(), val.size() * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
+  }
+  sync(h);
+  dst.uploaded = true;
+}
+
+static bool gen2_prepare(H* h) {
+  if (h->g2_ready) return h->g2_usable;
+  h->g2_ready = true;
+  h->g2_usable = false;
+  const HostCsr& A = h->hA;
+  if (!A.set) return false;
+  const int64_t n = A.n;
+  auto entry = [](const HostCsr& M, int p) { return M.cplx ? zc(M.val[2 * (size_t)p], M.val[2 * (size_t)p + 1]) : zc(M.val[p], 0.0); };
+  std::vector<zc> dinv(n, zc(1.0));
+  double q = 0.0;
+  std::vector<zc> bval;
+  if (h->has_b) {
+    const HostCsr& B = h->hB;
+    std::vector<double> colsum(n, 0.0);
+    for (int64_t i = 0; i < n; ++i) {
+      zc d(0.0);
+      for (int p = B.ptr[i]; p < B.ptr[i + 1]; ++p) if (B.col[p] == i) d = entry(B, p);
+      if (!(std::abs(d) > 0.0)) return false;
+      dinv[i] = zc(1.0) / d;
+    }
+    bval.resize(B.nnz);
+    for (int64_t i = 0; i < n; ++i) {
+      double rs = 0.0;
+      for (int p = B.ptr[i]; p < B.ptr[i + 1]; ++p) {
+        bval[p] = entry(B, p) * dinv[i];
+        if (B.col[p] != i) { rs += std::abs(bval[p]); colsum[B.col[p]] += std::abs(bval[p]); }
+        else bval[p] = zc(1.0);
+      }
+      q = std::max(q, rs);
+    }
+    for (int64_t i = 0; i < n; ++i) q = std::max(q, colsum[i]);
+    if (!(q < 0.9)) return false;      // the Jacobi sweeps need a strictly diagonally dominant B (rows and columns)
+  }
+  std::vector<zc> aval(A.nnz);
+  for (int64_t i = 0; i < n; ++i)
+    for (int p = A.ptr[i]; p < A.ptr[i + 1]; ++p) aval[p] = entry(A, p) * dinv[i];
+  std::vector<int> tptr, tcol;
+  std::vector<zc> tval;
+  upload_csr_z(h, n, A.ptr, A.col, aval, h->g2A);
+  host_transpose_conj(n, A.ptr, A.col, aval, tptr, tcol, tval);
+  upload_csr_z(h, n, tptr, tcol, tval, h->g2Ah);
+  if (h->has_b) {
+    upload_csr_z(h, n, h->hB.ptr, h->hB.col, bval, h->g2B);
+    host_transpose_conj(n, h->hB.ptr, h->hB.col, bval, tptr, tcol, tval);
+    upload_csr_z(h, n, tptr, tcol, tval, h->g2Bh);
+  }
+  std::vector<double> ones(n, 1.0);
+  h->g2_ones.ensure((size_t)n * sizeof(double));
+  FC_CUDA(cudaMemcpyAsync(h->g2_ones.p, ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  sync(h);
+  h->g2_q = q;
+  h->g2_usable = true;
+  if (getenv("FEASTCUDA_VERBOSE")) fprintf(stderr, "[feastcuda r%d] two-sided Lanczos: Jacobi contraction bound of D^-1 B: %.3f\n", h->rank, q);
+  return true;
+}
+
+static void msl2_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, const zc* theta, const zc* Zne, const zc* Wne, int ne,
+                        double target, int kmax, double jac_delta, MslOut& out) {
+  FC_REQUIRE(h->kind == OP_SPARSE && h->g2_usable && nc >= 1 && nc <= TS_MAXC, "two-sided Lanczos filter: sparse pencil, at most 64 columns per rank");
+  const int64_t n = h->ws_n;
+  const int64_t ldz = h->ws_ld, ld = 2 * (int64_t)nc;
+  FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
+  kmax = std::max(2, std::min(kmax, 16384));
+  const int pp = pow2_ge(nc);
+  const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
+  const bool hasb = h->has_b;
+  int KJ = 1;
+  if (hasb && h->g2_q > 0) KJ = std::max(1, (int)std::ceil(std::log(jac_delta) / std::log(h->g2_q)));
+  double* Vb[2] = {rblk(h, BS_KR), rblk(h, BS_KRH)};
+  double* Wb[2] = {rblk(h, BS_KP), rblk(h, BS_KV)};
+  double* X[2] = {rblk(h, BS_KS), rblk(h, BS_KT)};
+  double* T = rblk(h, BS_KX);
+  double* QA = rblk(h, BS_KB);
+  double* RQ = rblk(h, BS_RHS);
+  double* part = h->partial_r.as<double>();
+  const zd* basis = blk(h, basis_slot) + c0;
+  const size_t blk_bytes = (size_t)n * (size_t)ld * sizeof(double);
+
+  auto args0 = [&](const DevCsr& M) {
+    LzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.m = nc; a.ld = ld; a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
+    a.ptr = M.ptr.as<int>(); a.col = M.col.as<int>(); a.val = M.val.p;
+    return a;
+  };
+  int g = 0;
+  auto spmm = [&](const DevCsr& M, const double* src, double* dst) {
+    LzArgs a = args0(M);
+    a.U = src; a.prev = src; a.out = dst;
+    lz_launch<LZ_PLAIN, true>(h, a, &g);
+  };
+  // x ~ M^-1 r by KJ Jacobi sweeps from x_1 = r (unit diagonal); returns the buffer holding the result (r itself when KJ == 1)
+  auto jacobi = [&](const DevCsr& M, const double* r) -> const double* {
+    const double* x = r;
+    for (int i = 1; i < KJ; ++i) {
+      double* o = (x == X[0]) ? X[1] : X[0];
+      LzArgs a = args0(M);
+      a.U = x; a.prev = x; a.out = o; a.rhs = r; a.dinv = h->g2_ones.as<double>(); a.c1 = 0.0; a.c2 = 1.0;
+      lz_launch<LZ_CHEB, true>(h, a, &g);
+      x = o;
+    }
+    return x;
+  };
+  auto applyC = [&](const double* src) -> const double* {          // B'^-1 (A' src)
+    spmm(h->g2A, src, T);
+    return hasb ? jacobi(h->g2B, T) : T;
+  };
+  auto applyCh = [&](const double* src) -> const double* {         // A'^H (B'^-H src)
+    const double* s = hasb ? jacobi(h->g2Bh, src) : src;
+    spmm(h->g2Ah, s, T);
+    return T;
+  };
+  auto reduce = [&](int nslots, std::vector<double>& hostv) {
+    double* dev = h->red_ws.as<double>();
+    k_reduce_partials<double><<<1, 1024, ((size_t)nslots * FC_MAXCOLS + 1024) * sizeof(double), h->stream>>>(part, nslots, egrid, FC_MAXCOLS, nc, dev);
+    check_launch(h);
+    hostv.resize((size_t)nslots * nc);
+    FC_CUDA(cudaMemcpyAsync(hostv.data(), dev, hostv.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+  };
+  TsScal sc;
+  auto clear_sc = [&]() { memset(&sc, 0, sizeof(sc)); };
+
+  // ---- start block: v_0 = q (or C q - theta q), normalised; w_0 = v_0 ----------------------------------------------------
+  k_lz_real_part<true><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS, LzTail{});
+  check_launch(h);
+  FC_CUDA(cudaMemsetAsync(QA, 0, blk_bytes, h->stream));
+  if (!have_ritz) {
+    FC_CUDA(cudaMemcpyAsync(Vb[0], RQ, blk_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    const double* cq = applyC(RQ);
+    clear_sc();
+    for (int c = 0; c < nc; ++c) sc.a[c] = make_double2(theta[c].real(), theta[c].imag());
+    k_ts_lin3<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, cq, RQ, RQ, Vb[0], sc);      // C q - theta q  (b = 0)
+    check_launch(h);
+    clear_sc();
+    for (int c = 0; c < nc; ++c) {
+      zc acc(0.0);
+      for (int e = 0; e < ne; ++e) acc += Wne[e] / (Zne[e] - theta[c]);
+      sc.a[c] = make_double2(acc.real(), acc.imag());
+    }
+    k_ts_caxpy<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, RQ, QA, sc);                // q * sum_e w_e / (z_e - theta)
+    check_launch(h);
+  }
+  std::vector<double> hv;
+  k_ts_dot3<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Vb[0], Vb[0], part, FC_MAXCOLS);
+  check_launch(h);
+  reduce(4, hv);
+  std::vector<double> beta0(nc);
+  std::vector<char> dead(nc, 0);
+  clear_sc();
+  for (int c = 0; c < nc; ++c) {
+    beta0[c] = std::sqrt(std::max(hv[c], 0.0));
+    if (!(beta0[c] > 1e-290)) { dead[c] = 1; beta0[c] = 0.0; }
+    sc.a[c].x = dead[c] ? 0.0 : 1.0 / beta0[c];
+  }
+  k_ts_scale2<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Vb[0], nullptr, sc);
+  check_launch(h);
+  FC_CUDA(cudaMemcpyAsync(Wb[0], Vb[0], blk_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(RQ, Vb[0], blk_bytes, cudaMemcpyDeviceToDevice, h->stream));      // pass 2 starts from the same v_0
+  FC_CUDA(cudaMemsetAsync(Vb[1], 0, blk_bytes, h->stream));
+  FC_CUDA(cudaMemsetAsync(Wb[1], 0, blk_bytes, h->stream));
+
+  // ---- pass 1 (host scalars) --------------------------------------------------------------------------------------------------
+  Timer t1;
+  const size_t K1 = (size_t)kmax + 2;
+  std::vector<zc> alpha(K1 * nc, zc(0.0)), betap(K1 * nc, zc(0.0)), dd(K1 * nc, zc(1.0));
+  std::vector<double> delta(K1 * nc, 0.0), gam(K1 * nc, 0.0), scale(nc, 0.0);
+  std::vector<int> kc(nc, 0);                    // steps of column c (its T is kc x kc); 0 while the column is alive
+  std::vector<zc> lud((size_t)ne * nc), lug((size_t)ne * nc);
+  int cur = 0, k = 0;
+  double maxres = 0.0;
+  auto at = [&](int j, int c) { return (size_t)j * nc + c; };
+  for (int j = 0; j < kmax; ++j) {
+    const double* cv = applyC(Vb[cur]);
+    k_ts_dot<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Wb[cur], cv, part, FC_MAXCOLS);
+    check_launch(h);
+    reduce(2, hv);
+    clear_sc();
+    for (int c = 0; c < nc; ++c) {
+      zc al(0.0);
+      if (!dead[c] && !kc[c]) al = zc(hv[c], hv[nc + c]) / dd[at(j, c)];
+      alpha[at(j, c)] = al;
+      scale[c] = std::max(scale[c], std::abs(al));
+      sc.a[c] = make_double2(al.real(), al.imag());
+      const zc bp = betap[at(j, c)];
+      sc.b[c] = make_double2(bp.real(), bp.imag());
+    }
+    k_ts_lin3<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, cv, Vb[cur], Vb[cur ^ 1], Vb[cur ^ 1], sc);
+    check_launch(h);
+    const double* cw = applyCh(Wb[cur]);
+    for (int c = 0; c < nc; ++c) {
+      const zc al = std::conj(alpha[at(j, c)]);
+      sc.a[c] = make_double2(al.real(), al.imag());
+      zc gm(0.0);
+      if (j > 0 && !dead[c] && !kc[c]) gm = std::conj(delta[at(j, c)] * dd[at(j, c)] / dd[at(j - 1, c)]);
+      sc.b[c] = make_double2(gm.real(), gm.imag());
+    }
+    k_ts_lin3<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, cw, Wb[cur], Wb[cur ^ 1], Wb[cur ^ 1], sc);
+    check_launch(h);
+    k_ts_dot3<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Vb[cur ^ 1], Wb[cur ^ 1], part, FC_MAXCOLS);
+    check_launch(h);
+    reduce(4, hv);
+    clear_sc();
+    maxres = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      double dl = 0.0, gm = 0.0;
+      zc dn(1.0);
+      bool alive = !dead[c] && !kc[c];
+      if (alive) {
+        dl = std::sqrt(std::max(hv[c], 0.0));
+        gm = std::sqrt(std::max(hv[nc + c], 0.0));
+        const bool ok = dl > 1e-290 && gm > 1e-290 && dl > 1e-13 * std::max(scale[c], 1e-300);
+        if (ok) dn = zc(hv[2 * nc + c], hv[3 * nc + c]) / (dl * gm);
+        if (!ok || !(std::abs(dn) > 1e-10)) {      // invariant subspace reached, or a (near) breakdown of the two-sided process: the column stops here
+          alive = false;
+          kc[c] = j + 1;
+          if (!ok) dl = 0.0;
+        }
+        scale[c] = std::max(scale[c], dl);
+      }
+      delta[at(j + 1, c)] = dl;
+      gam[at(j + 1, c)] = gm;
+      dd[at(j + 1, c)] = alive ? dn : zc(1.0);
+      betap[at(j + 1, c)] = alive ? gm * dn / dd[at(j, c)] : zc(0.0);
+      sc.a[c].x = alive ? 1.0 / dl : 0.0;
+      sc.b[c].x = alive ? 1.0 / gm : 0.0;
+      // shifted residuals of every node: LU pivots of z I - T advanced by one step
+      if (!dead[c] && (kc[c] == 0 || kc[c] == j + 1)) {
+        for (int e = 0; e < ne; ++e) {
+          const size_t o = (size_t)e * nc + c;
+          zc d = Zne[e] - alpha[at(j, c)];
+          zc gg;
+          if (j == 0) gg = zc(1.0) / d;
+          else {
+            d -= betap[at(j, c)] * delta[at(j, c)] / lud[o];
+            gg = delta[at(j, c)] * lug[o] / d;
+          }
+          lud[o] = d;
+          lug[o] = gg;
+          maxres = std::max(maxres, dl * std::abs(gg));
+        }
+      }
+    }
+    k_ts_scale2<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Vb[cur ^ 1], Wb[cur ^ 1], sc);
+    check_launch(h);
+    cur ^= 1;
+    k = j + 1;
+    h->stats.krylov_iters++;
+    if (!(maxres > target)) { out.converged = true; break; }
+  }
+  out.k = k;
+  out.maxres = maxres;
+  h->stats.lz_steps_p1 += k;
+  h->stats.col_iters += (int64_t)k * nc;
+  h->stats.ms_lz_p1 += t1.ms();
+
+  // ---- coefficients: c_j = beta_0 sum_e w_e F_e [(z_e I - T)^-1 e_1]_j (complex Thomas solves on the host) ---------------------
+  std::vector<zc> coef((size_t)k * nc, zc(0.0)), ludv(k), luf(k);
+  for (int c = 0; c < nc; ++c) {
+    if (dead[c]) continue;
+    const int kk = kc[c] ? std::min(kc[c], k) : k;
+    for (int e = 0; e < ne; ++e) {
+      const zc z = Zne[e];
+      const zc wf = Wne[e] * (have_ritz ? zc(1.0) / (z - theta[c]) : zc(1.0)) * beta0[c];
+      ludv[0] = z - alpha[at(0, c)];
+      luf[0] = 1.0;
+      for (int j = 1; j < kk; ++j) {
+        const zc l = delta[at(j, c)] / ludv[j - 1];
+        ludv[j] = (z - alpha[at(j, c)]) - l * betap[at(j, c)];
+        luf[j] = l * luf[j - 1];
+      }
+      zc y = luf[kk - 1] / ludv[kk - 1];
+      coef[at(kk - 1, c)] += wf * y;
+      for (int j = kk - 2; j >= 0; --j) {
+        y = (luf[j] + betap[at(j + 1, c)] * y) / ludv[j];
+        coef[at(j, c)] += wf * y;
+      }
+    }
+  }
+
+  // ---- pass 2: replay the v-sequence, Q += c_j v_j ----------------------------------------------------------------------------------
+  Timer t2;
+  FC_CUDA(cudaMemcpyAsync(Vb[0], RQ, blk_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  FC_CUDA(cudaMemsetAsync(Vb[1], 0, blk_bytes, h->stream));
+  cur = 0;
+  for (int j = 0; j < k; ++j) {
+    clear_sc();
+    for (int c = 0; c < nc; ++c) sc.a[c] = make_double2(coef[at(j, c)].real(), coef[at(j, c)].imag());
+    k_ts_caxpy<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Vb[cur], QA, sc);
+    check_launch(h);
+    if (j == k - 1) break;
+    const double* cv = applyC(Vb[cur]);
+    clear_sc();
+    for (int c = 0; c < nc; ++c) {
+      sc.a[c] = make_double2(alpha[at(j, c)].real(), alpha[at(j, c)].imag());
+      sc.b[c] = make_double2(betap[at(j, c)].real(), betap[at(j, c)].imag());
+    }
+    k_ts_lin3<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, cv, Vb[cur], Vb[cur ^ 1], Vb[cur ^ 1], sc);
+    check_launch(h);
+    clear_sc();
+    for (int c = 0; c < nc; ++c) {
+      const bool alive = !dead[c] && (kc[c] == 0 || j + 1 < kc[c]);
+      sc.a[c].x = (alive && delta[at(j + 1, c)] > 0) ? 1.0 / delta[at(j + 1, c)] : 0.0;
+    }
+    k_ts_scale2<<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, Vb[cur ^ 1], nullptr, sc);
+    check_launch(h);
+    cur ^= 1;
+  }
+  k_lz_to_complex<true><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
+  check_launch(h);
+  sync(h);
+  h->stats.lz_steps_p2 += k;
+  h->stats.ms_lz_p2 += t2.ms();
+  h->stats.cheb_degree = KJ;
+}
+
+// =====================================================================================================
 // rank-revealing orthonormalisation (K7: _feast_qr_compress!, core/feast_aux.jl:101-131)
 // in: Z0 (n x ncols in slot `src`), out: orthonormal basis in the returned slot, rank
 // =====================================================================================================
@@ -1480,17 +1840,21 @@ static void allreduce_small(H* h, double* dev, size_t count) {   // sum over ran
   h->stats.allreduce_bytes += (int64_t)(count * sizeof(double));
 }
 
+static void nccl_barrier(H* h) {
+  if (h->nranks <= 1 || !h->nccl_comm) return;
+  double* d = h->small2.as<double>();
+  if (!d) return;
+  g_nccl.AllReduce(d, d, 1, 8, 0, h->nccl_comm, h->stream);
+  cudaStreamSynchronize(h->stream);
+}
+
 static void arena_release(H* h) {
   if (!h->arena) return;
   cudaStreamSynchronize(h->stream);
-  for (int p = 0; p < h->nranks && p < 16; ++p)
-    if (p != h->rank && h->peer_arena[p]) { cudaIpcCloseMemHandle(h->peer_arena[p]); h->peer_arena[p] = nullptr; }
-  if (h->nranks > 1 && h->nccl_comm) {   // nobody frees while a peer still has the mapping open
-    double* d = h->small2.as<double>();
-    if (d) { g_nccl.AllReduce(d, d, 1, 8, 0, h->nccl_comm, h->stream); cudaStreamSynchronize(h->stream); }
-  }
+  nccl_barrier(h);   // nobody unmaps while a peer may still be reading its rows
   for (int s = 0; s < BS_COUNT; ++s) { h->blk[s].p = nullptr; h->blk[s].cap = 0; h->blk[s].owned = true; }
-  cudaFree(h->arena);
+  peer_arena_destroy(h->parena);
+  for (int p = 0; p < 16; ++p) h->peer_arena[p] = nullptr;
   h->arena = nullptr;
   h->arena_bytes = 0;
 }
@@ -1504,34 +1868,31 @@ static void arena_allocate(H* h, int ld) {
   h->arena_slot_bytes = slot;
   h->arena_mbox_off = (size_t)BS_COUNT * slot;
   h->arena_bytes = h->arena_mbox_off + ((sizeof(LzMailbox) + 255) & ~(size_t)255);
-  FC_CUDA(cudaMalloc(&h->arena, h->arena_bytes));
+  std::string err = peer_arena_create(h->parena, h->device, h->nranks, h->rank, h->ipc_token, h->arena_bytes, [&]() { nccl_barrier(h); });
+  if (h->nranks > 1) {   // all or nothing
+    double fl = err.empty() ? 0.0 : 1.0;
+    double* d = h->small2.as<double>();
+    FC_CUDA(cudaMemcpyAsync(d, &fl, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FC_NCCL(g_nccl.AllReduce(d, d, 1, 8, 0, h->nccl_comm, h->stream));
+    FC_CUDA(cudaMemcpyAsync(&fl, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+    if (fl > 0 && err.empty()) { peer_arena_destroy(h->parena); err = "a peer rank could not map the shared arena"; }
+  }
+  if (!err.empty()) throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "row sharding: " + err);
+  // distances between rows must fit the kernels' signed 32-bit offsets (16-byte units)
+  FC_REQUIRE((double)h->parena.stride * (double)h->nranks / 16.0 < 2147483647.0, "row sharding: the ranks' arenas span more than 32 GB");
+  for (int p = 0; p < h->nranks; ++p) h->peer_arena[p] = (void*)(uintptr_t)(h->parena.base + (size_t)p * h->parena.stride);
+  h->arena = h->peer_arena[h->rank];
   FC_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
   for (int s = 0; s < BS_COUNT; ++s) {
     h->blk[s].p = (char*)h->arena + (size_t)s * slot;
     h->blk[s].cap = slot;
     h->blk[s].owned = false;
   }
-  h->peer_arena[h->rank] = h->arena;
   h->goff_rowbytes2[0] = h->goff_rowbytes2[1] = 0;
   h->xseq = 0;
-  if (h->nranks > 1) {
-    // every rank's cudaIpcMemHandle_t travels through one ncclAllGather; the peers' arenas are then mapped into this process
-    cudaIpcMemHandle_t mine;
-    FC_CUDA(cudaIpcGetMemHandle(&mine, h->arena));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    DBuf hb;
-    hb.ensure((size_t)64 * h->nranks);
-    FC_CUDA(cudaMemcpyAsync((char*)hb.p + 64 * h->rank, &mine, 64, cudaMemcpyHostToDevice, h->stream));
-    FC_REQUIRE(g_nccl.AllGather != nullptr, "libnccl: ncclAllGather missing");
-    FC_NCCL(g_nccl.AllGather((char*)hb.p + 64 * h->rank, hb.p, 64, /*ncclChar*/ 0, h->nccl_comm, h->stream));
-    std::vector<cudaIpcMemHandle_t> all(h->nranks);
-    FC_CUDA(cudaMemcpyAsync(all.data(), hb.p, (size_t)64 * h->nranks, cudaMemcpyDeviceToHost, h->stream));
-    sync(h);
-    hb.release();
-    for (int p = 0; p < h->nranks; ++p)
-      if (p != h->rank) FC_CUDA(cudaIpcOpenMemHandle(&h->peer_arena[p], all[p], cudaIpcMemLazyEnablePeerAccess));
-  }
   sync(h);
+  nccl_barrier(h);   // every rank's mailbox is zeroed before anyone writes into it
 }
 
 static void fill_xchg(H* h, LzXchg& x) {
@@ -1555,14 +1916,15 @@ static void xbarrier(H* h) {
 
 // gather offsets of A's local rows for blocks whose rows are `rowbytes` apart (two strides are in use: the compact Lanczos blocks
 // and the engine's complex blocks viewed as interleaved real columns)
-static const long long* resolve_goff(H* h, int64_t rowbytes) {
+static const int* resolve_goff(H* h, int64_t rowbytes) {
   const int64_t nnz = h->nnz_loc;
   const int slot = (h->goff_rowbytes2[0] == rowbytes) ? 0 : ((h->goff_rowbytes2[1] == rowbytes) ? 1 : -1);
-  if (slot >= 0) return h->goff.as<long long>() + (size_t)slot * (size_t)std::max<int64_t>(nnz, 1);
+  if (slot >= 0) return h->goff.as<int>() + (size_t)slot * (size_t)std::max<int64_t>(nnz, 1);
+  FC_REQUIRE(rowbytes % 16 == 0, "row sharding: rows must be multiples of 16 bytes");
   const int use = h->goff_next;
   h->goff_next ^= 1;
-  h->goff.ensure((size_t)2 * (size_t)std::max<int64_t>(nnz, 1) * sizeof(long long));
-  long long* out = h->goff.as<long long>() + (size_t)use * (size_t)std::max<int64_t>(nnz, 1);
+  h->goff.ensure((size_t)2 * (size_t)std::max<int64_t>(nnz, 1) * sizeof(int));
+  int* out = h->goff.as<int>() + (size_t)use * (size_t)std::max<int64_t>(nnz, 1);
   LzArenas ar;
   memset(&ar, 0, sizeof(ar));
   for (int p = 0; p < h->nranks; ++p) ar.base[p] = (const char*)h->peer_arena[p];
@@ -2076,10 +2438,32 @@ static void run_contour(H* h, zc Emid, double r, int m0, int64_t* fpm, const zc*
     Timer tsolve;
     zd* basis = blk(h, qb);
     const zd* rhs = basis;
-    if (h->has_b) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
+    // sparse pencils: ONE two-sided Lanczos recurrence per column serves all nodes (msl2_filter); ranks own column slices
+    const int cb = active / h->nranks, cr = active % h->nranks;
+    const int sl_c0 = h->rank * cb + std::min(h->rank, cr), sl_nc = cb + (h->rank < cr ? 1 : 0);
+    const bool use_msl2 = iterative && o.solver == FEASTCUDA_SOLVER_MSLANCZOS && sl_nc <= TS_MAXC && gen2_prepare(h);
+    if (h->has_b && !use_msl2) { apply_op(h, FEASTCUDA_B, active, basis, blk(h, BS_RHS)); rhs = blk(h, BS_RHS); }
     zero_cols(h, active, blk(h, BS_ACC));
-    std::vector<WorkItem> items = build_items(ne, active, h->nranks, h->rank, shard, cost);
+    std::vector<WorkItem> items;
+    if (!use_msl2) items = build_items(ne, active, h->nranks, h->rank, shard, cost);
     bool failed = false;
+    if (use_msl2 && sl_nc > 0) {
+      const bool first = !(o.ritz_guess && loop > 0);
+      double target = (first && o.inner_rel0 > 0) ? o.inner_rel0 : o.inner_rel;
+      if (!(target > 0)) target = tol;
+      if (o.adaptive && !first && std::isfinite(eps_val) && eps_val > 0) {
+        const double t = 2.0 * eps_tol / eps_val;
+        if (t >= 1e-6) target = std::min(0.1, t);
+      }
+      MslOut mo;
+      msl2_filter(h, qb, sl_c0, sl_nc, !first, lam.data() + sl_c0, Zne, Wne, ne, target, (first && o.maxiter0 > 0) ? o.maxiter0 : o.maxiter,
+                  o.b_delta > 0 ? o.b_delta : 1e-10, mo);
+      h->stats.node_solves += ne;
+      for (int e = 0; e < ne && e < 128; ++e) h->stats.node_iters[e] = mo.k;
+      if (getenv("FEASTCUDA_VERBOSE"))
+        fprintf(stderr, "[feastcuda r%d] general loop %d: two-sided lanczos k=%d maxres=%.3e converged=%d cols=[%d,%d) target=%.1e\n", h->rank, loop,
+                mo.k, mo.maxres, (int)mo.converged, sl_c0, sl_c0 + sl_nc, target);
+    }
     if (dense_items_batched(h, items, ne, active, Zne, Wne, 1.0, rhs, &failed) && failed) info_code = 8;
     for (const WorkItem& it : items) {
       zd* X = blk(h, BS_KX) + it.c0;
@@ -2316,6 +2700,7 @@ static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t
     h->dA.val32_ready = false;
     if (h->kind != OP_SPARSE || (h->has_b && h->hB.n != n)) { h->has_b = false; h->hB.set = false; h->dB.uploaded = false; }   // a B of another size never survives a new A
     h->cheb_ready = false;
+    h->g2_ready = false;
     h->kind = OP_SPARSE;
     h->n = n;
     release_factor_cache(h);
@@ -2325,6 +2710,7 @@ static int set_csr_common(H* h, int which, int64_t n, int64_t nnz, const int64_t
     h->dB.uploaded = false;
     h->has_b = true;
     h->cheb_ready = false;
+    h->g2_ready = false;
   }
   FC_CATCH
 }
@@ -2341,6 +2727,7 @@ int feastcuda_clear_b(feastcuda_handle h) {
   h->has_b = false;
   h->hB.set = false;
   h->cheb_ready = false;
+  h->g2_ready = false;
   h->denseB.set = false;
   h->bandB.set = false;
   h->dB.uploaded = false;
@@ -2700,6 +3087,9 @@ int feastcuda_nccl_init(feastcuda_handle h, int nranks, int rank, const char* id
   NcclId id;
   memcpy(id.internal, id128, 128);
   FC_NCCL(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
+  unsigned long long tk = 1469598103934665603ull;      // FNV-1a of the unique id: the same on every rank of this communicator
+  for (int i = 0; i < 128; ++i) { tk ^= (unsigned char)id128[i]; tk *= 1099511628211ull; }
+  h->ipc_token = tk;
   h->nranks = nranks;
   h->rank = rank;
   FC_CATCH

@@ -241,9 +241,8 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   __shared__ int s_last;
   double* t_so = scratch;
   double* t_tmp = scratch + FC_MAXCOLS;
-  if (t.x.nranks > 1) __threadfence_system();   // this CTA's vector rows must be visible to the peers before the flag is raised
-  else __threadfence();
-  __syncthreads();
+  __threadfence();      // this CTA's rows are visible device-wide before its ticket; the CTA that raises the cross-rank flag adds the
+  __syncthreads();      // system-scope fence (lz_exchange), which is cumulative over everything it has observed
   // two levels, both in a fixed order: the last CTA of every group of LZ_TAIL_GROUP consecutive CTAs sums the group's rows, the last
   // group to finish sums the group sums (a single CTA summing several hundred rows would cost more than the kernels it replaced)
   const int grp = (int)blockIdx.x / LZ_TAIL_GROUP, ngroups = ((int)gridDim.x + LZ_TAIL_GROUP - 1) / LZ_TAIL_GROUP;
@@ -327,7 +326,7 @@ struct LzArgs {
   LzTail tail;           // what the last CTA does after the row loop (pass 1: the step's scalars; sharded pass 2: the step barrier)
   // row-sharded runs: `n` rows are this rank's block; the uploaded column index of an entry is (owner rank << LZ_OWNER_SHIFT) | row
   // local to the owner, resolved once per row stride into `goff`
-  const long long* goff; // row-sharded runs: per stored entry, the byte offset from a local block to the gathered row (k_lz_resolve)
+  const int* goff;       // row-sharded runs: per stored entry, the distance (16-byte units) from a local block to the gathered row (k_lz_resolve)
   const int* tile_order; // row-sharded runs: the order in which the row tiles are dealt to the CTAs (nullptr: natural order)
 };
 constexpr int LZ_OWNER_SHIFT = 26;
@@ -379,9 +378,10 @@ template <bool CPLX> __device__ __forceinline__ int lz_elems(int m) { return CPL
 // beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
 // Narrow groups (G <= 4 lanes per row) also receive the row's SECOND chunk of G entries prefetched (myo2, mya2): a
 // 7-point row then needs no dependent metadata load inside the loop even with 4 lanes per row.
-// Row-sharded runs (SHARD): the metadata of an entry is a pre-resolved 64-bit BYTE offset from the local block to the gathered row
-// (k_lz_resolve: (arena[owner] - arena[self]) + local_row * row_bytes; the owner's copy of a block sits at the same arena offset as
-// the local one), so a halo row in a peer's HBM is read by the same load as a local row, over NVLink.
+// Row-sharded runs (SHARD): the metadata of an entry is a pre-resolved SIGNED 32-bit distance, in 16-byte units, from the local block to
+// the gathered row (k_lz_resolve: the ranks' arenas are mapped into one contiguous virtual range, peer_arena.hpp, and the owner's copy
+// of a block sits at the same arena offset as the local one), so a halo row in a peer's HBM is read by the same load as a local row --
+// over NVLink -- at the same instruction count as the single-GPU kernel.
 template <bool SHARD> struct LzOff;
 template <> struct LzOff<false> {
   typedef unsigned T;
@@ -390,12 +390,10 @@ template <> struct LzOff<false> {
   static __device__ __forceinline__ const double* at(const double* base, T o) { return base + o; }
 };
 template <> struct LzOff<true> {
-  typedef long long T;
+  typedef int T;
   static __device__ __forceinline__ T meta(const LzArgs& a, int p, unsigned) { return a.goff[p]; }
-  static __device__ __forceinline__ T own(unsigned eo_own) { return (long long)eo_own * 8; }
-  static __device__ __forceinline__ const double* at(const double* base, T o) {
-    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + o);
-  }
+  static __device__ __forceinline__ T own(unsigned eo_own) { return (int)(eo_own >> 1); }
+  static __device__ __forceinline__ const double* at(const double* base, T o) { return base + 2 * (long long)o; }
 };
 
 template <int G, int NC, bool CPLX, bool SHARD>
@@ -792,12 +790,12 @@ __global__ void __launch_bounds__(128) k_lz_barrier(LzXchg x) {
 
 // pre-resolved gather offsets of a row-sharded operator: enc = (owner << LZ_OWNER_SHIFT) | row local to the owner
 __global__ void __launch_bounds__(256) k_lz_resolve(int64_t nnz, const int* __restrict__ enc, long long row_bytes, int self,
-                                                    LzArenas ar, long long* __restrict__ goff) {
+                                                    LzArenas ar, int* __restrict__ goff) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned e = (unsigned)enc[i];
     const int owner = (int)(e >> LZ_OWNER_SHIFT);
     const long long local = (long long)(e & ((1u << LZ_OWNER_SHIFT) - 1u));
-    goff[i] = (long long)(ar.base[owner] - ar.base[self]) + local * row_bytes;
+    goff[i] = (int)(((long long)(ar.base[owner] - ar.base[self]) + local * row_bytes) / 16);
   }
 }
 

@@ -328,9 +328,14 @@ def _general_solve(kind, setA, setB, N, Emid, r, M0, fpm, contour=None, solver="
         solver_maxiter = 2000 if kind == "sparse" else 500
     if solver_restart is None:
         solver_restart = 3
+    # sparse pencils: ONE two-sided Lanczos recurrence per column serves every node of the contour (the engine keeps the per-node block
+    # BiCGStab when B is not diagonally dominant or the block is wider than 64 columns per rank); solver="bicgstab" forces the latter
     kw = dict(solver_tol=solver_tol, solver_maxiter=int(solver_maxiter),
-              solver="bicgstab" if kind == "sparse" else "direct", solver_restart=int(solver_restart))
-    for k in ("inner_rel", "shard", "check_every", "eps_floor", "ritz_guess"):
+              solver=("bicgstab" if solver_choice == "bicgstab" else "mslanczos") if kind == "sparse" else "direct",
+              solver_restart=int(solver_restart))
+    if kind == "sparse":
+        kw.update(ritz_guess=True, inner_rel=1e-3, adaptive=True)
+    for k in ("inner_rel", "shard", "check_every", "eps_floor", "ritz_guess", "adaptive", "inner_rel0", "maxiter0", "b_delta"):
         if k in extras:
             kw[k] = extras.pop(k)
     if extras:

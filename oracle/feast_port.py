@@ -1100,3 +1100,198 @@ def feast_hrr_mslanczos_gen_cheb(A, B, Emin, Emax, M0, fpm, Q0, inner_rel=1e-3, 
         Qb = X[:, :active].copy()
         have_ritz = True
     return fo.FeastResult(lam[:M_found].copy(), X[:, :M_found].copy(), M_found, res[:M_found].copy(), info, epsout, loop_count, stats)
+
+
+# ======================================================================================================================
+# General pencils as the CUDA engine runs them (csrc/feastcuda.cu:msl2_filter): TWO-SIDED multi-shift Lanczos, two passes, no stored
+# basis.  C = B'^-1 A' with the rows scaled by diag(B)^-1 and B'^-1 a FIXED number of Jacobi sweeps (a polynomial in B', so the
+# adjoint operator of the w-sequence is the same polynomial in B'^H).  ||v_j|| = ||w_j|| = 1, d_j = w_j^H v_j, T_k complex tridiagonal:
+#     C v_j = beta'_j v_{j-1} + alpha_j v_j + delta_{j+1} v_{j+1},      beta'_{j+1} = gamma_{j+1} d_{j+1} / d_j,
+#     C^H w_j = conj(delta_j d_j / d_{j-1}) w_{j-1} + conj(alpha_j) w_j + gamma_{j+1} w_{j+1}.
+# ======================================================================================================================
+def jacobi_setup(A, B):
+    """Row-scaled operators (A', B') with unit diagonal of B', their conjugate transposes, and the contraction bound q of I - B'."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix(A, dtype=complex)
+    n = A.shape[0]
+    if B is None:
+        return A, None, A.conj().T.tocsr(), None, 0.0
+    B = sp.csr_matrix(B, dtype=complex)
+    d = B.diagonal()
+    assert np.all(np.abs(d) > 0)
+    Dinv = sp.diags(1.0 / d)
+    Ap, Bp = (Dinv @ A).tocsr(), (Dinv @ B).tocsr()
+    off = abs(Bp - sp.identity(n, dtype=complex, format="csr"))
+    q = max(float(off.sum(axis=1).max()), float(off.sum(axis=0).max()))
+    return Ap, Bp, Ap.conj().T.tocsr(), Bp.conj().T.tocsr(), q
+
+
+def jacobi_solve(M, R, K):
+    """K Jacobi sweeps from x_1 = r for a unit-diagonal M (k_lz_spmm<LZ_CHEB> with c1 = 0, c2 = 1)."""
+    x = R
+    for _ in range(1, K):
+        x = x + (R - M @ x)
+    return x
+
+
+def mstwosided_filter(ops, Q, theta, Zne, Wne, target, kmax, jac_delta=1e-10, stats=None):
+    """sum_e w_e (z_e B - A)^-1 B q for the block Q (full contour); theta = Ritz values (residual start) or None."""
+    Ap, Bp, Ah, Bh, q = ops
+    n, m = Q.shape
+    ne = len(Zne)
+    Z, W = np.asarray(Zne), np.asarray(Wne)
+    KJ = 1 if Bp is None or q <= 0 else max(1, int(math.ceil(math.log(jac_delta) / math.log(q))))
+    applyC = (lambda X: Ap @ X) if Bp is None else (lambda X: jacobi_solve(Bp, Ap @ X, KJ))
+    applyCh = (lambda X: Ah @ X) if Bp is None else (lambda X: Ah @ jacobi_solve(Bh, X, KJ))
+    Qc = Q.astype(complex)
+    if theta is None:
+        b, F, acc = Qc, np.ones((ne, m), dtype=complex), np.zeros((n, m), dtype=complex)
+    else:
+        b = applyC(Qc) - Qc * theta
+        F = 1.0 / (Z[:, None] - theta[None, :])
+        acc = Qc * (W[:, None] * F).sum(axis=0)
+    beta0 = np.linalg.norm(b, axis=0)
+    v0 = b / np.where(beta0 > 0, beta0, 1.0)
+    alpha = np.zeros((kmax + 2, m), dtype=complex)
+    betap = np.zeros((kmax + 2, m), dtype=complex)
+    delta = np.zeros((kmax + 2, m))
+    dd = np.ones((kmax + 2, m), dtype=complex)
+    kc = np.zeros(m, dtype=int)
+    v, w = v0.copy(), v0.copy()
+    vp, wp = np.zeros_like(v), np.zeros_like(w)
+    lud = np.zeros((ne, m), dtype=complex)
+    lug = np.zeros((ne, m), dtype=complex)
+    scale = np.zeros(m)
+    k = 0
+    for j in range(kmax):
+        alive = (kc == 0) & (beta0 > 0)
+        cv = applyC(v)
+        al = np.where(alive, np.einsum("ij,ij->j", w.conj(), cv) / dd[j], 0.0)
+        alpha[j] = al
+        scale = np.maximum(scale, np.abs(al))
+        vh = cv - al * v - betap[j] * vp
+        cw = applyCh(w)
+        gmc = np.conj(delta[j] * dd[j] / dd[j - 1]) if j > 0 else np.zeros(m)
+        wh = cw - np.conj(al) * w - np.where(alive, gmc, 0.0) * wp
+        dl, gm = np.linalg.norm(vh, axis=0), np.linalg.norm(wh, axis=0)
+        ok = alive & (dl > 1e-290) & (gm > 1e-290) & (dl > 1e-13 * np.maximum(scale, 1e-300))
+        dn = np.where(ok, np.einsum("ij,ij->j", wh.conj(), vh) / np.where(ok, dl * gm, 1.0), 1.0)
+        stop = alive & (~ok | ~(np.abs(dn) > 1e-10))
+        kc = np.where(stop, j + 1, kc)
+        dl = np.where(alive & ~ok, 0.0, dl)
+        live = alive & ~stop
+        scale = np.maximum(scale, np.where(alive, dl, 0.0))
+        delta[j + 1] = np.where(alive, dl, 0.0)
+        dd[j + 1] = np.where(live, dn, 1.0)
+        betap[j + 1] = np.where(live, gm * dn / dd[j], 0.0)
+        worst = 0.0
+        for e in range(ne):
+            if j == 0:
+                d = Z[e] - al
+                g = 1.0 / d
+            else:
+                d = (Z[e] - al) - betap[j] * delta[j] / lud[e]
+                g = delta[j] * lug[e] / d
+            upd = alive
+            lud[e] = np.where(upd, d, lud[e])
+            lug[e] = np.where(upd, g, lug[e])
+            worst = max(worst, float(np.where(upd, delta[j + 1] * np.abs(g), 0.0).max()))
+        vp, wp = v, w
+        v = np.where(live, vh / np.where(live, dl, 1.0), 0.0)
+        w = np.where(live, wh / np.where(live, gm, 1.0), 0.0)
+        k = j + 1
+        if not worst > target:
+            break
+    coef = np.zeros((k, m), dtype=complex)
+    for c in range(m):
+        if not beta0[c] > 0:
+            continue
+        kk = min(kc[c], k) if kc[c] else k
+        for e in range(ne):
+            wf = W[e] * F[e, c] * beta0[c]
+            ludv = np.zeros(kk, dtype=complex)
+            luf = np.zeros(kk, dtype=complex)
+            ludv[0], luf[0] = Z[e] - alpha[0, c], 1.0
+            for j in range(1, kk):
+                l = delta[j, c] / ludv[j - 1]
+                ludv[j] = (Z[e] - alpha[j, c]) - l * betap[j, c]
+                luf[j] = l * luf[j - 1]
+            y = luf[kk - 1] / ludv[kk - 1]
+            coef[kk - 1, c] += wf * y
+            for j in range(kk - 2, -1, -1):
+                y = (luf[j] + betap[j + 1, c] * y) / ludv[j]
+                coef[j, c] += wf * y
+    # pass 2: the v-sequence alone
+    v, vp = v0.copy(), np.zeros_like(v0)
+    for j in range(k):
+        acc += coef[j] * v
+        if j == k - 1:
+            break
+        vh = applyC(v) - alpha[j] * v - betap[j] * vp
+        live = (beta0 > 0) & ((kc == 0) | (j + 1 < kc)) & (delta[j + 1] > 0)
+        vp, v = v, np.where(live, vh / np.where(live, delta[j + 1], 1.0), 0.0)
+    if stats is not None:
+        stats["lz_steps"].append(k)
+        stats["jacobi_sweeps"] = KJ
+    return acc
+
+
+def feast_general_mstwosided(A, B, Emid, r, M0, fpm, Q0, inner_rel=1e-3, inner_maxiter=2000, adaptive=True, verbose=False, jac_delta=1e-10):
+    """General FEAST (run_contour's loop: orthonormalised block, one-sided Rayleigh-Ritz, residuals with B) around mstwosided_filter."""
+    import scipy.linalg as sla
+    import scipy.sparse as sp
+    N = A.shape[0]
+    fo.feastdefault(fpm)
+    fo.check_feast_grci_input(N, M0, Emid, r, fpm)
+    Emid = complex(Emid)
+    Zne, Wne = fo.feast_gcontour(Emid, r, fpm)
+    eps_tol = fo.feast_tolerance(fpm)
+    Ac = sp.csr_matrix(A, dtype=complex)
+    Bc = sp.identity(N, dtype=complex, format="csr") if B is None else sp.csr_matrix(B, dtype=complex)
+    ops = jacobi_setup(A, B)
+    Qb = np.array(Q0, dtype=complex)
+    lam, res = np.zeros(M0, dtype=complex), np.zeros(M0)
+    X = np.zeros((N, M0), dtype=complex)
+    have_ritz, active = False, M0
+    info, epsout, loop_count, M_found = fo.SUCCESS, math.inf, 0, 0
+    stats = {"lz_steps": []}
+    for loop_idx in range(fpm[3] + 1):
+        loop_count = loop_idx
+        target = inner_rel
+        if adaptive and have_ritz and math.isfinite(epsout) and epsout > 0:
+            t = 2.0 * eps_tol / epsout
+            if t >= 1e-6:
+                target = min(0.1, t)
+        acc = mstwosided_filter(ops, Qb[:, :active], lam[:active].copy() if have_ritz else None, Zne, Wne, target, inner_maxiter, jac_delta, stats)
+        Qr, rank = fo.qr_compress(np.ascontiguousarray(acc), active)
+        if rank == 0:
+            info = fo.ERR_NO_CONV
+            break
+        lam_red, v_red = sla.eig(Qr.conj().T @ (Ac @ Qr), Qr.conj().T @ (Bc @ Qr))
+        Xc = np.zeros((N, M0), dtype=complex)
+        Xc[:, :rank] = Qr @ v_red
+        lam[:rank] = lam_red
+        M = fo.reorder_by_gcontour(lam, Xc, Emid, r, fpm, rank)
+        if M == 0:
+            info = fo.ERR_NO_CONV
+            break
+        nrm = np.linalg.norm(Xc[:, :rank], axis=0)
+        Xc[:, :rank] /= np.where(nrm > 0, nrm, 1.0)
+        X = Xc
+        R = Ac @ X[:, :M] - (Bc @ X[:, :M]) * lam[:M]
+        res[:M] = np.linalg.norm(R, axis=0) / np.maximum(np.abs(lam[:M]), 1.0)
+        epsout = float(res[:M].max())
+        M_found = M
+        if verbose:
+            print(f"loop {loop_idx}: M={M} rank={rank} epsout={epsout:.3e} k={stats['lz_steps'][-1]} KJ={stats.get('jacobi_sweeps')}", flush=True)
+        if epsout <= eps_tol:
+            break
+        if loop_idx == fpm[3]:
+            info = fo.ERR_NO_CONV
+            break
+        active = rank
+        Qb = X[:, :active].copy()
+        have_ritz = True
+    lam_out, q_out, res_out = lam[:M_found].copy(), X[:, :M_found].copy(), res[:M_found].copy()
+    fo.feast_sort_general(lam_out, q_out, res_out, M_found)
+    return fo.FeastResult(lam_out, q_out, M_found, res_out, info, epsout, loop_count, stats)

@@ -175,7 +175,7 @@ struct feastcuda_handle_s {
   int64_t goff_rowbytes = 0, goff_rowbytes2[2] = {0, 0};
   int goff_next = 0;
   feastcuda::DBuf tile_order;                  // order in which the gather kernels deal their row tiles (halo tiles spread out)
-  int tile_order_tr = 0;
+  int tile_order_tr = 0, halo_start = 0;
   feastcuda::DBuf lz_ticket, lz_grows;         // counters and group sums of the two-level tail reductions (kernels_lanczos.cuh: lz_tail)
   int64_t nnz_loc = 0;                         // stored entries of the local rows
   unsigned long long xseq = 0;                 // sequence number of the last cross-rank exchange

@@ -554,7 +554,8 @@ static int lz_grid_spmm(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0)
 }
 
 // Row-sharded runs: the order in which k_lz_spmm deals its row tiles.  Tiles holding a row with a stored entry in a peer's block (halo
-// gathers over NVLink) are spread evenly among the interior tiles, which keep their natural order (the L2 "moving front").
+// gathers over NVLink; for a symmetric pattern these are also the rows the peers read) come LAST, after the interior tiles in their
+// natural order (the L2 "moving front"): in pass 2 a kernel only has to wait for the peers' previous kernel just before these tiles.
 static const int* shard_tile_order(H* h, int rows_per_step) {
   const int tr = std::max(1, h->lz_tile_rows / rows_per_step) * rows_per_step;
   if (h->tile_order_tr == tr && h->tile_order.p) return h->tile_order.as<int>();
@@ -575,12 +576,9 @@ static const int* shard_tile_order(H* h, int rows_per_step) {
     (remote ? halo : inner).push_back(t);
   }
   order.reserve(ntiles);
-  size_t ih = 0, ii = 0;
-  for (int v = 0; v < ntiles; ++v) {
-    // place halo tile number ih when the running share of halo tiles falls behind
-    const bool want_halo = ih < halo.size() && ((double)(ih + 1) * ntiles <= (double)(v + 1) * halo.size() || ii >= inner.size());
-    order.push_back(want_halo ? halo[ih++] : inner[ii++]);
-  }
+  order.insert(order.end(), inner.begin(), inner.end());
+  order.insert(order.end(), halo.begin(), halo.end());
+  h->halo_start = (int)inner.size();
   h->tile_order.ensure((size_t)std::max(1, ntiles) * sizeof(int));
   FC_CUDA(cudaMemcpyAsync(h->tile_order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   sync(h);
@@ -606,6 +604,9 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
       if (a.goff != nullptr) {                                                             \
         if constexpr (!CPLX && NC <= 2 && MODE <= LZ_P2_PAIR) {                            \
           a.tile_order = shard_tile_order(h, 16 * (32 / G));                               \
+          a.halo_start = h->halo_start;                                                    \
+          a.nranks = h->nranks; a.rank = h->rank;                                          \
+          a.kdone = reinterpret_cast<const LzMailbox*>((const char*)h->arena + h->arena_mbox_off)->kdone; \
           k_lz_spmm<G, NC, MODE, 512, CPLX, true><<<grid, 512, 0, h->stream>>>(a);         \
         } else throw FcError(FEASTCUDA_ERR_UNSUPPORTED, "row-sharded gather: real blocks only"); \
       } else k_lz_spmm<G, NC, MODE, 512, CPLX><<<grid, 512, 0, h->stream>>>(a);            \
@@ -790,6 +791,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     return t;
   };
   const int bar_kind = sharded ? LZ_TAIL_BARRIER : LZ_TAIL_NONE;
+  xbarrier(h);   // row-sharded: no peer is still reading the blocks this sweep is about to overwrite
 
   // ---- real work blocks (each aliases a complex slot; n x ld doubles) -------------------------------------------
   double* RQ = rblk(h, BS_KS);
@@ -1003,8 +1005,13 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
       a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
       a.tile_rows = h->lz_tile_rows;
-      a.tail = mk_tail(bar_kind, j);
-      if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
+      if (sharded) {
+        // no rank waits at the end of a pass-2 kernel: it signals its completion to the peers, and the NEXT kernel waits for the peers'
+        // signals only before its halo tiles (which come last)
+        a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
+        a.wait_seq = (h->nranks > 1 && j > 0) ? h->xseq : 0;     // the signal of the previous pass-2 kernel
+        a.tail = mk_tail(LZ_TAIL_SIGNAL, j);
+      }
       if (q_mode == 0) lz_launch<LZ_P2, CPLX>(h, a, &g);
       else if (q_mode == 1) lz_launch<LZ_P2_SKIP, CPLX>(h, a, &g);
       else lz_launch<LZ_P2_PAIR, CPLX>(h, a, &g);
@@ -1013,6 +1020,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   }
   k_lz_to_complex<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, ldz, QA, blk(h, BS_ACC) + c0);
   check_launch(h);
+  xbarrier(h);   // row-sharded: every rank has finished its last gather of the Lanczos blocks
   sync(h);  // coef is a host buffer
   // algorithmic bytes of an AVERAGE pass-2 launch: paired accumulation moves the accumulator in every second launch only
   h->stats.bytes_kern[FEASTCUDA_KERN_LZ_P2] =

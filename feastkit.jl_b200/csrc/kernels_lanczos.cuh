@@ -69,6 +69,7 @@ constexpr int LZ_MBOX_SLOTS = 4;
 struct LzMailbox {   // lives in every rank's shared arena (zeroed at allocation)
   double data[LZ_MBOX_SLOTS][LZ_MAXRANKS][FC_MAXCOLS];
   unsigned long long flag[LZ_MBOX_SLOTS][LZ_MAXRANKS];
+  unsigned long long kdone[LZ_MAXRANKS];   // kdone[p]: sequence number of the last kernel rank p has completed (LZ_TAIL_SIGNAL)
 };
 struct LzXchg {
   int nranks, rank;                    // nranks <= 1: single GPU, nothing below is used
@@ -100,13 +101,12 @@ __device__ __forceinline__ void lz_exchange(const LzXchg& x, double* so, int m) 
     const int p = i / m, c = i % m;
     x.mbox[p]->data[slot][x.rank][c] = so[c];
   }
-  __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < x.nranks) {
-    __threadfence_system();
+    __threadfence_system();     // cumulative: everything this CTA has observed (the other CTAs' rows, the stores above) precedes the flag
     st_sys_u64(&x.mbox[threadIdx.x]->flag[slot][x.rank], x.seq);
     const unsigned long long* mine = &x.mbox[x.rank]->flag[slot][threadIdx.x];
-    while (ld_sys_u64(mine) != x.seq) { __nanosleep(20); }
+    while (ld_sys_u64(mine) != x.seq) { }
   }
   __syncthreads();
   if ((int)threadIdx.x < m) {
@@ -115,6 +115,17 @@ __device__ __forceinline__ void lz_exchange(const LzXchg& x, double* so, int m) 
     so[threadIdx.x] = s;
   }
   __syncthreads();
+}
+
+// "this rank has completed kernel number seq" to every peer, without waiting (pass 2 of a row-sharded run: the consumers wait lazily, just
+// before their halo tiles)
+__device__ __forceinline__ void lz_signal(const LzXchg& x) {
+  if (x.nranks <= 1) return;
+  __syncthreads();
+  if ((int)threadIdx.x < x.nranks && (int)threadIdx.x != x.rank) {
+    __threadfence_system();
+    st_sys_u64(&x.mbox[threadIdx.x]->kdone[x.rank], x.seq);
+  }
 }
 
 // fixed-order sum of the per-CTA partial rows (L2 reads: the rows were written by other CTAs of the same launch)
@@ -222,7 +233,7 @@ __device__ __forceinline__ void lz_scalars_beta(const LzScalars& s, int j, const
 
 // Tail of a producer kernel: the LAST CTA to finish (ticket counter) sums the per-CTA partial rows in a fixed order, exchanges the
 // sums with the other ranks and runs the scalar recurrences that used to be separate one-CTA launches.
-enum LzTailKind { LZ_TAIL_NONE = 0, LZ_TAIL_INIT = 1, LZ_TAIL_ALPHA = 2, LZ_TAIL_BETA = 3, LZ_TAIL_BARRIER = 4 };
+enum LzTailKind { LZ_TAIL_NONE = 0, LZ_TAIL_INIT = 1, LZ_TAIL_ALPHA = 2, LZ_TAIL_BETA = 3, LZ_TAIL_BARRIER = 4, LZ_TAIL_SIGNAL = 5 };
 constexpr int LZ_TAIL_GROUP = 16;   // CTAs per first-level group of the two-level tail reduction
 struct LzTail {
   int kind;          // LzTailKind
@@ -254,7 +265,7 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (t.kind != LZ_TAIL_BARRIER) {
+  if (t.kind != LZ_TAIL_BARRIER && t.kind != LZ_TAIL_SIGNAL) {
     lz_reduce_rows(partial + (int64_t)grp * LZ_TAIL_GROUP * pstride, gsize, pstride, m, t_so, t_tmp);
     if ((int)threadIdx.x < m) t.grows[(int64_t)grp * FC_MAXCOLS + threadIdx.x] = t_so[threadIdx.x];
     __threadfence();
@@ -270,6 +281,8 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   __threadfence();
   if (t.kind == LZ_TAIL_BARRIER) {
     lz_exchange(t.x, t_so, 0);
+  } else if (t.kind == LZ_TAIL_SIGNAL) {
+    lz_signal(t.x);
   } else {
     lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
     lz_exchange(t.x, t_so, m);
@@ -327,7 +340,11 @@ struct LzArgs {
   // row-sharded runs: `n` rows are this rank's block; the uploaded column index of an entry is (owner rank << LZ_OWNER_SHIFT) | row
   // local to the owner, resolved once per row stride into `goff`
   const int* goff;       // row-sharded runs: per stored entry, the distance (16-byte units) from a local block to the gathered row (k_lz_resolve)
-  const int* tile_order; // row-sharded runs: the order in which the row tiles are dealt to the CTAs (nullptr: natural order)
+  const int* tile_order; // row-sharded runs: the order in which the row tiles are dealt to the CTAs (nullptr: natural order); halo tiles last
+  int halo_start;        // position in tile_order of the first tile that reads (and is read by) a peer
+  unsigned long long wait_seq;          // > 0: before its first halo tile a warp waits until every peer has completed kernel wait_seq
+  const unsigned long long* kdone;      // the local mailbox's kdone[] (written by the peers)
+  int nranks, rank;
 };
 constexpr int LZ_OWNER_SHIFT = 26;
 struct LzArenas { const char* base[LZ_MAXRANKS]; };   // arena base of every rank as mapped in this process
@@ -545,7 +562,19 @@ __global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_
   if (g < p1_cur - p0_cur) { o_cur = OF::meta(a, p0_cur + g, ldu); a_cur = V::load(a.val, p0_cur + g); }
   if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = OF::meta(a, p0_cur + G + g, ldu); a_cur2 = V::load(a.val, p0_cur + G + g); }
 
+  // first iteration of this CTA that touches a halo tile (tiles are dealt in the order of `tile_order`, halo tiles last)
+  int it_h = 0x7fffffff;
+  if (SHARD && a.wait_seq != 0 && a.tile_order != nullptr) {
+    const int first = a.halo_start > (int)blockIdx.x ? (a.halo_start - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    it_h = first * spt;
+  }
   for (int it = 0; it < niter; ++it) {
+    if (SHARD && it == it_h) {
+      // the peers' previous kernel is complete: their rows of the gathered block are final, and they no longer read the rows this
+      // kernel is about to overwrite
+      if (lane < a.nranks && lane != a.rank) { while (ld_sys_u64(a.kdone + lane) < a.wait_seq) { } }
+      __syncwarp();
+    }
     const int row = r_cur;
     const bool valid = row < n;
     const int r_fut = next_row();

@@ -547,8 +547,22 @@ struct MslOut { int k = 0; double maxres = 0.0; bool converged = false; };
 
 static inline double* rblk(H* h, int slot) { return reinterpret_cast<double*>(blk(h, slot)); }
 
-static int lz_grid_spmm(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0) {
-  const int64_t tr = (int64_t)std::max(1, h->lz_tile_rows / rows_per_step) * rows_per_step;   // as in k_lz_spmm
+// rows per round-robin tile: the configured size (64), halved while the static deal of the tiles leaves the busiest CTA with more than
+// 3 % extra work (few rows per rank in row-sharded runs: 125 000 rows over 296 CTAs are 6.6 tiles of 64 rows each -> 7 for some)
+static int lz_pick_tile(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0) {
+  const int64_t ctas = (int64_t)h->sms * (ctas_per_sm > 0 ? ctas_per_sm : h->lz_ctas_per_sm);
+  int t = h->lz_tile_rows;
+  for (;;) {
+    const int64_t tr = (int64_t)std::max(1, t / rows_per_step) * rows_per_step;
+    const int64_t nt = (n + tr - 1) / tr;
+    const double per = (double)nt / (double)ctas;
+    if (per <= 1.0 || std::ceil(per) / per <= 1.03 || tr <= rows_per_step) return (int)tr;
+    t = (int)tr / 2;
+  }
+}
+
+static int lz_grid_spmm(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0, int tile_rows = 0) {
+  const int64_t tr = (int64_t)std::max(1, (tile_rows > 0 ? tile_rows : h->lz_tile_rows) / rows_per_step) * rows_per_step;   // as in k_lz_spmm
   const int64_t ntiles = (n + tr - 1) / tr;
   return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)h->sms * (ctas_per_sm > 0 ? ctas_per_sm : h->lz_ctas_per_sm)));
 }
@@ -556,8 +570,8 @@ static int lz_grid_spmm(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0)
 // Row-sharded runs: the order in which k_lz_spmm deals its row tiles.  Tiles holding a row with a stored entry in a peer's block (halo
 // gathers over NVLink; for a symmetric pattern these are also the rows the peers read) come LAST, after the interior tiles in their
 // natural order (the L2 "moving front"): in pass 2 a kernel only has to wait for the peers' previous kernel just before these tiles.
-static const int* shard_tile_order(H* h, int rows_per_step) {
-  const int tr = std::max(1, h->lz_tile_rows / rows_per_step) * rows_per_step;
+static const int* shard_tile_order(H* h, int rows_per_step, int tile_rows) {
+  const int tr = std::max(1, tile_rows / rows_per_step) * rows_per_step;
   if (h->tile_order_tr == tr && h->tile_order.p) return h->tile_order.as<int>();
   const int64_t n = h->n;
   const int ntiles = (int)((n + tr - 1) / tr);
@@ -599,11 +613,12 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
         k_lz_spmm<G, NC, MODE, 1024, CPLX><<<grid, 1024, 0, h->stream>>>(a);               \
       }                                                                                    \
     } else {                                                                               \
-      const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0);               \
+      a.tile_rows = lz_pick_tile(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0);                  \
+      const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0, a.tile_rows);  \
       *grid_out = grid;                                                                    \
       if (a.goff != nullptr) {                                                             \
         if constexpr (!CPLX && NC <= 2 && MODE <= LZ_P2_PAIR) {                            \
-          a.tile_order = shard_tile_order(h, 16 * (32 / G));                               \
+          a.tile_order = shard_tile_order(h, 16 * (32 / G), a.tile_rows);                               \
           a.halo_start = h->halo_start;                                                    \
           a.nranks = h->nranks; a.rank = h->rank;                                          \
           a.kdone = reinterpret_cast<const LzMailbox*>((const char*)h->arena + h->arena_mbox_off)->kdone; \

@@ -128,24 +128,29 @@ __device__ __forceinline__ void lz_signal(const LzXchg& x) {
   }
 }
 
-// fixed-order sum of the per-CTA partial rows (L2 reads: the rows were written by other CTAs of the same launch)
+// fixed-order sum of the per-CTA partial rows (L2 reads: the rows were written by other CTAs of the same launch).  The loads of a
+// thread are issued in batches of eight before any of them is consumed: the sum costs a few L2 latencies, not one per row.
 __device__ __forceinline__ void lz_reduce_rows(const double* partial, int nblocks, int pstride, int m, double* so /*[FC_MAXCOLS]*/,
                                                double* tmp /*[blockDim.x]*/) {
   int mp = 32;
   while (mp < m) mp <<= 1;
   const int c = threadIdx.x % mp, part = threadIdx.x / mp, nparts = max(1, (int)blockDim.x / mp);
-  double acc0 = 0.0, acc1 = 0.0;
+  double acc = 0.0;
   if (c < m && part < nparts) {
     const double* base = partial + c;
-    int b = part;
-    for (; b + nparts < nblocks; b += 2 * nparts) {
-      acc0 += __ldcg(base + (int64_t)b * pstride);
-      acc1 += __ldcg(base + (int64_t)(b + nparts) * pstride);
+    for (int b0 = part; b0 < nblocks; b0 += 8 * nparts) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int b = b0 + q * nparts;
+        v[q] = (b < nblocks) ? __ldcg(base + (int64_t)b * pstride) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += v[q];
     }
-    if (b < nblocks) acc0 += __ldcg(base + (int64_t)b * pstride);
   }
   __syncthreads();
-  tmp[threadIdx.x] = acc0 + acc1;
+  tmp[threadIdx.x] = acc;
   __syncthreads();
   if (part == 0 && c < m) {
     double t = tmp[c];

@@ -46,7 +46,7 @@ else:
     Q0 = rng.standard_normal((n, M0)) + 0j; Q0 /= np.linalg.norm(Q0, axis=0)
     fpm = fc.feastinit(); fpm[7] = 24; fpm[2] = 10; fpm[3] = 30
     t = time.time()
-    r = fc.pzifeast_gcsrgv(A, B, Emid, rad, M0, fpm, Q0=Q0, solver_tol=1e-11, solver_maxiter=maxiter, inner_rel=inner_rel)
+    r = fc.pzifeast_gcsrgv(A, B, Emid, rad, M0, fpm, Q0=Q0, solver_maxiter=maxiter, inner_rel=inner_rel)
     dt = time.time() - t
     print("config4 time", dt, "info", r.info, "M", r.M, "inside", len(inside), "loops", r.loop, "epsout", r.epsout)
     if r.M == len(inside): print("eig err", max(min(abs(g - x) for x in inside) for g in r.lambda_))

@@ -9,8 +9,15 @@ Rayleigh-Ritz, residual check, refinement loops until epsout <= 10^-fpm[3]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid 100] [--m0 64]
 
-N > 1 is launched by the driver under torchrun (one rank per GPU): the RHS columns of the filter are sharded over the
-ranks, ONE ncclAllReduce of the n x M0 accumulator per refinement loop (DESIGN.md "Multi-GPU").
+N > 1 is launched by the driver under torchrun (one rank per GPU): every rank owns a block of ROWS of A and of every vector
+(--shard rows, the default: halo rows pushed into the peers' HBM over NVLink by the producing kernels, dot products as one-shot
+peer-memory reductions, Rayleigh-Ritz on local rows; DESIGN.md "Multi-GPU"), or a slice of the RHS columns (--shard columns: ONE
+ncclAllReduce of the n x M0 accumulator per refinement loop).  Every rank checks its result (M, eigenvalues against the analytic
+spectrum, residuals, and the angle between the computed invariant subspace and the analytic eigenvectors); the line's `result`
+carries the worst value over the ranks.
+
+--config 1 | 3 | 4 run the other BASELINE configs at full size on one GPU (dense n = 8192; generalized Hermitian n = 500 000;
+general complex n = 250 000) and print a line of the same shape; they are not the headline and take minutes (config 3: ~10 min).
 
 `--impl reference`: the reference is Julia and cannot run in this image (no `julia`), so this arm times the CPU port of
 the same solve (oracle/feast_port.py) on the host cores: each step is a bounded sample (S lock-step Lanczos steps of both
@@ -54,6 +61,37 @@ def laplacian_3d_eigs(N, count):
     lam1 = 2.0 - 2.0 * np.cos(k * np.pi / (N + 1))
     allv = (lam1[:, None, None] + lam1[None, :, None] + lam1[None, None, :]).ravel()
     return np.sort(allv)[:count]
+
+
+def laplacian_3d_lowest_modes(N, count):
+    """(i, j, k) mode indices of the `count` lowest eigenvalues of the N^3 Dirichlet Laplacian (ties in a fixed order)."""
+    import numpy as np
+    k = np.arange(1, N + 1)
+    lam1 = 2.0 - 2.0 * np.cos(k * np.pi / (N + 1))
+    allv = (lam1[:, None, None] + lam1[None, :, None] + lam1[None, None, :]).ravel()
+    idx = np.argsort(allv, kind="stable")[:count]
+    return np.stack(np.unravel_index(idx, (N, N, N)), axis=1) + 1
+
+
+def analytic_subspace_angle(N, X, row0, nrows, allreduce):
+    """sin of the largest angle between span(X) (this rank's rows [row0, row0 + nrows) of the computed eigenvectors, n x M) and the
+    span of the M lowest analytic eigenvectors (sine products).  allreduce(array) sums a small array over the ranks in place."""
+    import numpy as np
+    M = X.shape[1]
+    modes = laplacian_3d_lowest_modes(N, M)
+    rows = np.arange(row0, row0 + nrows)
+    x, y, z = rows // (N * N), (rows // N) % N, rows % N          # row = x N^2 + y N + z (Kronecker order of laplacian_3d)
+    s = np.sqrt(2.0 / (N + 1)) * np.sin(np.outer(np.arange(1, N + 1), np.arange(1, N + 1)) * np.pi / (N + 1))   # s[mode-1, point]
+    V = np.empty((nrows, M))
+    for c, (i, j, k) in enumerate(modes):
+        V[:, c] = s[i - 1, x] * s[j - 1, y] * s[k - 1, z]
+    Xl = np.ascontiguousarray(X[row0:row0 + nrows])
+    G = V.T @ Xl                                                   # V^T X, summed over the ranks
+    allreduce(G)
+    R = Xl - V @ G                                                 # component of X outside the analytic invariant subspace
+    nr = np.array([np.sum(R * R, axis=0), np.sum(Xl * Xl, axis=0)])
+    allreduce(nr)
+    return float(np.sqrt((nr[0] / np.maximum(nr[1], 1e-300)).max()))
 
 
 def workload(N, M0):
@@ -193,7 +231,7 @@ def run_gpu(args):
     def e2e_step():
         barrier()
         t0 = time.perf_counter()
-        r = eng.solve_interval(Emin, Emax, args.m0, list(fpm), Z, W, Q0=Q0_host, x_real=True, shard=shard, gather_rows=False, **SOLVER_KW)
+        r = eng.solve_interval(Emin, Emax, args.m0, list(fpm), Z, W, Q0=Q0_host, x_real=True, shard=shard, gather_rows=False, reuse_output=True, **SOLVER_KW)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, r
 
@@ -240,6 +278,30 @@ def run_gpu(args):
     except Exception as exc:   # noqa: BLE001
         mx_error = f"{type(exc).__name__}: {exc}"
     opts = opts_fp64
+    # ---- parity, on EVERY rank: M, eigenvalues vs the analytic spectrum, residuals, subspace angle vs the analytic eigenvectors
+    M_loc, info_loc = last[0], last[1]
+    row0, nrows, _ = eng.row_range()
+
+    def allreduce_np(a):
+        if world > 1 and shard == "rows":      # column-sharded ranks hold every row already
+            tt = torch.from_numpy(a).cuda()
+            dist.all_reduce(tt)
+            a[...] = tt.cpu().numpy()
+        return a
+
+    angle = analytic_subspace_angle(args.grid, X, row0, nrows, allreduce_np) if M_loc == C3_M and args.grid >= 12 else float("nan")
+    eig_err_loc = float(np.abs(np.sort(lam) - ev[:M_loc]).max()) if M_loc else float("inf")
+    res_loc = float(res.max()) if M_loc else float("inf")
+    ok_loc = float(info_loc == 0 and M_loc == (C3_M if args.grid >= 12 else 10) and eig_err_loc <= 1e-10 * max(1.0, float(ev[C3_M])) and res_loc < 1e-12
+                   and (not np.isfinite(angle) or angle < 1e-8))
+    worst = [eig_err_loc, res_loc, -ok_loc, float(M_loc), -float(M_loc)]
+    if world > 1:
+        wt = torch.tensor(worst, device="cuda", dtype=torch.float64)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        worst = wt.cpu().tolist()
+    parity = {"all_ranks_ok": bool(-float(worst[2]) == 1.0), "same_M_on_all_ranks": bool(float(worst[3]) == -float(worst[4])),
+              "max_eig_err_vs_analytic_over_ranks": float(worst[0]), "max_residual_over_ranks": float(worst[1]),
+              "subspace_angle_vs_analytic": angle, "ranks": world}
     if world > 1:
         t = torch.tensor([ms_step, e2e_step_ms, mx_step], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -299,9 +361,12 @@ def run_gpu(args):
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(args),
            "result": {"M": M, "info": info, "epsout": eps, "loops": loop, "max_residual": float(res.max()) if M else None,
-                      "max_eig_err_vs_analytic": eig_err, "lanczos_steps_per_solve": st["lz_steps_p1"] / args.steps},
+                      "max_eig_err_vs_analytic": eig_err, "subspace_angle_vs_analytic": parity["subspace_angle_vs_analytic"],
+                      "lanczos_steps_per_solve": st["lz_steps_p1"] / args.steps, "parity": parity},
            "e2e": {"value": r.M / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
-                   "h2d_bytes_per_step": int(Q0.nbytes), "d2h_bytes_per_step": int(r.q.nbytes + r.lambda_.nbytes + r.res.nbytes)},
+                   "h2d_bytes_per_step": int(Q0.nbytes) if shard == "rows" or world == 1 else int(Q0.nbytes) * world,
+                   "d2h_bytes_per_step": (int(r.q.nbytes) if shard == "rows" or world == 1 else int(r.q.nbytes) * world) + int(r.lambda_.nbytes + r.res.nbytes) * world,
+                   "note": "whole-job bytes: row-sharded ranks copy their own rows of Q0 / X only, column-sharded ranks the full blocks"},
            "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
            "mixed_precision": None if args.no_mixed else ({"error": mx_error} if mx_error else {
                "what": "same solve with opts.mixed (fpm[42] 'single-precision solver'): FP32 Lanczos vectors and matrix entries, FP64 "

@@ -409,6 +409,7 @@ class Engine:
         """One C-ABI call with HOST buffers in and out (the end-to-end path).  The returned stats describe this solve.
         shard="rows" (multi-rank runs): row-sharded mode; gather_rows=False leaves only this rank's rows of q filled."""
         gather_rows = kw.pop("gather_rows", True)
+        reuse_output = kw.pop("reuse_output", False)    # True: q is a view of a buffer the NEXT solve overwrites (no 8 n M0-byte allocation per call)
         if self.distributed:
             self.set_row_sharding(kw.get("shard") == "rows")
         self.reset_stats()
@@ -425,7 +426,13 @@ class Engine:
             q = np.asfortranarray(Q0, dtype=np.float64) if q0_real else _colmajor_z(Q0)
         lam = np.zeros(M0, dtype=np.float64)
         res = np.zeros(M0, dtype=np.float64)
-        X = np.zeros((self.n, M0), dtype=np.float64 if x_real else np.complex128, order="F")
+        xkey = (self.n, int(M0), bool(x_real))
+        if reuse_output and getattr(self, "_xbuf_key", None) == xkey:
+            X = self._xbuf
+        else:
+            X = np.zeros((self.n, M0), dtype=np.float64 if x_real else np.complex128, order="F")
+            if reuse_output:
+                self._xbuf, self._xbuf_key = X, xkey
         M = np.zeros(1, dtype=np.int64)
         info = np.zeros(1, dtype=np.int64)
         loop = np.zeros(1, dtype=np.int64)
@@ -437,7 +444,7 @@ class Engine:
         for i in range(64):
             fpm[i] = int(a[i])
         m = int(M[0])
-        Xm = X[:, :m].copy()
+        Xm = X[:, :m] if reuse_output else X[:, :m].copy()
         if getattr(self, "row_sharded", False) and gather_rows and m > 0:
             Xm = self._gather_rows(Xm)
         return FeastResult(lam[:m].copy(), Xm, m, res[:m].copy(), int(info[0]), float(eps[0]), int(loop[0]), self.stats())

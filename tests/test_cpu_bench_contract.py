@@ -26,6 +26,12 @@ class StubEngine:
     def init_distributed(self):
         pass
 
+    def set_row_sharding(self, on=True):
+        pass
+
+    def row_range(self):
+        return 0, self.n, self.n
+
     def make_opts(self, **kw):
         return types.SimpleNamespace(**kw)
 
@@ -91,6 +97,7 @@ def test_gpu_arm_json_contract(monkeypatch, capsys):
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "strong"
     assert d["ms_per_step"] == pytest.approx(2360.0) and d["value"] == pytest.approx(35 / 2.36)
     assert d["gpu_launches"] > 0 and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert set(d["result"]["parity"]) >= {"all_ranks_ok", "same_M_on_all_ranks", "subspace_angle_vs_analytic", "ranks"}
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["frac"] == pytest.approx(r["achieved"] / r["peak"])
     assert r["traffic"] is None or r["traffic"] > 0

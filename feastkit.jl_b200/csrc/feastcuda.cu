@@ -47,7 +47,7 @@ static zd* blk(H* h, int slot) { return h->blk[slot].as<zd>(); }
 static void arena_allocate(H* h, int ld);
 static void fill_xchg(H* h, LzXchg& x);
 static LzPush make_push(H* h, int64_t rowbytes);
-static void halo_push(H* h, double* blockp, int64_t ld, int nelem, const LzTail& tail);
+static void halo_push(H* h, double* blockp, int64_t ld, int nelem, const LzTail& tail, const double* partial = nullptr, int m = 0, const int* done = nullptr);
 static void xbarrier(H* h);
 static void allreduce_small(H* h, double* dev, size_t count);
 static void sharded_apply(H* h, int m, const cx<double>* X, cx<double>* Y, const double* theta, std::vector<double>* norms2);
@@ -855,9 +855,6 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   };
   const int bar_kind = sharded ? LZ_TAIL_BARRIER : LZ_TAIL_NONE;
   xbarrier(h);   // row-sharded: no peer is still reading the blocks this sweep is about to overwrite
-  LzPush push_ld;   // the push list resolved for the compact row stride (fused into k_lz_update)
-  memset(&push_ld, 0, sizeof(push_ld));
-  if (sharded) push_ld = make_push(h, ld * (int64_t)sizeof(double));
 
   // ---- real work blocks (each aliases a complex slot; n x ld doubles) -------------------------------------------
   double* RQ = rblk(h, BS_KS);
@@ -996,8 +993,15 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
                                                      S.done_k, mk_tail(LZ_TAIL_BETA, j));
       else
         k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
-                                                   S.done_k, mk_tail(LZ_TAIL_BETA, j), push_ld);
+                                                   S.done_k, sharded ? LzTail{} : mk_tail(LZ_TAIL_BETA, j), LzPush{});
       check_launch(h);
+      if (sharded && !mixed) {
+        // the new vector's boundary rows go to the peers' ghost rows; the last CTA of this small launch sums the update kernel's partial
+        // rows, exchanges them with the peers and advances the step's scalars
+        LzTail tb = mk_tail(LZ_TAIL_BETA, j);
+        tb.ext_rows = egrid;
+        halo_push(h, cur(j + 1), ld, P, tb, part, nc, S.done_k);
+      }
       sample_end(h, ev);
       if (matfree) {
         k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, egrid, FC_MAXCOLS, nc);
@@ -2024,13 +2028,13 @@ static LzPush make_push(H* h, int64_t rowbytes) {
 }
 
 // boundary rows of a block -> the peers' ghost rows; the tail runs when the last CTA is done (signal / barrier / none)
-static void halo_push(H* h, double* blockp, int64_t ld, int nelem, const LzTail& tail) {
+static void halo_push(H* h, double* blockp, int64_t ld, int nelem, const LzTail& tail, const double* partial, int m, const int* done) {
   if (!h->row_sharded) return;
   LzPush ps = make_push(h, ld * (int64_t)sizeof(double));
   if (ps.npush == 0 && tail.kind == LZ_TAIL_NONE) return;
   const int warps = std::max(1, ps.npush);
-  const int grid = std::max(1, std::min((warps + 7) / 8, h->sms * 2));
-  k_halo_push<<<grid, 256, 0, h->stream>>>(ps, blockp, ld, nelem, tail);
+  const int grid = std::max(1, std::min((warps + 31) / 32, h->sms));
+  k_halo_push<<<grid, 1024, 0, h->stream>>>(ps, blockp, ld, nelem, tail, partial, FC_MAXCOLS, m, done);
   check_launch(h);
 }
 

@@ -245,6 +245,7 @@ struct LzTail {
   int j;             // Lanczos step
   int* ticket;       // device counters, zero between launches: [0] groups finished, [1 + g] CTAs of group g finished
   double* grows;     // [ngroups][FC_MAXCOLS] group sums (first level of the reduction)
+  int ext_rows;      // > 0: the partial rows come from the PREVIOUS kernel (ext_rows of them); the last CTA of this launch sums them all
   LzScalars s;
   LzXchg x;
 };
@@ -270,7 +271,7 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (t.kind != LZ_TAIL_BARRIER && t.kind != LZ_TAIL_SIGNAL) {
+  if (t.kind != LZ_TAIL_BARRIER && t.kind != LZ_TAIL_SIGNAL && t.ext_rows == 0) {
     lz_reduce_rows(partial + (int64_t)grp * LZ_TAIL_GROUP * pstride, gsize, pstride, m, t_so, t_tmp);
     if ((int)threadIdx.x < m) t.grows[(int64_t)grp * FC_MAXCOLS + threadIdx.x] = t_so[threadIdx.x];
     __threadfence();
@@ -289,7 +290,8 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   } else if (t.kind == LZ_TAIL_SIGNAL) {
     lz_signal(t.x);
   } else {
-    lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
+    if (t.ext_rows > 0) lz_reduce_rows(partial, t.ext_rows, pstride, m, t_so, t_tmp);
+    else lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
     lz_exchange(t.x, t_so, m);
     if (t.kind == LZ_TAIL_INIT) lz_scalars_init(t.s, t_so, m);
     else if (t.kind == LZ_TAIL_ALPHA) lz_scalars_alpha(t.s, t.j, t_so, m);
@@ -842,7 +844,9 @@ __global__ void __launch_bounds__(256) k_halo_resolve(int npush, const int* __re
 }
 
 // block rows -> the peers' ghost rows: one warp per push entry, `nelem` 16-byte elements per row; then the tail (signal / barrier)
-__global__ void __launch_bounds__(256) k_halo_push(LzPush ps, double* blockp, int64_t ld, int nelem, LzTail tail) {
+__global__ void __launch_bounds__(1024) k_halo_push(LzPush ps, double* blockp, int64_t ld, int nelem, LzTail tail, const double* partial,
+                                                    int pstride, int m, const int* done) {
+  if (done != nullptr && *done != 0) return;
   const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5), lane = threadIdx.x & 31;
   for (int q = warp; q < ps.npush; q += nwarps) {
     const double* src = blockp + (int64_t)ps.row[q] * ld;
@@ -850,8 +854,8 @@ __global__ void __launch_bounds__(256) k_halo_push(LzPush ps, double* blockp, in
     for (int e = lane; e < nelem; e += 32) stg2(dst + 2 * e, ldg2(src + 2 * e));
   }
   __threadfence_system();
-  __shared__ double tail_scratch[FC_MAXCOLS + 256];
-  lz_tail(tail, nullptr, 0, 0, tail_scratch);
+  __shared__ double tail_scratch[FC_MAXCOLS + 1024];
+  lz_tail(tail, partial, pstride, m, tail_scratch);
 }
 
 // compact Lanczos block -> engine block (real problems: zero imaginary part)

@@ -178,11 +178,6 @@ struct feastcuda_handle_s {
   int tile_order_tr = 0, halo_start = 0;
   feastcuda::DBuf lz_ticket, lz_grows;         // counters and group sums of the two-level tail reductions (kernels_lanczos.cuh: lz_tail)
   int64_t nnz_loc = 0;                         // stored entries of the local rows
-  int64_t nghost = 0, ghost_max = 0;           // ghost rows of this rank / the largest count over the ranks (slot sizing)
-  std::vector<int> push_row, push_peer, push_dst;   // boundary rows: (local row, peer, row index in the peer's block), sorted by row
-  std::vector<char> halo_row;                  // rows that read a ghost row or are pushed to a peer
-  feastcuda::DBuf d_push;                      // the push list on the device: rows | peers | destination rows
-  feastcuda::DBuf push_idx;                    // [n] first entry of a row in the push list, -1 for interior rows
   unsigned long long xseq = 0;                 // sequence number of the last cross-rank exchange
 
   feastcuda_stats stats;

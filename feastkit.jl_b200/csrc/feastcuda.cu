@@ -46,8 +46,7 @@ static zd* blk(H* h, int slot) { return h->blk[slot].as<zd>(); }
 
 static void arena_allocate(H* h, int ld);
 static void fill_xchg(H* h, LzXchg& x);
-static LzPush make_push(H* h, int64_t rowbytes);
-static void halo_push(H* h, double* blockp, int64_t ld, int nelem, const LzTail& tail, const double* partial = nullptr, int m = 0, const int* done = nullptr);
+static const int* resolve_goff(H* h, int64_t rowbytes);
 static void xbarrier(H* h);
 static void allreduce_small(H* h, double* dev, size_t count);
 static void sharded_apply(H* h, int m, const cx<double>* X, cx<double>* Y, const double* theta, std::vector<double>* norms2);
@@ -159,76 +158,29 @@ static void row_block(int64_t n, int nranks, int rank, int64_t* r0, int64_t* cnt
   *cnt = base + (rank < rem ? 1 : 0);
 }
 
-// Row-sharded upload: this rank's rows only.  Column indices become LOCAL row indices of the block vectors: own rows 0 .. n-1, then
-// the GHOST rows n .. n + nghost - 1, one per distinct remote column this rank's rows reference (sorted by global column).  Ghost rows
-// are filled by their owners: every kernel that produces a gathered block also stores its boundary rows into the peers' ghost rows
-// (NVLink stores are posted -- nobody waits for them; the gathers themselves only ever read local HBM).  The push list is built from
-// the same rule applied to every peer's rows (each rank holds the whole host matrix, like the reference's MPI ranks do).
+// row-sharded upload: this rank's rows only; a column index becomes (owner << LZ_OWNER_SHIFT) | row local to the owner
 static void upload_csr_rows(H* h, const HostCsr& src, DevCsr& dst) {
   FC_REQUIRE(!src.cplx, "row sharding: real symmetric operators only");
   const int64_t n = src.n;
-  const int P = h->nranks, self = h->rank;
+  const int P = h->nranks;
+  int64_t r0 = 0, cnt = 0;
+  row_block(n, P, h->rank, &r0, &cnt);
   const int64_t base = n / P, rem = n % P, bound = rem * (base + 1);
-  auto owner_of = [&](int64_t c) -> int { return (int)(c < bound ? c / (base + 1) : rem + (base > 0 ? (c - bound) / base : 0)); };
-  std::vector<int64_t> r0(P), cnt(P);
-  for (int p = 0; p < P; ++p) row_block(n, P, p, &r0[p], &cnt[p]);
-  // ghost list of every rank: sorted distinct remote columns referenced by its rows
-  std::vector<std::vector<int>> ghosts(P);
-  for (int p = 0; p < P; ++p) {
-    std::vector<int>& gl = ghosts[p];
-    for (int64_t r = r0[p]; r < r0[p] + cnt[p]; ++r)
-      for (int q = src.ptr[r]; q < src.ptr[r + 1]; ++q) {
-        const int c = src.col[q];
-        if (c < r0[p] || c >= r0[p] + cnt[p]) gl.push_back(c);
-      }
-    std::sort(gl.begin(), gl.end());
-    gl.erase(std::unique(gl.begin(), gl.end()), gl.end());
+  FC_REQUIRE(base + 1 < ((int64_t)1 << LZ_OWNER_SHIFT), "row sharding: too many rows per rank for the column encoding");
+  const int p0 = src.ptr[r0], p1 = src.ptr[r0 + cnt];
+  std::vector<int> ptr(cnt + 1), col((size_t)std::max(1, p1 - p0));
+  for (int64_t i = 0; i <= cnt; ++i) ptr[i] = src.ptr[r0 + i] - p0;
+  for (int p = p0; p < p1; ++p) {
+    const int64_t c = src.col[p];
+    int64_t owner, first;
+    if (c < bound) { owner = c / (base + 1); first = owner * (base + 1); }
+    else { owner = rem + (base > 0 ? (c - bound) / base : 0); first = bound + (owner - rem) * base; }
+    col[p - p0] = (int)(((unsigned)owner << LZ_OWNER_SHIFT) | (unsigned)(c - first));
   }
-  int64_t gmax = 0;
-  for (int p = 0; p < P; ++p) gmax = std::max<int64_t>(gmax, (int64_t)ghosts[p].size());
-  h->nghost = (int64_t)ghosts[self].size();
-  h->ghost_max = gmax;
-  // local CSR with local / ghost column indices
-  const int64_t nl = cnt[self];
-  const int p0 = src.ptr[r0[self]], p1 = src.ptr[r0[self] + nl];
-  std::vector<int> ptr(nl + 1), col((size_t)std::max(1, p1 - p0));
-  for (int64_t i = 0; i <= nl; ++i) ptr[i] = src.ptr[r0[self] + i] - p0;
-  const std::vector<int>& mine = ghosts[self];
-  for (int q = p0; q < p1; ++q) {
-    const int c = src.col[q];
-    if (c >= r0[self] && c < r0[self] + nl) col[q - p0] = (int)(c - r0[self]);
-    else col[q - p0] = (int)(nl + (std::lower_bound(mine.begin(), mine.end(), c) - mine.begin()));
-  }
-  // push list: my rows that appear in a peer's ghost list -> (peer, row index in the peer's block)
-  struct Push { int row, peer, dstrow; };
-  std::vector<Push> pushes;
-  for (int p = 0; p < P; ++p) {
-    if (p == self) continue;
-    const std::vector<int>& gl = ghosts[p];
-    auto lo = std::lower_bound(gl.begin(), gl.end(), (int)r0[self]);
-    auto hi = std::lower_bound(gl.begin(), gl.end(), (int)(r0[self] + nl));
-    for (auto it = lo; it != hi; ++it) pushes.push_back({(int)(*it - r0[self]), p, (int)(cnt[p] + (it - gl.begin()))});
-  }
-  std::sort(pushes.begin(), pushes.end(), [](const Push& a, const Push& b) { return a.row != b.row ? a.row < b.row : a.peer < b.peer; });
-  h->push_row.clear(); h->push_peer.clear(); h->push_dst.clear();
-  std::vector<int> pidx(nl, -1);       // first push entry of a row (entries of a row are consecutive), -1: interior row
-  for (size_t i = 0; i < pushes.size(); ++i) {
-    h->push_row.push_back(pushes[i].row); h->push_peer.push_back(pushes[i].peer); h->push_dst.push_back(pushes[i].dstrow);
-    if (pidx[pushes[i].row] < 0) pidx[pushes[i].row] = (int)i;
-  }
-  h->push_idx.ensure((size_t)std::max<int64_t>(nl, 1) * sizeof(int));
-  FC_CUDA(cudaMemcpyAsync(h->push_idx.p, pidx.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  const size_t np = h->push_row.size();
-  h->d_push.ensure(std::max<size_t>(np, 1) * 3 * sizeof(int));     // rows | peers | destination rows
-  if (np) {
-    FC_CUDA(cudaMemcpyAsync(h->d_push.as<int>(), h->push_row.data(), np * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    FC_CUDA(cudaMemcpyAsync(h->d_push.as<int>() + np, h->push_peer.data(), np * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    FC_CUDA(cudaMemcpyAsync(h->d_push.as<int>() + 2 * np, h->push_dst.data(), np * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  }
-  dst.ptr.ensure((nl + 1) * sizeof(int));
+  dst.ptr.ensure((cnt + 1) * sizeof(int));
   dst.col.ensure(col.size() * sizeof(int));
   dst.val.ensure((size_t)std::max(1, p1 - p0) * sizeof(double));
-  FC_CUDA(cudaMemcpyAsync(dst.ptr.p, ptr.data(), (nl + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  FC_CUDA(cudaMemcpyAsync(dst.ptr.p, ptr.data(), (cnt + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   FC_CUDA(cudaMemcpyAsync(dst.col.p, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (p1 > p0) FC_CUDA(cudaMemcpyAsync(dst.val.p, src.val.data() + p0, (size_t)(p1 - p0) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   sync(h);
@@ -236,13 +188,6 @@ static void upload_csr_rows(H* h, const HostCsr& src, DevCsr& dst) {
   h->nnz_loc = p1 - p0;
   h->goff_rowbytes2[0] = h->goff_rowbytes2[1] = 0;
   h->tile_order_tr = 0;
-  // rows that read a ghost row or are pushed to a peer: the tiles holding them are dealt last (shard_tile_order)
-  h->halo_row.assign(nl, 0);
-  for (int64_t i = 0; i < nl; ++i) {
-    bool hr = pidx[i] >= 0;
-    for (int q = ptr[i]; q < ptr[i + 1] && !hr; ++q) hr = col[q] >= nl;
-    h->halo_row[i] = hr ? 1 : 0;
-  }
 }
 
 static void finalize_sparse(H* h) {
@@ -623,24 +568,41 @@ static int lz_grid_spmm(H* h, int64_t n, int rows_per_step, int ctas_per_sm = 0,
 }
 
 // Row-sharded runs: the order in which k_lz_spmm deals its row tiles.  Tiles holding a row with a stored entry in a peer's block (halo
-// gathers over NVLink; for a symmetric pattern these are also the rows the peers read) come LAST, after the interior tiles in their
-// natural order (the L2 "moving front"): in pass 2 a kernel only has to wait for the peers' previous kernel just before these tiles.
+// gathers over NVLink; for a symmetric pattern these are also the rows the peers read) come in the second half of the sweep.
 static const int* shard_tile_order(H* h, int rows_per_step, int tile_rows) {
   const int tr = std::max(1, tile_rows / rows_per_step) * rows_per_step;
   if (h->tile_order_tr == tr && h->tile_order.p) return h->tile_order.as<int>();
   const int64_t n = h->n;
   const int ntiles = (int)((n + tr - 1) / tr);
   std::vector<int> inner, halo, order;
+  const HostCsr& A = h->hA;
+  const unsigned self = (unsigned)h->rank;
+  // owner of a global column: the block rule of row_block
+  const int64_t ng = h->n_glob, base = ng / h->nranks, rem = ng % h->nranks, bound = rem * (base + 1);
+  auto owner_of = [&](int64_t c) -> unsigned { return (unsigned)(c < bound ? c / (base + 1) : rem + (base > 0 ? (c - bound) / base : 0)); };
   for (int t = 0; t < ntiles; ++t) {
     bool remote = false;
-    const int64_t r0 = (int64_t)t * tr, r1 = std::min<int64_t>(n, r0 + tr);
-    for (int64_t r = r0; r < r1 && !remote; ++r) remote = h->halo_row[r] != 0;
+    const int64_t r0 = h->row0 + (int64_t)t * tr, r1 = std::min<int64_t>(h->row0 + n, r0 + tr);
+    for (int64_t r = r0; r < r1 && !remote; ++r)
+      for (int p = A.ptr[r]; p < A.ptr[r + 1]; ++p)
+        if (owner_of(A.col[p]) != self) { remote = true; break; }
     (remote ? halo : inner).push_back(t);
   }
+  // interior tiles in their natural order; the halo tiles are spread evenly over the second half of the sweep: late enough that the
+  // peers' completion signals have long arrived when the first of them is reached (lazy wait of pass 2), and interleaved with interior
+  // tiles so that the NVLink latency of their gathers hides behind local rows instead of stalling every CTA at the end
   order.reserve(ntiles);
-  order.insert(order.end(), inner.begin(), inner.end());
-  order.insert(order.end(), halo.begin(), halo.end());
-  h->halo_start = (int)inner.size();
+  const size_t first_half = std::min(inner.size(), (size_t)std::max(0, ntiles / 2));
+  order.insert(order.end(), inner.begin(), inner.begin() + first_half);
+  h->halo_start = (int)order.size();
+  {
+    const size_t rest = (size_t)ntiles - order.size();
+    size_t ih = 0, ii = first_half;
+    for (size_t v = 0; v < rest; ++v) {
+      const bool want_halo = ih < halo.size() && ((double)(ih + 1) * rest <= (double)(v + 1) * halo.size() || ii >= inner.size());
+      order.push_back(want_halo ? halo[ih++] : inner[ii++]);
+    }
+  }
   h->tile_order.ensure((size_t)std::max(1, ntiles) * sizeof(int));
   FC_CUDA(cudaMemcpyAsync(h->tile_order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   sync(h);
@@ -654,7 +616,7 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
   // G lanes per row, NC column-pair chunks per lane
 #define FC_LZ(G, NC)                                                                       \
   do {                                                                                     \
-    if (NC == 1 && h->lz_threads >= 1024 && !a.sharded) {                                                \
+    if (NC == 1 && h->lz_threads >= 1024 && a.goff == nullptr) {                                                \
       if constexpr (NC == 1) {                                                             \
         const int grid = lz_grid_spmm(h, a.n, 32 * (32 / G));                              \
         *grid_out = grid;                                                                  \
@@ -664,7 +626,7 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
       a.tile_rows = lz_pick_tile(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0);                  \
       const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0, a.tile_rows);  \
       *grid_out = grid;                                                                    \
-      if (a.sharded) {                                                                     \
+      if (a.goff != nullptr) {                                                             \
         if constexpr (!CPLX && NC <= 2 && MODE <= LZ_P2_PAIR) {                            \
           a.tile_order = shard_tile_order(h, 16 * (32 / G), a.tile_rows);                               \
           a.halo_start = h->halo_start;                                                    \
@@ -803,7 +765,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   // mixed precision (FP32 Lanczos vectors, real problems): 4-column elements, so every compact block is padded to a multiple of 4
   mixed = mixed && !CPLX && !matfree && !h->row_sharded && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
   const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : (mixed ? ((nc + 3) & ~3) : ((nc + 1) & ~1));
-  FC_REQUIRE((double)(n + (h->row_sharded ? h->nghost : 0)) * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
+  FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   kmax = std::max(1, std::min(kmax, 16384));
   check_every = std::max(1, check_every);
   const int P = CPLX ? nc : (nc + 1) / 2;
@@ -877,7 +839,6 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   if (!have_ritz) {
     k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RB, part, FC_MAXCOLS, mk_tail(LZ_TAIL_INIT, 0));
     check_launch(h);
-    if (sharded) halo_push(h, RB, ld, P, mk_tail(LZ_TAIL_BARRIER, 0));   // step 0 gathers the peers' boundary rows of the start block
     if (matfree) {
       k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, egrid, FC_MAXCOLS, nc);
       check_launch(h);
@@ -892,9 +853,8 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     }
     FC_CUDA(cudaMemcpyAsync(d_theta, theta, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     FC_CUDA(cudaMemcpyAsync(d_rho, rho.data(), (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS, LzTail{});
+    k_lz_real_part<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ldz, ld, basis, RQ, nullptr, FC_MAXCOLS, mk_tail(bar_kind, 0));
     check_launch(h);
-    if (sharded) halo_push(h, RQ, ld, P, mk_tail(LZ_TAIL_BARRIER, 0));
     LzArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.m = nc; a.ld = ld;
@@ -902,7 +862,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.U = RQ; a.prev = RQ; a.out = RB; a.Q = QA; a.s_coef = d_rho; a.s_theta = d_theta;
     a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
     a.tail = mk_tail(LZ_TAIL_INIT, 0);
-    a.sharded = sharded ? 1 : 0;
+    if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
     int g = 0;
     const int ev = sample_begin(h, FEASTCUDA_KERN_LZ_RES);
     if (matfree) {
@@ -918,7 +878,6 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       k_lz_scal_init<<<1, 1024, 0, h->stream>>>(S, part, g, FC_MAXCOLS, nc);
       check_launch(h);
     }
-    if (sharded) halo_push(h, RB, ld, P, mk_tail(LZ_TAIL_BARRIER, 0));
     sync(h);  // theta / rho are host buffers
   }
 
@@ -979,7 +938,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
         a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
         a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
         a.tail = mk_tail(LZ_TAIL_ALPHA, j);
-        a.sharded = sharded ? 1 : 0;
+        if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
         lz_launch<LZ_P1, CPLX>(h, a, &g);
       }
       sample_end(h, ev);
@@ -993,15 +952,8 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
                                                      S.done_k, mk_tail(LZ_TAIL_BETA, j));
       else
         k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
-                                                   S.done_k, sharded ? LzTail{} : mk_tail(LZ_TAIL_BETA, j), LzPush{});
+                                                   S.done_k, mk_tail(LZ_TAIL_BETA, j));
       check_launch(h);
-      if (sharded && !mixed) {
-        // the new vector's boundary rows go to the peers' ghost rows; the last CTA of this small launch sums the update kernel's partial
-        // rows, exchanges them with the peers and advances the step's scalars
-        LzTail tb = mk_tail(LZ_TAIL_BETA, j);
-        tb.ext_rows = egrid;
-        halo_push(h, cur(j + 1), ld, P, tb, part, nc, S.done_k);
-      }
       sample_end(h, ev);
       if (matfree) {
         k_lz_scal2<<<1, 1024, 0, h->stream>>>(S, j, part, egrid, FC_MAXCOLS, nc);
@@ -1081,14 +1033,13 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       if (sharded) {
         // no rank waits at the end of a pass-2 kernel: it signals its completion to the peers, and the NEXT kernel waits for the peers'
         // signals only before its halo tiles (which come last)
-        a.sharded = 1;
-        a.wait_seq = (h->nranks > 1 && j > 0) ? h->xseq : 0;     // the signal that followed the previous pass-2 kernel's pushes
+        a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
+        a.wait_seq = (h->nranks > 1 && j > 0) ? h->xseq : 0;     // the signal of the previous pass-2 kernel
+        a.tail = mk_tail(LZ_TAIL_SIGNAL, j);
       }
       if (q_mode == 0) lz_launch<LZ_P2, CPLX>(h, a, &g);
       else if (q_mode == 1) lz_launch<LZ_P2_SKIP, CPLX>(h, a, &g);
       else lz_launch<LZ_P2_PAIR, CPLX>(h, a, &g);
-      // row-sharded: the new vector's boundary rows go to the peers' ghost rows; the last CTA of the push signals "step j complete"
-      if (sharded) halo_push(h, cur(j + 1), ld, P, mk_tail(LZ_TAIL_SIGNAL, j));
     }
     sample_end(h, ev);
   }
@@ -1353,7 +1304,7 @@ static void msl_filter_gen(H* h, int basis_slot, int c0, int nc, bool have_ritz,
       k_lz_scal1<<<1, 1024, 0, h->stream>>>(S, j, part, gg, FC_MAXCOLS, nc);
       check_launch(h);
     }
-    k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, s_cur, s_oth, part, FC_MAXCOLS, done, LzTail{}, LzPush{});
+    k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, s_cur, s_oth, part, FC_MAXCOLS, done, LzTail{});
     check_launch(h);
     double* unew = cheb_solve(s_oth, fa, fb, done);
     if (pass1) {
@@ -1947,7 +1898,7 @@ static void arena_allocate(H* h, int ld) {
   h->small2.ensure((size_t)4 * FC_MAXCOLS * sizeof(zd) + 64);
   arena_release(h);
   for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
-  const size_t slot = (((size_t)(h->nloc_max + h->ghost_max) * (size_t)ld * sizeof(zd)) + 255) & ~(size_t)255;   // own rows + ghost rows
+  const size_t slot = (((size_t)h->nloc_max * (size_t)ld * sizeof(zd)) + 255) & ~(size_t)255;
   h->arena_slot_bytes = slot;
   h->arena_mbox_off = (size_t)BS_COUNT * slot;
   h->arena_bytes = h->arena_mbox_off + ((sizeof(LzMailbox) + 255) & ~(size_t)255);
@@ -1997,45 +1948,24 @@ static void xbarrier(H* h) {
   check_launch(h);
 }
 
-// push list resolved for blocks whose rows are `rowbytes` apart (two strides are in use: the compact Lanczos blocks and the engine's
-// complex blocks viewed as interleaved real columns)
-static LzPush make_push(H* h, int64_t rowbytes) {
-  LzPush ps;
-  memset(&ps, 0, sizeof(ps));
-  const size_t np = h->push_row.size();
-  ps.npush = (int)np;
-  ps.row = h->d_push.as<int>();
-  ps.idx = h->push_idx.as<int>();
-  int slot = (h->goff_rowbytes2[0] == rowbytes) ? 0 : ((h->goff_rowbytes2[1] == rowbytes) ? 1 : -1);
-  if (slot < 0) {
-    FC_REQUIRE(rowbytes % 16 == 0, "row sharding: rows must be multiples of 16 bytes");
-    slot = h->goff_next;
-    h->goff_next ^= 1;
-    h->goff.ensure((size_t)2 * std::max<size_t>(np, 1) * sizeof(int));
-    int* out = h->goff.as<int>() + (size_t)slot * std::max<size_t>(np, 1);
-    LzArenas ar;
-    memset(&ar, 0, sizeof(ar));
-    for (int p = 0; p < h->nranks; ++p) ar.base[p] = (const char*)h->peer_arena[p];
-    if (np) {
-      k_halo_resolve<<<std::max(1, h->sms), 256, 0, h->stream>>>((int)np, h->d_push.as<int>(), h->d_push.as<int>() + np, h->d_push.as<int>() + 2 * np,
-                                                                 (long long)rowbytes, h->rank, ar, out);
-      check_launch(h);
-    }
-    h->goff_rowbytes2[slot] = rowbytes;
-  }
-  ps.off = h->goff.as<int>() + (size_t)slot * std::max<size_t>(np, 1);
-  return ps;
-}
-
-// boundary rows of a block -> the peers' ghost rows; the tail runs when the last CTA is done (signal / barrier / none)
-static void halo_push(H* h, double* blockp, int64_t ld, int nelem, const LzTail& tail, const double* partial, int m, const int* done) {
-  if (!h->row_sharded) return;
-  LzPush ps = make_push(h, ld * (int64_t)sizeof(double));
-  if (ps.npush == 0 && tail.kind == LZ_TAIL_NONE) return;
-  const int warps = std::max(1, ps.npush);
-  const int grid = std::max(1, std::min((warps + 31) / 32, h->sms));
-  k_halo_push<<<grid, 1024, 0, h->stream>>>(ps, blockp, ld, nelem, tail, partial, FC_MAXCOLS, m, done);
+// gather offsets of A's local rows for blocks whose rows are `rowbytes` apart (two strides are in use: the compact Lanczos blocks
+// and the engine's complex blocks viewed as interleaved real columns)
+static const int* resolve_goff(H* h, int64_t rowbytes) {
+  const int64_t nnz = h->nnz_loc;
+  const int slot = (h->goff_rowbytes2[0] == rowbytes) ? 0 : ((h->goff_rowbytes2[1] == rowbytes) ? 1 : -1);
+  if (slot >= 0) return h->goff.as<int>() + (size_t)slot * (size_t)std::max<int64_t>(nnz, 1);
+  FC_REQUIRE(rowbytes % 16 == 0, "row sharding: rows must be multiples of 16 bytes");
+  const int use = h->goff_next;
+  h->goff_next ^= 1;
+  h->goff.ensure((size_t)2 * (size_t)std::max<int64_t>(nnz, 1) * sizeof(int));
+  int* out = h->goff.as<int>() + (size_t)use * (size_t)std::max<int64_t>(nnz, 1);
+  LzArenas ar;
+  memset(&ar, 0, sizeof(ar));
+  for (int p = 0; p < h->nranks; ++p) ar.base[p] = (const char*)h->peer_arena[p];
+  k_lz_resolve<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(nnz, h->dA.col.as<int>(), (long long)rowbytes, h->rank, ar, out);
   check_launch(h);
+  h->goff_rowbytes2[use] = rowbytes;
+  return out;
 }
 
 // =====================================================================================================
@@ -2124,9 +2054,8 @@ static void apply_op(H* h, int which, int m, const zd* X, zd* Y) {
 // viewed as 2m interleaved REAL columns (A is real), by the Lanczos gather kernel -- halo rows come from the peers' HBM
 static void sharded_apply(H* h, int m, const zd* X, zd* Y, const double* theta, std::vector<double>* norms2) {
   FC_REQUIRE(h->kind == OP_SPARSE && !h->dev_complex && !h->has_b, "row sharding: standard real symmetric sparse problems only");
+  xbarrier(h);   // the peers have written the rows this launch gathers
   const int64_t ldr = 2 * (int64_t)h->ws_ld;
-  halo_push(h, reinterpret_cast<double*>(const_cast<zd*>(X)), ldr, m, LzTail{});   // my boundary rows of X -> the peers' ghost rows
-  xbarrier(h);   // ... and theirs have arrived here
   double* part = h->partial_r.as<double>();
   double* d_theta = reinterpret_cast<double*>(h->small2.as<zd>() + 8);
   if (norms2) norms2->assign(m, 0.0);
@@ -2136,7 +2065,7 @@ static void sharded_apply(H* h, int m, const zd* X, zd* Y, const double* theta, 
     memset(&a, 0, sizeof(a));
     a.n = h->n; a.m = 2 * mc; a.ld = ldr;
     a.ptr = h->dA.ptr.as<int>(); a.col = h->dA.col.as<int>(); a.val = h->dA.val.p;
-    a.sharded = 1;
+    a.goff = resolve_goff(h, ldr * (int64_t)sizeof(double));
     a.U = reinterpret_cast<const double*>(X + c0); a.prev = a.U;
     a.out = reinterpret_cast<double*>(Y + c0);
     a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows;
@@ -2754,7 +2683,7 @@ int feastcuda_destroy(feastcuda_handle h) {
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int s = 0; s < BS_COUNT; ++s) h->blk[s].release();
   DBuf* bufs[] = {&h->partial, &h->partial_r, &h->kstate, &h->small, &h->small2, &h->gram_partial, &h->stage, &h->red_ws,
-                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->lz_ticket, &h->lz_grows, &h->tile_order, &h->goff, &h->d_push, &h->push_idx, &h->cheb_dinv, &h->dA.val32, &h->dB.val32, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB, &h->dense_pool, &h->dense_piv, &h->dense_xpool};
+                  &h->lz_scal, &h->lz_coef, &h->lz_state, &h->lz_ticket, &h->lz_grows, &h->tile_order, &h->goff, &h->cheb_dinv, &h->dA.val32, &h->dB.val32, &h->dA.ptr, &h->dA.col, &h->dA.val, &h->dB.ptr, &h->dB.col, &h->dB.val, &h->dDenseA, &h->dDenseB, &h->dBandA, &h->dBandB, &h->dense_pool, &h->dense_piv, &h->dense_xpool};
   for (DBuf* b : bufs) b->release();
   for (auto& b : h->lu_cache) b.release();
   for (auto& b : h->piv_cache) b.release();

@@ -245,7 +245,6 @@ struct LzTail {
   int j;             // Lanczos step
   int* ticket;       // device counters, zero between launches: [0] groups finished, [1 + g] CTAs of group g finished
   double* grows;     // [ngroups][FC_MAXCOLS] group sums (first level of the reduction)
-  int ext_rows;      // > 0: the partial rows come from the PREVIOUS kernel (ext_rows of them); the last CTA of this launch sums them all
   LzScalars s;
   LzXchg x;
 };
@@ -271,7 +270,7 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (t.kind != LZ_TAIL_BARRIER && t.kind != LZ_TAIL_SIGNAL && t.ext_rows == 0) {
+  if (t.kind != LZ_TAIL_BARRIER && t.kind != LZ_TAIL_SIGNAL) {
     lz_reduce_rows(partial + (int64_t)grp * LZ_TAIL_GROUP * pstride, gsize, pstride, m, t_so, t_tmp);
     if ((int)threadIdx.x < m) t.grows[(int64_t)grp * FC_MAXCOLS + threadIdx.x] = t_so[threadIdx.x];
     __threadfence();
@@ -290,8 +289,7 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   } else if (t.kind == LZ_TAIL_SIGNAL) {
     lz_signal(t.x);
   } else {
-    if (t.ext_rows > 0) lz_reduce_rows(partial, t.ext_rows, pstride, m, t_so, t_tmp);
-    else lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
+    lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
     lz_exchange(t.x, t_so, m);
     if (t.kind == LZ_TAIL_INIT) lz_scalars_init(t.s, t_so, m);
     else if (t.kind == LZ_TAIL_ALPHA) lz_scalars_alpha(t.s, t.j, t_so, m);
@@ -344,22 +342,17 @@ struct LzArgs {
   const double* dinv;    // LZ_CHEB*: 1 / diag(M), one double per row
   double c1, c2;         // LZ_CHEB*: recurrence coefficients of this step
   LzTail tail;           // what the last CTA does after the row loop (pass 1: the step's scalars; sharded pass 2: the step barrier)
-  // row-sharded runs: `n` rows are this rank's block, remote columns are ghost rows n .. n + nghost - 1 of the same block
-  int sharded;
+  // row-sharded runs: `n` rows are this rank's block; the uploaded column index of an entry is (owner rank << LZ_OWNER_SHIFT) | row
+  // local to the owner, resolved once per row stride into `goff`
+  const int* goff;       // row-sharded runs: per stored entry, the distance (16-byte units) from a local block to the gathered row (k_lz_resolve)
   const int* tile_order; // row-sharded runs: the order in which the row tiles are dealt to the CTAs (nullptr: natural order); halo tiles last
   int halo_start;        // position in tile_order of the first tile that reads (and is read by) a peer
   unsigned long long wait_seq;          // > 0: before its first halo tile a warp waits until every peer has completed kernel wait_seq
   const unsigned long long* kdone;      // the local mailbox's kdone[] (written by the peers)
   int nranks, rank;
 };
+constexpr int LZ_OWNER_SHIFT = 26;
 struct LzArenas { const char* base[LZ_MAXRANKS]; };   // arena base of every rank as mapped in this process
-// push list of a row-sharded block (see k_halo_push below)
-struct LzPush {
-  int npush;
-  const int* row;    // [npush] sorted by row
-  const int* off;    // [npush] for the row stride of the block being pushed
-  const int* idx;    // [n] first entry of a row, -1 for interior rows (fused pushes of the elementwise kernels)
-};
 __host__ __device__ constexpr bool lz_is_cheb(int mode) { return mode == LZ_CHEB || mode == LZ_CHEB_DOT; }
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -407,13 +400,22 @@ template <bool CPLX> __device__ __forceinline__ int lz_elems(int m) { return CPL
 // beyond the active columns read a clamped (valid) column: the loop body carries no predicates at all.
 // Narrow groups (G <= 4 lanes per row) also receive the row's SECOND chunk of G entries prefetched (myo2, mya2): a
 // 7-point row then needs no dependent metadata load inside the loop even with 4 lanes per row.
-// Row-sharded runs (SHARD): remote columns are GHOST rows appended to the local block (filled by their owners' pushes), so the gather
-// addresses them exactly like local rows; the SHARD instantiation only adds the tile order (halo tiles last) and the lazy wait.
-template <bool SHARD> struct LzOff {
+// Row-sharded runs (SHARD): the metadata of an entry is a pre-resolved SIGNED 32-bit distance, in 16-byte units, from the local block to
+// the gathered row (k_lz_resolve: the ranks' arenas are mapped into one contiguous virtual range, peer_arena.hpp, and the owner's copy
+// of a block sits at the same arena offset as the local one), so a halo row in a peer's HBM is read by the same load as a local row --
+// over NVLink -- at the same instruction count as the single-GPU kernel.
+template <bool SHARD> struct LzOff;
+template <> struct LzOff<false> {
   typedef unsigned T;
   static __device__ __forceinline__ T meta(const LzArgs& a, int p, unsigned ldu) { return (unsigned)a.col[p] * ldu; }
   static __device__ __forceinline__ T own(unsigned eo_own) { return eo_own; }
   static __device__ __forceinline__ const double* at(const double* base, T o) { return base + o; }
+};
+template <> struct LzOff<true> {
+  typedef int T;
+  static __device__ __forceinline__ T meta(const LzArgs& a, int p, unsigned) { return a.goff[p]; }
+  static __device__ __forceinline__ T own(unsigned eo_own) { return (int)(eo_own >> 1); }
+  static __device__ __forceinline__ const double* at(const double* base, T o) { return base + 2 * (long long)o; }
 };
 
 template <int G, int NC, bool CPLX, bool SHARD>
@@ -711,19 +713,11 @@ template <bool CPLX>
 __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int64_t ld, const double* __restrict__ s_ratio_a,
                                                    const double* __restrict__ U, double* __restrict__ T,
                                                    double* __restrict__ partial, int pstride, const int* __restrict__ done,
-                                                   LzTail tail, LzPush ps) {
+                                                   LzTail tail) {
   if (done != nullptr && *done != 0) return;
   EwMap2 e(pp);
   const int P = lz_elems<CPLX>(m);
   double2 acc = make_double2(0.0, 0.0);
-  bool pushed = false;
-  // row-sharded runs: a boundary row also goes to the ghost rows of the peers that gather it (posted NVLink stores)
-  auto push = [&](int64_t row, int64_t off, double2 r) {
-    int q = ps.idx[row];
-    if (q < 0) return;
-    pushed = true;
-    do { stg2(T + off + 2 * (long long)ps.off[q], r); ++q; } while (q < ps.npush && ps.row[q] == (int)row);
-  };
   if (e.pc < P) {
     const double2 ra = lz_scal<CPLX>(s_ratio_a, e.pc, m);
     const int64_t stride = (int64_t)gridDim.x * e.rpb;
@@ -741,7 +735,6 @@ __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int
         const int64_t off = (row + q * stride) * ld + 2 * e.pc;
         const double2 r = lz_next(tv[q], ra, uv[q]);
         stg2(T + off, r);
-        if (ps.idx != nullptr) push(row + q * stride, off, r);
         acc.x = fma(r.x, r.x, acc.x);
         acc.y = fma(r.y, r.y, acc.y);
       }
@@ -750,12 +743,10 @@ __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int
       const int64_t off = row * ld + 2 * e.pc;
       const double2 r = lz_next(ldg2(T + off), ra, ldg2(U + off));
       stg2(T + off, r);
-      if (ps.idx != nullptr) push(row, off, r);
       acc.x = fma(r.x, r.x, acc.x);
       acc.y = fma(r.y, r.y, acc.y);
     }
   }
-  if (pushed) __threadfence_system();
   block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
   __shared__ double tail_scratch[FC_MAXCOLS + 256];
   lz_tail(tail, partial, pstride, m, tail_scratch);
@@ -831,31 +822,15 @@ __global__ void __launch_bounds__(128) k_lz_barrier(LzXchg x) {
   lz_exchange(x, dummy, 0);
 }
 
-// ---- halo pushes of row-sharded runs ---------------------------------------------------------------------------------------------
-// Boundary rows (rows some peer holds as ghost rows) are stored into the peers' blocks by the kernel that produces them, or by
-// k_halo_push right after it.  Entry q of the push list: local row push_row[q] -> signed distance push_off[q] (16-byte units) from the
-// row's own position to the ghost row in the peer's copy of the same block (the ranks' arenas form one contiguous virtual range).
-
-__global__ void __launch_bounds__(256) k_halo_resolve(int npush, const int* __restrict__ row, const int* __restrict__ peer,
-                                                      const int* __restrict__ dstrow, long long row_bytes, int self, LzArenas ar,
-                                                      int* __restrict__ off) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npush; i += gridDim.x * blockDim.x)
-    off[i] = (int)(((long long)(ar.base[peer[i]] - ar.base[self]) + ((long long)dstrow[i] - (long long)row[i]) * row_bytes) / 16);
-}
-
-// block rows -> the peers' ghost rows: one warp per push entry, `nelem` 16-byte elements per row; then the tail (signal / barrier)
-__global__ void __launch_bounds__(1024) k_halo_push(LzPush ps, double* blockp, int64_t ld, int nelem, LzTail tail, const double* partial,
-                                                    int pstride, int m, const int* done) {
-  if (done != nullptr && *done != 0) return;
-  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5), lane = threadIdx.x & 31;
-  for (int q = warp; q < ps.npush; q += nwarps) {
-    const double* src = blockp + (int64_t)ps.row[q] * ld;
-    double* dst = blockp + (int64_t)ps.row[q] * ld + 2 * (long long)ps.off[q];
-    for (int e = lane; e < nelem; e += 32) stg2(dst + 2 * e, ldg2(src + 2 * e));
+// pre-resolved gather offsets of a row-sharded operator: enc = (owner << LZ_OWNER_SHIFT) | row local to the owner
+__global__ void __launch_bounds__(256) k_lz_resolve(int64_t nnz, const int* __restrict__ enc, long long row_bytes, int self,
+                                                    LzArenas ar, int* __restrict__ goff) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned e = (unsigned)enc[i];
+    const int owner = (int)(e >> LZ_OWNER_SHIFT);
+    const long long local = (long long)(e & ((1u << LZ_OWNER_SHIFT) - 1u));
+    goff[i] = (int)(((long long)(ar.base[owner] - ar.base[self]) + local * row_bytes) / 16);
   }
-  __threadfence_system();
-  __shared__ double tail_scratch[FC_MAXCOLS + 1024];
-  lz_tail(tail, partial, pstride, m, tail_scratch);
 }
 
 // compact Lanczos block -> engine block (real problems: zero imaginary part)

@@ -328,3 +328,85 @@ def test_multishift_arnoldi_port_on_the_reduced_config4_pencil():
         assert np.linalg.norm(Ad @ x - r.lambda_[j] * (Bd @ x)) < 1e-11 * max(1.0, abs(r.lambda_[j]))
     ro = fo.feast_general(A.tocsc(), B.tocsc(), Emid, rad, M0, list(fpm), Q0=Q0, residual="true")
     assert ro.M == r.M
+
+
+def test_chebyshev_generalized_lanczos_port_matches_the_oracle():
+    """The generalized filter AS THE ENGINE RUNS IT (fixed Chebyshev polynomial for B^-1, unnormalised vectors, P^-1 inner product):
+    same pairs as the oracle's zfeast_hcsrgv! restatement on a small FEM pair."""
+    import scipy.sparse as sp
+
+    def k1(n, h):
+        return sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) / h
+
+    def m1(n, h):
+        return h * sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]) / 6
+    dims = (6, 5, 4)
+    hs = [1.0 / (n + 1) for n in dims]
+    Ks, Ms = [k1(n, h) for n, h in zip(dims, hs)], [m1(n, h) for n, h in zip(dims, hs)]
+    K = sp.kron(sp.kron(Ks[0], Ms[1]), Ms[2]) + sp.kron(sp.kron(Ms[0], Ks[1]), Ms[2]) + sp.kron(sp.kron(Ms[0], Ms[1]), Ks[2])
+    Mass = sp.kron(sp.kron(Ms[0], Ms[1]), Ms[2])
+    n = K.shape[0]
+    D = sp.diags(np.exp(1j * np.random.default_rng(7).uniform(0, 2 * np.pi, n)))
+    A = (D @ K @ D.conj()).tocsr()
+    B = (D @ Mass @ D.conj()).tocsr()
+    A, B = ((A + A.conj().T) * 0.5).tocsr(), ((B + B.conj().T) * 0.5).tocsr()
+    w = np.sort(sla.eigh(A.toarray(), B.toarray(), eigvals_only=True))
+    want, M0 = 5, 12
+    assert w[want] - w[want - 1] > 1e-6 * w[want]
+    Emin, Emax = 0.0, 0.5 * (w[want - 1] + w[want])
+    Q0 = fo.seeded_subspace(n, M0)
+    fpm = fo.feastinit()
+    fpm[1] = 16
+    r = fp.feast_hrr_mslanczos_gen_cheb(A, B, Emin, Emax, M0, fpm, Q0)
+    ro = fo.feast_hcsrgv(A.tocsc(), B.tocsc(), Emin, Emax, M0, fo.feastinit(), Q0=Q0)
+    assert r.info == ro.info == 0 and r.M == ro.M == want
+    assert np.abs(np.sort(r.lambda_) - w[:want]).max() < 1e-10 * w[want] and r.res.max() < 1e-12
+    assert fo.subspace_angle(np.asarray(r.q), np.asarray(ro.q, dtype=complex)) < 1e-8
+    lo, hi = r.stats["cheb_interval"]
+    ev = np.sort(sla.eigvalsh((sp.diags(1 / np.sqrt(B.diagonal().real)) @ B @ sp.diags(1 / np.sqrt(B.diagonal().real))).toarray()))
+    assert lo <= ev[0] and hi >= ev[-1]          # the Chebyshev interval encloses the spectrum of D^-1 B
+
+
+def test_two_sided_lanczos_port_on_the_reduced_config4_pencil():
+    """The general filter AS THE ENGINE RUNS IT (two-sided multi-shift Lanczos, two passes, Jacobi sweeps for B): analytic eigenvalues
+    of the Toeplitz-Kronecker pencil and the oracle's general solver."""
+    dims = (8, 8, 6)
+    coef = [(0.4 + 0.1j, 1.0 + 0.05j, 0.9 - 0.05j), (0.3 - 0.1j, 0.8 + 0.1j, 0.75 + 0.05j), (0.5 + 0.2j, 0.6 - 0.05j, 0.65 + 0.02j)]
+    eps = 0.05
+    toe = lambda n, a, b, c: sp.diags([b * np.ones(n - 1), a * np.ones(n), c * np.ones(n - 1)], [-1, 0, 1])
+    I = [sp.identity(n) for n in dims]
+    T = [toe(n, *abc) for n, abc in zip(dims, coef)]
+    S = [toe(n, 0.0, abc[1], abc[2]) for n, abc in zip(dims, coef)]
+    ksum = lambda X: sp.kron(sp.kron(X[0], I[1]), I[2]) + sp.kron(sp.kron(I[0], X[1]), I[2]) + sp.kron(sp.kron(I[0], I[1]), X[2])
+    A = ksum(T).tocsr()
+    B = (sp.identity(A.shape[0]) + eps * ksum(S)).tocsr()
+    n = A.shape[0]
+    la, ls = [], []
+    for nn, (a, b, c) in zip(dims, coef):
+        th = np.arange(1, nn + 1) * np.pi / (nn + 1)
+        la.append(a + 2 * np.sqrt(b * c) * np.cos(th))
+        ls.append(2 * np.sqrt(b * c) * np.cos(th))
+    lamA = (la[0][:, None, None] + la[1][None, :, None] + la[2][None, None, :]).ravel()
+    lamS = (ls[0][:, None, None] + ls[1][None, :, None] + ls[2][None, None, :]).ravel()
+    lam = lamA / (1 + eps * lamS)
+    order = np.argsort(lam.real)
+    Emid = complex(lam[order[0]].real, lam[order[:17]].imag.mean())
+    dist = np.abs(lam - Emid)
+    rad = 0.5 * (np.sort(dist)[11] + np.sort(dist)[12])
+    inside = lam[dist <= rad]
+    assert len(inside) == 12
+    M0 = 24
+    Q0 = fo.seeded_subspace(n, M0)
+    fpm = fo.feastinit()
+    fpm[7], fpm[2] = 24, 10
+    r = fp.feast_general_mstwosided(A, B, Emid, rad, M0, list(fpm), Q0)
+    assert r.info == 0 and r.M == 12 and r.res.max() < 1e-10 and r.loop <= 3
+    left = list(inside)
+    for g in r.lambda_:
+        j = int(np.argmin([abs(g - x) for x in left]))
+        assert abs(g - left[j]) < 1e-9
+        left.pop(j)
+    ro = fo.feast_general(A.tocsc(), B.tocsc(), Emid, rad, M0, list(fpm), Q0=Q0, residual="true")
+    assert ro.M == r.M
+    ops = fp.jacobi_setup(A, B)
+    assert 0 < ops[4] < 0.9           # Jacobi contraction bound of D^-1 B

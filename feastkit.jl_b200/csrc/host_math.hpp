@@ -2,6 +2,7 @@
 // core/feast_tools.jl:212-371) and the m x m algebra that steers the device orthonormalisation
 // (the rank decision of _feast_qr_compress!, core/feast_aux.jl:101-131).
 #pragma once
+#include "zolotarev_tables.hpp"
 #include <algorithm>
 #include <cmath>
 #include <complex>
@@ -134,7 +135,7 @@ inline void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w
   if (n % 2 == 1) x[n / 2] = 0.0;
 }
 
-// feast_contour, core/feast_tools.jl:212-284 (Gauss fpm[16]=0, trapezoid fpm[16]=1)
+// feast_contour, core/feast_tools.jl:212-284 (Gauss fpm[16]=0, trapezoid fpm[16]=1, Zolotarev fpm[16]=2)
 inline int host_contour(double Emin, double Emax, int64_t* fpm, zc* Z, zc* W) {
   if (fpm[1] == FEAST_UNINIT || fpm[1] <= 0)
     if (host_feastdefault(fpm)) return 1;
@@ -146,9 +147,16 @@ inline int host_contour(double Emin, double Emax, int64_t* fpm, zc* Z, zc* W) {
   const double ba = -pi / 2, ab = pi / 2;
   std::vector<double> xg, wg;
   if (t16 == 0) gauss_legendre(ne, xg, wg);
-  if (t16 == 2) return 2;  // Zolotarev tables: SURVEY §8f rank 2
+  const int zoff = (t16 == 2) ? zolo_offset(ne) : -1;
   for (int e = 0; e < ne; ++e) {
-    if (t16 == 0) {
+    if (t16 == 2) {
+      // zolotarev_point (core/feast_tools.jl:182-210): table value, or the reference's fallback for an ne without a table
+      zc xe, we;
+      if (zoff >= 0) { const ZoloNode& zn = ZOLO_NODES[zoff + e]; xe = zc(zn.xr, zn.xi); we = zc(zn.wr, zn.wi); }
+      else { const double th = pi * (2.0 * (e + 1) - 1.0) / (2.0 * ne); xe = zc(std::cos(th), std::sin(th)); we = zc(0.0, pi / ne); }
+      Z[e] = xe * r + Emid;       // core/feast_tools.jl:263-266 (the ellipse ratio fpm[18] does not enter)
+      W[e] = we * r;
+    } else if (t16 == 0) {
       const double th = ba * xg[e] + ab;
       Z[e] = zc(Emid + r * std::cos(th), r * aspect * std::sin(th));
       const zc jac(r * aspect * std::cos(th), r * std::sin(th));

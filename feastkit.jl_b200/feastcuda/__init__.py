@@ -99,8 +99,6 @@ def feast_contour(Emin, Emax, fpm):
     Z = np.zeros(ne, dtype=np.complex128)
     W = np.zeros(ne, dtype=np.complex128)
     rc = L.load().feastcuda_contour(float(Emin), float(Emax), L.iptr(a), Z.ctypes.data_as(L._dp), W.ctypes.data_as(L._dp))
-    if rc == L.ERR_UNSUPPORTED:
-        raise NotImplementedError("Zolotarev quadrature (fpm[16]=2) is not built yet")
     L.check(rc)
     return Z, W
 

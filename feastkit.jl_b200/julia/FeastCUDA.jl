@@ -416,6 +416,16 @@ end
 nccl_init!(nranks::Integer, rank::Integer, id::Vector{UInt8}) =
     check(ccall((:feastcuda_nccl_init, libfeastcuda), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), handle(), nranks, rank, id), handle())
 
+# Row sharding (after nccl_init!; real symmetric sparse standard problems): every rank owns a block of rows of A and of every block
+# vector; Q0 / X stay global arrays of which a rank reads / writes its own rows (INTEGRATION.md section 5)
+row_sharding!(on::Bool=true) =
+    check(ccall((:feastcuda_set_row_sharding, libfeastcuda), Cint, (Ptr{Cvoid}, Cint), handle(), on ? 1 : 0), handle())
+function row_range()
+    r0 = Ref{Int64}(0); nr = Ref{Int64}(0); ng = Ref{Int64}(0)
+    check(ccall((:feastcuda_row_range, libfeastcuda), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), handle(), r0, nr, ng), handle())
+    return (r0[] + 1):(r0[] + nr[]), ng[]          # this rank's rows (1-based), global order
+end
+
 # ---- stage-level wrappers: the block arithmetic inside feast_srci!/feast_hrci!/feast_grci! (kernel/feast_kernel.jl) ------
 # Q_proj .+= w .* Y (:143,:519,:766)
 accumulate!(Qacc::Matrix{ComplexF64}, w::Number, Y::Matrix{ComplexF64}) = (check(ccall((:feastcuda_accumulate, libfeastcuda), Cint,

@@ -260,8 +260,28 @@ def check_feast_grci_input(N, M0, Emid, r, fpm):
 # --------------------------------------------------------------------------
 # contours: core/feast_tools.jl:212-398
 # --------------------------------------------------------------------------
-def _zolotarev_unavailable(*_):
-    raise NotImplementedError("Zolotarev tables (core/feast_tools.jl:50-210) are SURVEY §8f rank 2, not restated yet")
+_ZOLO = None
+
+
+def zolotarev_point(n, k):
+    """zolotarev_point(n, k), core/feast_tools.jl:182-210: table value (tests/golden/zolotarev_tables.json, transcribed from the
+    reference's ZOLOTAREV_TABLES by tests/golden/make_zolotarev.py) or the reference's fallback for an n without a table."""
+    global _ZOLO
+    if _ZOLO is None:
+        import json
+        import pathlib
+        _ZOLO = json.loads((pathlib.Path(__file__).resolve().parents[1] / "tests" / "golden" / "zolotarev_tables.json").read_text())["tables"]
+    t = _ZOLO.get(str(n))
+    if t is not None:
+        if k == 0:
+            return 0j, complex(*t["we0"])
+        if 1 <= k <= len(t["nodes"]):
+            a, b, c, d = t["nodes"][k - 1]
+            return complex(a, b), complex(c, d)
+    if k == 0:
+        return 0j, 1 + 0j
+    theta = math.pi * (2 * k - 1) / (2 * n)
+    return complex(math.cos(theta), math.sin(theta)), complex(0.0, math.pi / n)
 
 
 def feast_contour(Emin, Emax, fpm):
@@ -284,7 +304,9 @@ def feast_contour(Emin, Emax, fpm):
             jac = r * 1j * math.sin(theta) + r * aspect * math.cos(theta)
             W[e] = 0.25 * wg[e] * jac
         elif fpm16 == 2:
-            _zolotarev_unavailable()
+            zxe, zwe = zolotarev_point(ne, e + 1)
+            Z[e] = zxe * r + Emid
+            W[e] = zwe * r
         else:
             theta = math.pi - (math.pi / ne) / 2 - (math.pi / ne) * e
             Z[e] = Emid + r * math.cos(theta) + 1j * r * aspect * math.sin(theta)

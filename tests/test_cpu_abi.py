@@ -217,3 +217,15 @@ def test_complex_symmetric_and_polynomial_host_helpers():
     for i, lam in enumerate(w):
         assert np.linalg.norm((K + lam * Cm + lam * lam * M) @ V[:N, i]) < 1e-10 * np.linalg.norm(V[:N, i]) * max(1, abs(lam)) ** 2
         assert np.allclose(V[N:, i], lam * V[:N, i], atol=1e-10 * max(1, abs(lam)))
+
+
+def test_zolotarev_contour_matches_the_oracle(lib):
+    """fpm[16] = 2: libfeastcuda's compiled tables against the oracle's (both generated from the reference's ZOLOTAREV_TABLES)."""
+    import feastcuda as fc
+    for ne in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 20):
+        fpm, fpo = fc.feastinit(), fo.feastinit()
+        fpm[1] = fpo[1] = ne
+        fpm[15] = fpo[15] = 2
+        Z, W = fc.feast_contour(0.5, 3.5, fpm)
+        Zo, Wo = fo.feast_contour(0.5, 3.5, fpo)
+        assert np.array_equal(Z, Zo) and np.array_equal(W, Wo)

@@ -92,7 +92,7 @@ def _check_common(d):
 
 
 def test_gpu_arm_json_contract(monkeypatch, capsys):
-    d = _run_bench(monkeypatch, capsys, ["--grid", "12", "--m0", "40", "--steps", "2", "--warmup", "3", "--cpu-sample-steps", "2"], StubEngine())
+    d = _run_bench(monkeypatch, capsys, ["--grid", "12", "--m0", "40", "--steps", "2", "--warmup", "3", "--cpu-sample-steps", "2", "--cpu-pair-grid", "8"], StubEngine())
     _check_common(d)
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "strong"
     assert d["ms_per_step"] == pytest.approx(2360.0) and d["value"] == pytest.approx(35 / 2.36)
@@ -104,6 +104,9 @@ def test_gpu_arm_json_contract(monkeypatch, capsys):
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and "sample" in c
+    pair = c["reference_path_pair"]          # the oracle's restatement of the reference's serial path, run to completion beside the engine
+    assert pair["n"] == 512 and pair["cpu_true_filter"]["info"] == 0 and pair["cpu_true_filter"]["M"] == 10 and pair["cpu_true_filter"]["seconds"] > 0
+    assert set(pair["gpu"]) >= {"seconds", "info", "M"}
     m = d["mixed_precision"]
     assert m["ms_per_step"] == pytest.approx(1400.0) and m["result"]["M"] == 35 and "kernels" in m
 

@@ -438,3 +438,24 @@ def test_rci_state_machines_drive_a_full_solve(engine):
     assert np.allclose(st.zAq, Q0.conj().T @ G @ Q0, atol=1e-10) and np.allclose(st.zSq, Q0.conj().T @ H @ Q0, atol=1e-10)
     assert np.allclose(np.sort(lam), want_h[(want_h >= 1.5) & (want_h <= 4.5)], atol=1e-9)
     assert abs(lam[np.argmin(abs(lam - 3.0))] - np.linalg.eigvalsh(Ad)[1]) < 0.05          # exact only near the centre
+
+
+def test_zolotarev_quadrature_solves_like_the_oracle():
+    """fpm[16] = 2 (Zolotarev rule, core/feast_tools.jl:44-210,263-266): the same contour in libfeastcuda and in the oracle, same pairs."""
+    import feastcuda as fc
+    n = 60
+    A = fo.laplacian_1d(n).tocsc()
+    lam = 2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    Emin, Emax = 0.5, 1.5
+    inside = lam[(lam >= Emin) & (lam <= Emax)]
+    M0 = 2 * len(inside)
+    Q0 = fo.seeded_subspace(n, M0, complex_storage=False)
+    fpm, fpo = fc.feastinit(), fo.feastinit()
+    fpm[15] = fpo[15] = 2
+    r = fc.feast_scsrev(A, Emin, Emax, M0, fpm, Q0=Q0, **TIGHT)
+    ro = fo.feast_scsrev(A, Emin, Emax, M0, fpo, Q0=Q0.astype(complex), filter="true")
+    assert r.info == ro.info == 0 and r.M == ro.M == len(inside)
+    assert np.abs(np.sort(r.lambda_) - inside).max() < 1e-10 and r.res.max() < 1e-12
+    assert fo.subspace_angle(r.q.astype(complex), ro.q.astype(complex)) < 1e-8
+    rd = fc.feast_syev(A.toarray(), Emin, Emax, M0, list(fpm), Q0=Q0)          # dense route: the cached LU per Zolotarev node
+    assert rd.info == 0 and rd.M == len(inside) and np.abs(np.sort(rd.lambda_) - inside).max() < 1e-10

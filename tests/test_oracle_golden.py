@@ -410,3 +410,30 @@ def test_two_sided_lanczos_port_on_the_reduced_config4_pencil():
     assert ro.M == r.M
     ops = fp.jacobi_setup(A, B)
     assert 0 < ops[4] < 0.9           # Jacobi contraction bound of D^-1 B
+
+
+def test_zolotarev_contour_tables():
+    """fpm[16] = 2 (core/feast_tools.jl:44-210, 263-266): table nodes lie on the unit half circle, the rule is symmetric about the
+    imaginary axis, and the rational filter it defines is the Zolotarev filter: ~1 inside the interval, decaying outside at the rate
+    the reference quotes per table (n = 8: 1.12e-2 per FEAST loop)."""
+    for ne in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20):
+        fpm = fo.feastinit()
+        fpm[1], fpm[15] = ne, 2
+        Z, W = fo.feast_contour(-1.0, 1.0, fpm)
+        assert len(Z) == ne and np.allclose(np.abs(Z), 1.0, atol=1e-2) and np.all(Z.imag > 0)    # (one node of FEAST's n = 20 table has |xe| = 0.9928)
+        assert np.allclose(np.sort(Z.real), -np.sort(-Z.real)[::-1], atol=1e-15)
+    fpm = fo.feastinit()
+    fpm[1], fpm[15] = 8, 2
+    Z, W = fo.feast_contour(2.0, 6.0, fpm)                       # mapped: Zne = xe * r + Emid, Wne = we * r
+    xe, we = fo.zolotarev_point(8, 1)
+    assert Z[0] == xe * 2.0 + 4.0 and W[0] == we * 2.0
+    _, we0 = fo.zolotarev_point(8, 0)
+    rho = lambda lam: (we0 + sum(2 * w / (z - lam) for z, w in zip(Z, W)).real) if False else sum(2 * (w / (z - lam)).real for z, w in zip(Z, W))
+    inside = np.array([rho(x) for x in np.linspace(2.2, 5.8, 9)])
+    outside = np.array([rho(x) for x in (0.0, 1.0, 7.0, 8.0, 40.0)])
+    assert np.all(inside > 0.4) and np.abs(outside).max() < 0.1 * inside.min()
+    # an ne without a table falls back like the reference does (core/feast_tools.jl:196-209)
+    fpm = fo.feastinit()
+    fpm[1], fpm[15] = 9, 2
+    Z9, W9 = fo.feast_contour(-1.0, 1.0, fpm)
+    assert np.allclose(W9, 1j * np.pi / 9)

@@ -208,7 +208,7 @@ def config_dict(args):
     return {"workload": f"configs[2]: sparse 3D 7-point Laplacian CSR n={args.grid ** 3} Float64, M0={args.m0}, 8 Gauss nodes, "
                         f"interval (0, mid(lambda_35, lambda_36)) -> M=35, fpm[3]=12",
             "grid": args.grid, "n": args.grid ** 3, "M0": args.m0, "nodes": 8, "inner_solver": "multi-shift two-pass Lanczos",
-            "inner_rel": SOLVER_KW["inner_rel"], "parallelism": f"{args.shard if args.gpus > 1 else 'single GPU'} x{args.gpus}",
+            "inner_rel": SOLVER_KW["inner_rel"], "fpm42": 0 if args.fp64 else 1, "parallelism": f"{args.shard if args.gpus > 1 else 'single GPU'} x{args.gpus}",
             "l2": "inputs larger than L2 (each block vector is 512 MB, L2 is 126 MB)"}
 
 
@@ -240,7 +240,10 @@ def run_gpu(args):
     fpm = fc.feastinit()
     fc.feastdefault_(fpm)
     Z, W = fc.feast_contour(Emin, Emax, fpm)
-    opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, **SOLVER_KW)
+    # the headline runs what the reference-named API runs by default: fpm[42] = 1 ("single-precision solver", the reference's default,
+    # core/feast_parameters.jl:316-319) -> FP32 Krylov vectors inside the FP64 refinement loop; --fp64 keeps FP64 vectors (fpm[42] = 0)
+    head_mixed = False if args.fp64 else "fpm"
+    opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, mixed=head_mixed, **SOLVER_KW)
     # pinned host copies of the step's input (e2e leg)
     Q0_pinned = torch.from_numpy(Q0.T.copy()).pin_memory()   # (M0, n) C-order == (n, M0) column-major
     Q0_host = Q0_pinned.numpy().T
@@ -261,7 +264,7 @@ def run_gpu(args):
     def e2e_step():
         barrier()
         t0 = time.perf_counter()
-        r = eng.solve_interval(Emin, Emax, args.m0, list(fpm), Z, W, Q0=Q0_host, x_real=True, shard=shard, gather_rows=False, reuse_output=True, **SOLVER_KW)
+        r = eng.solve_interval(Emin, Emax, args.m0, list(fpm), Z, W, Q0=Q0_host, x_real=True, shard=shard, gather_rows=False, reuse_output=True, mixed=head_mixed, **SOLVER_KW)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, r
 
@@ -289,10 +292,10 @@ def run_gpu(args):
             e2e_ms.append(ms)
     e2e_step_ms = sum(e2e_ms) / len(e2e_ms)
     lam, X, res = eng.fetch_results(args.m0, last[0], True)      # the FP64 solve's pairs, before the secondary leg overwrites them
-    # secondary leg, reported beside the headline and never mixed into it: the same solve with fpm[42]'s "single-precision
-    # solver" (FP32 Lanczos vectors inside the FP64 refinement loop, opts.mixed)
+    # secondary leg, reported beside the headline and never mixed into it: the same solve with the OTHER precision setting (FP64 Krylov
+    # vectors when the headline follows fpm[42] = 1, FP32 vectors under --fp64)
     opts_fp64 = opts
-    opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, mixed=not args.no_mixed, **SOLVER_KW)
+    opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, mixed=bool(args.fp64), **SOLVER_KW)
     mx_ms, mx_last, mx_error, st_mx, mx_step, mx_lam, mx_res = [], None, None, None, float("nan"), None, None
     try:      # the secondary leg must never cost the headline its JSON line
         if not args.no_mixed:
@@ -373,7 +376,9 @@ def run_gpu(args):
         traffic = summ.get("lz_p2_paired_average" if dom == "lz_p2" and "lz_p2_paired_average" in summ else dom, {}).get("dram_bytes_per_launch")
     roofline = None
     if dom:
-        roofline = {"bound": "hbm", "kernel": {"lz_p1": "k_lz_spmm<LZ_P1>", "lz_p2": "k_lz_spmm<LZ_P2_PAIR|LZ_P2_SKIP> (pass 2, average launch)", "lz_upd": "k_lz_update"}[dom],
+        kfam = "k_lz32_spmm" if st.get("lz_steps_fp32", 0) * 2 > st["lz_steps_p1"] else "k_lz_spmm"
+        roofline = {"bound": "hbm", "kernel": {"lz_p1": kfam + "<LZ_P1>", "lz_p2": kfam + "<LZ_P2_PAIR|LZ_P2_SKIP> (pass 2, average launch)",
+                                               "lz_upd": kfam.replace("spmm", "update")}[dom],
                     "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": traffic,
                     "peak_source": peak_src, "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"],
                     "share_of_step": share[dom] / (ms_step * args.steps), "all_kernels": kern}
@@ -390,19 +395,21 @@ def run_gpu(args):
     if cpu is not None:
         cpu["reference_path_pair"] = reference_path_pair(eng, fc, args.cpu_pair_grid)
     out = {"metric": METRIC, "value": M / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64" if args.fp64 else "f64 outer loop / f32 Krylov vectors (fpm[42] = 1, the reference's default)", "data": "synthetic",
            "config": config_dict(args),
            "result": {"M": M, "info": info, "epsout": eps, "loops": loop, "max_residual": float(res.max()) if M else None,
                       "max_eig_err_vs_analytic": eig_err, "subspace_angle_vs_analytic": parity["subspace_angle_vs_analytic"],
-                      "lanczos_steps_per_solve": st["lz_steps_p1"] / args.steps, "parity": parity},
+                      "lanczos_steps_per_solve": st["lz_steps_p1"] / args.steps, "fp32_steps_per_solve": st.get("lz_steps_fp32", 0) / args.steps,
+                      "parity": parity},
            "e2e": {"value": r.M / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
                    "h2d_bytes_per_step": int(Q0.nbytes) if shard == "rows" or world == 1 else int(Q0.nbytes) * world,
                    "d2h_bytes_per_step": (int(r.q.nbytes) if shard == "rows" or world == 1 else int(r.q.nbytes) * world) + int(r.lambda_.nbytes + r.res.nbytes) * world,
                    "note": "whole-job bytes: row-sharded ranks copy their own rows of Q0 / X only, column-sharded ranks the full blocks"},
            "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
            "mixed_precision": None if args.no_mixed else ({"error": mx_error} if mx_error else {
-               "what": "same solve with opts.mixed (fpm[42] 'single-precision solver'): FP32 Lanczos vectors and matrix entries, FP64 "
-                       "scalars, accumulator, Rayleigh-Ritz and residuals; not the headline",
+               "what": ("same solve with FP32 Lanczos vectors and matrix entries (fpm[42] = 1), FP64 scalars, accumulator, Rayleigh-Ritz and residuals"
+                        if args.fp64 else "same solve with FP64 Krylov vectors throughout (fpm[42] = 0 / mixed=False)") + "; not the headline",
                "ms_per_step": mx_step, "value": mx_last[0] / (mx_step / 1e3), "unit": UNIT,
                "result": {"M": mx_last[0], "info": mx_last[1], "epsout": mx_last[2], "loops": mx_last[3],
                           "max_residual": float(mx_res.max()) if mx_last[0] else None,
@@ -619,7 +626,8 @@ def main():
     ap.add_argument("--cpu-pair-grid", type=int, default=16, help="grid of the end-to-end CPU-oracle / GPU pair (n = grid^3)")
     ap.add_argument("--shard", default="rows", choices=["rows", "columns"], help="multi-GPU partition of the Lanczos filter (N > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-mixed", action="store_true", help="skip the secondary mixed-precision leg (profiling runs)")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the secondary leg with the other precision setting (profiling runs)")
+    ap.add_argument("--fp64", action="store_true", help="headline with FP64 Krylov vectors (fpm[42] = 0) instead of the reference's default fpm[42] = 1")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4], help="index into BASELINE.json's configs (2 = the headline workload)")
     ap.add_argument("--n", type=int, default=0, help="--config 1: matrix order (default 8192)")
     ap.add_argument("--n3", type=int, nargs=3, default=None, help="--config 3|4: grid (default: the full size)")

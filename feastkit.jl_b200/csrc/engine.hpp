@@ -172,7 +172,7 @@ struct feastcuda_handle_s {
   size_t arena_bytes = 0, arena_slot_bytes = 0, arena_mbox_off = 0;
   void* peer_arena[16] = {nullptr};            // every rank's arena as mapped in this process (peer_arena[rank] == arena)
   feastcuda::DBuf goff;                        // pre-resolved gather offsets of A's local rows (kernels_lanczos.cuh: k_lz_resolve), two row strides cached
-  int64_t goff_rowbytes = 0, goff_rowbytes2[2] = {0, 0};
+  int64_t goff_rowbytes4[4] = {0, 0, 0, 0};
   int goff_next = 0;
   feastcuda::DBuf tile_order;                  // order in which the gather kernels deal their row tiles (halo tiles spread out)
   int tile_order_tr = 0, halo_start = 0;

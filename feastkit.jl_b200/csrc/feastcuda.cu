@@ -186,7 +186,7 @@ static void upload_csr_rows(H* h, const HostCsr& src, DevCsr& dst) {
   sync(h);
   dst.uploaded = true;
   h->nnz_loc = p1 - p0;
-  h->goff_rowbytes2[0] = h->goff_rowbytes2[1] = 0;
+  for (int sl = 0; sl < 4; ++sl) h->goff_rowbytes4[sl] = 0;
   h->tile_order_tr = 0;
 }
 
@@ -690,9 +690,16 @@ static void lz32_launch(H* h, LzArgs32& a, int* grid_out) {
   // against 0.242 / 0.344 ms -- resident warps matter more than loads in flight per warp.
 #define FC_LZ32(G)                                                                 \
   do {                                                                             \
-    const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G));                          \
+    a.tile_rows = lz_pick_tile(h, a.n, 16 * (32 / G));                             \
+    const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G), 0, a.tile_rows);          \
     *grid_out = grid;                                                              \
-    k_lz32_spmm<G, MODE, 512><<<grid, 512, 0, h->stream>>>(a);                     \
+    if (a.goff != nullptr) {                                                       \
+      a.tile_order = shard_tile_order(h, 16 * (32 / G), a.tile_rows);              \
+      a.halo_start = h->halo_start;                                                \
+      a.nranks = h->nranks; a.rank = h->rank;                                      \
+      a.kdone = reinterpret_cast<const LzMailbox*>((const char*)h->arena + h->arena_mbox_off)->kdone; \
+      k_lz32_spmm<G, MODE, 512, 2, 4, true><<<grid, 512, 0, h->stream>>>(a);       \
+    } else k_lz32_spmm<G, MODE, 512><<<grid, 512, 0, h->stream>>>(a);              \
   } while (0)
   if (P <= 1) FC_LZ32(1);
   else if (P <= 2) FC_LZ32(2);
@@ -763,7 +770,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   // the work blocks are COMPACT: row stride = the slice's own column count (in doubles: even(nc) real, 2 nc complex), so a
   // rank that owns 8 of 64 columns streams dense 64-byte rows instead of touching 64 bytes out of every 512
   // mixed precision (FP32 Lanczos vectors, real problems): 4-column elements, so every compact block is padded to a multiple of 4
-  mixed = mixed && !CPLX && !matfree && !h->row_sharded && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
+  mixed = mixed && !CPLX && !matfree && (int64_t)((nc + 3) & ~3) <= 2 * h->ws_ld;   // the padded FP64 blocks must fit their slots
   const int64_t ldz = h->ws_ld, ld = CPLX ? 2 * (int64_t)nc : (mixed ? ((nc + 3) & ~3) : ((nc + 1) & ~1));
   FC_REQUIRE((double)n * (double)ld < 4294967296.0, "multi-shift Lanczos: n*ld must be below 2^32 (32-bit gather offsets)");
   kmax = std::max(1, std::min(kmax, 16384));
@@ -887,13 +894,14 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   auto cur32 = [&](int j) -> float* { return j == 0 ? F0 : reinterpret_cast<float*>((j & 1) ? UA : UB); };
   if (mixed) {
     if (!h->dA.val32_ready) {
-      h->dA.val32.ensure((size_t)std::max<int64_t>(h->hA.nnz, 1) * sizeof(float));
-      k_lz32_vals<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(h->hA.nnz, h->dA.val.as<double>(), h->dA.val32.as<float>());
+      h->dA.val32.ensure((size_t)std::max<int64_t>(h->nnz_loc, 1) * sizeof(float));
+      k_lz32_vals<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(h->nnz_loc, h->dA.val.as<double>(), h->dA.val32.as<float>());
       check_launch(h);
       h->dA.val32_ready = true;
     }
     k_lz32_narrow<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, RB, F0);
     check_launch(h);
+    xbarrier(h);   // row-sharded: step 0 gathers the peers' rows of the rounded start block
   }
   auto args32 = [&](int j) {
     LzArgs32 a;
@@ -903,6 +911,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     a.U = cur32(j); a.prev = j > 0 ? cur32(j - 1) : cur32(j); a.out = cur32(j + 1);
     a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
     a.tile_rows = h->lz_tile_rows;
+    if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(float));     // the FLOAT blocks' row stride
     return a;
   };
 
@@ -1017,6 +1026,10 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       LzArgs32 a = args32(j);
       a.Q = QA; a.s_ratio_a = S.ratio_a + (size_t)j * rowsz; a.s_coef = d_coef + (size_t)j * rowsz;
       a.s_coef_prev = j > 0 ? d_coef + (size_t)(j - 1) * rowsz : nullptr;
+      if (sharded) {
+        a.wait_seq = (h->nranks > 1 && j > 0) ? h->xseq : 0;     // the signal of the previous pass-2 kernel
+        a.tail = mk_tail(LZ_TAIL_SIGNAL, j);
+      }
       if (q_mode == 0) lz32_launch<LZ_P2>(h, a, &g);
       else if (q_mode == 1) lz32_launch<LZ_P2_SKIP>(h, a, &g);
       else lz32_launch<LZ_P2_PAIR>(h, a, &g);
@@ -1923,7 +1936,7 @@ static void arena_allocate(H* h, int ld) {
     h->blk[s].cap = slot;
     h->blk[s].owned = false;
   }
-  h->goff_rowbytes2[0] = h->goff_rowbytes2[1] = 0;
+  for (int sl = 0; sl < 4; ++sl) h->goff_rowbytes4[sl] = 0;
   h->xseq = 0;
   sync(h);
   nccl_barrier(h);   // every rank's mailbox is zeroed before anyone writes into it
@@ -1951,20 +1964,20 @@ static void xbarrier(H* h) {
 // gather offsets of A's local rows for blocks whose rows are `rowbytes` apart (two strides are in use: the compact Lanczos blocks
 // and the engine's complex blocks viewed as interleaved real columns)
 static const int* resolve_goff(H* h, int64_t rowbytes) {
-  const int64_t nnz = h->nnz_loc;
-  const int slot = (h->goff_rowbytes2[0] == rowbytes) ? 0 : ((h->goff_rowbytes2[1] == rowbytes) ? 1 : -1);
-  if (slot >= 0) return h->goff.as<int>() + (size_t)slot * (size_t)std::max<int64_t>(nnz, 1);
+  const size_t nnz1 = (size_t)std::max<int64_t>(h->nnz_loc, 1);
+  for (int sl = 0; sl < 4; ++sl)
+    if (h->goff_rowbytes4[sl] == rowbytes) return h->goff.as<int>() + (size_t)sl * nnz1;
   FC_REQUIRE(rowbytes % 16 == 0, "row sharding: rows must be multiples of 16 bytes");
   const int use = h->goff_next;
-  h->goff_next ^= 1;
-  h->goff.ensure((size_t)2 * (size_t)std::max<int64_t>(nnz, 1) * sizeof(int));
-  int* out = h->goff.as<int>() + (size_t)use * (size_t)std::max<int64_t>(nnz, 1);
+  h->goff_next = (h->goff_next + 1) & 3;
+  h->goff.ensure((size_t)4 * nnz1 * sizeof(int));
+  int* out = h->goff.as<int>() + (size_t)use * nnz1;
   LzArenas ar;
   memset(&ar, 0, sizeof(ar));
   for (int p = 0; p < h->nranks; ++p) ar.base[p] = (const char*)h->peer_arena[p];
-  k_lz_resolve<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(nnz, h->dA.col.as<int>(), (long long)rowbytes, h->rank, ar, out);
+  k_lz_resolve<<<std::max(1, h->sms * 4), 256, 0, h->stream>>>(h->nnz_loc, h->dA.col.as<int>(), (long long)rowbytes, h->rank, ar, out);
   check_launch(h);
-  h->goff_rowbytes2[use] = rowbytes;
+  h->goff_rowbytes4[use] = rowbytes;
   return out;
 }
 

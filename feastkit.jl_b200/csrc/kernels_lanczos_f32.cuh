@@ -38,6 +38,28 @@ struct LzArgs32 {
   const int* done;
   const double* s_coef_prev;   // LZ_P2_PAIR: c_{j-1} / beta_{j-1}
   LzTail tail;           // pass 1: the step's scalar recurrences, run by the last CTA (kernels_lanczos.cuh)
+  // row-sharded runs (see LzArgs): pre-resolved gather distances in 16-byte units (the FLOAT blocks' row stride), tile order, lazy wait
+  const int* goff;
+  const int* tile_order;
+  int halo_start;
+  unsigned long long wait_seq;
+  const unsigned long long* kdone;
+  int nranks, rank;
+};
+
+// gather metadata of an entry: element offset col * ld (single GPU) or the signed distance to the row in its owner's block (row-sharded)
+template <bool SHARD> struct Lz32Off;
+template <> struct Lz32Off<false> {
+  typedef unsigned T;
+  static __device__ __forceinline__ T meta(const LzArgs32& a, int p, unsigned ldu) { return (unsigned)a.col[p] * ldu; }
+  static __device__ __forceinline__ T own(unsigned eo_own) { return eo_own; }
+  static __device__ __forceinline__ const float* at(const float* base, T o) { return base + o; }
+};
+template <> struct Lz32Off<true> {
+  typedef int T;
+  static __device__ __forceinline__ T meta(const LzArgs32& a, int p, unsigned) { return a.goff[p]; }
+  static __device__ __forceinline__ T own(unsigned eo_own) { return (int)(eo_own >> 2); }
+  static __device__ __forceinline__ const float* at(const float* base, T o) { return base + 4 * (long long)o; }
 };
 
 __device__ __forceinline__ float4 ldg4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -80,12 +102,14 @@ __device__ __forceinline__ void lz32_dot(double (&d)[4], float4 x, float4 y) {
 }
 
 // acc += sum_p val[p] * U[col[p], element]  over the stored entries [p0, p1) of the row, CSR order (see lz_gather)
-template <int G, int UNMAX>
-__device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, int p0, int p1, unsigned myo, float mya, unsigned myo2,
-                                            float mya2, int g, unsigned gmask, const float* Ul, float4& acc) {
+template <int G, int UNMAX, bool SHARD>
+__device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo_, int p0, int p1, typename Lz32Off<SHARD>::T myo, float mya,
+                                            typename Lz32Off<SHARD>::T myo2, float mya2, int g, unsigned gmask, const float* Ul, float4& acc) {
+  typedef Lz32Off<SHARD> OF;
   constexpr int UN = (G >= UNMAX) ? UNMAX : G;   // gathers in flight per lane
   constexpr bool PF2 = (G <= 4);
   const unsigned ldu = (unsigned)a.ld;
+  const typename OF::T row_eo = OF::own(row_eo_);
   for (int pb = p0; pb < p1; pb += G) {
     const int cnt = min(G, p1 - pb);
     if (PF2 && pb == p0 + G) {
@@ -94,10 +118,10 @@ __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, 
     } else if (pb != p0) {
       myo = row_eo;
       mya = 0.f;
-      if (g < cnt) { myo = (unsigned)a.col[pb + g] * ldu; mya = a.val[pb + g]; }
+      if (g < cnt) { myo = OF::meta(a, pb + g, ldu); mya = a.val[pb + g]; }
     }
     for (int t = 0; t < cnt; t += UN) {
-      unsigned eo[UN];
+      typename OF::T eo[UN];
       float aa[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -106,7 +130,7 @@ __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, 
       }
       float4 xv[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) xv[u] = ldg4f(Ul + eo[u]);
+      for (int u = 0; u < UN; ++u) xv[u] = ldg4f(OF::at(Ul, eo[u]));
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         acc.x = __fmaf_rn(aa[u], xv[u].x, acc.x);
@@ -120,9 +144,11 @@ __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo, 
 
 // MODE: LZ_P1 (out = (A u) inv_beta - ratio_b prev; partial = u . out) or LZ_P2 (out = t - ratio_a u; Q += coef u)
 // (THREADS, MINB, UNMAX): 512 x 2 CTAs/SM x 4 gathers in flight (64 registers) or fewer resident warps with more loads in flight each
-template <int G, int MODE, int THREADS, int MINB = 1024 / THREADS, int UNMAX = 4>
+template <int G, int MODE, int THREADS, int MINB = 1024 / THREADS, int UNMAX = 4, bool SHARD = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
   static_assert(MODE == LZ_P1 || lz_is_p2(MODE), "FP32 vectors exist only inside the two Lanczos passes");
+  typedef Lz32Off<SHARD> OF;
+  typedef typename OF::T off_t;
   if (a.done != nullptr && *a.done != 0) return;
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
@@ -139,12 +165,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int niter = my_tiles * spt;
   const int lane_row = wib * RPW + sub;
-  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR;
+  int it_f = 0, s_f = 0, base_f = (int)blockIdx.x * TR, t_f = (int)blockIdx.x;
+  if (SHARD && a.tile_order != nullptr && my_tiles > 0) base_f = a.tile_order[t_f] * TR;
   auto next_row = [&]() -> int {
     const int r = (it_f < niter) ? base_f + lane_row : n;
     ++it_f;
-    if (++s_f == spt) { s_f = 0; base_f += ((int)gridDim.x - 1) * TR + STEP; }
-    else base_f += STEP;
+    if (++s_f == spt) {
+      s_f = 0;
+      if (SHARD && a.tile_order != nullptr) {
+        t_f += (int)gridDim.x;
+        base_f = (it_f < niter) ? a.tile_order[t_f] * TR : 0;
+      } else base_f += ((int)gridDim.x - 1) * TR + STEP;
+    } else base_f += STEP;
     return r < n ? r : n;
   };
 
@@ -173,21 +205,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
   if (r_cur < n) { p0_cur = a.ptr[r_cur]; p1_cur = a.ptr[r_cur + 1]; }
   if (r_nxt < n) { p0_nxt = a.ptr[r_nxt]; p1_nxt = a.ptr[r_nxt + 1]; }
   constexpr bool PF2 = (G <= 4);
-  unsigned o_cur = (r_cur < n ? (unsigned)r_cur : 0u) * ldu, o_cur2 = o_cur;
+  off_t o_cur = OF::own((r_cur < n ? (unsigned)r_cur : 0u) * ldu), o_cur2 = o_cur;
   float a_cur = 0.f, a_cur2 = 0.f;
-  if (g < p1_cur - p0_cur) { o_cur = (unsigned)a.col[p0_cur + g] * ldu; a_cur = a.val[p0_cur + g]; }
-  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = (unsigned)a.col[p0_cur + G + g] * ldu; a_cur2 = a.val[p0_cur + G + g]; }
+  if (g < p1_cur - p0_cur) { o_cur = OF::meta(a, p0_cur + g, ldu); a_cur = a.val[p0_cur + g]; }
+  if (PF2 && g + G < p1_cur - p0_cur) { o_cur2 = OF::meta(a, p0_cur + G + g, ldu); a_cur2 = a.val[p0_cur + G + g]; }
 
+  int it_h = 0x7fffffff;     // first iteration of this CTA that may touch a halo tile (see k_lz_spmm)
+  if (SHARD && a.wait_seq != 0 && a.tile_order != nullptr) {
+    const int first = a.halo_start > (int)blockIdx.x ? (a.halo_start - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    it_h = first * spt;
+  }
   for (int it = 0; it < niter; ++it) {
+    if (SHARD && it == it_h) {
+      if (lane < a.nranks && lane != a.rank) { while (ld_sys_u64(a.kdone + lane) < a.wait_seq) { } }
+      __syncwarp();
+    }
     const int row = r_cur;
     const bool valid = row < n;
     const int r_fut = next_row();
     int p0_fut = 0, p1_fut = 0;
     if (r_fut < n) { p0_fut = a.ptr[r_fut]; p1_fut = a.ptr[r_fut + 1]; }
-    unsigned o_nxt = (r_nxt < n ? (unsigned)r_nxt : 0u) * ldu, o_nxt2 = o_nxt;
+    off_t o_nxt = OF::own((r_nxt < n ? (unsigned)r_nxt : 0u) * ldu), o_nxt2 = o_nxt;
     float a_nxt = 0.f, a_nxt2 = 0.f;
-    if (g < p1_nxt - p0_nxt) { o_nxt = (unsigned)a.col[p0_nxt + g] * ldu; a_nxt = a.val[p0_nxt + g]; }
-    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = (unsigned)a.col[p0_nxt + G + g] * ldu; a_nxt2 = a.val[p0_nxt + G + g]; }
+    if (g < p1_nxt - p0_nxt) { o_nxt = OF::meta(a, p0_nxt + g, ldu); a_nxt = a.val[p0_nxt + g]; }
+    if (PF2 && g + G < p1_nxt - p0_nxt) { o_nxt2 = OF::meta(a, p0_nxt + G + g, ldu); a_nxt2 = a.val[p0_nxt + G + g]; }
 
     const unsigned eo_own = (valid ? (unsigned)row : 0u) * ldu;
     const float4 uo = ldg4f(Ul + eo_own);
@@ -198,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
       q1 = ldg2(Ql + eo_own + 2);
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    lz32_gather<G, UNMAX>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
+    lz32_gather<G, UNMAX, SHARD>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
     if (valid && g < P) {
       const float4 t = lz32_t(acc, s_sc[0][g], s_sc[1][g], pv);
       if constexpr (MODE == LZ_P1) {

@@ -72,6 +72,9 @@ def _solver_kw(kind, solver, solver_tol, solver_maxiter, solver_restart, extras)
         kw["ritz_guess"] = True
         kw["inner_rel"] = 1e-3
         kw["adaptive"] = True
+        # fpm[42] ("mixed precision: 1 = single-precision solver", default 1, core/feast_parameters.jl:316-319): the engine honours it where
+        # it has an FP32 inner solver (real symmetric standard problems on the Lanczos filter); mixed=False keeps FP64 Krylov vectors
+        kw["mixed"] = "fpm"
     kw["filter"] = "true"
     for k in ("inner_rel", "ritz_guess", "filter", "shard", "check_every", "inner_rel0", "maxiter0", "keep_going", "adaptive", "eps_floor", "mixed", "b_delta"):
         if k in extras:

@@ -86,7 +86,7 @@ def _check_common(d):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "e2e", "cpu_baseline"):
         assert key in d, key
-    assert d["unit"] == "eigenpairs/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["unit"] == "eigenpairs/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"].startswith("f64")
     assert "workload" in d["config"] and "model" not in d["config"] and d["data"] == "synthetic"
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
 
@@ -95,7 +95,8 @@ def test_gpu_arm_json_contract(monkeypatch, capsys):
     d = _run_bench(monkeypatch, capsys, ["--grid", "12", "--m0", "40", "--steps", "2", "--warmup", "3", "--cpu-sample-steps", "2", "--cpu-pair-grid", "8"], StubEngine())
     _check_common(d)
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "strong"
-    assert d["ms_per_step"] == pytest.approx(2360.0) and d["value"] == pytest.approx(35 / 2.36)
+    assert d["ms_per_step"] == pytest.approx(1400.0) and d["value"] == pytest.approx(35 / 1.4)      # headline: fpm[42] = 1 (FP32 Krylov vectors)
+    assert d["config"]["fpm42"] == 1 and "f32" in d["dtype"]
     assert d["gpu_launches"] > 0 and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert set(d["result"]["parity"]) >= {"all_ranks_ok", "same_M_on_all_ranks", "subspace_angle_vs_analytic", "ranks"}
     r = d["roofline"]
@@ -107,14 +108,14 @@ def test_gpu_arm_json_contract(monkeypatch, capsys):
     pair = c["reference_path_pair"]          # the oracle's restatement of the reference's serial path, run to completion beside the engine
     assert pair["n"] == 512 and pair["cpu_true_filter"]["info"] == 0 and pair["cpu_true_filter"]["M"] == 10 and pair["cpu_true_filter"]["seconds"] > 0
     assert set(pair["gpu"]) >= {"seconds", "info", "M"}
-    m = d["mixed_precision"]
-    assert m["ms_per_step"] == pytest.approx(1400.0) and m["result"]["M"] == 35 and "kernels" in m
+    m = d["mixed_precision"]                   # the secondary leg: the other precision setting (FP64 vectors here)
+    assert m["ms_per_step"] == pytest.approx(2360.0) and m["result"]["M"] == 35 and "kernels" in m
 
 
 def test_gpu_arm_survives_a_failing_secondary_leg(monkeypatch, capsys):
-    d = _run_bench(monkeypatch, capsys, ["--grid", "12", "--m0", "40", "--steps", "1", "--warmup", "3", "--no-cpu"], StubEngine(fail_mixed=True))
+    d = _run_bench(monkeypatch, capsys, ["--grid", "12", "--m0", "40", "--steps", "1", "--warmup", "3", "--no-cpu", "--fp64"], StubEngine(fail_mixed=True))
     _check_common(d)
-    assert d["ms_per_step"] == pytest.approx(2360.0) and d["cpu_baseline"] is None
+    assert d["ms_per_step"] == pytest.approx(2360.0) and d["cpu_baseline"] is None and d["dtype"] == "f64"
     assert d["mixed_precision"] == {"error": "RuntimeError: boom"}
 
 

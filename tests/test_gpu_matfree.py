@@ -43,7 +43,7 @@ def test_feast_matvec_with_a_compiled_cuda_operator(N, M0, k_in):
     r = fc.feast_matvec((ex.feastcuda_example_laplacian3d, grid), None, N ** 3, (Emin, Emax), M0=M0, fpm=fc.feastinit(), Q0=Q0,
                         solver_maxiter=2000)
     _check(r, ro, A)
-    rs = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000)
+    rs = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000, mixed=False)    # matrix-free runs FP64 vectors
     assert r.loop == rs.loop and abs(r.stats["lz_steps_p1"] - rs.stats["lz_steps_p1"]) <= 16
     assert r.stats["lz_steps_p2"] == r.stats["lz_steps_p1"] > 0
 

@@ -227,7 +227,7 @@ def test_mslanczos_inexact_matches_cpu_port_loop_for_loop():
     ev = fo.laplacian_3d_eigs(N)
     Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
     Q0 = fo.seeded_subspace(N ** 3, M0, complex_storage=False)
-    r = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000, adaptive=False)
+    r = fc.feast_scsrev(A, Emin, Emax, M0, fc.feastinit(), Q0=Q0, solver_maxiter=2000, adaptive=False, mixed=False)   # FP64 recurrence = the port's
     rp = fp.feast_hrr_mslanczos(A.tocsr(), Emin, Emax, M0, fo.feastinit(), Q0, inner_rel=1e-3, inner_maxiter=2000, adaptive=False)
     ro = fo.feast_scsrev(A, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
     _check_pairs(r, ro, A)
@@ -316,7 +316,8 @@ def test_float32_entry_points_types_and_tolerance():
     ev = fo.laplacian_3d_eigs(N)
     Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
     rs = fc.sfeast_scsrev(L3, Emin, Emax, 20, fc.feastinit(), Q0=fo.seeded_subspace(N ** 3, 20, complex_storage=False))
-    rd = fc.dfeast_scsrev(L3.astype(np.float64), Emin, Emax, 20, fc.feastinit(), Q0=fo.seeded_subspace(N ** 3, 20, complex_storage=False))
+    rd = fc.dfeast_scsrev(L3.astype(np.float64), Emin, Emax, 20, fc.feastinit(), Q0=fo.seeded_subspace(N ** 3, 20, complex_storage=False),
+                          mixed=False)
     assert rs.info == 0 and rs.M == rd.M == 10
     assert np.abs(np.sort(rs.lambda_) - ev[:10]).max() <= 1e-4 * ev[9]
     assert rs.res.max() <= np.sqrt(np.finfo(np.float32).eps) and rs.loop <= rd.loop   # stops at the Float32 tolerance

@@ -64,7 +64,7 @@ static void ensure_workspace(H* h, int64_t n, int m0) {
   }
   const int maxblocks = h->sms * 8;
   h->partial.ensure((size_t)3 * maxblocks * FC_MAXCOLS * sizeof(zd));
-  h->partial_r.ensure((size_t)2 * maxblocks * FC_MAXCOLS * sizeof(double));   // two dot products per CTA in k_lz_spmm<LZ_P1B>
+  h->partial_r.ensure((size_t)maxblocks * FC_MAXCOLS * sizeof(double));
   h->kstate.ensure(sizeof(KrylovState<double>));
   h->small.ensure((size_t)8 * FC_MAXCOLS * FC_MAXCOLS * sizeof(zd));
   h->small2.ensure((size_t)4 * FC_MAXCOLS * sizeof(zd) + 64);
@@ -627,7 +627,7 @@ static void lz_launch(H* h, LzArgs& a, int* grid_out) {
       const int grid = lz_grid_spmm(h, a.n, 16 * (32 / G), NC >= 3 ? 1 : 0, a.tile_rows);  \
       *grid_out = grid;                                                                    \
       if (a.goff != nullptr) {                                                             \
-        if constexpr (!CPLX && NC <= 2 && (MODE <= LZ_P2_PAIR || MODE == LZ_P1B)) {        \
+        if constexpr (!CPLX && NC <= 2 && MODE <= LZ_P2_PAIR) {                            \
           a.tile_order = shard_tile_order(h, 16 * (32 / G), a.tile_rows);                               \
           a.halo_start = h->halo_start;                                                    \
           a.nranks = h->nranks; a.rank = h->rank;                                          \
@@ -808,7 +808,7 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
     h->lz_ticket.ensure(256 * sizeof(int));
     FC_CUDA(cudaMemsetAsync(h->lz_ticket.p, 0, 256 * sizeof(int), h->stream));
   }
-  h->lz_grows.ensure((size_t)2 * 128 * FC_MAXCOLS * sizeof(double));
+  h->lz_grows.ensure((size_t)128 * FC_MAXCOLS * sizeof(double));
   int* ticket = h->lz_ticket.as<int>();
   double* grows = h->lz_grows.as<double>();
   FC_CUDA(cudaMemcpyAsync(d_z, Zne, (size_t)ne * sizeof(zd), cudaMemcpyHostToDevice, h->stream));
@@ -916,9 +916,6 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
   };
 
   // ---- pass 1: build T_k, device-side convergence flag ----------------------------------------------------------
-  unsigned long long upd_seq = 0;                     // sequence number of the last update kernel's completion signal (row-sharded)
-  h->gram_partial.ensure((size_t)h->sms * 8 * FC_MAXCOLS * sizeof(double));
-  double* part2 = h->gram_partial.as<double>();       // the update kernel's (unused) norm partials must not clobber the SpMM's rows
   Timer t1;
   int* flag = reinterpret_cast<int*>(pinned_buf(h, 64));
   flag[0] = 0;
@@ -939,9 +936,8 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
       } else if (mixed) {
         LzArgs32 a = args32(j);
         a.partial = part; a.pstride = FC_MAXCOLS; a.done = S.done_k;
-        a.tail = mk_tail(LZ_TAIL_AB, j);
-        if (sharded) a.wait_seq = (h->nranks > 1 && j > 0) ? upd_seq : 0;     // the peers' update kernel of step j-1 (lazy wait before the halo tiles)
-        lz32_launch<LZ_P1B>(h, a, &g);
+        a.tail = mk_tail(LZ_TAIL_ALPHA, j);
+        lz32_launch<LZ_P1>(h, a, &g);
       } else {
         LzArgs a;
         memset(&a, 0, sizeof(a));
@@ -950,12 +946,9 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
         a.U = cur(j); a.prev = j > 0 ? cur(j - 1) : cur(j); a.out = cur(j + 1);
         a.s_inv_beta = S.inv_beta + (size_t)j * rowsz; a.s_ratio_b = S.ratio_b + (size_t)j * rowsz;
         a.partial = part; a.pstride = FC_MAXCOLS; a.tile_rows = h->lz_tile_rows; a.done = S.done_k;
-        a.tail = mk_tail(LZ_TAIL_AB, j);
-        if (sharded) {
-          a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
-          a.wait_seq = (h->nranks > 1 && j > 0) ? upd_seq : 0;     // the peers' update kernel of step j-1 (lazy wait before the halo tiles)
-        }
-        lz_launch<LZ_P1B, CPLX>(h, a, &g);
+        a.tail = mk_tail(LZ_TAIL_ALPHA, j);
+        if (sharded) a.goff = resolve_goff(h, ld * (int64_t)sizeof(double));
+        lz_launch<LZ_P1, CPLX>(h, a, &g);
       }
       sample_end(h, ev);
       if (matfree) {
@@ -963,16 +956,12 @@ static void msl_filter(H* h, int basis_slot, int c0, int nc, bool have_ritz, con
         check_launch(h);
       }
       ev = smp ? sample_begin(h, FEASTCUDA_KERN_LZ_UPD, j) : -1;
-      // the sparse path takes beta_{j+1} from the SpMM kernel's second dot product (LZ_P1B): the update has no reduction of its own;
-      // row-sharded: it only signals its completion (the next SpMM waits for the peers' signals before its halo tiles)
-      LzTail ut = matfree ? mk_tail(LZ_TAIL_BETA, j) : mk_tail(sharded ? LZ_TAIL_SIGNAL : LZ_TAIL_NONE, j);
-      if (sharded) upd_seq = h->xseq;
       if (mixed)
-        k_lz32_update<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, S.ratio_a + (size_t)j * rowsz, cur32(j), cur32(j + 1), part2, FC_MAXCOLS,
-                                                     S.done_k, ut);
+        k_lz32_update<<<egrid4, 256, 0, h->stream>>>(n, nc, pp4, ld, S.ratio_a + (size_t)j * rowsz, cur32(j), cur32(j + 1), part, FC_MAXCOLS,
+                                                     S.done_k, mk_tail(LZ_TAIL_BETA, j));
       else
-        k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), matfree ? part : part2,
-                                                   FC_MAXCOLS, S.done_k, ut);
+        k_lz_update<CPLX><<<egrid, 256, 0, h->stream>>>(n, nc, pp, ld, S.ratio_a + (size_t)j * rowsz, cur(j), cur(j + 1), part, FC_MAXCOLS,
+                                                   S.done_k, mk_tail(LZ_TAIL_BETA, j));
       check_launch(h);
       sample_end(h, ev);
       if (matfree) {
@@ -1196,7 +1185,7 @@ static void msl_filter_gen(H* h, int basis_slot, int c0, int nc, bool have_ritz,
   const int pp = pow2_ge(P);
   const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
   const int K = cheb_degree(h->cheb_lo, h->cheb_hi, cheb_delta);
-  const int slice = getenv("FEASTCUDA_GEN_SLICE") ? atoi(getenv("FEASTCUDA_GEN_SLICE")) : 128;   // complex columns per gather launch (slices measured SLOWER: 2 x 48 columns 0.52 ms against 0.30 ms unsliced)
+  const int slice = getenv("FEASTCUDA_GEN_SLICE") ? atoi(getenv("FEASTCUDA_GEN_SLICE")) : 64;   // complex columns per gather launch
   const double* dinv = h->cheb_dinv.as<double>();
 
   // ---- device scalars (layout as in msl_filter) -------------------------------------------------------------------

@@ -37,13 +37,8 @@ enum LzMode {
   //   out = u + c1 (u - prev) + c2 dinv[row] (rhs - M u)          (u gathered, prev / rhs own-row, out may alias prev)
   // c1 = c2-independent of the column, so a solve is a FIXED polynomial in M: no dot products, no data-dependent control flow
   LZ_CHEB = 6,
-  LZ_CHEB_DOT = 7,  // as LZ_CHEB;  partial[0] = Re(conj(out) . rhs)   (last step: beta^2 = u_{j+1}^H s_{j+1})
-  // as LZ_P1 with a second dot product: partial[1] = |out|^2.  beta_{j+1}^2 = |t|^2 - alpha_j^2 then follows from the SAME reduction as
-  // alpha_j (||v_j|| = 1), so a pass-1 step has ONE reduction -- one cross-rank exchange in row-sharded runs -- instead of two, and the
-  // update kernel needs no reduction at all
-  LZ_P1B = 8
+  LZ_CHEB_DOT = 7   // as LZ_CHEB;  partial[0] = Re(conj(out) . rhs)   (last step: beta^2 = u_{j+1}^H s_{j+1})
 };
-__host__ __device__ constexpr bool lz_is_p1(int mode) { return mode == LZ_P1 || mode == LZ_P1B; }
 __host__ __device__ constexpr bool lz_is_p2(int mode) { return mode == LZ_P2 || mode == LZ_P2_SKIP || mode == LZ_P2_PAIR; }
 
 // ---- per-step scalar recurrences -------------------------------------------------------------------------------
@@ -72,7 +67,7 @@ struct LzScalars {
 constexpr int LZ_MAXRANKS = 16;
 constexpr int LZ_MBOX_SLOTS = 4;
 struct LzMailbox {   // lives in every rank's shared arena (zeroed at allocation)
-  double data[LZ_MBOX_SLOTS][LZ_MAXRANKS][2 * FC_MAXCOLS];
+  double data[LZ_MBOX_SLOTS][LZ_MAXRANKS][FC_MAXCOLS];
   unsigned long long flag[LZ_MBOX_SLOTS][LZ_MAXRANKS];
   unsigned long long kdone[LZ_MAXRANKS];   // kdone[p]: sequence number of the last kernel rank p has completed (LZ_TAIL_SIGNAL)
 };
@@ -114,10 +109,10 @@ __device__ __forceinline__ void lz_exchange(const LzXchg& x, double* so, int m) 
     while (ld_sys_u64(mine) != x.seq) { }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+  if ((int)threadIdx.x < m) {
     double s = 0.0;
-    for (int p = 0; p < x.nranks; ++p) s += ld_sys_f64(&x.mbox[x.rank]->data[slot][p][c]);
-    so[c] = s;
+    for (int p = 0; p < x.nranks; ++p) s += ld_sys_f64(&x.mbox[x.rank]->data[slot][p][threadIdx.x]);
+    so[threadIdx.x] = s;
   }
   __syncthreads();
 }
@@ -241,23 +236,9 @@ __device__ __forceinline__ void lz_scalars_beta(const LzScalars& s, int j, const
   }
 }
 
-// after k_lz_spmm<LZ_P1B> of step j: so[c] = u_j . t, so[FC_MAXCOLS + c] = |t|^2  ->  alpha_j, then beta_{j+1}^2 = |t|^2 - alpha_j^2
-// (u_{j+1} = t - alpha_j v_j with ||v_j|| = 1 and v_j . t = alpha_j), then everything lz_scalars_beta does
-__device__ __forceinline__ void lz_scalars_ab(const LzScalars& s, int j, double* so, int m, double* tmp) {
-  lz_scalars_alpha(s, j, so, m);
-  const int c = threadIdx.x;
-  if (c < m) {
-    const double al = s.alpha[(int64_t)j * FC_MAXCOLS + c];
-    so[c] = fmax(so[FC_MAXCOLS + c] - al * al, 0.0);
-  }
-  __syncthreads();
-  lz_scalars_beta(s, j, so, m, tmp);
-}
-
 // Tail of a producer kernel: the LAST CTA to finish (ticket counter) sums the per-CTA partial rows in a fixed order, exchanges the
 // sums with the other ranks and runs the scalar recurrences that used to be separate one-CTA launches.
-enum LzTailKind { LZ_TAIL_NONE = 0, LZ_TAIL_INIT = 1, LZ_TAIL_ALPHA = 2, LZ_TAIL_BETA = 3, LZ_TAIL_BARRIER = 4, LZ_TAIL_SIGNAL = 5,
-                  LZ_TAIL_AB = 6 /* alpha_j and beta_{j+1} from the two dot products of k_lz_spmm<LZ_P1B> */ };
+enum LzTailKind { LZ_TAIL_NONE = 0, LZ_TAIL_INIT = 1, LZ_TAIL_ALPHA = 2, LZ_TAIL_BETA = 3, LZ_TAIL_BARRIER = 4, LZ_TAIL_SIGNAL = 5 };
 constexpr int LZ_TAIL_GROUP = 16;   // CTAs per first-level group of the two-level tail reduction
 struct LzTail {
   int kind;          // LzTailKind
@@ -270,12 +251,12 @@ struct LzTail {
 
 // every thread of the CTA calls this after the CTA's partial row is written (or with nothing written for LZ_TAIL_BARRIER);
 // blockDim.x must be a power of two >= 128
-// scratch: 2 * FC_MAXCOLS + blockDim.x doubles of shared memory the caller no longer needs
+// scratch: FC_MAXCOLS + blockDim.x doubles of shared memory the caller no longer needs
 __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, int pstride, int m, double* scratch) {
   if (t.kind == LZ_TAIL_NONE) return;
   __shared__ int s_last;
   double* t_so = scratch;
-  double* t_tmp = scratch + 2 * FC_MAXCOLS;
+  double* t_tmp = scratch + FC_MAXCOLS;
   __threadfence();      // this CTA's rows are visible device-wide before its ticket; the CTA that raises the cross-rank flag adds the
   __syncthreads();      // system-scope fence (lz_exchange), which is cumulative over everything it has observed
   // two levels, both in a fixed order: the last CTA of every group of LZ_TAIL_GROUP consecutive CTAs sums the group's rows, the last
@@ -289,12 +270,9 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int nslot = (t.kind == LZ_TAIL_AB) ? 2 : 1;
   if (t.kind != LZ_TAIL_BARRIER && t.kind != LZ_TAIL_SIGNAL) {
-    for (int sl = 0; sl < nslot; ++sl) {
-      lz_reduce_rows(partial + ((int64_t)sl * gridDim.x + (int64_t)grp * LZ_TAIL_GROUP) * pstride, gsize, pstride, m, t_so, t_tmp);
-      if ((int)threadIdx.x < m) t.grows[((int64_t)sl * ngroups + grp) * FC_MAXCOLS + threadIdx.x] = t_so[threadIdx.x];
-    }
+    lz_reduce_rows(partial + (int64_t)grp * LZ_TAIL_GROUP * pstride, gsize, pstride, m, t_so, t_tmp);
+    if ((int)threadIdx.x < m) t.grows[(int64_t)grp * FC_MAXCOLS + threadIdx.x] = t_so[threadIdx.x];
     __threadfence();
   }
   __syncthreads();
@@ -311,11 +289,10 @@ __device__ __forceinline__ void lz_tail(const LzTail& t, const double* partial, 
   } else if (t.kind == LZ_TAIL_SIGNAL) {
     lz_signal(t.x);
   } else {
-    for (int sl = 0; sl < nslot; ++sl) lz_reduce_rows(t.grows + (int64_t)sl * ngroups * FC_MAXCOLS, ngroups, FC_MAXCOLS, m, t_so + sl * FC_MAXCOLS, t_tmp);
-    lz_exchange(t.x, t_so, (nslot - 1) * FC_MAXCOLS + m);
+    lz_reduce_rows(t.grows, ngroups, FC_MAXCOLS, m, t_so, t_tmp);
+    lz_exchange(t.x, t_so, m);
     if (t.kind == LZ_TAIL_INIT) lz_scalars_init(t.s, t_so, m);
     else if (t.kind == LZ_TAIL_ALPHA) lz_scalars_alpha(t.s, t.j, t_so, m);
-    else if (t.kind == LZ_TAIL_AB) lz_scalars_ab(t.s, t.j, t_so, m, t_tmp);
     else lz_scalars_beta(t.s, t.j, t_so, m, t_tmp);
   }
   if (threadIdx.x == 0) *t.ticket = 0;
@@ -558,9 +535,9 @@ __global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_
     s_sc[w][pc] = lz_scal<CPLX>(src, pc, a.m);
   }
   __syncthreads();
-  double2 dot[NC], dot2[NC];
+  double2 dot[NC];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) { dot[k] = make_double2(0.0, 0.0); dot2[k] = make_double2(0.0, 0.0); }
+  for (int k = 0; k < NC; ++k) dot[k] = make_double2(0.0, 0.0);
 
   // software pipeline over the CSR metadata: row pointers two iterations ahead, the first G (offset, val) pairs one
   // iteration ahead, so the vector gathers of an iteration never wait behind a pointer chase.  (Measured on B200: a
@@ -621,7 +598,7 @@ __global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_
       acc[k] = make_double2(0.0, 0.0);
       if constexpr (MODE == LZ_RES) uo[k] = ldg2(Wl[k] + eo_own);
       else if constexpr (MODE != LZ_PLAIN) uo[k] = ldg2(Ul[k] + eo_own);
-      if constexpr (lz_is_p1(MODE) || lz_is_p2(MODE) || lz_is_cheb(MODE)) pv[k] = ldg2(Pl[k] + eo_own);
+      if constexpr (MODE == LZ_P1 || lz_is_p2(MODE) || lz_is_cheb(MODE)) pv[k] = ldg2(Pl[k] + eo_own);
     }
     double2 rh[NC];
     double di = 0.0;
@@ -657,14 +634,10 @@ __global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_
           if (a.Q != nullptr) stg2(Ql[k] + eo_own, make_double2(cf.x * uo[k].x, cf.y * uo[k].y));
         } else {
           const double2 t = lz_t(acc[k], s_sc[0][pc], s_sc[1][pc], pv[k]);
-          if constexpr (lz_is_p1(MODE)) {
+          if constexpr (MODE == LZ_P1) {
             stg2(Ol[k] + eo_own, t);
             dot[k].x = fma(uo[k].x, t.x, dot[k].x);
             dot[k].y = fma(uo[k].y, t.y, dot[k].y);
-            if constexpr (MODE == LZ_P1B) {
-              dot2[k].x = fma(t.x, t.x, dot2[k].x);
-              dot2[k].y = fma(t.y, t.y, dot2[k].y);
-            }
           } else {
             stg2(Ol[k] + eo_own, lz_next(t, s_sc[2][pc], uo[k]));
             if constexpr (MODE != LZ_P2_SKIP) {
@@ -688,27 +661,22 @@ __global__ void __launch_bounds__(THREADS, (NC >= 3) ? 1 : 1024 / THREADS) k_lz_
   }
 
   __shared__ double2 red[(THREADS / 32) * 32 * NC];   // CTA reduction of the dot products, then the tail's scratch
-  if constexpr (lz_is_p1(MODE) || MODE == LZ_RES || MODE == LZ_CHEB_DOT) {
+  if constexpr (MODE == LZ_P1 || MODE == LZ_RES || MODE == LZ_CHEB_DOT) {
     // fixed-order CTA reduction: every launch sums in the same order (pass 2 relies on pass 1's exact scalars)
     const int width = G * NC;   // pairs per row group
-    constexpr int NSLOT = (MODE == LZ_P1B) ? 2 : 1;
 #pragma unroll
-    for (int sl = 0; sl < NSLOT; ++sl) {
-      if (sl > 0) __syncthreads();
-#pragma unroll
-      for (int k = 0; k < NC; ++k) red[(wib * RPW + sub) * width + g + G * k] = (sl == 0) ? dot[k] : dot2[k];
-      __syncthreads();
-      const int ngroups = wpb * RPW;
-      double* prow = a.partial + ((int64_t)sl * gridDim.x + blockIdx.x) * a.pstride;     // slot sl: rows [sl * gridDim.x, (sl + 1) * gridDim.x)
-      for (int pc = threadIdx.x; pc < width; pc += THREADS) {
-        if (pc < P) {
-          double sx = 0.0, sy = 0.0;
-          for (int q = 0; q < ngroups; ++q) { const double2 v = red[q * width + pc]; sx += v.x; sy += v.y; }
-          if (CPLX) prow[pc] = sx + sy;   // Re(conj(u) t) = sum of both components
-          else {
-            prow[2 * pc] = sx;
-            if (2 * pc + 1 < a.m) prow[2 * pc + 1] = sy;
-          }
+    for (int k = 0; k < NC; ++k) red[(wib * RPW + sub) * width + g + G * k] = dot[k];
+    __syncthreads();
+    const int ngroups = wpb * RPW;
+    for (int pc = threadIdx.x; pc < width; pc += THREADS) {
+      if (pc < P) {
+        double sx = 0.0, sy = 0.0;
+        for (int q = 0; q < ngroups; ++q) { const double2 v = red[q * width + pc]; sx += v.x; sy += v.y; }
+        if (CPLX) a.partial[(int64_t)blockIdx.x * a.pstride + pc] = sx + sy;   // Re(conj(u) t) = sum of both components
+        else {
+          double* o = a.partial + (int64_t)blockIdx.x * a.pstride + 2 * pc;
+          o[0] = sx;
+          if (2 * pc + 1 < a.m) o[1] = sy;
         }
       }
     }
@@ -780,7 +748,7 @@ __global__ void __launch_bounds__(256) k_lz_update(int64_t n, int m, int pp, int
     }
   }
   block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
-  __shared__ double tail_scratch[2 * FC_MAXCOLS + 256];
+  __shared__ double tail_scratch[FC_MAXCOLS + 256];
   lz_tail(tail, partial, pstride, m, tail_scratch);
 }
 
@@ -844,7 +812,7 @@ __global__ void __launch_bounds__(256) k_lz_real_part(int64_t n, int m, int pp, 
     }
   }
   if (partial != nullptr) block_reduce_pairs<CPLX>(acc, pp, P, m, partial + (int64_t)blockIdx.x * pstride);
-  __shared__ double tail_scratch[2 * FC_MAXCOLS + 256];
+  __shared__ double tail_scratch[FC_MAXCOLS + 256];
   lz_tail(tail, partial, pstride, m, tail_scratch);
 }
 

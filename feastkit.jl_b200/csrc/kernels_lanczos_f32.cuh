@@ -146,7 +146,7 @@ __device__ __forceinline__ void lz32_gather(const LzArgs32& a, unsigned row_eo_,
 // (THREADS, MINB, UNMAX): 512 x 2 CTAs/SM x 4 gathers in flight (64 registers) or fewer resident warps with more loads in flight each
 template <int G, int MODE, int THREADS, int MINB = 1024 / THREADS, int UNMAX = 4, bool SHARD = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
-  static_assert(lz_is_p1(MODE) || lz_is_p2(MODE), "FP32 vectors exist only inside the two Lanczos passes");
+  static_assert(MODE == LZ_P1 || lz_is_p2(MODE), "FP32 vectors exist only inside the two Lanczos passes");
   typedef Lz32Off<SHARD> OF;
   typedef typename OF::T off_t;
   if (a.done != nullptr && *a.done != 0) return;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
     s_cp[i] = (MODE == LZ_P2_PAIR && a.s_coef_prev != nullptr && i < a.m) ? a.s_coef_prev[i] : 0.0;
   }
   __syncthreads();
-  double dot[4] = {0.0, 0.0, 0.0, 0.0}, dot2[4] = {0.0, 0.0, 0.0, 0.0};
+  double dot[4] = {0.0, 0.0, 0.0, 0.0};
 
   const unsigned ldu = (unsigned)a.ld;
   const int pcl = 4 * min(g, P - 1);             // lanes beyond the active elements read a clamped (valid) element
@@ -242,10 +242,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
     lz32_gather<G, UNMAX, SHARD>(a, eo_own, p0_cur, p1_cur, o_cur, a_cur, o_cur2, a_cur2, g, gmask, Ul, acc);
     if (valid && g < P) {
       const float4 t = lz32_t(acc, s_sc[0][g], s_sc[1][g], pv);
-      if constexpr (lz_is_p1(MODE)) {
+      if constexpr (MODE == LZ_P1) {
         stg4f(Ol + eo_own, t);
         lz32_dot(dot, uo, t);
-        if constexpr (MODE == LZ_P1B) lz32_dot(dot2, t, t);
       } else {
         stg4f(Ol + eo_own, lz32_next(t, s_sc[2][g], uo));
         if constexpr (MODE != LZ_P2_SKIP) {
@@ -271,23 +270,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lz32_spmm(LzArgs32 a) {
   }
 
   __shared__ double red[(THREADS / 32) * 32 * 4];
-  if constexpr (lz_is_p1(MODE)) {
-    // fixed-order CTA reduction (pass 2 relies on pass 1's exact scalars); LZ_P1B: second slot |t|^2
+  if constexpr (MODE == LZ_P1) {
+    // fixed-order CTA reduction (pass 2 relies on pass 1's exact scalars)
     const int width = 4 * G;   // columns per row group
-    constexpr int NSLOT = (MODE == LZ_P1B) ? 2 : 1;
 #pragma unroll
-    for (int sl = 0; sl < NSLOT; ++sl) {
-      if (sl > 0) __syncthreads();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) red[(wib * RPW + sub) * width + 4 * g + q] = (sl == 0) ? dot[q] : dot2[q];
-      __syncthreads();
-      const int ngroups = wpb * RPW;
-      for (int c = threadIdx.x; c < width; c += THREADS) {
-        if (c < a.m) {
-          double s = 0.0;
-          for (int q = 0; q < ngroups; ++q) s += red[q * width + c];
-          a.partial[((int64_t)sl * gridDim.x + blockIdx.x) * a.pstride + c] = s;
-        }
+    for (int q = 0; q < 4; ++q) red[(wib * RPW + sub) * width + 4 * g + q] = dot[q];
+    __syncthreads();
+    const int ngroups = wpb * RPW;
+    for (int c = threadIdx.x; c < width; c += THREADS) {
+      if (c < a.m) {
+        double s = 0.0;
+        for (int q = 0; q < ngroups; ++q) s += red[q * width + c];
+        a.partial[(int64_t)blockIdx.x * a.pstride + c] = s;
       }
     }
   }
@@ -348,7 +342,7 @@ __global__ void __launch_bounds__(256) k_lz32_update(int64_t n, int m, int pp, i
     }
   }
   block_reduce_quads(acc, pp, m, partial + (int64_t)blockIdx.x * pstride);
-  __shared__ double tail_scratch[2 * FC_MAXCOLS + 256];
+  __shared__ double tail_scratch[FC_MAXCOLS + 256];
   lz_tail(tail, partial, pstride, m, tail_scratch);
 }
 

@@ -1185,7 +1185,7 @@ static void msl_filter_gen(H* h, int basis_slot, int c0, int nc, bool have_ritz,
   const int pp = pow2_ge(P);
   const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + (256 / pp) - 1) / (256 / pp), (int64_t)h->sms * h->lz_egrid_mult));
   const int K = cheb_degree(h->cheb_lo, h->cheb_hi, cheb_delta);
-  const int slice = getenv("FEASTCUDA_GEN_SLICE") ? atoi(getenv("FEASTCUDA_GEN_SLICE")) : 64;   // complex columns per gather launch
+  const int slice = getenv("FEASTCUDA_GEN_SLICE") ? atoi(getenv("FEASTCUDA_GEN_SLICE")) : 128;   // complex columns per gather launch (slices measured SLOWER: 2 x 48 columns 0.52 ms against 0.30 ms unsliced)
   const double* dinv = h->cheb_dinv.as<double>();
 
   // ---- device scalars (layout as in msl_filter) -------------------------------------------------------------------

@@ -370,13 +370,18 @@ def run_gpu(args):
     dom = max(share, key=share.get) if share else None
     traffic = None
     prof = ROOT / "profiles" / "ncu_summary.json"
-    if prof.exists() and dom:
+    fp32_run = st.get("lz_steps_fp32", 0) * 2 > st["lz_steps_p1"]
+    if prof.exists() and dom and world == 1:          # the captures are single-GPU launches over all 64 columns
         summ = json.loads(prof.read_text())
-        # pass 2 alternates two launch kinds (accumulating / skipping): its per-launch traffic is their average
-        traffic = summ.get("lz_p2_paired_average" if dom == "lz_p2" and "lz_p2_paired_average" in summ else dom, {}).get("dram_bytes_per_launch")
+        # pass 2 alternates two launch kinds (accumulating / skipping): its per-launch traffic is their average;
+        # the FP32-vector kernels have their own captures (r2_lz32_*)
+        fam = "lz32" if fp32_run else "lz"
+        key = {"lz_p2": fam + "_p2_paired_average", "lz_p1": "r2_lz32_p1" if fp32_run else "lz_p1",
+               "lz_upd": "r2_lz32_upd" if fp32_run else "lz_upd"}.get(dom, dom)
+        traffic = summ.get(key, {}).get("dram_bytes_per_launch")
     roofline = None
     if dom:
-        kfam = "k_lz32_spmm" if st.get("lz_steps_fp32", 0) * 2 > st["lz_steps_p1"] else "k_lz_spmm"
+        kfam = "k_lz32_spmm" if fp32_run else "k_lz_spmm"
         roofline = {"bound": "hbm", "kernel": {"lz_p1": kfam + "<LZ_P1>", "lz_p2": kfam + "<LZ_P2_PAIR|LZ_P2_SKIP> (pass 2, average launch)",
                                                "lz_upd": kfam.replace("spmm", "update")}[dom],
                     "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": traffic,

@@ -594,5 +594,6 @@ def default_engine(device=None):
 from .api import *  # noqa: E402,F401,F403  (reference-named drivers)
 from .families import *  # noqa: E402,F401,F403  (complex-symmetric and polynomial names)
 from .utils import *  # noqa: E402,F401,F403  (host-side helpers of the API surface)
+from .fixtures import *  # noqa: E402,F401,F403  (readers of the FEAST example-system files)
 from .rci import (FeastRCIState, Ref, dfeast_srci, feast_grci, feast_grcix, feast_hrci, feast_hrcix, feast_srci, feast_srcix,  # noqa: E402,F401
                   ifeast_grci, ifeast_hrci, ifeast_srci, pdfeast_srci, zfeast_grci, zfeast_hrci)

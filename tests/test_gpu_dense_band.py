@@ -164,3 +164,24 @@ def test_banded_known_answers_and_random_pencil(engine):
     X, _, _ = engine.block_solve(z, RHS, solver="direct")
     want_x = np.linalg.solve(z * np.eye(n) - Af, RHS)
     assert np.abs(X - want_x).max() < 1e-10 * np.abs(want_x).max()
+
+
+def test_fixture_files_feed_the_sparse_dense_and_banded_drivers(tmp_path):
+    """The on-disk input format of the original FEAST example systems (examples/feast/utils.jl:15-150) read by feastcuda.fixtures and
+    solved by the reference-named drivers: the KA5 / KA8 operators (runtests.jl:399-412, 605-636) written to a file first."""
+    import feastcuda as fc
+    A = fo.laplacian_1d(10)
+    fc.write_mm_coordinate(tmp_path / "lap10.mtx", A)
+    w = np.linalg.eigvalsh(A.toarray())
+    want = w[(w >= 0.5) & (w <= 3.1)]
+    Q0 = fo.seeded_subspace(10, 10, complex_storage=False)
+    rs = fc.feast_scsrev(fc.read_mm_sparse_real("lap10", data_dir=tmp_path), 0.5, 3.1, 10, fc.feastinit(), Q0=Q0, **{
+        "solver_tol": 1e-12, "solver_maxiter": 4000, "ritz_guess": True, "inner_rel": 1e-9})
+    rd = fc.feast_syev(fc.read_mm_dense_real("lap10", data_dir=tmp_path), 0.5, 3.1, 10, fc.feastinit(), Q0=Q0)
+    band, kl, ku = fc.read_banded_real("lap10", data_dir=tmp_path)
+    assert (kl, ku) == (1, 1)
+    rb = fc.feast_sbev(np.ascontiguousarray(band[:ku + 1]), ku, 0.5, 3.1, 10, fc.feastinit(), Q0=Q0)   # upper band = rows 0..ku
+    rg = fc.feast_gbev(band.astype(complex), kl, 1.8, 1.3, 10, fc.feastinit(), Q0=fo.seeded_subspace(10, 10))
+    for r in (rs, rd, rb):
+        assert r.info == 0 and r.M == len(want) and np.allclose(np.sort(r.lambda_), want, atol=1e-10) and r.res.max() < 1e-12
+    assert rg.info == 0 and rg.M == len(want) and np.allclose(np.sort(rg.lambda_.real), want, atol=1e-8)

@@ -18,6 +18,7 @@ import os
 import numpy as np
 
 from . import _lib as L
+from ._host import column_major
 from ._lib import (A, B, CSC, CSR, FILTER_REFERENCE, FILTER_TRUE, GEN, HERM, SHARD_BALANCED, SHARD_COLUMNS, SHARD_NODES,
                    SOLVER_BICGSTAB, SOLVER_DIRECT, SOLVER_MSLANCZOS, SYM, FeastCudaError, SolverOpts, Stats)
 
@@ -245,10 +246,11 @@ class Engine:
         if M.ndim != 2 or M.shape[1] != n:
             raise ValueError("Matrix must be square")
         if np.iscomplexobj(M):
-            a = np.asfortranarray(M, dtype=np.complex128)
+            a = column_major(M, np.complex128)
             self._ck(self.lib.feastcuda_set_dense_z(self.h, which, n, a.ctypes.data_as(L._dp), n, structure))
         else:
-            a = np.asfortranarray(M, dtype=np.float64)
+            # a row-major real matrix declared SYMMETRIC is its own column-major image: no host copy at all
+            a = np.ascontiguousarray(M, dtype=np.float64) if (structure == SYM and M.flags.c_contiguous) else column_major(M, np.float64)
             self._ck(self.lib.feastcuda_set_dense_d(self.h, which, n, L.dptr(a), n, structure))
         if which == A:
             self.n = n

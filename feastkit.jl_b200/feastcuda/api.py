@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
+from ._host import column_major, dense_equals_own_adjoint
 
 __all__ = [
     "feast_scsrev", "feast_scsrgv", "feast_hcsrev", "feast_hcsrgv", "feast_scsrevx", "feast_scsrgvx", "feast_hcsrevx",
@@ -29,7 +30,7 @@ def issymmetric(M):
     if sp.issparse(M):
         return (abs(M - M.T)).nnz == 0 if M.shape[0] == M.shape[1] else False
     M = np.asarray(M)
-    return M.shape[0] == M.shape[1] and np.array_equal(M, M.T)
+    return M.ndim == 2 and M.shape[0] == M.shape[1] and dense_equals_own_adjoint(M, False)
 
 
 def ishermitian(M):
@@ -37,7 +38,7 @@ def ishermitian(M):
     if sp.issparse(M):
         return (abs(M - M.conj().T)).nnz == 0 if M.shape[0] == M.shape[1] else False
     M = np.asarray(M)
-    return M.shape[0] == M.shape[1] and np.array_equal(M, M.conj().T)
+    return M.ndim == 2 and M.shape[0] == M.shape[1] and dense_equals_own_adjoint(M, True)
 
 
 M0_CAP = 128

@@ -481,6 +481,27 @@ def toeplitz_pencil(dims, eps=0.05):
     return A, B, lamA / (1 + eps * lamS)
 
 
+def band_workload(N, kb=7, c=0.3, want=40, centre=2.5):
+    """The banded line (not a BASELINE config): A = T_N (x) I_kb + I_N (x) c T_kb with the kb-index fastest -- a real symmetric
+    band matrix of order kb N and half-bandwidth kb whose eigenvalues t_i + mu_a are analytic.  The interval sits in the middle of the
+    spectrum, its ends in the widest gaps near the targets."""
+    import numpy as np
+    import scipy.sparse as sp
+    TN = sp.diags([-np.ones(N - 1), 2 * np.ones(N), -np.ones(N - 1)], [-1, 0, 1])
+    D = c * sp.diags([-np.ones(kb - 1), 2 * np.ones(kb), -np.ones(kb - 1)], [-1, 0, 1])
+    A = (sp.kron(TN, sp.identity(kb)) + sp.kron(sp.identity(N), D)).tocsc()
+    t = 2 - 2 * np.cos(np.arange(1, N + 1) * np.pi / (N + 1))
+    mu = c * (2 - 2 * np.cos(np.arange(1, kb + 1) * np.pi / (kb + 1)))
+    lam = np.sort((t[:, None] + mu[None, :]).ravel())
+    i0 = int(np.searchsorted(lam, centre))
+    widest = lambda i: max(range(i - 4, i + 5), key=lambda q: lam[q] - lam[q - 1])
+    lo, hi = widest(i0), widest(i0 + want)
+    AB = np.zeros((kb + 1, kb * N))                      # LAPACK upper band storage, diagonal in row kb (banded/feast_banded.jl:205-214)
+    for d in range(kb + 1):
+        AB[kb - d, d:] = A.diagonal(d)
+    return A, AB, lam[lo:hi], 0.5 * (lam[lo - 1] + lam[lo]), 0.5 * (lam[hi - 1] + lam[hi])
+
+
 def fp64_gemm_peak(n=8192, reps=3):
     """Denominator only: the library ZGEMM / DGEMM rate of this box (torch.matmul -> cuBLAS), TFLOP/s (real flops)."""
     import torch
@@ -554,6 +575,19 @@ def run_other_config(args):
         workload = f"configs[3]: zfeast_hcsrgv! trilinear-FEM stiffness/mass pair {dims[0]}x{dims[1]}x{dims[2]} (n={n}), complex Hermitian, M0=96, 16 nodes, lowest {want} pairs"
         flops = None
         h2d = Q0.nbytes + A.data.nbytes + A.indices.nbytes + B.data.nbytes + B.indices.nbytes
+    elif cfg == 5:
+        kb, Nb = 7, (args.n or 999999) // 7
+        Asp, AB, exact, Emin, Emax = band_workload(Nb, kb)
+        n, M0 = kb * Nb, 64
+        Q0 = rng.standard_normal((n, M0))
+        Q0 /= np.linalg.norm(Q0, axis=0)
+        solve = lambda: fc.dfeast_sbev(AB, kb, Emin, Emax, M0, fc.feastinit(), Q0=Q0)
+        check = lambda r: float(np.abs(np.sort(r.lambda_) - exact).max()) if r.M == len(exact) else None
+        workload = (f"banded path (SURVEY 8a a14/a15; not a BASELINE config): dfeast_sbev! real symmetric band n={n}, half-bandwidth {kb} "
+                    f"(T_N (x) I_7 + I_N (x) 0.3 T_7, analytic spectrum), M0=64, 8 Gauss nodes, {len(exact)} eigenvalues around 2.5 "
+                    f"(interval width {Emax - Emin:.2e}); one band LU per node (all nodes in one launch), cached across the refinement loops")
+        flops = None
+        h2d = AB.nbytes + Q0.nbytes
     else:
         dims = (args.n3 or (50, 50, 100))
         A, B, lam = toeplitz_pencil(dims)
@@ -605,17 +639,33 @@ def run_other_config(args):
     else:
         dom = max(kern, key=lambda k_: kern[k_]["avg_ms"] * kern[k_]["sampled"]) if kern else None
         roofline = None if dom is None else {"bound": "hbm", "kernel": {"lz_cheb": "k_lz_spmm<LZ_CHEB> (Chebyshev / Jacobi step of the inner solve with B)",
-                                                                          "lz_p1": "k_lz_spmm<LZ_P1> (A times the Lanczos block)"}.get(dom, dom),
+                                                                          "lz_p1": "k_lz_spmm<LZ_P1> (A times the Lanczos block)",
+                                                                          "band_lu": "k_band_lu_warp (band LU, one warp per node; n dependent steps: latency-bound)",
+                                                                          "band_solve": "k_band_solve_win (band substitutions, one warp per node x 32 columns; latency-bound)"}.get(dom, dom),
                                              "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s", "frac": kern[dom]["gbs"] / hbm, "traffic": None,
                                              "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"], "all_kernels": kern}
-    out = {"metric": f"FEAST solve eigenpairs/s, BASELINE configs[{cfg}] at full size (wall-time in ms_per_step)", "value": r.M / (ms / 1e3), "unit": UNIT,
+    cpu = None
+    if cfg == 5 and not args.no_cpu:
+        # the reference's :serial path restated (sequential node loop, one sparse LU of the band matrix per node, cached; Rayleigh-Ritz;
+        # refinement) run TO COMPLETION on the same inputs
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import feast_oracle as fo
+        t0 = time.perf_counter()
+        ro = fo.feast_hrr(Asp.astype(complex), None, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
+        sec = time.perf_counter() - t0
+        cpu = {"value": ro.M / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"the whole solve at full size, run to completion: oracle/feast_oracle.py feast_hrr (true filter), {sec:.1f} s, "
+                         f"info={ro.info}, M={ro.M}, loops={ro.loop}, epsout={ro.epsout:.2e}",
+               "max_eig_diff_gpu_vs_cpu": float(np.abs(np.sort(ro.lambda_.real) - np.sort(r.lambda_)).max()) if ro.M == r.M else None}
+    name = "banded path, n=10^6 k=7" if cfg == 5 else f"BASELINE configs[{cfg}] at full size"
+    out = {"metric": f"FEAST solve eigenpairs/s, {name} (wall-time in ms_per_step)", "value": r.M / (ms / 1e3), "unit": UNIT,
            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "n": int(n), "M0": M0},
            "result": {"M": r.M, "expected_M": int(len(exact)), "info": r.info, "epsout": r.epsout, "loops": r.loop, "max_residual": float(r.res.max()) if r.M else None,
                       "max_eig_err_vs_analytic": check(r), "lanczos_steps": st["lz_steps_p1"], "inner_solve_degree": st.get("cheb_degree", 0)},
            "e2e": {"value": r.M / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(r.q.nbytes + r.lambda_.nbytes + r.res.nbytes),
                    "note": "timed through the reference-named API with host matrices and host Q0 (operator upload included); device-resident time: result of feastcuda_stats.ms_total below"},
-           "device_ms_total": st["ms_total"], "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": None}
+           "device_ms_total": st["ms_total"], "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(out))
 
 
@@ -633,8 +683,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mixed", action="store_true", help="skip the secondary leg with the other precision setting (profiling runs)")
     ap.add_argument("--fp64", action="store_true", help="headline with FP64 Krylov vectors (fpm[42] = 0) instead of the reference's default fpm[42] = 1")
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4], help="index into BASELINE.json's configs (2 = the headline workload)")
-    ap.add_argument("--n", type=int, default=0, help="--config 1: matrix order (default 8192)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="index into BASELINE.json's configs (2 = the headline workload); 5 = the banded path (n = 10^6, k = 7)")
+    ap.add_argument("--n", type=int, default=0, help="--config 1: matrix order (default 8192); --config 5: matrix order (default 999999)")
     ap.add_argument("--n3", type=int, nargs=3, default=None, help="--config 3|4: grid (default: the full size)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -643,7 +693,7 @@ def main():
         if "--steps" not in sys.argv:
             args.steps = 1
         if "--warmup" not in sys.argv:
-            args.warmup = 1 if args.config == 1 else 0
+            args.warmup = 1 if args.config in (1, 5) else 0
         run_other_config(args)
     else:
         run_gpu(args)

@@ -302,42 +302,143 @@ void band_prepare(H* h) {
   release_factor_cache(h);
 }
 
-bool band_node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X) {
-  const int n = (int)h->n;
-  const int ka = (int)h->bandA.k, kb = h->has_b ? (int)h->bandB.k : 0;
-  const int k = std::max(ka, kb);
-  const int ldf = 3 * k + 1;
-  const int64_t ld = h->ws_ld;
+// 2 (default): batched-over-nodes warp LU + register-window solve; 1: the one-CTA LU / thread-per-column solve of round 1
+static int band_impl() {
+  static const int v = getenv("FEASTCUDA_BAND_IMPL") ? atoi(getenv("FEASTCUDA_BAND_IMPL")) : 2;
+  return v;
+}
+
+static int band_halfwidth(H* h) { return std::max((int)h->bandA.k, h->has_b ? (int)h->bandB.k : 0); }
+
+static void band_ensure_node(H* h, int node) {
   if ((int)h->lu_cache.size() <= node) {
     h->lu_cache.resize(node + 1);
     h->piv_cache.resize(node + 1);
     h->lu_shift.resize(node + 1, zc(NAN, NAN));
   }
-  if (!(h->lu_shift[node] == z)) {
+}
+
+// factor (z_q B - A) for every node of [first, first + count) whose cached shift differs; all of them in ONE LU launch
+static bool band_factor_range(H* h, int first, int count, const zc* shifts) {
+  const int n = (int)h->n;
+  const int ka = (int)h->bandA.k, kb = h->has_b ? (int)h->bandB.k : 0;
+  const int k = std::max(ka, kb);
+  const int ldf = 3 * k + 1;
+  band_ensure_node(h, first + count - 1);
+  std::vector<int> todo;
+  for (int q = 0; q < count; ++q)
+    if (!(h->lu_shift[first + q] == shifts[q])) todo.push_back(q);
+  if (todo.empty()) return true;
+  const bool warp_lu = band_impl() >= 2 && k <= FC_BAND_LU_MAXK;
+  for (int q : todo) {
+    const int node = first + q;
+    h->lu_shift[node] = zc(NAN, NAN);
     h->lu_cache[node].ensure((size_t)ldf * n * sizeof(zd));
     h->piv_cache[node].ensure((size_t)(n + 1) * sizeof(int));
-    zd* F = h->lu_cache[node].as<zd>();
-    int* ipiv = h->piv_cache[node].as<int>();
-    int* dinfo = ipiv + n;
-    FC_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), h->stream));
+    FC_CUDA(cudaMemsetAsync(h->piv_cache[node].as<int>() + n, 0, sizeof(int), h->stream));
     const int64_t total = (int64_t)ldf * n;
     k_band_shift<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 8)), 256, 0, h->stream>>>(
-        n, k, ka, kb, h->dBandA.as<zd>(), h->has_b ? h->dBandB.as<zd>() : nullptr, mk<double>(z.real(), z.imag()), F);
+        n, k, ka, kb, h->dBandA.as<zd>(), h->has_b ? h->dBandB.as<zd>() : nullptr, mk<double>(shifts[q].real(), shifts[q].imag()),
+        h->lu_cache[node].as<zd>());
     launched(h);
-    k_band_lu<<<1, 256, 0, h->stream>>>(n, k, F, ipiv, dinfo);
-    launched(h);
-    int info = 0;
-    FC_CUDA(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    FC_CUDA(cudaStreamSynchronize(h->stream));
-    if (info != 0) { h->lu_shift[node] = zc(NAN, NAN); return false; }
-    h->lu_shift[node] = z;
+    if (!warp_lu) {
+      k_band_lu<<<1, 256, 0, h->stream>>>(n, k, h->lu_cache[node].as<zd>(), h->piv_cache[node].as<int>(), h->piv_cache[node].as<int>() + n);
+      launched(h);
+    }
   }
-  const zd* F = h->lu_cache[node].as<zd>();
-  const int* ipiv = h->piv_cache[node].as<int>();
-  FC_CUDA(cudaMemcpy2DAsync(X, (size_t)ld * sizeof(zd), RHS, (size_t)ld * sizeof(zd), (size_t)m * sizeof(zd), (size_t)n,
-                            cudaMemcpyDeviceToDevice, h->stream));
-  k_band_solve<<<(m + 63) / 64, 64, 0, h->stream>>>(n, k, F, ipiv, m, ld, X);
+  if (warp_lu) {
+    for (size_t t0 = 0; t0 < todo.size(); t0 += FC_BAND_BATCH) {
+      const int cnt = (int)std::min<size_t>(FC_BAND_BATCH, todo.size() - t0);
+      BandBatch bb;
+      memset(&bb, 0, sizeof(bb));
+      for (int t = 0; t < cnt; ++t) {
+        bb.F[t] = h->lu_cache[first + todo[t0 + t]].as<zd>();
+        bb.ipiv[t] = h->piv_cache[first + todo[t0 + t]].as<int>();
+      }
+      const int ev = sample_begin(h, FEASTCUDA_KERN_BAND_LU);
+      k_band_lu_warp<<<cnt, 32, 0, h->stream>>>(n, k, bb);
+      launched(h);
+      sample_end(h, ev);
+      // algorithmic bytes of the launch: every factor is read once and written once (the 5 KB window of a step lives in L1), pivots written
+      h->stats.bytes_kern[FEASTCUDA_KERN_BAND_LU] = (double)cnt * (2.0 * ldf * (double)n * sizeof(zd) + 4.0 * n);
+    }
+  }
+  std::vector<int> info(todo.size(), 0);
+  for (size_t t = 0; t < todo.size(); ++t)
+    FC_CUDA(cudaMemcpyAsync(&info[t], h->piv_cache[first + todo[t]].as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  FC_CUDA(cudaStreamSynchronize(h->stream));
+  bool all_ok = true;
+  for (size_t t = 0; t < todo.size(); ++t) {
+    if (info[t] != 0) all_ok = false;                       // exactly singular shifted matrix -> LAPACK info > 0 (banded:108-112)
+    else h->lu_shift[first + todo[t]] = shifts[todo[t]];
+  }
+  return all_ok;
+}
+
+template <int K>
+static void band_launch_win(H* h, int n, int k, const BandBatch& bb, int cnt, int m, int64_t ld, const zd* RHS, zd* X, int64_t xbatch) {
+  k_band_solve_win<K><<<dim3((m + 31) / 32, cnt), 32, 0, h->stream>>>(n, k, bb, m, ld, RHS, X, xbatch);
   launched(h);
+}
+
+// X_q = (z_q B - A)^-1 RHS for the node range [first, first + count) with cached factors; X_q = Xbase + q * xbatch (row-major n x ld)
+static void band_solve_range(H* h, int first, int count, int m, const zd* RHS, zd* Xbase, int64_t xbatch) {
+  const int n = (int)h->n;
+  const int k = band_halfwidth(h);
+  const int ldf = 3 * k + 1;
+  const int64_t ld = h->ws_ld;
+  if (band_impl() >= 2 && k <= FC_BAND_WIN_MAXK) {
+    FC_REQUIRE(RHS != Xbase, "band solve: the solution block must not alias the right-hand side");
+    for (int q0 = 0; q0 < count; q0 += FC_BAND_BATCH) {
+      const int cnt = std::min(FC_BAND_BATCH, count - q0);
+      BandBatch bb;
+      memset(&bb, 0, sizeof(bb));
+      for (int t = 0; t < cnt; ++t) {
+        bb.F[t] = h->lu_cache[first + q0 + t].as<zd>();
+        bb.ipiv[t] = h->piv_cache[first + q0 + t].as<int>();
+      }
+      zd* X = Xbase + (int64_t)q0 * xbatch;
+      const int ev = sample_begin(h, FEASTCUDA_KERN_BAND_SOLVE);
+      if (k <= 2) band_launch_win<2>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else if (k <= 4) band_launch_win<4>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else if (k <= 8) band_launch_win<8>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else band_launch_win<16>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      sample_end(h, ev);
+      // per node: the factor and the pivots are read by both sweeps of every 32-column group, x moves four times (RHS -> y -> x)
+      h->stats.bytes_kern[FEASTCUDA_KERN_BAND_SOLVE] =
+          (double)cnt * ((double)((m + 31) / 32) * (2.0 * ldf * (double)n * sizeof(zd) + 4.0 * n) + 4.0 * (double)n * m * sizeof(zd));
+    }
+    return;
+  }
+  for (int q = 0; q < count; ++q) {
+    zd* X = Xbase + (int64_t)q * xbatch;
+    FC_CUDA(cudaMemcpy2DAsync(X, (size_t)ld * sizeof(zd), RHS, (size_t)ld * sizeof(zd), (size_t)m * sizeof(zd), (size_t)n,
+                              cudaMemcpyDeviceToDevice, h->stream));
+    k_band_solve<<<(m + 63) / 64, 64, 0, h->stream>>>(n, k, h->lu_cache[first + q].as<zd>(), h->piv_cache[first + q].as<int>(), m, ld, X);
+    launched(h);
+  }
+}
+
+bool band_node_solve(H* h, int node, zc z, int m, const zd* RHS, zd* X) {
+  if (!band_factor_range(h, node, 1, &z)) return false;
+  band_solve_range(h, node, 1, m, RHS, X, 0);
+  return true;
+}
+
+// all nodes [first, first+count) of a sweep at once: one LU launch for the nodes that need a factor, one solve launch for all
+// (node, column group) pairs; solutions land in the shared solution pool (slot q -> node first+q).  Returns false without touching
+// anything when the pool would not fit (the caller then solves node by node).
+bool band_batch_fits(H* h, int count) {
+  return band_impl() >= 2 && (double)count * (double)h->n * (double)h->ws_ld * sizeof(zd) <= 32.0 * 1073741824.0;
+}
+
+bool band_batch_solve(H* h, int first, int count, const zc* shifts, int m, const zd* RHS, zd** Xpool, int64_t* xbatch) {
+  if (!band_factor_range(h, first, count, shifts)) return false;
+  const int64_t xb = (int64_t)h->n * h->ws_ld;
+  h->dense_xpool.ensure((size_t)count * xb * sizeof(zd));
+  band_solve_range(h, first, count, m, RHS, h->dense_xpool.as<zd>(), xb);
+  *Xpool = h->dense_xpool.as<zd>();
+  *xbatch = xb;
   return true;
 }
 

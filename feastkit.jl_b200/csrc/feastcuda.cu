@@ -245,7 +245,7 @@ static void spmm_dispatch(H* h, SpmmArgs<double, TA>& a, int grid) {
 
 // ---- sampled kernel timings: CUDA events on the launching stream around selected launches ---------------------
 // sample_begin returns a slot (or -1 when the pool is exhausted); `tag` lets the caller discard samples later
-static int sample_begin(H* h, int kind, int tag = 0) {
+int feastcuda::sample_begin(H* h, int kind, int tag) {
   if (h->ev_used + 2 > 512) return -1;
   while (h->ev_pool.size() < h->ev_used + 2) {
     cudaEvent_t e;
@@ -258,7 +258,7 @@ static int sample_begin(H* h, int kind, int tag = 0) {
   h->ev_pending.push_back({kind, tag, a, b});
   return (int)h->ev_pending.size() - 1;
 }
-static void sample_end(H* h, int slot) {
+void feastcuda::sample_end(H* h, int slot) {
   if (slot >= 0) FC_CUDA(cudaEventRecord(h->ev_pool[h->ev_pending[slot].b], h->stream));
 }
 // the stream must be idle; samples whose tag is >= tag_limit are dropped (launches that ran as no-ops)
@@ -2136,17 +2136,19 @@ static void eig_residual_norms(H* h, int m, const zd* X, const std::vector<zc>& 
   }
 }
 
-// dense operators: every node of the sweep goes through the batched LU / substitution kernels together
+// dense and banded operators: every node of the sweep goes through the batched LU / substitution kernels together
 static bool dense_items_batched(H* h, std::vector<WorkItem>& items, int ne, int active, const zc* Zne, const zc* Wne, double wfac,
                                 const zd* rhs, bool* failed) {
-  if (h->kind != OP_DENSE || items.empty()) return false;
+  if ((h->kind != OP_DENSE && h->kind != OP_BAND) || items.empty()) return false;
   for (size_t q = 0; q < items.size(); ++q)
     if (items[q].c0 != 0 || items[q].nc != active || items[q].node != items[0].node + (int)q) return false;
+  if (h->kind == OP_BAND && !band_batch_fits(h, (int)items.size())) return false;
   std::vector<zc> zs;
   for (const WorkItem& it : items) zs.push_back(Zne[it.node]);
   zd* Xp = nullptr;
   int64_t xb = 0;
-  const bool ok = dense_batch_solve(h, ne, items[0].node, (int)items.size(), zs.data(), active, rhs, &Xp, &xb);
+  const bool ok = (h->kind == OP_DENSE) ? dense_batch_solve(h, ne, items[0].node, (int)items.size(), zs.data(), active, rhs, &Xp, &xb)
+                                        : band_batch_solve(h, items[0].node, (int)items.size(), zs.data(), active, rhs, &Xp, &xb);
   h->stats.node_solves += (int64_t)items.size();
   if (!ok) *failed = true;
   else
@@ -2312,6 +2314,7 @@ static void run_interval(H* h, double Emin, double Emax, int m0, int64_t* fpm, c
       axpby_cols(h, it.nc, 2.0 * Wne[it.node], 1.0, X, blk(h, BS_ACC) + it.c0);
     }
     sync(h);
+    drain_events(h);    // samples of the direct (band) kernels
     h->stats.ms_solve += tsolve.ms();
     if (h->nranks > 1) {
       // one exchange per refinement loop: MPI.Allreduce(Q_proj), parallel/feast_mpi.jl:119,341,858
@@ -2531,6 +2534,7 @@ static void run_contour(H* h, zc Emid, double r, int m0, int64_t* fpm, const zc*
       axpby_cols(h, it.nc, Wne[it.node], 1.0, X, blk(h, BS_ACC) + it.c0);   // q += w_e Y (kernel:762-766)
     }
     sync(h);
+    drain_events(h);    // samples of the direct (band) kernels
     h->stats.ms_solve += tsolve.ms();
     if (h->nranks > 1) {
       allreduce_block(h, blk(h, BS_ACC), (int64_t)n * h->ws_ld);

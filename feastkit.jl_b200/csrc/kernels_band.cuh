@@ -116,6 +116,202 @@ __global__ void __launch_bounds__(64) k_band_solve(int n, int k, const zdb* __re
   }
 }
 
+// =====================================================================================================
+// Batched-over-nodes variants (round 2; the kernels above remain for wide bands and as the A/B reference, FEASTCUDA_BAND_IMPL=1).
+// A band factorisation is n dependent steps, so the parallelism is ACROSS quadrature nodes and right-hand-side columns: every node of a
+// sweep is factored by its own warp in ONE launch, and all (node, 32-column group) pairs are solved by their own warp in ONE launch.
+// CPU restatement: oracle/feast_port.py band_lu / band_solve_window.
+// =====================================================================================================
+constexpr int FC_BAND_BATCH = 32;      // nodes per launch (pointers travel by value in the launch parameters)
+constexpr int FC_BAND_LU_MAXK = 32;    // widest half-bandwidth served by the warp LU
+constexpr int FC_BAND_WIN_MAXK = 16;   // widest half-bandwidth served by the register-window solve
+
+struct BandBatch {
+  zdb* F[FC_BAND_BATCH];      // factor (3k+1) x n of node q
+  int* ipiv[FC_BAND_BATCH];   // n pivots + the info word
+};
+
+// zgbtf2 (kl = ku = k) with ONE WARP per node: no block barriers, the pivot search is a shuffle butterfly, the (km x (ju - j)) rank-1
+// update is spread over the lanes; the window a step touches (2k + 1 columns of 3k + 1 rows: 5 KB at k = 7) lives in L1.
+__global__ void __launch_bounds__(32) k_band_lu_warp(int n, int k, BandBatch bb) {
+  zdb* F = bb.F[blockIdx.x];
+  int* ipiv = bb.ipiv[blockIdx.x];
+  const int ldf = 3 * k + 1, kv = 2 * k, lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  int ju = 0, info = 0;
+  for (int j = 0; j < n; ++j) {
+    const int km = min(k, n - 1 - j);
+    zdb* colj = F + (int64_t)j * ldf + kv;   // colj[i] = A[j+i, j]
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = lane; i <= km; i += 32) {
+      const zdb v = colj[i];
+      const double a = fabs(v.x) + fabs(v.y);
+      if (a > best) { best = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const int jp = (best < 0.0) ? 0 : bi;     // a column of NaNs: no candidate, flagged below
+    if (lane == 0) ipiv[j] = j + jp;
+    ju = max(ju, min(j + k + jp, n - 1));
+    if (!(best > 0.0)) {                        // exactly singular (zgbtf2: info = j, the column is skipped)
+      if (info == 0) info = j + 1;
+      continue;
+    }
+    if (jp != 0) {
+      for (int c = j + lane; c <= ju; c += 32) {   // swap rows j and j+jp over the columns j..ju
+        zdb* e0 = F + (int64_t)c * ldf + (kv + j - c);
+        const zdb t = e0[0];
+        e0[0] = e0[jp];
+        e0[jp] = t;
+      }
+      __syncwarp();
+    }
+    const zdb inv = mk<double>(1.0, 0.0) / colj[0];
+    for (int i = 1 + lane; i <= km; i += 32) colj[i] = colj[i] * inv;
+    __syncwarp();
+    const int nc = ju - j;
+    for (int e = lane; e < nc * km; e += 32) {
+      const int cc = e / km + 1, i = e % km + 1;       // column j+cc, row j+i
+      zdb* colc = F + (int64_t)(j + cc) * ldf + (kv - cc);   // colc[i] = A[j+i, j+cc]
+      colc[i] = colc[i] - colj[i] * colc[0];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) ipiv[n] = info;
+}
+
+__device__ __forceinline__ void band_cp16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void band_cp4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void band_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void band_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void band_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// w -= a * b
+__device__ __forceinline__ void band_fnma(zdb& w, const zdb a, const zdb b) {
+  w.x = fma(-a.x, b.x, w.x); w.x = fma(a.y, b.y, w.x);
+  w.y = fma(-a.x, b.y, w.y); w.y = fma(-a.y, b.x, w.y);
+}
+
+// zgbtrs (no transpose) for all nodes of a sweep: one warp per (node, group of 32 right-hand-side columns), one thread per column.
+// The rows a step touches slide through a REGISTER window (K+1 values forward, 2K+1 backward; K >= k is the compile-time size), so x
+// moves once per row and sweep: read RHS -> store y, read y -> store x.  Factor columns, pivots and the rows entering the window are
+// staged CH steps ahead by cp.async into a double-buffered, warp-private shared-memory ring (no block barriers; a chunk of CH steps
+// is longer than the HBM latency).  X must not alias RHS.  X_q = X + q * xbatch.
+template <int K>
+__global__ void __launch_bounds__(32) k_band_solve_win(int n, int k, BandBatch bb, int m, int64_t ld, const zdb* __restrict__ RHS,
+                                                       zdb* __restrict__ X, int64_t xbatch) {
+  constexpr int CH = 16, LDFMAX = 3 * K + 1;
+  __shared__ __align__(16) zdb sF[2][CH * LDFMAX];
+  __shared__ __align__(16) zdb sX[2][CH * 32];
+  __shared__ int sP[2][CH];
+  const int lane = threadIdx.x, node = blockIdx.y;
+  const int c = blockIdx.x * 32 + lane;
+  const bool act = c < m;
+  const int cr = act ? c : (m - 1);             // idle lanes shadow the last column (loads only)
+  const zdb* F = bb.F[node];
+  const int* ipiv = bb.ipiv[node];
+  const zdb* b = RHS + cr;
+  zdb* x = X + (int64_t)node * xbatch + cr;
+  const int ldf = 3 * k + 1, kv = 2 * k;
+  const int nch = (n + CH - 1) / CH;
+
+  // ---------------- forward: L y = P b ----------------
+  auto stage_fwd = [&](int ch, int buf) {
+    const int j0 = ch * CH, cnt = min(CH, n - j0);
+    const zdb* src = F + (int64_t)j0 * ldf;
+    for (int e = lane; e < cnt * ldf; e += 32) band_cp16(&sF[buf][e], src + e);
+    if (lane < cnt) band_cp4(&sP[buf][lane], ipiv + j0 + lane);
+    for (int s = 0; s < cnt; ++s) {
+      const int row = j0 + s + 1 + K;            // enters the window at the end of step j0 + s
+      if (row < n) band_cp16(&sX[buf][s * 32 + lane], b + (int64_t)row * ld);
+    }
+  };
+  zdb w[K + 1];
+#pragma unroll
+  for (int i = 0; i <= K; ++i) w[i] = (i < n) ? b[(int64_t)i * ld] : czero<double>();
+  stage_fwd(0, 0);
+  band_commit();
+  for (int ch = 0; ch < nch; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nch) stage_fwd(ch + 1, buf ^ 1);
+    band_commit();
+    band_wait1();
+    __syncwarp();
+    const int j0 = ch * CH, cnt = min(CH, n - j0);
+    for (int s = 0; s < cnt; ++s) {
+      const int j = j0 + s;
+      const zdb* Lc = &sF[buf][s * ldf + kv];    // Lc[i] = multiplier of row j+i
+      const int p = sP[buf][s] - j;
+      if (p != 0) {
+        const zdb t = w[0];
+#pragma unroll
+        for (int i = 1; i <= K; ++i)
+          if (i == p) { w[0] = w[i]; w[i] = t; }
+      }
+      const zdb xj = w[0];
+      if (act) x[(int64_t)j * ld] = xj;
+#pragma unroll
+      for (int i = 1; i <= K; ++i)
+        if (i <= k) band_fnma(w[i], Lc[i], xj);
+#pragma unroll
+      for (int i = 1; i <= K; ++i) w[i - 1] = w[i];
+      w[K] = (j + 1 + K < n) ? sX[buf][s * 32 + lane] : czero<double>();
+    }
+    __syncwarp();
+  }
+  band_wait0();
+  __threadfence_block();
+  __syncwarp();
+
+  // ---------------- backward: U x = y ----------------
+  auto stage_bwd = [&](int ch, int buf) {
+    const int jhi = n - 1 - ch * CH, jlo = max(0, jhi - CH + 1), cnt = jhi - jlo + 1;
+    const zdb* src = F + (int64_t)jlo * ldf;
+    for (int e = lane; e < cnt * ldf; e += 32) band_cp16(&sF[buf][e], src + e);
+    for (int s = 0; s < cnt; ++s) {
+      const int row = jhi - s - 1 - 2 * K;       // enters the window at the end of step jhi - s
+      if (row >= 0) band_cp16(&sX[buf][s * 32 + lane], x + (int64_t)row * ld);
+    }
+  };
+  zdb v[2 * K + 1];
+#pragma unroll
+  for (int d = 0; d <= 2 * K; ++d) v[d] = (n - 1 - d >= 0) ? x[(int64_t)(n - 1 - d) * ld] : czero<double>();
+  stage_bwd(0, 0);
+  band_commit();
+  for (int ch = 0; ch < nch; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nch) stage_bwd(ch + 1, buf ^ 1);
+    band_commit();
+    band_wait1();
+    __syncwarp();
+    const int jhi = n - 1 - ch * CH, jlo = max(0, jhi - CH + 1);
+    for (int s = 0; s <= jhi - jlo; ++s) {
+      const int j = jhi - s;
+      const zdb* Uc = &sF[buf][(j - jlo) * ldf];  // Uc[kv - d] = U[j-d, j]
+      const zdb xj = v[0] / Uc[kv];
+      if (act) x[(int64_t)j * ld] = xj;
+#pragma unroll
+      for (int d = 1; d <= 2 * K; ++d)
+        if (d <= kv) band_fnma(v[d], Uc[kv - d], xj);
+#pragma unroll
+      for (int d = 1; d <= 2 * K; ++d) v[d - 1] = v[d];
+      v[2 * K] = (j - 1 - 2 * K >= 0) ? sX[buf][s * 32 + lane] : czero<double>();
+    }
+    __syncwarp();
+  }
+  band_wait0();
+}
+
 // Y = A X for a general band matrix (2k+1) x n, row-major blocks
 __global__ void __launch_bounds__(256) k_band_apply(int n, int k, const zdb* __restrict__ AB, int m, int64_t ld,
                                                     const zdb* __restrict__ X, zdb* __restrict__ Y) {

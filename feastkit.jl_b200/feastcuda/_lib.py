@@ -16,7 +16,7 @@ A, B = 0, 1
 CSR, CSC = 0, 1
 SYM, HERM, GEN = 0, 1, 2
 SOLVER_DIRECT, SOLVER_BICGSTAB, SOLVER_MSLANCZOS = 0, 1, 2
-KERN_NAMES = ("spmm_z", "lz_p1", "lz_upd", "lz_p2", "lz_res", "lz_cheb", "k6", "k7")
+KERN_NAMES = ("spmm_z", "lz_p1", "lz_upd", "lz_p2", "lz_res", "lz_cheb", "band_lu", "band_solve")
 FILTER_REFERENCE, FILTER_TRUE = 0, 1
 SHARD_NODES, SHARD_COLUMNS, SHARD_BALANCED = 0, 1, 2      # "rows" is a mode of the handle (feastcuda_set_row_sharding)
 

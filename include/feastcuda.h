@@ -101,7 +101,9 @@ enum { FEASTCUDA_KERN_SPMM_Z = 0,   /* complex shifted SpMM (BiCGStab)          
        FEASTCUDA_KERN_LZ_UPD = 2,   /* Lanczos pass-1 vector update + norm         */
        FEASTCUDA_KERN_LZ_P2 = 3,    /* Lanczos pass-2 fused SpMM + accumulate      */
        FEASTCUDA_KERN_LZ_RES = 4,   /* Ritz-residual start block                   */
-       FEASTCUDA_KERN_LZ_CHEB = 5 };/* one Chebyshev step of the inner solve with B (generalized Lanczos filter) */
+       FEASTCUDA_KERN_LZ_CHEB = 5,  /* one Chebyshev step of the inner solve with B (generalized Lanczos filter) */
+       FEASTCUDA_KERN_BAND_LU = 6,  /* band LU of every node that needs a factor (one launch)                     */
+       FEASTCUDA_KERN_BAND_SOLVE = 7 };/* band forward/backward substitution of all nodes x columns (one launch)  */
 
 /* ---- lifetime --------------------------------------------------------------------------------- */
 int feastcuda_create(feastcuda_handle* h, int device);

@@ -1295,3 +1295,95 @@ def feast_general_mstwosided(A, B, Emid, r, M0, fpm, Q0, inner_rel=1e-3, inner_m
     lam_out, q_out, res_out = lam[:M_found].copy(), X[:, :M_found].copy(), res[:M_found].copy()
     fo.feast_sort_general(lam_out, q_out, res_out, M_found)
     return fo.FeastResult(lam_out, q_out, M_found, res_out, info, epsout, loop_count, stats)
+
+
+# =====================================================================================================================
+# banded direct solves: port of csrc/kernels_band.cuh (k_band_shift, k_band_lu_warp, k_band_solve_win)
+# =====================================================================================================================
+def band_shift(AB, BB, z, ka, kb):
+    """F = z B - A in the factor layout of the engine: (3k+1) x n, k = max(ka, kb), entry (i, j) at F[2k + i - j, j], the top k rows zero
+    (fill-in of the pivoted factorisation); rows that fall outside the matrix are zero.  AB / BB: general band (2k+1) x n, diagonal in
+    row k (BB None: B = I).  Replaces fill_shifted_banded! (banded/feast_banded.jl:216-237, 273-296, 511-559)."""
+    n = AB.shape[1]
+    k = max(ka, kb if BB is not None else 0)
+    F = np.zeros((3 * k + 1, n), dtype=complex)
+    for j in range(n):
+        for i in range(max(0, j - k), min(n - 1, j + k) + 1):
+            d = i - j
+            v = 0j
+            if -ka <= d <= ka:
+                v -= AB[ka + d, j]
+            if BB is not None:
+                if -kb <= d <= kb:
+                    v += z * BB[kb + d, j]
+            elif d == 0:
+                v += z
+            F[2 * k + d, j] = v
+    return F, k
+
+
+def band_lu(F, k):
+    """Unblocked band LU with partial pivoting (LAPACK zgbtf2, kl = ku = k) in place; returns (ipiv 0-based, info).  The CUDA kernel runs
+    exactly these steps with one warp per quadrature node: pivot = first entry of largest |re| + |im| in the column, row swap over the
+    columns j..ju, scaling, rank-1 update of the (km x (ju - j)) window."""
+    ldf, n = F.shape
+    kv = 2 * k
+    ipiv = np.zeros(n, dtype=np.int64)
+    ju, info = 0, 0
+    for j in range(n):
+        km = min(k, n - 1 - j)
+        col = F[kv:kv + km + 1, j]
+        mag = np.abs(col.real) + np.abs(col.imag)
+        jp = int(np.argmax(mag))                      # first maximum
+        ipiv[j] = j + jp
+        ju = max(ju, min(j + k + jp, n - 1))
+        if not mag[jp] > 0.0:
+            info = info or j + 1
+            continue
+        if jp:
+            for c in range(j, ju + 1):
+                r0 = kv + j - c
+                F[r0, c], F[r0 + jp, c] = F[r0 + jp, c], F[r0, c]
+        F[kv + 1:kv + km + 1, j] /= F[kv, j]
+        for c in range(j + 1, ju + 1):
+            r0 = kv + j - c                           # row of A[j, c] in column c
+            F[r0 + 1:r0 + km + 1, c] -= F[kv + 1:kv + km + 1, j] * F[r0, c]
+    return ipiv, info
+
+
+def band_solve_window(F, ipiv, k, K, rhs):
+    """x = (L U)^-1 P rhs for ONE right-hand-side column the way k_band_solve_win<K> does it: the rows a step touches live in a window
+    (K + 1 values in the forward sweep, 2K + 1 in the backward sweep, K >= k a compile-time size on the GPU) that slides by one row per
+    step -- one load and one store of x per row and sweep; multipliers beyond the bandwidth are skipped by the predicate i <= k, rows
+    outside the matrix carry zero factors.  LAPACK zgbtrs (banded/feast_banded.jl:141, 683)."""
+    n = F.shape[1]
+    kv = 2 * k
+    assert K >= k
+    y = np.zeros(n, dtype=complex)
+    w = np.zeros(K + 1, dtype=complex)
+    w[:min(K + 1, n)] = rhs[:min(K + 1, n)]
+    for j in range(n):
+        p = int(ipiv[j]) - j
+        if p:
+            w[0], w[p] = w[p], w[0]
+        xj = w[0]
+        y[j] = xj
+        for i in range(1, K + 1):
+            if i <= k:
+                w[i] -= F[kv + i, j] * xj
+        w[:K] = w[1:].copy()
+        w[K] = rhs[j + 1 + K] if j + 1 + K < n else 0.0
+    x = np.zeros(n, dtype=complex)
+    v = np.zeros(2 * K + 1, dtype=complex)
+    for d in range(2 * K + 1):
+        if n - 1 - d >= 0:
+            v[d] = y[n - 1 - d]
+    for j in range(n - 1, -1, -1):
+        xj = v[0] / F[kv, j]
+        x[j] = xj
+        for d in range(1, 2 * K + 1):
+            if d <= kv:
+                v[d] -= F[kv - d, j] * xj
+        v[:2 * K] = v[1:].copy()
+        v[2 * K] = y[j - 1 - 2 * K] if j - 1 - 2 * K >= 0 else 0.0
+    return x

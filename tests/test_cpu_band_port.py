@@ -1,0 +1,52 @@
+"""CPU test of the band-kernel restatement (oracle/feast_port.py band_shift / band_lu / band_solve_window = csrc/kernels_band.cuh
+k_band_shift / k_band_lu_warp / k_band_solve_win) against LAPACK's zgbtrf / zgbtrs (banded/feast_banded.jl:108,141,678,683)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import feast_port as fp
+
+
+def _general_band(rng, n, k):
+    AB = np.zeros((2 * k + 1, n), dtype=complex)
+    Af = np.zeros((n, n), dtype=complex)
+    for j in range(n):
+        for i in range(max(0, j - k), min(n - 1, j + k) + 1):
+            AB[k + i - j, j] = Af[i, j] = rng.standard_normal() + 1j * rng.standard_normal()
+    return AB, Af
+
+
+@pytest.mark.parametrize("n,ka,kb,K", [(1, 0, 0, 2), (2, 1, 0, 2), (5, 1, 1, 2), (9, 3, 2, 4), (40, 7, 2, 8), (33, 7, 7, 16), (20, 2, 5, 8),
+                                       (12, 4, 0, 4), (70, 9, 3, 16)])
+def test_band_factor_layout_pivots_and_window_solve_match_lapack(n, ka, kb, K):
+    rng = np.random.default_rng(100 * n + ka)
+    AB, Af = _general_band(rng, n, ka)
+    BB, Bf = _general_band(rng, n, kb)
+    z = 0.3 + 0.2j
+    for with_b in (True, False):
+        F, k = fp.band_shift(AB, BB if with_b else None, z, ka, kb)
+        S = z * (Bf if with_b else np.eye(n)) - Af
+        assert k == (max(ka, kb) if with_b else ka) and F.shape == (3 * k + 1, n)
+        assert not F[:k].any()                                               # fill-in rows start at zero
+        for j in range(n):
+            for i in range(max(0, j - k), min(n - 1, j + k) + 1):
+                assert abs(F[2 * k + i - j, j] - S[i, j]) < 1e-14
+        lu, piv, info_l = sla.lapack.zgbtrf(F.copy(), k, k)
+        ipiv, info = fp.band_lu(F, k)
+        assert info == info_l == 0
+        assert np.array_equal(ipiv, piv) or np.array_equal(ipiv + 1, piv)    # same pivot rows as LAPACK (0- or 1-based wrapper)
+        assert np.abs(lu - F).max() < 1e-12 * max(1.0, np.abs(lu).max())
+        for Kw in sorted({max(K, k), max(2 * K, k)}):                        # a window wider than the band changes nothing
+            b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+            x = fp.band_solve_window(F, ipiv, k, Kw, b)
+            want = np.linalg.solve(S, b)
+            assert np.abs(x - want).max() < 1e-10 * np.abs(want).max()
+
+
+def test_band_lu_reports_the_first_zero_pivot_like_zgbtf2():
+    AB = np.zeros((3, 4), dtype=complex)
+    AB[1] = [1.0, 0.0, 2.0, 3.0]          # diagonal with a zero, no off-diagonals: z = 0 -> -A singular in column 2
+    F, k = fp.band_shift(AB, None, 0.0, 1, 0)
+    lu, piv, info_l = sla.lapack.zgbtrf(F.copy(), 1, 1)
+    _, info = fp.band_lu(F, k)
+    assert info == info_l == 2

@@ -185,3 +185,39 @@ def test_fixture_files_feed_the_sparse_dense_and_banded_drivers(tmp_path):
     for r in (rs, rd, rb):
         assert r.info == 0 and r.M == len(want) and np.allclose(np.sort(r.lambda_), want, atol=1e-10) and r.res.max() < 1e-12
     assert rg.info == 0 and rg.M == len(want) and np.allclose(np.sort(rg.lambda_.real), want, atol=1e-8)
+
+
+@pytest.mark.parametrize("n,k,m,generalized", [(5000, 7, 40, False), (777, 12, 33, True), (300, 20, 5, False), (200, 40, 64, False),
+                                               (37, 1, 1, False), (64, 3, 70, True), (3, 1, 3, False), (1, 0, 2, False)])
+def test_band_block_solve_every_kernel_path_matches_lapack(engine, n, k, m, generalized):
+    """Stage-level band solve (feastcuda_block_solve on a banded pencil = zgbtrf + zgbtrs, banded/feast_banded.jl:108,141) against LAPACK
+    for every kernel choice: the warp LU + register-window solve with its four window sizes (k <= 2, 4, 8, 16), the warp LU with the
+    thread-per-column solve (16 < k <= 32) and the one-CTA LU (k > 32); column counts that do not fill a warp; the chunk tails of the
+    shared-memory staging (n not a multiple of 16, n smaller than a window)."""
+    import feastcuda as fc
+    rng = np.random.default_rng(7 * n + k)
+    Af = np.zeros((n, n))
+    Bf = np.zeros((n, n))
+    kb = min(k, 2)
+    for dd in range(min(k, n - 1) + 1):
+        v = rng.standard_normal(n - dd) * (2.0 if dd == 0 else 0.5)
+        Af += np.diag(v, dd) + (np.diag(v, -dd) if dd else 0)
+        if dd <= kb:
+            u = rng.uniform(0.05, 0.1, n - dd) if dd else rng.uniform(1.0, 2.0, n)
+            Bf += np.diag(u, dd) + (np.diag(u, -dd) if dd else 0)
+    engine.set_band(fc.A, fo.full_to_banded(Af, k), k, fc.SYM)
+    if generalized:
+        engine.set_band(fc.B, fo.full_to_banded(Bf, kb), kb, fc.SYM)
+    else:
+        engine.clear_b()
+    z = 0.3 + 0.05j
+    S = z * (Bf if generalized else np.eye(n)) - Af
+    RHS = rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m))
+    want = sla.solve_banded((k, k), fo.full_to_general_banded(S, k), RHS) if n > 1 else RHS / S[0, 0]
+    X, _, _ = engine.block_solve(z, RHS, solver="direct")
+    assert np.abs(X - want).max() < 1e-10 * np.abs(want).max()
+    # a second solve with the cached factor and other right-hand sides
+    RHS2 = rng.standard_normal((n, m)) + 0j
+    X2, _, _ = engine.block_solve(z, RHS2, solver="direct")
+    want2 = sla.solve_banded((k, k), fo.full_to_general_banded(S, k), RHS2) if n > 1 else RHS2 / S[0, 0]
+    assert np.abs(X2 - want2).max() < 1e-10 * np.abs(want2).max()

@@ -646,15 +646,15 @@ def run_other_config(args):
                                              "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"], "all_kernels": kern}
     cpu = None
     if cfg == 5 and not args.no_cpu:
-        # the reference's :serial path restated (sequential node loop, one sparse LU of the band matrix per node, cached; Rayleigh-Ritz;
-        # refinement) run TO COMPLETION on the same inputs
+        # the reference's :serial banded path restated (sequential node loop, one LAPACK band LU per node -- zgbtrf/zgbtrs, cached; Rayleigh-Ritz;
+        # refinement; banded/feast_banded.jl:561-823) run TO COMPLETION on the same inputs
         sys.path.insert(0, str(ROOT / "oracle"))
         import feast_oracle as fo
         t0 = time.perf_counter()
-        ro = fo.feast_hrr(Asp.astype(complex), None, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true")
+        ro = fo.feast_hrr(Asp.astype(complex), None, Emin, Emax, M0, fo.feastinit(), Q0=Q0.astype(complex), filter="true", band_k=kb)
         sec = time.perf_counter() - t0
         cpu = {"value": ro.M / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"the whole solve at full size, run to completion: oracle/feast_oracle.py feast_hrr (true filter), {sec:.1f} s, "
+               "sample": f"the whole solve at full size, run to completion: oracle/feast_oracle.py feast_hrr (LAPACK band LU per node, true filter), {sec:.1f} s, "
                          f"info={ro.info}, M={ro.M}, loops={ro.loop}, epsout={ro.epsout:.2e}",
                "max_eig_diff_gpu_vs_cpu": float(np.abs(np.sort(ro.lambda_.real) - np.sort(r.lambda_)).max()) if ro.M == r.M else None}
     name = "banded path, n=10^6 k=7" if cfg == 5 else f"BASELINE configs[{cfg}] at full size"

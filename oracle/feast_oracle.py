@@ -533,8 +533,23 @@ def solve_shifted_iterative(A, B, z, rhs, tol, maxiter, restart, stats=None):
     return X, True
 
 
-def _factor(A, B, z):
-    """lu(z*B - A) for dense (zgetrf) or sparse (UMFPACK -> SuperLU) inputs."""
+def _factor(A, B, z, band_k=None):
+    """lu(z*B - A) for dense (zgetrf), sparse (UMFPACK -> SuperLU) or -- band_k given -- banded inputs (the reference's banded route:
+    shifted band in gbtrf layout, LAPACK.gbtrf!, banded/feast_banded.jl:216-237, 100-112, 678)."""
+    if band_k is not None and sp.issparse(A):
+        n, k = A.shape[0], int(band_k)
+        Bm = sp.identity(n, dtype=np.complex128, format="csc") if B is None else B
+        S = (z * Bm - A).tocsc().astype(np.complex128)
+        ab = np.zeros((3 * k + 1, n), dtype=np.complex128)
+        for d in range(-k, k + 1):
+            if d >= 0:
+                ab[2 * k - d, d:] = S.diagonal(d)
+            else:
+                ab[2 * k - d, :n + d] = S.diagonal(d)
+        lu, piv, info = sla.lapack.zgbtrf(ab, k, k, overwrite_ab=True)
+        if info != 0:
+            raise np.linalg.LinAlgError(f"zgbtrf info = {info}")
+        return ("band", (lu, piv, k))
     if sp.issparse(A):
         n = A.shape[0]
         Bm = sp.identity(n, dtype=np.complex128, format="csc") if B is None else B
@@ -547,6 +562,10 @@ def _factor(A, B, z):
 
 def _solve_factor(fac, rhs):
     kind, f = fac
+    if kind == "band":                      # LAPACK.gbtrs!, banded/feast_banded.jl:141, 683
+        lu, piv, k = f
+        x, info = sla.lapack.zgbtrs(lu, k, k, np.asfortranarray(rhs, dtype=np.complex128), piv)
+        return x
     if kind == "sparse":
         return f.solve(np.ascontiguousarray(rhs, dtype=np.complex128))
     return sla.lu_solve(f, rhs)
@@ -557,8 +576,11 @@ def _solve_factor(fac, rhs):
 # --------------------------------------------------------------------------
 def feast_hrr(A, B, Emin, Emax, M0, fpm, Q0=None, solver="direct", solver_tol=0.0,
               solver_maxiter=500, solver_restart=30, filter="reference", contour=None,
-              node_range=None):
+              node_range=None, band_k=None):
     """Hermitian FEAST with QR-compress + Rayleigh-Ritz.
+
+    band_k: half-bandwidth of a banded pencil given in sparse form -> the per-node factorisations are LAPACK band LUs (zgbtrf/zgbtrs),
+        the reference's banded route (banded/feast_banded.jl:561-823); everything else is unchanged.
 
     A, B: dense ndarray or scipy sparse, Hermitian (B may be None = identity).
     filter="reference": accumulate the COMPLEX half-contour sum 2*w*Y exactly as the
@@ -608,7 +630,7 @@ def feast_hrr(A, B, Emin, Emax, M0, fpm, Q0=None, solver="direct", solver_tol=0.
             weight = 2 * Wne[e]
             if solver == "direct":
                 if fac_cache[e] is None:
-                    fac_cache[e] = _factor(Ac, Bc, z)
+                    fac_cache[e] = _factor(Ac, Bc, z, band_k)
                 Y = _solve_factor(fac_cache[e], rhs)
             else:
                 Y, ok = solve_shifted_iterative(Ac, Bc, z, rhs, tol_value, solver_maxiter, solver_restart, stats)
@@ -624,7 +646,7 @@ def feast_hrr(A, B, Emin, Emax, M0, fpm, Q0=None, solver="direct", solver_tol=0.
                 zc = np.conj(z)
                 if solver == "direct":
                     if fac_cache_c[e] is None:
-                        fac_cache_c[e] = _factor(Ac, Bc, zc)
+                        fac_cache_c[e] = _factor(Ac, Bc, zc, band_k)
                     Yc = _solve_factor(fac_cache_c[e], rhs)
                 else:
                     Yc, ok = solve_shifted_iterative(Ac, Bc, zc, rhs, tol_value, solver_maxiter, solver_restart, stats)

@@ -50,3 +50,24 @@ def test_band_lu_reports_the_first_zero_pivot_like_zgbtf2():
     lu, piv, info_l = sla.lapack.zgbtrf(F.copy(), 1, 1)
     _, info = fp.band_lu(F, k)
     assert info == info_l == 2
+
+
+def test_oracle_banded_route_equals_its_sparse_route():
+    """feast_oracle.feast_hrr(band_k=...) -- per-node LAPACK band LUs, the reference's banded route (banded/feast_banded.jl:561-823) --
+    returns the eigenpairs of the SuperLU route on a banded pencil (KA8-like operator at n = 60, k = 3, generalized)."""
+    import scipy.sparse as sp
+    import feast_oracle as fo
+    rng = np.random.default_rng(5)
+    n, k = 60, 3
+    A = sp.diags([rng.standard_normal(n - abs(d)) * (2.0 if d == 0 else 0.4) for d in range(k + 1)], list(range(k + 1)))
+    A = (A + sp.triu(A, 1).T).tocsc()
+    B = sp.diags([rng.uniform(1.0, 2.0, n), rng.uniform(0.05, 0.1, n - 1)], [0, 1])
+    B = (B + sp.triu(B, 1).T).tocsc()
+    w = sla.eigh(A.toarray(), B.toarray(), eigvals_only=True)
+    Emin, Emax = 0.5 * (w[19] + w[20]), 0.5 * (w[27] + w[28])
+    Q0 = fo.seeded_subspace(n, 16, complex_storage=False).astype(complex)
+    r1 = fo.feast_hrr(A, B, Emin, Emax, 16, fo.feastinit(), Q0=Q0, filter="true")
+    r2 = fo.feast_hrr(A, B, Emin, Emax, 16, fo.feastinit(), Q0=Q0, filter="true", band_k=k)
+    assert r1.info == r2.info == 0 and r1.M == r2.M == 8 and r1.loop == r2.loop
+    assert np.abs(np.sort(r1.lambda_) - w[20:28]).max() < 1e-12 and np.abs(np.sort(r2.lambda_) - w[20:28]).max() < 1e-12
+    assert fo.subspace_angle(r1.q, r2.q) < 1e-9

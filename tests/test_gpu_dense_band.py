@@ -174,14 +174,14 @@ def test_fixture_files_feed_the_sparse_dense_and_banded_drivers(tmp_path):
     fc.write_mm_coordinate(tmp_path / "lap10.mtx", A)
     w = np.linalg.eigvalsh(A.toarray())
     want = w[(w >= 0.5) & (w <= 3.1)]
-    Q0 = fo.seeded_subspace(10, 10, complex_storage=False)
-    rs = fc.feast_scsrev(fc.read_mm_sparse_real("lap10", data_dir=tmp_path), 0.5, 3.1, 10, fc.feastinit(), Q0=Q0, **{
+    Q0 = fo.seeded_subspace(10, 8, complex_storage=False)
+    rs = fc.feast_scsrev(fc.read_mm_sparse_real("lap10", data_dir=tmp_path), 0.5, 3.1, 8, fc.feastinit(), Q0=Q0, **{
         "solver_tol": 1e-12, "solver_maxiter": 4000, "ritz_guess": True, "inner_rel": 1e-9})
-    rd = fc.feast_syev(fc.read_mm_dense_real("lap10", data_dir=tmp_path), 0.5, 3.1, 10, fc.feastinit(), Q0=Q0)
+    rd = fc.feast_syev(fc.read_mm_dense_real("lap10", data_dir=tmp_path), 0.5, 3.1, 8, fc.feastinit(), Q0=Q0)
     band, kl, ku = fc.read_banded_real("lap10", data_dir=tmp_path)
     assert (kl, ku) == (1, 1)
-    rb = fc.feast_sbev(np.ascontiguousarray(band[:ku + 1]), ku, 0.5, 3.1, 10, fc.feastinit(), Q0=Q0)   # upper band = rows 0..ku
-    rg = fc.feast_gbev(band.astype(complex), kl, 1.8, 1.3, 10, fc.feastinit(), Q0=fo.seeded_subspace(10, 10))
+    rb = fc.feast_sbev(np.ascontiguousarray(band[:ku + 1]), ku, 0.5, 3.1, 8, fc.feastinit(), Q0=Q0)   # upper band = rows 0..ku
+    rg = fc.feast_gbev(band.astype(complex), kl, 1.8, 1.3, 8, fc.feastinit(), Q0=fo.seeded_subspace(10, 8))
     for r in (rs, rd, rb):
         assert r.info == 0 and r.M == len(want) and np.allclose(np.sort(r.lambda_), want, atol=1e-10) and r.res.max() < 1e-12
     assert rg.info == 0 and rg.M == len(want) and np.allclose(np.sort(rg.lambda_.real), want, atol=1e-8)

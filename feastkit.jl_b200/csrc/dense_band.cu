@@ -127,35 +127,64 @@ static bool dense_factor_range(H* h, int first, int count, const zc* shifts) {
     k_dense_shift<<<grid, 256, 0, h->stream>>>(n, h->dDenseA.as<zd>(), h->has_b ? h->dDenseB.as<zd>() : nullptr, dz.as<zd>(), LU, nn);
     launched(h);
   }
-  for (int k0 = 0; k0 < n; k0 += FC_LU_NB) {
-    const int nbw = std::min(FC_LU_NB, n - k0);
-    if (cpn > 1) {
-      int n_ = n, k0_ = k0, nbw_ = nbw, cpn_ = cpn;
-      zd* lu_ = LU;
-      int64_t nn_ = nn, pst_ = pst;
-      int* ipiv_ = ipiv;
-      int* info_ = dinfo.as<int>();
-      double* pv_ = dpart.as<double>();
-      int* pi_ = reinterpret_cast<int*>(dpart.as<double>() + (size_t)count * cpn);
-      void* args[] = {&n_, &k0_, &nbw_, &lu_, &nn_, &ipiv_, &pst_, &info_, &cpn_, &pv_, &pi_};
-      FC_CUDA(cudaLaunchCooperativeKernel((void*)k_dense_panel_lu_coop, dim3(count * cpn), dim3(512), args, 0, h->stream));
-    } else {
-      k_dense_panel_lu<<<count, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, pst, dinfo.as<int>());
-    }
+  // Two-level blocking.  Panels are FC_LU_NB = 32 columns wide (latency-bound pivot searches), but a rank-32 update of the whole trailing
+  // matrix reads and writes C for 8 flop per byte (ncu: 1.7 TB/s, tensor pipe 37 % busy at n = 8192).  So the panels of an OUTER block
+  // of `nbo` columns update only the rest of that block; the columns to its right get the block's row interchanges, the triangular
+  // solve with the block's unit-lower L11 (panel by panel) and ONE rank-nbo update when the block is complete.  nbo = 32 is the
+  // one-level right-looking algorithm of round 1 (same operations in the same order).
+  static const int nbo_env = getenv("FEASTCUDA_DENSE_NBO") ? atoi(getenv("FEASTCUDA_DENSE_NBO")) : 128;
+  const int nbo = std::max(FC_LU_NB, (nbo_env / FC_LU_NB) * FC_LU_NB);
+  auto u12 = [&](int k0, int nbw, int c0, int c1) {       // U12 = L11^-1 A12 for the columns [c0, c1) (row interchanges already applied)
+    if (c1 <= c0) return;
+    k_dense_trsm_u12<<<dim3((c1 - c0 + 127) / 128, count), 128, 0, h->stream>>>(n, k0, nbw, c0, c1, LU, nn);
     launched(h);
-    if (k0 > 0) {
-      k_dense_laswp<<<dim3((k0 + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, 0, k0, LU, nn, ipiv, pst);
+  };
+  for (int o0 = 0; o0 < n; o0 += nbo) {
+    const int oend = std::min(n, o0 + nbo);
+    for (int k0 = o0; k0 < oend; k0 += FC_LU_NB) {
+      const int nbw = std::min(FC_LU_NB, oend - k0);
+      if (cpn > 1) {
+        int n_ = n, k0_ = k0, nbw_ = nbw, cpn_ = cpn;
+        zd* lu_ = LU;
+        int64_t nn_ = nn, pst_ = pst;
+        int* ipiv_ = ipiv;
+        int* info_ = dinfo.as<int>();
+        double* pv_ = dpart.as<double>();
+        int* pi_ = reinterpret_cast<int*>(dpart.as<double>() + (size_t)count * cpn);
+        void* args[] = {&n_, &k0_, &nbw_, &lu_, &nn_, &ipiv_, &pst_, &info_, &cpn_, &pv_, &pi_};
+        FC_CUDA(cudaLaunchCooperativeKernel((void*)k_dense_panel_lu_coop, dim3(count * cpn), dim3(512), args, 0, h->stream));
+      } else {
+        k_dense_panel_lu<<<count, 512, 0, h->stream>>>(n, k0, nbw, LU, nn, ipiv, pst, dinfo.as<int>());
+      }
       launched(h);
+      if (k0 > 0) {
+        k_dense_laswp<<<dim3((k0 + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, 0, k0, LU, nn, ipiv, pst);
+        launched(h);
+      }
+      const int c0 = k0 + nbw, inblk = oend - c0;          // the rest of the outer block
+      if (inblk > 0) {
+        k_dense_laswp<<<dim3((inblk + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, c0, oend, LU, nn, ipiv, pst);
+        launched(h);
+        u12(k0, nbw, c0, oend);
+        // A22[c0:n, c0:oend] -= L21[c0:n, k0:c0] * U12[k0:c0, c0:oend]   (all column-major, ld = n), every node in the same launch
+        zgemm(h, n - c0, inblk, nbw, LU + c0 + (int64_t)k0 * n, 1, n, LU + k0 + (int64_t)c0 * n, 1, n, LU + c0 + (int64_t)c0 * n, 1, n,
+              -1.0, 1, count, nn, nn, nn);
+      }
     }
-    const int rest = n - k0 - nbw;
+    const int rest = n - oend;
     if (rest > 0) {
-      k_dense_laswp<<<dim3((rest + 255) / 256, count), 256, 0, h->stream>>>(n, k0, nbw, k0 + nbw, n, LU, nn, ipiv, pst);
+      // the columns right of the block: all of the block's row interchanges in order, U12 = L11^-1 A12 panel by panel, one rank-(oend - o0) update
+      k_dense_laswp<<<dim3((rest + 255) / 256, count), 256, 0, h->stream>>>(n, o0, oend - o0, oend, n, LU, nn, ipiv, pst);
       launched(h);
-      k_dense_trsm_u12<<<dim3((rest + 127) / 128, count), 128, 0, h->stream>>>(n, k0, nbw, LU, nn);
-      launched(h);
-      // A22 -= L21 * U12   (all column-major, ld = n), every node in the same launch
-      zgemm(h, rest, rest, nbw, LU + (k0 + nbw) + (int64_t)k0 * n, 1, n, LU + k0 + (int64_t)(k0 + nbw) * n, 1, n,
-            LU + (k0 + nbw) + (int64_t)(k0 + nbw) * n, 1, n, -1.0, 1, count, nn, nn, nn);
+      for (int k0 = o0; k0 < oend; k0 += FC_LU_NB) {
+        const int nbw = std::min(FC_LU_NB, oend - k0), below = oend - k0 - nbw;
+        u12(k0, nbw, oend, n);
+        if (below > 0)   // A12[k0+nbw:oend, oend:n] -= L11[k0+nbw:oend, k0:k0+nbw] * U12[k0:k0+nbw, oend:n]
+          zgemm(h, below, rest, nbw, LU + (k0 + nbw) + (int64_t)k0 * n, 1, n, LU + k0 + (int64_t)oend * n, 1, n,
+                LU + (k0 + nbw) + (int64_t)oend * n, 1, n, -1.0, 1, count, nn, nn, nn);
+      }
+      zgemm(h, rest, rest, oend - o0, LU + oend + (int64_t)o0 * n, 1, n, LU + o0 + (int64_t)oend * n, 1, n, LU + oend + (int64_t)oend * n, 1, n,
+            -1.0, 1, count, nn, nn, nn);
     }
   }
   k_dense_piv_to_perm<<<count, 32, 0, h->stream>>>(n, ipiv, ipiv + n, pst);
@@ -302,9 +331,10 @@ void band_prepare(H* h) {
   release_factor_cache(h);
 }
 
-// 2 (default): batched-over-nodes warp LU + register-window solve; 1: the one-CTA LU / thread-per-column solve of round 1
+// 3 (default): batched over nodes, LU with the active window in a shared-memory ring + lane-parallel substitutions (k <= 15);
+// 2: warp LU on global memory + register-window substitutions; 1: the one-CTA LU / thread-per-column solve of round 1
 static int band_impl() {
-  static const int v = getenv("FEASTCUDA_BAND_IMPL") ? atoi(getenv("FEASTCUDA_BAND_IMPL")) : 2;
+  static const int v = getenv("FEASTCUDA_BAND_IMPL") ? atoi(getenv("FEASTCUDA_BAND_IMPL")) : 3;
   return v;
 }
 
@@ -356,7 +386,9 @@ static bool band_factor_range(H* h, int first, int count, const zc* shifts) {
         bb.ipiv[t] = h->piv_cache[first + todo[t0 + t]].as<int>();
       }
       const int ev = sample_begin(h, FEASTCUDA_KERN_BAND_LU);
-      k_band_lu_warp<<<cnt, 32, 0, h->stream>>>(n, k, bb);
+      if (band_impl() >= 3 && k <= 7) k_band_lu_smem<7, 32><<<cnt, 32, 0, h->stream>>>(n, k, bb);
+      else if (band_impl() >= 3 && k <= 15) k_band_lu_smem<15, 64><<<cnt, 32, 0, h->stream>>>(n, k, bb);
+      else k_band_lu_warp<<<cnt, 32, 0, h->stream>>>(n, k, bb);
       launched(h);
       sample_end(h, ev);
       // algorithmic bytes of the launch: every factor is read once and written once (the 5 KB window of a step lives in L1), pivots written
@@ -373,6 +405,13 @@ static bool band_factor_range(H* h, int first, int count, const zc* shifts) {
     else h->lu_shift[first + todo[t]] = shifts[todo[t]];
   }
   return all_ok;
+}
+
+template <int G>
+static void band_launch_lanes(H* h, int n, int k, const BandBatch& bb, int cnt, int m, int64_t ld, const zd* RHS, zd* X, int64_t xbatch) {
+  constexpr int CPW = 32 / G;
+  k_band_solve_lanes<G><<<dim3((m + CPW - 1) / CPW, cnt), 32, 0, h->stream>>>(n, k, bb, m, ld, RHS, X, xbatch);
+  launched(h);
 }
 
 template <int K>
@@ -399,14 +438,18 @@ static void band_solve_range(H* h, int first, int count, int m, const zd* RHS, z
       }
       zd* X = Xbase + (int64_t)q0 * xbatch;
       const int ev = sample_begin(h, FEASTCUDA_KERN_BAND_SOLVE);
-      if (k <= 2) band_launch_win<2>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      if (band_impl() >= 3 && k <= 1) band_launch_lanes<4>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else if (band_impl() >= 3 && k <= 3) band_launch_lanes<8>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else if (band_impl() >= 3 && k <= 7) band_launch_lanes<16>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else if (band_impl() >= 3 && k <= 15) band_launch_lanes<32>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
+      else if (k <= 2) band_launch_win<2>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
       else if (k <= 4) band_launch_win<4>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
       else if (k <= 8) band_launch_win<8>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
       else band_launch_win<16>(h, n, k, bb, cnt, m, ld, RHS, X, xbatch);
       sample_end(h, ev);
-      // per node: the factor and the pivots are read by both sweeps of every 32-column group, x moves four times (RHS -> y -> x)
+      // per node (minimum traffic): the factor is read once per sweep, the pivots once, x moves four times (RHS -> y -> x)
       h->stats.bytes_kern[FEASTCUDA_KERN_BAND_SOLVE] =
-          (double)cnt * ((double)((m + 31) / 32) * (2.0 * ldf * (double)n * sizeof(zd) + 4.0 * n) + 4.0 * (double)n * m * sizeof(zd));
+          (double)cnt * (2.0 * ldf * (double)n * sizeof(zd) + 4.0 * n + 4.0 * (double)n * m * sizeof(zd));
     }
     return;
   }

@@ -131,6 +131,95 @@ struct BandBatch {
   int* ipiv[FC_BAND_BATCH];   // n pivots + the info word
 };
 
+__device__ __forceinline__ void band_cp16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void band_cp4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void band_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void band_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void band_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// The warp LU with the active window in SHARED memory: columns j .. j + 2k (all a step can touch) live in a ring of W column slots
+// (slot = column mod W); a column enters by cp.async W - 2k - 1 steps before its first possible use and returns to global memory
+// right after its own pivot step.  In k_band_lu_warp every phase of a step (pivot search, swap, scaling, update) reads what the
+// previous phase stored through L2 (stores do not allocate in L1): 4 400 cycles per column at k = 7; here the phases meet in
+// shared memory.  KMAX = 7 (W = 32, 11 KB) or 15 (W = 64, 46 KB).
+template <int KMAX, int W>
+__global__ void __launch_bounds__(32) k_band_lu_smem(int n, int k, BandBatch bb) {
+  constexpr int LDFMAX = 3 * KMAX + 1, PEND = W - 2 * KMAX - 1;
+  static_assert(PEND >= 1 && (W & (W - 1)) == 0, "ring size");
+  __shared__ __align__(16) zdb sW[W * LDFMAX];
+  zdb* F = bb.F[blockIdx.x];
+  int* ipiv = bb.ipiv[blockIdx.x];
+  const int ldf = 3 * k + 1, kv = 2 * k, lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  auto slot = [&](int c) -> zdb* { return sW + (c & (W - 1)) * ldf; };
+  // one commit group per column, in column order (empty groups past the matrix keep the count uniform)
+  for (int c = 0; c < W; ++c) {
+    if (c < n)
+      for (int e = lane; e < ldf; e += 32) band_cp16(slot(c) + e, F + (int64_t)c * ldf + e);
+    band_commit();
+  }
+  int ju = 0, info = 0;
+  for (int j = 0; j < n; ++j) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // columns <= j + 2k have landed
+    __syncwarp();
+    const int km = min(k, n - 1 - j);
+    zdb* colj = slot(j) + kv;                // colj[i] = A[j+i, j]
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = lane; i <= km; i += 32) {
+      const zdb v = colj[i];
+      const double a = fabs(v.x) + fabs(v.y);
+      if (a > best) { best = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const int jp = (best < 0.0) ? 0 : bi;
+    if (lane == 0) ipiv[j] = j + jp;
+    ju = max(ju, min(j + k + jp, n - 1));
+    if (best > 0.0) {
+      if (jp != 0) {
+        for (int c = j + lane; c <= ju; c += 32) {   // swap rows j and j+jp over the columns j..ju
+          zdb* e0 = slot(c) + (kv + j - c);
+          const zdb t = e0[0];
+          e0[0] = e0[jp];
+          e0[jp] = t;
+        }
+        __syncwarp();
+      }
+      const zdb inv = mk<double>(1.0, 0.0) / colj[0];
+      for (int i = 1 + lane; i <= km; i += 32) colj[i] = colj[i] * inv;
+      __syncwarp();
+      const int nc = ju - j;
+      for (int e = lane; e < nc * km; e += 32) {
+        const int cc = e / km + 1, i = e % km + 1;       // column j+cc, row j+i
+        zdb* colc = slot(j + cc) + (kv - cc);             // colc[i] = A[j+i, j+cc]
+        colc[i] = colc[i] - colj[i] * colc[0];
+      }
+      __syncwarp();
+    } else if (info == 0) {
+      info = j + 1;                                     // exactly singular (zgbtf2: info = j, the column is skipped)
+    }
+    // column j is final: back to global memory, its slot takes column j + W
+    for (int e = lane; e < ldf; e += 32) F[(int64_t)j * ldf + e] = slot(j)[e];
+    __syncwarp();
+    if (j + W < n)
+      for (int e = lane; e < ldf; e += 32) band_cp16(slot(j) + e, F + (int64_t)(j + W) * ldf + e);
+    band_commit();
+  }
+  band_wait0();
+  if (lane == 0) ipiv[n] = info;
+}
+
 // zgbtf2 (kl = ku = k) with ONE WARP per node: no block barriers, the pivot search is a shuffle butterfly, the (km x (ju - j)) rank-1
 // update is spread over the lanes; the window a step touches (2k + 1 columns of 3k + 1 rows: 5 KB at k = 7) lives in L1.
 __global__ void __launch_bounds__(32) k_band_lu_warp(int n, int k, BandBatch bb) {
@@ -185,17 +274,6 @@ __global__ void __launch_bounds__(32) k_band_lu_warp(int n, int k, BandBatch bb)
   if (lane == 0) ipiv[n] = info;
 }
 
-__device__ __forceinline__ void band_cp16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void band_cp4(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void band_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void band_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void band_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // w -= a * b
 __device__ __forceinline__ void band_fnma(zdb& w, const zdb a, const zdb b) {
   w.x = fma(-a.x, b.x, w.x); w.x = fma(a.y, b.y, w.x);
@@ -306,6 +384,130 @@ __global__ void __launch_bounds__(32) k_band_solve_win(int n, int k, BandBatch b
 #pragma unroll
       for (int d = 1; d <= 2 * K; ++d) v[d - 1] = v[d];
       v[2 * K] = (j - 1 - 2 * K >= 0) ? sX[buf][s * 32 + lane] : czero<double>();
+    }
+    __syncwarp();
+  }
+  band_wait0();
+}
+
+// The same substitutions with the window of a column spread over G LANES (G = 4, 8, 16, 32 >= 2k + 1): lane i of a column's group
+// holds row j + i (forward) resp. j - i (backward) of the running right-hand side.  A step is: broadcast x_j from lane 0 (after the
+// pivot swap, two shuffles), ONE complex FMA per lane with its own multiplier, shift the window by a shuffle, the lane at the far end
+// takes the entering row from the staging ring.  The dependent chain of a step is shuffle -> 2 FMA -> shuffle (~80 cycles) where the
+// one-thread-per-column window kernel above walks k (resp. 2k) FMAs, 2k register moves and a division per step with a single warp
+// on its SM (measured: 1 800 cycles per row for both sweeps at k = 7).  32 / G columns per warp.
+template <typename T>
+__device__ __forceinline__ cx<T> band_shfl(cx<T> v, int src, int width) {
+  cx<T> r;
+  r.x = __shfl_sync(0xffffffffu, v.x, src, width);
+  r.y = __shfl_sync(0xffffffffu, v.y, src, width);
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ cx<T> band_shfl_down(cx<T> v, int width) {
+  cx<T> r;
+  r.x = __shfl_down_sync(0xffffffffu, v.x, 1, width);
+  r.y = __shfl_down_sync(0xffffffffu, v.y, 1, width);
+  return r;
+}
+
+template <int G>
+__global__ void __launch_bounds__(32) k_band_solve_lanes(int n, int k, BandBatch bb, int m, int64_t ld, const zdb* __restrict__ RHS,
+                                                         zdb* __restrict__ X, int64_t xbatch) {
+  constexpr int CH = 16, CPW = 32 / G, KMAX = (G - 1) / 2, LDFMAX = 3 * KMAX + 1;
+  __shared__ __align__(16) zdb sF[2][CH * LDFMAX];
+  __shared__ __align__(16) zdb sX[2][CH * CPW];
+  __shared__ int sP[2][CH];
+  const int lane = threadIdx.x, node = blockIdx.y;
+  const int g = lane / G, i = lane % G;            // column of the warp, window slot
+  const int c = blockIdx.x * CPW + g;
+  const bool act = c < m;
+  const int cr = act ? c : (m - 1);                // idle groups shadow the last column (loads only)
+  const zdb* F = bb.F[node];
+  const int* ipiv = bb.ipiv[node];
+  zdb* Xn = X + (int64_t)node * xbatch;
+  const int ldf = 3 * k + 1, kv = 2 * k;
+  const int nch = (n + CH - 1) / CH;
+  const int col0 = blockIdx.x * CPW;
+
+  // ---------------- forward: L y = P b ----------------
+  auto stage_fwd = [&](int ch, int buf) {
+    const int j0 = ch * CH, cnt = min(CH, n - j0);
+    const zdb* src = F + (int64_t)j0 * ldf;
+    for (int e = lane; e < cnt * ldf; e += 32) band_cp16(&sF[buf][e], src + e);
+    if (lane < cnt) band_cp4(&sP[buf][lane], ipiv + j0 + lane);
+    for (int e = lane; e < cnt * CPW; e += 32) {
+      const int s = e / CPW, gg = e % CPW;
+      const int row = j0 + s + 1 + k;              // enters the window at the end of step j0 + s
+      if (row < n) band_cp16(&sX[buf][e], RHS + (int64_t)row * ld + min(col0 + gg, m - 1));
+    }
+  };
+  zdb w = (i <= k && i < n) ? RHS[(int64_t)i * ld + cr] : czero<double>();
+  stage_fwd(0, 0);
+  band_commit();
+  for (int ch = 0; ch < nch; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nch) stage_fwd(ch + 1, buf ^ 1);
+    band_commit();
+    band_wait1();
+    __syncwarp();
+    const int j0 = ch * CH, cnt = min(CH, n - j0);
+    for (int s = 0; s < cnt; ++s) {
+      const int j = j0 + s;
+      const int p = sP[buf][s] - j;
+      const zdb lmul = (i >= 1 && i <= k) ? sF[buf][s * ldf + kv + i] : czero<double>();   // multiplier of row j + i
+      const zdb enter = (j + 1 + k < n) ? sX[buf][s * CPW + g] : czero<double>();
+      const zdb v0 = band_shfl(w, 0, G);
+      zdb xj = v0;
+      if (p != 0) {
+        const zdb vp = band_shfl(w, p, G);
+        if (i == 0) w = vp;
+        else if (i == p) w = v0;
+        xj = vp;
+      }
+      if (i == 0 && act) Xn[(int64_t)j * ld + cr] = xj;
+      band_fnma(w, lmul, xj);                       // lanes outside 1..k carry a zero multiplier
+      w = band_shfl_down(w, G);
+      if (i == k) w = enter;
+    }
+    __syncwarp();
+  }
+  band_wait0();
+  __threadfence_block();
+  __syncwarp();
+
+  // ---------------- backward: U x = y ----------------
+  auto stage_bwd = [&](int ch, int buf) {
+    const int jhi = n - 1 - ch * CH, jlo = max(0, jhi - CH + 1), cnt = jhi - jlo + 1;
+    const zdb* src = F + (int64_t)jlo * ldf;
+    for (int e = lane; e < cnt * ldf; e += 32) band_cp16(&sF[buf][e], src + e);
+    for (int e = lane; e < cnt * CPW; e += 32) {
+      const int s = e / CPW, gg = e % CPW;
+      const int row = jhi - s - 1 - kv;            // enters the window at the end of step jhi - s
+      if (row >= 0) band_cp16(&sX[buf][e], Xn + (int64_t)row * ld + min(col0 + gg, m - 1));
+    }
+  };
+  zdb v = (i <= kv && n - 1 - i >= 0) ? Xn[(int64_t)(n - 1 - i) * ld + cr] : czero<double>();
+  stage_bwd(0, 0);
+  band_commit();
+  for (int ch = 0; ch < nch; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nch) stage_bwd(ch + 1, buf ^ 1);
+    band_commit();
+    band_wait1();
+    __syncwarp();
+    const int jhi = n - 1 - ch * CH, jlo = max(0, jhi - CH + 1);
+    for (int s = 0; s <= jhi - jlo; ++s) {
+      const int j = jhi - s;
+      const zdb* Uc = &sF[buf][(j - jlo) * ldf];   // Uc[kv - d] = U[j-d, j]
+      const zdb rinv = mk<double>(1.0, 0.0) / Uc[kv];
+      const zdb umul = (i >= 1 && i <= kv) ? Uc[kv - i] : czero<double>();
+      const zdb enter = (j - 1 - kv >= 0) ? sX[buf][s * CPW + g] : czero<double>();
+      const zdb xj = band_shfl(v, 0, G) * rinv;
+      if (i == 0 && act) Xn[(int64_t)j * ld + cr] = xj;
+      band_fnma(v, umul, xj);
+      v = band_shfl_down(v, G);
+      if (i == kv) v = enter;
     }
     __syncwarp();
   }

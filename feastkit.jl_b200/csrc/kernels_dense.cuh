@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(256) k_dense_laswp(int n, int k0, int nbw, int
   }
 }
 
-// U12 = L11^-1 A12 (unit lower L11 = panel rows/cols [k0, k0+nbw)); one thread per column of A12
-__global__ void __launch_bounds__(128) k_dense_trsm_u12(int n, int k0, int nbw, zdd* __restrict__ LU, int64_t batch_stride) {
+// U12 = L11^-1 A12 (unit lower L11 = panel rows/cols [k0, k0+nbw)) for the columns [c0, c1) of A12; one thread per column
+__global__ void __launch_bounds__(128) k_dense_trsm_u12(int n, int k0, int nbw, int c0, int c1, zdd* __restrict__ LU, int64_t batch_stride) {
   zdd* M = LU + (int64_t)blockIdx.y * batch_stride;
   __shared__ zdd sL[FC_LU_NB][FC_LU_NB + 1];
   for (int e = threadIdx.x; e < nbw * nbw; e += blockDim.x) {
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(128) k_dense_trsm_u12(int n, int k0, int nbw, 
     sL[i][j] = M[(k0 + i) + (int64_t)(k0 + j) * n];
   }
   __syncthreads();
-  const int c = k0 + nbw + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
   zdd* colp = M + (int64_t)c * n + k0;
   for (int i = 1; i < nbw; ++i) {
     zdd s = colp[i];

@@ -640,8 +640,8 @@ def run_other_config(args):
         dom = max(kern, key=lambda k_: kern[k_]["avg_ms"] * kern[k_]["sampled"]) if kern else None
         roofline = None if dom is None else {"bound": "hbm", "kernel": {"lz_cheb": "k_lz_spmm<LZ_CHEB> (Chebyshev / Jacobi step of the inner solve with B)",
                                                                           "lz_p1": "k_lz_spmm<LZ_P1> (A times the Lanczos block)",
-                                                                          "band_lu": "k_band_lu_warp (band LU, one warp per node; n dependent steps: latency-bound)",
-                                                                          "band_solve": "k_band_solve_win (band substitutions, one warp per node x 32 columns; latency-bound)"}.get(dom, dom),
+                                                                          "band_lu": "k_band_lu_smem (band LU, one warp per node, window in shared memory; n dependent steps: instruction-issue-bound)",
+                                                                          "band_solve": "k_band_solve_lanes (band substitutions of all nodes x columns in one launch, window spread over lanes; n dependent steps: instruction-issue-bound)"}.get(dom, dom),
                                              "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s", "frac": kern[dom]["gbs"] / hbm, "traffic": None,
                                              "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"], "all_kernels": kern}
     cpu = None

@@ -130,9 +130,10 @@ static bool dense_factor_range(H* h, int first, int count, const zc* shifts) {
   // Two-level blocking.  Panels are FC_LU_NB = 32 columns wide (latency-bound pivot searches), but a rank-32 update of the whole trailing
   // matrix reads and writes C for 8 flop per byte (ncu: 1.7 TB/s, tensor pipe 37 % busy at n = 8192).  So the panels of an OUTER block
   // of `nbo` columns update only the rest of that block; the columns to its right get the block's row interchanges, the triangular
-  // solve with the block's unit-lower L11 (panel by panel) and ONE rank-nbo update when the block is complete.  nbo = 32 is the
-  // one-level right-looking algorithm of round 1 (same operations in the same order).
-  static const int nbo_env = getenv("FEASTCUDA_DENSE_NBO") ? atoi(getenv("FEASTCUDA_DENSE_NBO")) : 128;
+  // solve with the block's unit-lower L11 (panel by panel) and ONE rank-nbo update when the block is complete (ncu, rank 128 at n = 8192:
+  // 24.2 TFLOP/s = 0.66 of the ZGEMM rate measured on the box, DMMA pipe 65 % busy).  nbo = 32 is the one-level right-looking algorithm of
+  // round 1 (same operations in the same order).
+  static const int nbo_env = getenv("FEASTCUDA_DENSE_NBO") ? atoi(getenv("FEASTCUDA_DENSE_NBO")) : 256;   // measured at n = 8192: 32 -> 1 298 ms, 128 -> 1 049, 256 -> 937, 512 -> 954
   const int nbo = std::max(FC_LU_NB, (nbo_env / FC_LU_NB) * FC_LU_NB);
   auto u12 = [&](int k0, int nbw, int c0, int c1) {       // U12 = L11^-1 A12 for the columns [c0, c1) (row interchanges already applied)
     if (c1 <= c0) return;

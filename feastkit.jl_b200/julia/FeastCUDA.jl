@@ -133,7 +133,9 @@ end
 # (sparse/feast_sparse.jl:246-499) and _feast_banded_complex_hermitian (banded/feast_banded.jl:561-823)
 function _solve_interval(setA!, setB!, N::Int, Emin, Emax, M0::Int, fpm::Vector{Int}, ::Type{VT};
                          Zne=nothing, Wne=nothing, solver::Symbol=:direct, solver_tol::Real=0.0, solver_maxiter::Int=500,
-                         solver_restart::Int=30, sparse::Bool=false, eps_floor::Float64=0.0, mixed::Int=0) where {VT}
+                         solver_restart::Int=30, sparse::Bool=false, eps_floor::Float64=0.0, mixed::Int=(sparse ? 2 : 0)) where {VT}
+    # mixed: 0 = FP64 Krylov vectors, 1 = FP32 vectors, 2 = follow fpm[42] (the reference's default fpm[42] = 1, core/feast_parameters.jl:316-319,
+    # is honoured for sparse problems: real symmetric standard pencils run FP32 Lanczos vectors inside the FP64 refinement loop)
     feastdefault!(fpm)
     # check_feast_srci_input (core/feast_aux.jl:369-399): thrown before any device call, exactly as the reference does
     N > 0 || throw(ArgumentError("Matrix size N must be positive"))

@@ -131,3 +131,43 @@ def test_reference_arm_runs_the_cpu_port(monkeypatch, capsys):
     _check_common(d)
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_banded_line_json_contract_with_the_cpu_oracle_run_to_completion(monkeypatch, capsys):
+    """bench.py --config 5 (the banded line): workload construction (band storage = the oracle's, analytic eigenvalues), the roofline
+    object from the sampled band kernels and the cpu_baseline leg -- the oracle's restatement of the reference's banded route (LAPACK
+    band LU per node) run to completion on the same inputs.  The solve itself is replaced by a stand-in that returns the analytic pairs."""
+    import torch
+    import feastcuda as fc
+    import feast_oracle as fo
+    sys.path.insert(0, str(ROOT))
+    import bench
+    import __graft_entry__ as g
+    seen = {}
+
+    def fake_sbev(AB, k, Emin, Emax, M0, fpm, Q0=None):
+        A = fo.banded_to_full(np.asarray(AB), k, hermitian=False)
+        w, V = np.linalg.eigh(A)
+        sel = (w >= Emin) & (w <= Emax)
+        seen["n"], seen["k"] = AB.shape[1], k
+        stats = {"n_kern": [0] * 6 + [1, 4], "ms_kern": [0.0] * 6 + [2.0, 4.0], "bytes_kern": [0.0] * 6 + [1e6, 8e6], "ms_total": 7.0,
+                 "kernel_launches": 40, "lz_steps_p1": 0, "cheb_degree": 0}
+        return fc.FeastResult(w[sel], V[:, sel], int(sel.sum()), np.full(int(sel.sum()), 1e-14), 0, 1e-14, 3, stats)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(fc, "dfeast_sbev", fake_sbev)
+    monkeypatch.setattr(g, "build", lambda *a, **k: None)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "5", "--n", "700"])
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    _check_common(d)
+    assert seen == {"n": 700, "k": 7} and d["config"]["n"] == 700 and "banded" in d["metric"]
+    assert d["result"]["M"] == d["result"]["expected_M"] > 20 and d["result"]["max_eig_err_vs_analytic"] < 1e-12
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["kernel"].startswith("k_band_solve_lanes") and r["frac"] == pytest.approx(r["achieved"] / r["peak"])
+    assert set(r["all_kernels"]) == {"band_lu", "band_solve"} and r["all_kernels"]["band_solve"]["avg_ms"] == pytest.approx(1.0)
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["value"] > 0 and "run to completion" in c["sample"] and c["max_eig_diff_gpu_vs_cpu"] < 1e-10

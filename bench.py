@@ -410,6 +410,7 @@ def run_gpu(args):
            "e2e": {"value": r.M / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
                    "h2d_bytes_per_step": int(Q0.nbytes) if shard == "rows" or world == 1 else int(Q0.nbytes) * world,
                    "d2h_bytes_per_step": (int(r.q.nbytes) if shard == "rows" or world == 1 else int(r.q.nbytes) * world) + int(r.lambda_.nbytes + r.res.nbytes) * world,
+                   "operator_h2d_bytes_once": int(A.nnz * 12 + 4 * (A.shape[0] + 1)),     # CSR upload at set_csr (int32 indices), outside the timed region
                    "note": "whole-job bytes: row-sharded ranks copy their own rows of Q0 / X only, column-sharded ranks the full blocks"},
            "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
            "mixed_precision": None if args.no_mixed else ({"error": mx_error} if mx_error else {

@@ -576,8 +576,12 @@ def _solve_factor(fac, rhs):
 # --------------------------------------------------------------------------
 def feast_hrr(A, B, Emin, Emax, M0, fpm, Q0=None, solver="direct", solver_tol=0.0,
               solver_maxiter=500, solver_restart=30, filter="reference", contour=None,
-              node_range=None, band_k=None):
+              node_range=None, band_k=None, node_pool=None):
     """Hermitian FEAST with QR-compress + Rayleigh-Ritz.
+
+    node_pool: callable rhs -> sum_e 2 w_e (z_e B - A)^-1 rhs evaluated by workers that each own one quadrature node and its cached
+        factorisation -- the reference's :threads backend (`Threads.@threads for e in 1:ne`, parallel/feast_parallel.jl:586); direct
+        solves with the plain half-contour sum only (filter="reference", or a real pencil with a real basis).
 
     band_k: half-bandwidth of a banded pencil given in sparse form -> the per-node factorisations are LAPACK band LUs (zgbtrf/zgbtrs),
         the reference's banded route (banded/feast_banded.jl:561-823); everything else is unchanged.
@@ -626,7 +630,11 @@ def feast_hrr(A, B, Emin, Emax, M0, fpm, Q0=None, solver="direct", solver_tol=0.
         basis = Q_basis[:, :active]
         rhs = basis.copy() if Bc is None else Bc @ basis
         failed = False
-        for e, z in enumerate(Zne):
+        pooled = node_pool is not None and solver == "direct" and (filter == "reference" or real_mode)
+        if pooled:
+            Q_proj[:, :active] = node_pool(rhs)
+            stats["solves"] += len(Zne)
+        for e, z in enumerate(() if pooled else Zne):
             weight = 2 * Wne[e]
             if solver == "direct":
                 if fac_cache[e] is None:

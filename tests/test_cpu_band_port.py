@@ -71,3 +71,31 @@ def test_oracle_banded_route_equals_its_sparse_route():
     assert r1.info == r2.info == 0 and r1.M == r2.M == 8 and r1.loop == r2.loop
     assert np.abs(np.sort(r1.lambda_) - w[20:28]).max() < 1e-12 and np.abs(np.sort(r2.lambda_) - w[20:28]).max() < 1e-12
     assert fo.subspace_angle(r1.q, r2.q) < 1e-9
+
+
+def test_oracle_node_pool_equals_the_sequential_node_loop():
+    """feast_oracle.feast_hrr(node_pool=...) -- one worker per quadrature node with its cached factorisation, the shape of the reference's
+    :threads backend (parallel/feast_parallel.jl:586) -- returns bit-identical pairs to the sequential node loop (:serial)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import feast_oracle as fo
+    A = fo.laplacian_3d(7).tocsc().astype(complex)
+    ev = fo.laplacian_3d_eigs(7)
+    Emin, Emax = 0.0, 0.5 * (ev[9] + ev[10])
+    Q0 = fo.seeded_subspace(343, 20, complex_storage=False).astype(complex)
+    fpm = fo.feastinit()
+    fo.feastdefault(fpm)
+    Zne, Wne = fo.feast_contour(Emin, Emax, fpm)
+    facs = [None] * len(Zne)
+
+    def one(e, rhs):
+        if facs[e] is None:
+            facs[e] = fo._factor(A, None, Zne[e])
+        return 2 * Wne[e] * fo._solve_factor(facs[e], rhs)
+
+    def pool(rhs):
+        with ThreadPoolExecutor(len(Zne)) as ex:
+            return sum(ex.map(lambda e: one(e, rhs), range(len(Zne))))
+    r1 = fo.feast_hrr(A, None, Emin, Emax, 20, fo.feastinit(), Q0=Q0, filter="true")
+    r2 = fo.feast_hrr(A, None, Emin, Emax, 20, fo.feastinit(), Q0=Q0, filter="true", node_pool=pool)
+    assert r1.info == r2.info == 0 and r1.M == r2.M == 10 and r1.loop == r2.loop
+    assert np.abs(np.sort(r1.lambda_) - np.sort(r2.lambda_)).max() < 1e-13 and np.abs(np.sort(r2.lambda_) - ev[:10]).max() < 1e-12

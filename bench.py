@@ -173,7 +173,7 @@ def reference_path_pair(eng, fc, N):
     out["gpu"] = {"seconds": time.perf_counter() - t0, "info": int(rg.info), "M": int(rg.M), "loops": int(rg.loop), "epsout": float(rg.epsout),
                   "max_eig_err_vs_analytic": float(np.abs(np.sort(rg.lambda_) - ev[:rg.M]).max()) if rg.M else None}
     out["note"] = ("oracle = CPU restatement of FeastKit's :serial sparse path with a direct solver, run to completion; at 40^3 the same path "
-                   "needs 767.5 s on 8 cores against 73.5 ms on the GPU (tools/cpu_reference_path_40.py, BASELINE.md section 4), the GMRES path "
+                   "needs 767.5 s (:serial) / 128.2 s (:threads analog) on 8 cores against 73.5 ms on the GPU (tools/cpu_reference_path_40.py, BASELINE.md section 4), the GMRES path "
                    "returns info = 5; 100^3 is extrapolated by the 'port' entry")
     return out
 

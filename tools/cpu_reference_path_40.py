@@ -40,7 +40,7 @@ def main():
     threads = "--threads" in sys.argv
     N = int(args[0]) if args else 40
     A, ev, Emin, Emax, Q0 = bench.workload(N, 64)
-    Ac = A.tocsc().astype(np.complex128)
+    Ac = A.tocsc()            # real symmetric pencil + real basis + true filter: the oracle's real mode (rho = Re g), like feast_scsrev
     fpm = fo.feastinit()
     fo.feastdefault(fpm)
     Zne, Wne = fo.feast_contour(Emin, Emax, fpm)

@@ -248,6 +248,17 @@ def run_gpu(args):
     # pinned host copies of the step's input (e2e leg)
     Q0_pinned = torch.from_numpy(Q0.T.copy()).pin_memory()   # (M0, n) C-order == (n, M0) column-major
     Q0_host = Q0_pinned.numpy().T
+    if shard == "rows" and world > 1:
+        # the first upload maps the peers' arenas (CUDA VMM handles over Unix sockets); a node without peer access fails on EVERY rank alike
+        # (all-or-nothing inside the library) -> the run continues column-sharded instead of dying
+        try:
+            eng.upload_subspace(args.m0, Q0_host)
+        except fc.FeastCudaError as exc:
+            if rank == 0:
+                print(f"bench.py: row sharding unavailable ({exc}); continuing with --shard columns", file=sys.stderr)
+            shard = args.shard = "columns"
+            eng.set_row_sharding(False)
+            opts = eng.make_opts(q0_real=True, x_real=True, shard=shard, mixed=head_mixed, **SOLVER_KW)
 
     def barrier():
         if world > 1:
